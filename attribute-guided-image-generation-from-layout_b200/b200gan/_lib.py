@@ -1,0 +1,356 @@
+"""ctypes binding of libb200gan.so (the C ABI declared in include/b200gan.h).
+
+`K` is the kernel namespace every op in this package calls.  There is NO CPU or PyTorch fallback: if the
+shared library is missing or a tensor is not on a CUDA device the call raises.  (tests/ may replace `K` with
+a CPU emulation of the ABI to validate host-side wiring; nothing in the product does.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libb200gan.so")
+
+MODE_PLAIN, MODE_AFFINE, MODE_CBN, MODE_SPADE = 0, 1, 2, 3
+
+
+class ConvDesc(C.Structure):
+    """Mirror of b200_conv_desc (include/b200gan.h)."""
+    _fields_ = [
+        ("B", C.c_int), ("Qh", C.c_int), ("Qw", C.c_int),
+        ("Cin", C.c_int), ("Cout", C.c_int),
+        ("Th", C.c_int), ("Tw", C.c_int),
+        ("in_sy", C.c_int), ("in_sx", C.c_int),
+        ("tap_sy", C.c_int), ("tap_sx", C.c_int),
+        ("tap_oy", C.c_int), ("tap_ox", C.c_int),
+        ("Hi", C.c_int), ("Wi", C.c_int),
+        ("up_shift", C.c_int),
+        ("in_sn", C.c_int64), ("in_sh", C.c_int64), ("in_sw", C.c_int64), ("in_sc", C.c_int64),
+        ("out_sy", C.c_int), ("out_sx", C.c_int), ("out_oy", C.c_int), ("out_ox", C.c_int),
+        ("Ho", C.c_int), ("Wo", C.c_int),
+        ("out_sn", C.c_int64), ("out_sh", C.c_int64), ("out_sw", C.c_int64), ("out_sc", C.c_int64),
+        ("ldw", C.c_int64),
+        ("relu", C.c_int),
+    ]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise B200Error("b200gan kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Kernels:
+    """Thin, allocation-explicit wrappers: one method per C entry point (or per fixed sequence of them)."""
+
+    def __init__(self, path: str = LIB_PATH):
+        if not os.path.exists(path):
+            raise B200Error("libb200gan.so not found at %s — build it with `python -c 'import __graft_entry__ as g; "
+                            "g.build()'` (no fallback path exists)" % path)
+        self.lib = C.CDLL(path)
+        self.lib.b200_last_error.restype = C.c_char_p
+        self.lib.b200_launch_count.restype = C.c_int64
+        self.lib.b200_bn_chunks.argtypes = [C.c_int64, C.c_int]
+
+    # ---- plumbing -------------------------------------------------------------------------------------
+    def _check(self, rc: int, name: str):
+        if rc != 0:
+            raise B200Error("%s failed: %s" % (name, self.lib.b200_last_error().decode()))
+
+    def launch_count(self) -> int:
+        return int(self.lib.b200_launch_count())
+
+    def version(self) -> int:
+        return int(self.lib.b200_version())
+
+    # ---- crops ----------------------------------------------------------------------------------------
+    def crop_fwd(self, feats, boxes, box_to_img, wx, wy, HH, WW):
+        N, Cc, H, W = feats.shape
+        B = boxes.shape[0]
+        out = torch.empty((B, Cc, HH, WW), dtype=torch.float32, device=feats.device)
+        self._check(self.lib.b200_crop_fwd(_ptr(feats), _ptr(boxes), _ptr(box_to_img), _ptr(wx), _ptr(wy), _ptr(out),
+                                           N, Cc, H, W, B, HH, WW, _stream()), "b200_crop_fwd")
+        return out
+
+    def crop_taps(self, boxes, wx, wy, H, W, HH, WW):
+        B = boxes.shape[0]
+        dev = boxes.device
+        ix0 = torch.empty((B, WW), dtype=torch.int32, device=dev)
+        iy0 = torch.empty((B, HH), dtype=torch.int32, device=dev)
+        fx = torch.empty((B, WW), dtype=torch.float32, device=dev)
+        fy = torch.empty((B, HH), dtype=torch.float32, device=dev)
+        self._check(self.lib.b200_crop_taps(_ptr(boxes), _ptr(wx), _ptr(wy), _ptr(ix0), _ptr(iy0), _ptr(fx), _ptr(fy),
+                                            H, W, B, HH, WW, _stream()), "b200_crop_taps")
+        return ix0, iy0, fx, fy
+
+    def crop_bwd(self, dcrops, boxes, img_box_start, box_order, wx, wy, N, H, W):
+        B, Cc, HH, WW = dcrops.shape
+        dfeats = torch.empty((N, Cc, H, W), dtype=torch.float32, device=dcrops.device)
+        ws = torch.empty((max(1, B * Cc * H * WW),), dtype=torch.float32, device=dcrops.device)
+        self._check(self.lib.b200_crop_bwd(_ptr(dcrops), _ptr(boxes), _ptr(img_box_start), _ptr(box_order), _ptr(wx),
+                                           _ptr(wy), _ptr(dfeats), _ptr(ws), N, Cc, H, W, B, HH, WW, _stream()),
+                    "b200_crop_bwd")
+        return dfeats
+
+    # ---- gather-GEMM convolutions -----------------------------------------------------------------------
+    def conv_gemm(self, desc: ConvDesc, inp, wmat, bias, scale, out, tc: bool):
+        fn = self.lib.b200_conv_gemm_tc if tc else self.lib.b200_conv_gemm_f32
+        self._check(fn(C.byref(desc), _ptr(inp), _ptr(wmat), _ptr(bias), _ptr(scale), _ptr(out), _stream()),
+                    "b200_conv_gemm_tc" if tc else "b200_conv_gemm_f32")
+
+    def conv_tc_ntile(self, cout: int) -> int:
+        return int(self.lib.b200_conv_tc_ntile(int(cout)))
+
+    def wgrad_gemm(self, desc: ConvDesc, P, G, ws, splits: int, tc: bool):
+        fn = self.lib.b200_wgrad_gemm_tc if tc else self.lib.b200_wgrad_gemm_f32
+        self._check(fn(C.byref(desc), _ptr(P), _ptr(G), _ptr(ws), int(splits), _stream()),
+                    "b200_wgrad_gemm_tc" if tc else "b200_wgrad_gemm_f32")
+
+    def wgrad_reduce(self, ws, splits, M, Th, Tw, Cc, dst, dst_offset, s_m, s_ty, s_tx, s_c, scale=None,
+                     accumulate=False, ws_row_offset=0, ws_rows=None):
+        """dst (+dst_offset elements) receives rows [ws_row_offset, ws_row_offset+M) of the partial results;
+        ws holds `ws_rows` rows per split (default M)."""
+        rows_total = M if ws_rows is None else ws_rows
+        K = Th * Tw * Cc
+        if not (dst.is_cuda and ws.is_cuda):
+            raise B200Error("wgrad_reduce: CUDA tensors required")
+        wptr = C.c_void_p(ws.data_ptr() + 4 * int(ws_row_offset) * K)
+        dptr = C.c_void_p(dst.data_ptr() + 4 * int(dst_offset))
+        self._check(self.lib.b200_wgrad_reduce(wptr, int(splits), C.c_int64(rows_total * K), int(M), int(Th), int(Tw),
+                                               int(Cc), dptr, C.c_int64(s_m), C.c_int64(s_ty), C.c_int64(s_tx),
+                                               C.c_int64(s_c), _ptr(scale), int(bool(accumulate)), _stream()),
+                    "b200_wgrad_reduce")
+
+    def pack_weight(self, src, src_offset, dst, dst_row_offset, bf16, M, Mpad, Th, Tw, Cc, ldw, s_m, s_ky, s_kx, s_c,
+                    ky0=0, kx0=0, kstep=1):
+        esz = 2 if bf16 else 4
+        sptr = C.c_void_p(src.data_ptr() + 4 * int(src_offset))
+        dptr = C.c_void_p(dst.data_ptr() + esz * int(dst_row_offset) * int(ldw))
+        if not (src.is_cuda and dst.is_cuda):
+            raise B200Error("pack_weight: CUDA tensors required")
+        self._check(self.lib.b200_pack_weight(sptr, dptr, int(bool(bf16)), int(M), int(Mpad), int(Th), int(Tw), int(Cc),
+                                              C.c_int64(ldw), C.c_int64(s_m), C.c_int64(s_ky), C.c_int64(s_kx),
+                                              C.c_int64(s_c), int(ky0), int(kx0), int(kstep), _stream()),
+                    "b200_pack_weight")
+
+    # ---- normalisation --------------------------------------------------------------------------------------
+    def bn_chunks(self, rows, Cc):
+        return int(self.lib.b200_bn_chunks(C.c_int64(rows), int(Cc)))
+
+    def bn_stats(self, x2d, running_mean, running_var, momentum):
+        rows, Cc = x2d.shape
+        dev = x2d.device
+        mean = torch.empty((Cc,), dtype=torch.float32, device=dev)
+        var = torch.empty((Cc,), dtype=torch.float32, device=dev)
+        ws = torch.empty((2 * Cc * self.bn_chunks(rows, Cc),), dtype=torch.float64, device=dev)
+        self._check(self.lib.b200_bn_stats(_ptr(x2d), C.c_int64(rows), Cc, _ptr(mean), _ptr(var), _ptr(running_mean),
+                                           _ptr(running_var), C.c_float(momentum), _ptr(ws), _stream()), "b200_bn_stats")
+        return mean, var
+
+    def norm_fwd(self, x2d, mean, var, eps, mode, gamma, beta, idx, rows_per_seg, residual, relu):
+        rows, Cc = x2d.shape
+        y = torch.empty_like(x2d)
+        self._check(self.lib.b200_norm_fwd(_ptr(x2d), _ptr(y), C.c_int64(rows), Cc, _ptr(mean), _ptr(var),
+                                           C.c_float(eps), int(mode), _ptr(gamma), _ptr(beta), _ptr(idx),
+                                           int(rows_per_seg), _ptr(residual), int(bool(relu)), _stream()),
+                    "b200_norm_fwd")
+        return y
+
+    def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes):
+        """reduce -> finalize -> apply.  Returns dx, dgamma, dbeta, dtable, dgb (None where not applicable)."""
+        rows, Cc = x2d.shape
+        dev = x2d.device
+        if mode == MODE_CBN:
+            seg = int(rows_per_seg)
+        else:
+            nchunks = self.bn_chunks(rows, Cc)
+            seg = (rows + nchunks - 1) // nchunks
+        nseg = (rows + seg - 1) // seg
+        seg_sums = torch.empty((nseg * Cc * 2,), dtype=torch.float64, device=dev)
+        self._check(self.lib.b200_norm_bwd_reduce(_ptr(dy), _ptr(x2d), _ptr(y), C.c_int64(rows), Cc, _ptr(mean),
+                                                  _ptr(var), C.c_float(eps), int(mode), _ptr(gamma), _ptr(idx), seg,
+                                                  int(bool(relu)), _ptr(seg_sums), _stream()), "b200_norm_bwd_reduce")
+        s = torch.empty((Cc * 2,), dtype=torch.float32, device=dev)
+        dgamma = dbeta = dtable = dgb = None
+        if mode == MODE_AFFINE:
+            dgamma = torch.empty((Cc,), dtype=torch.float32, device=dev)
+            dbeta = torch.empty((Cc,), dtype=torch.float32, device=dev)
+        if mode == MODE_CBN:
+            dtable = torch.empty((num_classes, 2 * Cc), dtype=torch.float32, device=dev)
+        self._check(self.lib.b200_norm_bwd_finalize(_ptr(seg_sums), nseg, Cc, int(mode), _ptr(gamma), _ptr(idx),
+                                                    int(num_classes), _ptr(s), _ptr(dgamma), _ptr(dbeta), _ptr(dtable),
+                                                    _stream()), "b200_norm_bwd_finalize")
+        dx = torch.empty_like(x2d)
+        if mode == MODE_SPADE:
+            dgb = torch.empty((rows, 2 * Cc), dtype=torch.float32, device=dev)
+        self._check(self.lib.b200_norm_bwd_apply(_ptr(dy), _ptr(x2d), _ptr(y), _ptr(dx), C.c_int64(rows), Cc, _ptr(mean),
+                                                 _ptr(var), C.c_float(eps), int(mode), _ptr(gamma), _ptr(idx),
+                                                 int(rows_per_seg) if mode == MODE_CBN else 1, int(bool(relu)), _ptr(s),
+                                                 _ptr(dgb), _stream()), "b200_norm_bwd_apply")
+        return dx, dgamma, dbeta, dtable, dgb
+
+    # ---- elementwise / pooling / layout ------------------------------------------------------------------------
+    def relu_fwd(self, x):
+        y = torch.empty_like(x)
+        self._check(self.lib.b200_relu_fwd(_ptr(x), _ptr(y), C.c_int64(x.numel()), _stream()), "b200_relu_fwd")
+        return y
+
+    def relu_bwd(self, dy, y):
+        dx = torch.empty_like(dy)
+        self._check(self.lib.b200_relu_bwd(_ptr(dy), _ptr(y), _ptr(dx), C.c_int64(dy.numel()), _stream()), "b200_relu_bwd")
+        return dx
+
+    def add(self, a, b, out=None):
+        if out is None:
+            out = torch.empty_like(a)
+        self._check(self.lib.b200_add(_ptr(a), _ptr(b), _ptr(out), C.c_int64(a.numel()), _stream()), "b200_add")
+        return out
+
+    def pool_fwd(self, x, N, H, W, Cc, f, scale):
+        y = torch.empty((N, H // f, W // f, Cc), dtype=torch.float32, device=x.device)
+        self._check(self.lib.b200_pool_fwd(_ptr(x), _ptr(y), N, H, W, Cc, f, C.c_float(scale), _stream()), "b200_pool_fwd")
+        return y
+
+    def unpool_fwd(self, x, N, H, W, Cc, f, scale):
+        y = torch.empty((N, H * f, W * f, Cc), dtype=torch.float32, device=x.device)
+        self._check(self.lib.b200_unpool_fwd(_ptr(x), _ptr(y), N, H, W, Cc, f, C.c_float(scale), _stream()),
+                    "b200_unpool_fwd")
+        return y
+
+    def concat_fwd(self, a, Ca, a_div, b, Cb, b_div, rows):
+        out = torch.empty((rows, Ca + Cb), dtype=torch.float32, device=a.device)
+        self._check(self.lib.b200_concat_fwd(_ptr(a), Ca, a_div, _ptr(b), Cb, b_div, _ptr(out), C.c_int64(rows), _stream()),
+                    "b200_concat_fwd")
+        return out
+
+    def concat_bwd(self, dout, Ca, a_div, Cb, b_div, rows, need_a=True, need_b=True):
+        dev = dout.device
+        da = torch.empty((rows // a_div, Ca), dtype=torch.float32, device=dev) if need_a else None
+        db = torch.empty((rows // b_div, Cb), dtype=torch.float32, device=dev) if need_b else None
+        self._check(self.lib.b200_concat_bwd(_ptr(dout), Ca, a_div, _ptr(da), Cb, b_div, _ptr(db), C.c_int64(rows),
+                                             _stream()), "b200_concat_bwd")
+        return da, db
+
+    def gather_rows(self, table, idx):
+        rows, D = idx.shape[0], table.shape[1]
+        out = torch.empty((rows, D), dtype=torch.float32, device=table.device)
+        self._check(self.lib.b200_gather_rows(_ptr(table), _ptr(idx), _ptr(out), rows, D, _stream()), "b200_gather_rows")
+        return out
+
+    def scatter_rows(self, dout, idx, num_classes):
+        rows, D = dout.shape
+        dtable = torch.empty((num_classes, D), dtype=torch.float32, device=dout.device)
+        self._check(self.lib.b200_scatter_rows(_ptr(dout), _ptr(idx), _ptr(dtable), rows, D, num_classes, _stream()),
+                    "b200_scatter_rows")
+        return dtable
+
+    def permute_rows(self, x, src_row, rowlen):
+        rows = src_row.shape[0]
+        out = torch.empty((rows, rowlen), dtype=torch.float32, device=x.device)
+        self._check(self.lib.b200_permute_rows(_ptr(x), _ptr(src_row), _ptr(out), rows, rowlen, _stream()),
+                    "b200_permute_rows")
+        return out
+
+    def mask_outer_fwd(self, v, mask, O, H, W, Cc):
+        out = torch.empty((O, H + 2, W + 2, Cc), dtype=torch.float32, device=v.device)
+        self._check(self.lib.b200_mask_outer_fwd(_ptr(v), _ptr(mask), _ptr(out), O, H, W, Cc, _stream()),
+                    "b200_mask_outer_fwd")
+        return out
+
+    def mask_outer_bwd(self, dout, mask, O, H, W, Cc):
+        dv = torch.empty((O, Cc), dtype=torch.float32, device=dout.device)
+        self._check(self.lib.b200_mask_outer_bwd(_ptr(dout), _ptr(mask), _ptr(dv), O, H, W, Cc, _stream()),
+                    "b200_mask_outer_bwd")
+        return dv
+
+    def lstm_gates_fwd(self, pre_x, pre_h, c_prev, rows, hid, gates=None, c_out=None, h_out=None):
+        dev = pre_x.device
+        if gates is None:
+            gates = torch.empty((rows, 4 * hid), dtype=torch.float32, device=dev)
+            c_out = torch.empty((rows, hid), dtype=torch.float32, device=dev)
+            h_out = torch.empty((rows, hid), dtype=torch.float32, device=dev)
+        self._check(self.lib.b200_lstm_gates_fwd(_ptr(pre_x), _ptr(pre_h), _ptr(c_prev), _ptr(gates), _ptr(c_out),
+                                                 _ptr(h_out), C.c_int64(rows), hid, _stream()), "b200_lstm_gates_fwd")
+        return gates, c_out, h_out
+
+    def lstm_gates_bwd(self, dh, dc_next, gates, c_prev, c_out, rows, hid, dpre=None, dc_prev=None):
+        dev = dh.device
+        if dpre is None:
+            dpre = torch.empty((rows, 4 * hid), dtype=torch.float32, device=dev)
+        if dc_prev is None:
+            dc_prev = torch.empty((rows, hid), dtype=torch.float32, device=dev)
+        self._check(self.lib.b200_lstm_gates_bwd(_ptr(dh), _ptr(dc_next), _ptr(gates), _ptr(c_prev), _ptr(c_out),
+                                                 _ptr(dpre), _ptr(dc_prev), C.c_int64(rows), hid, _stream()),
+                    "b200_lstm_gates_bwd")
+        return dpre, dc_prev
+
+    def reparam_fwd(self, mu, logvar, eps):
+        z = torch.empty_like(mu)
+        self._check(self.lib.b200_reparam_fwd(_ptr(mu), _ptr(logvar), _ptr(eps), _ptr(z), C.c_int64(mu.numel()), _stream()),
+                    "b200_reparam_fwd")
+        return z
+
+    def reparam_bwd(self, dz, logvar, eps):
+        dmu = torch.empty_like(dz)
+        dlv = torch.empty_like(dz)
+        self._check(self.lib.b200_reparam_bwd(_ptr(dz), _ptr(logvar), _ptr(eps), _ptr(dmu), _ptr(dlv),
+                                              C.c_int64(dz.numel()), _stream()), "b200_reparam_bwd")
+        return dmu, dlv
+
+    def transpose(self, x, B, R, Cc):
+        y = torch.empty((B, Cc, R), dtype=torch.float32, device=x.device)
+        self._check(self.lib.b200_transpose(_ptr(x), _ptr(y), B, R, Cc, _stream()), "b200_transpose")
+        return y
+
+    def colsum(self, x2d):
+        rows, Cc = x2d.shape
+        out = torch.empty((Cc,), dtype=torch.float32, device=x2d.device)
+        ws = torch.empty((Cc * self.bn_chunks(rows, Cc),), dtype=torch.float64, device=x2d.device)
+        self._check(self.lib.b200_colsum(_ptr(x2d), C.c_int64(rows), Cc, _ptr(out), _ptr(ws), _stream()), "b200_colsum")
+        return out
+
+    # ---- spectral norm --------------------------------------------------------------------------------------
+    def sn_power_iter(self, W2d_param, h, w, u, v, do_iter, eps):
+        dev = u.device
+        out2 = torch.empty((2,), dtype=torch.float32, device=dev)
+        ws = torch.empty((8 * w + h,), dtype=torch.float32, device=dev)
+        self._check(self.lib.b200_sn_power_iter(_ptr(W2d_param), h, w, _ptr(u), _ptr(v), int(bool(do_iter)),
+                                                C.c_float(eps), _ptr(out2), _ptr(ws), _stream()), "b200_sn_power_iter")
+        return out2
+
+    def sn_grad(self, g, W, u, v, sig2, h, w):
+        dW = torch.empty_like(W)
+        ws = torch.empty((1024,), dtype=torch.float64, device=W.device)
+        self._check(self.lib.b200_sn_grad(_ptr(g), _ptr(W), _ptr(u), _ptr(v), _ptr(sig2), _ptr(dW), h, w, 0, _ptr(ws),
+                                          _stream()), "b200_sn_grad")
+        return dW
+
+
+_K: Optional[Kernels] = None
+
+
+class _Lazy:
+    """Resolves to the loaded library on first attribute access (import of the package stays cheap and CPU-safe)."""
+
+    def __getattr__(self, name):
+        global _K
+        if _K is None:
+            _K = Kernels()
+        return getattr(_K, name)
+
+
+K = _Lazy()

@@ -1,0 +1,109 @@
+"""Layer modules: subclasses of the torch.nn layers the reference uses (same constructors, default init and
+state_dict keys) whose forward runs the libb200gan kernels on channel-last activations."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .ops import ConvGeom, WeightPacks
+
+
+def _sn_state(m):
+    return (m.weight_u, m.weight_v) if getattr(m, "_b200_sn", False) else None
+
+
+def _weight(m):
+    return m.weight_orig if getattr(m, "_b200_sn", False) else m.weight
+
+
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d with square kernel / stride / padding as used on the path."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._geom = ConvGeom(self.in_channels, self.out_channels, self.kernel_size[0], self.kernel_size[1],
+                              self.stride[0], self.padding[0])
+        self._packs = WeightPacks()
+
+    def forward(self, x, x_layout="cl", out_layout="cl", relu=False):
+        return ops.conv2d(x, _weight(self), self.bias, self._geom, self._packs, x_layout, out_layout, relu,
+                          _sn_state(self), self.training)
+
+
+class ConvTranspose2d(nn.ConvTranspose2d):
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        assert self.bias is None, "ConvTranspose2d on the path has no bias"
+        # conv orientation: Y = this layer's input (in_channels), X = its output (out_channels)
+        self._geom = ConvGeom(self.out_channels, self.in_channels, self.kernel_size[0], self.kernel_size[1],
+                              self.stride[0], self.padding[0])
+        self._packs = WeightPacks()
+
+    def forward(self, x):
+        N, H, W, _ = x.shape
+        s, p, k = self.stride[0], self.padding[0], self.kernel_size[0]
+        out_hw = ((H - 1) * s - 2 * p + k, (W - 1) * s - 2 * p + k)
+        return ops.conv_transpose2d(x, self.weight, self._geom, self._packs, out_hw)
+
+
+class Linear(nn.Linear):
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._packs = WeightPacks()
+
+    def forward(self, x, relu=False):
+        return ops.linear(x, _weight(self), self.bias, self._packs, relu, _sn_state(self), self.training)
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """Works on (..., C) channel-last tensors (also serves BatchNorm1d's (B, C) case)."""
+
+    def forward(self, x, relu=False, residual=None):
+        if self.training and self.track_running_stats:
+            self.num_batches_tracked.add_(1)
+        w = self.weight if self.affine else None
+        b = self.bias if self.affine else None
+        return ops.batch_norm(x, w, b, self.running_mean, self.running_var, self.training, relu, residual)
+
+
+class BatchNorm1d(nn.BatchNorm1d):
+    def forward(self, x, relu=False):
+        if self.training and self.track_running_stats:
+            self.num_batches_tracked.add_(1)
+        return ops.batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var, self.training, relu)
+
+
+class Embedding(nn.Embedding):
+    def forward(self, idx_i32):
+        return ops.embedding(self.weight, idx_i32)
+
+
+class ReLU(nn.ReLU):
+    def forward(self, x):
+        return ops.relu(x)
+
+
+def add_sn(m):
+    """discriminator.py:15-22 — wrap every Conv2d / ConvTranspose2d / Linear / Embedding below `m` with spectral
+    normalisation.  State layout equals torch.nn.utils.spectral_norm's (weight_orig parameter, weight_u / weight_v
+    buffers, u ~ normalize(N(0,1)) of size Cout, v of size Cin*kh*kw); the power iteration, the 1/sigma scaling and
+    the gradient through sigma run in libb200gan (b200_sn_power_iter, conv epilogue scale, b200_sn_grad)."""
+    for name, c in m.named_children():
+        m.add_module(name, add_sn(c))
+    if isinstance(m, (Conv2d, Linear)):
+        if getattr(m, "_b200_sn", False):
+            raise RuntimeError("spectral norm already applied")
+        w = m._parameters.pop("weight")
+        m.register_parameter("weight_orig", w)
+        h, wd = w.shape[0], w[0].numel()
+        u = F.normalize(w.new_empty(h).normal_(0, 1), dim=0, eps=ops.SN_EPS)
+        v = F.normalize(w.new_empty(wd).normal_(0, 1), dim=0, eps=ops.SN_EPS)
+        m.register_buffer("weight_u", u)
+        m.register_buffer("weight_v", v)
+        m._b200_sn = True
+        return m
+    if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear, nn.Embedding)):
+        raise NotImplementedError("add_sn: %s has no libb200gan spectral-norm path" % type(m).__name__)
+    return m

@@ -1,0 +1,780 @@
+"""torch.autograd.Function layer over the libb200gan C ABI.
+
+Tensor conventions: "cl" (channel-last) activations are contiguous (N, H, W, C) fp32 tensors; "nchw" tensors are
+the reference-boundary layout (3-channel images / crops) and are addressed through strides, never transposed.
+Every forward and backward here launches only kernels of this repository (plus torch allocations / views).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, MODE_AFFINE, MODE_CBN, MODE_PLAIN, MODE_SPADE
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+SN_EPS = 1e-12
+
+# ----------------------------------------------------------------------------------------------------------
+# precision policy: "fp32" = CUDA-core fp32 gather-GEMMs (tight parity); "bf16" = tcgen05 bf16 operands with
+# fp32 accumulation wherever the layer shape is eligible (channels % 64 == 0, channel-last), fp32 otherwise.
+# ----------------------------------------------------------------------------------------------------------
+_PRECISION = "fp32"
+_CACHE_EPOCH = 0
+
+
+def set_precision(p: str):
+    global _PRECISION
+    if p not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION = p
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def bump_weight_epoch():
+    """Invalidate every packed-weight cache entry (call after weights change behind autograd's back, e.g. a CUDA
+    graph replay that contains the optimizer step)."""
+    global _CACHE_EPOCH
+    _CACHE_EPOCH += 1
+
+
+def _rup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def cl_strides(H: int, W: int, C: int):
+    return (H * W * C, W * C, C, 1)
+
+
+def nchw_strides(C: int, H: int, W: int):
+    return (C * H * W, W, 1, H * W)  # (sn, sh, sw, sc)
+
+
+def _dims(x: torch.Tensor, layout: str):
+    if layout == "cl":
+        N, H, W, C = x.shape
+        return N, H, W, C, cl_strides(H, W, C)
+    N, C, H, W = x.shape
+    return N, H, W, C, nchw_strides(C, H, W)
+
+
+def _empty(N, H, W, C, layout, device):
+    if layout == "cl":
+        return torch.empty((N, H, W, C), dtype=torch.float32, device=device), cl_strides(H, W, C)
+    return torch.empty((N, C, H, W), dtype=torch.float32, device=device), nchw_strides(C, H, W)
+
+
+class ConvGeom:
+    """A convolution in *conv orientation*: X (N,Hx,Wx,Cx) * W (Cy,Cx,kh,kw) -> Y (N,Hy,Wy,Cy).
+    nn.ConvTranspose2d is the same geometry run backwards (its input is Y, its output X)."""
+
+    def __init__(self, Cx, Cy, kh, kw, stride, pad, cx_offset=0, cx_total=None):
+        self.Cx, self.Cy, self.kh, self.kw, self.s, self.p = Cx, Cy, kh, kw, stride, pad
+        # the parameter may hold more input channels than this op uses (ConvLSTM x / h halves)
+        self.cx_offset = cx_offset
+        self.cx_total = Cx if cx_total is None else cx_total
+
+    def out_hw(self, Hx, Wx):
+        return (Hx + 2 * self.p - self.kh) // self.s + 1, (Wx + 2 * self.p - self.kw) // self.s + 1
+
+    def key(self):
+        return (self.Cx, self.Cy, self.kh, self.kw, self.s, self.p, self.cx_offset, self.cx_total)
+
+
+class WeightPacks:
+    """Packed GEMM operands of one parameter tensor, rebuilt when the parameter's version changes."""
+
+    def __init__(self, stamp_src=None):
+        self.store: Dict[tuple, tuple] = {}
+        # tensors whose (data_ptr, version) identify the weights when `w` is a per-call temporary (fused gamma|beta)
+        self.stamp_src = stamp_src
+
+    def get(self, key, w: torch.Tensor, builder):
+        src = self.stamp_src if self.stamp_src is not None else (w,)
+        stamp = tuple((t.data_ptr(), t._version) for t in src) + (_CACHE_EPOCH,)
+        hit = self.store.get(key)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        val = builder()
+        self.store[key] = (stamp, val)
+        return val
+
+
+def _tc_fwd_ok(g: ConvGeom, x_layout: str) -> bool:
+    return _PRECISION == "bf16" and x_layout == "cl" and g.Cx % 64 == 0
+
+
+def _tc_dgrad_ok(g: ConvGeom, dy_layout: str) -> bool:
+    return _PRECISION == "bf16" and dy_layout == "cl" and g.Cy % 64 == 0
+
+
+def _tc_wgrad_ok(g: ConvGeom, x_layout: str, dy_layout: str) -> bool:
+    return _PRECISION == "bf16" and x_layout == "cl" and dy_layout == "cl" and g.Cx % 64 == 0 and g.Cy % 64 == 0
+
+
+def _pack_fwd(g: ConvGeom, w: torch.Tensor, tc: bool):
+    """wmat[co][(ky*kw+kx)*Cx + c] = w[co, cx_offset+c, ky, kx]"""
+    K = g.kh * g.kw * g.Cx
+    ldw = _rup(K, 64) if tc else _rup(K, 4)
+    mpad = _rup(g.Cy, _lib.K.conv_tc_ntile(g.Cy)) if tc else g.Cy
+    dst = torch.empty((mpad, ldw), dtype=torch.bfloat16 if tc else torch.float32, device=w.device)
+    kk = g.kh * g.kw
+    _lib.K.pack_weight(w, g.cx_offset * kk, dst, 0, tc, g.Cy, mpad, g.kh, g.kw, g.Cx, ldw, g.cx_total * kk, g.kw, 1, kk)
+    return dst, ldw
+
+
+def _dgrad_phases(g: ConvGeom):
+    out = []
+    for py in range(g.s):
+        for px in range(g.s):
+            ky0, kx0 = (py + g.p) % g.s, (px + g.p) % g.s
+            Th = (g.kh - ky0 + g.s - 1) // g.s if g.kh > ky0 else 0
+            Tw = (g.kw - kx0 + g.s - 1) // g.s if g.kw > kx0 else 0
+            out.append((py, px, ky0, kx0, Th, Tw))
+    return out
+
+
+def _pack_dgrad(g: ConvGeom, w: torch.Tensor, tc: bool):
+    """per output phase: wmat[ci][(j*Tw+i)*Cy + co] = w[co, cx_offset+ci, ky0+s*j, kx0+s*i]"""
+    packs = []
+    kk = g.kh * g.kw
+    for (py, px, ky0, kx0, Th, Tw) in _dgrad_phases(g):
+        if Th == 0 or Tw == 0:
+            packs.append(None)
+            continue
+        K = Th * Tw * g.Cy
+        ldw = _rup(K, 64) if tc else _rup(K, 4)
+        mpad = _rup(g.Cx, _lib.K.conv_tc_ntile(g.Cx)) if tc else g.Cx
+        dst = torch.empty((mpad, ldw), dtype=torch.bfloat16 if tc else torch.float32, device=w.device)
+        _lib.K.pack_weight(w, g.cx_offset * kk, dst, 0, tc, g.Cx, mpad, Th, Tw, g.Cy, ldw, kk, g.kw, 1, g.cx_total * kk,
+                           ky0, kx0, g.s)
+        packs.append((dst, ldw))
+    return packs
+
+
+def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bias=None, scale=None, relu=False):
+    """Y = epilogue(conv(X, W))"""
+    N, Hx, Wx, Cx, xs = _dims(x, x_layout)
+    assert Cx == g.Cx, (Cx, g.Cx)
+    Hy, Wy = g.out_hw(Hx, Wx)
+    tc = _tc_fwd_ok(g, x_layout)
+    wmat, ldw = packs.get(("fwd", tc) + g.key(), w, lambda: _pack_fwd(g, w, tc))
+    y, ys = _empty(N, Hy, Wy, g.Cy, out_layout, x.device)
+    d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=g.Cx, Cout=g.Cy, Th=g.kh, Tw=g.kw, in_sy=g.s, in_sx=g.s, tap_sy=1, tap_sx=1,
+                 tap_oy=-g.p, tap_ox=-g.p, Hi=Hx, Wi=Wx, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3],
+                 out_sy=1, out_sx=1, out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ys[0], out_sh=ys[1], out_sw=ys[2],
+                 out_sc=ys[3], ldw=ldw, relu=int(relu))
+    _lib.K.conv_gemm(d, x, wmat, bias, scale, y, tc)
+    return y
+
+
+def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layout, scale=None):
+    """dX = conv^T(dY, W)  (also the forward of nn.ConvTranspose2d)"""
+    N, Hy, Wy, Cy, ds = _dims(dy, dy_layout)
+    assert Cy == g.Cy, (Cy, g.Cy)
+    Hx, Wx = x_hw
+    tc = _tc_dgrad_ok(g, dy_layout)
+    phase_packs = packs.get(("dgrad", tc) + g.key(), w, lambda: _pack_dgrad(g, w, tc))
+    phases = _dgrad_phases(g)
+    dx, xs = _empty(N, Hx, Wx, g.Cx, out_layout, dy.device)
+    if any(p is None for p in phase_packs):
+        dx.zero_()
+    for (py, px, ky0, kx0, Th, Tw), pk in zip(phases, phase_packs):
+        if pk is None:
+            continue
+        Qh, Qw = (Hx - py + g.s - 1) // g.s, (Wx - px + g.s - 1) // g.s
+        if Qh <= 0 or Qw <= 0:
+            continue
+        wmat, ldw = pk
+        d = ConvDesc(B=N, Qh=Qh, Qw=Qw, Cin=g.Cy, Cout=g.Cx, Th=Th, Tw=Tw, in_sy=1, in_sx=1, tap_sy=-1, tap_sx=-1,
+                     tap_oy=(py + g.p - ky0) // g.s, tap_ox=(px + g.p - kx0) // g.s, Hi=Hy, Wi=Wy, up_shift=0,
+                     in_sn=ds[0], in_sh=ds[1], in_sw=ds[2], in_sc=ds[3], out_sy=g.s, out_sx=g.s, out_oy=py, out_ox=px,
+                     Ho=Hx, Wo=Wx, out_sn=xs[0], out_sh=xs[1], out_sw=xs[2], out_sc=xs[3], ldw=ldw, relu=0)
+        _lib.K.conv_gemm(d, dy, wmat, None, scale, dx, tc)
+    return dx
+
+
+def _wgrad_splits(g: ConvGeom, Q: int, tc: bool) -> int:
+    tm, tn = (128, 128 if g.Cx >= 128 else 64) if tc else (64, 64)
+    tiles = -(-g.Cy // tm) * g.kh * g.kw * -(-g.Cx // tn)
+    splits = max(1, min(-(-592 // tiles), max(1, Q // 256), 64))
+    return splits
+
+
+def conv_wgrad(g: ConvGeom, x, x_layout, dy, dy_layout, dw: torch.Tensor, accumulate=False):
+    """dW[co, cx_offset+c, ky, kx] (+)= sum X (*) dY; dw is the full (Cy, cx_total, kh, kw) gradient buffer."""
+    N, Hx, Wx, Cx, xs = _dims(x, x_layout)
+    _, Hy, Wy, Cy, ds = _dims(dy, dy_layout)
+    assert Cx == g.Cx and Cy == g.Cy
+    tc = _tc_wgrad_ok(g, x_layout, dy_layout)
+    Q = N * Hy * Wy
+    splits = _wgrad_splits(g, Q, tc)
+    K = g.kh * g.kw * g.Cx
+    ws = torch.empty((splits * g.Cy * K,), dtype=torch.float32, device=x.device)
+    d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=g.Cx, Cout=g.Cy, Th=g.kh, Tw=g.kw, in_sy=g.s, in_sx=g.s, tap_sy=1, tap_sx=1,
+                 tap_oy=-g.p, tap_ox=-g.p, Hi=Hx, Wi=Wx, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3],
+                 out_sy=1, out_sx=1, out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ds[0], out_sh=ds[1], out_sw=ds[2],
+                 out_sc=ds[3], ldw=K, relu=0)
+    _lib.K.wgrad_gemm(d, dy, x, ws, splits, tc)
+    kk = g.kh * g.kw
+    _lib.K.wgrad_reduce(ws, splits, g.Cy, g.kh, g.kw, g.Cx, dw, g.cx_offset * kk, g.cx_total * kk, g.kw, 1, kk,
+                        accumulate=accumulate)
+    return dw
+
+
+def bias_grad(dy: torch.Tensor, layout: str) -> torch.Tensor:
+    if layout == "cl":
+        return _lib.K.colsum(dy.reshape(-1, dy.shape[-1]))
+    N, C, H, W = dy.shape
+    per = _lib.K.pool_fwd(dy, N * C, H, W, 1, H, 1.0) if H == W else None
+    if per is None:
+        raise _lib.B200Error("bias_grad: non-square NCHW output")
+    return _lib.K.colsum(per.reshape(N, C))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# convolution / transposed convolution / linear  (+ optional spectral norm, bias, fused ReLU)
+# ----------------------------------------------------------------------------------------------------------
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, sn_u, sn_v, g: ConvGeom, packs: WeightPacks, transposed: bool, x_layout: str,
+                out_layout: str, relu: bool, training: bool, out_hw):
+        sig2 = None
+        if sn_u is not None:
+            h, wd = w.shape[0], w[0].numel()
+            sig2 = _lib.K.sn_power_iter(w, h, wd, sn_u, sn_v, training, SN_EPS)
+            ctx.sn = (sn_u.clone(), sn_v.clone(), sig2)
+        else:
+            ctx.sn = None
+        scale = sig2[1:] if sig2 is not None else None
+        if not transposed:
+            y = conv_forward(g, packs, w, x, x_layout, out_layout, bias, scale, relu)
+        else:
+            assert bias is None and not relu
+            y = conv_dgrad(g, packs, w, x, x_layout, out_hw, out_layout, scale)
+        ctx.g, ctx.packs, ctx.transposed = g, packs, transposed
+        ctx.x_layout, ctx.out_layout, ctx.relu = x_layout, out_layout, relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        g, packs = ctx.g, ctx.packs
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = _lib.K.relu_bwd(dy, y)
+        scale = ctx.sn[2][1:] if ctx.sn is not None else None
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if not ctx.transposed:
+                _, Hx, Wx, _, _ = _dims(x, ctx.x_layout)
+                dx = conv_dgrad(g, packs, w, dy, ctx.out_layout, (Hx, Wx), ctx.x_layout, scale)
+            else:
+                dx = conv_forward(g, packs, w, dy, ctx.out_layout, ctx.x_layout, None, scale, False)
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty_like(w)
+            if not ctx.transposed:
+                conv_wgrad(g, x, ctx.x_layout, dy, ctx.out_layout, gw)
+            else:
+                conv_wgrad(g, dy, ctx.out_layout, x, ctx.x_layout, gw)
+            if ctx.sn is not None:
+                u, v, sig2 = ctx.sn
+                dw = _lib.K.sn_grad(gw, w, u, v, sig2, w.shape[0], w[0].numel())
+            else:
+                dw = gw
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = bias_grad(dy, ctx.out_layout)
+        return dx, dw, db, None, None, None, None, None, None, None, None, None, None
+
+
+def conv2d(x, w, bias, g: ConvGeom, packs: WeightPacks, x_layout="cl", out_layout="cl", relu=False, sn=None,
+           training=True):
+    u, v = sn if sn is not None else (None, None)
+    return _ConvFn.apply(x, w, bias, u, v, g, packs, False, x_layout, out_layout, relu, training, None)
+
+
+def conv_transpose2d(x, w, g: ConvGeom, packs: WeightPacks, out_hw, x_layout="cl", out_layout="cl"):
+    """x plays dY of the conv-orientation geometry g (g.Cy = x channels, g.Cx = output channels)."""
+    return _ConvFn.apply(x, w, None, None, None, g, packs, True, x_layout, out_layout, False, True, out_hw)
+
+
+def linear(x2d, w, bias, packs: WeightPacks, relu=False, sn=None, training=True, geom: Optional[ConvGeom] = None):
+    B, Cin = x2d.shape
+    g = geom if geom is not None else ConvGeom(Cin, w.shape[0], 1, 1, 1, 0)
+    y = _ConvFn.apply(x2d.view(B, 1, 1, Cin), w.view(w.shape[0], w.shape[1], 1, 1), bias, sn[0] if sn else None,
+                      sn[1] if sn else None, g, packs, False, "cl", "cl", relu, training, None)
+    return y.view(B, g.Cy)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# normalisation
+# ----------------------------------------------------------------------------------------------------------
+class _NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, idx, running_mean, running_var, mode, training, relu, residual, rows_per_seg,
+                num_classes):
+        shape = x.shape
+        C = shape[-1]
+        x2 = x.reshape(-1, C)
+        if training:
+            mean, var = _lib.K.bn_stats(x2, running_mean, running_var, BN_MOMENTUM)
+        else:
+            mean, var = running_mean, running_var
+        g2 = gamma.reshape(-1, 2 * C) if mode == MODE_SPADE else gamma
+        r2 = residual.reshape(-1, C) if residual is not None else None
+        y = _lib.K.norm_fwd(x2, mean, var, BN_EPS, mode, g2, beta, idx, rows_per_seg, r2, relu)
+        ctx.mode, ctx.relu, ctx.rows_per_seg, ctx.num_classes, ctx.training = mode, relu, rows_per_seg, num_classes, training
+        ctx.has_residual = residual is not None
+        ctx.save_for_backward(x2, y if relu else None, mean, var, g2, idx)
+        ctx.shape = shape
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        if not ctx.training:
+            raise NotImplementedError("b200gan: backward through eval-mode batch norm is not on the reference path")
+        x2, y, mean, var, g2, idx = ctx.saved_tensors
+        C = x2.shape[1]
+        dy2 = dy.contiguous().reshape(-1, C)
+        dx, dgamma, dbeta, dtable, dgb = _lib.K.norm_bwd(dy2, x2, y, mean, var, BN_EPS, ctx.mode, g2, idx,
+                                                         ctx.rows_per_seg, ctx.relu, ctx.num_classes)
+        dres = None
+        if ctx.has_residual:
+            dres = _lib.K.relu_bwd(dy2, y).view(ctx.shape) if ctx.relu else dy
+        if ctx.mode == MODE_AFFINE:
+            gg, gb = dgamma, dbeta
+        elif ctx.mode == MODE_CBN:
+            gg, gb = dtable, None
+        elif ctx.mode == MODE_SPADE:
+            gg, gb = dgb.view(ctx.shape[:-1] + (2 * C,)), None
+        else:
+            gg, gb = None, None
+        return dx.view(ctx.shape), gg, gb, None, None, None, None, None, None, dres, None, None
+
+
+def batch_norm(x, weight, bias, running_mean, running_var, training, relu=False, residual=None):
+    mode = MODE_AFFINE if weight is not None else MODE_PLAIN
+    return _NormFn.apply(x, weight, bias, None, running_mean, running_var, mode, training, relu, residual, 1, 0)
+
+
+def cond_batch_norm(x, table, idx_i32, running_mean, running_var, training, relu=False):
+    """x (O,H,W,C); table (num_classes, 2C) = [gamma | beta]; idx_i32 (O,)"""
+    rows_per_seg = x.shape[1] * x.shape[2]
+    return _NormFn.apply(x, table, None, idx_i32, running_mean, running_var, MODE_CBN, training, relu, None,
+                         rows_per_seg, table.shape[0])
+
+
+def spade_norm(x, gb, running_mean, running_var, training, relu=False):
+    """x (N,H,W,C); gb (N,H,W,2C) = fused [gamma | beta] conv output"""
+    return _NormFn.apply(x, gb, None, None, running_mean, running_var, MODE_SPADE, training, relu, None, 1, 0)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# pointwise / pooling / layout
+# ----------------------------------------------------------------------------------------------------------
+class _ReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = _lib.K.relu_fwd(x.contiguous())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return _lib.K.relu_bwd(dy.contiguous(), y)
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return _lib.K.add(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+class _PoolFn(torch.autograd.Function):
+    """y = scale * sum over f x f blocks (cl tensors; an NCHW tensor is passed as (N*C, H, W, 1))"""
+
+    @staticmethod
+    def forward(ctx, x, f, scale):
+        N, H, W, C = x.shape
+        ctx.f, ctx.scale = f, scale
+        return _lib.K.pool_fwd(x.contiguous(), N, H, W, C, f, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, C = dy.shape
+        return _lib.K.unpool_fwd(dy.contiguous(), N, H, W, C, ctx.f, ctx.scale), None, None
+
+
+class _UnpoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, f, scale):
+        N, H, W, C = x.shape
+        ctx.f, ctx.scale = f, scale
+        return _lib.K.unpool_fwd(x.contiguous(), N, H, W, C, f, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, C = dy.shape
+        return _lib.K.pool_fwd(dy.contiguous(), N, H, W, C, ctx.f, ctx.scale), None, None
+
+
+def relu(x):
+    return _ReluFn.apply(x)
+
+
+def add(a, b):
+    return _AddFn.apply(a, b)
+
+
+def avg_pool2(x):
+    return _PoolFn.apply(x, 2, 0.25)
+
+
+def pool(x, f, scale):
+    return _PoolFn.apply(x, f, scale)
+
+
+def upsample_nearest(x, f):
+    return _UnpoolFn.apply(x, f, 1.0)
+
+
+def pool_nchw(x, f, scale):
+    N, C, H, W = x.shape
+    return _PoolFn.apply(x.reshape(N * C, H, W, 1), f, scale).view(N, C, H // f, W // f)
+
+
+def upsample_nearest_nchw(x, f):
+    N, C, H, W = x.shape
+    return _UnpoolFn.apply(x.reshape(N * C, H, W, 1), f, 1.0).view(N, C, H * f, W * f)
+
+
+class _TransposeFn(torch.autograd.Function):
+    """(B, R, C) -> (B, C, R)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, R, C = x.shape
+        return _lib.K.transpose(x.contiguous(), B, R, C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, R = dy.shape
+        return _lib.K.transpose(dy.contiguous(), B, C, R)
+
+
+def nchw_to_cl(x):
+    N, C, H, W = x.shape
+    return _TransposeFn.apply(x.reshape(N, C, H * W)).view(N, H, W, C)
+
+
+def cl_to_nchw(x):
+    N, H, W, C = x.shape
+    return _TransposeFn.apply(x.reshape(N, H * W, C)).view(N, C, H, W)
+
+
+class _ConcatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, a_div, b_div, rows):
+        Ca, Cb = a.shape[-1], b.shape[-1]
+        ctx.meta = (Ca, a_div, Cb, b_div, rows, a.shape, b.shape)
+        return _lib.K.concat_fwd(a.contiguous(), Ca, a_div, b.contiguous(), Cb, b_div, rows)
+
+    @staticmethod
+    def backward(ctx, dout):
+        Ca, a_div, Cb, b_div, rows, sa, sb = ctx.meta
+        da, db = _lib.K.concat_bwd(dout.contiguous(), Ca, a_div, Cb, b_div, rows, ctx.needs_input_grad[0],
+                                   ctx.needs_input_grad[1])
+        return (da.view(sa) if da is not None else None), (db.view(sb) if db is not None else None), None, None, None
+
+
+def concat_channels(a, b, a_div=1, b_div=1, rows=None):
+    """out[row] = [a[row // a_div] | b[row // b_div]]; a, b are (rows/div, C) views"""
+    if rows is None:
+        rows = a.shape[0] * a_div
+    return _ConcatFn.apply(a, b, a_div, b_div, rows)
+
+
+class _EmbeddingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, idx_i32):
+        ctx.save_for_backward(idx_i32)
+        ctx.n = table.shape[0]
+        return _lib.K.gather_rows(table, idx_i32)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        return _lib.K.scatter_rows(dout.contiguous(), idx, ctx.n), None
+
+
+def embedding(table, idx_i32):
+    return _EmbeddingFn.apply(table, idx_i32)
+
+
+class _MaskOuterFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, mask):
+        O, H, W = mask.shape[0], mask.shape[-2], mask.shape[-1]
+        ctx.save_for_backward(mask)
+        ctx.dims = (O, H, W, v.shape[1])
+        return _lib.K.mask_outer_fwd(v.contiguous(), mask, O, H, W, v.shape[1])
+
+    @staticmethod
+    def backward(ctx, dout):
+        (mask,) = ctx.saved_tensors
+        O, H, W, C = ctx.dims
+        return _lib.K.mask_outer_bwd(dout.contiguous(), mask, O, H, W, C), None
+
+
+def mask_outer(v, mask):
+    """(O,C) x (O,1,H,W) -> (O,H+2,W+2,C): the padding-1 1x1 convolution of embedding (x) mask (rank-1 form)"""
+    return _MaskOuterFn.apply(v, mask.contiguous())
+
+
+class _ReparamFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        ctx.save_for_backward(logvar, eps)
+        return _lib.K.reparam_fwd(mu.contiguous(), logvar.contiguous(), eps)
+
+    @staticmethod
+    def backward(ctx, dz):
+        logvar, eps = ctx.saved_tensors
+        dmu, dlv = _lib.K.reparam_bwd(dz.contiguous(), logvar, eps)
+        return dmu, dlv, None
+
+
+def reparameterize(mu, logvar, eps):
+    return _ReparamFn.apply(mu, logvar, eps)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# per-batch index plans (obj_to_img lives on the CPU by contract, train64.py:150)
+# ----------------------------------------------------------------------------------------------------------
+class BatchPlan:
+    """Device-side index tensors derived from obj_to_img: crop grouping and the time-major ConvLSTM packing."""
+
+    def __init__(self, obj_to_img: Sequence[int], n_images: Optional[int], device):
+        ids = list(int(v) for v in obj_to_img)
+        O = len(ids)
+        self.O = O
+        N = (max(ids) + 1) if n_images is None else n_images
+        self.N = N
+
+        def dev(lst):
+            return torch.tensor(lst, dtype=torch.int32).to(device)
+
+        # crops: boxes grouped by image, ascending box id inside an image
+        order = sorted(range(O), key=lambda b: (ids[b], b))
+        start = [0] * (N + 1)
+        for b in ids:
+            start[b + 1] += 1
+        for i in range(N):
+            start[i + 1] += start[i]
+        self.box_to_img = dev(ids)
+        self.box_order = dev(order)
+        self.img_box_start = dev(start)
+        # ConvLSTM sequences: runs of equal ids in batch order (generator_obj_att.py:286-304)
+        lens, starts = [], []
+        prev = None
+        for i, v in enumerate(ids):
+            if i == 0 or v != prev:
+                starts.append(i)
+                lens.append(1)
+            else:
+                lens[-1] += 1
+            prev = v
+        self.seq_lens, self.seq_starts = lens, starts
+        S = len(lens)
+        self.S = S
+        perm = sorted(range(S), key=lambda i: (-lens[i], i))
+        rank = [0] * S
+        for r, i in enumerate(perm):
+            rank[i] = r
+        T = max(lens) if lens else 0
+        n_t = [sum(1 for L in lens if L > t) for t in range(T)]
+        offs = [0]
+        for n in n_t:
+            offs.append(offs[-1] + n)
+        self.T, self.n_t, self.offs = T, n_t, offs
+        pack_src = [0] * O          # packed row -> object index
+        hprev_src = [-1] * O        # packed row -> packed row of the previous step (or -1)
+        for t in range(T):
+            for j in range(n_t[t]):
+                img = perm[j]
+                pack_src[offs[t] + j] = starts[img] + t
+                if t > 0:
+                    hprev_src[offs[t] + j] = offs[t - 1] + j
+        unpack_src = [0] * O        # object index -> packed row
+        for r, o in enumerate(pack_src):
+            unpack_src[o] = r
+        final_rows = [offs[lens[i] - 1] + rank[i] for i in range(S)]   # sequence i -> packed row of its last step
+        scatter_final = [-1] * O
+        for i, r in enumerate(final_rows):
+            scatter_final[r] = i
+        self.pack_src, self.unpack_src = dev(pack_src), dev(unpack_src)
+        self.hprev_src = dev(hprev_src)
+        self.final_rows, self.scatter_final = dev(final_rows), dev(scatter_final)
+
+
+_PLANS: Dict[tuple, BatchPlan] = {}
+
+
+def get_plan(obj_to_img: torch.Tensor, n_images: Optional[int], device) -> BatchPlan:
+    ids = tuple(obj_to_img.tolist())
+    key = (ids, n_images, str(device))
+    p = _PLANS.get(key)
+    if p is None:
+        if len(_PLANS) > 64:
+            _PLANS.clear()
+        p = BatchPlan(ids, n_images, device)
+        _PLANS[key] = p
+    return p
+
+
+# ----------------------------------------------------------------------------------------------------------
+# box crops
+# ----------------------------------------------------------------------------------------------------------
+_LINSPACE: Dict[tuple, torch.Tensor] = {}
+
+
+def crop_weights(S: int, device) -> torch.Tensor:
+    """[linspace(1,0,S) | linspace(0,1,S)] built on the CPU in fp32 as bilinear.py:272-275 does, then uploaded."""
+    key = (S, str(device))
+    w = _LINSPACE.get(key)
+    if w is None:
+        w = torch.cat([torch.linspace(1, 0, steps=S), torch.linspace(0, 1, steps=S)]).to(device)
+        _LINSPACE[key] = w
+    return w
+
+
+class _CropFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, boxes, plan: BatchPlan, HH, WW):
+        feats = feats.contiguous()
+        boxes = boxes.contiguous().float()
+        wx, wy = crop_weights(WW, feats.device), crop_weights(HH, feats.device)
+        ctx.save_for_backward(boxes, wx, wy)
+        ctx.plan, ctx.dims = plan, feats.shape
+        return _lib.K.crop_fwd(feats, boxes, plan.box_to_img, wx, wy, HH, WW)
+
+    @staticmethod
+    def backward(ctx, dcrops):
+        boxes, wx, wy = ctx.saved_tensors
+        N, C, H, W = ctx.dims
+        p = ctx.plan
+        d = _lib.K.crop_bwd(dcrops.contiguous(), boxes, p.img_box_start, p.box_order, wx, wy, N, H, W)
+        return d, None, None, None, None
+
+
+def crop_bbox_batch(feats, bbox, bbox_to_feats, HH, WW=None):
+    if WW is None:
+        WW = HH
+    plan = get_plan(bbox_to_feats.cpu() if bbox_to_feats.is_cuda else bbox_to_feats, feats.shape[0], feats.device)
+    return _CropFn.apply(feats, bbox, plan, HH, WW)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# ConvLSTM over per-image object sequences (hoisted input convolution, time-major packing, manual BPTT)
+# ----------------------------------------------------------------------------------------------------------
+class ConvLSTMLayer:
+    def __init__(self, cin, hid, k=5):
+        self.cin, self.hid, self.k = cin, hid, k
+        self.gx = ConvGeom(cin, 4 * hid, k, k, 1, k // 2, 0, cin + hid)
+        self.gh = ConvGeom(hid, 4 * hid, k, k, 1, k // 2, cin, cin + hid)
+        self.packs = WeightPacks()
+
+
+class _ConvLSTMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, plan: BatchPlan, layers: List[ConvLSTMLayer], *params):
+        # params = (w0, b0, w1, b1, ...)
+        O, H, W, C0 = x.shape
+        P, hw = plan.O, H * W
+        saved = []
+        xin = _lib.K.permute_rows(x.contiguous().view(O, hw * C0), plan.pack_src, hw * C0).view(P, H, W, C0)
+        dev = x.device
+        for li, L in enumerate(layers):
+            w, b = params[2 * li], params[2 * li + 1]
+            hid = L.hid
+            pre_x = conv_forward(L.gx, L.packs, w, xin, "cl", "cl", b, None, False)        # (P,H,W,4h)
+            h_all = torch.empty((P, H, W, hid), dtype=torch.float32, device=dev)
+            c_all = torch.empty((P, H, W, hid), dtype=torch.float32, device=dev)
+            gates = torch.empty((P, H, W, 4 * hid), dtype=torch.float32, device=dev)
+            for t in range(plan.T):
+                n, o = plan.n_t[t], plan.offs[t]
+                pre_h = c_prev = None
+                if t > 0:
+                    op = plan.offs[t - 1]
+                    pre_h = conv_forward(L.gh, L.packs, w, h_all[op:op + n], "cl", "cl", None, None, False)
+                    c_prev = c_all[op:op + n]
+                _lib.K.lstm_gates_fwd(pre_x[o:o + n], pre_h, c_prev, n * hw, hid, gates[o:o + n], c_all[o:o + n],
+                                      h_all[o:o + n])
+            saved.append((xin, h_all, c_all, gates))
+            xin = h_all
+        hid_last = layers[-1].hid
+        out = _lib.K.permute_rows(xin.view(P, hw * hid_last), plan.final_rows, hw * hid_last).view(plan.S, H, W, hid_last)
+        ctx.plan, ctx.layers, ctx.saved_acts, ctx.dims = plan, layers, saved, (O, H, W, C0)
+        ctx.save_for_backward(*params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        plan, layers, saved = ctx.plan, ctx.layers, ctx.saved_acts
+        params = ctx.saved_tensors
+        O, H, W, C0 = ctx.dims
+        P, hw = plan.O, H * W
+        hid_last = layers[-1].hid
+        dH = _lib.K.permute_rows(dout.contiguous().view(plan.S, hw * hid_last), plan.scatter_final,
+                                 hw * hid_last).view(P, H, W, hid_last)
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        for li in range(len(layers) - 1, -1, -1):
+            L = layers[li]
+            w = params[2 * li]
+            hid = L.hid
+            xin, h_all, c_all, gates = saved[li]
+            dpre = torch.empty((P, H, W, 4 * hid), dtype=torch.float32, device=dout.device)
+            dc_next = None
+            n_next = 0
+            for t in range(plan.T - 1, -1, -1):
+                n, o = plan.n_t[t], plan.offs[t]
+                c_prev = c_all[plan.offs[t - 1]:plan.offs[t - 1] + n] if t > 0 else None
+                dc_prev = torch.empty((n, H, W, hid), dtype=torch.float32, device=dout.device)
+                if n_next > 0:
+                    _lib.K.lstm_gates_bwd(dH[o:o + n_next], dc_next, gates[o:o + n_next], c_prev[:n_next] if t > 0 else None,
+                                          c_all[o:o + n_next], n_next * hw, hid, dpre[o:o + n_next], dc_prev[:n_next])
+                if n > n_next:
+                    a, bnd = o + n_next, o + n
+                    _lib.K.lstm_gates_bwd(dH[a:bnd], None, gates[a:bnd], c_prev[n_next:n] if t > 0 else None,
+                                          c_all[a:bnd], (n - n_next) * hw, hid, dpre[a:bnd], dc_prev[n_next:n])
+                if t > 0:
+                    op = plan.offs[t - 1]
+                    dh_rec = conv_dgrad(L.gh, L.packs, w, dpre[o:o + n], "cl", (H, W), "cl", None)
+                    _lib.K.add(dH[op:op + n], dh_rec, out=dH[op:op + n])
+                dc_next, n_next = dc_prev, n
+            gw = torch.empty_like(w)
+            conv_wgrad(L.gx, xin, "cl", dpre, "cl", gw)
+            hprev = _lib.K.permute_rows(h_all.view(P, hw * hid), plan.hprev_src, hw * hid).view(P, H, W, hid)
+            conv_wgrad(L.gh, hprev, "cl", dpre, "cl", gw)
+            grads[2 * li] = gw
+            grads[2 * li + 1] = _lib.K.colsum(dpre.view(P * hw, 4 * hid))
+            dxin = conv_dgrad(L.gx, L.packs, w, dpre, "cl", (H, W), "cl", None)
+            dH = dxin
+        dx = _lib.K.permute_rows(dH.view(P, hw * C0), plan.unpack_src, hw * C0).view(O, H, W, C0)
+        return (dx, None, None) + tuple(grads)
+
+
+def conv_lstm(x, plan: BatchPlan, layers: List[ConvLSTMLayer], params: Sequence[torch.Tensor]):
+    return _ConvLSTMFn.apply(x, plan, layers, *params)

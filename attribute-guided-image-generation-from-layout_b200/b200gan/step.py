@@ -1,0 +1,195 @@
+"""One G+D training step with the B200 modules — the wiring of the reference's train64.py:141-370 / train128.py.
+
+`TrainStep` owns the four networks (Generator, Image/Object/Attribute discriminators with spectral norm) and their
+Adam optimizers exactly as train64.py:99-114 builds them, and exposes `step(batch)` = attribute estimation, D-step
+(forward, losses, backward, 3x Adam) and G-step (forward, losses, backward, Adam).  The loss arithmetic on the tiny
+logit tensors stays in PyTorch; everything inside the networks runs libb200gan kernels.
+
+Two things the reference computes and then throws away are skipped (and subtracted from the FLOP numerator in
+bench.py): the autograd graph of the D-step's generator forward (all its uses are detached, train64.py:195-240) and
+the discriminators' weight gradients during the G-step (zeroed before use, train64.py:254-256).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+LAMBDAS = dict(img_adv=1.0, obj_adv=1.0, obj_cls=1.0, z_rec=8.0, img_rec=1.0, kl=0.01, att_cls=2.0)  # train64.py:439-446
+NUM_OBJECTS, NUM_ATTRIBUTES = 179, 106                                                               # data/vocab.json
+
+
+def default_pos_weight() -> torch.Tensor:
+    """(100000 - count) / count (train64.py:25-28) over a synthetic count table; the real table is
+    attribute_counts.py in the reference tree and is passed in by callers that have it."""
+    counts = torch.arange(NUM_ATTRIBUTES, dtype=torch.float32) * 37.0 + 150.0
+    return (100000.0 - counts) / counts
+
+
+def build_networks(image_size: int = 64, z_dim: int = 64, embedding_dim: int = 64):
+    """train64.py:99-109 / train128.py:100-110"""
+    if image_size == 128:
+        from models.generator_obj_att128 import Generator
+        from models.discriminator import AttributeDiscriminator128 as AttributeDiscriminator
+    else:
+        from models.generator_obj_att import Generator
+        from models.discriminator import AttributeDiscriminator
+    from models.discriminator import ImageDiscriminator, ObjectDiscriminator, add_sn
+    netG = Generator(num_embeddings=NUM_OBJECTS, obj_att_dim=embedding_dim, z_dim=z_dim, clstm_layers=3,
+                     obj_size=image_size // 2, attribute_dim=NUM_ATTRIBUTES)
+    netD_image = add_sn(ImageDiscriminator(conv_dim=embedding_dim))
+    netD_object = add_sn(ObjectDiscriminator(n_class=NUM_OBJECTS))
+    netD_att = add_sn(AttributeDiscriminator(n_attribute=NUM_ATTRIBUTES))
+    return netG, netD_image, netD_object, netD_att
+
+
+def bce_const(logits, value: float):
+    return F.binary_cross_entropy_with_logits(logits, torch.full_like(logits, value))
+
+
+def estimate_attributes(att_logits, attribute):
+    """train64.py:155-166 (intended semantics): un-annotated objects get their arg-max attribute switched on."""
+    none = (attribute.sum(dim=1, keepdim=True) == 0).to(attribute.dtype)
+    idx = att_logits.argmax(1, keepdim=True)
+    est = attribute.clone()
+    est.scatter_(1, idx, torch.maximum(est.gather(1, idx), none))
+    return est
+
+
+class TrainStep:
+    def __init__(self, image_size: int = 64, device="cuda", lr: float = 2e-4, lambdas: Optional[Dict[str, float]] = None,
+                 pos_weight: Optional[torch.Tensor] = None, skip_dead_work: bool = True, fused_adam: bool = True,
+                 capturable: bool = False):
+        self.image_size, self.obj_size = image_size, image_size // 2
+        self.device = torch.device(device)
+        self.lam = dict(LAMBDAS if lambdas is None else lambdas)
+        self.netG, self.netD_image, self.netD_object, self.netD_att = [n.to(self.device) for n in
+                                                                       build_networks(image_size)]
+        self.pos_weight = (default_pos_weight() if pos_weight is None else pos_weight).to(self.device)
+        self.skip_dead_work = skip_dead_work
+        kw = dict(lr=lr, betas=(0.5, 0.999))
+        if self.device.type == "cuda":
+            kw.update(fused=fused_adam, capturable=capturable)
+        self.opt_G = torch.optim.Adam(self.netG.parameters(), **kw)                  # train64.py:111-114
+        self.opt_D = [torch.optim.Adam(n.parameters(), **kw) for n in (self.netD_image, self.netD_object, self.netD_att)]
+        self.d_nets = (self.netD_image, self.netD_object, self.netD_att)
+
+    # ---- batch handling ---------------------------------------------------------------------------------
+    def to_device(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """train64.py:149-151: everything but obj_to_img moves to the device; index sets that the reference derives with
+        nonzero() on the device are derived here from the CPU copy (no device sync inside the step)."""
+        b = {k: (v if k == "obj_to_img" else v.to(self.device, non_blocking=True)) for k, v in batch.items()}
+        att = batch["attribute"]
+        b["att_idx"] = att.sum(dim=1).nonzero().view(-1).to(self.device)
+        return b
+
+    def generator(self, b, attribute_est):
+        return self.netG(b["imgs"], b["objs"], b["boxes"], b["masks"], b["obj_to_img"], b["z"], b["attribute"],
+                         b["masks_shift"], b["boxes_shift"], attribute_est)
+
+    # ---- losses (train64.py:195-252, 284-364) ----------------------------------------------------------------
+    def d_loss(self, b, fake):
+        crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift = [t.detach() for t in fake[:7]]
+        D_i, D_o, D_a = self.d_nets
+        objs = b["objs"]
+        l = {}
+        l["d_img_fake"] = 0.4 * bce_const(D_i(img_rec), 0) + 0.4 * bce_const(D_i(img_rand), 0) + 0.2 * bce_const(D_i(img_shift), 0)
+        l["d_img_real"] = bce_const(D_i(b["imgs"]), 1)
+        l["d_obj_fake"] = 0.4 * bce_const(D_o(crops_input_rec, objs)[0], 0) + 0.4 * bce_const(D_o(crops_rand, objs)[0], 0) \
+            + 0.2 * bce_const(D_o(crops_shift, objs)[0], 0)
+        src, cls = D_o(crops_input, objs)
+        l["d_obj_real"] = bce_const(src, 1)
+        l["d_obj_cls"] = F.cross_entropy(cls, objs)
+        att_cls = D_a(crops_input)
+        idx = b["att_idx"]
+        l["d_att"] = F.binary_cross_entropy_with_logits(att_cls.index_select(0, idx), b["attribute_GT"].index_select(0, idx),
+                                                        pos_weight=self.pos_weight)
+        lam = self.lam
+        total = lam["img_adv"] * (l["d_img_fake"] + l["d_img_real"]) + lam["obj_adv"] * (l["d_obj_fake"] + l["d_obj_real"]) \
+            + lam["obj_cls"] * l["d_obj_cls"] + lam["att_cls"] * l["d_att"]
+        return total, l
+
+    def g_loss(self, b, out):
+        (crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift, mu, logvar, z_rand_rec,
+         z_rand_shift) = out
+        D_i, D_o, D_a = self.d_nets
+        imgs, z, objs, attribute = b["imgs"], b["z"], b["objs"], b["attribute"]
+        N = imgs.shape[0]
+        n_change = math.floor(N / 3)
+        rec_mask = torch.ones(N, device=imgs.device)
+        rec_mask[:n_change] = 0
+        l = {}
+        l["g_img_rec"] = (rec_mask * (img_rec - imgs).abs().view(N, -1).mean(1)).sum() / (N - n_change)
+        l["g_z_rec"] = 0.5 * (z_rand_rec - z).abs().mean() + 0.5 * (z_rand_shift - z).abs().mean()
+        l["g_kl"] = -0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp())
+        l["g_img_adv"] = 0.4 * bce_const(D_i(img_rec), 1) + 0.4 * bce_const(D_i(img_rand), 1) + 0.2 * bce_const(D_i(img_shift), 1)
+        idx = b["att_idx"]
+        att_t = attribute.index_select(0, idx)
+        adv, cls, att = [], [], []
+        for crops in (crops_input_rec, crops_rand, crops_shift):
+            src, c = D_o(crops, objs)
+            adv.append(bce_const(src, 1))
+            cls.append(F.cross_entropy(c, objs))
+            att.append(F.binary_cross_entropy_with_logits(D_a(crops).index_select(0, idx), att_t, pos_weight=self.pos_weight))
+        w = (0.4, 0.4, 0.2)
+        l["g_obj_adv"] = sum(wi * v for wi, v in zip(w, adv))
+        l["g_obj_cls"] = sum(wi * v for wi, v in zip(w, cls))
+        l["g_obj_att"] = sum(wi * v for wi, v in zip(w, att))
+        lam = self.lam
+        total = lam["img_rec"] * l["g_img_rec"] + lam["z_rec"] * l["g_z_rec"] + lam["img_adv"] * l["g_img_adv"] \
+            + lam["obj_adv"] * l["g_obj_adv"] + lam["obj_cls"] * l["g_obj_cls"] + lam["att_cls"] * l["g_obj_att"] \
+            + lam["kl"] * l["g_kl"]
+        return total, l
+
+    # ---- the step --------------------------------------------------------------------------------------------
+    def step(self, b: Dict[str, torch.Tensor], optimizer_step: bool = True, seeds=None):
+        """b: device batch from to_device().  seeds: optional (seed_d, seed_g) for torch.manual_seed before each generator
+        forward (pins the CropEncoder noise like the parity harness of the oracle)."""
+        from models.bilinear import crop_bbox_batch
+        D_i, D_o, D_a = self.d_nets
+        b = dict(b)
+        b["attribute_GT"] = b["attribute"].clone()
+        with torch.no_grad():
+            crops = crop_bbox_batch(b["imgs"], b["boxes"], b["obj_to_img"], self.obj_size)     # train64.py:160
+            est_logits = D_a(crops)                                                             # train64.py:161
+        attribute_est = estimate_attributes(est_logits, b["attribute"])
+        # ---------------- D-step ----------------
+        if seeds is not None:
+            torch.manual_seed(seeds[0])
+        if self.skip_dead_work:
+            with torch.no_grad():
+                fake = self.generator(b, attribute_est)                                           # train64.py:191
+        else:
+            fake = self.generator(b, attribute_est)
+        d_total, d_terms = self.d_loss(b, fake)
+        for n in self.d_nets:
+            n.zero_grad(set_to_none=True)
+        d_total.backward()
+        if optimizer_step:
+            for o in self.opt_D:
+                o.step()
+        # ---------------- G-step ----------------
+        if seeds is not None:
+            torch.manual_seed(seeds[1])
+        if self.skip_dead_work:
+            for n in self.d_nets:
+                for p in n.parameters():
+                    p.requires_grad_(False)
+        try:
+            out = self.generator(b, attribute_est)                                                # train64.py:280
+            g_total, g_terms = self.g_loss(b, out)
+            self.netG.zero_grad(set_to_none=True)
+            g_total.backward()
+        finally:
+            if self.skip_dead_work:
+                for n in self.d_nets:
+                    for p in n.parameters():
+                        p.requires_grad_(True)
+        if optimizer_step:
+            self.opt_G.step()
+        return dict(d_loss=d_total.detach(), g_loss=g_total.detach(), d_terms=d_terms, g_terms=g_terms, out_g=out,
+                    attribute_est=attribute_est)

@@ -1,0 +1,265 @@
+// conv_simt.cu — fp32 CUDA-core gather-GEMM convolutions (forward-type and weight-gradient).
+// This is the bit-tight parity path (plain fp32 FMA accumulation) and the handler of the skinny cases the
+// tcgen05 path does not take (Cin = 3 first layers, Linear heads).  Descriptor semantics: include/b200gan.h.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+struct RowGeom {
+    int64_t in_base;   // n * in_sn
+    int iy0, ix0;      // qy*in_sy + tap_oy, qx*in_sx + tap_ox
+    int valid;
+};
+
+__device__ __forceinline__ void decode_row(const b200_conv_desc& d, int64_t m, int64_t M, RowGeom& g) {
+    g.valid = m < M;
+    if (!g.valid) { g.in_base = 0; g.iy0 = g.ix0 = 0; return; }
+    int qx = (int)(m % d.Qw);
+    int qy = (int)((m / d.Qw) % d.Qh);
+    int64_t n = m / ((int64_t)d.Qw * d.Qh);
+    g.in_base = n * d.in_sn;
+    g.iy0 = qy * d.in_sy + d.tap_oy;
+    g.ix0 = qx * d.in_sx + d.tap_ox;
+}
+
+__device__ __forceinline__ int64_t out_offset(const b200_conv_desc& d, int64_t m, int64_t M) {
+    if (m >= M) return -1;
+    int qx = (int)(m % d.Qw);
+    int qy = (int)((m / d.Qw) % d.Qh);
+    int64_t n = m / ((int64_t)d.Qw * d.Qh);
+    int oy = qy * d.out_sy + d.out_oy, ox = qx * d.out_sx + d.out_ox;
+    if (oy < 0 || oy >= d.Ho || ox < 0 || ox >= d.Wo) return -1;
+    return n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// forward-type gather GEMM: out[m, co] = sum_k A[m, k] * wmat[co, k]
+// VEC: Cin % 16 == 0, in_sc == 1, 16-byte aligned rows -> one tap per K step and float4 gathers
+// ----------------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256) conv_gemm_f32_kernel(b200_conv_desc d, const float* __restrict__ in,
+                                                            const float* __restrict__ wmat,
+                                                            const float* __restrict__ bias,
+                                                            const float* __restrict__ scale, float* __restrict__ out) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    __shared__ int64_t row_out[BM];
+
+    const int tid = threadIdx.x;
+    const int64_t M = (int64_t)d.B * d.Qh * d.Qw;
+    const int K = d.Th * d.Tw * d.Cin;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+
+    // loader mapping: 64 rows x 4 k-quads
+    const int lr = tid >> 2;
+    const int lk = (tid & 3) * 4;
+    RowGeom rg;
+    decode_row(d, m0 + lr, M, rg);
+    if (tid < BM) row_out[tid] = out_offset(d, m0 + tid, M);
+
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int wrow = n0 + lr;
+    const bool wvalid = wrow < d.Cout;
+    const bool wvec = (d.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(wmat) & 15) == 0);
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (VEC) {
+            int tap = k0 / d.Cin, c0 = k0 - tap * d.Cin;
+            int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
+            int iy = rg.iy0 + tyy * d.tap_sy, ix = rg.ix0 + txx * d.tap_sx;
+            if (rg.valid && iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi) {
+                const float* p = in + rg.in_base + (int64_t)(iy >> d.up_shift) * d.in_sh +
+                                 (int64_t)(ix >> d.up_shift) * d.in_sw + c0 + lk;
+                float4 v = *reinterpret_cast<const float4*>(p);
+                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int k = k0 + lk + e;
+                if (rg.valid && k < K) {
+                    int tap = k / d.Cin, c = k - tap * d.Cin;
+                    int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
+                    int iy = rg.iy0 + tyy * d.tap_sy, ix = rg.ix0 + txx * d.tap_sx;
+                    if (iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi)
+                        a[e] = in[rg.in_base + (int64_t)(iy >> d.up_shift) * d.in_sh +
+                                  (int64_t)(ix >> d.up_shift) * d.in_sw + (int64_t)c * d.in_sc];
+                }
+            }
+        }
+        float b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (wvalid) {
+            const float* p = wmat + (int64_t)wrow * d.ldw + k0 + lk;
+            if (wvec && k0 + lk + 3 < K) {
+                float4 v = *reinterpret_cast<const float4*>(p);
+                b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (k0 + lk + e < K) b[e] = p[e];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            As[lk + e][lr] = a[e];
+            Bs[lk + e][lr] = b[e];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float ar[4] = {av.x, av.y, av.z, av.w};
+            float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+    }
+    __syncthreads();
+    const float alpha = scale ? *scale : 1.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t ro = row_out[ty * 4 + i];
+        if (ro < 0) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int co = n0 + tx * 4 + j;
+            if (co >= d.Cout) continue;
+            float v = acc[i][j] * alpha + (bias ? bias[co] : 0.f);
+            if (d.relu) v = fmaxf(v, 0.f);
+            out[ro + (int64_t)co * d.out_sc] = v;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// weight-gradient gather GEMM: R[m, tap*Cin + c] = sum_q P[q, m] * G_tap[q, c]
+// grid: (ceil(Cout/64), taps * ceil(Cin/64), splits)
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wgrad_gemm_f32_kernel(b200_conv_desc d, const float* __restrict__ P,
+                                                             const float* __restrict__ G, float* __restrict__ ws,
+                                                             int64_t rows_per_split) {
+    __shared__ __align__(16) float Ps[BK][BM + 4];
+    __shared__ __align__(16) float Gs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int64_t Q = (int64_t)d.B * d.Qh * d.Qw;
+    const int ctiles = (d.Cin + BN - 1) / BN;
+    const int tap = blockIdx.y / ctiles;
+    const int c0 = (blockIdx.y % ctiles) * BN;
+    const int m0 = blockIdx.x * BM;
+    const int tyy = tap / d.Tw, txx = tap % d.Tw;
+    const int64_t q_begin = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t q_end = q_begin + rows_per_split < Q ? q_begin + rows_per_split : Q;
+
+    // loader mapping: 16 pixels x 16 channel-quads
+    const int lq = tid >> 4;
+    const int lc = (tid & 15) * 4;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int64_t q0 = q_begin; q0 < q_end; q0 += BK) {
+        int64_t q = q0 + lq;
+        float p[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (q < q_end) {
+            int qx = (int)(q % d.Qw);
+            int qy = (int)((q / d.Qw) % d.Qh);
+            int64_t n = q / ((int64_t)d.Qw * d.Qh);
+            int oy = qy * d.out_sy + d.out_oy, ox = qx * d.out_sx + d.out_ox;
+            if (oy >= 0 && oy < d.Ho && ox >= 0 && ox < d.Wo) {
+                const float* pp = P + n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (m0 + lc + e < d.Cout) p[e] = pp[(int64_t)(m0 + lc + e) * d.out_sc];
+            }
+            int iy = qy * d.in_sy + d.tap_oy + tyy * d.tap_sy, ix = qx * d.in_sx + d.tap_ox + txx * d.tap_sx;
+            if (iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi) {
+                const float* gp = G + n * d.in_sn + (int64_t)(iy >> d.up_shift) * d.in_sh +
+                                  (int64_t)(ix >> d.up_shift) * d.in_sw;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (c0 + lc + e < d.Cin) g[e] = gp[(int64_t)(c0 + lc + e) * d.in_sc];
+            }
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&Ps[lq][lc]) = make_float4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<float4*>(&Gs[lq][lc]) = make_float4(g[0], g[1], g[2], g[3]);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 av = *reinterpret_cast<const float4*>(&Ps[kk][ty * 4]);
+            float4 bv = *reinterpret_cast<const float4*>(&Gs[kk][tx * 4]);
+            float ar[4] = {av.x, av.y, av.z, av.w};
+            float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+    }
+    const int64_t Kt = (int64_t)d.Th * d.Tw * d.Cin;
+    float* dst = ws + (int64_t)blockIdx.z * d.Cout * Kt;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m >= d.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int c = c0 + tx * 4 + j;
+            if (c >= d.Cin) continue;
+            dst[(int64_t)m * Kt + (int64_t)tap * d.Cin + c] = acc[i][j];
+        }
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_conv_gemm_f32(const b200_conv_desc* d, const float* in, const float* wmat, const float* bias,
+                                  const float* scale, float* out, b200_stream_t stream) {
+    int64_t M = (int64_t)d->B * d->Qh * d->Qw;
+    if (M == 0 || d->Cout == 0) return 0;
+    B200_REQUIRE(d->Cin > 0 && d->Th > 0 && d->Tw > 0, "conv_gemm_f32: bad descriptor");
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((d->Cout + BN - 1) / BN));
+    B200_REQUIRE(grid.y < 65536, "conv_gemm_f32: Cout too large");
+    bool vec = d->Cin % 16 == 0 && d->in_sc == 1 && d->in_sn % 4 == 0 && d->in_sh % 4 == 0 && d->in_sw % 4 == 0 &&
+               (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    if (vec)
+        conv_gemm_f32_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(*d, in, wmat, bias, scale, out);
+    else
+        conv_gemm_f32_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(*d, in, wmat, bias, scale, out);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_wgrad_gemm_f32(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+                                   b200_stream_t stream) {
+    int64_t Q = (int64_t)d->B * d->Qh * d->Qw;
+    B200_REQUIRE(splits >= 1 && splits < 65536, "wgrad_gemm_f32: bad splits");
+    int64_t rps = (Q + splits - 1) / splits;
+    rps = (rps + BK - 1) / BK * BK;
+    if (rps < BK) rps = BK;
+    int ctiles = (d->Cin + BN - 1) / BN;
+    dim3 grid((unsigned)((d->Cout + BM - 1) / BM), (unsigned)(d->Th * d->Tw * ctiles), (unsigned)splits);
+    B200_REQUIRE(grid.y < 65536, "wgrad_gemm_f32: too many tap tiles");
+    wgrad_gemm_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(*d, P, G, ws, rps);
+    B200_CHECK_LAUNCH();
+    return 0;
+}

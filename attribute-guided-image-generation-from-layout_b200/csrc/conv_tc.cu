@@ -1,0 +1,593 @@
+// conv_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM convolutions for sm_100a (K1/K2 forward-type, K3 weight gradient).
+//
+// Forward-type kernel (conv fwd, dgrad, ConvTranspose phases): one CTA computes a 128 x BN output tile.
+//   warps 0-3 : A producers — gather the im2col rows of the tile straight from the NHWC fp32 activation
+//               (coalesced 16-byte loads, zero fill for padding), convert to bf16 and store them into shared
+//               memory in the canonical K-major SWIZZLE_128B layout; afterwards they run the epilogue
+//               (tcgen05.ld from TMEM, scale / bias / ReLU, strided store).
+//   warp 4    : B producer — TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) loads of the packed bf16 weight matrix.
+//   warp 5    : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM).
+//   smem ring : STAGES x (A 128x64 bf16 = 16 KB, B BNx64 bf16), mbarrier full/empty pairs, tcgen05.commit releases.
+// Weight-gradient kernel: R[m, c] = sum_pixels P[pix, m] * G[pix, c]; both operands are pixel-major tiles
+//   (64 pixels x 128 B of channels) = the canonical MN-major SWIZZLE_128B layout, so the same producer code feeds
+//   them; split over the pixel range with fp32 partials reduced by b200_wgrad_reduce (deterministic).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace b200 {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int kSpinLimit = 1 << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > kSpinLimit) __trap();   // a broken pipeline must not hang the GPU
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor), bf16 x bf16 -> f32, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+struct SmemTail {            // lives after the operand ring
+    uint64_t full[8];
+    uint64_t empty[8];
+    uint64_t tmem_full;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// forward-type kernel
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap, b200_conv_desc d,
+                                                           const float* __restrict__ in,
+                                                           const float* __restrict__ bias,
+                                                           const float* __restrict__ scale, float* __restrict__ out) {
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_BYTES;
+    SmemTail* tail = reinterpret_cast<SmemTail*>(smem_b + STAGES * B_BYTES);
+    int64_t* row_base = reinterpret_cast<int64_t*>(tail + 1);
+    int64_t* row_out = row_base + BM;
+    int* row_iy = reinterpret_cast<int*>(row_out + BM);
+    int* row_ix = row_iy + BM;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int64_t M = (int64_t)d.B * d.Qh * d.Qw;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int cpb = d.Cin / BK;                     // channel blocks per tap
+    const int num_kb = d.Th * d.Tw * cpb;
+
+    if (tid < BM) {
+        int64_t m = m0 + tid;
+        if (m < M) {
+            int qx = (int)(m % d.Qw);
+            int qy = (int)((m / d.Qw) % d.Qh);
+            int64_t n = m / ((int64_t)d.Qw * d.Qh);
+            row_base[tid] = n * d.in_sn;
+            row_iy[tid] = qy * d.in_sy + d.tap_oy;
+            row_ix[tid] = qx * d.in_sx + d.tap_ox;
+            int oy = qy * d.out_sy + d.out_oy, ox = qx * d.out_sx + d.out_ox;
+            row_out[tid] = (oy >= 0 && oy < d.Ho && ox >= 0 && ox < d.Wo)
+                               ? n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw
+                               : -1;
+        } else {
+            row_base[tid] = -1;
+            row_iy[tid] = row_ix[tid] = 0;
+            row_out[tid] = -1;
+        }
+    }
+    if (warp == 4 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    }
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(smem_u32(&tail->full[s]), 128 + 1);
+                mbar_init(smem_u32(&tail->empty[s]), 1);
+            }
+            mbar_init(smem_u32(&tail->tmem_full), 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(&tail->tmem_base), TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+
+    if (warp < 4) {
+        // ===================== A producers =====================
+        const int j = lane & 15;          // 16-byte fp32 chunk (4 channels) within the 64-channel block
+        const int rsub = lane >> 4;       // 2 rows per warp instruction
+        int tap = 0, cc = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+            mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
+            const int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
+            const int dy = tyy * d.tap_sy, dx = txx * d.tap_sx;
+            const int c0 = cc * BK + j * 4;
+            float4 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int r = warp * 32 + i * 2 + rsub;
+                const int iy = row_iy[r] + dy, ix = row_ix[r] + dx;
+                const int64_t base = row_base[r];
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base >= 0 && iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi) {
+                    const float* p = in + base + (int64_t)(iy >> d.up_shift) * d.in_sh +
+                                     (int64_t)(ix >> d.up_shift) * d.in_sw + c0;
+                    v[i] = __ldg(reinterpret_cast<const float4*>(p));
+                }
+            }
+            const uint32_t a_base = smem_u32(smem_a + s * A_BYTES);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int r = warp * 32 + i * 2 + rsub;
+                const uint32_t addr = a_base + r * 128 + ((((uint32_t)j >> 1) ^ ((uint32_t)r & 7u)) << 4) + (j & 1) * 8;
+                st_shared_v2(addr, pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+            }
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&tail->full[s]));
+            if (++cc == cpb) { cc = 0; ++tap; }
+        }
+        // ===================== epilogue =====================
+        mbar_wait(smem_u32(&tail->tmem_full), 0);
+        tc_fence_after();
+        const int row = warp * 32 + lane;
+        const int64_t ro = row_out[row];
+        const float alpha = scale ? *scale : 1.f;
+        const bool vec = d.out_sc == 1 && ((d.out_sn | d.out_sh | d.out_sw) & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (d.Cout & 3) == 0;
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r);
+            if (ro >= 0) {
+                float o[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    int co = n0 + cb + e;
+                    float val = __uint_as_float(r[e]) * alpha + ((bias && co < d.Cout) ? bias[co] : 0.f);
+                    o[e] = d.relu ? fmaxf(val, 0.f) : val;
+                }
+                if (vec && n0 + cb + 16 <= d.Cout) {
+                    float4* p = reinterpret_cast<float4*>(out + ro + n0 + cb);
+                    p[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    p[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    p[2] = make_float4(o[8], o[9], o[10], o[11]);
+                    p[3] = make_float4(o[12], o[13], o[14], o[15]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        int co = n0 + cb + e;
+                        if (co < d.Cout) out[ro + (int64_t)co * d.out_sc] = o[e];
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ===================== B producer (TMA) =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
+                const uint32_t bar = smem_u32(&tail->full[s]);
+                mbar_arrive_expect_tx(bar, B_BYTES);
+                tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tmap, kb * BK, n0, bar);
+            }
+        }
+    } else {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+            mbar_wait(smem_u32(&tail->full[s]), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint64_t adesc = make_desc(smem_u32(smem_a + s * A_BYTES), 16, 1024);
+                const uint64_t bdesc = make_desc(smem_u32(smem_b + s * B_BYTES), 16, 1024);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                umma_commit(smem_u32(&tail->empty[s]));
+                if (kb == num_kb - 1) umma_commit(smem_u32(&tail->tmem_full));
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight-gradient kernel: R[m0:m0+128, tap, c0:c0+BNW] over a pixel split
+// ------------------------------------------------------------------------------------------------------------
+struct PixInfo {
+    int64_t p_off;   // offset of P row (or -1)
+    int64_t g_off;   // offset of G pixel for this tap (or -1)
+};
+
+template <int BNW, int STAGES>
+__global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(b200_conv_desc d, const float* __restrict__ P,
+                                                            const float* __restrict__ G, float* __restrict__ ws,
+                                                            int64_t rows_per_split) {
+    constexpr int PA_BYTES = 2 * 64 * 128;            // 128 P channels x 64 pixels (two MN atoms)
+    constexpr int GB_BYTES = (BNW / 64) * 64 * 128;   // BNW G channels x 64 pixels
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * PA_BYTES;
+    SmemTail* tail = reinterpret_cast<SmemTail*>(smem_b + STAGES * GB_BYTES);
+    PixInfo* pix = reinterpret_cast<PixInfo*>(tail + 1);   // [STAGES][64]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int64_t Q = (int64_t)d.B * d.Qh * d.Qw;
+    const int ctiles = (d.Cin + BNW - 1) / BNW;
+    const int tap = blockIdx.y / ctiles;
+    const int c0 = (blockIdx.y % ctiles) * BNW;
+    const int m0 = blockIdx.x * BM;
+    const int tyy = tap / d.Tw, txx = tap % d.Tw;
+    const int64_t q_begin = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t q_end = q_begin + rows_per_split < Q ? q_begin + rows_per_split : Q;
+    const int num_kb = q_end > q_begin ? (int)((q_end - q_begin + 63) / 64) : 0;
+
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(smem_u32(&tail->full[s]), 128);
+                mbar_init(smem_u32(&tail->empty[s]), 1);
+            }
+            mbar_init(smem_u32(&tail->tmem_full), 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(&tail->tmem_base), BNW < 32 ? 32 : BNW);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+
+    if (warp < 4) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+            mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
+            PixInfo* pi = pix + s * 64;
+            if (tid < 64) {
+                int64_t q = q_begin + (int64_t)kb * 64 + tid;
+                PixInfo info;
+                info.p_off = -1;
+                info.g_off = -1;
+                if (q < q_end) {
+                    int qx = (int)(q % d.Qw);
+                    int qy = (int)((q / d.Qw) % d.Qh);
+                    int64_t n = q / ((int64_t)d.Qw * d.Qh);
+                    int oy = qy * d.out_sy + d.out_oy, ox = qx * d.out_sx + d.out_ox;
+                    if (oy >= 0 && oy < d.Ho && ox >= 0 && ox < d.Wo)
+                        info.p_off = n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
+                    int iy = qy * d.in_sy + d.tap_oy + tyy * d.tap_sy, ix = qx * d.in_sx + d.tap_ox + txx * d.tap_sx;
+                    if (iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi)
+                        info.g_off = n * d.in_sn + (int64_t)(iy >> d.up_shift) * d.in_sh +
+                                     (int64_t)(ix >> d.up_shift) * d.in_sw;
+                }
+                pi[tid] = info;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // ---- P tile: 64 pixels x 128 channels; a warp instruction covers one pixel row (32 lanes x 4 channels)
+            {
+                const int ch = lane * 4;
+                const int atom = lane >> 4, j = lane & 15;
+                float4 v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int prow = warp * 16 + i;
+                    const int64_t off = pi[prow].p_off;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (off >= 0 && m0 + ch < d.Cout) v[i] = __ldg(reinterpret_cast<const float4*>(P + off + m0 + ch));
+                }
+                const uint32_t a_base = smem_u32(smem_a + s * PA_BYTES) + atom * 8192;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int prow = warp * 16 + i;
+                    const uint32_t addr = a_base + prow * 128 + ((((uint32_t)j >> 1) ^ ((uint32_t)prow & 7u)) << 4) + (j & 1) * 8;
+                    st_shared_v2(addr, pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+                }
+            }
+            // ---- G tile: 64 pixels x BNW channels
+            if (BNW == 128) {
+                const int ch = lane * 4;
+                const int atom = lane >> 4, j = lane & 15;
+                float4 v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int prow = warp * 16 + i;
+                    const int64_t off = pi[prow].g_off;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (off >= 0 && c0 + ch < d.Cin) v[i] = __ldg(reinterpret_cast<const float4*>(G + off + c0 + ch));
+                }
+                const uint32_t b_base = smem_u32(smem_b + s * GB_BYTES) + atom * 8192;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int prow = warp * 16 + i;
+                    const uint32_t addr = b_base + prow * 128 + ((((uint32_t)j >> 1) ^ ((uint32_t)prow & 7u)) << 4) + (j & 1) * 8;
+                    st_shared_v2(addr, pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+                }
+            } else {
+                const int j = lane & 15, rsub = lane >> 4;
+                const int ch = j * 4;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int prow = warp * 16 + i * 2 + rsub;
+                    const int64_t off = pi[prow].g_off;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (off >= 0 && c0 + ch < d.Cin) v[i] = __ldg(reinterpret_cast<const float4*>(G + off + c0 + ch));
+                }
+                const uint32_t b_base = smem_u32(smem_b + s * GB_BYTES);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int prow = warp * 16 + i * 2 + rsub;
+                    const uint32_t addr = b_base + prow * 128 + ((((uint32_t)j >> 1) ^ ((uint32_t)prow & 7u)) << 4) + (j & 1) * 8;
+                    st_shared_v2(addr, pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&tail->full[s]));
+        }
+        // ---- epilogue: TMEM lane = P channel m, column = G channel c
+        const int64_t Kt = (int64_t)d.Th * d.Tw * d.Cin;
+        float* dst = ws + (int64_t)blockIdx.z * d.Cout * Kt;
+        const int m = m0 + warp * 32 + lane;
+        if (num_kb > 0) {
+            mbar_wait(smem_u32(&tail->tmem_full), 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int cb = 0; cb < BNW; cb += 16) {
+            uint32_t r[16];
+            if (num_kb > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) r[e] = 0u;
+            }
+            if (m < d.Cout) {
+                float* p = dst + (int64_t)m * Kt + (int64_t)tap * d.Cin + c0 + cb;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (c0 + cb + e < d.Cin) p[e] = __uint_as_float(r[e]);
+            }
+        }
+    } else if (warp == 5) {
+        constexpr uint32_t idesc = make_idesc(BNW, 1, 1);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+            mbar_wait(smem_u32(&tail->full[s]), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                // MN-major SWIZZLE_128B: LBO = stride between 64-element MN atoms (8192 B), SBO = stride between
+                // 8-row K groups (1024 B); each UMMA (K = 16 pixels) advances 16 rows = 2048 B
+                const uint64_t adesc = make_desc(smem_u32(smem_a + s * PA_BYTES), 8192, 1024);
+                const uint64_t bdesc = make_desc(smem_u32(smem_b + s * GB_BYTES), 8192, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+                umma_commit(smem_u32(&tail->empty[s]));
+                if (kb == num_kb - 1) umma_commit(smem_u32(&tail->tmem_full));
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, BNW < 32 ? 32 : BNW);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int BN, int STAGES>
+static int launch_fwd(const b200_conv_desc* d, const float* in, const void* wmat, const float* bias,
+                      const float* scale, float* out, cudaStream_t st) {
+    EncodeTiledFn enc = get_encode_fn();
+    B200_REQUIRE(enc != nullptr, "conv_gemm_tc: cuTensorMapEncodeTiled unavailable");
+    int64_t M = (int64_t)d->B * d->Qh * d->Qw;
+    int ntiles = (d->Cout + BN - 1) / BN;
+    CUtensorMap tmap;
+    cuuint64_t gdim[2] = {(cuuint64_t)d->ldw, (cuuint64_t)ntiles * BN};
+    cuuint64_t gstr[1] = {(cuuint64_t)d->ldw * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wmat), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    constexpr int smem_bytes = 1024 + STAGES * (A_BYTES + BN * BK * 2) + (int)sizeof(SmemTail) + BM * 24;
+    auto kern = conv_gemm_tc_kernel<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles);
+    kern<<<grid, 192, smem_bytes, st>>>(tmap, *d, in, bias, scale, out);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int BNW, int STAGES>
+static int launch_wgrad(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+                        cudaStream_t st) {
+    int64_t Q = (int64_t)d->B * d->Qh * d->Qw;
+    int64_t rps = (Q + splits - 1) / splits;
+    rps = (rps + 63) / 64 * 64;
+    if (rps < 64) rps = 64;
+    constexpr int smem_bytes = 1024 + STAGES * (2 * 8192 + (BNW / 64) * 8192) + (int)sizeof(SmemTail) + STAGES * 64 * 16;
+    auto kern = wgrad_gemm_tc_kernel<BNW, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        B200_REQUIRE(e == cudaSuccess, "wgrad_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    int ctiles = (d->Cin + BNW - 1) / BNW;
+    dim3 grid((unsigned)((d->Cout + BM - 1) / BM), (unsigned)(d->Th * d->Tw * ctiles), (unsigned)splits);
+    B200_REQUIRE(grid.y < 65536 && grid.z < 65536, "wgrad_gemm_tc: grid too large");
+    kern<<<grid, 192, smem_bytes, st>>>(*d, P, G, ws, rps);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_conv_tc_ntile(int Cout) { return Cout >= 128 ? 128 : (Cout >= 64 ? 64 : 16); }
+
+extern "C" int b200_conv_gemm_tc(const b200_conv_desc* d, const float* in, const void* wmat_bf16, const float* bias,
+                                 const float* scale, float* out, b200_stream_t stream) {
+    int64_t M = (int64_t)d->B * d->Qh * d->Qw;
+    if (M == 0 || d->Cout == 0) return 0;
+    B200_REQUIRE(d->Cin % 64 == 0 && d->in_sc == 1, "conv_gemm_tc: needs Cin %% 64 == 0 and channel-last input");
+    B200_REQUIRE(((d->in_sn | d->in_sh | d->in_sw) & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0,
+                 "conv_gemm_tc: input rows must be 16-byte aligned");
+    B200_REQUIRE(d->ldw % 64 == 0 && d->ldw >= (int64_t)d->Th * d->Tw * d->Cin, "conv_gemm_tc: bad ldw");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(wmat_bf16) & 15) == 0, "conv_gemm_tc: wmat must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    int bn = b200_conv_tc_ntile(d->Cout);
+    if (bn == 128) return tc::launch_fwd<128, 3>(d, in, wmat_bf16, bias, scale, out, st);
+    if (bn == 64) return tc::launch_fwd<64, 4>(d, in, wmat_bf16, bias, scale, out, st);
+    return tc::launch_fwd<16, 4>(d, in, wmat_bf16, bias, scale, out, st);
+}
+
+extern "C" int b200_wgrad_gemm_tc(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+                                  b200_stream_t stream) {
+    B200_REQUIRE(splits >= 1, "wgrad_gemm_tc: bad splits");
+    B200_REQUIRE(d->Cin % 64 == 0 && d->in_sc == 1 && d->Cout % 64 == 0 && d->out_sc == 1,
+                 "wgrad_gemm_tc: needs channel-last operands with channels %% 64 == 0");
+    B200_REQUIRE(((d->in_sn | d->in_sh | d->in_sw | d->out_sn | d->out_sh | d->out_sw) & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(P) & 15) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0,
+                 "wgrad_gemm_tc: operand rows must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    if (d->Cin >= 128) return tc::launch_wgrad<128, 3>(d, P, G, ws, splits, st);
+    return tc::launch_wgrad<64, 4>(d, P, G, ws, splits, st);
+}

@@ -1,0 +1,534 @@
+// elementwise.cu — HBM-bound pointwise / pooling / layout kernels of the G+D step (all channel-last fp32).
+// Reference call sites are cited per entry point in include/b200gan.h.
+#include "common.cuh"
+
+namespace b200 {
+
+#define GRID_STRIDE(i, n) \
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+__global__ void relu_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4, const float* xt,
+                                float* yt, int tail) {
+    GRID_STRIDE(i, n4) {
+        float4 v = x[i];
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        y[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < tail) yt[threadIdx.x] = fmaxf(xt[threadIdx.x], 0.f);
+}
+
+__global__ void relu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float4* __restrict__ dx,
+                                int64_t n4, const float* dyt, const float* yt, float* dxt, int tail) {
+    GRID_STRIDE(i, n4) {
+        float4 g = dy[i], v = y[i];
+        g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f; g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
+        dx[i] = g;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < tail) dxt[threadIdx.x] = yt[threadIdx.x] > 0.f ? dyt[threadIdx.x] : 0.f;
+}
+
+__global__ void add_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ o,
+                           int64_t n4, const float* at, const float* bt, float* ot, int tail) {
+    GRID_STRIDE(i, n4) {
+        float4 u = a[i], v = b[i];
+        o[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < tail) ot[threadIdx.x] = at[threadIdx.x] + bt[threadIdx.x];
+}
+
+// y[n,qy,qx,c] = scale * sum_{dy,dx<f} x[n,qy*f+dy,qx*f+dx,c]
+__global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int f,
+                                float scale) {
+    int Ho = H / f, Wo = W / f;
+    int64_t total = (int64_t)N * Ho * Wo * C;
+    GRID_STRIDE(t, total) {
+        int c = (int)(t % C);
+        int qx = (int)((t / C) % Wo);
+        int qy = (int)((t / ((int64_t)C * Wo)) % Ho);
+        int n = (int)(t / ((int64_t)C * Wo * Ho));
+        const float* p = x + (((int64_t)n * H + (int64_t)qy * f) * W + (int64_t)qx * f) * C + c;
+        float acc = 0.f;
+        for (int dy = 0; dy < f; ++dy)
+            for (int dx = 0; dx < f; ++dx) acc += p[((int64_t)dy * W + dx) * C];
+        y[t] = acc * scale;
+    }
+}
+
+__global__ void unpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int f,
+                                  float scale) {
+    int Ho = H * f, Wo = W * f;
+    int64_t total = (int64_t)N * Ho * Wo * C;
+    GRID_STRIDE(t, total) {
+        int c = (int)(t % C);
+        int ox = (int)((t / C) % Wo);
+        int oy = (int)((t / ((int64_t)C * Wo)) % Ho);
+        int n = (int)(t / ((int64_t)C * Wo * Ho));
+        y[t] = scale * x[(((int64_t)n * H + oy / f) * W + ox / f) * C + c];
+    }
+}
+
+__global__ void concat_fwd_kernel(const float* __restrict__ a, int Ca, int a_div, const float* __restrict__ b, int Cb,
+                                  int b_div, float* __restrict__ out, int64_t rows) {
+    int Ct = Ca + Cb;
+    int64_t total = rows * Ct;
+    GRID_STRIDE(t, total) {
+        int c = (int)(t % Ct);
+        int64_t r = t / Ct;
+        out[t] = c < Ca ? a[(r / a_div) * Ca + c] : b[(r / b_div) * Cb + (c - Ca)];
+    }
+}
+
+// adjoint of concat: da[ra][c] = sum_{r in [ra*a_div, (ra+1)*a_div)} dout[r][c] (ascending r), same for b
+__global__ void concat_bwd_kernel(const float* __restrict__ dout, int Ca, int a_div, float* __restrict__ da, int Cb,
+                                  int b_div, float* __restrict__ db, int64_t rows) {
+    int Ct = Ca + Cb;
+    int64_t na = da ? (rows / a_div) * Ca : 0;
+    int64_t nb = db ? (rows / b_div) * Cb : 0;
+    GRID_STRIDE(t, na + nb) {
+        if (t < na) {
+            int c = (int)(t % Ca);
+            int64_t r0 = (t / Ca) * a_div;
+            float acc = 0.f;
+            for (int k = 0; k < a_div; ++k) acc += dout[(r0 + k) * Ct + c];
+            da[t] = acc;
+        } else {
+            int64_t u = t - na;
+            int c = (int)(u % Cb);
+            int64_t r0 = (u / Cb) * b_div;
+            float acc = 0.f;
+            for (int k = 0; k < b_div; ++k) acc += dout[(r0 + k) * Ct + Ca + c];
+            db[u] = acc;
+        }
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int32_t* __restrict__ idx,
+                                   float* __restrict__ out, int rows, int D) {
+    int64_t total = (int64_t)rows * D;
+    GRID_STRIDE(t, total) {
+        int c = (int)(t % D);
+        int r = (int)(t / D);
+        out[t] = table[(int64_t)idx[r] * D + c];
+    }
+}
+
+__global__ void scatter_rows_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx,
+                                    float* __restrict__ dtable, int rows, int D, int num_classes) {
+    int64_t total = (int64_t)num_classes * D;
+    GRID_STRIDE(t, total) {
+        int c = (int)(t % D);
+        int k = (int)(t / D);
+        float acc = 0.f;
+        for (int r = 0; r < rows; ++r)
+            if (idx[r] == k) acc += dout[(int64_t)r * D + c];
+        dtable[t] = acc;
+    }
+}
+
+__global__ void permute_rows_kernel(const float4* __restrict__ x, const int32_t* __restrict__ src_row,
+                                    float4* __restrict__ out, int rows, int rowlen4) {
+    int64_t total = (int64_t)rows * rowlen4;
+    GRID_STRIDE(t, total) {
+        int c = (int)(t % rowlen4);
+        int r = (int)(t / rowlen4);
+        int s = src_row[r];
+        out[t] = s >= 0 ? x[(int64_t)s * rowlen4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+__global__ void mask_outer_fwd_kernel(const float* __restrict__ v, const float* __restrict__ mask,
+                                      float* __restrict__ out, int O, int H, int W, int C) {
+    int Hp = H + 2, Wp = W + 2;
+    int64_t total = (int64_t)O * Hp * Wp * C;
+    GRID_STRIDE(t, total) {
+        int c = (int)(t % C);
+        int x = (int)((t / C) % Wp);
+        int y = (int)((t / ((int64_t)C * Wp)) % Hp);
+        int o = (int)(t / ((int64_t)C * Wp * Hp));
+        float r = 0.f;
+        if (y >= 1 && y <= H && x >= 1 && x <= W) r = mask[((int64_t)o * H + (y - 1)) * W + (x - 1)] * v[(int64_t)o * C + c];
+        out[t] = r;
+    }
+}
+
+// dv[o,c] = sum_{y,x} mask[o,y,x] * dout[o,y+1,x+1,c]; one block per (o, 32-channel group), fixed-order tree
+__global__ void mask_outer_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ mask,
+                                      float* __restrict__ dv, int O, int H, int W, int C) {
+    __shared__ float red[8][32];
+    int o = blockIdx.x;
+    int c = blockIdx.y * 32 + threadIdx.x;
+    int Wp = W + 2;
+    float acc = 0.f;
+    if (c < C) {
+        for (int p = threadIdx.y; p < H * W; p += 8) {
+            int y = p / W, x = p % W;
+            float m = mask[((int64_t)o * H + y) * W + x];
+            if (m != 0.f) acc += m * dout[(((int64_t)o * (H + 2) + (y + 1)) * Wp + (x + 1)) * C + c];
+        }
+    }
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float s = 0.f;
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        dv[(int64_t)o * C + c] = s;
+    }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void lstm_gates_fwd_kernel(const float* __restrict__ pre_x, const float* __restrict__ pre_h,
+                                      const float* __restrict__ c_prev, float* __restrict__ gates,
+                                      float* __restrict__ c_out, float* __restrict__ h_out, int64_t rows, int hid) {
+    int64_t total = rows * hid;
+    GRID_STRIDE(t, total) {
+        int k = (int)(t % hid);
+        int64_t r = t / hid;
+        int64_t base = r * 4 * hid + k;
+        float pi = pre_x[base], pf = pre_x[base + hid], po = pre_x[base + 2 * hid], pg = pre_x[base + 3 * hid];
+        if (pre_h) { pi += pre_h[base]; pf += pre_h[base + hid]; po += pre_h[base + 2 * hid]; pg += pre_h[base + 3 * hid]; }
+        float i = sigmoidf_(pi), f = sigmoidf_(pf), o = sigmoidf_(po), g = tanhf(pg);
+        float cp = c_prev ? c_prev[t] : 0.f;
+        float cn = f * cp + i * g;
+        gates[base] = i; gates[base + hid] = f; gates[base + 2 * hid] = o; gates[base + 3 * hid] = g;
+        c_out[t] = cn;
+        h_out[t] = o * tanhf(cn);
+    }
+}
+
+__global__ void lstm_gates_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dc_next,
+                                      const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                      const float* __restrict__ c_out, float* __restrict__ dpre,
+                                      float* __restrict__ dc_prev, int64_t rows, int hid) {
+    int64_t total = rows * hid;
+    GRID_STRIDE(t, total) {
+        int k = (int)(t % hid);
+        int64_t r = t / hid;
+        int64_t base = r * 4 * hid + k;
+        float i = gates[base], f = gates[base + hid], o = gates[base + 2 * hid], g = gates[base + 3 * hid];
+        float tc = tanhf(c_out[t]);
+        float dhv = dh[t];
+        float dc = (dc_next ? dc_next[t] : 0.f) + dhv * o * (1.f - tc * tc);
+        float cp = c_prev ? c_prev[t] : 0.f;
+        dpre[base] = dc * g * i * (1.f - i);
+        dpre[base + hid] = dc * cp * f * (1.f - f);
+        dpre[base + 2 * hid] = dhv * tc * o * (1.f - o);
+        dpre[base + 3 * hid] = dc * i * (1.f - g * g);
+        dc_prev[t] = dc * f;
+    }
+}
+
+__global__ void reparam_fwd_kernel(const float* mu, const float* logvar, const float* eps, float* z, int64_t n) {
+    GRID_STRIDE(t, n) { z[t] = eps[t] * expf(logvar[t] * 0.5f) + mu[t]; }
+}
+__global__ void reparam_bwd_kernel(const float* dz, const float* logvar, const float* eps, float* dmu, float* dlogvar,
+                                   int64_t n) {
+    GRID_STRIDE(t, n) {
+        float g = dz[t];
+        dmu[t] = g;
+        dlogvar[t] = g * eps[t] * 0.5f * expf(logvar[t] * 0.5f);
+    }
+}
+
+// column sums: stage 1 per-chunk partial (double), stage 2 fixed-order combine
+__global__ void colsum_partial_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t rows_per_chunk,
+                                      double* __restrict__ ws) {
+    __shared__ double red[8][33];
+    int c = blockIdx.y * 32 + threadIdx.x;
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
+    int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+    double acc = 0.0;
+    if (c < C)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += (double)x[r * C + c];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double s = 0.0;
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        ws[(int64_t)blockIdx.x * C + c] = s;
+    }
+}
+__global__ void colsum_final_kernel(const double* __restrict__ ws, int nchunks, int C, float* __restrict__ out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int k = 0; k < nchunks; ++k) s += ws[(int64_t)k * C + c];
+    out[c] = (float)s;
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ src, void* __restrict__ dst, int dst_bf16, int M, int Mpad,
+                                   int Th, int Tw, int C, int64_t ldw, int64_t s_m, int64_t s_ky, int64_t s_kx,
+                                   int64_t s_c, int ky0, int kx0, int kstep) {
+    int64_t total = (int64_t)Mpad * ldw;
+    int K = Th * Tw * C;
+    GRID_STRIDE(t, total) {
+        int64_t m = t / ldw;
+        int k = (int)(t % ldw);
+        float v = 0.f;
+        if (m < M && k < K) {
+            int c = k % C;
+            int tap = k / C;
+            int i = tap % Tw, j = tap / Tw;
+            v = src[m * s_m + (int64_t)(ky0 + kstep * j) * s_ky + (int64_t)(kx0 + kstep * i) * s_kx + (int64_t)c * s_c];
+        }
+        if (dst_bf16) {
+            // round-to-nearest-even fp32 -> bf16
+            uint32_t u = __float_as_uint(v);
+            uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+            if ((u & 0x7F800000u) == 0x7F800000u) r = u;  // inf / nan pass through
+            reinterpret_cast<uint16_t*>(dst)[t] = (uint16_t)(r >> 16);
+        } else {
+            reinterpret_cast<float*>(dst)[t] = v;
+        }
+    }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int64_t split_stride, int M, int Th, int Tw, int C,
+                                    float* __restrict__ dst, int64_t s_m, int64_t s_ty, int64_t s_tx, int64_t s_c,
+                                    const float* __restrict__ scale, int accumulate) {
+    int64_t K = (int64_t)Th * Tw * C;
+    int64_t total = (int64_t)M * K;
+    float alpha = scale ? *scale : 1.f;
+    GRID_STRIDE(t, total) {
+        int64_t m = t / K;
+        int k = (int)(t % K);
+        int c = k % C;
+        int tap = k / C;
+        int tx = tap % Tw, ty = tap / Tw;
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += ws[(int64_t)s * split_stride + t];
+        float* p = dst + m * s_m + (int64_t)ty * s_ty + (int64_t)tx * s_tx + (int64_t)c * s_c;
+        *p = accumulate ? (*p + alpha * acc) : alpha * acc;
+    }
+}
+
+// y[b][c][r] = x[b][r][c]  (batched R x C -> C x R transpose; NCHW <-> channel-last)
+__global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
+    __shared__ float tile[32][33];
+    const float* xb = x + (int64_t)blockIdx.z * R * C;
+    float* yb = y + (int64_t)blockIdx.z * R * C;
+    int c = blockIdx.x * 32 + threadIdx.x;
+    for (int k = threadIdx.y; k < 32; k += 8) {
+        int r = blockIdx.y * 32 + k;
+        if (r < R && c < C) tile[k][threadIdx.x] = xb[(int64_t)r * C + c];
+    }
+    __syncthreads();
+    int r2 = blockIdx.y * 32 + threadIdx.x;
+    for (int k = threadIdx.y; k < 32; k += 8) {
+        int c2 = blockIdx.x * 32 + k;
+        if (r2 < R && c2 < C) yb[(int64_t)c2 * R + r2] = tile[threadIdx.x][k];
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int b200_relu_fwd(const float* x, float* y, int64_t n, b200_stream_t stream) {
+    if (n == 0) return 0;
+    int64_t n4 = (aligned16(x) && aligned16(y)) ? n / 4 : 0;
+    int tail = (int)(n - n4 * 4);
+    B200_REQUIRE(tail < 256, "relu_fwd: unaligned large tensor");
+    relu_fwd_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const float4*)x, (float4*)y, n4,
+                                                                                   x + n4 * 4, y + n4 * 4, tail);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, b200_stream_t stream) {
+    if (n == 0) return 0;
+    int64_t n4 = (aligned16(dy) && aligned16(y) && aligned16(dx)) ? n / 4 : 0;
+    int tail = (int)(n - n4 * 4);
+    B200_REQUIRE(tail < 256, "relu_bwd: unaligned large tensor");
+    relu_bwd_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>(
+        (const float4*)dy, (const float4*)y, (float4*)dx, n4, dy + n4 * 4, y + n4 * 4, dx + n4 * 4, tail);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_add(const float* a, const float* b, float* out, int64_t n, b200_stream_t stream) {
+    if (n == 0) return 0;
+    int64_t n4 = (aligned16(a) && aligned16(b) && aligned16(out)) ? n / 4 : 0;
+    int tail = (int)(n - n4 * 4);
+    B200_REQUIRE(tail < 256, "add: unaligned large tensor");
+    add_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const float4*)a, (const float4*)b,
+                                                                              (float4*)out, n4, a + n4 * 4, b + n4 * 4,
+                                                                              out + n4 * 4, tail);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_pool_fwd(const float* x, float* y, int N, int H, int W, int C, int f, float scale,
+                             b200_stream_t stream) {
+    B200_REQUIRE(f >= 1 && H % f == 0 && W % f == 0, "pool_fwd: H=%d W=%d not divisible by f=%d", H, W, f);
+    int64_t total = (int64_t)N * (H / f) * (W / f) * C;
+    if (total == 0) return 0;
+    pool_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_unpool_fwd(const float* x, float* y, int N, int H, int W, int C, int f, float scale,
+                               b200_stream_t stream) {
+    int64_t total = (int64_t)N * H * f * W * f * C;
+    if (total == 0) return 0;
+    unpool_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_concat_fwd(const float* a, int Ca, int a_div, const float* b, int Cb, int b_div, float* out,
+                               int64_t rows, b200_stream_t stream) {
+    if (rows == 0) return 0;
+    concat_fwd_kernel<<<grid_for(rows * (Ca + Cb), 256), 256, 0, as_stream(stream)>>>(a, Ca, a_div, b, Cb, b_div, out,
+                                                                                      rows);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_concat_bwd(const float* dout, int Ca, int a_div, float* da, int Cb, int b_div, float* db,
+                               int64_t rows, b200_stream_t stream) {
+    if (rows == 0) return 0;
+    B200_REQUIRE(rows % a_div == 0 && rows % b_div == 0, "concat_bwd: rows not divisible by broadcast factors");
+    concat_bwd_kernel<<<grid_for(rows * (Ca + Cb), 256), 256, 0, as_stream(stream)>>>(dout, Ca, a_div, da, Cb, b_div,
+                                                                                      db, rows);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_gather_rows(const float* table, const int32_t* idx, float* out, int rows, int D,
+                                b200_stream_t stream) {
+    if (rows == 0) return 0;
+    gather_rows_kernel<<<grid_for((int64_t)rows * D, 256), 256, 0, as_stream(stream)>>>(table, idx, out, rows, D);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_scatter_rows(const float* dout, const int32_t* idx, float* dtable, int rows, int D,
+                                 int num_classes, b200_stream_t stream) {
+    scatter_rows_kernel<<<grid_for((int64_t)num_classes * D, 128), 128, 0, as_stream(stream)>>>(dout, idx, dtable, rows,
+                                                                                                D, num_classes);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_permute_rows(const float* x, const int32_t* src_row, float* out, int rows, int rowlen,
+                                 b200_stream_t stream) {
+    if (rows == 0) return 0;
+    B200_REQUIRE(rowlen % 4 == 0 && aligned16(x) && aligned16(out), "permute_rows: rowlen %% 4 != 0 or unaligned");
+    permute_rows_kernel<<<grid_for((int64_t)rows * (rowlen / 4), 256), 256, 0, as_stream(stream)>>>(
+        (const float4*)x, src_row, (float4*)out, rows, rowlen / 4);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_mask_outer_fwd(const float* v, const float* mask, float* out, int O, int H, int W, int C,
+                                   b200_stream_t stream) {
+    if (O == 0) return 0;
+    int64_t total = (int64_t)O * (H + 2) * (W + 2) * C;
+    mask_outer_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(v, mask, out, O, H, W, C);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_mask_outer_bwd(const float* dout, const float* mask, float* dv, int O, int H, int W, int C,
+                                   b200_stream_t stream) {
+    if (O == 0) return 0;
+    dim3 grid(O, (C + 31) / 32), block(32, 8);
+    mask_outer_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(dout, mask, dv, O, H, W, C);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_lstm_gates_fwd(const float* pre_x, const float* pre_h, const float* c_prev, float* gates,
+                                   float* c_out, float* h_out, int64_t rows, int hid, b200_stream_t stream) {
+    if (rows == 0) return 0;
+    lstm_gates_fwd_kernel<<<grid_for(rows * hid, 256), 256, 0, as_stream(stream)>>>(pre_x, pre_h, c_prev, gates, c_out,
+                                                                                    h_out, rows, hid);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_lstm_gates_bwd(const float* dh, const float* dc_next, const float* gates, const float* c_prev,
+                                   const float* c_out, float* dpre, float* dc_prev, int64_t rows, int hid,
+                                   b200_stream_t stream) {
+    if (rows == 0) return 0;
+    lstm_gates_bwd_kernel<<<grid_for(rows * hid, 256), 256, 0, as_stream(stream)>>>(dh, dc_next, gates, c_prev, c_out,
+                                                                                    dpre, dc_prev, rows, hid);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, int64_t n,
+                                b200_stream_t stream) {
+    if (n == 0) return 0;
+    reparam_fwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(mu, logvar, eps, z, n);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu_add,
+                                float* dlogvar_add, int64_t n, b200_stream_t stream) {
+    if (n == 0) return 0;
+    reparam_bwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(dz, logvar, eps, dmu_add, dlogvar_add, n);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_bn_chunks(int64_t rows, int C) {
+    int cblocks = (C + 31) / 32;
+    int64_t target = (int64_t)kNumSMs * 8 / cblocks;
+    if (target < 1) target = 1;
+    int64_t by_rows = (rows + 31) / 32;
+    int64_t n = by_rows < target ? by_rows : target;
+    if (n < 1) n = 1;
+    if (n > 1024) n = 1024;
+    return (int)n;
+}
+
+extern "C" int b200_colsum(const float* x, int64_t rows, int C, float* out, double* ws, b200_stream_t stream) {
+    int nchunks = b200_bn_chunks(rows, C);
+    int64_t rpc = (rows + nchunks - 1) / nchunks;
+    if (rpc < 1) rpc = 1;
+    dim3 grid(nchunks, (C + 31) / 32), block(32, 8);
+    colsum_partial_kernel<<<grid, block, 0, as_stream(stream)>>>(x, rows, C, rpc, ws);
+    B200_CHECK_LAUNCH();
+    colsum_final_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(ws, nchunks, C, out);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_pack_weight(const float* src, void* dst, int dst_bf16, int M, int Mpad, int Th, int Tw, int C,
+                                int64_t ldw, int64_t s_m, int64_t s_ky, int64_t s_kx, int64_t s_c, int ky0, int kx0,
+                                int kstep, b200_stream_t stream) {
+    B200_REQUIRE(ldw >= (int64_t)Th * Tw * C && Mpad >= M, "pack_weight: ldw/Mpad too small");
+    int64_t total = (int64_t)Mpad * ldw;
+    if (total == 0) return 0;
+    pack_weight_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(src, dst, dst_bf16, M, Mpad, Th, Tw, C, ldw,
+                                                                            s_m, s_ky, s_kx, s_c, ky0, kx0, kstep);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_wgrad_reduce(const float* ws, int splits, int64_t split_stride, int M, int Th, int Tw, int C,
+                                 float* dst, int64_t s_m, int64_t s_ty, int64_t s_tx, int64_t s_c, const float* scale,
+                                 int accumulate, b200_stream_t stream) {
+    int64_t total = (int64_t)M * Th * Tw * C;
+    if (total == 0) return 0;
+    wgrad_reduce_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(ws, splits, split_stride, M, Th, Tw, C, dst,
+                                                                             s_m, s_ty, s_tx, s_c, scale, accumulate);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_transpose(const float* x, float* y, int B, int R, int C, b200_stream_t stream) {
+    if (B == 0 || R == 0 || C == 0) return 0;
+    B200_REQUIRE(B < 65536, "transpose: batch too large");
+    dim3 grid((C + 31) / 32, (R + 31) / 32, B), block(32, 8);
+    B200_REQUIRE(grid.y < 65536, "transpose: R too large");
+    transpose_kernel<<<grid, block, 0, as_stream(stream)>>>(x, y, R, C);
+    B200_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,315 @@
+// norm.cu — batch-norm statistics (K6) and the fused normalise/modulate/ReLU/residual apply (K7), fwd + bwd.
+// Replaces nn.BatchNorm1d/2d (F.batch_norm training semantics: biased var for normalisation, unbiased for
+// running_var, momentum 0.1), ConditionalBatchNorm2d (generator_obj_att.py:31-44) and SPADE's modulation
+// (models/spade/networks/normalization.py:94-108).  x is (rows, C) channel-last; all reductions are two-stage,
+// fixed order, accumulated in fp64 (deterministic).
+#include "common.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------------------
+// statistics
+// ---------------------------------------------------------------------------------------------------------
+__global__ void bn_stats_partial_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t rows_per_chunk,
+                                        double* __restrict__ ws) {
+    __shared__ double r1[8][33], r2[8][33];
+    int c = blockIdx.y * 32 + threadIdx.x;
+    int64_t a = (int64_t)blockIdx.x * rows_per_chunk;
+    int64_t b = a + rows_per_chunk < rows ? a + rows_per_chunk : rows;
+    double s1 = 0.0, s2 = 0.0;
+    if (c < C) {
+        for (int64_t r = a + threadIdx.y; r < b; r += 8) {
+            double v = (double)x[r * C + c];
+            s1 += v;
+            s2 += v * v;
+        }
+    }
+    r1[threadIdx.y][threadIdx.x] = s1;
+    r2[threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int k = 0; k < 8; ++k) { t1 += r1[k][threadIdx.x]; t2 += r2[k][threadIdx.x]; }
+        ws[((int64_t)blockIdx.x * C + c) * 2 + 0] = t1;
+        ws[((int64_t)blockIdx.x * C + c) * 2 + 1] = t2;
+    }
+}
+
+__global__ void bn_stats_final_kernel(const double* __restrict__ ws, int nchunks, int C, int64_t rows, float* mean,
+                                      float* var, float* running_mean, float* running_var, float momentum) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < nchunks; ++k) { s1 += ws[((int64_t)k * C + c) * 2]; s2 += ws[((int64_t)k * C + c) * 2 + 1]; }
+    double m = s1 / (double)rows;
+    double v = s2 / (double)rows - m * m;
+    if (v < 0.0) v = 0.0;
+    mean[c] = (float)m;
+    var[c] = (float)v;
+    if (running_mean) {
+        double unb = rows > 1 ? v * (double)rows / (double)(rows - 1) : v;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward apply
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void norm_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t rows, int C,
+                                const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const int32_t* __restrict__ idx, int rows_per_seg, const float4* __restrict__ residual,
+                                int relu) {
+    int C4 = C >> 2;
+    int64_t total = rows * C4;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(t % C4) << 2;
+        int64_t r = t / C4;
+        float4 v = x[t];
+        float4 m = *reinterpret_cast<const float4*>(mean + c);
+        float4 vv = *reinterpret_cast<const float4*>(var + c);
+        float4 o;
+        o.x = (v.x - m.x) * (1.f / sqrtf(vv.x + eps));
+        o.y = (v.y - m.y) * (1.f / sqrtf(vv.y + eps));
+        o.z = (v.z - m.z) * (1.f / sqrtf(vv.z + eps));
+        o.w = (v.w - m.w) * (1.f / sqrtf(vv.w + eps));
+        if (MODE == B200_NORM_AFFINE) {
+            float4 g = *reinterpret_cast<const float4*>(gamma + c);
+            float4 b = *reinterpret_cast<const float4*>(beta + c);
+            o.x = o.x * g.x + b.x; o.y = o.y * g.y + b.y; o.z = o.z * g.z + b.z; o.w = o.w * g.w + b.w;
+        } else if (MODE == B200_NORM_CBN) {
+            const float* row = gamma + (int64_t)idx[r / rows_per_seg] * 2 * C;
+            float4 g = *reinterpret_cast<const float4*>(row + c);
+            float4 b = *reinterpret_cast<const float4*>(row + C + c);
+            o.x = g.x * o.x + b.x; o.y = g.y * o.y + b.y; o.z = g.z * o.z + b.z; o.w = g.w * o.w + b.w;
+        } else if (MODE == B200_NORM_SPADE) {
+            const float* row = gamma + r * 2 * C;
+            float4 g = *reinterpret_cast<const float4*>(row + c);
+            float4 b = *reinterpret_cast<const float4*>(row + C + c);
+            o.x = o.x * (1.f + g.x) + b.x; o.y = o.y * (1.f + g.y) + b.y;
+            o.z = o.z * (1.f + g.z) + b.z; o.w = o.w * (1.f + g.w) + b.w;
+        }
+        if (residual) {
+            float4 q = residual[t];
+            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        y[t] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward stage 1: per-segment sums
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void norm_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                       const float* __restrict__ y, int64_t rows, int C, const float* __restrict__ mean,
+                                       const float* __restrict__ var, float eps, const float* __restrict__ gamma,
+                                       int rows_per_seg, int relu, double* __restrict__ seg_sums) {
+    __shared__ double r1[8][33], r2[8][33];
+    int c = blockIdx.y * 32 + threadIdx.x;
+    int64_t a = (int64_t)blockIdx.x * rows_per_seg;
+    int64_t b = a + rows_per_seg < rows ? a + rows_per_seg : rows;
+    double s1 = 0.0, s2 = 0.0;
+    if (c < C) {
+        float m = mean[c], rstd = 1.f / sqrtf(var[c] + eps);
+        for (int64_t r = a + threadIdx.y; r < b; r += 8) {
+            float g = dy[r * C + c];
+            if (relu && !(y[r * C + c] > 0.f)) g = 0.f;
+            float xh = (x[r * C + c] - m) * rstd;
+            if (MODE == B200_NORM_SPADE) g *= 1.f + gamma[r * 2 * C + c];
+            s1 += (double)g;
+            s2 += (double)g * (double)xh;
+        }
+    }
+    r1[threadIdx.y][threadIdx.x] = s1;
+    r2[threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int k = 0; k < 8; ++k) { t1 += r1[k][threadIdx.x]; t2 += r2[k][threadIdx.x]; }
+        seg_sums[((int64_t)blockIdx.x * C + c) * 2 + 0] = t1;
+        seg_sums[((int64_t)blockIdx.x * C + c) * 2 + 1] = t2;
+    }
+}
+
+// stage 2: s[c] = (sum dxhat, sum dxhat*xhat); parameter gradients
+__global__ void norm_bwd_finalize_kernel(const double* __restrict__ seg, int nseg, int C, int mode,
+                                         const float* __restrict__ gamma, const int32_t* __restrict__ idx, float* s,
+                                         float* dgamma, float* dbeta) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    if (mode == B200_NORM_CBN) {
+        for (int k = 0; k < nseg; ++k) {
+            double g = (double)gamma[(int64_t)idx[k] * 2 * C + c];
+            s1 += g * seg[((int64_t)k * C + c) * 2];
+            s2 += g * seg[((int64_t)k * C + c) * 2 + 1];
+        }
+    } else {
+        for (int k = 0; k < nseg; ++k) { s1 += seg[((int64_t)k * C + c) * 2]; s2 += seg[((int64_t)k * C + c) * 2 + 1]; }
+        if (mode == B200_NORM_AFFINE) {
+            if (dbeta) dbeta[c] = (float)s1;
+            if (dgamma) dgamma[c] = (float)s2;
+            double g = (double)gamma[c];
+            s1 *= g;
+            s2 *= g;
+        }
+    }
+    s[c * 2] = (float)s1;
+    s[c * 2 + 1] = (float)s2;
+}
+
+// CBN embedding gradient: dtable[k][c] = sum_{o: idx[o]==k} sum(dyr*xhat); dtable[k][C+c] = sum_{o} sum(dyr)
+__global__ void cbn_dtable_kernel(const double* __restrict__ seg, int nseg, int C, const int32_t* __restrict__ idx,
+                                  int num_classes, float* __restrict__ dtable) {
+    int64_t total = (int64_t)num_classes * C;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(t % C);
+        int k = (int)(t / C);
+        double a = 0.0, b = 0.0;
+        for (int o = 0; o < nseg; ++o)
+            if (idx[o] == k) { a += seg[((int64_t)o * C + c) * 2 + 1]; b += seg[((int64_t)o * C + c) * 2]; }
+        dtable[(int64_t)k * 2 * C + c] = (float)a;
+        dtable[(int64_t)k * 2 * C + C + c] = (float)b;
+    }
+}
+
+// stage 3
+template <int MODE>
+__global__ void norm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                      const float* __restrict__ y, float* __restrict__ dx, int64_t rows, int C,
+                                      const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                      const float* __restrict__ gamma, const int32_t* __restrict__ idx,
+                                      int rows_per_seg, int relu, const float* __restrict__ s, float* __restrict__ dgb) {
+    int64_t total = rows * C;
+    float inv_rows = 1.f / (float)rows;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(t % C);
+        int64_t r = t / C;
+        float g = dy[t];
+        if (relu && !(y[t] > 0.f)) g = 0.f;
+        float rstd = 1.f / sqrtf(var[c] + eps);
+        float xh = (x[t] - mean[c]) * rstd;
+        float dxh = g;
+        if (MODE == B200_NORM_AFFINE) dxh = g * gamma[c];
+        else if (MODE == B200_NORM_CBN) dxh = g * gamma[(int64_t)idx[r / rows_per_seg] * 2 * C + c];
+        else if (MODE == B200_NORM_SPADE) {
+            dxh = g * (1.f + gamma[r * 2 * C + c]);
+            dgb[r * 2 * C + c] = g * xh;
+            dgb[r * 2 * C + C + c] = g;
+        }
+        dx[t] = rstd * (dxh - s[c * 2] * inv_rows - xh * s[c * 2 + 1] * inv_rows);
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_bn_stats(const float* x, int64_t rows, int C, float* mean, float* var, float* running_mean,
+                             float* running_var, float momentum, double* ws, b200_stream_t stream) {
+    B200_REQUIRE(rows > 0 && C > 0, "bn_stats: empty input");
+    int nchunks = b200_bn_chunks(rows, C);
+    int64_t rpc = (rows + nchunks - 1) / nchunks;
+    dim3 grid(nchunks, (C + 31) / 32), block(32, 8);
+    bn_stats_partial_kernel<<<grid, block, 0, as_stream(stream)>>>(x, rows, C, rpc, ws);
+    B200_CHECK_LAUNCH();
+    bn_stats_final_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(ws, nchunks, C, rows, mean, var, running_mean,
+                                                                          running_var, momentum);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_norm_fwd(const float* x, float* y, int64_t rows, int C, const float* mean, const float* var,
+                             float eps, int mode, const float* gamma, const float* beta, const int32_t* idx,
+                             int rows_per_seg, const float* residual, int relu, b200_stream_t stream) {
+    B200_REQUIRE(C % 4 == 0, "norm_fwd: C=%d must be a multiple of 4", C);
+    if (rows == 0) return 0;
+    int64_t total = rows * (C / 4);
+    int g = grid_for(total, 256);
+    cudaStream_t st = as_stream(stream);
+    const float4* x4 = (const float4*)x;
+    float4* y4 = (float4*)y;
+    const float4* r4 = (const float4*)residual;
+    if (rows_per_seg < 1) rows_per_seg = 1;
+    switch (mode) {
+        case B200_NORM_PLAIN:
+            norm_fwd_kernel<B200_NORM_PLAIN><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu);
+            break;
+        case B200_NORM_AFFINE:
+            norm_fwd_kernel<B200_NORM_AFFINE><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu);
+            break;
+        case B200_NORM_CBN:
+            norm_fwd_kernel<B200_NORM_CBN><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu);
+            break;
+        case B200_NORM_SPADE:
+            norm_fwd_kernel<B200_NORM_SPADE><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu);
+            break;
+        default:
+            return set_error("norm_fwd: bad mode %d", mode);
+    }
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_norm_bwd_reduce(const float* dy, const float* x, const float* y, int64_t rows, int C,
+                                    const float* mean, const float* var, float eps, int mode, const float* gamma,
+                                    const int32_t* idx, int rows_per_seg, int relu, double* seg_sums,
+                                    b200_stream_t stream) {
+    (void)idx;
+    B200_REQUIRE(rows > 0 && rows_per_seg > 0, "norm_bwd_reduce: empty input");
+    int nseg = (int)((rows + rows_per_seg - 1) / rows_per_seg);
+    dim3 grid(nseg, (C + 31) / 32), block(32, 8);
+    cudaStream_t st = as_stream(stream);
+    if (mode == B200_NORM_SPADE)
+        norm_bwd_reduce_kernel<B200_NORM_SPADE><<<grid, block, 0, st>>>(dy, x, y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums);
+    else
+        norm_bwd_reduce_kernel<B200_NORM_PLAIN><<<grid, block, 0, st>>>(dy, x, y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, int mode, const float* gamma,
+                                      const int32_t* idx, int num_classes, float* s, float* dgamma, float* dbeta,
+                                      float* dtable, b200_stream_t stream) {
+    cudaStream_t st = as_stream(stream);
+    norm_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(seg_sums, nseg, C, mode, gamma, idx, s, dgamma, dbeta);
+    B200_CHECK_LAUNCH();
+    if (mode == B200_NORM_CBN && dtable) {
+        cbn_dtable_kernel<<<grid_for((int64_t)num_classes * C, 128), 128, 0, st>>>(seg_sums, nseg, C, idx, num_classes, dtable);
+        B200_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+extern "C" int b200_norm_bwd_apply(const float* dy, const float* x, const float* y, float* dx, int64_t rows, int C,
+                                   const float* mean, const float* var, float eps, int mode, const float* gamma,
+                                   const int32_t* idx, int rows_per_seg, int relu, const float* s, float* dgb,
+                                   b200_stream_t stream) {
+    if (rows == 0) return 0;
+    int g = grid_for(rows * C, 256);
+    cudaStream_t st = as_stream(stream);
+    if (rows_per_seg < 1) rows_per_seg = 1;
+    switch (mode) {
+        case B200_NORM_PLAIN:
+            norm_bwd_apply_kernel<B200_NORM_PLAIN><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb);
+            break;
+        case B200_NORM_AFFINE:
+            norm_bwd_apply_kernel<B200_NORM_AFFINE><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb);
+            break;
+        case B200_NORM_CBN:
+            norm_bwd_apply_kernel<B200_NORM_CBN><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb);
+            break;
+        case B200_NORM_SPADE:
+            B200_REQUIRE(dgb != nullptr, "norm_bwd_apply: SPADE needs dgb");
+            norm_bwd_apply_kernel<B200_NORM_SPADE><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb);
+            break;
+        default:
+            return set_error("norm_bwd_apply: bad mode %d", mode);
+    }
+    B200_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,163 @@
+// sn.cu — spectral normalisation (K5): one power iteration per forward call and the gradient through W/sigma.
+// Replaces torch.nn.utils.spectral_norm's pre-forward hook as installed by add_sn (discriminator.py:15-22):
+//   v <- normalize(W^T u, eps), u <- normalize(W v, eps)  (in place), sigma = u . (W v), weight = weight_orig / sigma.
+// W is the (h, w) row-major view of weight_orig.  All reductions are fixed order.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kSnRowChunks = 8;
+
+// partial[chunk][j] = sum_{i in chunk} W[i][j] * u[i]
+__global__ void sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u, int h, int w, int rows_per_chunk,
+                              float* __restrict__ partial) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= w) return;
+    int i0 = blockIdx.y * rows_per_chunk;
+    int i1 = i0 + rows_per_chunk < h ? i0 + rows_per_chunk : h;
+    float acc = 0.f;
+    for (int i = i0; i < i1; ++i) acc += W[(int64_t)i * w + j] * u[i];
+    partial[(int64_t)blockIdx.y * w + j] = acc;
+}
+
+__device__ float block_sum_1024(float v, float* red) {
+    // fixed-order block reduction (blockDim.x == 1024)
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float t = 0.f;
+    if (wid == 0) {
+        t = red[lane];
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// t = sum_chunks partial; v = t / max(||t||, eps)
+__global__ void sn_norm_v_kernel(const float* __restrict__ partial, int nchunks, int w, float eps, float* __restrict__ v) {
+    __shared__ float red[33];
+    float ss = 0.f;
+    for (int j = threadIdx.x; j < w; j += 1024) {
+        float t = 0.f;
+        for (int k = 0; k < nchunks; ++k) t += partial[(int64_t)k * w + j];
+        v[j] = t;  // unnormalised for now
+        ss += t * t;
+    }
+    float tot = block_sum_1024(ss, red);
+    float inv = 1.f / fmaxf(sqrtf(tot), eps);
+    for (int j = threadIdx.x; j < w; j += 1024) v[j] *= inv;
+}
+
+// wv[i] = sum_j W[i][j] v[j]; one warp per row
+__global__ void sn_wv_kernel(const float* __restrict__ W, const float* __restrict__ v, int h, int w,
+                             float* __restrict__ wv) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= h) return;
+    float acc = 0.f;
+    for (int j = lane; j < w; j += 32) acc += W[(int64_t)row * w + j] * v[j];
+    acc = warp_sum(acc);
+    if (lane == 0) wv[row] = acc;
+}
+
+// do_iter: u = wv / max(||wv||, eps); sigma = u . wv; out2 = [sigma, 1/sigma]
+__global__ void sn_norm_u_kernel(const float* __restrict__ wv, int h, float eps, int do_iter, float* __restrict__ u,
+                                 float* __restrict__ out2) {
+    __shared__ float red[33];
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < h; i += 1024) ss += wv[i] * wv[i];
+    float tot = block_sum_1024(ss, red);
+    float inv = 1.f / fmaxf(sqrtf(tot), eps);
+    float dot = 0.f;
+    for (int i = threadIdx.x; i < h; i += 1024) {
+        float un = do_iter ? wv[i] * inv : u[i];
+        if (do_iter) u[i] = un;
+        dot += un * wv[i];
+    }
+    float sigma = block_sum_1024(dot, red);
+    if (threadIdx.x == 0) {
+        out2[0] = sigma;
+        out2[1] = 1.f / sigma;
+    }
+}
+
+__global__ void sn_dot_partial_kernel(const float* __restrict__ g, const float* __restrict__ W, int64_t n,
+                                      double* __restrict__ part) {
+    __shared__ double red[8];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += (double)g[i] * (double)W[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += red[k];
+        part[1 + blockIdx.x] = s;
+    }
+}
+__global__ void sn_dot_final_kernel(double* part, int nblocks) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < nblocks; ++k) s += part[1 + k];
+        part[0] = s;
+    }
+}
+__global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* __restrict__ u,
+                                     const float* __restrict__ v, const float* __restrict__ sig2,
+                                     const double* __restrict__ part, float* __restrict__ dW, int h, int w,
+                                     int accumulate) {
+    int64_t n = (int64_t)h * w;
+    float inv = sig2[1];
+    float coef = (float)(part[0]) * inv * inv;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        int j = (int)(t % w);
+        int i = (int)(t / w);
+        float val = g[t] * inv - coef * u[i] * v[j];
+        dW[t] = accumulate ? dW[t] + val : val;
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_sn_power_iter(const float* W, int h, int w, float* u, float* v, int do_iter, float eps,
+                                  float* out2, float* ws, b200_stream_t stream) {
+    cudaStream_t st = as_stream(stream);
+    float* partial = ws;                       // kSnRowChunks * w
+    float* wv = ws + (int64_t)kSnRowChunks * w;  // h
+    if (do_iter) {
+        int nch = h < 64 ? 1 : kSnRowChunks;
+        int rpc = (h + nch - 1) / nch;
+        dim3 grid((w + 127) / 128, nch);
+        sn_wtu_kernel<<<grid, 128, 0, st>>>(W, u, h, w, rpc, partial);
+        B200_CHECK_LAUNCH();
+        sn_norm_v_kernel<<<1, 1024, 0, st>>>(partial, nch, w, eps, v);
+        B200_CHECK_LAUNCH();
+    }
+    sn_wv_kernel<<<(h + 7) / 8, 256, 0, st>>>(W, v, h, w, wv);
+    B200_CHECK_LAUNCH();
+    sn_norm_u_kernel<<<1, 1024, 0, st>>>(wv, h, eps, do_iter, u, out2);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_sn_grad(const float* g, const float* W, const float* u, const float* v, const float* sig2,
+                            float* dW, int h, int w, int accumulate, double* ws, b200_stream_t stream) {
+    cudaStream_t st = as_stream(stream);
+    int64_t n = (int64_t)h * w;
+    int nblocks = grid_for(n, 256, 4);
+    if (nblocks > 1023) nblocks = 1023;
+    sn_dot_partial_kernel<<<nblocks, 256, 0, st>>>(g, W, n, ws);
+    B200_CHECK_LAUNCH();
+    sn_dot_final_kernel<<<1, 32, 0, st>>>(ws, nblocks);
+    B200_CHECK_LAUNCH();
+    sn_grad_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(g, u, v, sig2, ws, dW, h, w, accumulate);
+    B200_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,140 @@
+"""Discriminators — module surface of the reference's models/discriminator.py on libb200gan kernels.
+
+add_sn, OptimizedBlock, ResidualBlock, ImageDiscriminator, ObjectDiscriminator, AttributeDiscriminator and
+AttributeDiscriminator128 keep the reference's names, constructor signatures, forward signatures / return values and
+state_dict keys (discriminator.py:15-278).  Inputs are NCHW images / crops; logits come back as plain fp32 tensors.
+"""
+import torch
+import torch.nn as nn
+
+from b200gan import ops
+from b200gan import nn as bnn
+from b200gan.nn import add_sn  # noqa: F401  (discriminator.py:15-22)
+
+
+class OptimizedBlock(nn.Module):
+    """discriminator.py:29-60: pool?(conv3(ReLU(conv3(x)))) + sc1x1(pool?(x)); x is the NCHW network input"""
+
+    def __init__(self, dim_in, dim_out, downsample=False):
+        super().__init__()
+        self.downsample = downsample
+        self.resi = nn.Sequential(
+            bnn.Conv2d(dim_in, dim_out, kernel_size=3, stride=1, padding=1, bias=True),
+            bnn.ReLU(inplace=True),
+            bnn.Conv2d(dim_out, dim_out, kernel_size=3, stride=1, padding=1, bias=True))
+        self.learnable_sc = (dim_in != dim_out) or downsample
+        if self.learnable_sc:
+            self.sc = bnn.Conv2d(dim_in, dim_out, kernel_size=1, padding=0, bias=True)
+
+    def forward(self, x):
+        h = self.resi[0](x, x_layout="nchw", relu=True)
+        h = self.resi[2](h)
+        s = x
+        if self.downsample:
+            h = ops.avg_pool2(h)
+            s = ops.pool_nchw(x, 2, 0.25)
+        return ops.add(h, self.sc(s, x_layout="nchw"))
+
+
+class ResidualBlock(nn.Module):
+    """discriminator.py:63-99.  resi[0] is an in-place ReLU evaluated before the shortcut, so BOTH branches consume
+    relu(x); avg-pool commutes with the sum of the two branches, so one pool serves both."""
+
+    def __init__(self, dim_in, dim_out, downsample=False):
+        super().__init__()
+        self.downsample = downsample
+        self.resi = nn.Sequential(
+            bnn.ReLU(inplace=True),
+            bnn.Conv2d(dim_in, dim_in, kernel_size=3, stride=1, padding=1, bias=True),
+            bnn.ReLU(inplace=True),
+            bnn.Conv2d(dim_in, dim_out, kernel_size=3, stride=1, padding=1, bias=True))
+        self.learnable_sc = (dim_in != dim_out) or downsample
+        if self.learnable_sc:
+            self.sc = bnn.Conv2d(dim_in, dim_out, kernel_size=1, padding=0, bias=True)
+
+    def forward(self, x):
+        r = ops.relu(x)
+        h = self.resi[1](r, relu=True)
+        h = self.resi[3](h)
+        s = self.sc(r) if self.learnable_sc else r
+        out = ops.add(h, s)
+        return ops.avg_pool2(out) if self.downsample else out
+
+
+def _trunk(main, relu_sum_input):
+    h = main(relu_sum_input)
+    h = ops.relu(h)
+    N, H, W, C = h.shape
+    return ops.pool(h, H, 1.0).view(N, C)     # in-place ReLU then sum over (H, W) (discriminator.py:224-226)
+
+
+class AttributeDiscriminator128(nn.Module):
+    """discriminator.py:102-141"""
+
+    def __init__(self, conv_dim=64, downsample_first=False, n_attribute=128):
+        super().__init__()
+        self.main = nn.Sequential(
+            OptimizedBlock(3, conv_dim, downsample=downsample_first),
+            ResidualBlock(conv_dim, conv_dim * 2, downsample=True),
+            ResidualBlock(conv_dim * 2, conv_dim * 4, downsample=True),
+            ResidualBlock(conv_dim * 4, conv_dim * 8, downsample=True),
+            ResidualBlock(conv_dim * 8, conv_dim * 16, downsample=True),
+            ResidualBlock(conv_dim * 16, conv_dim * 16, downsample=True))
+        self.classifier_att = bnn.Linear(conv_dim * 16, n_attribute)
+
+    def forward(self, x):
+        return self.classifier_att(_trunk(self.main, x))
+
+
+class AttributeDiscriminator(nn.Module):
+    """discriminator.py:144-181"""
+
+    def __init__(self, conv_dim=64, downsample_first=False, n_attribute=128):
+        super().__init__()
+        self.main = nn.Sequential(
+            OptimizedBlock(3, conv_dim, downsample=downsample_first),
+            ResidualBlock(conv_dim, conv_dim * 2, downsample=True),
+            ResidualBlock(conv_dim * 2, conv_dim * 4, downsample=True),
+            ResidualBlock(conv_dim * 4, conv_dim * 8, downsample=True),
+            ResidualBlock(conv_dim * 8, conv_dim * 16, downsample=True))
+        self.classifier_att = bnn.Linear(conv_dim * 16, n_attribute)
+
+    def forward(self, x):
+        return self.classifier_att(_trunk(self.main, x))
+
+
+class ImageDiscriminator(nn.Module):
+    """discriminator.py:184-230"""
+
+    def __init__(self, conv_dim=64):
+        super().__init__()
+        self.ch = conv_dim
+        self.main = nn.Sequential(
+            OptimizedBlock(3, self.ch, downsample=True),
+            ResidualBlock(self.ch, self.ch * 2, downsample=True),
+            ResidualBlock(self.ch * 2, self.ch * 4, downsample=True),
+            ResidualBlock(self.ch * 4, self.ch * 8, downsample=True),
+            ResidualBlock(self.ch * 8, self.ch * 16, downsample=True))
+        self.classifier = bnn.Linear(self.ch * 16, 1, bias=False)
+
+    def forward(self, x):
+        return self.classifier(_trunk(self.main, x)).view(-1)
+
+
+class ObjectDiscriminator(nn.Module):
+    """discriminator.py:233-278"""
+
+    def __init__(self, conv_dim=64, n_class=0, downsample_first=False, n_attribute=128):
+        super().__init__()
+        self.main = nn.Sequential(
+            OptimizedBlock(3, conv_dim, downsample=downsample_first),
+            ResidualBlock(conv_dim, conv_dim * 2, downsample=True),
+            ResidualBlock(conv_dim * 2, conv_dim * 4, downsample=True),
+            ResidualBlock(conv_dim * 4, conv_dim * 8, downsample=True),
+            ResidualBlock(conv_dim * 8, conv_dim * 16, downsample=True))
+        self.classifier_src = bnn.Linear(conv_dim * 16, 1)
+        self.classifier_cls = bnn.Linear(conv_dim * 16, n_class)
+
+    def forward(self, x, y=None):
+        h = _trunk(self.main, x)
+        return self.classifier_src(h).view(-1), self.classifier_cls(h)

@@ -1,0 +1,208 @@
+/* b200gan.h — C ABI of libb200gan.so: the sm_100a kernels behind the G+D training step of the
+ * attribute-guided layout-to-image GAN (reference: ubc-vision/attribute-guided-image-generation-from-layout).
+ *
+ * Conventions
+ *  - every pointer is DEVICE memory owned by the caller (PyTorch), including workspaces;
+ *    the library never allocates, frees, synchronises or throws;
+ *  - every entry point is asynchronous on `stream` and returns 0, or a negative code with a
+ *    thread-local message retrievable through b200_last_error();
+ *  - activations are fp32; "rows x C" tensors are channel-last (N*H*W rows, C contiguous); conv
+ *    tensors carry explicit element strides so NCHW (3-channel images / crops, the layout at the
+ *    reference boundary) and NHWC (internal) are both addressed without a transpose;
+ *  - reductions are deterministic (fixed order, no floating point atomics).
+ *
+ * Each entry cites the reference interface it replaces (file:line under the reference root).
+ */
+#ifndef B200GAN_H
+#define B200GAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+const char* b200_last_error(void);
+int b200_version(void);
+/* number of kernel launches issued through this library by the calling process (for bench.py's gpu_launches) */
+int64_t b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Box crops — replaces models/bilinear.py:26-41,67-104,107-136 (crop_bbox_batch -> F.grid_sample,
+ * bilinear, zeros padding, align_corners=False) and its autograd backward.
+ * feats (N,C,H,W) NCHW; boxes (B,4) [x0,y0,x1,y1] in [0,1]; box_to_img (B) int32;
+ * wx (2*WW) = [linspace(1,0,WW) | linspace(0,1,WW)] and wy (2*HH) built on the HOST in fp32 exactly
+ * as bilinear.py:272-275 does; crops (B,C,HH,WW).
+ * b200_crop_taps exports the integer part (floor indices) for the bit-exact index contract.
+ * b200_crop_bwd is a deterministic two-pass gather: ws needs B*C*H*WW floats; img_box_start (N+1) int32
+ * are offsets into box_order (B) int32 = box ids grouped by image (ascending box id inside an image).
+ */
+int b200_crop_fwd(const float* feats, const float* boxes, const int32_t* box_to_img, const float* wx, const float* wy,
+                  float* crops, int N, int C, int H, int W, int B, int HH, int WW, b200_stream_t stream);
+int b200_crop_taps(const float* boxes, const float* wx, const float* wy, int32_t* ix0, int32_t* iy0, float* fx,
+                   float* fy, int H, int W, int B, int HH, int WW, b200_stream_t stream);
+int b200_crop_bwd(const float* dcrops, const float* boxes, const int32_t* img_box_start, const int32_t* box_order,
+                  const float* wx, const float* wy, float* dfeats, float* ws, int N, int C, int H, int W, int B,
+                  int HH, int WW, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Convolutions as gather-GEMMs — replace every nn.Conv2d / nn.ConvTranspose2d / nn.Linear forward,
+ * dgrad and wgrad on the path (generator_obj_att.py:93,374-393,432-435,474-483,528-544,582-586;
+ * generator_obj_att128.py:549-557; discriminator.py:36-44,70-79,128,168,218,252-253;
+ * models/spade/networks/normalization.py:88-92).
+ *
+ * One descriptor covers forward convs (any stride), stride-1 dgrad, the four output phases of a
+ * stride-2 dgrad / ConvTranspose forward, nearest-upsampled inputs and NCHW/NHWC addressing:
+ *   out[n, qy*out_sy+out_oy, qx*out_sx+out_ox, co] =
+ *       epilogue( sum_{ty<Th, tx<Tw, c<Cin} in[n, (qy*in_sy + ty*tap_sy + tap_oy) >> up, (qx*in_sx + ...) >> up, c]
+ *                                          * wmat[co, (ty*Tw+tx)*Cin + c] )
+ * taps outside [0,Hi)x[0,Wi) (logical, i.e. after upsampling) read zero; outputs outside [0,Ho)x[0,Wo) are dropped.
+ * epilogue(v) = relu?( v * (*scale if scale) + bias[co] ).
+ */
+typedef struct {
+    int B, Qh, Qw;                 /* output grid: rows M = B*Qh*Qw */
+    int Cin, Cout;
+    int Th, Tw;                    /* tap grid */
+    int in_sy, in_sx;              /* input step per output grid step */
+    int tap_sy, tap_sx;            /* input step per tap (may be negative) */
+    int tap_oy, tap_ox;            /* input offset of tap 0 */
+    int Hi, Wi;                    /* logical input extent (after nearest upsampling) */
+    int up_shift;                  /* physical input coordinate = logical >> up_shift */
+    int64_t in_sn, in_sh, in_sw, in_sc;     /* input element strides (physical) */
+    int out_sy, out_sx, out_oy, out_ox;    /* output coordinate = q*out_s + out_o */
+    int Ho, Wo;
+    int64_t out_sn, out_sh, out_sw, out_sc; /* output element strides */
+    int64_t ldw;                   /* row stride (elements) of wmat */
+    int relu;
+} b200_conv_desc;
+
+/* fp32 CUDA-core path (bit-tight parity mode). wmat fp32 [Cout][ldw]. */
+int b200_conv_gemm_f32(const b200_conv_desc* d, const float* in, const float* wmat, const float* bias,
+                       const float* scale, float* out, b200_stream_t stream);
+/* tcgen05 path: bf16 operands (activations converted on the fly), fp32 accumulate in TMEM.
+ * wmat bf16 [Cout_pad][ldw] with Cout_pad a multiple of the N tile (b200_conv_tc_ntile), ldw a multiple of 64,
+ * zero padded; requires Cin % 64 == 0 and in_sc == 1. */
+int b200_conv_gemm_tc(const b200_conv_desc* d, const float* in, const void* wmat_bf16, const float* bias,
+                      const float* scale, float* out, b200_stream_t stream);
+int b200_conv_tc_ntile(int Cout);
+
+/* Weight-gradient gather-GEMM:  R[m, (ty*Tw+tx)*Cg + c] = sum_{n,qy,qx} P[n,qy,qx,m] * G[n, gather(qy,qx,ty,tx), c]
+ * where `d` describes the gather of G exactly as above (d->Cin = Cg) and P is addressed with d's out_* fields
+ * (d->Cout = number of P channels m).  Split over the row range into `splits` partial results written to
+ * ws ([splits][Cout][Th*Tw*Cin] fp32); b200_wgrad_reduce sums them in fixed order into the parameter layout. */
+int b200_wgrad_gemm_f32(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+                        b200_stream_t stream);
+int b200_wgrad_gemm_tc(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+                       b200_stream_t stream);
+/* dst[m*s_m + ty*s_ty + tx*s_tx + c*s_c] (=|+=) alpha * sum_s ws[s*split_stride + m*Th*Tw*C + (ty*Tw+tx)*C + c];
+ * alpha = *scale or 1; split_stride = elements between consecutive partial results (rows_total*Th*Tw*C), so a row
+ * window of a taller partial buffer can be reduced by offsetting ws. */
+int b200_wgrad_reduce(const float* ws, int splits, int64_t split_stride, int M, int Th, int Tw, int C, float* dst,
+                      int64_t s_m, int64_t s_ty, int64_t s_tx, int64_t s_c, const float* scale, int accumulate,
+                      b200_stream_t stream);
+/* Weight packing from the parameter layout into GEMM matrices (fp32 or bf16), taps (ky0+kstep*j, kx0+kstep*i):
+ * dst[m*ldw + (j*Tw+i)*C + c] = src[m*s_m + (ky0+kstep*j)*s_ky + (kx0+kstep*i)*s_kx + c*s_c]; rows m in [M,Mpad) and
+ * columns beyond Th*Tw*C are zero filled. */
+int b200_pack_weight(const float* src, void* dst, int dst_bf16, int M, int Mpad, int Th, int Tw, int C, int64_t ldw,
+                     int64_t s_m, int64_t s_ky, int64_t s_kx, int64_t s_c, int ky0, int kx0, int kstep,
+                     b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Normalisation family — replaces nn.BatchNorm1d/2d, ConditionalBatchNorm2d (generator_obj_att.py:31-44),
+ * SPADE's param-free BN + modulation (normalization.py:94-108), fused with ReLU / residual add.
+ * x, y: (rows, C) channel-last fp32.
+ */
+/* batch statistics (biased var) + running-stat update (momentum, unbiased var) — F.batch_norm training semantics.
+ * ws: 2*C*nchunks doubles, nchunks = b200_bn_chunks(rows, C). running_* may be NULL. */
+int b200_bn_chunks(int64_t rows, int C);
+int b200_bn_stats(const float* x, int64_t rows, int C, float* mean, float* var, float* running_mean,
+                  float* running_var, float momentum, double* ws, b200_stream_t stream);
+enum { B200_NORM_PLAIN = 0, B200_NORM_AFFINE = 1, B200_NORM_CBN = 2, B200_NORM_SPADE = 3 };
+/* y = relu?( residual? + (x-mean)*rsqrt(var+eps) * g + b ):
+ *   PLAIN g=1,b=0 | AFFINE g=gamma[c], b=beta[c] | CBN g=table[idx[row/rows_per_seg]][c], b=table[..][C+c]
+ *   | SPADE g=1+gb[row][c], b=gb[row][C+c]  (gb = the fused gamma|beta conv output, (rows,2C)) */
+int b200_norm_fwd(const float* x, float* y, int64_t rows, int C, const float* mean, const float* var, float eps,
+                  int mode, const float* gamma, const float* beta, const int32_t* idx, int rows_per_seg,
+                  const float* residual, int relu, b200_stream_t stream);
+/* backward, stage 1: per-segment sums of (dyr*g, dyr*g*xhat) [and for CBN the raw (dyr, dyr*xhat)] where dyr = dy masked by
+ * y>0 when relu; seg_sums: (nseg, C, 2) doubles, nseg = rows / rows_per_seg.  For CBN pass rows_per_seg = H*W. */
+int b200_norm_bwd_reduce(const float* dy, const float* x, const float* y, int64_t rows, int C, const float* mean,
+                         const float* var, float eps, int mode, const float* gamma, const int32_t* idx,
+                         int rows_per_seg, int relu, double* seg_sums, b200_stream_t stream);
+/* stage 2: combine segments in fixed order -> s (C,2) floats = (sum dxhat, sum dxhat*xhat); parameter gradients:
+ * AFFINE: dgamma[c], dbeta[c]; CBN: dtable (num_classes, 2C) deterministic segmented sum by class (dtable is overwritten). */
+int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, int mode, const float* gamma, const int32_t* idx,
+                           int num_classes, float* s, float* dgamma, float* dbeta, float* dtable,
+                           b200_stream_t stream);
+/* stage 3: dx = rstd*(dxhat - s1/rows - xhat*s2/rows); SPADE additionally writes dgb (rows,2C) = (dyr*xhat | dyr). */
+int b200_norm_bwd_apply(const float* dy, const float* x, const float* y, float* dx, int64_t rows, int C,
+                        const float* mean, const float* var, float eps, int mode, const float* gamma,
+                        const int32_t* idx, int rows_per_seg, int relu, const float* s, float* dgb,
+                        b200_stream_t stream);
+/* eval-mode normalisation uses b200_norm_fwd with mean/var = running stats. */
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise / pooling / layout — replace nn.ReLU, residual adds, F.avg_pool2d (discriminator.py:25-26),
+ * F.interpolate nearest (normalization.py:100, generator_obj_att128.py:588), AdaptiveAvgPool2d, sum over (H,W)
+ * (discriminator.py:226,270; generator_obj_att.py:445), torch.cat, nn.Embedding, ConvLSTM gate math
+ * (generator_obj_att.py:102-112), the VAE reparameterisation (generator_obj_att.py:417-420) and the
+ * embedding (x) mask broadcast of LayoutEncoder (generator_obj_att.py:489-490).
+ */
+int b200_relu_fwd(const float* x, float* y, int64_t n, b200_stream_t stream);
+int b200_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, b200_stream_t stream);
+int b200_add(const float* a, const float* b, float* out, int64_t n, b200_stream_t stream);
+/* y[n, qy, qx, c] = scale * sum_{f x f block} x[n, qy*f+dy, qx*f+dx, c]  (x: (N,H,W,C), H%f==0) */
+int b200_pool_fwd(const float* x, float* y, int N, int H, int W, int C, int f, float scale, b200_stream_t stream);
+/* y[n, iy, ix, c] = scale * x[n, iy/f, ix/f, c]  (x: (N,H,W,C) -> y: (N,H*f,W*f,C)) */
+int b200_unpool_fwd(const float* x, float* y, int N, int H, int W, int C, int f, float scale, b200_stream_t stream);
+/* out[row] = [ a[row / a_div][0:Ca] | b[row / b_div][0:Cb] ] and its adjoint (sums over the broadcast rows, fixed order) */
+int b200_concat_fwd(const float* a, int Ca, int a_div, const float* b, int Cb, int b_div, float* out, int64_t rows,
+                    b200_stream_t stream);
+int b200_concat_bwd(const float* dout, int Ca, int a_div, float* da, int Cb, int b_div, float* db, int64_t rows,
+                    b200_stream_t stream);
+int b200_gather_rows(const float* table, const int32_t* idx, float* out, int rows, int D, b200_stream_t stream);
+/* dtable[k] = sum over rows with idx==k, ascending row order (deterministic); dtable (num_classes, D) overwritten */
+int b200_scatter_rows(const float* dout, const int32_t* idx, float* dtable, int rows, int D, int num_classes,
+                      b200_stream_t stream);
+/* out[o, y+1, x+1, c] = mask[o,y,x] * v[o,c], zero ring (1x1 conv with padding 1 of a rank-1 tensor) */
+int b200_mask_outer_fwd(const float* v, const float* mask, float* out, int O, int H, int W, int C,
+                        b200_stream_t stream);
+int b200_mask_outer_bwd(const float* dout, const float* mask, float* dv, int O, int H, int W, int C,
+                        b200_stream_t stream);
+/* ConvLSTM cell pointwise part; pre = pre_x + pre_h, channels ordered [i|f|o|g] each `hid` wide; rows = n*H*W.
+ * gates (rows,4*hid) receives the activated gates for the backward. pre_h / c_prev may be NULL (t = 0). */
+int b200_lstm_gates_fwd(const float* pre_x, const float* pre_h, const float* c_prev, float* gates, float* c_out,
+                        float* h_out, int64_t rows, int hid, b200_stream_t stream);
+/* dpre (rows,4*hid), dc_prev (rows,hid) from dh, dc_next (NULL = 0), saved gates, c_prev (NULL = 0), c_out */
+int b200_lstm_gates_bwd(const float* dh, const float* dc_next, const float* gates, const float* c_prev,
+                        const float* c_out, float* dpre, float* dc_prev, int64_t rows, int hid,
+                        b200_stream_t stream);
+int b200_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, int64_t n, b200_stream_t stream);
+int b200_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu_add, float* dlogvar_add,
+                     int64_t n, b200_stream_t stream);
+/* out[c] = sum_rows x[row][c] (bias gradients), deterministic; ws: C*b200_bn_chunks(rows,C) doubles */
+int b200_colsum(const float* x, int64_t rows, int C, float* out, double* ws, b200_stream_t stream);
+/* y[b][c][r] = x[b][r][c]: batched (R x C) transpose, i.e. NCHW <-> channel-last at module boundaries */
+int b200_transpose(const float* x, float* y, int B, int R, int C, b200_stream_t stream);
+/* row gather / scatter-overwrite for the time-major packing of ConvLSTM sequences: out[r] = x[src_row[r]] (rowlen floats) */
+int b200_permute_rows(const float* x, const int32_t* src_row, float* out, int rows, int rowlen, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spectral normalisation — replaces torch.nn.utils.spectral_norm's pre-forward hook installed by add_sn
+ * (discriminator.py:15-22): one power iteration in place on u (h) and v (w), sigma = u.(W v); W (h,w) row-major
+ * view of weight_orig.  out2 = [sigma, 1/sigma].  ws: 8*w + h floats.
+ * b200_sn_grad: dW = g*inv_sigma - (<g, W> * inv_sigma^2) * u v^T  (gradient through W/sigma with u, v constant),
+ * g = gradient w.r.t. the normalised weight, same layout as W.  ws: 1024 doubles.
+ */
+int b200_sn_power_iter(const float* W, int h, int w, float* u, float* v, int do_iter, float eps, float* out2,
+                       float* ws, b200_stream_t stream);
+int b200_sn_grad(const float* g, const float* W, const float* u, const float* v, const float* sig2, float* dW, int h,
+                 int w, int accumulate, double* ws, b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GAN_H */

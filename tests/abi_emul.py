@@ -1,0 +1,381 @@
+"""CPU emulation of the libb200gan C ABI — TEST INFRASTRUCTURE ONLY.
+
+Each method restates, with plain torch CPU ops, the contract a C entry point documents in include/b200gan.h.  It is
+(1) the executable spec the `-m gpu` op tests compare every kernel against and (2) a stand-in that lets the
+`-m "not gpu"` suite exercise the host-side wiring (autograd formulas, descriptors, packing plans, module surface)
+without a GPU.  Nothing in the product imports this file.
+"""
+import torch
+import torch.nn.functional as F
+
+MODE_PLAIN, MODE_AFFINE, MODE_CBN, MODE_SPADE = 0, 1, 2, 3
+
+
+def _flat(t):
+    return t.reshape(-1) if t.is_contiguous() else None
+
+
+def _storage_view(t: torch.Tensor, offset: int, size, stride):
+    """View into the underlying storage of `t` starting `offset` elements after t's own first element."""
+    return torch.as_strided(t, size, stride, t.storage_offset() + offset)
+
+
+class EmulKernels:
+    def __init__(self):
+        self.launches = 0
+
+    def launch_count(self):
+        return self.launches
+
+    def version(self):
+        return 100
+
+    def conv_tc_ntile(self, cout):
+        return 128 if cout >= 128 else (64 if cout >= 64 else 16)
+
+    def bn_chunks(self, rows, C):
+        return 4
+
+    # ---- crops ----------------------------------------------------------------------------------------
+    @staticmethod
+    def _coords(boxes, w, lo, hi, size):
+        S = w.numel() // 2
+        sw, ew = w[:S], w[S:]
+        a = 2 * boxes[:, lo] - 1
+        b = 2 * boxes[:, hi] - 1
+        g = sw[None] * a[:, None] + ew[None] * b[:, None]
+        return ((g + 1) * size - 1) / 2
+
+    def crop_taps(self, boxes, wx, wy, H, W, HH, WW):
+        ix = self._coords(boxes, wx, 0, 2, W)
+        iy = self._coords(boxes, wy, 1, 3, H)
+        ix0, iy0 = torch.floor(ix), torch.floor(iy)
+        return ix0.to(torch.int32), iy0.to(torch.int32), ix - ix0, iy - iy0
+
+    def _crop_matrices(self, boxes, wx, wy, H, W):
+        ix0, iy0, fx, fy = self.crop_taps(boxes, wx, wy, H, W, wy.numel() // 2, wx.numel() // 2)
+        B = boxes.shape[0]
+
+        def mat(i0, f, size):
+            S = i0.shape[1]
+            M = torch.zeros(B, S, size + 2)
+            idx = (i0.long() + 1).clamp(0, size + 1)           # shift by one so -1 lands in a discarded column
+            ok0 = (i0 >= 0) & (i0 < size)
+            ok1 = (i0 + 1 >= 0) & (i0 + 1 < size)
+            M.scatter_add_(2, idx.unsqueeze(-1), ((1 - f) * ok0).unsqueeze(-1))
+            idx1 = (i0.long() + 2).clamp(0, size + 1)
+            M.scatter_add_(2, idx1.unsqueeze(-1), (f * ok1).unsqueeze(-1))
+            return M[:, :, 1:size + 1]
+
+        return mat(iy0, fy, H), mat(ix0, fx, W)                 # (B,HH,H), (B,WW,W)
+
+    def crop_fwd(self, feats, boxes, box_to_img, wx, wy, HH, WW):
+        self.launches += 1
+        N, C, H, W = feats.shape
+        My, Mx = self._crop_matrices(boxes, wx, wy, H, W)
+        src = feats[box_to_img.long()]
+        return torch.einsum("bih,bchw,bjw->bcij", My, src, Mx)
+
+    def crop_bwd(self, dcrops, boxes, img_box_start, box_order, wx, wy, N, H, W):
+        self.launches += 2
+        B, C = dcrops.shape[:2]
+        My, Mx = self._crop_matrices(boxes, wx, wy, H, W)
+        d = torch.einsum("bih,bcij,bjw->bchw", My, dcrops, Mx)
+        out = torch.zeros(N, C, H, W)
+        start = img_box_start.tolist()
+        order = box_order.long()
+        for n in range(N):
+            ids = order[start[n]:start[n + 1]]
+            if ids.numel():
+                out[n] = d[ids].sum(0)
+        return out
+
+    # ---- gather GEMMs -------------------------------------------------------------------------------------
+    @staticmethod
+    def _gather(d, inp):
+        """A[m, tap, c] per the descriptor; returns (M, T, Cin) and the output row offsets."""
+        B, Qh, Qw = d.B, d.Qh, d.Qw
+        Hp = ((d.Hi - 1) >> d.up_shift) + 1
+        Wp = ((d.Wi - 1) >> d.up_shift) + 1
+        x = _storage_view(inp, 0, (B, Hp, Wp, d.Cin), (d.in_sn, d.in_sh, d.in_sw, d.in_sc))
+        qy = torch.arange(Qh)
+        qx = torch.arange(Qw)
+        cols = []
+        for ty in range(d.Th):
+            for tx in range(d.Tw):
+                iy = qy * d.in_sy + ty * d.tap_sy + d.tap_oy
+                ix = qx * d.in_sx + tx * d.tap_sx + d.tap_ox
+                vy = (iy >= 0) & (iy < d.Hi)
+                vx = (ix >= 0) & (ix < d.Wi)
+                g = x[:, (iy.clamp(0, d.Hi - 1) >> d.up_shift)][:, :, (ix.clamp(0, d.Wi - 1) >> d.up_shift)]
+                g = g * (vy[:, None] & vx[None, :]).to(g.dtype)[None, :, :, None]
+                cols.append(g.reshape(B * Qh * Qw, d.Cin))
+        return torch.stack(cols, dim=1)
+
+    @staticmethod
+    def _out_index(d):
+        qy = torch.arange(d.Qh)
+        qx = torch.arange(d.Qw)
+        oy = qy * d.out_sy + d.out_oy
+        ox = qx * d.out_sx + d.out_ox
+        ok = ((oy >= 0) & (oy < d.Ho))[:, None] & ((ox >= 0) & (ox < d.Wo))[None, :]
+        off = oy[:, None] * d.out_sh + ox[None, :] * d.out_sw
+        n = torch.arange(d.B) * d.out_sn
+        off = (n[:, None, None] + off[None]).reshape(-1)
+        ok = ok[None].expand(d.B, -1, -1).reshape(-1)
+        return off, ok
+
+    def conv_gemm(self, d, inp, wmat, bias, scale, out, tc):
+        self.launches += 1
+        A = self._gather(d, inp)
+        K = d.Th * d.Tw * d.Cin
+        Wm = wmat.float()[:d.Cout, :K]
+        A2 = A.reshape(A.shape[0], K)
+        if tc:
+            A2 = A2.to(torch.bfloat16).float()
+        y = A2 @ Wm.t()
+        if scale is not None:
+            y = y * scale.reshape(-1)[0]
+        if bias is not None:
+            y = y + bias[None]
+        if d.relu:
+            y = F.relu(y)
+        off, ok = self._out_index(d)
+        flat = torch.as_strided(out, (out.untyped_storage().nbytes() // 4 - out.storage_offset(),), (1,), out.storage_offset())
+        co = torch.arange(d.Cout) * d.out_sc
+        idx = (off[ok][:, None] + co[None]).reshape(-1)
+        flat[idx] = y[ok].reshape(-1)
+
+    def wgrad_gemm(self, d, P, G, ws, splits, tc):
+        self.launches += 1
+        A = self._gather(d, G)                                   # (Q, T, Cin)
+        off, ok = self._out_index(d)
+        flatP = torch.as_strided(P, (P.untyped_storage().nbytes() // 4 - P.storage_offset(),), (1,), P.storage_offset())
+        co = torch.arange(d.Cout) * d.out_sc
+        Pm = flatP[(off.clamp(min=0)[:, None] + co[None])] * ok[:, None].to(P.dtype)
+        if tc:
+            A = A.to(torch.bfloat16).float()
+            Pm = Pm.to(torch.bfloat16).float()
+        K = d.Th * d.Tw * d.Cin
+        R = Pm.t() @ A.reshape(A.shape[0], K)
+        wsv = ws.view(splits, d.Cout, K)
+        wsv.zero_()
+        wsv[0] = R
+
+    def wgrad_reduce(self, ws, splits, M, Th, Tw, C, dst, dst_offset, s_m, s_ty, s_tx, s_c, scale=None, accumulate=False,
+                     ws_row_offset=0, ws_rows=None):
+        self.launches += 1
+        rows = M if ws_rows is None else ws_rows
+        K = Th * Tw * C
+        R = ws.view(splits, rows, K)[:, ws_row_offset:ws_row_offset + M].sum(0).view(M, Th, Tw, C)
+        if scale is not None:
+            R = R * scale.reshape(-1)[0]
+        view = _storage_view(dst, dst_offset, (M, Th, Tw, C), (s_m, s_ty, s_tx, s_c))
+        if accumulate:
+            view += R
+        else:
+            view.copy_(R)
+
+    def pack_weight(self, src, src_offset, dst, dst_row_offset, bf16, M, Mpad, Th, Tw, C, ldw, s_m, s_ky, s_kx, s_c,
+                    ky0=0, kx0=0, kstep=1):
+        self.launches += 1
+        v = _storage_view(src.detach(), src_offset + ky0 * s_ky + kx0 * s_kx, (M, Th, Tw, C),
+                          (s_m, s_ky * kstep, s_kx * kstep, s_c))
+        out = torch.zeros(Mpad, ldw)
+        out[:M, :Th * Tw * C] = v.reshape(M, -1)
+        dst[dst_row_offset:dst_row_offset + Mpad] = out.to(dst.dtype)
+
+    # ---- normalisation --------------------------------------------------------------------------------------
+    def bn_stats(self, x2d, running_mean, running_var, momentum):
+        self.launches += 2
+        rows = x2d.shape[0]
+        xd = x2d.double()
+        mean = xd.mean(0)
+        var = (xd * xd).mean(0) - mean * mean
+        var = var.clamp(min=0)
+        if running_mean is not None:
+            unb = var * rows / (rows - 1) if rows > 1 else var
+            running_mean.mul_(1 - momentum).add_(momentum * mean.float())
+            running_var.mul_(1 - momentum).add_(momentum * unb.float())
+        return mean.float(), var.float()
+
+    @staticmethod
+    def _g_b(mode, gamma, beta, idx, rows_per_seg, rows, C):
+        if mode == MODE_PLAIN:
+            return None, None
+        if mode == MODE_AFFINE:
+            return gamma[None], beta[None]
+        if mode == MODE_CBN:
+            t = gamma[idx.long()].repeat_interleave(rows_per_seg, dim=0)
+            return t[:, :C], t[:, C:]
+        return 1 + gamma[:, :C], gamma[:, C:]
+
+    def norm_fwd(self, x2d, mean, var, eps, mode, gamma, beta, idx, rows_per_seg, residual, relu):
+        self.launches += 1
+        rows, C = x2d.shape
+        xh = (x2d - mean[None]) * (1.0 / torch.sqrt(var + eps))[None]
+        g, b = self._g_b(mode, gamma, beta, idx, rows_per_seg, rows, C)
+        y = xh if g is None else xh * g + b
+        if residual is not None:
+            y = y + residual
+        return F.relu(y) if relu else y
+
+    def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes):
+        self.launches += 4
+        rows, C = x2d.shape
+        rstd = 1.0 / torch.sqrt(var + eps)
+        xh = (x2d - mean[None]) * rstd[None]
+        g = dy * (y > 0).to(dy.dtype) if relu else dy
+        gm, _ = self._g_b(mode, gamma, gamma if mode == MODE_AFFINE else None, idx, rows_per_seg, rows, C)
+        dxh = g if gm is None else g * gm
+        s1 = dxh.double().sum(0).float()
+        s2 = (dxh.double() * xh.double()).sum(0).float()
+        dx = rstd[None] * (dxh - s1[None] / rows - xh * s2[None] / rows)
+        dgamma = dbeta = dtable = dgb = None
+        if mode == MODE_AFFINE:
+            dgamma = (g.double() * xh.double()).sum(0).float()
+            dbeta = g.double().sum(0).float()
+        elif mode == MODE_CBN:
+            nseg = rows // rows_per_seg
+            a = (g * xh).view(nseg, rows_per_seg, C).sum(1)
+            b = g.view(nseg, rows_per_seg, C).sum(1)
+            dtable = torch.zeros(num_classes, 2 * C)
+            dtable.index_add_(0, idx.long(), torch.cat([a, b], dim=1))
+        elif mode == MODE_SPADE:
+            dgb = torch.cat([g * xh, g], dim=1)
+        return dx, dgamma, dbeta, dtable, dgb
+
+    # ---- elementwise ----------------------------------------------------------------------------------------
+    def relu_fwd(self, x):
+        self.launches += 1
+        return F.relu(x)
+
+    def relu_bwd(self, dy, y):
+        self.launches += 1
+        return dy * (y > 0).to(dy.dtype)
+
+    def add(self, a, b, out=None):
+        self.launches += 1
+        if out is None:
+            return a + b
+        out.copy_(a + b)
+        return out
+
+    def pool_fwd(self, x, N, H, W, C, f, scale):
+        self.launches += 1
+        return x.reshape(N, H // f, f, W // f, f, C).sum(dim=(2, 4)) * scale
+
+    def unpool_fwd(self, x, N, H, W, C, f, scale):
+        self.launches += 1
+        v = x.reshape(N, H, 1, W, 1, C).expand(N, H, f, W, f, C)
+        return (v * scale).reshape(N, H * f, W * f, C).contiguous()
+
+    def concat_fwd(self, a, Ca, a_div, b, Cb, b_div, rows):
+        self.launches += 1
+        aa = a.reshape(-1, Ca).repeat_interleave(a_div, dim=0)
+        bb = b.reshape(-1, Cb).repeat_interleave(b_div, dim=0)
+        return torch.cat([aa, bb], dim=1)
+
+    def concat_bwd(self, dout, Ca, a_div, Cb, b_div, rows, need_a=True, need_b=True):
+        self.launches += 1
+        d = dout.reshape(rows, Ca + Cb)
+        da = d[:, :Ca].reshape(rows // a_div, a_div, Ca).sum(1) if need_a else None
+        db = d[:, Ca:].reshape(rows // b_div, b_div, Cb).sum(1) if need_b else None
+        return da, db
+
+    def gather_rows(self, table, idx):
+        self.launches += 1
+        return table[idx.long()]
+
+    def scatter_rows(self, dout, idx, num_classes):
+        self.launches += 1
+        out = torch.zeros(num_classes, dout.shape[1])
+        out.index_add_(0, idx.long(), dout)
+        return out
+
+    def permute_rows(self, x, src_row, rowlen):
+        self.launches += 1
+        src = src_row.long()
+        xv = x.reshape(-1, rowlen)
+        out = xv[src.clamp(min=0)] * (src >= 0).to(x.dtype)[:, None]
+        return out
+
+    def mask_outer_fwd(self, v, mask, O, H, W, C):
+        self.launches += 1
+        out = torch.zeros(O, H + 2, W + 2, C)
+        out[:, 1:H + 1, 1:W + 1] = mask.reshape(O, H, W, 1) * v.reshape(O, 1, 1, C)
+        return out
+
+    def mask_outer_bwd(self, dout, mask, O, H, W, C):
+        self.launches += 1
+        return (dout[:, 1:H + 1, 1:W + 1] * mask.reshape(O, H, W, 1)).sum(dim=(1, 2))
+
+    def lstm_gates_fwd(self, pre_x, pre_h, c_prev, rows, hid, gates=None, c_out=None, h_out=None):
+        self.launches += 1
+        pre = pre_x.reshape(rows, 4 * hid)
+        if pre_h is not None:
+            pre = pre + pre_h.reshape(rows, 4 * hid)
+        i, f, o, g = torch.split(pre, hid, dim=1)
+        i, f, o, g = torch.sigmoid(i), torch.sigmoid(f), torch.sigmoid(o), torch.tanh(g)
+        cp = c_prev.reshape(rows, hid) if c_prev is not None else 0
+        cn = f * cp + i * g
+        hn = o * torch.tanh(cn)
+        gt = torch.cat([i, f, o, g], dim=1)
+        if gates is None:
+            return gt, cn, hn
+        gates.copy_(gt.view(gates.shape))
+        c_out.copy_(cn.view(c_out.shape))
+        h_out.copy_(hn.view(h_out.shape))
+        return gates, c_out, h_out
+
+    def lstm_gates_bwd(self, dh, dc_next, gates, c_prev, c_out, rows, hid, dpre=None, dc_prev=None):
+        self.launches += 1
+        i, f, o, g = torch.split(gates.reshape(rows, 4 * hid), hid, dim=1)
+        tc = torch.tanh(c_out.reshape(rows, hid))
+        dhv = dh.reshape(rows, hid)
+        dc = dhv * o * (1 - tc * tc)
+        if dc_next is not None:
+            dc = dc + dc_next.reshape(rows, hid)
+        cp = c_prev.reshape(rows, hid) if c_prev is not None else torch.zeros(rows, hid)
+        dp = torch.cat([dc * g * i * (1 - i), dc * cp * f * (1 - f), dhv * tc * o * (1 - o), dc * i * (1 - g * g)], dim=1)
+        dcp = dc * f
+        if dpre is None:
+            return dp, dcp
+        dpre.copy_(dp.view(dpre.shape))
+        dc_prev.copy_(dcp.view(dc_prev.shape))
+        return dpre, dc_prev
+
+    def reparam_fwd(self, mu, logvar, eps):
+        self.launches += 1
+        return eps * torch.exp(logvar * 0.5) + mu
+
+    def reparam_bwd(self, dz, logvar, eps):
+        self.launches += 1
+        return dz.clone(), dz * eps * 0.5 * torch.exp(logvar * 0.5)
+
+    def transpose(self, x, B, R, C):
+        self.launches += 1
+        return x.reshape(B, R, C).transpose(1, 2).contiguous()
+
+    def colsum(self, x2d):
+        self.launches += 2
+        return x2d.double().sum(0).float()
+
+    # ---- spectral norm ------------------------------------------------------------------------------------------
+    def sn_power_iter(self, W, h, w, u, v, do_iter, eps):
+        self.launches += 4
+        Wm = W.detach().reshape(h, w)
+        if do_iter:
+            v.copy_(F.normalize(torch.mv(Wm.t(), u), dim=0, eps=eps))
+            wv = torch.mv(Wm, v)
+            u.copy_(F.normalize(wv, dim=0, eps=eps))
+        else:
+            wv = torch.mv(Wm, v)
+        sigma = torch.dot(u, wv)
+        return torch.stack([sigma, 1.0 / sigma])
+
+    def sn_grad(self, g, W, u, v, sig2, h, w):
+        self.launches += 3
+        inv = sig2[1]
+        dot = (g.double() * W.detach().double()).sum().float()
+        return (g.reshape(h, w) * inv - dot * inv * inv * torch.outer(u, v)).reshape(W.shape)
