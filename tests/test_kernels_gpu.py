@@ -1,0 +1,385 @@
+"""-m gpu: every libb200gan entry point against its CPU restatement (tests/abi_emul.py) or the torch op it replaces,
+called through the C ABI exactly as the product does.  Tolerances: fp32 paths 1e-5 relative (summation order only),
+tcgen05 bf16-operand paths 2e-2 relative (stated bf16 bound), index work bit-exact."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from abi_emul import EmulKernels  # noqa: E402
+from b200gan import _lib, ops  # noqa: E402
+from oracle import gan_oracle as O  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+E = EmulKernels()
+
+
+@pytest.fixture(scope="module")
+def K():
+    assert torch.cuda.is_available()
+    return _lib.Kernels()
+
+
+def cu(*ts):
+    return [t.cuda() if isinstance(t, torch.Tensor) else t for t in ts]
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def close(a, b, tol, what=""):
+    e = rel(a, b)
+    assert e <= tol, "%s: rel err %.3e > %.1e" % (what, e, tol)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# crops
+# ---------------------------------------------------------------------------------------------------------
+def _crop_inputs(seed=0, N=3, C=3, H=64, W=64, B=11):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(N, C, H, W, generator=g)
+    xy0 = torch.rand(B, 2, generator=g) * 0.6
+    boxes = torch.cat([xy0, (xy0 + torch.rand(B, 2, generator=g) * 0.4 + 0.05).clamp(max=1.0)], 1)
+    boxes[0] = torch.tensor([0.0, 0.0, 1.0, 1.0])
+    boxes[1] = torch.tensor([0.5, 0.5, 0.5, 0.5])
+    b2i = torch.sort(torch.randint(0, N, (B,), generator=g))[0]
+    return feats, boxes, b2i
+
+
+@pytest.mark.parametrize("HH,WW,H", [(32, 32, 64), (64, 64, 128), (16, 24, 48)])
+def test_crop_taps_bit_exact(K, HH, WW, H):
+    feats, boxes, b2i = _crop_inputs(H=H, W=H)
+    wx, wy = ops.crop_weights(WW, "cuda"), ops.crop_weights(HH, "cuda")
+    ix0, iy0, fx, fy = K.crop_taps(boxes.cuda(), wx, wy, H, H, HH, WW)
+    rx0, ry0, rfx, rfy = O.crop_taps(boxes, H, H, HH, WW)
+    assert torch.equal(ix0.cpu(), rx0) and torch.equal(iy0.cpu(), ry0), "floor indices must be bit-exact"
+    assert torch.equal(fx.cpu(), rfx) and torch.equal(fy.cpu(), rfy), "fractional weights must be bit-exact"
+
+
+def test_crop_fwd_bwd_vs_reference_golden(K):
+    g = torch.load(os.path.join(GOLD, "crop.pt"))
+    feats = g["feats"].cuda().requires_grad_(True)
+    crops = ops.crop_bbox_batch(feats, g["boxes"].cuda(), g["b2f"], 32)
+    assert float((crops.cpu() - g["crops"]).abs().max()) < 2e-6
+    (crops * g["w"].cuda()).sum().backward()
+    assert float((feats.grad.cpu() - g["dfeats"]).abs().max()) < 2e-5
+    cu_ = ops.crop_bbox_batch(g["feats"].cuda(), g["boxes"].cuda(), g["b2f_u"], 16, 24)     # unsorted mapping
+    assert float((cu_.cpu() - g["crops_u"]).abs().max()) < 2e-6
+
+
+def test_crop_edge_cases(K):
+    feats, boxes, b2i = _crop_inputs(N=4, B=5)
+    b2i = torch.tensor([0, 0, 0, 3, 3])            # images 1 and 2 own no box
+    x = feats.cuda().requires_grad_(True)
+    y = ops.crop_bbox_batch(x, boxes[:5].cuda(), b2i, 32)
+    ref_in = feats.clone().requires_grad_(True)
+    ref = O.crop_bbox_batch(ref_in, boxes[:5], b2i, 32)
+    close(y, ref, 1e-6, "crop fwd")
+    y.sum().backward()
+    ref.sum().backward()
+    assert float((x.grad.cpu() - ref_in.grad).abs().max()) < 1e-4
+    assert float(x.grad[1].abs().max()) == 0.0 and float(x.grad[2].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# convolutions (forward / dgrad / wgrad through the ops layer, i.e. descriptors + packing + kernels)
+# ---------------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # Cx, Cy, k, s, p, H, N, x_layout, out_layout, bias
+    (3, 64, 7, 1, 3, 32, 3, "nchw", "cl", False),
+    (3, 64, 3, 1, 1, 16, 2, "nchw", "cl", True),
+    (64, 128, 4, 2, 1, 32, 3, "cl", "cl", False),
+    (64, 128, 4, 2, 1, 33, 2, "cl", "cl", False),       # odd extent (LayoutEncoder 66 -> 33 -> 16)
+    (128, 64, 3, 1, 1, 8, 5, "cl", "cl", True),
+    (64, 64, 1, 1, 0, 16, 2, "cl", "cl", True),
+    (64, 3, 7, 1, 3, 16, 2, "cl", "nchw", True),
+    (192, 256, 3, 1, 1, 8, 2, "cl", "cl", False),
+    (128, 128, 5, 1, 2, 16, 1, "cl", "cl", False),
+    (256, 512, 4, 2, 1, 8, 4, "cl", "cl", False),
+]
+
+
+def _conv_ref(x_nchw, w, b, s, p, relu, scale):
+    y = F.conv2d(x_nchw, w, None, stride=s, padding=p)
+    if scale is not None:
+        y = y * scale
+    if b is not None:
+        y = y + b.view(1, -1, 1, 1)
+    return F.relu(y) if relu else y
+
+
+def _to_layout(t_nchw, layout):
+    return t_nchw.contiguous() if layout == "nchw" else t_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def _from_layout(t, layout):
+    return t if layout == "nchw" else t.permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_bwd(K, case, precision):
+    Cx, Cy, k, s, p, H, N, xl, ol, has_b = case
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    g = torch.Generator().manual_seed(Cx * 7 + Cy + k)
+    x = torch.randn(N, Cx, H, H, generator=g)
+    w = torch.randn(Cy, Cx, k, k, generator=g) / (Cx * k * k) ** 0.5
+    b = torch.randn(Cy, generator=g) if has_b else None
+    ops.set_precision(precision)
+    try:
+        geom = ops.ConvGeom(Cx, Cy, k, k, s, p)
+        packs = ops.WeightPacks()
+        xd = _to_layout(x, xl).cuda().requires_grad_(True)
+        wd = w.cuda().requires_grad_(True)
+        bd = b.cuda().requires_grad_(True) if has_b else None
+        y = ops.conv2d(xd, wd, bd, geom, packs, xl, ol, relu=True)
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        br = b.clone().requires_grad_(True) if has_b else None
+        yr = _conv_ref(xr, wr, br, s, p, True, None)
+        close(_from_layout(y, ol), yr, tol, "fwd")
+        gy = torch.randn(yr.shape, generator=g)
+        y.backward(_to_layout(gy, ol).cuda())
+        yr.backward(gy)
+        close(_from_layout(xd.grad, xl), xr.grad, tol, "dgrad")
+        close(wd.grad, wr.grad, tol, "wgrad")
+        if has_b:
+            close(bd.grad, br.grad, tol, "bias grad")
+    finally:
+        ops.set_precision("fp32")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("Cin,Cout,H", [(256, 256, 8), (256, 128, 16), (128, 64, 8)])
+def test_conv_transpose(K, Cin, Cout, H, precision):
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(2, Cin, H, H, generator=g)
+    w = torch.randn(Cin, Cout, 4, 4, generator=g) / (Cin * 4) ** 0.5
+    ops.set_precision(precision)
+    try:
+        geom = ops.ConvGeom(Cout, Cin, 4, 4, 2, 1)
+        xd = _to_layout(x, "cl").cuda().requires_grad_(True)
+        wd = w.cuda().requires_grad_(True)
+        y = ops.conv_transpose2d(xd, wd, geom, ops.WeightPacks(), (2 * H, 2 * H))
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        yr = F.conv_transpose2d(xr, wr, None, stride=2, padding=1)
+        close(_from_layout(y, "cl"), yr, tol, "convT fwd")
+        gy = torch.randn(yr.shape, generator=g)
+        y.backward(_to_layout(gy, "cl").cuda())
+        yr.backward(gy)
+        close(_from_layout(xd.grad, "cl"), xr.grad, tol, "convT dgrad")
+        close(wd.grad, wr.grad, tol, "convT wgrad")
+    finally:
+        ops.set_precision("fp32")
+
+
+def test_linear_and_spectral_norm(K):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 170, generator=g)
+    w = torch.randn(128, 170, generator=g) * 0.1
+    b = torch.randn(128, generator=g)
+    u = F.normalize(torch.randn(128, generator=g), dim=0)
+    v = F.normalize(torch.randn(170, generator=g), dim=0)
+    xd, wd, bd = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    ud, vd = u.cuda(), v.cuda()
+    y = ops.linear(xd, wd, bd, ops.WeightPacks(), sn=(ud, vd), training=True)
+    st = {"l.weight_orig": w.clone().requires_grad_(True), "l.weight_u": u.clone(), "l.weight_v": v.clone(), "l.bias": b.clone().requires_grad_(True)}
+    xr = x.clone().requires_grad_(True)
+    yr = F.linear(xr, O.sn_weight(st, "l", True), st["l.bias"])
+    close(y, yr, 1e-5, "sn linear fwd")
+    close(ud, st["l.weight_u"], 1e-6, "u")
+    close(vd, st["l.weight_v"], 1e-6, "v")
+    gy = torch.randn(yr.shape, generator=g)
+    y.backward(gy.cuda())
+    yr.backward(gy)
+    close(xd.grad, xr.grad, 1e-5, "sn dgrad")
+    close(wd.grad, st["l.weight_orig"].grad, 2e-5, "sn wgrad")
+    close(bd.grad, st["l.bias"].grad, 1e-5, "bias")
+
+
+@pytest.mark.parametrize("h,w", [(64, 27), (1, 1024), (179, 1024), (1024, 9216)])
+def test_sn_power_iteration(K, h, w):
+    g = torch.Generator().manual_seed(h + w)
+    W = torch.randn(h, w, generator=g)
+    u = F.normalize(torch.randn(h, generator=g), dim=0)
+    v = F.normalize(torch.randn(w, generator=g), dim=0)
+    ud, vd = u.cuda(), v.cuda()
+    for do_iter in (1, 1, 0):
+        s_gpu = K.sn_power_iter(W.cuda(), h, w, ud, vd, do_iter, 1e-12)
+        s_cpu = E.sn_power_iter(W, h, w, u, v, do_iter, 1e-12)
+        close(s_gpu, s_cpu, 2e-5, "sigma")
+        close(ud, u, 2e-5, "u")
+        close(vd, v, 2e-5, "v")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# normalisation
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("relu", [False, True])
+def test_norm_fwd_bwd(K, mode, relu):
+    g = torch.Generator().manual_seed(10 + mode)
+    O_, hw, C, ncls = 6, 20, 64, 9
+    rows = O_ * hw
+    x = torch.randn(rows, C, generator=g) * 2 + 0.5
+    idx = torch.randint(0, ncls, (O_,), generator=g).to(torch.int32)
+    if mode == 1:
+        gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    elif mode == 2:
+        gamma, beta = torch.randn(ncls, 2 * C, generator=g), None
+    elif mode == 3:
+        gamma, beta = torch.randn(rows, 2 * C, generator=g), None
+    else:
+        gamma = beta = None
+    rm, rv = torch.zeros(C), torch.ones(C)
+    rmd, rvd = rm.cuda(), rv.cuda()
+    mean_d, var_d = K.bn_stats(x.cuda(), rmd, rvd, 0.1)
+    mean_c, var_c = E.bn_stats(x, rm, rv, 0.1)
+    close(mean_d, mean_c, 1e-6, "mean")
+    close(var_d, var_c, 1e-6, "var")
+    close(rmd, rm, 1e-6, "running_mean")
+    close(rvd, rv, 1e-6, "running_var")
+    res = torch.randn(rows, C, generator=g) if (mode == 1 and not relu) else None
+    a = cu(x, mean_c, var_c)
+    yd = K.norm_fwd(a[0], a[1], a[2], 1e-5, mode, *cu(gamma, beta, idx if mode == 2 else None), hw, *cu(res), relu)
+    yc = E.norm_fwd(x, mean_c, var_c, 1e-5, mode, gamma, beta, idx, hw, res, relu)
+    close(yd, yc, 1e-6, "norm fwd")
+    dy = torch.randn(rows, C, generator=g)
+    outs_d = K.norm_bwd(*cu(dy, x, yc, mean_c, var_c), 1e-5, mode, *cu(gamma, idx if mode == 2 else None), hw, relu, ncls)
+    outs_c = E.norm_bwd(dy, x, yc, mean_c, var_c, 1e-5, mode, gamma, idx, hw, relu, ncls)
+    for name, d, c in zip(("dx", "dgamma", "dbeta", "dtable", "dgb"), outs_d, outs_c):
+        assert (d is None) == (c is None), name
+        if d is not None:
+            close(d, c, 2e-5, name)
+
+
+def test_bn_stats_shapes(K):
+    for rows, C in ((1, 64), (7, 128), (100000, 64), (4096, 1024)):
+        x = torch.randn(rows, C) + 3.0
+        m, v = K.bn_stats(x.cuda(), None, None, 0.1)
+        close(m, x.double().mean(0), 1e-6, "mean %d" % rows)
+        if rows > 1:
+            assert float((v.cpu() - x.double().var(0, unbiased=False).float()).abs().max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# elementwise / pooling / layout
+# ---------------------------------------------------------------------------------------------------------
+def test_elementwise_family(K):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(5, 8, 8, 64, generator=g)
+    y = torch.randn(5, 8, 8, 64, generator=g)
+    close(K.relu_fwd(x.cuda()), F.relu(x), 0, "relu")
+    close(K.relu_bwd(y.cuda(), F.relu(x).cuda()), E.relu_bwd(y, F.relu(x)), 0, "relu bwd")
+    close(K.add(x.cuda(), y.cuda()), x + y, 0, "add")
+    odd = torch.randn(1003, generator=g)
+    close(K.relu_fwd(odd.cuda()), F.relu(odd), 0, "relu tail")
+    for f, sc in ((2, 0.25), (8, 1.0), (4, 1.0 / 16)):
+        close(K.pool_fwd(x.cuda(), 5, 8, 8, 64, f, sc), E.pool_fwd(x, 5, 8, 8, 64, f, sc), 1e-6, "pool")
+        close(K.unpool_fwd(x.cuda(), 5, 8, 8, 64, f, sc), E.unpool_fwd(x, 5, 8, 8, 64, f, sc), 1e-7, "unpool")
+    a, b = torch.randn(6 * 4, 64, generator=g), torch.randn(6, 128, generator=g)
+    close(K.concat_fwd(a.cuda(), 64, 1, b.cuda(), 128, 4, 24), E.concat_fwd(a, 64, 1, b, 128, 4, 24), 0, "concat")
+    d = torch.randn(24, 192, generator=g)
+    da, db = K.concat_bwd(d.cuda(), 64, 1, 128, 4, 24)
+    ra, rb = E.concat_bwd(d, 64, 1, 128, 4, 24)
+    close(da, ra, 1e-6, "concat bwd a")
+    close(db, rb, 1e-6, "concat bwd b")
+    table = torch.randn(179, 128, generator=g)
+    idx = torch.randint(0, 179, (40,), generator=g).to(torch.int32)
+    close(K.gather_rows(table.cuda(), idx.cuda()), table[idx.long()], 0, "gather")
+    dd = torch.randn(40, 128, generator=g)
+    close(K.scatter_rows(dd.cuda(), idx.cuda(), 179), E.scatter_rows(dd, idx, 179), 1e-6, "scatter")
+    src = torch.tensor([3, -1, 0, 2, 2], dtype=torch.int32)
+    xr = torch.randn(4, 64, generator=g)
+    close(K.permute_rows(xr.cuda(), src.cuda(), 64), E.permute_rows(xr, src, 64), 0, "permute")
+    v = torch.randn(7, 64, generator=g)
+    mask = (torch.rand(7, 1, 16, 16, generator=g) > 0.5).float()
+    close(K.mask_outer_fwd(v.cuda(), mask.cuda(), 7, 16, 16, 64), E.mask_outer_fwd(v, mask, 7, 16, 16, 64), 0, "mask outer")
+    do = torch.randn(7, 18, 18, 64, generator=g)
+    close(K.mask_outer_bwd(do.cuda(), mask.cuda(), 7, 16, 16, 64), E.mask_outer_bwd(do, mask, 7, 16, 16, 64), 1e-6, "mask outer bwd")
+    mu, lv, eps = [torch.randn(9, 64, generator=g) for _ in range(3)]
+    close(K.reparam_fwd(*cu(mu, lv, eps)), E.reparam_fwd(mu, lv, eps), 1e-6, "reparam")
+    for dgpu, dcpu in zip(K.reparam_bwd(*cu(mu, lv, eps)), E.reparam_bwd(mu, lv, eps)):
+        close(dgpu, dcpu, 1e-6, "reparam bwd")
+    t = torch.randn(3, 50, 7, generator=g)
+    close(K.transpose(t.cuda(), 3, 50, 7), t.transpose(1, 2), 0, "transpose")
+    close(K.colsum(d.cuda()), d.sum(0), 1e-6, "colsum")
+
+
+def test_lstm_gates(K):
+    g = torch.Generator().manual_seed(2)
+    rows, hid = 3 * 64, 64
+    px, ph, cp = torch.randn(rows, 4 * hid, generator=g), torch.randn(rows, 4 * hid, generator=g), torch.randn(rows, hid, generator=g)
+    for with_prev in (True, False):
+        a = (px, ph, cp) if with_prev else (px, None, None)
+        gd, cd, hd = K.lstm_gates_fwd(*cu(*a), rows, hid)
+        gc, cc, hc = E.lstm_gates_fwd(*a, rows, hid)
+        close(gd, gc, 1e-6, "gates")
+        close(cd, cc, 1e-6, "c")
+        close(hd, hc, 1e-6, "h")
+        dh, dcn = torch.randn(rows, hid, generator=g), torch.randn(rows, hid, generator=g)
+        b = (dh, dcn if with_prev else None, gc, cp if with_prev else None, cc)
+        dpd, dcd = K.lstm_gates_bwd(*cu(*b), rows, hid)
+        dpc, dcc = E.lstm_gates_bwd(*b, rows, hid)
+        close(dpd, dpc, 1e-5, "dpre")
+        close(dcd, dcc, 1e-5, "dc_prev")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_lstm_vs_oracle(K, precision):
+    tol = 2e-5 if precision == "fp32" else 3e-2
+    g = torch.Generator().manual_seed(4)
+    o2i = torch.tensor([0, 0, 0, 1, 2, 2, 2, 2, 3, 3])
+    x = torch.randn(10, 512, 8, 8, generator=g) * 0.5
+    sd = {}
+    cin = 512
+    layers = []
+    for i, hid in enumerate((128, 64, 64)):
+        sd["c.cell_list.%d.conv.weight" % i] = (torch.randn(4 * hid, cin + hid, 5, 5, generator=g) / ((cin + hid) * 25) ** 0.5).requires_grad_(True)
+        sd["c.cell_list.%d.conv.bias" % i] = (torch.randn(4 * hid, generator=g) * 0.1).requires_grad_(True)
+        layers.append(ops.ConvLSTMLayer(cin, hid, 5))
+        cin = hid
+    xr = x.clone().requires_grad_(True)
+    yr = O.conv_lstm(sd, "c", xr, o2i)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    ops.set_precision(precision)
+    try:
+        xd = x.permute(0, 2, 3, 1).contiguous().cuda().requires_grad_(True)
+        params = []
+        for i in range(3):
+            params += [sd["c.cell_list.%d.conv.weight" % i].detach().cuda().requires_grad_(True),
+                       sd["c.cell_list.%d.conv.bias" % i].detach().cuda().requires_grad_(True)]
+        plan = ops.get_plan(o2i, None, "cuda")
+        y = ops.conv_lstm(xd, plan, layers, params)
+        close(y.permute(0, 3, 1, 2), yr, tol, "clstm fwd")
+        y.backward(gy.permute(0, 2, 3, 1).contiguous().cuda())
+        close(xd.grad.permute(0, 3, 1, 2), xr.grad, tol * 2, "clstm dx")
+        for i in range(3):
+            close(params[2 * i].grad, sd["c.cell_list.%d.conv.weight" % i].grad, tol * 2, "clstm dW%d" % i)
+            close(params[2 * i + 1].grad, sd["c.cell_list.%d.conv.bias" % i].grad, tol * 2, "clstm db%d" % i)
+    finally:
+        ops.set_precision("fp32")
+
+
+def test_tc_matches_fp32_at_scale(K):
+    """size-independent property at BASELINE size (O=256 crops, 64->128 k4s2 at 32x32): the tcgen05 result equals the fp32
+    CUDA-core result within the bf16 operand bound, and conv is linear: conv(a*x) == a*conv(x)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(256, 32, 32, 64, generator=g).cuda()
+    w = (torch.randn(128, 64, 4, 4, generator=g) / 32).cuda()
+    geom = ops.ConvGeom(64, 128, 4, 4, 2, 1)
+    y32 = ops.conv_forward(geom, ops.WeightPacks(), w, x, "cl", "cl")
+    ops.set_precision("bf16")
+    try:
+        ytc = ops.conv_forward(geom, ops.WeightPacks(), w, x, "cl", "cl")
+        ytc2 = ops.conv_forward(geom, ops.WeightPacks(), w, x * 2.0, "cl", "cl")
+    finally:
+        ops.set_precision("fp32")
+    close(ytc, y32, 1e-2, "tc vs fp32")
+    assert torch.equal(ytc2, ytc * 2.0), "scaling by a power of two must commute exactly with the bf16 GEMM"

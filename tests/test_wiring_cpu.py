@@ -1,0 +1,71 @@
+"""not gpu: host-side wiring (module surface, autograd formulas, conv descriptors, ConvLSTM packing plans, state_dict
+layout) validated on the CPU by swapping the kernel namespace for the ABI emulation (tests/abi_emul.py)."""
+import os
+
+import pytest
+import torch
+
+from helpers import check_step_against, load_states, oracle_step, rel
+from oracle import gan_oracle as O
+
+
+def test_state_dict_surface(emul):
+    from b200gan.step import build_networks
+    for size in (64, 128):
+        nets = build_networks(size)
+        states = O.make_states(size, 0)
+        for net, key in zip(nets, ("G", "D_img", "D_obj", "D_att")):
+            sd = net.state_dict()
+            assert set(sd.keys()) == set(states[key].keys()), key
+            for k, v in sd.items():
+                assert tuple(v.shape) == tuple(states[key][k].shape) and v.dtype == states[key][k].dtype, (key, k)
+    n_params = sum(p.numel() for p in build_networks(64)[0].parameters())
+    assert n_params == 30295491            # G64 parameter count of the reference
+
+
+def test_step_wiring_matches_oracle_64(emul):
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    from b200gan.step import TrainStep
+    states = O.make_states(64, 0)
+    batch = O.synth_batch(2, 64, None, 7)
+    ts = TrainStep(64, device="cpu")
+    load_states(ts, states)
+    res = ts.step(ts.to_device(batch), optimizer_step=False, seeds=(123, 124))
+    model = O.OracleModel(64, 0, states)
+    ref = oracle_step(model, batch)
+    cos = check_step_against(ts, res, ref, img_tol=1e-4, loss_tol=1e-5, grad_tol=2e-2, cos_min=0.9999)
+    assert cos > 0.99999
+    for name, net, st in (("G", ts.netG, model.G), ("D_img", ts.netD_image, model.D_img), ("D_obj", ts.netD_object, model.D_obj),
+                          ("D_att", ts.netD_att, model.D_att)):
+        for k, v in net.state_dict().items():
+            if not O.is_parameter(k):
+                assert rel(v.float(), st[k].float()) < 1e-5 or float((v.float() - st[k].float()).abs().max()) < 1e-6, (name, k)
+    assert emul.launches > 1000
+
+
+def test_ragged_and_unsorted_layouts(emul):
+    """sequence lengths 1..5 with a single-object image; crops accept an unsorted box->image map"""
+    from b200gan import ops
+    o2i = torch.tensor([0, 1, 1, 1, 1, 1, 2, 2, 3])
+    plan = ops.get_plan(o2i, 4, "cpu")
+    assert plan.seq_lens == [1, 5, 2, 1] and plan.T == 5 and plan.n_t == [4, 2, 1, 1, 1]
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(9, 512, 8, 8, generator=g) * 0.3
+    sd, layers, cin = {}, [], 512
+    for i, hid in enumerate((128, 64, 64)):
+        sd["c.cell_list.%d.conv.weight" % i] = torch.randn(4 * hid, cin + hid, 5, 5, generator=g) / ((cin + hid) * 25) ** 0.5
+        sd["c.cell_list.%d.conv.bias" % i] = torch.randn(4 * hid, generator=g) * 0.1
+        layers.append(ops.ConvLSTMLayer(cin, hid, 5))
+        cin = hid
+    ref = O.conv_lstm(sd, "c", x, o2i)
+    params = []
+    for i in range(3):
+        params += [sd["c.cell_list.%d.conv.weight" % i], sd["c.cell_list.%d.conv.bias" % i]]
+    out = ops.conv_lstm(x.permute(0, 2, 3, 1).contiguous(), plan, layers, params)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 1e-5
+    feats = torch.randn(3, 3, 16, 16, generator=g)
+    boxes = torch.rand(5, 4, generator=g).sort(dim=1)[0][:, [0, 1, 2, 3]]
+    boxes = torch.stack([boxes[:, 0], boxes[:, 1], boxes[:, 2], boxes[:, 3]], 1)
+    b2f = torch.tensor([2, 0, 1, 0, 2])
+    c = ops.crop_bbox_batch(feats, boxes, b2f, 8)
+    assert rel(c, O.crop_bbox_batch(feats, boxes, b2f, 8)) < 1e-5
