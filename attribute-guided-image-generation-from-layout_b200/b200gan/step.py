@@ -77,6 +77,15 @@ class TrainStep:
         self.opt_G = torch.optim.Adam(self.netG.parameters(), **kw)                  # train64.py:111-114
         self.opt_D = [torch.optim.Adam(n.parameters(), **kw) for n in (self.netD_image, self.netD_object, self.netD_att)]
         self.d_nets = (self.netD_image, self.netD_object, self.netD_att)
+        self.ddp_d = self.ddp_g = None
+
+    def enable_data_parallel(self, bucket_bytes: int = 25 << 20, group=None):
+        """Shard-local step + bucketed gradient all-reduce overlapped with backward (b200gan/ddp.py)."""
+        from .ddp import GradBucketer, broadcast_module
+        for n in (self.netG,) + tuple(self.d_nets):
+            broadcast_module(n, group=group)
+        self.ddp_d = GradBucketer([p for n in self.d_nets for p in n.parameters()], bucket_bytes, group)
+        self.ddp_g = GradBucketer(list(self.netG.parameters()), bucket_bytes, group)
 
     # ---- batch handling ---------------------------------------------------------------------------------
     def to_device(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -168,7 +177,11 @@ class TrainStep:
         d_total, d_terms = self.d_loss(b, fake)
         for n in self.d_nets:
             n.zero_grad(set_to_none=True)
+        if self.ddp_d is not None:
+            self.ddp_d.arm()
         d_total.backward()
+        if self.ddp_d is not None:
+            self.ddp_d.finish()
         if optimizer_step:
             for o in self.opt_D:
                 o.step()
@@ -183,7 +196,11 @@ class TrainStep:
             out = self.generator(b, attribute_est)                                                # train64.py:280
             g_total, g_terms = self.g_loss(b, out)
             self.netG.zero_grad(set_to_none=True)
+            if self.ddp_g is not None:
+                self.ddp_g.arm()
             g_total.backward()
+            if self.ddp_g is not None:
+                self.ddp_g.finish()
         finally:
             if self.skip_dead_work:
                 for n in self.d_nets:

@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — G+D train-step throughput (images/sec) of the B200-native path, the metric of BASELINE.json.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size 64|128] [--batch B]
+                  [--precision bf16|fp32] [--no-graph] [--no-cpu-baseline]
+
+Workload at N=1: BASELINE.json configs[1] — 64x64 model (train64.py), batch 32, 8 objects/image, random-init weights,
+synthetic VG-shaped layouts; one "step" = attribute estimation + D-step + G-step (forward, losses, backward) + the four
+Adam updates.  For N>1 every rank runs the same per-GPU workload on its own shard (weak scaling) and gradients are
+all-reduced over NCCL in buckets overlapped with backward (b200gan/ddp.py).
+
+Prints ONE JSON line (see README / DESIGN.md for the keys).  `--impl reference` times the reference algorithm's CPU
+path (the oracle port, oracle/gan_oracle.py — the reference itself is pure Python and does not exist on the GPU box)
+on the host cores with a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "attribute-guided-image-generation-from-layout_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+OBJS_PER_IMAGE = 8
+
+
+# ------------------------------------------------------------------------------------------------------------
+# FLOP model (FlopCounterMode fit of the reference autograd): per G+D step
+# ------------------------------------------------------------------------------------------------------------
+def step_flops(size, n_images, n_objs, skip_dead=True):
+    if size == 64:
+        f = 73.3e9 * n_images + 65.7e9 * n_objs
+        dead = 3.9e9 * n_images + 6.3e9 * n_objs      # D weight gradients of the G-step, skipped here
+    else:
+        f = 620.2e9 * n_images + 223.2e9 * n_objs
+        dead = 3.9e9 * 4 * n_images + 6.3e9 * 4 * n_objs
+    return f - (dead if skip_dead else 0.0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: the clocks line, sampled DURING the timed region)
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(size, n_images, steps, warmup, threads):
+    from oracle import gan_oracle as O
+    torch.set_num_threads(threads)
+    states = O.make_states(size, 0)
+    model = O.OracleModel(size, 0, states)
+    batch = O.synth_batch(n_images, size, OBJS_PER_IMAGE, 3)
+    opts = [torch.optim.Adam([v for v in st.values() if v.requires_grad], lr=2e-4, betas=(0.5, 0.999))
+            for st in (model.G, model.D_img, model.D_obj, model.D_att)]
+
+    def one():
+        b = dict(batch)
+        b["attribute_GT"] = b["attribute"].clone()
+        nets = model.nets()
+        with torch.no_grad():
+            crops = O.crop_bbox_batch(b["imgs"], b["boxes"], b["obj_to_img"], model.obj_size)
+        est = O.estimate_attributes(nets["att"](crops).detach(), b["attribute"])
+        out = model.generator(b, est)
+        d_loss, _ = O.d_step_loss(nets, b, out, model.pos_weight)
+        model.zero_grad((model.D_img, model.D_obj, model.D_att))
+        d_loss.backward()
+        for o in opts[1:]:
+            o.step()
+        out = model.generator(b, est)
+        g_loss, _ = O.g_step_loss(nets, b, out, model.pos_weight)
+        model.zero_grad((model.G,))
+        g_loss.backward()
+        opts[0].step()
+        return float(d_loss), float(g_loss)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return n_images * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = 2
+    rate, sec = cpu_reference_rate(args.size, n, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "G+D train-step images/sec", "value": rate, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n_per_gpu=n, note="CPU sample"),
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": "%d steps of the %dx%d G+D step (incl. Adam) at batch %d, %d objects/image, oracle port of the "
+                                   "reference on %d host threads" % (args.steps, args.size, args.size, n, OBJS_PER_IMAGE, threads)},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_per_gpu, note=""):
+    return {"workload": "%dx%d model (train%d.py) G+D train step, batch %d per GPU, %d objects/image, random-init weights, "
+                        "synthetic VG layouts%s" % (args.size, args.size, args.size, n_per_gpu, OBJS_PER_IMAGE,
+                                                    (" [" + note + "]") if note else ""),
+            "image_size": args.size, "batch_per_gpu": n_per_gpu, "objects_per_image": OBJS_PER_IMAGE,
+            "parallelism": "dp%d" % args.gpus, "optimizer": "Adam (4 optimizers) inside the timed step",
+            "l2": "per-step working set (activations + 61M-parameter weights/Adam state, > 1 GB) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from b200gan import _lib, ops
+    from b200gan.step import TrainStep
+    from oracle import gan_oracle as O       # synthetic batch generator + cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU for --impl b200 (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.set_precision(args.precision)
+    n_img = args.batch
+    n_obj = n_img * OBJS_PER_IMAGE
+
+    torch.manual_seed(1234)
+    ts = TrainStep(args.size, device=dev, capturable=(not args.no_graph) and world == 1)
+    if world > 1:
+        ts.enable_data_parallel()
+        args.no_graph = True       # NCCL work is issued from autograd hooks; the multi-GPU step runs eagerly
+    torch.cuda.manual_seed(100 + rank)
+    ts.netG.crop_encoder.eps_source = lambda o, z, d: torch.randn(o, z, device=d)
+
+    host = O.synth_batch(n_img, args.size, OBJS_PER_IMAGE, seed=10 + rank)
+    pinned = {k: (v if k == "obj_to_img" else v.pin_memory()) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host.items() if k != "obj_to_img")
+    b = ts.to_device(pinned)
+    torch.cuda.synchronize()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def eager_step(batch):
+        return ts.step(batch, optimizer_step=True)
+
+    # ---- warm-up (eager) -----------------------------------------------------------------------------------
+    for _ in range(max(1, args.warmup if args.no_graph else 2)):
+        res = eager_step(b)
+    torch.cuda.synchronize()
+    launches_before = _lib.K.launch_count()
+    res = eager_step(b)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.K.launch_count() - launches_before
+
+    graph = None
+    static_out = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                eager_step(b)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                r = eager_step(b)
+                static_out = (r["d_loss"], r["g_loss"])
+            ops.bump_weight_epoch()
+            for _ in range(args.warmup):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:   # graph capture is an optimisation, never a correctness requirement
+            if rank == 0:
+                print("[bench] CUDA graph capture unavailable (%s: %s); timing eagerly" % (type(e).__name__, e), file=sys.stderr)
+            graph = None
+            ops.bump_weight_epoch()
+            torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+            return static_out
+        r = eager_step(b)
+        return r["d_loss"], r["g_loss"]
+
+    # ---- device-resident timing -----------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        losses = run_step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    assert all(torch.isfinite(l).all() for l in losses), "non-finite loss in the timed region"
+
+    # ---- end-to-end timing: pinned host batch -> device every step, losses read back every step ----------------
+    static_b = b
+    d2h_bytes = 8
+    sync_all()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        for k, v in pinned.items():
+            if k != "obj_to_img":
+                static_b[k].copy_(v, non_blocking=True)
+        losses = run_step()
+        host_losses = torch.stack([losses[0].reshape(()), losses[1].reshape(())]).cpu()
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1) / args.steps
+    assert torch.isfinite(host_losses).all()
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel family (tcgen05 gather-GEMMs), timed with CUDA events per launch ------
+    roof = None
+    if rank == 0:
+        roof = kernel_roofline(ts, b, args)
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, sec = cpu_reference_rate(args.size, 2, 2, 1, threads)
+        cpu_base = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                    "sample": "1 warm-up + 2 timed %dx%d G+D steps (incl. Adam) at batch 2, %d objects/image, oracle port of the "
+                              "reference on %d host threads" % (args.size, args.size, OBJS_PER_IMAGE, threads)}
+    if rank == 0:
+        total_imgs = n_img * world
+        line = {
+            "metric": "G+D train-step images/sec", "value": total_imgs / (ms / 1e3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic", "config": workload_config(args, n_img),
+            "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes * world,
+                    "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": ms_e2e},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "cuda_graph": graph is not None,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu_base,
+            "step_tflops": step_flops(args.size, n_img, n_obj) / (ms / 1e3) / 1e12,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(ts, b, args):
+    """Time every launch of the dominant kernel family inside one eager step with CUDA events on the launching stream
+    and divide the algorithmic FLOPs of those launches (2*M*N*K of the convolution each launch computes) by the summed
+    duration.  Peak = MEASURED_PEAKS.json bf16 sustained figure (kernel timed inside a long step), else the
+    B200_PROFILING.md fallback."""
+    from b200gan import _lib, ops
+    K = _lib.K
+    real = _lib._K if _lib._K is not None else None
+    if real is None:
+        return None
+    records = []
+    orig_conv, orig_wgrad = real.conv_gemm, real.wgrad_gemm
+
+    def flops_of(d, wgrad):
+        rows = d.B * d.Qh * d.Qw
+        return 2.0 * rows * d.Cout * d.Th * d.Tw * d.Cin
+
+    def timed(fn, wgrad):
+        def wrapper(desc, *a, **kw):
+            tc = a[-1] if not kw else kw.get("tc", a[-1])
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn(desc, *a, **kw)
+            e.record()
+            records.append((bool(tc), wgrad, flops_of(desc, wgrad), s, e))
+        return wrapper
+
+    real.conv_gemm = timed(orig_conv, False)
+    real.wgrad_gemm = timed(orig_wgrad, True)
+    try:
+        ops.bump_weight_epoch()
+        ts.step(b, optimizer_step=False)
+        torch.cuda.synchronize()
+    finally:
+        real.conv_gemm, real.wgrad_gemm = orig_conv, orig_wgrad
+    tc_t = sum(s.elapsed_time(e) for tc, _, _, s, e in records if tc) / 1e3
+    tc_f = sum(f for tc, _, f, _, _ in records if tc)
+    simt_t = sum(s.elapsed_time(e) for tc, _, _, s, e in records if not tc) / 1e3
+    simt_f = sum(f for tc, _, f, _, _ in records if not tc)
+    peak, src = 1390.5, "fallback"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, src = float(mp["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        peak, src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+    if tc_t > 0:
+        ach = tc_f / tc_t / 1e12
+        name = "conv_gemm_tc_kernel + wgrad_gemm_tc_kernel (tcgen05 gather-GEMMs)"
+    else:
+        ach = simt_f / max(simt_t, 1e-9) / 1e12
+        name = "conv_gemm_f32_kernel + wgrad_gemm_f32_kernel (fp32 CUDA-core gather-GEMMs)"
+    return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_source": src, "traffic": None, "launches": len([1 for r in records if r[0]]) if tc_t > 0 else len(records),
+            "kernel_time_ms_per_step": (tc_t if tc_t > 0 else simt_t) * 1e3,
+            "other_gemm_ms_per_step": (simt_t if tc_t > 0 else 0.0) * 1e3,
+            "algorithmic_tflop_per_step": (tc_f if tc_t > 0 else simt_f) / 1e12}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=64, choices=[64, 128])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -121,15 +121,22 @@ def _from_layout(t, layout):
     return t if layout == "nchw" else t.permute(0, 3, 1, 2)
 
 
+def _bf(t):
+    return t.bfloat16().float()
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_fwd_bwd(K, case, precision):
+    """fp32: against F.conv2d autograd (with bias + fused ReLU).  bf16: the tcgen05 kernels round both operands to bf16
+    and accumulate in fp32, so against the SAME computation on bf16-rounded operands they must agree to summation order
+    (1e-4); layers the tensor path does not take (3-channel side) fall back to fp32 kernels and are held to 2e-2."""
     Cx, Cy, k, s, p, H, N, xl, ol, has_b = case
-    tol = 1e-5 if precision == "fp32" else 2e-2
     g = torch.Generator().manual_seed(Cx * 7 + Cy + k)
     x = torch.randn(N, Cx, H, H, generator=g)
     w = torch.randn(Cy, Cx, k, k, generator=g) / (Cx * k * k) ** 0.5
     b = torch.randn(Cy, generator=g) if has_b else None
+    relu = precision == "fp32"
     ops.set_precision(precision)
     try:
         geom = ops.ConvGeom(Cx, Cy, k, k, s, p)
@@ -137,18 +144,31 @@ def test_conv_fwd_bwd(K, case, precision):
         xd = _to_layout(x, xl).cuda().requires_grad_(True)
         wd = w.cuda().requires_grad_(True)
         bd = b.cuda().requires_grad_(True) if has_b else None
-        y = ops.conv2d(xd, wd, bd, geom, packs, xl, ol, relu=True)
-        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
-        br = b.clone().requires_grad_(True) if has_b else None
-        yr = _conv_ref(xr, wr, br, s, p, True, None)
-        close(_from_layout(y, ol), yr, tol, "fwd")
-        gy = torch.randn(yr.shape, generator=g)
+        y = ops.conv2d(xd, wd, bd, geom, packs, xl, ol, relu=relu)
+        if precision == "fp32":
+            tf = td = tw = 1e-5
+            xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+            br = b.clone().requires_grad_(True) if has_b else None
+            yr = _conv_ref(xr, wr, br, s, p, relu, None)
+            gy = torch.randn(yr.shape, generator=g)
+            yr.backward(gy)
+            dxr, dwr, dbr = xr.grad, wr.grad, (br.grad if has_b else None)
+        else:
+            tf = 1e-4 if ops._tc_fwd_ok(geom, xl) else 2e-2
+            td = 1e-4 if ops._tc_dgrad_ok(geom, ol) else 2e-2
+            tw = 1e-4 if ops._tc_wgrad_ok(geom, xl, ol) else 2e-2
+            xq, wq = (_bf(x), _bf(w)) if ops._tc_fwd_ok(geom, xl) else (x, w)
+            yr = _conv_ref(xq, wq, b, s, p, False, None)
+            gy = torch.randn(yr.shape, generator=g)
+            dxr = torch.nn.grad.conv2d_input(x.shape, _bf(w), _bf(gy), stride=s, padding=p)
+            dwr = torch.nn.grad.conv2d_weight(_bf(x), w.shape, _bf(gy), stride=s, padding=p)
+            dbr = gy.sum(dim=(0, 2, 3)) if has_b else None
+        close(_from_layout(y, ol), yr, tf, "fwd")
         y.backward(_to_layout(gy, ol).cuda())
-        yr.backward(gy)
-        close(_from_layout(xd.grad, xl), xr.grad, tol, "dgrad")
-        close(wd.grad, wr.grad, tol, "wgrad")
+        close(_from_layout(xd.grad, xl), dxr, td, "dgrad")
+        close(wd.grad, dwr, tw, "wgrad")
         if has_b:
-            close(bd.grad, br.grad, tol, "bias grad")
+            close(bd.grad, dbr, 1e-5, "bias grad")
     finally:
         ops.set_precision("fp32")
 
@@ -156,24 +176,25 @@ def test_conv_fwd_bwd(K, case, precision):
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("Cin,Cout,H", [(256, 256, 8), (256, 128, 16), (128, 64, 8)])
 def test_conv_transpose(K, Cin, Cout, H, precision):
-    tol = 1e-5 if precision == "fp32" else 2e-2
+    tol = 1e-5 if precision == "fp32" else 1e-4
     g = torch.Generator().manual_seed(Cin + Cout)
     x = torch.randn(2, Cin, H, H, generator=g)
     w = torch.randn(Cin, Cout, 4, 4, generator=g) / (Cin * 4) ** 0.5
+    q = _bf if precision == "bf16" else (lambda t: t)
     ops.set_precision(precision)
     try:
         geom = ops.ConvGeom(Cout, Cin, 4, 4, 2, 1)
         xd = _to_layout(x, "cl").cuda().requires_grad_(True)
         wd = w.cuda().requires_grad_(True)
         y = ops.conv_transpose2d(xd, wd, geom, ops.WeightPacks(), (2 * H, 2 * H))
-        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
-        yr = F.conv_transpose2d(xr, wr, None, stride=2, padding=1)
+        yr = F.conv_transpose2d(q(x), q(w), None, stride=2, padding=1)
         close(_from_layout(y, "cl"), yr, tol, "convT fwd")
         gy = torch.randn(yr.shape, generator=g)
         y.backward(_to_layout(gy, "cl").cuda())
-        yr.backward(gy)
-        close(_from_layout(xd.grad, "cl"), xr.grad, tol, "convT dgrad")
-        close(wd.grad, wr.grad, tol, "convT wgrad")
+        dxr = F.conv2d(q(gy), q(w), None, stride=2, padding=1)
+        dwr = torch.nn.grad.conv2d_weight(q(gy), (Cin, Cout, 4, 4), q(x), stride=2, padding=1)
+        close(_from_layout(xd.grad, "cl"), dxr, tol, "convT dgrad")
+        close(wd.grad, dwr, tol, "convT wgrad")
     finally:
         ops.set_precision("fp32")
 
