@@ -22,7 +22,7 @@ def _worker(rank, world, port, out):
     broadcast_module(net)
     unused = torch.nn.Linear(3, 3)     # a parameter that never receives a gradient
     params = list(net.parameters()) + list(unused.parameters())
-    bk = GradBucketer(params, bucket_bytes=1024)
+    bk = GradBucketer(params, bucket_bytes=256)
     assert len(bk.buckets) >= 3
     g = torch.Generator().manual_seed(42)
     x = torch.randn(8, 16, generator=g)
