@@ -208,5 +208,6 @@ class TrainStep:
                         p.requires_grad_(True)
         if optimizer_step:
             self.opt_G.step()
-        return dict(d_loss=d_total.detach(), g_loss=g_total.detach(), d_terms=d_terms, g_terms=g_terms, out_g=out,
+        return dict(d_loss=d_total.detach(), g_loss=g_total.detach(), d_terms={k: v.detach() for k, v in d_terms.items()},
+                    g_terms={k: v.detach() for k, v in g_terms.items()}, out_g=[t.detach() for t in out],
                     attribute_est=attribute_est)

@@ -1,6 +1,7 @@
 // common.cuh — shared helpers for libb200gan (error reporting, launch accounting, reductions).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -46,5 +47,38 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+
+// ---- activation storage types: channel-last activations are fp32 (B200_F32) or bf16 (B200_BF16) ----------------------
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 4 consecutive elements (pointer must be 4-element aligned: 16 B for fp32, 8 B for bf16)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x), b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+// dispatch helper: run `BODY` with `T` bound to the storage type selected by an int dtype code
+#define B200_DISPATCH_DT(dt, T, ...)                          \
+    do {                                                      \
+        if ((dt) == B200_BF16) { typedef b200::bf16 T; __VA_ARGS__; } \
+        else { typedef float T; __VA_ARGS__; }                \
+    } while (0)
 
 }  // namespace b200

@@ -220,6 +220,9 @@ def run_b200(args):
 
     graph = None
     static_out = None
+    del res
+    import gc
+    gc.collect()
     if not args.no_graph:
         try:
             side = torch.cuda.Stream()
