@@ -107,15 +107,35 @@ class Kernels:
         return dfeats
 
     # ---- gather-GEMM convolutions -----------------------------------------------------------------------
+    def cast_bf16(self, x):
+        """fp32 -> bf16 copy of a contiguous tensor (the operand format of the tcgen05 gather-GEMMs)"""
+        y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        self._check(self.lib.b200_cast_bf16(_ptr(x), _ptr(y), C.c_int64(x.numel()), _stream()), "b200_cast_bf16")
+        return y
+
     def conv_gemm(self, desc: ConvDesc, inp, wmat, bias, scale, out, tc: bool):
-        fn = self.lib.b200_conv_gemm_tc if tc else self.lib.b200_conv_gemm_f32
-        self._check(fn(C.byref(desc), _ptr(inp), _ptr(wmat), _ptr(bias), _ptr(scale), _ptr(out), _stream()),
-                    "b200_conv_gemm_tc" if tc else "b200_conv_gemm_f32")
+        if not tc:
+            self._check(self.lib.b200_conv_gemm_f32(C.byref(desc), _ptr(inp), _ptr(wmat), _ptr(bias), _ptr(scale),
+                                                    _ptr(out), _stream()), "b200_conv_gemm_f32")
+            return
+        if inp.dtype != torch.bfloat16:
+            raise B200Error("conv_gemm(tc): the activation operand must be bf16 (use cast_bf16)")
+        splits = int(self.lib.b200_conv_tc_splits(C.byref(desc)))
+        ws = None
+        if splits > 1:
+            nt = self.conv_tc_ntile(desc.Cout)
+            ldo = (desc.Cout + nt - 1) // nt * nt
+            ws = torch.empty((splits * desc.B * desc.Qh * desc.Qw * ldo,), dtype=torch.float32, device=inp.device)
+        self._check(self.lib.b200_conv_gemm_tc(C.byref(desc), _ptr(inp), _ptr(wmat), _ptr(bias), _ptr(scale), _ptr(out),
+                                               int(out.dtype == torch.bfloat16), _ptr(ws), splits, _stream()),
+                    "b200_conv_gemm_tc")
 
     def conv_tc_ntile(self, cout: int) -> int:
         return int(self.lib.b200_conv_tc_ntile(int(cout)))
 
     def wgrad_gemm(self, desc: ConvDesc, P, G, ws, splits: int, tc: bool):
+        if tc and (P.dtype != torch.bfloat16 or G.dtype != torch.bfloat16):
+            raise B200Error("wgrad_gemm(tc): both operands must be bf16 (use cast_bf16)")
         fn = self.lib.b200_wgrad_gemm_tc if tc else self.lib.b200_wgrad_gemm_f32
         self._check(fn(C.byref(desc), _ptr(P), _ptr(G), _ptr(ws), int(splits), _stream()),
                     "b200_wgrad_gemm_tc" if tc else "b200_wgrad_gemm_f32")

@@ -157,12 +157,26 @@ def _pack_dgrad(g: ConvGeom, w: torch.Tensor, tc: bool):
     return packs
 
 
+def as_bf16(x: torch.Tensor) -> torch.Tensor:
+    """bf16 operand copy of a channel-last activation for the tcgen05 gather-GEMMs (no-op when already bf16)"""
+    if x.dtype == torch.bfloat16:
+        return x
+    return _lib.K.cast_bf16(x.contiguous())
+
+
+def _need_f32(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype != torch.float32:
+        raise _lib.B200Error("fp32 gather-GEMM received a %s operand" % x.dtype)
+    return x
+
+
 def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bias=None, scale=None, relu=False):
-    """Y = epilogue(conv(X, W))"""
+    """Y = epilogue(conv(X, W)); on the tcgen05 path x may be passed already cast (as_bf16)"""
     N, Hx, Wx, Cx, xs = _dims(x, x_layout)
     assert Cx == g.Cx, (Cx, g.Cx)
     Hy, Wy = g.out_hw(Hx, Wx)
     tc = _tc_fwd_ok(g, x_layout)
+    x = as_bf16(x) if tc else _need_f32(x)
     wmat, ldw = packs.get(("fwd", tc) + g.key(), w, lambda: _pack_fwd(g, w, tc))
     y, ys = _empty(N, Hy, Wy, g.Cy, out_layout, x.device)
     d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=g.Cx, Cout=g.Cy, Th=g.kh, Tw=g.kw, in_sy=g.s, in_sx=g.s, tap_sy=1, tap_sx=1,
@@ -179,6 +193,7 @@ def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layo
     assert Cy == g.Cy, (Cy, g.Cy)
     Hx, Wx = x_hw
     tc = _tc_dgrad_ok(g, dy_layout)
+    dy = as_bf16(dy) if tc else _need_f32(dy)
     phase_packs = packs.get(("dgrad", tc) + g.key(), w, lambda: _pack_dgrad(g, w, tc))
     phases = _dgrad_phases(g)
     dx, xs = _empty(N, Hx, Wx, g.Cx, out_layout, dy.device)
@@ -212,6 +227,7 @@ def conv_wgrad(g: ConvGeom, x, x_layout, dy, dy_layout, dw: torch.Tensor, accumu
     _, Hy, Wy, Cy, ds = _dims(dy, dy_layout)
     assert Cx == g.Cx and Cy == g.Cy
     tc = _tc_wgrad_ok(g, x_layout, dy_layout)
+    x, dy = (as_bf16(x), as_bf16(dy)) if tc else (_need_f32(x), _need_f32(dy))
     Q = N * Hy * Wy
     splits = _wgrad_splits(g, Q, tc)
     K = g.kh * g.kw * g.Cx
@@ -253,14 +269,20 @@ class _ConvFn(torch.autograd.Function):
             ctx.sn = None
         scale = sig2[1:] if sig2 is not None else None
         if not transposed:
-            y = conv_forward(g, packs, w, x, x_layout, out_layout, bias, scale, relu)
+            fwd_tc, wgrad_tc = _tc_fwd_ok(g, x_layout), _tc_wgrad_ok(g, x_layout, out_layout)
+        else:
+            fwd_tc, wgrad_tc = _tc_dgrad_ok(g, x_layout), _tc_wgrad_ok(g, out_layout, x_layout)
+        x_op = as_bf16(x) if fwd_tc else x      # cast once; the bf16 copy is also what a tcgen05 weight gradient consumes
+        if not transposed:
+            y = conv_forward(g, packs, w, x_op, x_layout, out_layout, bias, scale, relu)
         else:
             assert bias is None and not relu
-            y = conv_dgrad(g, packs, w, x, x_layout, out_hw, out_layout, scale)
+            y = conv_dgrad(g, packs, w, x_op, x_layout, out_hw, out_layout, scale)
         ctx.g, ctx.packs, ctx.transposed = g, packs, transposed
         ctx.x_layout, ctx.out_layout, ctx.relu = x_layout, out_layout, relu
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.x_dims = _dims(x, x_layout)[:4]
+        ctx.save_for_backward(x_op if (fwd_tc and wgrad_tc) else x, w, y if relu else None)
         return y
 
     @staticmethod
@@ -272,18 +294,26 @@ class _ConvFn(torch.autograd.Function):
             dy = _lib.K.relu_bwd(dy, y)
         scale = ctx.sn[2][1:] if ctx.sn is not None else None
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not ctx.transposed:
+            dgrad_tc, wgrad_tc = _tc_dgrad_ok(g, ctx.out_layout), _tc_wgrad_ok(g, ctx.x_layout, ctx.out_layout)
+        else:
+            dgrad_tc, wgrad_tc = _tc_fwd_ok(g, ctx.out_layout), _tc_wgrad_ok(g, ctx.out_layout, ctx.x_layout)
+        dyb = as_bf16(dy) if ((need_dx and dgrad_tc) or (need_dw and wgrad_tc)) else None   # one cast for both GEMMs
+        if need_dx:
+            dy_op = dyb if dgrad_tc else dy
             if not ctx.transposed:
-                _, Hx, Wx, _, _ = _dims(x, ctx.x_layout)
-                dx = conv_dgrad(g, packs, w, dy, ctx.out_layout, (Hx, Wx), ctx.x_layout, scale)
+                _, Hx, Wx, _ = ctx.x_dims
+                dx = conv_dgrad(g, packs, w, dy_op, ctx.out_layout, (Hx, Wx), ctx.x_layout, scale)
             else:
-                dx = conv_forward(g, packs, w, dy, ctx.out_layout, ctx.x_layout, None, scale, False)
-        if ctx.needs_input_grad[1]:
+                dx = conv_forward(g, packs, w, dy_op, ctx.out_layout, ctx.x_layout, None, scale, False)
+        if need_dw:
             gw = torch.empty_like(w)
+            dy_op = dyb if wgrad_tc else dy
             if not ctx.transposed:
-                conv_wgrad(g, x, ctx.x_layout, dy, ctx.out_layout, gw)
+                conv_wgrad(g, x, ctx.x_layout, dy_op, ctx.out_layout, gw)
             else:
-                conv_wgrad(g, dy, ctx.out_layout, x, ctx.x_layout, gw)
+                conv_wgrad(g, dy_op, ctx.out_layout, x, ctx.x_layout, gw)
             if ctx.sn is not None:
                 u, v, sig2 = ctx.sn
                 dw = _lib.K.sn_grad(gw, w, u, v, sig2, w.shape[0], w[0].numel())
@@ -765,12 +795,13 @@ class _ConvLSTMFn(torch.autograd.Function):
                     _lib.K.add(dH[op:op + n], dh_rec, out=dH[op:op + n])
                 dc_next, n_next = dc_prev, n
             gw = torch.empty_like(w)
-            conv_wgrad(L.gx, xin, "cl", dpre, "cl", gw)
+            dpre_op = as_bf16(dpre) if _tc_dgrad_ok(L.gx, "cl") else dpre     # one cast for the three GEMMs below
+            conv_wgrad(L.gx, xin, "cl", dpre_op, "cl", gw)
             hprev = _lib.K.permute_rows(h_all.view(P, hw * hid), plan.hprev_src, hw * hid).view(P, H, W, hid)
-            conv_wgrad(L.gh, hprev, "cl", dpre, "cl", gw)
+            conv_wgrad(L.gh, hprev, "cl", dpre_op, "cl", gw)
             grads[2 * li] = gw
             grads[2 * li + 1] = _lib.K.colsum(dpre.view(P * hw, 4 * hid))
-            dxin = conv_dgrad(L.gx, L.packs, w, dpre, "cl", (H, W), "cl", None)
+            dxin = conv_dgrad(L.gx, L.packs, w, dpre_op, "cl", (H, W), "cl", None)
             dH = dxin
         dx = _lib.K.permute_rows(dH.view(P, hw * C0), plan.unpack_src, hw * C0).view(O, H, W, C0)
         return (dx, None, None) + tuple(grads)

@@ -1,10 +1,12 @@
 // conv_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM convolutions for sm_100a (K1/K2 forward-type, K3 weight gradient).
 //
 // Forward-type kernel (conv fwd, dgrad, ConvTranspose phases): one CTA computes a 128 x BN output tile.
-//   warps 0-3 : A producers — gather the im2col rows of the tile straight from the NHWC fp32 activation
-//               (coalesced 16-byte loads, zero fill for padding), convert to bf16 and store them into shared
-//               memory in the canonical K-major SWIZZLE_128B layout; afterwards they run the epilogue
-//               (tcgen05.ld from TMEM, scale / bias / ReLU, strided store).
+//   warps 0-3 : A producers — gather the im2col rows of the tile straight from the channel-last bf16 activation with
+//               16-byte cp.async (LDGSTS, zero fill for padding / tile tails) into the canonical K-major
+//               SWIZZLE_128B layout; completion is signalled on the stage's mbarrier by
+//               cp.async.mbarrier.arrive.noinc, so STAGES k-blocks are in flight per CTA and no register staging
+//               exists; afterwards the same warps run the epilogue (tcgen05.ld from TMEM, scale / bias / ReLU,
+//               strided fp32 or bf16 store, or raw fp32 partials when the K range is split over gridDim.z).
 //   warp 4    : B producer — TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) loads of the packed bf16 weight matrix.
 //   warp 5    : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM).
 //   smem ring : STAGES x (A 128x64 bf16 = 16 KB, B BNx64 bf16), mbarrier full/empty pairs, tcgen05.commit releases.
@@ -106,6 +108,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// 16-byte LDGSTS; src_bytes = 0 zero-fills the destination (padding taps, rows beyond M)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival when every cp.async issued so far by this thread has landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -125,11 +136,19 @@ struct SmemTail {            // lives after the operand ring
 // ------------------------------------------------------------------------------------------------------------
 // forward-type kernel
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_bf16x8(void* p, const float* o) {
+    uint4 u;
+    u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap, b200_conv_desc d,
-                                                           const float* __restrict__ in,
+                                                           const __nv_bfloat16* __restrict__ in,
                                                            const float* __restrict__ bias,
-                                                           const float* __restrict__ scale, float* __restrict__ out) {
+                                                           const float* __restrict__ scale, void* __restrict__ out_v,
+                                                           int out_bf16, float* __restrict__ split_ws,
+                                                           int kb_per_split) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
@@ -148,7 +167,9 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int cpb = d.Cin / BK;                     // channel blocks per tap
-    const int num_kb = d.Th * d.Tw * cpb;
+    const int num_kb_total = d.Th * d.Tw * cpb;
+    const int kb_begin = blockIdx.z * kb_per_split;
+    const int num_kb = (kb_begin + kb_per_split < num_kb_total ? kb_begin + kb_per_split : num_kb_total) - kb_begin;
 
     if (tid < BM) {
         int64_t m = m0 + tid;
@@ -175,7 +196,7 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
     if (warp == 5) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
-                mbar_init(smem_u32(&tail->full[s]), 128 + 1);
+                mbar_init(smem_u32(&tail->full[s]), 128 + 1);   // 128 cp.async completions + the TMA expect_tx arrival
                 mbar_init(smem_u32(&tail->empty[s]), 1);
             }
             mbar_init(smem_u32(&tail->tmem_full), 1);
@@ -191,71 +212,101 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
 
     if (warp < 4) {
         // ===================== A producers =====================
-        const int j = lane & 15;          // 16-byte fp32 chunk (4 channels) within the 64-channel block
-        const int rsub = lane >> 4;       // 2 rows per warp instruction
-        int tap = 0, cc = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        // 8 lanes cover one 128-byte row (64 channels); 16 rows per pass, 8 passes per k-block
+        const int j = tid & 7;
+        const int rg = tid >> 3;
+        int64_t rb[8];
+        int riy[8], rix[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int r = p * 16 + rg;
+            rb[p] = row_base[r];
+            riy[p] = row_iy[r];
+            rix[p] = row_ix[r];
+        }
+        const uint32_t dst_off = (uint32_t)rg * 128u + ((((uint32_t)j) ^ ((uint32_t)rg & 7u)) << 4);
+        int tap = kb_begin / cpb, cc = kb_begin - tap * cpb;
+        for (int i = 0; i < num_kb; ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
             mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
             const int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
             const int dy = tyy * d.tap_sy, dx = txx * d.tap_sx;
-            const int c0 = cc * BK + j * 4;
-            float4 v[16];
+            const int c0 = cc * BK + j * 8;
+            const uint32_t a_dst = smem_u32(smem_a + s * A_BYTES) + dst_off;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int r = warp * 32 + i * 2 + rsub;
-                const int iy = row_iy[r] + dy, ix = row_ix[r] + dx;
-                const int64_t base = row_base[r];
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (base >= 0 && iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi) {
-                    const float* p = in + base + (int64_t)(iy >> d.up_shift) * d.in_sh +
-                                     (int64_t)(ix >> d.up_shift) * d.in_sw + c0;
-                    v[i] = __ldg(reinterpret_cast<const float4*>(p));
-                }
+            for (int p = 0; p < 8; ++p) {
+                const int iy = riy[p] + dy, ix = rix[p] + dx;
+                const bool ok = rb[p] >= 0 && iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi;
+                const __nv_bfloat16* src = ok ? in + rb[p] + (int64_t)(iy >> d.up_shift) * d.in_sh +
+                                                    (int64_t)(ix >> d.up_shift) * d.in_sw + c0
+                                              : in;
+                cp_async16(a_dst + p * 2048, src, ok ? 16u : 0u);
             }
-            const uint32_t a_base = smem_u32(smem_a + s * A_BYTES);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int r = warp * 32 + i * 2 + rsub;
-                const uint32_t addr = a_base + r * 128 + ((((uint32_t)j >> 1) ^ ((uint32_t)r & 7u)) << 4) + (j & 1) * 8;
-                st_shared_v2(addr, pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
-            }
-            fence_proxy_async();
-            mbar_arrive(smem_u32(&tail->full[s]));
+            cp_async_arrive_noinc(smem_u32(&tail->full[s]));
             if (++cc == cpb) { cc = 0; ++tap; }
         }
         // ===================== epilogue =====================
         mbar_wait(smem_u32(&tail->tmem_full), 0);
         tc_fence_after();
         const int row = warp * 32 + lane;
-        const int64_t ro = row_out[row];
-        const float alpha = scale ? *scale : 1.f;
-        const bool vec = d.out_sc == 1 && ((d.out_sn | d.out_sh | d.out_sw) & 3) == 0 &&
-                         (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (d.Cout & 3) == 0;
+        if (gridDim.z > 1) {
+            // split-K: raw fp32 partials, [split][M][gridDim.y * BN]; conv_splitk_reduce_kernel applies the epilogue
+            const int64_t m = m0 + row;
+            const int ldo = gridDim.y * BN;
+            float* dst = split_ws + ((int64_t)blockIdx.z * M + m) * ldo + n0;
 #pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r);
-            if (ro >= 0) {
-                float o[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    int co = n0 + cb + e;
-                    float val = __uint_as_float(r[e]) * alpha + ((bias && co < d.Cout) ? bias[co] : 0.f);
-                    o[e] = d.relu ? fmaxf(val, 0.f) : val;
+            for (int cb = 0; cb < BN; cb += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r);
+                if (m < M) {
+                    float4* p = reinterpret_cast<float4*>(dst + cb);
+                    p[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+                    p[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+                    p[2] = make_float4(__uint_as_float(r[8]), __uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
+                    p[3] = make_float4(__uint_as_float(r[12]), __uint_as_float(r[13]), __uint_as_float(r[14]), __uint_as_float(r[15]));
                 }
-                if (vec && n0 + cb + 16 <= d.Cout) {
-                    float4* p = reinterpret_cast<float4*>(out + ro + n0 + cb);
-                    p[0] = make_float4(o[0], o[1], o[2], o[3]);
-                    p[1] = make_float4(o[4], o[5], o[6], o[7]);
-                    p[2] = make_float4(o[8], o[9], o[10], o[11]);
-                    p[3] = make_float4(o[12], o[13], o[14], o[15]);
-                } else {
+            }
+        } else {
+            const int64_t ro = row_out[row];
+            const float alpha = scale ? *scale : 1.f;
+            float* out = reinterpret_cast<float*>(out_v);
+            __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(out_v);
+            const bool vec = d.out_sc == 1 && (d.Cout & 7) == 0 &&
+                             (out_bf16 ? (((d.out_sn | d.out_sh | d.out_sw) & 7) == 0 && (reinterpret_cast<uintptr_t>(out_v) & 15) == 0)
+                                       : (((d.out_sn | d.out_sh | d.out_sw) & 3) == 0 && (reinterpret_cast<uintptr_t>(out_v) & 15) == 0));
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r);
+                if (ro >= 0) {
+                    float o[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         int co = n0 + cb + e;
-                        if (co < d.Cout) out[ro + (int64_t)co * d.out_sc] = o[e];
+                        float val = __uint_as_float(r[e]) * alpha + ((bias && co < d.Cout) ? bias[co] : 0.f);
+                        o[e] = d.relu ? fmaxf(val, 0.f) : val;
+                    }
+                    if (vec && n0 + cb + 16 <= d.Cout) {
+                        if (out_bf16) {
+                            st_bf16x8(outh + ro + n0 + cb, o);
+                            st_bf16x8(outh + ro + n0 + cb + 8, o + 8);
+                        } else {
+                            float4* p = reinterpret_cast<float4*>(out + ro + n0 + cb);
+                            p[0] = make_float4(o[0], o[1], o[2], o[3]);
+                            p[1] = make_float4(o[4], o[5], o[6], o[7]);
+                            p[2] = make_float4(o[8], o[9], o[10], o[11]);
+                            p[3] = make_float4(o[12], o[13], o[14], o[15]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            int co = n0 + cb + e;
+                            if (co < d.Cout) {
+                                if (out_bf16) outh[ro + (int64_t)co * d.out_sc] = __float2bfloat16_rn(o[e]);
+                                else out[ro + (int64_t)co * d.out_sc] = o[e];
+                            }
+                        }
                     }
                 }
             }
@@ -263,21 +314,21 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
     } else if (warp == 4) {
         // ===================== B producer (TMA) =====================
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
                 const uint32_t bar = smem_u32(&tail->full[s]);
                 mbar_arrive_expect_tx(bar, B_BYTES);
-                tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tmap, kb * BK, n0, bar);
+                tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tmap, (kb_begin + i) * BK, n0, bar);
             }
         }
     } else {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        for (int i = 0; i < num_kb; ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
             mbar_wait(smem_u32(&tail->full[s]), ph);
             tc_fence_after();
             if (lane == 0) {
@@ -285,9 +336,9 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
                 const uint64_t bdesc = make_desc(smem_u32(smem_b + s * B_BYTES), 16, 1024);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) != 0);
                 umma_commit(smem_u32(&tail->empty[s]));
-                if (kb == num_kb - 1) umma_commit(smem_u32(&tail->tmem_full));
+                if (i == num_kb - 1) umma_commit(smem_u32(&tail->tmem_full));
             }
             __syncwarp();
         }
@@ -295,6 +346,42 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// split-K second pass: out = epilogue( sum_z ws[z][m][co] ), fixed summation order
+__global__ void conv_splitk_reduce_kernel(b200_conv_desc d, const float* __restrict__ ws, int splits, int ldo,
+                                          const float* __restrict__ bias, const float* __restrict__ scale,
+                                          void* __restrict__ out_v, int out_bf16) {
+    const int64_t M = (int64_t)d.B * d.Qh * d.Qw;
+    const int C4 = (d.Cout + 3) >> 2;
+    const int64_t total = M * C4;
+    const float alpha = scale ? *scale : 1.f;
+    float* out = reinterpret_cast<float*>(out_v);
+    __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(out_v);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int co = (int)(t % C4) << 2;
+        const int64_t m = t / C4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < splits; ++z) {
+            float4 v = *reinterpret_cast<const float4*>(ws + ((int64_t)z * M + m) * ldo + co);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        int qx = (int)(m % d.Qw);
+        int qy = (int)((m / d.Qw) % d.Qh);
+        int64_t n = m / ((int64_t)d.Qw * d.Qh);
+        int oy = qy * d.out_sy + d.out_oy, ox = qx * d.out_sx + d.out_ox;
+        if (oy < 0 || oy >= d.Ho || ox < 0 || ox >= d.Wo) continue;
+        const int64_t ro = n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
+        float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (co + e >= d.Cout) break;
+            float v = o[e] * alpha + (bias ? bias[co + e] : 0.f);
+            if (d.relu) v = fmaxf(v, 0.f);
+            if (out_bf16) outh[ro + (int64_t)(co + e) * d.out_sc] = __float2bfloat16_rn(v);
+            else out[ro + (int64_t)(co + e) * d.out_sc] = v;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -306,9 +393,9 @@ struct PixInfo {
 };
 
 template <int BNW, int STAGES>
-__global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(b200_conv_desc d, const float* __restrict__ P,
-                                                            const float* __restrict__ G, float* __restrict__ ws,
-                                                            int64_t rows_per_split) {
+__global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(b200_conv_desc d, const __nv_bfloat16* __restrict__ P,
+                                                            const __nv_bfloat16* __restrict__ G,
+                                                            float* __restrict__ ws, int64_t rows_per_split) {
     constexpr int PA_BYTES = 2 * 64 * 128;            // 128 P channels x 64 pixels (two MN atoms)
     constexpr int GB_BYTES = (BNW / 64) * 64 * 128;   // BNW G channels x 64 pixels
     extern __shared__ uint8_t smem_raw[];
@@ -348,6 +435,19 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(b200_conv_desc d, co
     const uint32_t tmem_base = tail->tmem_base;
 
     if (warp < 4) {
+        // 16 lanes cover the 256 bytes (128 channels) of one pixel; 8 pixels per pass, 8 passes per 64-pixel k-block
+        const int j16 = tid & 15;
+        const int pg = tid >> 4;
+        const uint32_t p_dst_off = (uint32_t)(j16 >> 3) * 8192u + (uint32_t)pg * 128u + ((((uint32_t)j16 & 7u) ^ (uint32_t)pg) << 4);
+        const int pch = m0 + j16 * 8;             // first of this lane's 8 P channels
+        const bool p_ch_ok = pch < d.Cout;
+        // G tile: BNW == 128 -> same mapping; BNW == 64 -> 8 lanes per pixel, 16 pixels per pass, 4 passes
+        const int gj = BNW == 128 ? j16 : (tid & 7);
+        const int gpg = BNW == 128 ? pg : (tid >> 3);
+        const uint32_t g_dst_off = BNW == 128 ? p_dst_off
+                                              : ((uint32_t)gpg * 128u + ((((uint32_t)gj) ^ ((uint32_t)gpg & 7u)) << 4));
+        const int gch = c0 + gj * 8;
+        const bool g_ch_ok = gch < d.Cin;
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -373,66 +473,34 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(b200_conv_desc d, co
                 pi[tid] = info;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            // ---- P tile: 64 pixels x 128 channels; a warp instruction covers one pixel row (32 lanes x 4 channels)
             {
-                const int ch = lane * 4;
-                const int atom = lane >> 4, j = lane & 15;
-                float4 v[16];
+                const uint32_t a_dst = smem_u32(smem_a + s * PA_BYTES) + p_dst_off;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int prow = warp * 16 + i;
-                    const int64_t off = pi[prow].p_off;
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (off >= 0 && m0 + ch < d.Cout) v[i] = __ldg(reinterpret_cast<const float4*>(P + off + m0 + ch));
-                }
-                const uint32_t a_base = smem_u32(smem_a + s * PA_BYTES) + atom * 8192;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int prow = warp * 16 + i;
-                    const uint32_t addr = a_base + prow * 128 + ((((uint32_t)j >> 1) ^ ((uint32_t)prow & 7u)) << 4) + (j & 1) * 8;
-                    st_shared_v2(addr, pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+                for (int p = 0; p < 8; ++p) {
+                    const int64_t off = pi[p * 8 + pg].p_off;
+                    const bool ok = off >= 0 && p_ch_ok;
+                    cp_async16(a_dst + p * 1024, ok ? P + off + pch : P, ok ? 16u : 0u);
                 }
             }
-            // ---- G tile: 64 pixels x BNW channels
-            if (BNW == 128) {
-                const int ch = lane * 4;
-                const int atom = lane >> 4, j = lane & 15;
-                float4 v[16];
+            {
+                const uint32_t b_dst = smem_u32(smem_b + s * GB_BYTES) + g_dst_off;
+                if (BNW == 128) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int prow = warp * 16 + i;
-                    const int64_t off = pi[prow].g_off;
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (off >= 0 && c0 + ch < d.Cin) v[i] = __ldg(reinterpret_cast<const float4*>(G + off + c0 + ch));
-                }
-                const uint32_t b_base = smem_u32(smem_b + s * GB_BYTES) + atom * 8192;
+                    for (int p = 0; p < 8; ++p) {
+                        const int64_t off = pi[p * 8 + gpg].g_off;
+                        const bool ok = off >= 0 && g_ch_ok;
+                        cp_async16(b_dst + p * 1024, ok ? G + off + gch : G, ok ? 16u : 0u);
+                    }
+                } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int prow = warp * 16 + i;
-                    const uint32_t addr = b_base + prow * 128 + ((((uint32_t)j >> 1) ^ ((uint32_t)prow & 7u)) << 4) + (j & 1) * 8;
-                    st_shared_v2(addr, pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
-                }
-            } else {
-                const int j = lane & 15, rsub = lane >> 4;
-                const int ch = j * 4;
-                float4 v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int prow = warp * 16 + i * 2 + rsub;
-                    const int64_t off = pi[prow].g_off;
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (off >= 0 && c0 + ch < d.Cin) v[i] = __ldg(reinterpret_cast<const float4*>(G + off + c0 + ch));
-                }
-                const uint32_t b_base = smem_u32(smem_b + s * GB_BYTES);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int prow = warp * 16 + i * 2 + rsub;
-                    const uint32_t addr = b_base + prow * 128 + ((((uint32_t)j >> 1) ^ ((uint32_t)prow & 7u)) << 4) + (j & 1) * 8;
-                    st_shared_v2(addr, pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+                    for (int p = 0; p < 4; ++p) {
+                        const int64_t off = pi[p * 16 + gpg].g_off;
+                        const bool ok = off >= 0 && g_ch_ok;
+                        cp_async16(b_dst + p * 2048, ok ? G + off + gch : G, ok ? 16u : 0u);
+                    }
                 }
             }
-            fence_proxy_async();
-            mbar_arrive(smem_u32(&tail->full[s]));
+            cp_async_arrive_noinc(smem_u32(&tail->full[s]));
         }
         // ---- epilogue: TMEM lane = P channel m, column = G channel c
         const int64_t Kt = (int64_t)d.Th * d.Tw * d.Cin;
@@ -453,9 +521,17 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(b200_conv_desc d, co
             }
             if (m < d.Cout) {
                 float* p = dst + (int64_t)m * Kt + (int64_t)tap * d.Cin + c0 + cb;
+                if (c0 + cb + 16 <= d.Cin && ((Kt | d.Cin) & 3) == 0) {
+                    float4* p4 = reinterpret_cast<float4*>(p);
+                    p4[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+                    p4[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+                    p4[2] = make_float4(__uint_as_float(r[8]), __uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
+                    p4[3] = make_float4(__uint_as_float(r[12]), __uint_as_float(r[13]), __uint_as_float(r[14]), __uint_as_float(r[15]));
+                } else {
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    if (c0 + cb + e < d.Cin) p[e] = __uint_as_float(r[e]);
+                    for (int e = 0; e < 16; ++e)
+                        if (c0 + cb + e < d.Cin) p[e] = __uint_as_float(r[e]);
+                }
             }
         }
     } else if (warp == 5) {
@@ -504,8 +580,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 template <int BN, int STAGES>
-static int launch_fwd(const b200_conv_desc* d, const float* in, const void* wmat, const float* bias,
-                      const float* scale, float* out, cudaStream_t st) {
+static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const void* wmat, const float* bias,
+                      const float* scale, void* out, int out_bf16, float* split_ws, int splits, cudaStream_t st) {
     EncodeTiledFn enc = get_encode_fn();
     B200_REQUIRE(enc != nullptr, "conv_gemm_tc: cuTensorMapEncodeTiled unavailable");
     int64_t M = (int64_t)d->B * d->Qh * d->Qw;
@@ -527,14 +603,23 @@ static int launch_fwd(const b200_conv_desc* d, const float* in, const void* wmat
         B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles);
-    kern<<<grid, 192, smem_bytes, st>>>(tmap, *d, in, bias, scale, out);
+    const int num_kb = d->Th * d->Tw * (d->Cin / BK);
+    int kbps = (num_kb + splits - 1) / splits;
+    splits = (num_kb + kbps - 1) / kbps;          // no empty split
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles, (unsigned)splits);
+    kern<<<grid, 192, smem_bytes, st>>>(tmap, *d, in, bias, scale, out, out_bf16, split_ws, kbps);
     B200_CHECK_LAUNCH();
+    if (splits > 1) {
+        int64_t total = M * ((d->Cout + 3) / 4);
+        conv_splitk_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(*d, split_ws, splits, ntiles * BN, bias, scale,
+                                                                        out, out_bf16);
+        B200_CHECK_LAUNCH();
+    }
     return 0;
 }
 
 template <int BNW, int STAGES>
-static int launch_wgrad(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+static int launch_wgrad(const b200_conv_desc* d, const __nv_bfloat16* P, const __nv_bfloat16* G, float* ws, int splits,
                         cudaStream_t st) {
     int64_t Q = (int64_t)d->B * d->Qh * d->Qw;
     int64_t rps = (Q + splits - 1) / splits;
@@ -556,6 +641,16 @@ static int launch_wgrad(const b200_conv_desc* d, const float* P, const float* G,
     return 0;
 }
 
+__global__ void cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int64_t n4) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = x[t];
+        uint2 u;
+        u.x = pack_bf16(v.x, v.y);
+        u.y = pack_bf16(v.z, v.w);
+        y[t] = u;
+    }
+}
+
 }  // namespace tc
 }  // namespace b200
 
@@ -563,31 +658,60 @@ using namespace b200;
 
 extern "C" int b200_conv_tc_ntile(int Cout) { return Cout >= 128 ? 128 : (Cout >= 64 ? 64 : 16); }
 
-extern "C" int b200_conv_gemm_tc(const b200_conv_desc* d, const float* in, const void* wmat_bf16, const float* bias,
-                                 const float* scale, float* out, b200_stream_t stream) {
+/* split-K plan: enough CTAs to fill the 148 SMs twice when the output tile grid alone cannot */
+extern "C" int b200_conv_tc_splits(const b200_conv_desc* d) {
+    int64_t M = (int64_t)d->B * d->Qh * d->Qw;
+    int bn = b200_conv_tc_ntile(d->Cout);
+    int64_t tiles = ((M + 127) / 128) * ((d->Cout + bn - 1) / bn);
+    int num_kb = d->Th * d->Tw * (d->Cin / 64);
+    if (tiles >= 148 || num_kb < 8) return 1;
+    int64_t s = (296 + tiles - 1) / tiles;
+    if (s > num_kb / 4) s = num_kb / 4;
+    if (s > 32) s = 32;
+    return s < 1 ? 1 : (int)s;
+}
+
+extern "C" int b200_cast_bf16(const float* x, void* y, int64_t n, b200_stream_t stream) {
+    if (n == 0) return 0;
+    B200_REQUIRE(n % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
+                 "cast_bf16: needs n %% 4 == 0 and aligned pointers");
+    tc::cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), n / 4);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_conv_gemm_tc(const b200_conv_desc* d, const void* in_bf16, const void* wmat_bf16, const float* bias,
+                                 const float* scale, void* out, int out_bf16, float* split_ws, int splits,
+                                 b200_stream_t stream) {
     int64_t M = (int64_t)d->B * d->Qh * d->Qw;
     if (M == 0 || d->Cout == 0) return 0;
     B200_REQUIRE(d->Cin % 64 == 0 && d->in_sc == 1, "conv_gemm_tc: needs Cin %% 64 == 0 and channel-last input");
-    B200_REQUIRE(((d->in_sn | d->in_sh | d->in_sw) & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0,
+    B200_REQUIRE(((d->in_sn | d->in_sh | d->in_sw) & 7) == 0 && (reinterpret_cast<uintptr_t>(in_bf16) & 15) == 0,
                  "conv_gemm_tc: input rows must be 16-byte aligned");
     B200_REQUIRE(d->ldw % 64 == 0 && d->ldw >= (int64_t)d->Th * d->Tw * d->Cin, "conv_gemm_tc: bad ldw");
     B200_REQUIRE((reinterpret_cast<uintptr_t>(wmat_bf16) & 15) == 0, "conv_gemm_tc: wmat must be 16-byte aligned");
+    B200_REQUIRE(splits >= 1 && (splits == 1 || split_ws != nullptr), "conv_gemm_tc: split-K needs a workspace");
+    B200_REQUIRE(splits == 1 || (reinterpret_cast<uintptr_t>(split_ws) & 15) == 0, "conv_gemm_tc: unaligned workspace");
     cudaStream_t st = as_stream(stream);
+    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(in_bf16);
     int bn = b200_conv_tc_ntile(d->Cout);
-    if (bn == 128) return tc::launch_fwd<128, 3>(d, in, wmat_bf16, bias, scale, out, st);
-    if (bn == 64) return tc::launch_fwd<64, 4>(d, in, wmat_bf16, bias, scale, out, st);
-    return tc::launch_fwd<16, 4>(d, in, wmat_bf16, bias, scale, out, st);
+    if (bn == 128) return tc::launch_fwd<128, 3>(d, in, wmat_bf16, bias, scale, out, out_bf16, split_ws, splits, st);
+    if (bn == 64) return tc::launch_fwd<64, 4>(d, in, wmat_bf16, bias, scale, out, out_bf16, split_ws, splits, st);
+    return tc::launch_fwd<16, 4>(d, in, wmat_bf16, bias, scale, out, out_bf16, split_ws, splits, st);
 }
 
-extern "C" int b200_wgrad_gemm_tc(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+extern "C" int b200_wgrad_gemm_tc(const b200_conv_desc* d, const void* P_bf16, const void* G_bf16, float* ws, int splits,
                                   b200_stream_t stream) {
     B200_REQUIRE(splits >= 1, "wgrad_gemm_tc: bad splits");
     B200_REQUIRE(d->Cin % 64 == 0 && d->in_sc == 1 && d->Cout % 64 == 0 && d->out_sc == 1,
                  "wgrad_gemm_tc: needs channel-last operands with channels %% 64 == 0");
-    B200_REQUIRE(((d->in_sn | d->in_sh | d->in_sw | d->out_sn | d->out_sh | d->out_sw) & 3) == 0 &&
-                     (reinterpret_cast<uintptr_t>(P) & 15) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0,
+    B200_REQUIRE(((d->in_sn | d->in_sh | d->in_sw | d->out_sn | d->out_sh | d->out_sw) & 7) == 0 &&
+                     (reinterpret_cast<uintptr_t>(P_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(G_bf16) & 15) == 0,
                  "wgrad_gemm_tc: operand rows must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
+    const __nv_bfloat16* P = reinterpret_cast<const __nv_bfloat16*>(P_bf16);
+    const __nv_bfloat16* G = reinterpret_cast<const __nv_bfloat16*>(G_bf16);
     if (d->Cin >= 128) return tc::launch_wgrad<128, 3>(d, P, G, ws, splits, st);
     return tc::launch_wgrad<64, 4>(d, P, G, ws, splits, st);
 }

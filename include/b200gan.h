@@ -82,12 +82,20 @@ typedef struct {
 /* fp32 CUDA-core path (bit-tight parity mode). wmat fp32 [Cout][ldw]. */
 int b200_conv_gemm_f32(const b200_conv_desc* d, const float* in, const float* wmat, const float* bias,
                        const float* scale, float* out, b200_stream_t stream);
-/* tcgen05 path: bf16 operands (activations converted on the fly), fp32 accumulate in TMEM.
- * wmat bf16 [Cout_pad][ldw] with Cout_pad a multiple of the N tile (b200_conv_tc_ntile), ldw a multiple of 64,
- * zero padded; requires Cin % 64 == 0 and in_sc == 1. */
-int b200_conv_gemm_tc(const b200_conv_desc* d, const float* in, const void* wmat_bf16, const float* bias,
-                      const float* scale, float* out, b200_stream_t stream);
+/* tcgen05 path: bf16 operands, fp32 accumulate in TMEM.  `in_bf16` is the channel-last activation stored as bf16
+ * (b200_cast_bf16 produces it from an fp32 tensor); the descriptor's input strides are in bf16 elements and must be
+ * multiples of 8 (16-byte rows).  wmat bf16 [Cout_pad][ldw] with Cout_pad a multiple of the N tile
+ * (b200_conv_tc_ntile), ldw a multiple of 64, zero padded; requires Cin % 64 == 0 and in_sc == 1.
+ * out is fp32 (out_bf16 = 0) or bf16 (out_bf16 = 1) with the descriptor's output strides in elements of that type.
+ * splits > 1 divides the K range (taps x channel blocks) over gridDim.z: partial sums go to split_ws
+ * (splits * M * Cout_pad floats, caller-owned) and a second kernel reduces them in fixed order and applies the
+ * epilogue; b200_conv_tc_splits returns the library's choice for a descriptor (1 = no split). */
+int b200_conv_gemm_tc(const b200_conv_desc* d, const void* in_bf16, const void* wmat_bf16, const float* bias,
+                      const float* scale, void* out, int out_bf16, float* split_ws, int splits, b200_stream_t stream);
 int b200_conv_tc_ntile(int Cout);
+int b200_conv_tc_splits(const b200_conv_desc* d);
+/* y[i] = bf16(x[i]) (round to nearest even), n % 4 == 0 */
+int b200_cast_bf16(const float* x, void* y_bf16, int64_t n, b200_stream_t stream);
 
 /* Weight-gradient gather-GEMM:  R[m, (ty*Tw+tx)*Cg + c] = sum_{n,qy,qx} P[n,qy,qx,m] * G[n, gather(qy,qx,ty,tx), c]
  * where `d` describes the gather of G exactly as above (d->Cin = Cg) and P is addressed with d's out_* fields
@@ -95,7 +103,8 @@ int b200_conv_tc_ntile(int Cout);
  * ws ([splits][Cout][Th*Tw*Cin] fp32); b200_wgrad_reduce sums them in fixed order into the parameter layout. */
 int b200_wgrad_gemm_f32(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
                         b200_stream_t stream);
-int b200_wgrad_gemm_tc(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+/* tcgen05 variant: P and G are bf16 channel-last tensors (strides in bf16 elements, multiples of 8) */
+int b200_wgrad_gemm_tc(const b200_conv_desc* d, const void* P_bf16, const void* G_bf16, float* ws, int splits,
                        b200_stream_t stream);
 /* dst[m*s_m + ty*s_ty + tx*s_tx + c*s_c] (=|+=) alpha * sum_s ws[s*split_stride + m*Th*Tw*C + (ty*Tw+tx)*C + c];
  * alpha = *scale or 1; split_stride = elements between consecutive partial results (rows_total*Th*Tw*C), so a row

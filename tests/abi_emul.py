@@ -125,9 +125,14 @@ class EmulKernels:
         ok = ok[None].expand(d.B, -1, -1).reshape(-1)
         return off, ok
 
+    def cast_bf16(self, x):
+        self.launches += 1
+        return x.to(torch.bfloat16)
+
     def conv_gemm(self, d, inp, wmat, bias, scale, out, tc):
         self.launches += 1
-        A = self._gather(d, inp)
+        assert (inp.dtype == torch.bfloat16) == bool(tc), "tcgen05 path takes bf16 operands, the fp32 path fp32"
+        A = self._gather(d, inp.float() if tc else inp)
         K = d.Th * d.Tw * d.Cin
         Wm = wmat.float()[:d.Cout, :K]
         A2 = A.reshape(A.shape[0], K)
@@ -148,6 +153,9 @@ class EmulKernels:
 
     def wgrad_gemm(self, d, P, G, ws, splits, tc):
         self.launches += 1
+        assert (P.dtype == torch.bfloat16) == bool(tc) and (G.dtype == torch.bfloat16) == bool(tc)
+        if tc:
+            P, G = P.float(), G.float()
         A = self._gather(d, G)                                   # (Q, T, Cin)
         off, ok = self._out_index(d)
         flatP = torch.as_strided(P, (P.untyped_storage().nbytes() // 4 - P.storage_offset(),), (1,), P.storage_offset())
