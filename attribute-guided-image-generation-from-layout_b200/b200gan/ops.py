@@ -214,10 +214,14 @@ def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layo
     return dx
 
 
-def _wgrad_splits(g: ConvGeom, Q: int, tc: bool) -> int:
-    tm, tn = (128, 128 if g.Cx >= 128 else 64) if tc else (64, 64)
-    tiles = -(-g.Cy // tm) * g.kh * g.kw * -(-g.Cx // tn)
-    splits = max(1, min(-(-592 // tiles), max(1, Q // 256), 64))
+def _wgrad_splits(g: ConvGeom, Q: int, tc: bool, rows=None, cols=None) -> int:
+    if tc:
+        tiles = -(-g.Cy // 128) * g.kh * g.kw * -(-g.Cx // (128 if g.Cx >= 128 else 64))
+    elif rows is not None:          # flattened (tap, channel) column tiles of the skinny-operand kernel
+        tiles = -(-rows // 64) * -(-cols // 64)
+    else:
+        tiles = -(-g.Cy // 64) * g.kh * g.kw * -(-g.Cx // 64)
+    splits = max(1, min(-(-592 // tiles), max(1, Q // 256), 256 if rows is not None else 64))
     return splits
 
 
@@ -228,16 +232,32 @@ def conv_wgrad(g: ConvGeom, x, x_layout, dy, dy_layout, dw: torch.Tensor, accumu
     assert Cx == g.Cx and Cy == g.Cy
     tc = _tc_wgrad_ok(g, x_layout, dy_layout)
     x, dy = (as_bf16(x), as_bf16(dy)) if tc else (_need_f32(x), _need_f32(dy))
+    kk = g.kh * g.kw
+    if not tc and g.Cy <= 8 and g.Cx > 8 and g.s == 1:
+        # skinny OUTPUT side (the 64->3 image convolutions): swap the roles so the 3-channel tensor is the gathered,
+        # tap-flattened operand:  dW[co,c,ky,kx] = sum_{q'} X[q'][c] * dY[q' - (ky,kx) + p][co]
+        Q = N * Hx * Wx
+        K = kk * g.Cy
+        splits = _wgrad_splits(g, Q, False, rows=g.Cx, cols=K)
+        ws = torch.empty((splits * g.Cx * K,), dtype=torch.float32, device=x.device)
+        d = ConvDesc(B=N, Qh=Hx, Qw=Wx, Cin=g.Cy, Cout=g.Cx, Th=g.kh, Tw=g.kw, in_sy=1, in_sx=1, tap_sy=-1, tap_sx=-1,
+                     tap_oy=g.p, tap_ox=g.p, Hi=Hy, Wi=Wy, up_shift=0, in_sn=ds[0], in_sh=ds[1], in_sw=ds[2], in_sc=ds[3],
+                     out_sy=1, out_sx=1, out_oy=0, out_ox=0, Ho=Hx, Wo=Wx, out_sn=xs[0], out_sh=xs[1], out_sw=xs[2],
+                     out_sc=xs[3], ldw=K, relu=0)
+        _lib.K.wgrad_gemm(d, x, dy, ws, splits, False)
+        # ws rows = input channel c, columns = (ky, kx, co)  ->  dw[co, cx_offset + c, ky, kx]
+        _lib.K.wgrad_reduce(ws, splits, g.Cx, g.kh, g.kw, g.Cy, dw, g.cx_offset * kk, kk, g.kw, 1, g.cx_total * kk,
+                            accumulate=accumulate)
+        return dw
     Q = N * Hy * Wy
-    splits = _wgrad_splits(g, Q, tc)
-    K = g.kh * g.kw * g.Cx
+    K = kk * g.Cx
+    splits = _wgrad_splits(g, Q, tc, rows=(g.Cy if (not tc and g.Cx <= 8) else None), cols=K)
     ws = torch.empty((splits * g.Cy * K,), dtype=torch.float32, device=x.device)
     d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=g.Cx, Cout=g.Cy, Th=g.kh, Tw=g.kw, in_sy=g.s, in_sx=g.s, tap_sy=1, tap_sx=1,
                  tap_oy=-g.p, tap_ox=-g.p, Hi=Hx, Wi=Wx, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3],
                  out_sy=1, out_sx=1, out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ds[0], out_sh=ds[1], out_sw=ds[2],
                  out_sc=ds[3], ldw=K, relu=0)
     _lib.K.wgrad_gemm(d, dy, x, ws, splits, tc)
-    kk = g.kh * g.kw
     _lib.K.wgrad_reduce(ws, splits, g.Cy, g.kh, g.kw, g.Cx, dw, g.cx_offset * kk, g.cx_total * kk, g.kw, 1, kk,
                         accumulate=accumulate)
     return dw

@@ -228,6 +228,107 @@ __global__ void __launch_bounds__(256) wgrad_gemm_f32_kernel(b200_conv_desc d, c
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// weight-gradient for a skinny gathered operand (Cin <= 8: the 3-channel image / crop side).  The 64-wide column tile
+// runs over the flattened (tap, channel) index instead of one tap's channels, so a 7x7x3 layer needs 3 column tiles
+// instead of 49 nearly empty ones.  grid: (ceil(Cout/64), ceil(Th*Tw*Cin/64), splits)
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wgrad_gemm_f32_flatk_kernel(b200_conv_desc d, const float* __restrict__ P,
+                                                                   const float* __restrict__ G, float* __restrict__ ws,
+                                                                   int64_t rows_per_split) {
+    __shared__ __align__(16) float Ps[BK][BM + 4];
+    __shared__ __align__(16) float Gs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int64_t Q = (int64_t)d.B * d.Qh * d.Qw;
+    const int Kt = d.Th * d.Tw * d.Cin;
+    const int k0 = blockIdx.y * BN;
+    const int m0 = blockIdx.x * BM;
+    const int64_t q_begin = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t q_end = q_begin + rows_per_split < Q ? q_begin + rows_per_split : Q;
+
+    const int lq = tid >> 4;
+    const int lc = (tid & 15) * 4;
+    const int ty = tid >> 4, tx = tid & 15;
+    // this thread's 4 gathered columns: (tap offset, channel offset), fixed over the pixel loop
+    int goy[4], gox[4];
+    int64_t gco[4];
+    bool gok[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        int k = k0 + lc + e;
+        gok[e] = k < Kt;
+        int tap = gok[e] ? k / d.Cin : 0;
+        int c = gok[e] ? k - tap * d.Cin : 0;
+        int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
+        goy[e] = d.tap_oy + tyy * d.tap_sy;
+        gox[e] = d.tap_ox + txx * d.tap_sx;
+        gco[e] = (int64_t)c * d.in_sc;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int64_t q0 = q_begin; q0 < q_end; q0 += BK) {
+        int64_t q = q0 + lq;
+        float p[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (q < q_end) {
+            int qx = (int)(q % d.Qw);
+            int qy = (int)((q / d.Qw) % d.Qh);
+            int64_t n = q / ((int64_t)d.Qw * d.Qh);
+            int oy = qy * d.out_sy + d.out_oy, ox = qx * d.out_sx + d.out_ox;
+            if (oy >= 0 && oy < d.Ho && ox >= 0 && ox < d.Wo) {
+                const float* pp = P + n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
+                if (d.out_sc == 1 && m0 + lc + 3 < d.Cout && ((d.out_sn | d.out_sh | d.out_sw) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(P) & 15) == 0) {
+                    float4 v = *reinterpret_cast<const float4*>(pp + m0 + lc);
+                    p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (m0 + lc + e < d.Cout) p[e] = pp[(int64_t)(m0 + lc + e) * d.out_sc];
+                }
+            }
+            const float* gb = G + n * d.in_sn;
+            const int by = qy * d.in_sy, bx = qx * d.in_sx;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int iy = by + goy[e], ix = bx + gox[e];
+                if (gok[e] && iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi)
+                    g[e] = __ldg(gb + (int64_t)(iy >> d.up_shift) * d.in_sh + (int64_t)(ix >> d.up_shift) * d.in_sw + gco[e]);
+            }
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&Ps[lq][lc]) = make_float4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<float4*>(&Gs[lq][lc]) = make_float4(g[0], g[1], g[2], g[3]);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 av = *reinterpret_cast<const float4*>(&Ps[kk][ty * 4]);
+            float4 bv = *reinterpret_cast<const float4*>(&Gs[kk][tx * 4]);
+            float ar[4] = {av.x, av.y, av.z, av.w};
+            float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+    }
+    float* dst = ws + (int64_t)blockIdx.z * d.Cout * Kt;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m >= d.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = k0 + tx * 4 + j;
+            if (k >= Kt) continue;
+            dst[(int64_t)m * Kt + k] = acc[i][j];
+        }
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -256,6 +357,12 @@ extern "C" int b200_wgrad_gemm_f32(const b200_conv_desc* d, const float* P, cons
     int64_t rps = (Q + splits - 1) / splits;
     rps = (rps + BK - 1) / BK * BK;
     if (rps < BK) rps = BK;
+    if (d->Cin <= 8) {
+        dim3 grid((unsigned)((d->Cout + BM - 1) / BM), (unsigned)((d->Th * d->Tw * d->Cin + BN - 1) / BN), (unsigned)splits);
+        wgrad_gemm_f32_flatk_kernel<<<grid, 256, 0, as_stream(stream)>>>(*d, P, G, ws, rps);
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
     int ctiles = (d->Cin + BN - 1) / BN;
     dim3 grid((unsigned)((d->Cout + BM - 1) / BM), (unsigned)(d->Th * d->Tw * ctiles), (unsigned)splits);
     B200_REQUIRE(grid.y < 65536, "wgrad_gemm_f32: too many tap tiles");

@@ -36,34 +36,52 @@ __global__ void add_kernel(const float4* __restrict__ a, const float4* __restric
     if (blockIdx.x == 0 && threadIdx.x < tail) ot[threadIdx.x] = at[threadIdx.x] + bt[threadIdx.x];
 }
 
-// y[n,qy,qx,c] = scale * sum_{dy,dx<f} x[n,qy*f+dy,qx*f+dx,c]
+// y[n,qy,qx,c] = scale * sum_{dy,dx<f} x[n,qy*f+dy,qx*f+dx,c];  V = channels per thread (4 when C % 4 == 0)
+template <int V>
 __global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int f,
                                 float scale) {
-    int Ho = H / f, Wo = W / f;
-    int64_t total = (int64_t)N * Ho * Wo * C;
+    const int Ho = H / f, Wo = W / f, Cv = C / V;
+    const int64_t total = (int64_t)N * Ho * Wo * Cv;
     GRID_STRIDE(t, total) {
-        int c = (int)(t % C);
-        int qx = (int)((t / C) % Wo);
-        int qy = (int)((t / ((int64_t)C * Wo)) % Ho);
-        int n = (int)(t / ((int64_t)C * Wo * Ho));
+        const int c = (int)(t % Cv) * V;
+        const int qx = (int)((t / Cv) % Wo);
+        const int qy = (int)((t / ((int64_t)Cv * Wo)) % Ho);
+        const int n = (int)(t / ((int64_t)Cv * Wo * Ho));
         const float* p = x + (((int64_t)n * H + (int64_t)qy * f) * W + (int64_t)qx * f) * C + c;
-        float acc = 0.f;
-        for (int dy = 0; dy < f; ++dy)
-            for (int dx = 0; dx < f; ++dx) acc += p[((int64_t)dy * W + dx) * C];
-        y[t] = acc * scale;
+        if (V == 4) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int dy = 0; dy < f; ++dy)
+                for (int dx = 0; dx < f; ++dx) {
+                    const float4 v = *reinterpret_cast<const float4*>(p + ((int64_t)dy * W + dx) * C);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            *reinterpret_cast<float4*>(y + t * 4) = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+        } else {
+            float acc = 0.f;
+            for (int dy = 0; dy < f; ++dy)
+                for (int dx = 0; dx < f; ++dx) acc += p[((int64_t)dy * W + dx) * C];
+            y[t] = acc * scale;
+        }
     }
 }
 
+template <int V>
 __global__ void unpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int f,
                                   float scale) {
-    int Ho = H * f, Wo = W * f;
-    int64_t total = (int64_t)N * Ho * Wo * C;
+    const int Ho = H * f, Wo = W * f, Cv = C / V;
+    const int64_t total = (int64_t)N * Ho * Wo * Cv;
     GRID_STRIDE(t, total) {
-        int c = (int)(t % C);
-        int ox = (int)((t / C) % Wo);
-        int oy = (int)((t / ((int64_t)C * Wo)) % Ho);
-        int n = (int)(t / ((int64_t)C * Wo * Ho));
-        y[t] = scale * x[(((int64_t)n * H + oy / f) * W + ox / f) * C + c];
+        const int c = (int)(t % Cv) * V;
+        const int ox = (int)((t / Cv) % Wo);
+        const int oy = (int)((t / ((int64_t)Cv * Wo)) % Ho);
+        const int n = (int)(t / ((int64_t)Cv * Wo * Ho));
+        const float* p = x + (((int64_t)n * H + oy / f) * W + ox / f) * C + c;
+        if (V == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(p);
+            *reinterpret_cast<float4*>(y + t * 4) = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+        } else {
+            y[t] = scale * p[0];
+        }
     }
 }
 
@@ -138,16 +156,22 @@ __global__ void permute_rows_kernel(const float4* __restrict__ x, const int32_t*
 
 __global__ void mask_outer_fwd_kernel(const float* __restrict__ v, const float* __restrict__ mask,
                                       float* __restrict__ out, int O, int H, int W, int C) {
-    int Hp = H + 2, Wp = W + 2;
-    int64_t total = (int64_t)O * Hp * Wp * C;
+    const int Hp = H + 2, Wp = W + 2, C4 = C >> 2;
+    const int64_t total = (int64_t)O * Hp * Wp * C4;
     GRID_STRIDE(t, total) {
-        int c = (int)(t % C);
-        int x = (int)((t / C) % Wp);
-        int y = (int)((t / ((int64_t)C * Wp)) % Hp);
-        int o = (int)(t / ((int64_t)C * Wp * Hp));
-        float r = 0.f;
-        if (y >= 1 && y <= H && x >= 1 && x <= W) r = mask[((int64_t)o * H + (y - 1)) * W + (x - 1)] * v[(int64_t)o * C + c];
-        out[t] = r;
+        const int c = (int)(t % C4) << 2;
+        const int x = (int)((t / C4) % Wp);
+        const int y = (int)((t / ((int64_t)C4 * Wp)) % Hp);
+        const int o = (int)(t / ((int64_t)C4 * Wp * Hp));
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 1 && y <= H && x >= 1 && x <= W) {
+            const float m = mask[((int64_t)o * H + (y - 1)) * W + (x - 1)];
+            if (m != 0.f) {
+                const float4 q = *reinterpret_cast<const float4*>(v + (int64_t)o * C + c);
+                r = make_float4(m * q.x, m * q.y, m * q.z, m * q.w);
+            }
+        }
+        *reinterpret_cast<float4*>(out + t * 4) = r;
     }
 }
 
@@ -248,12 +272,15 @@ __global__ void colsum_partial_kernel(const float* __restrict__ x, int64_t rows,
         ws[(int64_t)blockIdx.x * C + c] = s;
     }
 }
+// one warp per column: lanes stride over the chunks, fixed-order shuffle tree
 __global__ void colsum_final_kernel(const double* __restrict__ ws, int nchunks, int C, float* __restrict__ out) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
+    int lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int k = 0; k < nchunks; ++k) s += ws[(int64_t)k * C + c];
-    out[c] = (float)s;
+    for (int k = lane; k < nchunks; k += 32) s += ws[(int64_t)k * C + c];
+    s = warp_sum(s);
+    if (lane == 0) out[c] = (float)s;
 }
 
 __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restrict__ dst, int dst_bf16, int M, int Mpad,
@@ -365,7 +392,10 @@ extern "C" int b200_pool_fwd(const float* x, float* y, int N, int H, int W, int 
     B200_REQUIRE(f >= 1 && H % f == 0 && W % f == 0, "pool_fwd: H=%d W=%d not divisible by f=%d", H, W, f);
     int64_t total = (int64_t)N * (H / f) * (W / f) * C;
     if (total == 0) return 0;
-    pool_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
+    if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+        pool_fwd_kernel<4><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
+    else
+        pool_fwd_kernel<1><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -374,7 +404,10 @@ extern "C" int b200_unpool_fwd(const float* x, float* y, int N, int H, int W, in
                                b200_stream_t stream) {
     int64_t total = (int64_t)N * H * f * W * f * C;
     if (total == 0) return 0;
-    unpool_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
+    if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+        unpool_fwd_kernel<4><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
+    else
+        unpool_fwd_kernel<1><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -427,7 +460,8 @@ extern "C" int b200_permute_rows(const float* x, const int32_t* src_row, float* 
 extern "C" int b200_mask_outer_fwd(const float* v, const float* mask, float* out, int O, int H, int W, int C,
                                    b200_stream_t stream) {
     if (O == 0) return 0;
-    int64_t total = (int64_t)O * (H + 2) * (W + 2) * C;
+    B200_REQUIRE(C % 4 == 0, "mask_outer_fwd: C=%d must be a multiple of 4", C);
+    int64_t total = (int64_t)O * (H + 2) * (W + 2) * (C / 4);
     mask_outer_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(v, mask, out, O, H, W, C);
     B200_CHECK_LAUNCH();
     return 0;
@@ -495,7 +529,7 @@ extern "C" int b200_colsum(const float* x, int64_t rows, int C, float* out, doub
     dim3 grid(nchunks, (C + 31) / 32), block(32, 8);
     colsum_partial_kernel<<<grid, block, 0, as_stream(stream)>>>(x, rows, C, rpc, ws);
     B200_CHECK_LAUNCH();
-    colsum_final_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(ws, nchunks, C, out);
+    colsum_final_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, nchunks, C, out);
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -35,12 +35,17 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ x, int64_t row
     }
 }
 
+// one warp per channel: lanes stride over the chunks, fixed-order shuffle tree (deterministic)
 __global__ void bn_stats_final_kernel(const double* __restrict__ ws, int nchunks, int C, int64_t rows, float* mean,
                                       float* var, float* running_mean, float* running_var, float momentum) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
+    int lane = threadIdx.x & 31;
     double s1 = 0.0, s2 = 0.0;
-    for (int k = 0; k < nchunks; ++k) { s1 += ws[((int64_t)k * C + c) * 2]; s2 += ws[((int64_t)k * C + c) * 2 + 1]; }
+    for (int k = lane; k < nchunks; k += 32) { s1 += ws[((int64_t)k * C + c) * 2]; s2 += ws[((int64_t)k * C + c) * 2 + 1]; }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane != 0) return;
     double m = s1 / (double)rows;
     double v = s2 / (double)rows - m * m;
     if (v < 0.0) v = 0.0;
@@ -135,28 +140,32 @@ __global__ void norm_bwd_reduce_kernel(const float* __restrict__ dy, const float
     }
 }
 
-// stage 2: s[c] = (sum dxhat, sum dxhat*xhat); parameter gradients
+// stage 2: s[c] = (sum dxhat, sum dxhat*xhat); parameter gradients.  One warp per channel, fixed-order shuffle tree.
 __global__ void norm_bwd_finalize_kernel(const double* __restrict__ seg, int nseg, int C, int mode,
                                          const float* __restrict__ gamma, const int32_t* __restrict__ idx, float* s,
                                          float* dgamma, float* dbeta) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
+    int lane = threadIdx.x & 31;
     double s1 = 0.0, s2 = 0.0;
     if (mode == B200_NORM_CBN) {
-        for (int k = 0; k < nseg; ++k) {
+        for (int k = lane; k < nseg; k += 32) {
             double g = (double)gamma[(int64_t)idx[k] * 2 * C + c];
             s1 += g * seg[((int64_t)k * C + c) * 2];
             s2 += g * seg[((int64_t)k * C + c) * 2 + 1];
         }
     } else {
-        for (int k = 0; k < nseg; ++k) { s1 += seg[((int64_t)k * C + c) * 2]; s2 += seg[((int64_t)k * C + c) * 2 + 1]; }
-        if (mode == B200_NORM_AFFINE) {
-            if (dbeta) dbeta[c] = (float)s1;
-            if (dgamma) dgamma[c] = (float)s2;
-            double g = (double)gamma[c];
-            s1 *= g;
-            s2 *= g;
-        }
+        for (int k = lane; k < nseg; k += 32) { s1 += seg[((int64_t)k * C + c) * 2]; s2 += seg[((int64_t)k * C + c) * 2 + 1]; }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane != 0) return;
+    if (mode == B200_NORM_AFFINE) {
+        if (dbeta) dbeta[c] = (float)s1;
+        if (dgamma) dgamma[c] = (float)s2;
+        double g = (double)gamma[c];
+        s1 *= g;
+        s2 *= g;
     }
     s[c * 2] = (float)s1;
     s[c * 2 + 1] = (float)s2;
@@ -177,31 +186,59 @@ __global__ void cbn_dtable_kernel(const double* __restrict__ seg, int nseg, int 
     }
 }
 
-// stage 3
+// stage 3 (4 channels per thread)
 template <int MODE>
 __global__ void norm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                       const float* __restrict__ y, float* __restrict__ dx, int64_t rows, int C,
                                       const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                       const float* __restrict__ gamma, const int32_t* __restrict__ idx,
                                       int rows_per_seg, int relu, const float* __restrict__ s, float* __restrict__ dgb) {
-    int64_t total = rows * C;
-    float inv_rows = 1.f / (float)rows;
+    const int C4 = C >> 2;
+    const int64_t total = rows * C4;
+    const float inv_rows = 1.f / (float)rows;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(t % C);
-        int64_t r = t / C;
-        float g = dy[t];
-        if (relu && !(y[t] > 0.f)) g = 0.f;
-        float rstd = 1.f / sqrtf(var[c] + eps);
-        float xh = (x[t] - mean[c]) * rstd;
-        float dxh = g;
-        if (MODE == B200_NORM_AFFINE) dxh = g * gamma[c];
-        else if (MODE == B200_NORM_CBN) dxh = g * gamma[(int64_t)idx[r / rows_per_seg] * 2 * C + c];
-        else if (MODE == B200_NORM_SPADE) {
-            dxh = g * (1.f + gamma[r * 2 * C + c]);
-            dgb[r * 2 * C + c] = g * xh;
-            dgb[r * 2 * C + C + c] = g;
+        const int c = (int)(t % C4) << 2;
+        const int64_t r = t / C4;
+        const float4 g4 = *reinterpret_cast<const float4*>(dy + t * 4);
+        const float4 x4 = *reinterpret_cast<const float4*>(x + t * 4);
+        float g[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+        if (relu) {
+            const float4 y4 = *reinterpret_cast<const float4*>(y + t * 4);
+            if (!(y4.x > 0.f)) g[0] = 0.f;
+            if (!(y4.y > 0.f)) g[1] = 0.f;
+            if (!(y4.z > 0.f)) g[2] = 0.f;
+            if (!(y4.w > 0.f)) g[3] = 0.f;
         }
-        dx[t] = rstd * (dxh - s[c * 2] * inv_rows - xh * s[c * 2 + 1] * inv_rows);
+        const float4 m4 = *reinterpret_cast<const float4*>(mean + c);
+        const float4 v4 = *reinterpret_cast<const float4*>(var + c);
+        const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+        const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+        float ga[4] = {1.f, 1.f, 1.f, 1.f};
+        if (MODE == B200_NORM_AFFINE) {
+            const float4 q = *reinterpret_cast<const float4*>(gamma + c);
+            ga[0] = q.x; ga[1] = q.y; ga[2] = q.z; ga[3] = q.w;
+        } else if (MODE == B200_NORM_CBN) {
+            const float4 q = *reinterpret_cast<const float4*>(gamma + (int64_t)idx[r / rows_per_seg] * 2 * C + c);
+            ga[0] = q.x; ga[1] = q.y; ga[2] = q.z; ga[3] = q.w;
+        } else if (MODE == B200_NORM_SPADE) {
+            const float4 q = *reinterpret_cast<const float4*>(gamma + r * 2 * C + c);
+            ga[0] = 1.f + q.x; ga[1] = 1.f + q.y; ga[2] = 1.f + q.z; ga[3] = 1.f + q.w;
+        }
+        float o[4], gx[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float rstd = 1.f / sqrtf(vv[e] + eps);
+            const float xh = (xv[e] - mv[e]) * rstd;
+            const float dxh = g[e] * ga[e];
+            gx[e] = g[e] * xh;
+            o[e] = rstd * (dxh - s[(c + e) * 2] * inv_rows - xh * s[(c + e) * 2 + 1] * inv_rows);
+        }
+        if (MODE == B200_NORM_SPADE) {
+            *reinterpret_cast<float4*>(dgb + r * 2 * C + c) = make_float4(gx[0], gx[1], gx[2], gx[3]);
+            *reinterpret_cast<float4*>(dgb + r * 2 * C + C + c) = make_float4(g[0], g[1], g[2], g[3]);
+        }
+        *reinterpret_cast<float4*>(dx + t * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -217,8 +254,8 @@ extern "C" int b200_bn_stats(const float* x, int64_t rows, int C, float* mean, f
     dim3 grid(nchunks, (C + 31) / 32), block(32, 8);
     bn_stats_partial_kernel<<<grid, block, 0, as_stream(stream)>>>(x, rows, C, rpc, ws);
     B200_CHECK_LAUNCH();
-    bn_stats_final_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(ws, nchunks, C, rows, mean, var, running_mean,
-                                                                          running_var, momentum);
+    bn_stats_final_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, nchunks, C, rows, mean, var, running_mean,
+                                                                      running_var, momentum);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -276,7 +313,7 @@ extern "C" int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, i
                                       const int32_t* idx, int num_classes, float* s, float* dgamma, float* dbeta,
                                       float* dtable, b200_stream_t stream) {
     cudaStream_t st = as_stream(stream);
-    norm_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(seg_sums, nseg, C, mode, gamma, idx, s, dgamma, dbeta);
+    norm_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(seg_sums, nseg, C, mode, gamma, idx, s, dgamma, dbeta);
     B200_CHECK_LAUNCH();
     if (mode == B200_NORM_CBN && dtable) {
         cbn_dtable_kernel<<<grid_for((int64_t)num_classes * C, 128), 128, 0, st>>>(seg_sums, nseg, C, idx, num_classes, dtable);
@@ -290,7 +327,8 @@ extern "C" int b200_norm_bwd_apply(const float* dy, const float* x, const float*
                                    const int32_t* idx, int rows_per_seg, int relu, const float* s, float* dgb,
                                    b200_stream_t stream) {
     if (rows == 0) return 0;
-    int g = grid_for(rows * C, 256);
+    B200_REQUIRE(C % 4 == 0, "norm_bwd_apply: C=%d must be a multiple of 4", C);
+    int g = grid_for(rows * (C / 4), 256);
     cudaStream_t st = as_stream(stream);
     if (rows_per_seg < 1) rows_per_seg = 1;
     switch (mode) {

@@ -69,3 +69,25 @@ def test_ragged_and_unsorted_layouts(emul):
     b2f = torch.tensor([2, 0, 1, 0, 2])
     c = ops.crop_bbox_batch(feats, boxes, b2f, 8)
     assert rel(c, O.crop_bbox_batch(feats, boxes, b2f, 8)) < 1e-5
+
+
+def test_step_wiring_bf16_operand_routing(emul):
+    """bf16 mode: every tensor-core-eligible GEMM must receive bf16 operands (the emulation asserts the dtype contract
+    of b200_conv_gemm_tc / b200_wgrad_gemm_tc) and everything else fp32; results stay within the stated bf16 bound."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    from b200gan import ops
+    from b200gan.step import TrainStep
+    states = O.make_states(64, 0)
+    batch = O.synth_batch(2, 64, None, 7)
+    ops.set_precision("bf16")
+    try:
+        ts = TrainStep(64, device="cpu")
+        load_states(ts, states)
+        res = ts.step(ts.to_device(batch), optimizer_step=False, seeds=(123, 124))
+    finally:
+        ops.set_precision("fp32")
+    ref = oracle_step(O.OracleModel(64, 0, states), batch)
+    for i in (4, 5, 6):
+        assert rel(res["out_g"][i], ref["out_g"][i]) < 6e-2
+    assert abs(float(res["d_loss"]) - float(ref["d_loss"])) < 5e-2 * abs(float(ref["d_loss"]))
+    assert abs(float(res["g_loss"]) - float(ref["g_loss"])) < 5e-2 * abs(float(ref["g_loss"]))
