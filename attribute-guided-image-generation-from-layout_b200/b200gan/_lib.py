@@ -130,6 +130,9 @@ class Kernels:
                                                int(out.dtype == torch.bfloat16), _ptr(ws), splits, _stream()),
                     "b200_conv_gemm_tc")
 
+    def conv_tc_set_im2col(self, enable: bool) -> bool:
+        return bool(self.lib.b200_conv_tc_set_im2col(int(bool(enable))))
+
     def conv_tc_ntile(self, cout: int) -> int:
         return int(self.lib.b200_conv_tc_ntile(int(cout)))
 

@@ -14,6 +14,7 @@
 //   (64 pixels x 128 B of channels) = the canonical MN-major SWIZZLE_128B layout, so the same producer code feeds
 //   them; split over the pixel range with fp32 partials reduced by b200_wgrad_reduce (deterministic).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -60,6 +61,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+
+// TMA im2col load: `pixelsPerColumn` consecutive output pixels (w fastest, wrapping over h and n inside the tensor map's
+// bounding box) x `channelsPerPixel` channels starting at channel c; {w, h, n} = input coordinates of tap (0,0) of the
+// first pixel, {off_w, off_h} = tap offsets; out-of-image taps are zero filled by the hardware
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t smem_dst, const CUtensorMap* tmap, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
         : "memory");
 }
 
@@ -142,8 +154,9 @@ __device__ __forceinline__ void st_bf16x8(void* p, const float* o) {
     *reinterpret_cast<uint4*>(p) = u;
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap, b200_conv_desc d,
+template <int BN, int STAGES, bool ATMA>
+__global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                           const __grid_constant__ CUtensorMap tmap_a, b200_conv_desc d,
                                                            const __nv_bfloat16* __restrict__ in,
                                                            const float* __restrict__ bias,
                                                            const float* __restrict__ scale, void* __restrict__ out_v,
@@ -192,11 +205,13 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
     }
     if (warp == 4 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+        if (ATMA) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     }
     if (warp == 5) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
-                mbar_init(smem_u32(&tail->full[s]), 128 + 1);   // 128 cp.async completions + the TMA expect_tx arrival
+                // cp.async path: 128 cp.async completions + the TMA expect_tx arrival; im2col path: the expect_tx arrival only
+                mbar_init(smem_u32(&tail->full[s]), ATMA ? 1 : 128 + 1);
                 mbar_init(smem_u32(&tail->empty[s]), 1);
             }
             mbar_init(smem_u32(&tail->tmem_full), 1);
@@ -226,7 +241,7 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
         }
         const uint32_t dst_off = (uint32_t)rg * 128u + ((((uint32_t)j) ^ ((uint32_t)rg & 7u)) << 4);
         int tap = kb_begin / cpb, cc = kb_begin - tap * cpb;
-        for (int i = 0; i < num_kb; ++i) {
+        for (int i = 0; i < (ATMA ? 0 : num_kb); ++i) {
             const int s = i % STAGES;
             const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
             mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
@@ -312,14 +327,32 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
             }
         }
     } else if (warp == 4) {
-        // ===================== B producer (TMA) =====================
+        // ===================== B producer (TMA), and the A producer on the im2col path =====================
         if (lane == 0) {
+            // im2col base coordinates of the tile's first output pixel (tap (0,0) in the tensor map's offset convention)
+            int aw = 0, ah = 0, an = 0, tap = 0, cc = 0;
+            if (ATMA) {
+                const int qx = (int)(m0 % d.Qw);
+                const int qy = (int)((m0 / d.Qw) % d.Qh);
+                an = (int)(m0 / ((int64_t)d.Qw * d.Qh));
+                aw = qx * d.in_sx + (d.tap_sx > 0 ? d.tap_ox : d.tap_ox - (d.Tw - 1));
+                ah = qy * d.in_sy + (d.tap_sy > 0 ? d.tap_oy : d.tap_oy - (d.Th - 1));
+                tap = kb_begin / cpb;
+                cc = kb_begin - tap * cpb;
+            }
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
                 const uint32_t bar = smem_u32(&tail->full[s]);
-                mbar_arrive_expect_tx(bar, B_BYTES);
+                mbar_arrive_expect_tx(bar, ATMA ? A_BYTES + B_BYTES : B_BYTES);
+                if (ATMA) {
+                    const int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
+                    const uint16_t ow = (uint16_t)(d.tap_sx > 0 ? txx : d.Tw - 1 - txx);
+                    const uint16_t oh = (uint16_t)(d.tap_sy > 0 ? tyy : d.Th - 1 - tyy);
+                    tma_load_im2col_4d(smem_u32(smem_a + s * A_BYTES), &tmap_a, cc * BK, aw, ah, an, ow, oh, bar);
+                    if (++cc == cpb) { cc = 0; ++tap; }
+                }
                 tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tmap, (kb_begin + i) * BK, n0, bar);
             }
         }
@@ -579,14 +612,74 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn get_encode_im2col_fn() {
+    static EncodeIm2colFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeIm2colFn>(p);
+    }
+    return fn;
+}
+
+// The activation operand can be fetched by TMA im2col when the gather is a plain strided window walk:
+// unit tap steps, no fused nearest-upsampling, corners / offsets inside the 4-D im2col encoding limits.
+static bool im2col_eligible(const b200_conv_desc* d) {
+    if (d->up_shift != 0) return false;
+    if ((d->tap_sy != 1 && d->tap_sy != -1) || (d->tap_sx != 1 && d->tap_sx != -1)) return false;
+    if (d->in_sy < 1 || d->in_sy > 8 || d->in_sx < 1 || d->in_sx > 8) return false;
+    if (d->Th > 255 || d->Tw > 255) return false;
+    const int lw = d->tap_sx > 0 ? d->tap_ox : d->tap_ox - (d->Tw - 1);
+    const int lh = d->tap_sy > 0 ? d->tap_oy : d->tap_oy - (d->Th - 1);
+    const int uw = lw + (d->Qw - 1) * d->in_sx + 1 - d->Wi;
+    const int uh = lh + (d->Qh - 1) * d->in_sy + 1 - d->Hi;
+    if (lw < -128 || lw > 127 || lh < -128 || lh > 127 || uw < -128 || uw > 127 || uh < -128 || uh > 127) return false;
+    // the bounding box [lower, dim + upper) must be non-empty
+    if (d->Wi + uw - lw < 1 || d->Hi + uh - lh < 1) return false;
+    return get_encode_im2col_fn() != nullptr;
+}
+
+static int encode_im2col(const b200_conv_desc* d, const void* in, CUtensorMap* tmap) {
+    EncodeIm2colFn enc = get_encode_im2col_fn();
+    const int lw = d->tap_sx > 0 ? d->tap_ox : d->tap_ox - (d->Tw - 1);
+    const int lh = d->tap_sy > 0 ? d->tap_oy : d->tap_oy - (d->Th - 1);
+    const int uw = lw + (d->Qw - 1) * d->in_sx + 1 - d->Wi;
+    const int uh = lh + (d->Qh - 1) * d->in_sy + 1 - d->Hi;
+    cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->B};
+    cuuint64_t gstr[3] = {(cuuint64_t)d->in_sw * 2, (cuuint64_t)d->in_sh * 2, (cuuint64_t)d->in_sn * 2};
+    int lower[2] = {lw, lh}, upper[2] = {uw, uh};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->in_sx, (cuuint32_t)d->in_sy, 1};
+    CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, lower, upper,
+                     (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm_tc: cuTensorMapEncodeIm2col failed (%d)", (int)r);
+    // drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (descriptor word 1, bit 21 must be
+    // clear) — the same fix-up the CUTLASS im2col traits apply
+    static int drv = -1;
+    if (drv < 0 && cudaDriverGetVersion(&drv) != cudaSuccess) drv = 0;
+    const uint64_t bytes = (uint64_t)d->B * (uint64_t)d->in_sn * 2;
+    if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(tmap)[1] &= ~(1ull << 21);
+    return 0;
+}
+
 template <int BN, int STAGES>
 static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const void* wmat, const float* bias,
-                      const float* scale, void* out, int out_bf16, float* split_ws, int splits, cudaStream_t st) {
+                      const float* scale, void* out, int out_bf16, float* split_ws, int splits, int use_im2col,
+                      cudaStream_t st) {
     EncodeTiledFn enc = get_encode_fn();
     B200_REQUIRE(enc != nullptr, "conv_gemm_tc: cuTensorMapEncodeTiled unavailable");
     int64_t M = (int64_t)d->B * d->Qh * d->Qw;
     int ntiles = (d->Cout + BN - 1) / BN;
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap_a;
     cuuint64_t gdim[2] = {(cuuint64_t)d->ldw, (cuuint64_t)ntiles * BN};
     cuuint64_t gstr[1] = {(cuuint64_t)d->ldw * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
@@ -595,11 +688,20 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    const bool atma = use_im2col && im2col_eligible(d);
+    if (atma) {
+        if (encode_im2col(d, in, &tmap_a) != 0) return -1;
+    } else {
+        tmap_a = tmap;
+    }
     constexpr int smem_bytes = 1024 + STAGES * (A_BYTES + BN * BK * 2) + (int)sizeof(SmemTail) + BM * 24;
-    auto kern = conv_gemm_tc_kernel<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     smem_bytes);
         B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
@@ -607,7 +709,12 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
     int kbps = (num_kb + splits - 1) / splits;
     splits = (num_kb + kbps - 1) / kbps;          // no empty split
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles, (unsigned)splits);
-    kern<<<grid, 192, smem_bytes, st>>>(tmap, *d, in, bias, scale, out, out_bf16, split_ws, kbps);
+    if (atma)
+        conv_gemm_tc_kernel<BN, STAGES, true><<<grid, 192, smem_bytes, st>>>(tmap, tmap_a, *d, in, bias, scale, out,
+                                                                            out_bf16, split_ws, kbps);
+    else
+        conv_gemm_tc_kernel<BN, STAGES, false><<<grid, 192, smem_bytes, st>>>(tmap, tmap_a, *d, in, bias, scale, out,
+                                                                             out_bf16, split_ws, kbps);
     B200_CHECK_LAUNCH();
     if (splits > 1) {
         int64_t total = M * ((d->Cout + 3) / 4);
@@ -656,6 +763,16 @@ __global__ void cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict
 
 using namespace b200;
 
+static int g_use_im2col = []() {
+    const char* e = getenv("B200_NO_IM2COL");      // diagnostic switch: force the cp.async gather everywhere
+    return (e && e[0] == '1') ? 0 : 1;
+}();
+extern "C" int b200_conv_tc_set_im2col(int enable) {
+    int old = g_use_im2col;
+    g_use_im2col = enable ? 1 : 0;
+    return old;
+}
+
 extern "C" int b200_conv_tc_ntile(int Cout) { return Cout >= 128 ? 128 : (Cout >= 64 ? 64 : 16); }
 
 /* split-K plan: enough CTAs to fill the 148 SMs twice when the output tile grid alone cannot */
@@ -696,9 +813,10 @@ extern "C" int b200_conv_gemm_tc(const b200_conv_desc* d, const void* in_bf16, c
     cudaStream_t st = as_stream(stream);
     const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(in_bf16);
     int bn = b200_conv_tc_ntile(d->Cout);
-    if (bn == 128) return tc::launch_fwd<128, 3>(d, in, wmat_bf16, bias, scale, out, out_bf16, split_ws, splits, st);
-    if (bn == 64) return tc::launch_fwd<64, 4>(d, in, wmat_bf16, bias, scale, out, out_bf16, split_ws, splits, st);
-    return tc::launch_fwd<16, 4>(d, in, wmat_bf16, bias, scale, out, out_bf16, split_ws, splits, st);
+    const int use_im2col = g_use_im2col;
+    if (bn == 128) return tc::launch_fwd<128, 3>(d, in, wmat_bf16, bias, scale, out, out_bf16, split_ws, splits, use_im2col, st);
+    if (bn == 64) return tc::launch_fwd<64, 4>(d, in, wmat_bf16, bias, scale, out, out_bf16, split_ws, splits, use_im2col, st);
+    return tc::launch_fwd<16, 4>(d, in, wmat_bf16, bias, scale, out, out_bf16, split_ws, splits, use_im2col, st);
 }
 
 extern "C" int b200_wgrad_gemm_tc(const b200_conv_desc* d, const void* P_bf16, const void* G_bf16, float* ws, int splits,

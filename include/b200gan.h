@@ -93,6 +93,11 @@ int b200_conv_gemm_f32(const b200_conv_desc* d, const float* in, const float* wm
 int b200_conv_gemm_tc(const b200_conv_desc* d, const void* in_bf16, const void* wmat_bf16, const float* bias,
                       const float* scale, void* out, int out_bf16, float* split_ws, int splits, b200_stream_t stream);
 int b200_conv_tc_ntile(int Cout);
+/* The activation operand is fetched by TMA im2col (cuTensorMapEncodeIm2col: 128 output pixels x 64 channels per
+ * request, zero fill outside the image) whenever the descriptor is a plain strided window walk, else by 16-byte
+ * cp.async gathers.  b200_conv_tc_set_im2col(0) forces the cp.async path (parity tests compare the two); returns the
+ * previous setting. */
+int b200_conv_tc_set_im2col(int enable);
 int b200_conv_tc_splits(const b200_conv_desc* d);
 /* y[i] = bf16(x[i]) (round to nearest even), n % 4 == 0 */
 int b200_cast_bf16(const float* x, void* y_bf16, int64_t n, b200_stream_t stream);

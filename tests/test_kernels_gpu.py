@@ -404,3 +404,53 @@ def test_tc_matches_fp32_at_scale(K):
         ops.set_precision("fp32")
     close(ytc, y32, 1e-2, "tc vs fp32")
     assert torch.equal(ytc2, ytc * 2.0), "scaling by a power of two must commute exactly with the bf16 GEMM"
+
+
+IM2COL_CASES = [
+    # (Cx, Cy, k, s, p, H, N, transposed)
+    (64, 64, 3, 1, 1, 64, 3, False),      # D blocks at 64x64
+    (128, 128, 3, 1, 1, 16, 5, False),
+    (64, 128, 4, 2, 1, 66, 3, False),     # LayoutEncoder c2 (odd geometry 66 -> 33)
+    (128, 256, 4, 2, 1, 33, 3, False),    # 33 -> 16
+    (128, 256, 5, 1, 2, 8, 7, False),     # ConvLSTM gate conv
+    (192, 256, 3, 1, 1, 8, 2, False),
+    (512, 512, 1, 1, 0, 4, 9, False),     # 1x1 shortcut
+    (128, 256, 4, 2, 1, 8, 3, True),      # ConvTranspose phases (dgrad descriptors, negative tap steps)
+]
+
+
+@pytest.mark.parametrize("case", IM2COL_CASES)
+def test_im2col_path_equals_cpasync_path(K, case):
+    """The TMA-im2col A-operand path and the cp.async gather path fetch the same bf16 tiles, so forward, dgrad and the
+    ConvTranspose phases must agree BIT-EXACTLY between the two (same MMA order, same epilogue)."""
+    Cx, Cy, k, s, p, H, N, transposed = case
+    g = torch.Generator().manual_seed(Cx + Cy * 3 + k)
+    geom = ops.ConvGeom(Cx, Cy, k, k, s, p)
+    w = (torch.randn(Cy, Cx, k, k, generator=g) / (Cx * k * k) ** 0.5).cuda()
+    Hy = geom.out_hw(H, H)[0]
+    x = torch.randn(N, H, H, Cx, generator=g).cuda()
+    dy = torch.randn(N, Hy, Hy, Cy, generator=g).cuda()
+    ops.set_precision("bf16")
+    outs = []
+    try:
+        for enable in (True, False):
+            prev = _lib.K.conv_tc_set_im2col(enable)
+            try:
+                packs = ops.WeightPacks()
+                if not transposed:
+                    y = ops.conv_forward(geom, packs, w, x, "cl", "cl")
+                    dx = ops.conv_dgrad(geom, packs, w, dy, "cl", (H, H), "cl")
+                else:
+                    y = ops.conv_dgrad(geom, packs, w, dy, "cl", (H, H), "cl")
+                    dx = ops.conv_forward(geom, packs, w, x, "cl", "cl")
+                outs.append((y.clone(), dx.clone()))
+            finally:
+                _lib.K.conv_tc_set_im2col(prev)
+    finally:
+        ops.set_precision("fp32")
+    assert torch.equal(outs[0][0], outs[1][0]), "forward differs between im2col and cp.async"
+    assert torch.equal(outs[0][1], outs[1][1]), "dgrad differs between im2col and cp.async"
+    # and both agree with the fp32 CUDA-core path within the bf16 operand bound
+    y32 = ops.conv_forward(geom, ops.WeightPacks(), w, x, "cl", "cl") if not transposed else \
+        ops.conv_dgrad(geom, ops.WeightPacks(), w, dy, "cl", (H, H), "cl")
+    close(outs[0][0], y32, 2e-2, "tc vs fp32")
