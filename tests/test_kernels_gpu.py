@@ -443,13 +443,17 @@ def test_im2col_path_equals_cpasync_path(K, case):
                 else:
                     y = ops.conv_dgrad(geom, packs, w, dy, "cl", (H, H), "cl")
                     dx = ops.conv_forward(geom, packs, w, x, "cl", "cl")
-                outs.append((y.clone(), dx.clone()))
+                dw = ops.conv_wgrad(geom, x, "cl", dy, "cl", torch.empty_like(w))
+                outs.append((y.clone(), dx.clone(), dw.clone()))
             finally:
                 _lib.K.conv_tc_set_im2col(prev)
     finally:
         ops.set_precision("fp32")
     assert torch.equal(outs[0][0], outs[1][0]), "forward differs between im2col and cp.async"
     assert torch.equal(outs[0][1], outs[1][1]), "dgrad differs between im2col and cp.async"
+    assert torch.equal(outs[0][2], outs[1][2]), "wgrad differs between im2col and cp.async"
+    dwr = torch.nn.grad.conv2d_weight(_bf(x.cpu()).permute(0, 3, 1, 2), w.shape, _bf(dy.cpu()).permute(0, 3, 1, 2), stride=s, padding=p)
+    close(outs[0][2], dwr, 1e-4, "wgrad vs reference on bf16-rounded operands")
     # and both agree with the fp32 CUDA-core path within the bf16 operand bound
     y32 = ops.conv_forward(geom, ops.WeightPacks(), w, x, "cl", "cl") if not transposed else \
         ops.conv_dgrad(geom, ops.WeightPacks(), w, dy, "cl", (H, H), "cl")
