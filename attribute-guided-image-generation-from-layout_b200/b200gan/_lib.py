@@ -35,6 +35,7 @@ class ConvDesc(C.Structure):
         ("out_sn", C.c_int64), ("out_sh", C.c_int64), ("out_sw", C.c_int64), ("out_sc", C.c_int64),
         ("ldw", C.c_int64),
         ("relu", C.c_int),
+        ("scale_rows", C.c_int),
     ]
 
 
@@ -174,56 +175,59 @@ class Kernels:
     def bn_chunks(self, rows, Cc):
         return int(self.lib.b200_bn_chunks(C.c_int64(rows), int(Cc)))
 
-    def bn_stats(self, x2d, running_mean, running_var, momentum):
+    def bn_stats(self, x2d, running_mean, running_var, momentum, groups=1):
         rows, Cc = x2d.shape
         dev = x2d.device
-        mean = torch.empty((Cc,), dtype=torch.float32, device=dev)
-        var = torch.empty((Cc,), dtype=torch.float32, device=dev)
-        ws = torch.empty((2 * Cc * self.bn_chunks(rows, Cc),), dtype=torch.float64, device=dev)
-        self._check(self.lib.b200_bn_stats(_ptr(x2d), C.c_int64(rows), Cc, _ptr(mean), _ptr(var), _ptr(running_mean),
-                                           _ptr(running_var), C.c_float(momentum), _ptr(ws), _stream()), "b200_bn_stats")
+        mean = torch.empty((groups, Cc), dtype=torch.float32, device=dev)
+        var = torch.empty((groups, Cc), dtype=torch.float32, device=dev)
+        ws = torch.empty((2 * Cc * groups * self.bn_chunks(rows // groups, Cc),), dtype=torch.float64, device=dev)
+        self._check(self.lib.b200_bn_stats(_ptr(x2d), C.c_int64(rows), Cc, int(groups), _ptr(mean), _ptr(var),
+                                           _ptr(running_mean), _ptr(running_var), C.c_float(momentum), _ptr(ws),
+                                           _stream()), "b200_bn_stats")
         return mean, var
 
-    def norm_fwd(self, x2d, mean, var, eps, mode, gamma, beta, idx, rows_per_seg, residual, relu):
+    def norm_fwd(self, x2d, mean, var, eps, mode, gamma, beta, idx, rows_per_seg, residual, relu, groups=1):
         rows, Cc = x2d.shape
         y = torch.empty_like(x2d)
-        self._check(self.lib.b200_norm_fwd(_ptr(x2d), _ptr(y), C.c_int64(rows), Cc, _ptr(mean), _ptr(var),
+        self._check(self.lib.b200_norm_fwd(_ptr(x2d), _ptr(y), C.c_int64(rows), Cc, int(groups), _ptr(mean), _ptr(var),
                                            C.c_float(eps), int(mode), _ptr(gamma), _ptr(beta), _ptr(idx),
                                            int(rows_per_seg), _ptr(residual), int(bool(relu)), _stream()),
                     "b200_norm_fwd")
         return y
 
-    def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes):
+    def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes, groups=1):
         """reduce -> finalize -> apply.  Returns dx, dgamma, dbeta, dtable, dgb (None where not applicable)."""
         rows, Cc = x2d.shape
         dev = x2d.device
+        rpg = rows // groups
         if mode == MODE_CBN:
             seg = int(rows_per_seg)
         else:
-            nchunks = self.bn_chunks(rows, Cc)
-            seg = (rows + nchunks - 1) // nchunks
-        nseg = (rows + seg - 1) // seg
+            nchunks = self.bn_chunks(rpg, Cc)
+            seg = (rpg + nchunks - 1) // nchunks
+        nseg = groups * ((rpg + seg - 1) // seg)
         seg_sums = torch.empty((nseg * Cc * 2,), dtype=torch.float64, device=dev)
-        self._check(self.lib.b200_norm_bwd_reduce(_ptr(dy), _ptr(x2d), _ptr(y), C.c_int64(rows), Cc, _ptr(mean),
-                                                  _ptr(var), C.c_float(eps), int(mode), _ptr(gamma), _ptr(idx), seg,
-                                                  int(bool(relu)), _ptr(seg_sums), _stream()), "b200_norm_bwd_reduce")
-        s = torch.empty((Cc * 2,), dtype=torch.float32, device=dev)
+        self._check(self.lib.b200_norm_bwd_reduce(_ptr(dy), _ptr(x2d), _ptr(y), C.c_int64(rows), Cc, int(groups),
+                                                  _ptr(mean), _ptr(var), C.c_float(eps), int(mode), _ptr(gamma),
+                                                  _ptr(idx), seg, int(bool(relu)), _ptr(seg_sums), _stream()),
+                    "b200_norm_bwd_reduce")
+        s = torch.empty((groups * Cc * 2,), dtype=torch.float32, device=dev)
         dgamma = dbeta = dtable = dgb = None
         if mode == MODE_AFFINE:
             dgamma = torch.empty((Cc,), dtype=torch.float32, device=dev)
             dbeta = torch.empty((Cc,), dtype=torch.float32, device=dev)
         if mode == MODE_CBN:
             dtable = torch.empty((num_classes, 2 * Cc), dtype=torch.float32, device=dev)
-        self._check(self.lib.b200_norm_bwd_finalize(_ptr(seg_sums), nseg, Cc, int(mode), _ptr(gamma), _ptr(idx),
-                                                    int(num_classes), _ptr(s), _ptr(dgamma), _ptr(dbeta), _ptr(dtable),
-                                                    _stream()), "b200_norm_bwd_finalize")
+        self._check(self.lib.b200_norm_bwd_finalize(_ptr(seg_sums), nseg, Cc, int(groups), int(mode), _ptr(gamma),
+                                                    _ptr(idx), int(num_classes), _ptr(s), _ptr(dgamma), _ptr(dbeta),
+                                                    _ptr(dtable), _stream()), "b200_norm_bwd_finalize")
         dx = torch.empty_like(x2d)
         if mode == MODE_SPADE:
             dgb = torch.empty((rows, 2 * Cc), dtype=torch.float32, device=dev)
-        self._check(self.lib.b200_norm_bwd_apply(_ptr(dy), _ptr(x2d), _ptr(y), _ptr(dx), C.c_int64(rows), Cc, _ptr(mean),
-                                                 _ptr(var), C.c_float(eps), int(mode), _ptr(gamma), _ptr(idx),
-                                                 int(rows_per_seg) if mode == MODE_CBN else 1, int(bool(relu)), _ptr(s),
-                                                 _ptr(dgb), _stream()), "b200_norm_bwd_apply")
+        self._check(self.lib.b200_norm_bwd_apply(_ptr(dy), _ptr(x2d), _ptr(y), _ptr(dx), C.c_int64(rows), Cc,
+                                                 int(groups), _ptr(mean), _ptr(var), C.c_float(eps), int(mode),
+                                                 _ptr(gamma), _ptr(idx), int(rows_per_seg) if mode == MODE_CBN else 1,
+                                                 int(bool(relu)), _ptr(s), _ptr(dgb), _stream()), "b200_norm_bwd_apply")
         return dx, dgamma, dbeta, dtable, dgb
 
     # ---- elementwise / pooling / layout ------------------------------------------------------------------------
@@ -347,20 +351,34 @@ class Kernels:
         return out
 
     # ---- spectral norm --------------------------------------------------------------------------------------
-    def sn_power_iter(self, W2d_param, h, w, u, v, do_iter, eps):
+    def sn_power_iter(self, W2d_param, h, w, u, v, do_iter, eps, inv_out=None, sigma_out=None):
+        """one power iteration (in place on u, v); writes 1/sigma to inv_out[0] (a 1-element view) and returns it"""
         dev = u.device
-        out2 = torch.empty((2,), dtype=torch.float32, device=dev)
+        if inv_out is None:
+            inv_out = torch.empty((1,), dtype=torch.float32, device=dev)
         ws = torch.empty((8 * w + h,), dtype=torch.float32, device=dev)
         self._check(self.lib.b200_sn_power_iter(_ptr(W2d_param), h, w, _ptr(u), _ptr(v), int(bool(do_iter)),
-                                                C.c_float(eps), _ptr(out2), _ptr(ws), _stream()), "b200_sn_power_iter")
-        return out2
+                                                C.c_float(eps), _ptr(sigma_out), _ptr(inv_out), _ptr(ws), _stream()),
+                    "b200_sn_power_iter")
+        return inv_out
 
-    def sn_grad(self, g, W, u, v, sig2, h, w):
-        dW = torch.empty_like(W)
+    def sn_grad(self, g, W, u, v, inv_sigma, h, w, dW=None, accumulate=False):
+        if dW is None:
+            dW = torch.empty_like(W)
         ws = torch.empty((1024,), dtype=torch.float64, device=W.device)
-        self._check(self.lib.b200_sn_grad(_ptr(g), _ptr(W), _ptr(u), _ptr(v), _ptr(sig2), _ptr(dW), h, w, 0, _ptr(ws),
-                                          _stream()), "b200_sn_grad")
+        self._check(self.lib.b200_sn_grad(_ptr(g), _ptr(W), _ptr(u), _ptr(v), _ptr(inv_sigma), _ptr(dW), h, w,
+                                          int(bool(accumulate)), _ptr(ws), _stream()), "b200_sn_grad")
         return dW
+
+    def copy_into(self, dst, dst_row, src):
+        """dst[dst_row : dst_row + src.shape[0]] = src (contiguous tensors of equal row size and dtype)"""
+        if not (dst.is_cuda and src.is_cuda):
+            raise B200Error("copy_into: CUDA tensors required")
+        if dst.dtype != src.dtype or dst[0].numel() != src[0].numel() or not (dst.is_contiguous() and src.is_contiguous()):
+            raise B200Error("copy_into: mismatched row layout")
+        rowb = dst[0].numel() * dst.element_size()
+        self._check(self.lib.b200_copy(C.c_void_p(dst.data_ptr() + int(dst_row) * rowb), _ptr(src),
+                                       C.c_size_t(src.shape[0] * rowb), _stream()), "b200_copy")
 
 
 _K: Optional[Kernels] = None

@@ -280,14 +280,13 @@ class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, sn_u, sn_v, g: ConvGeom, packs: WeightPacks, transposed: bool, x_layout: str,
                 out_layout: str, relu: bool, training: bool, out_hw):
-        sig2 = None
+        scale = None
         if sn_u is not None:
             h, wd = w.shape[0], w[0].numel()
-            sig2 = _lib.K.sn_power_iter(w, h, wd, sn_u, sn_v, training, SN_EPS)
-            ctx.sn = (sn_u.clone(), sn_v.clone(), sig2)
+            scale = _lib.K.sn_power_iter(w, h, wd, sn_u, sn_v, training, SN_EPS)      # (1,) = 1/sigma
+            ctx.sn = (sn_u.clone(), sn_v.clone(), scale)
         else:
             ctx.sn = None
-        scale = sig2[1:] if sig2 is not None else None
         if not transposed:
             fwd_tc, wgrad_tc = _tc_fwd_ok(g, x_layout), _tc_wgrad_ok(g, x_layout, out_layout)
         else:
@@ -312,7 +311,7 @@ class _ConvFn(torch.autograd.Function):
         dy = dy.contiguous()
         if ctx.relu:
             dy = _lib.K.relu_bwd(dy, y)
-        scale = ctx.sn[2][1:] if ctx.sn is not None else None
+        scale = ctx.sn[2] if ctx.sn is not None else None
         dx = dw = db = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not ctx.transposed:
@@ -335,8 +334,8 @@ class _ConvFn(torch.autograd.Function):
             else:
                 conv_wgrad(g, dy_op, ctx.out_layout, x, ctx.x_layout, gw)
             if ctx.sn is not None:
-                u, v, sig2 = ctx.sn
-                dw = _lib.K.sn_grad(gw, w, u, v, sig2, w.shape[0], w[0].numel())
+                u, v, inv_sigma = ctx.sn
+                dw = _lib.K.sn_grad(gw, w, u, v, inv_sigma, w.shape[0], w[0].numel())
             else:
                 dw = gw
         if ctx.has_bias and ctx.needs_input_grad[2]:

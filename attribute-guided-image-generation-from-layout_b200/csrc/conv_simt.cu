@@ -129,11 +129,12 @@ __global__ void __launch_bounds__(256) conv_gemm_f32_kernel(b200_conv_desc d, co
         }
     }
     __syncthreads();
-    const float alpha = scale ? *scale : 1.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int64_t ro = row_out[ty * 4 + i];
         if (ro < 0) continue;
+        const int64_t mrow = m0 + ty * 4 + i;
+        const float alpha = scale ? scale[d.scale_rows > 0 ? mrow / d.scale_rows : 0] : 1.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int co = n0 + tx * 4 + j;

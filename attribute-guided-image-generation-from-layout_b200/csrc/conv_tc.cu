@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
             }
         } else {
             const int64_t ro = row_out[row];
-            const float alpha = scale ? *scale : 1.f;
+            const int64_t mrow = m0 + row;
+            const float alpha = scale ? scale[(d.scale_rows > 0 && mrow < M) ? mrow / d.scale_rows : 0] : 1.f;
             float* out = reinterpret_cast<float*>(out_v);
             __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(out_v);
             const bool vec = d.out_sc == 1 && (d.Cout & 7) == 0 &&
@@ -389,12 +390,12 @@ __global__ void conv_splitk_reduce_kernel(b200_conv_desc d, const float* __restr
     const int64_t M = (int64_t)d.B * d.Qh * d.Qw;
     const int C4 = (d.Cout + 3) >> 2;
     const int64_t total = M * C4;
-    const float alpha = scale ? *scale : 1.f;
     float* out = reinterpret_cast<float*>(out_v);
     __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(out_v);
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int co = (int)(t % C4) << 2;
         const int64_t m = t / C4;
+        const float alpha = scale ? scale[d.scale_rows > 0 ? m / d.scale_rows : 0] : 1.f;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int z = 0; z < splits; ++z) {
             float4 v = *reinterpret_cast<const float4*>(ws + ((int64_t)z * M + m) * ldo + co);

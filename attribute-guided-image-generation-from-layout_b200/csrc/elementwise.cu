@@ -566,3 +566,11 @@ extern "C" int b200_transpose(const float* x, float* y, int B, int R, int C, b20
     B200_CHECK_LAUNCH();
     return 0;
 }
+
+extern "C" int b200_copy(void* dst, const void* src, size_t bytes, b200_stream_t stream) {
+    if (bytes == 0) return 0;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, as_stream(stream));
+    if (e != cudaSuccess) return set_error("copy: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}

@@ -8,14 +8,17 @@
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------------------------
-// statistics
+// statistics.  `groups` independent calls batched along the row dimension (rows = groups * rows_per_group) keep
+// separate statistics: grid.z = group, chunks never straddle a group.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void bn_stats_partial_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t rows_per_chunk,
-                                        double* __restrict__ ws) {
+__global__ void bn_stats_partial_kernel(const float* __restrict__ x, int64_t rows_per_group, int C,
+                                        int64_t rows_per_chunk, double* __restrict__ ws) {
     __shared__ double r1[8][33], r2[8][33];
     int c = blockIdx.y * 32 + threadIdx.x;
-    int64_t a = (int64_t)blockIdx.x * rows_per_chunk;
-    int64_t b = a + rows_per_chunk < rows ? a + rows_per_chunk : rows;
+    int64_t g0 = (int64_t)blockIdx.z * rows_per_group;
+    int64_t a = g0 + (int64_t)blockIdx.x * rows_per_chunk;
+    int64_t e = g0 + rows_per_group;
+    int64_t b = a + rows_per_chunk < e ? a + rows_per_chunk : e;
     double s1 = 0.0, s2 = 0.0;
     if (c < C) {
         for (int64_t r = a + threadIdx.y; r < b; r += 8) {
@@ -30,32 +33,43 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ x, int64_t row
     if (threadIdx.y == 0 && c < C) {
         double t1 = 0.0, t2 = 0.0;
         for (int k = 0; k < 8; ++k) { t1 += r1[k][threadIdx.x]; t2 += r2[k][threadIdx.x]; }
-        ws[((int64_t)blockIdx.x * C + c) * 2 + 0] = t1;
-        ws[((int64_t)blockIdx.x * C + c) * 2 + 1] = t2;
+        int64_t chunk = (int64_t)blockIdx.z * gridDim.x + blockIdx.x;
+        ws[(chunk * C + c) * 2 + 0] = t1;
+        ws[(chunk * C + c) * 2 + 1] = t2;
     }
 }
 
-// one warp per channel: lanes stride over the chunks, fixed-order shuffle tree (deterministic)
-__global__ void bn_stats_final_kernel(const double* __restrict__ ws, int nchunks, int C, int64_t rows, float* mean,
-                                      float* var, float* running_mean, float* running_var, float momentum) {
+// one warp per channel: lanes stride over the chunks, fixed-order shuffle tree (deterministic); the groups' running
+// statistics updates are applied one after the other, as the separate calls would have
+__global__ void bn_stats_final_kernel(const double* __restrict__ ws, int nchunks, int C, int groups,
+                                      int64_t rows_per_group, float* mean, float* var, float* running_mean,
+                                      float* running_var, float momentum) {
     int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     int lane = threadIdx.x & 31;
-    double s1 = 0.0, s2 = 0.0;
-    for (int k = lane; k < nchunks; k += 32) { s1 += ws[((int64_t)k * C + c) * 2]; s2 += ws[((int64_t)k * C + c) * 2 + 1]; }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane != 0) return;
-    double m = s1 / (double)rows;
-    double v = s2 / (double)rows - m * m;
-    if (v < 0.0) v = 0.0;
-    mean[c] = (float)m;
-    var[c] = (float)v;
-    if (running_mean) {
-        double unb = rows > 1 ? v * (double)rows / (double)(rows - 1) : v;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    float rm = 0.f, rv = 0.f;
+    if (running_mean && lane == 0) { rm = running_mean[c]; rv = running_var[c]; }
+    for (int g = 0; g < groups; ++g) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = lane; k < nchunks; k += 32) {
+            const double* p = ws + (((int64_t)g * nchunks + k) * C + c) * 2;
+            s1 += p[0];
+            s2 += p[1];
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            double m = s1 / (double)rows_per_group;
+            double v = s2 / (double)rows_per_group - m * m;
+            if (v < 0.0) v = 0.0;
+            mean[(int64_t)g * C + c] = (float)m;
+            var[(int64_t)g * C + c] = (float)v;
+            double unb = rows_per_group > 1 ? v * (double)rows_per_group / (double)(rows_per_group - 1) : v;
+            rm = (1.f - momentum) * rm + momentum * (float)m;
+            rv = (1.f - momentum) * rv + momentum * (float)unb;
+        }
     }
+    if (running_mean && lane == 0) { running_mean[c] = rm; running_var[c] = rv; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -66,15 +80,16 @@ __global__ void norm_fwd_kernel(const float4* __restrict__ x, float4* __restrict
                                 const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const int32_t* __restrict__ idx, int rows_per_seg, const float4* __restrict__ residual,
-                                int relu) {
+                                int relu, int64_t rows_per_group) {
     int C4 = C >> 2;
     int64_t total = rows * C4;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)(t % C4) << 2;
         int64_t r = t / C4;
         float4 v = x[t];
-        float4 m = *reinterpret_cast<const float4*>(mean + c);
-        float4 vv = *reinterpret_cast<const float4*>(var + c);
+        const int64_t go = (r / rows_per_group) * C;
+        float4 m = *reinterpret_cast<const float4*>(mean + go + c);
+        float4 vv = *reinterpret_cast<const float4*>(var + go + c);
         float4 o;
         o.x = (v.x - m.x) * (1.f / sqrtf(vv.x + eps));
         o.y = (v.y - m.y) * (1.f / sqrtf(vv.y + eps));
@@ -112,14 +127,18 @@ template <int MODE>
 __global__ void norm_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                        const float* __restrict__ y, int64_t rows, int C, const float* __restrict__ mean,
                                        const float* __restrict__ var, float eps, const float* __restrict__ gamma,
-                                       int rows_per_seg, int relu, double* __restrict__ seg_sums) {
+                                       int rows_per_seg, int relu, double* __restrict__ seg_sums,
+                                       int64_t rows_per_group, int segs_per_group) {
     __shared__ double r1[8][33], r2[8][33];
     int c = blockIdx.y * 32 + threadIdx.x;
-    int64_t a = (int64_t)blockIdx.x * rows_per_seg;
-    int64_t b = a + rows_per_seg < rows ? a + rows_per_seg : rows;
+    const int g = blockIdx.x / segs_per_group;
+    const int64_t gend = (int64_t)(g + 1) * rows_per_group;
+    int64_t a = (int64_t)g * rows_per_group + (int64_t)(blockIdx.x - g * segs_per_group) * rows_per_seg;
+    int64_t b = a + rows_per_seg < gend ? a + rows_per_seg : gend;
+    (void)rows;
     double s1 = 0.0, s2 = 0.0;
     if (c < C) {
-        float m = mean[c], rstd = 1.f / sqrtf(var[c] + eps);
+        float m = mean[(int64_t)g * C + c], rstd = 1.f / sqrtf(var[(int64_t)g * C + c] + eps);
         for (int64_t r = a + threadIdx.y; r < b; r += 8) {
             float g = dy[r * C + c];
             if (relu && !(y[r * C + c] > 0.f)) g = 0.f;
@@ -140,35 +159,48 @@ __global__ void norm_bwd_reduce_kernel(const float* __restrict__ dy, const float
     }
 }
 
-// stage 2: s[c] = (sum dxhat, sum dxhat*xhat); parameter gradients.  One warp per channel, fixed-order shuffle tree.
+// stage 2: s[g][c] = (sum dxhat, sum dxhat*xhat) per group; parameter gradients summed over the groups.
+// One warp per channel, fixed-order shuffle tree.
 __global__ void norm_bwd_finalize_kernel(const double* __restrict__ seg, int nseg, int C, int mode,
                                          const float* __restrict__ gamma, const int32_t* __restrict__ idx, float* s,
-                                         float* dgamma, float* dbeta) {
+                                         float* dgamma, float* dbeta, int groups) {
     int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     int lane = threadIdx.x & 31;
-    double s1 = 0.0, s2 = 0.0;
-    if (mode == B200_NORM_CBN) {
-        for (int k = lane; k < nseg; k += 32) {
-            double g = (double)gamma[(int64_t)idx[k] * 2 * C + c];
-            s1 += g * seg[((int64_t)k * C + c) * 2];
-            s2 += g * seg[((int64_t)k * C + c) * 2 + 1];
+    const int spg = nseg / groups;
+    double t1 = 0.0, t2 = 0.0;
+    for (int g = 0; g < groups; ++g) {
+        double s1 = 0.0, s2 = 0.0;
+        if (mode == B200_NORM_CBN) {
+            for (int k = g * spg + lane; k < (g + 1) * spg; k += 32) {
+                double w = (double)gamma[(int64_t)idx[k] * 2 * C + c];
+                s1 += w * seg[((int64_t)k * C + c) * 2];
+                s2 += w * seg[((int64_t)k * C + c) * 2 + 1];
+            }
+        } else {
+            for (int k = g * spg + lane; k < (g + 1) * spg; k += 32) {
+                s1 += seg[((int64_t)k * C + c) * 2];
+                s2 += seg[((int64_t)k * C + c) * 2 + 1];
+            }
         }
-    } else {
-        for (int k = lane; k < nseg; k += 32) { s1 += seg[((int64_t)k * C + c) * 2]; s2 += seg[((int64_t)k * C + c) * 2 + 1]; }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        t1 += s1;
+        t2 += s2;
+        if (lane == 0) {
+            if (mode == B200_NORM_AFFINE) {
+                double w = (double)gamma[c];
+                s1 *= w;
+                s2 *= w;
+            }
+            s[((int64_t)g * C + c) * 2] = (float)s1;
+            s[((int64_t)g * C + c) * 2 + 1] = (float)s2;
+        }
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane != 0) return;
-    if (mode == B200_NORM_AFFINE) {
-        if (dbeta) dbeta[c] = (float)s1;
-        if (dgamma) dgamma[c] = (float)s2;
-        double g = (double)gamma[c];
-        s1 *= g;
-        s2 *= g;
+    if (lane == 0 && mode == B200_NORM_AFFINE) {
+        if (dbeta) dbeta[c] = (float)t1;
+        if (dgamma) dgamma[c] = (float)t2;
     }
-    s[c * 2] = (float)s1;
-    s[c * 2 + 1] = (float)s2;
 }
 
 // CBN embedding gradient: dtable[k][c] = sum_{o: idx[o]==k} sum(dyr*xhat); dtable[k][C+c] = sum_{o} sum(dyr)
@@ -192,10 +224,11 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ dy, const float*
                                       const float* __restrict__ y, float* __restrict__ dx, int64_t rows, int C,
                                       const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                       const float* __restrict__ gamma, const int32_t* __restrict__ idx,
-                                      int rows_per_seg, int relu, const float* __restrict__ s, float* __restrict__ dgb) {
+                                      int rows_per_seg, int relu, const float* __restrict__ s, float* __restrict__ dgb,
+                                      int64_t rows_per_group) {
     const int C4 = C >> 2;
     const int64_t total = rows * C4;
-    const float inv_rows = 1.f / (float)rows;
+    const float inv_rows = 1.f / (float)rows_per_group;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(t % C4) << 2;
         const int64_t r = t / C4;
@@ -210,8 +243,9 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ dy, const float*
             if (!(y4.z > 0.f)) g[2] = 0.f;
             if (!(y4.w > 0.f)) g[3] = 0.f;
         }
-        const float4 m4 = *reinterpret_cast<const float4*>(mean + c);
-        const float4 v4 = *reinterpret_cast<const float4*>(var + c);
+        const int64_t go = (r / rows_per_group) * C;
+        const float4 m4 = *reinterpret_cast<const float4*>(mean + go + c);
+        const float4 v4 = *reinterpret_cast<const float4*>(var + go + c);
         const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
         const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
         float ga[4] = {1.f, 1.f, 1.f, 1.f};
@@ -232,7 +266,7 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ dy, const float*
             const float xh = (xv[e] - mv[e]) * rstd;
             const float dxh = g[e] * ga[e];
             gx[e] = g[e] * xh;
-            o[e] = rstd * (dxh - s[(c + e) * 2] * inv_rows - xh * s[(c + e) * 2 + 1] * inv_rows);
+            o[e] = rstd * (dxh - s[(go + c + e) * 2] * inv_rows - xh * s[(go + c + e) * 2 + 1] * inv_rows);
         }
         if (MODE == B200_NORM_SPADE) {
             *reinterpret_cast<float4*>(dgb + r * 2 * C + c) = make_float4(gx[0], gx[1], gx[2], gx[3]);
@@ -246,25 +280,31 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ dy, const float*
 
 using namespace b200;
 
-extern "C" int b200_bn_stats(const float* x, int64_t rows, int C, float* mean, float* var, float* running_mean,
-                             float* running_var, float momentum, double* ws, b200_stream_t stream) {
-    B200_REQUIRE(rows > 0 && C > 0, "bn_stats: empty input");
-    int nchunks = b200_bn_chunks(rows, C);
-    int64_t rpc = (rows + nchunks - 1) / nchunks;
-    dim3 grid(nchunks, (C + 31) / 32), block(32, 8);
-    bn_stats_partial_kernel<<<grid, block, 0, as_stream(stream)>>>(x, rows, C, rpc, ws);
+extern "C" int b200_bn_stats(const float* x, int64_t rows, int C, int groups, float* mean, float* var,
+                             float* running_mean, float* running_var, float momentum, double* ws,
+                             b200_stream_t stream) {
+    B200_REQUIRE(rows > 0 && C > 0 && groups >= 1 && rows % groups == 0, "bn_stats: bad rows=%lld groups=%d", (long long)rows, groups);
+    B200_REQUIRE(groups < 65536, "bn_stats: too many groups");
+    int64_t rpg = rows / groups;
+    int nchunks = b200_bn_chunks(rpg, C);
+    int64_t rpc = (rpg + nchunks - 1) / nchunks;
+    dim3 grid(nchunks, (C + 31) / 32, groups), block(32, 8);
+    bn_stats_partial_kernel<<<grid, block, 0, as_stream(stream)>>>(x, rpg, C, rpc, ws);
     B200_CHECK_LAUNCH();
-    bn_stats_final_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, nchunks, C, rows, mean, var, running_mean,
+    bn_stats_final_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, nchunks, C, groups, rpg, mean, var, running_mean,
                                                                       running_var, momentum);
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_norm_fwd(const float* x, float* y, int64_t rows, int C, const float* mean, const float* var,
-                             float eps, int mode, const float* gamma, const float* beta, const int32_t* idx,
-                             int rows_per_seg, const float* residual, int relu, b200_stream_t stream) {
+extern "C" int b200_norm_fwd(const float* x, float* y, int64_t rows, int C, int groups, const float* mean,
+                             const float* var, float eps, int mode, const float* gamma, const float* beta,
+                             const int32_t* idx, int rows_per_seg, const float* residual, int relu,
+                             b200_stream_t stream) {
     B200_REQUIRE(C % 4 == 0, "norm_fwd: C=%d must be a multiple of 4", C);
     if (rows == 0) return 0;
+    B200_REQUIRE(groups >= 1 && rows % groups == 0, "norm_fwd: rows %% groups != 0");
+    const int64_t rpg = rows / groups;
     int64_t total = rows * (C / 4);
     int g = grid_for(total, 256);
     cudaStream_t st = as_stream(stream);
@@ -274,16 +314,16 @@ extern "C" int b200_norm_fwd(const float* x, float* y, int64_t rows, int C, cons
     if (rows_per_seg < 1) rows_per_seg = 1;
     switch (mode) {
         case B200_NORM_PLAIN:
-            norm_fwd_kernel<B200_NORM_PLAIN><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu);
+            norm_fwd_kernel<B200_NORM_PLAIN><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu, rpg);
             break;
         case B200_NORM_AFFINE:
-            norm_fwd_kernel<B200_NORM_AFFINE><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu);
+            norm_fwd_kernel<B200_NORM_AFFINE><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu, rpg);
             break;
         case B200_NORM_CBN:
-            norm_fwd_kernel<B200_NORM_CBN><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu);
+            norm_fwd_kernel<B200_NORM_CBN><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu, rpg);
             break;
         case B200_NORM_SPADE:
-            norm_fwd_kernel<B200_NORM_SPADE><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu);
+            norm_fwd_kernel<B200_NORM_SPADE><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu, rpg);
             break;
         default:
             return set_error("norm_fwd: bad mode %d", mode);
@@ -292,28 +332,30 @@ extern "C" int b200_norm_fwd(const float* x, float* y, int64_t rows, int C, cons
     return 0;
 }
 
-extern "C" int b200_norm_bwd_reduce(const float* dy, const float* x, const float* y, int64_t rows, int C,
+extern "C" int b200_norm_bwd_reduce(const float* dy, const float* x, const float* y, int64_t rows, int C, int groups,
                                     const float* mean, const float* var, float eps, int mode, const float* gamma,
                                     const int32_t* idx, int rows_per_seg, int relu, double* seg_sums,
                                     b200_stream_t stream) {
     (void)idx;
-    B200_REQUIRE(rows > 0 && rows_per_seg > 0, "norm_bwd_reduce: empty input");
-    int nseg = (int)((rows + rows_per_seg - 1) / rows_per_seg);
-    dim3 grid(nseg, (C + 31) / 32), block(32, 8);
+    B200_REQUIRE(rows > 0 && rows_per_seg > 0 && groups >= 1 && rows % groups == 0, "norm_bwd_reduce: bad sizes");
+    const int64_t rpg = rows / groups;
+    const int spg = (int)((rpg + rows_per_seg - 1) / rows_per_seg);
+    dim3 grid(spg * groups, (C + 31) / 32), block(32, 8);
     cudaStream_t st = as_stream(stream);
     if (mode == B200_NORM_SPADE)
-        norm_bwd_reduce_kernel<B200_NORM_SPADE><<<grid, block, 0, st>>>(dy, x, y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums);
+        norm_bwd_reduce_kernel<B200_NORM_SPADE><<<grid, block, 0, st>>>(dy, x, y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg);
     else
-        norm_bwd_reduce_kernel<B200_NORM_PLAIN><<<grid, block, 0, st>>>(dy, x, y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums);
+        norm_bwd_reduce_kernel<B200_NORM_PLAIN><<<grid, block, 0, st>>>(dy, x, y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg);
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, int mode, const float* gamma,
+extern "C" int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, int groups, int mode, const float* gamma,
                                       const int32_t* idx, int num_classes, float* s, float* dgamma, float* dbeta,
                                       float* dtable, b200_stream_t stream) {
     cudaStream_t st = as_stream(stream);
-    norm_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(seg_sums, nseg, C, mode, gamma, idx, s, dgamma, dbeta);
+    B200_REQUIRE(groups >= 1 && nseg % groups == 0, "norm_bwd_finalize: nseg %% groups != 0");
+    norm_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(seg_sums, nseg, C, mode, gamma, idx, s, dgamma, dbeta, groups);
     B200_CHECK_LAUNCH();
     if (mode == B200_NORM_CBN && dtable) {
         cbn_dtable_kernel<<<grid_for((int64_t)num_classes * C, 128), 128, 0, st>>>(seg_sums, nseg, C, idx, num_classes, dtable);
@@ -323,27 +365,29 @@ extern "C" int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, i
 }
 
 extern "C" int b200_norm_bwd_apply(const float* dy, const float* x, const float* y, float* dx, int64_t rows, int C,
-                                   const float* mean, const float* var, float eps, int mode, const float* gamma,
-                                   const int32_t* idx, int rows_per_seg, int relu, const float* s, float* dgb,
-                                   b200_stream_t stream) {
+                                   int groups, const float* mean, const float* var, float eps, int mode,
+                                   const float* gamma, const int32_t* idx, int rows_per_seg, int relu, const float* s,
+                                   float* dgb, b200_stream_t stream) {
     if (rows == 0) return 0;
     B200_REQUIRE(C % 4 == 0, "norm_bwd_apply: C=%d must be a multiple of 4", C);
+    B200_REQUIRE(groups >= 1 && rows % groups == 0, "norm_bwd_apply: rows %% groups != 0");
+    const int64_t rpg = rows / groups;
     int g = grid_for(rows * (C / 4), 256);
     cudaStream_t st = as_stream(stream);
     if (rows_per_seg < 1) rows_per_seg = 1;
     switch (mode) {
         case B200_NORM_PLAIN:
-            norm_bwd_apply_kernel<B200_NORM_PLAIN><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb);
+            norm_bwd_apply_kernel<B200_NORM_PLAIN><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb, rpg);
             break;
         case B200_NORM_AFFINE:
-            norm_bwd_apply_kernel<B200_NORM_AFFINE><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb);
+            norm_bwd_apply_kernel<B200_NORM_AFFINE><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb, rpg);
             break;
         case B200_NORM_CBN:
-            norm_bwd_apply_kernel<B200_NORM_CBN><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb);
+            norm_bwd_apply_kernel<B200_NORM_CBN><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb, rpg);
             break;
         case B200_NORM_SPADE:
             B200_REQUIRE(dgb != nullptr, "norm_bwd_apply: SPADE needs dgb");
-            norm_bwd_apply_kernel<B200_NORM_SPADE><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb);
+            norm_bwd_apply_kernel<B200_NORM_SPADE><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb, rpg);
             break;
         default:
             return set_error("norm_bwd_apply: bad mode %d", mode);

@@ -66,7 +66,7 @@ __global__ void sn_wv_kernel(const float* __restrict__ W, const float* __restric
 
 // do_iter: u = wv / max(||wv||, eps); sigma = u . wv; out2 = [sigma, 1/sigma]
 __global__ void sn_norm_u_kernel(const float* __restrict__ wv, int h, float eps, int do_iter, float* __restrict__ u,
-                                 float* __restrict__ out2) {
+                                 float* __restrict__ sigma_out, float* __restrict__ inv_out) {
     __shared__ float red[33];
     float ss = 0.f;
     for (int i = threadIdx.x; i < h; i += 1024) ss += wv[i] * wv[i];
@@ -80,8 +80,8 @@ __global__ void sn_norm_u_kernel(const float* __restrict__ wv, int h, float eps,
     }
     float sigma = block_sum_1024(dot, red);
     if (threadIdx.x == 0) {
-        out2[0] = sigma;
-        out2[1] = 1.f / sigma;
+        if (sigma_out) *sigma_out = sigma;
+        *inv_out = 1.f / sigma;
     }
 }
 
@@ -101,18 +101,18 @@ __global__ void sn_dot_partial_kernel(const float* __restrict__ g, const float* 
     }
 }
 __global__ void sn_dot_final_kernel(double* part, int nblocks) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int k = 0; k < nblocks; ++k) s += part[1 + k];
-        part[0] = s;
-    }
+    // one warp, fixed order: lanes stride over the block partials, shuffle tree
+    double s = 0.0;
+    for (int k = threadIdx.x; k < nblocks; k += 32) s += part[1 + k];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) part[0] = s;
 }
 __global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* __restrict__ u,
-                                     const float* __restrict__ v, const float* __restrict__ sig2,
+                                     const float* __restrict__ v, const float* __restrict__ inv_sigma,
                                      const double* __restrict__ part, float* __restrict__ dW, int h, int w,
                                      int accumulate) {
     int64_t n = (int64_t)h * w;
-    float inv = sig2[1];
+    float inv = *inv_sigma;
     float coef = (float)(part[0]) * inv * inv;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
         int j = (int)(t % w);
@@ -127,7 +127,7 @@ __global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* _
 using namespace b200;
 
 extern "C" int b200_sn_power_iter(const float* W, int h, int w, float* u, float* v, int do_iter, float eps,
-                                  float* out2, float* ws, b200_stream_t stream) {
+                                  float* sigma_out, float* inv_sigma_out, float* ws, b200_stream_t stream) {
     cudaStream_t st = as_stream(stream);
     float* partial = ws;                       // kSnRowChunks * w
     float* wv = ws + (int64_t)kSnRowChunks * w;  // h
@@ -142,12 +142,12 @@ extern "C" int b200_sn_power_iter(const float* W, int h, int w, float* u, float*
     }
     sn_wv_kernel<<<(h + 7) / 8, 256, 0, st>>>(W, v, h, w, wv);
     B200_CHECK_LAUNCH();
-    sn_norm_u_kernel<<<1, 1024, 0, st>>>(wv, h, eps, do_iter, u, out2);
+    sn_norm_u_kernel<<<1, 1024, 0, st>>>(wv, h, eps, do_iter, u, sigma_out, inv_sigma_out);
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_sn_grad(const float* g, const float* W, const float* u, const float* v, const float* sig2,
+extern "C" int b200_sn_grad(const float* g, const float* W, const float* u, const float* v, const float* inv_sigma,
                             float* dW, int h, int w, int accumulate, double* ws, b200_stream_t stream) {
     cudaStream_t st = as_stream(stream);
     int64_t n = (int64_t)h * w;
@@ -157,7 +157,7 @@ extern "C" int b200_sn_grad(const float* g, const float* W, const float* u, cons
     B200_CHECK_LAUNCH();
     sn_dot_final_kernel<<<1, 32, 0, st>>>(ws, nblocks);
     B200_CHECK_LAUNCH();
-    sn_grad_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(g, u, v, sig2, ws, dW, h, w, accumulate);
+    sn_grad_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(g, u, v, inv_sigma, ws, dW, h, w, accumulate);
     B200_CHECK_LAUNCH();
     return 0;
 }

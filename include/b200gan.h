@@ -60,7 +60,7 @@ int b200_crop_bwd(const float* dcrops, const float* boxes, const int32_t* img_bo
  *       epilogue( sum_{ty<Th, tx<Tw, c<Cin} in[n, (qy*in_sy + ty*tap_sy + tap_oy) >> up, (qx*in_sx + ...) >> up, c]
  *                                          * wmat[co, (ty*Tw+tx)*Cin + c] )
  * taps outside [0,Hi)x[0,Wi) (logical, i.e. after upsampling) read zero; outputs outside [0,Ho)x[0,Wo) are dropped.
- * epilogue(v) = relu?( v * (*scale if scale) + bias[co] ).
+ * epilogue(v) = relu?( v * (scale ? scale[scale_rows ? m / scale_rows : 0] : 1) + bias[co] ), m = output row index.
  */
 typedef struct {
     int B, Qh, Qw;                 /* output grid: rows M = B*Qh*Qw */
@@ -77,6 +77,7 @@ typedef struct {
     int64_t out_sn, out_sh, out_sw, out_sc; /* output element strides */
     int64_t ldw;                   /* row stride (elements) of wmat */
     int relu;
+    int scale_rows;                /* 0: one scalar *scale; > 0: scale[m / scale_rows] (per-group 1/sigma of batched calls) */
 } b200_conv_desc;
 
 /* fp32 CUDA-core path (bit-tight parity mode). wmat fp32 [Cout][ldw]. */
@@ -129,30 +130,38 @@ int b200_pack_weight(const float* src, void* dst, int dst_bf16, int M, int Mpad,
  * SPADE's param-free BN + modulation (normalization.py:94-108), fused with ReLU / residual add.
  * x, y: (rows, C) channel-last fp32.
  */
-/* batch statistics (biased var) + running-stat update (momentum, unbiased var) — F.batch_norm training semantics.
- * ws: 2*C*nchunks doubles, nchunks = b200_bn_chunks(rows, C). running_* may be NULL. */
+/* `groups`: several independent calls of the same layer batched along the row dimension (rows = groups *
+ * rows_per_group, group g = rows [g*rows_per_group, (g+1)*rows_per_group)) keep SEPARATE batch statistics — this is how
+ * the three generator passes / the fake+real discriminator passes of one step share a launch without merging
+ * their statistics.  mean, var are (groups, C); running statistics receive the groups' updates in order.
+ *
+ * batch statistics (biased var) + running-stat update (momentum, unbiased var) — F.batch_norm training semantics.
+ * ws: 2*C*groups*b200_bn_chunks(rows/groups, C) doubles. running_* may be NULL. */
 int b200_bn_chunks(int64_t rows, int C);
-int b200_bn_stats(const float* x, int64_t rows, int C, float* mean, float* var, float* running_mean,
+int b200_bn_stats(const float* x, int64_t rows, int C, int groups, float* mean, float* var, float* running_mean,
                   float* running_var, float momentum, double* ws, b200_stream_t stream);
 enum { B200_NORM_PLAIN = 0, B200_NORM_AFFINE = 1, B200_NORM_CBN = 2, B200_NORM_SPADE = 3 };
 /* y = relu?( residual? + (x-mean)*rsqrt(var+eps) * g + b ):
  *   PLAIN g=1,b=0 | AFFINE g=gamma[c], b=beta[c] | CBN g=table[idx[row/rows_per_seg]][c], b=table[..][C+c]
  *   | SPADE g=1+gb[row][c], b=gb[row][C+c]  (gb = the fused gamma|beta conv output, (rows,2C)) */
-int b200_norm_fwd(const float* x, float* y, int64_t rows, int C, const float* mean, const float* var, float eps,
-                  int mode, const float* gamma, const float* beta, const int32_t* idx, int rows_per_seg,
+int b200_norm_fwd(const float* x, float* y, int64_t rows, int C, int groups, const float* mean, const float* var,
+                  float eps, int mode, const float* gamma, const float* beta, const int32_t* idx, int rows_per_seg,
                   const float* residual, int relu, b200_stream_t stream);
 /* backward, stage 1: per-segment sums of (dyr*g, dyr*g*xhat) [and for CBN the raw (dyr, dyr*xhat)] where dyr = dy masked by
- * y>0 when relu; seg_sums: (nseg, C, 2) doubles, nseg = rows / rows_per_seg.  For CBN pass rows_per_seg = H*W. */
-int b200_norm_bwd_reduce(const float* dy, const float* x, const float* y, int64_t rows, int C, const float* mean,
-                         const float* var, float eps, int mode, const float* gamma, const int32_t* idx,
-                         int rows_per_seg, int relu, double* seg_sums, b200_stream_t stream);
-/* stage 2: combine segments in fixed order -> s (C,2) floats = (sum dxhat, sum dxhat*xhat); parameter gradients:
- * AFFINE: dgamma[c], dbeta[c]; CBN: dtable (num_classes, 2C) deterministic segmented sum by class (dtable is overwritten). */
-int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, int mode, const float* gamma, const int32_t* idx,
-                           int num_classes, float* s, float* dgamma, float* dbeta, float* dtable,
+ * y>0 when relu; segments never straddle a group: seg_sums is (groups * ceil(rows_per_group / rows_per_seg), C, 2)
+ * doubles.  For CBN pass rows_per_seg = H*W. */
+int b200_norm_bwd_reduce(const float* dy, const float* x, const float* y, int64_t rows, int C, int groups,
+                         const float* mean, const float* var, float eps, int mode, const float* gamma,
+                         const int32_t* idx, int rows_per_seg, int relu, double* seg_sums, b200_stream_t stream);
+/* stage 2: combine segments in fixed order -> s (groups, C, 2) floats = (sum dxhat, sum dxhat*xhat); parameter gradients
+ * (summed over groups): AFFINE: dgamma[c], dbeta[c]; CBN: dtable (num_classes, 2C) deterministic segmented sum by class
+ * (dtable is overwritten). */
+int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, int groups, int mode, const float* gamma,
+                           const int32_t* idx, int num_classes, float* s, float* dgamma, float* dbeta, float* dtable,
                            b200_stream_t stream);
-/* stage 3: dx = rstd*(dxhat - s1/rows - xhat*s2/rows); SPADE additionally writes dgb (rows,2C) = (dyr*xhat | dyr). */
-int b200_norm_bwd_apply(const float* dy, const float* x, const float* y, float* dx, int64_t rows, int C,
+/* stage 3: dx = rstd*(dxhat - s1/rows_per_group - xhat*s2/rows_per_group); SPADE additionally writes dgb (rows,2C) =
+ * (dyr*xhat | dyr). */
+int b200_norm_bwd_apply(const float* dy, const float* x, const float* y, float* dx, int64_t rows, int C, int groups,
                         const float* mean, const float* var, float eps, int mode, const float* gamma,
                         const int32_t* idx, int rows_per_seg, int relu, const float* s, float* dgb,
                         b200_stream_t stream);
@@ -207,14 +216,17 @@ int b200_permute_rows(const float* x, const int32_t* src_row, float* out, int ro
 /* ------------------------------------------------------------------------------------------------
  * Spectral normalisation — replaces torch.nn.utils.spectral_norm's pre-forward hook installed by add_sn
  * (discriminator.py:15-22): one power iteration in place on u (h) and v (w), sigma = u.(W v); W (h,w) row-major
- * view of weight_orig.  out2 = [sigma, 1/sigma].  ws: 8*w + h floats.
+ * view of weight_orig.  *sigma_out = sigma, *inv_sigma_out = 1/sigma.  ws: 8*w + h floats.
  * b200_sn_grad: dW = g*inv_sigma - (<g, W> * inv_sigma^2) * u v^T  (gradient through W/sigma with u, v constant),
  * g = gradient w.r.t. the normalised weight, same layout as W.  ws: 1024 doubles.
  */
-int b200_sn_power_iter(const float* W, int h, int w, float* u, float* v, int do_iter, float eps, float* out2,
-                       float* ws, b200_stream_t stream);
-int b200_sn_grad(const float* g, const float* W, const float* u, const float* v, const float* sig2, float* dW, int h,
+int b200_sn_power_iter(const float* W, int h, int w, float* u, float* v, int do_iter, float eps, float* sigma_out,
+                       float* inv_sigma_out, float* ws, b200_stream_t stream);
+int b200_sn_grad(const float* g, const float* W, const float* u, const float* v, const float* inv_sigma, float* dW, int h,
                  int w, int accumulate, double* ws, b200_stream_t stream);
+
+/* plain device-to-device copy on the stream (row concatenation of batched calls) */
+int b200_copy(void* dst, const void* src, size_t bytes, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -140,7 +140,11 @@ class EmulKernels:
             A2 = A2.to(torch.bfloat16).float()
         y = A2 @ Wm.t()
         if scale is not None:
-            y = y * scale.reshape(-1)[0]
+            sr = getattr(d, "scale_rows", 0)
+            if sr > 0:
+                y = y * scale.reshape(-1)[(torch.arange(y.shape[0]) // sr)][:, None]
+            else:
+                y = y * scale.reshape(-1)[0]
         if bias is not None:
             y = y + bias[None]
         if d.relu:
@@ -194,17 +198,18 @@ class EmulKernels:
         dst[dst_row_offset:dst_row_offset + Mpad] = out.to(dst.dtype)
 
     # ---- normalisation --------------------------------------------------------------------------------------
-    def bn_stats(self, x2d, running_mean, running_var, momentum):
+    def bn_stats(self, x2d, running_mean, running_var, momentum, groups=1):
         self.launches += 2
-        rows = x2d.shape[0]
-        xd = x2d.double()
-        mean = xd.mean(0)
-        var = (xd * xd).mean(0) - mean * mean
-        var = var.clamp(min=0)
+        rows, C = x2d.shape
+        rpg = rows // groups
+        xd = x2d.double().view(groups, rpg, C)
+        mean = xd.mean(1)
+        var = ((xd * xd).mean(1) - mean * mean).clamp(min=0)
         if running_mean is not None:
-            unb = var * rows / (rows - 1) if rows > 1 else var
-            running_mean.mul_(1 - momentum).add_(momentum * mean.float())
-            running_var.mul_(1 - momentum).add_(momentum * unb.float())
+            for g in range(groups):
+                unb = var[g] * rpg / (rpg - 1) if rpg > 1 else var[g]
+                running_mean.mul_(1 - momentum).add_(momentum * mean[g].float())
+                running_var.mul_(1 - momentum).add_(momentum * unb.float())
         return mean.float(), var.float()
 
     @staticmethod
@@ -218,27 +223,32 @@ class EmulKernels:
             return t[:, :C], t[:, C:]
         return 1 + gamma[:, :C], gamma[:, C:]
 
-    def norm_fwd(self, x2d, mean, var, eps, mode, gamma, beta, idx, rows_per_seg, residual, relu):
+    def norm_fwd(self, x2d, mean, var, eps, mode, gamma, beta, idx, rows_per_seg, residual, relu, groups=1):
         self.launches += 1
         rows, C = x2d.shape
-        xh = (x2d - mean[None]) * (1.0 / torch.sqrt(var + eps))[None]
+        rpg = rows // groups
+        mean_r = mean.view(groups, C).repeat_interleave(rpg, dim=0)
+        rstd_r = (1.0 / torch.sqrt(var.view(groups, C) + eps)).repeat_interleave(rpg, dim=0)
+        xh = (x2d - mean_r) * rstd_r
         g, b = self._g_b(mode, gamma, beta, idx, rows_per_seg, rows, C)
         y = xh if g is None else xh * g + b
         if residual is not None:
             y = y + residual
         return F.relu(y) if relu else y
 
-    def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes):
+    def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes, groups=1):
         self.launches += 4
         rows, C = x2d.shape
-        rstd = 1.0 / torch.sqrt(var + eps)
-        xh = (x2d - mean[None]) * rstd[None]
+        rpg = rows // groups
+        mean_r = mean.view(groups, C).repeat_interleave(rpg, dim=0)
+        rstd_r = (1.0 / torch.sqrt(var.view(groups, C) + eps)).repeat_interleave(rpg, dim=0)
+        xh = (x2d - mean_r) * rstd_r
         g = dy * (y > 0).to(dy.dtype) if relu else dy
         gm, _ = self._g_b(mode, gamma, gamma if mode == MODE_AFFINE else None, idx, rows_per_seg, rows, C)
         dxh = g if gm is None else g * gm
-        s1 = dxh.double().sum(0).float()
-        s2 = (dxh.double() * xh.double()).sum(0).float()
-        dx = rstd[None] * (dxh - s1[None] / rows - xh * s2[None] / rows)
+        s1 = dxh.double().view(groups, rpg, C).sum(1).float().repeat_interleave(rpg, dim=0)
+        s2 = (dxh.double() * xh.double()).view(groups, rpg, C).sum(1).float().repeat_interleave(rpg, dim=0)
+        dx = rstd_r * (dxh - s1 / rpg - xh * s2 / rpg)
         dgamma = dbeta = dtable = dgb = None
         if mode == MODE_AFFINE:
             dgamma = (g.double() * xh.double()).sum(0).float()
@@ -370,7 +380,7 @@ class EmulKernels:
         return x2d.double().sum(0).float()
 
     # ---- spectral norm ------------------------------------------------------------------------------------------
-    def sn_power_iter(self, W, h, w, u, v, do_iter, eps):
+    def sn_power_iter(self, W, h, w, u, v, do_iter, eps, inv_out=None, sigma_out=None):
         self.launches += 4
         Wm = W.detach().reshape(h, w)
         if do_iter:
@@ -380,10 +390,26 @@ class EmulKernels:
         else:
             wv = torch.mv(Wm, v)
         sigma = torch.dot(u, wv)
-        return torch.stack([sigma, 1.0 / sigma])
+        if inv_out is None:
+            inv_out = torch.empty(1)
+        inv_out.copy_((1.0 / sigma).reshape(1))
+        if sigma_out is not None:
+            sigma_out.copy_(sigma.reshape(1))
+        return inv_out
 
-    def sn_grad(self, g, W, u, v, sig2, h, w):
+    def sn_grad(self, g, W, u, v, inv_sigma, h, w, dW=None, accumulate=False):
         self.launches += 3
-        inv = sig2[1]
+        inv = inv_sigma.reshape(-1)[0]
         dot = (g.double() * W.detach().double()).sum().float()
-        return (g.reshape(h, w) * inv - dot * inv * inv * torch.outer(u, v)).reshape(W.shape)
+        val = (g.reshape(h, w) * inv - dot * inv * inv * torch.outer(u, v)).reshape(W.shape)
+        if dW is None:
+            return val
+        if accumulate:
+            dW += val
+        else:
+            dW.copy_(val)
+        return dW
+
+    def copy_into(self, dst, dst_row, src):
+        self.launches += 1
+        dst[dst_row:dst_row + src.shape[0]].copy_(src)

@@ -241,11 +241,14 @@ def test_sn_power_iteration(K, h, w):
 # ---------------------------------------------------------------------------------------------------------
 # normalisation
 # ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("groups", [1, 3])
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("relu", [False, True])
-def test_norm_fwd_bwd(K, mode, relu):
+def test_norm_fwd_bwd(K, mode, relu, groups):
+    """groups > 1: independent calls batched along the rows keep separate statistics (and sequential running-stat
+    updates); the emulation restates exactly that."""
     g = torch.Generator().manual_seed(10 + mode)
-    O_, hw, C, ncls = 6, 20, 64, 9
+    O_, hw, C, ncls = 6 * groups, 20, 64, 9
     rows = O_ * hw
     x = torch.randn(rows, C, generator=g) * 2 + 0.5
     idx = torch.randint(0, ncls, (O_,), generator=g).to(torch.int32)
@@ -259,20 +262,24 @@ def test_norm_fwd_bwd(K, mode, relu):
         gamma = beta = None
     rm, rv = torch.zeros(C), torch.ones(C)
     rmd, rvd = rm.cuda(), rv.cuda()
-    mean_d, var_d = K.bn_stats(x.cuda(), rmd, rvd, 0.1)
-    mean_c, var_c = E.bn_stats(x, rm, rv, 0.1)
+    x = x + torch.arange(groups).repeat_interleave(rows // groups)[:, None].float()      # distinct group statistics
+    mean_d, var_d = K.bn_stats(x.cuda(), rmd, rvd, 0.1, groups)
+    mean_c, var_c = E.bn_stats(x, rm, rv, 0.1, groups)
+    if groups > 1:
+        sep = [E.bn_stats(x[i * rows // groups:(i + 1) * rows // groups], None, None, 0.1)[0] for i in range(groups)]
+        close(mean_c, torch.cat(sep), 1e-6, "grouped stats == separate calls")
     close(mean_d, mean_c, 1e-6, "mean")
     close(var_d, var_c, 1e-6, "var")
     close(rmd, rm, 1e-6, "running_mean")
     close(rvd, rv, 1e-6, "running_var")
     res = torch.randn(rows, C, generator=g) if (mode == 1 and not relu) else None
     a = cu(x, mean_c, var_c)
-    yd = K.norm_fwd(a[0], a[1], a[2], 1e-5, mode, *cu(gamma, beta, idx if mode == 2 else None), hw, *cu(res), relu)
-    yc = E.norm_fwd(x, mean_c, var_c, 1e-5, mode, gamma, beta, idx, hw, res, relu)
+    yd = K.norm_fwd(a[0], a[1], a[2], 1e-5, mode, *cu(gamma, beta, idx if mode == 2 else None), hw, *cu(res), relu, groups)
+    yc = E.norm_fwd(x, mean_c, var_c, 1e-5, mode, gamma, beta, idx, hw, res, relu, groups)
     close(yd, yc, 1e-6, "norm fwd")
     dy = torch.randn(rows, C, generator=g)
-    outs_d = K.norm_bwd(*cu(dy, x, yc, mean_c, var_c), 1e-5, mode, *cu(gamma, idx if mode == 2 else None), hw, relu, ncls)
-    outs_c = E.norm_bwd(dy, x, yc, mean_c, var_c, 1e-5, mode, gamma, idx, hw, relu, ncls)
+    outs_d = K.norm_bwd(*cu(dy, x, yc, mean_c, var_c), 1e-5, mode, *cu(gamma, idx if mode == 2 else None), hw, relu, ncls, groups)
+    outs_c = E.norm_bwd(dy, x, yc, mean_c, var_c, 1e-5, mode, gamma, idx, hw, relu, ncls, groups)
     for name, d, c in zip(("dx", "dgamma", "dbeta", "dtable", "dgb"), outs_d, outs_c):
         assert (d is None) == (c is None), name
         if d is not None:
