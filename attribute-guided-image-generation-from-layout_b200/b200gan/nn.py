@@ -10,8 +10,26 @@ from . import ops
 from .ops import ConvGeom, WeightPacks
 
 
-def _sn_state(m):
-    return (m.weight_u, m.weight_v) if getattr(m, "_b200_sn", False) else None
+def _sn_call(m, groups=1):
+    """The spectral-norm evaluation this forward uses: the one `sn_prepare` staged for the layer, else `groups` power
+    iterations run here (torch.nn.utils.spectral_norm's pre-forward hook, once per batched call)."""
+    if not getattr(m, "_b200_sn", False):
+        return None
+    staged = m.__dict__.pop("_sn_staged", None)
+    if staged is not None and staged.groups == groups:
+        return staged
+    return ops.sn_iterate(m.weight_orig, m.weight_u, m.weight_v, groups, m.training)
+
+
+def sn_prepare(net, groups=1):
+    """Run the power iterations of every spectral-normalised layer below `net` up front (they depend on the weights
+    only), `groups` per layer for `groups` batched calls, and stage the results for the layers' next forward."""
+    layers = net.__dict__.get("_sn_layers")
+    if layers is None:
+        layers = [m for m in net.modules() if getattr(m, "_b200_sn", False)]
+        net.__dict__["_sn_layers"] = layers
+    for m in layers:
+        m.__dict__["_sn_staged"] = ops.sn_iterate(m.weight_orig, m.weight_u, m.weight_v, groups, m.training)
 
 
 def _weight(m):
@@ -27,9 +45,10 @@ class Conv2d(nn.Conv2d):
                               self.stride[0], self.padding[0])
         self._packs = WeightPacks()
 
-    def forward(self, x, x_layout="cl", out_layout="cl", relu=False):
+    def forward(self, x, x_layout="cl", out_layout="cl", relu=False, groups=1):
+        """groups: number of independent calls batched along dim 0 (each gets its own spectral-norm iteration)"""
         return ops.conv2d(x, _weight(self), self.bias, self._geom, self._packs, x_layout, out_layout, relu,
-                          _sn_state(self), self.training)
+                          _sn_call(self, groups))
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):
@@ -53,26 +72,27 @@ class Linear(nn.Linear):
         super().__init__(*a, **kw)
         self._packs = WeightPacks()
 
-    def forward(self, x, relu=False):
-        return ops.linear(x, _weight(self), self.bias, self._packs, relu, _sn_state(self), self.training)
+    def forward(self, x, relu=False, groups=1):
+        return ops.linear(x, _weight(self), self.bias, self._packs, relu, _sn_call(self, groups))
 
 
 class BatchNorm2d(nn.BatchNorm2d):
     """Works on (..., C) channel-last tensors (also serves BatchNorm1d's (B, C) case)."""
 
-    def forward(self, x, relu=False, residual=None):
+    def forward(self, x, relu=False, residual=None, groups=1):
         if self.training and self.track_running_stats:
-            self.num_batches_tracked.add_(1)
+            self.num_batches_tracked.add_(groups)
         w = self.weight if self.affine else None
         b = self.bias if self.affine else None
-        return ops.batch_norm(x, w, b, self.running_mean, self.running_var, self.training, relu, residual)
+        return ops.batch_norm(x, w, b, self.running_mean, self.running_var, self.training, relu, residual, groups)
 
 
 class BatchNorm1d(nn.BatchNorm1d):
-    def forward(self, x, relu=False):
+    def forward(self, x, relu=False, groups=1):
         if self.training and self.track_running_stats:
-            self.num_batches_tracked.add_(1)
-        return ops.batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var, self.training, relu)
+            self.num_batches_tracked.add_(groups)
+        return ops.batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var, self.training, relu, None,
+                              groups)
 
 
 class Embedding(nn.Embedding):

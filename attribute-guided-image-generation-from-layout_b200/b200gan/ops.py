@@ -170,6 +170,14 @@ def _need_f32(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
+def _scale_rows(scale, rows: int) -> int:
+    """rows of the GEMM that share one entry of `scale` (0 = a single scalar): batched spectral-norm calls"""
+    if scale is None or scale.numel() == 1:
+        return 0
+    assert rows % scale.numel() == 0, (rows, scale.numel())
+    return rows // scale.numel()
+
+
 def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bias=None, scale=None, relu=False):
     """Y = epilogue(conv(X, W)); on the tcgen05 path x may be passed already cast (as_bf16)"""
     N, Hx, Wx, Cx, xs = _dims(x, x_layout)
@@ -182,7 +190,7 @@ def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bi
     d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=g.Cx, Cout=g.Cy, Th=g.kh, Tw=g.kw, in_sy=g.s, in_sx=g.s, tap_sy=1, tap_sx=1,
                  tap_oy=-g.p, tap_ox=-g.p, Hi=Hx, Wi=Wx, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3],
                  out_sy=1, out_sx=1, out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ys[0], out_sh=ys[1], out_sw=ys[2],
-                 out_sc=ys[3], ldw=ldw, relu=int(relu))
+                 out_sc=ys[3], ldw=ldw, relu=int(relu), scale_rows=_scale_rows(scale, N * Hy * Wy))
     _lib.K.conv_gemm(d, x, wmat, bias, scale, y, tc)
     return y
 
@@ -209,7 +217,8 @@ def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layo
         d = ConvDesc(B=N, Qh=Qh, Qw=Qw, Cin=g.Cy, Cout=g.Cx, Th=Th, Tw=Tw, in_sy=1, in_sx=1, tap_sy=-1, tap_sx=-1,
                      tap_oy=(py + g.p - ky0) // g.s, tap_ox=(px + g.p - kx0) // g.s, Hi=Hy, Wi=Wy, up_shift=0,
                      in_sn=ds[0], in_sh=ds[1], in_sw=ds[2], in_sc=ds[3], out_sy=g.s, out_sx=g.s, out_oy=py, out_ox=px,
-                     Ho=Hx, Wo=Wx, out_sn=xs[0], out_sh=xs[1], out_sw=xs[2], out_sc=xs[3], ldw=ldw, relu=0)
+                     Ho=Hx, Wo=Wx, out_sn=xs[0], out_sh=xs[1], out_sw=xs[2], out_sc=xs[3], ldw=ldw, relu=0,
+                     scale_rows=_scale_rows(scale, N * Qh * Qw))
         _lib.K.conv_gemm(d, dy, wmat, None, scale, dx, tc)
     return dx
 
@@ -276,17 +285,36 @@ def bias_grad(dy: torch.Tensor, layout: str) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------
 # convolution / transposed convolution / linear  (+ optional spectral norm, bias, fused ReLU)
 # ----------------------------------------------------------------------------------------------------------
+class SNCall:
+    """State of one (possibly batched) spectral-norm evaluation of a layer: `groups` sequential power iterations
+    (one per batched call, torch.nn.utils.spectral_norm's pre-forward hook run `groups` times) -> inv (groups,) = 1/sigma
+    per call and the u, v vectors each call's sigma was computed with (u_hist (groups,h), v_hist (groups,w))."""
+
+    __slots__ = ("groups", "inv", "u_hist", "v_hist")
+
+    def __init__(self, groups, inv, u_hist, v_hist):
+        self.groups, self.inv, self.u_hist, self.v_hist = groups, inv, u_hist, v_hist
+
+
+def sn_iterate(w, u, v, groups: int, training: bool) -> SNCall:
+    """`groups` power iterations of one layer, in place on its u / v buffers (discriminator.py:15-22 hook semantics)"""
+    h, wd = w.shape[0], w[0].numel()
+    inv = torch.empty((groups,), dtype=torch.float32, device=w.device)
+    u_hist = torch.empty((groups, h), dtype=torch.float32, device=w.device)
+    v_hist = torch.empty((groups, wd), dtype=torch.float32, device=w.device)
+    for gi in range(groups):
+        _lib.K.sn_power_iter(w, h, wd, u, v, training, SN_EPS, inv_out=inv[gi:gi + 1])
+        _lib.K.copy_into(u_hist, gi, u.view(1, h))
+        _lib.K.copy_into(v_hist, gi, v.view(1, wd))
+    return SNCall(groups, inv, u_hist, v_hist)
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, sn_u, sn_v, g: ConvGeom, packs: WeightPacks, transposed: bool, x_layout: str,
-                out_layout: str, relu: bool, training: bool, out_hw):
-        scale = None
-        if sn_u is not None:
-            h, wd = w.shape[0], w[0].numel()
-            scale = _lib.K.sn_power_iter(w, h, wd, sn_u, sn_v, training, SN_EPS)      # (1,) = 1/sigma
-            ctx.sn = (sn_u.clone(), sn_v.clone(), scale)
-        else:
-            ctx.sn = None
+    def forward(ctx, x, w, bias, sn: Optional[SNCall], g: ConvGeom, packs: WeightPacks, transposed: bool, x_layout: str,
+                out_layout: str, relu: bool, out_hw):
+        scale = sn.inv if sn is not None else None
+        ctx.sn = sn
         if not transposed:
             fwd_tc, wgrad_tc = _tc_fwd_ok(g, x_layout), _tc_wgrad_ok(g, x_layout, out_layout)
         else:
@@ -307,11 +335,11 @@ class _ConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
-        g, packs = ctx.g, ctx.packs
+        g, packs, sn = ctx.g, ctx.packs, ctx.sn
         dy = dy.contiguous()
         if ctx.relu:
             dy = _lib.K.relu_bwd(dy, y)
-        scale = ctx.sn[2] if ctx.sn is not None else None
+        scale = sn.inv if sn is not None else None
         dx = dw = db = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not ctx.transposed:
@@ -329,36 +357,41 @@ class _ConvFn(torch.autograd.Function):
         if need_dw:
             gw = torch.empty_like(w)
             dy_op = dyb if wgrad_tc else dy
-            if not ctx.transposed:
-                conv_wgrad(g, x, ctx.x_layout, dy_op, ctx.out_layout, gw)
-            else:
-                conv_wgrad(g, dy_op, ctx.out_layout, x, ctx.x_layout, gw)
-            if ctx.sn is not None:
-                u, v, inv_sigma = ctx.sn
-                dw = _lib.K.sn_grad(gw, w, u, v, inv_sigma, w.shape[0], w[0].numel())
-            else:
+            if sn is None:
+                if not ctx.transposed:
+                    conv_wgrad(g, x, ctx.x_layout, dy_op, ctx.out_layout, gw)
+                else:
+                    conv_wgrad(g, dy_op, ctx.out_layout, x, ctx.x_layout, gw)
                 dw = gw
+            else:
+                # batched calls have their own sigma, u, v: gradient through W / sigma_g per group of rows
+                assert not ctx.transposed
+                n = x.shape[0] // sn.groups
+                h, wd = w.shape[0], w[0].numel()
+                dw = torch.empty_like(w)
+                for gi in range(sn.groups):
+                    conv_wgrad(g, x[gi * n:(gi + 1) * n], ctx.x_layout, dy_op[gi * n:(gi + 1) * n], ctx.out_layout, gw)
+                    _lib.K.sn_grad(gw, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = bias_grad(dy, ctx.out_layout)
-        return dx, dw, db, None, None, None, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None
 
 
-def conv2d(x, w, bias, g: ConvGeom, packs: WeightPacks, x_layout="cl", out_layout="cl", relu=False, sn=None,
-           training=True):
-    u, v = sn if sn is not None else (None, None)
-    return _ConvFn.apply(x, w, bias, u, v, g, packs, False, x_layout, out_layout, relu, training, None)
+def conv2d(x, w, bias, g: ConvGeom, packs: WeightPacks, x_layout="cl", out_layout="cl", relu=False,
+           sn: Optional[SNCall] = None):
+    return _ConvFn.apply(x, w, bias, sn, g, packs, False, x_layout, out_layout, relu, None)
 
 
 def conv_transpose2d(x, w, g: ConvGeom, packs: WeightPacks, out_hw, x_layout="cl", out_layout="cl"):
     """x plays dY of the conv-orientation geometry g (g.Cy = x channels, g.Cx = output channels)."""
-    return _ConvFn.apply(x, w, None, None, None, g, packs, True, x_layout, out_layout, False, True, out_hw)
+    return _ConvFn.apply(x, w, None, None, g, packs, True, x_layout, out_layout, False, out_hw)
 
 
-def linear(x2d, w, bias, packs: WeightPacks, relu=False, sn=None, training=True, geom: Optional[ConvGeom] = None):
+def linear(x2d, w, bias, packs: WeightPacks, relu=False, sn: Optional[SNCall] = None, geom: Optional[ConvGeom] = None):
     B, Cin = x2d.shape
     g = geom if geom is not None else ConvGeom(Cin, w.shape[0], 1, 1, 1, 0)
-    y = _ConvFn.apply(x2d.view(B, 1, 1, Cin), w.view(w.shape[0], w.shape[1], 1, 1), bias, sn[0] if sn else None,
-                      sn[1] if sn else None, g, packs, False, "cl", "cl", relu, training, None)
+    y = _ConvFn.apply(x2d.view(B, 1, 1, Cin), w.view(w.shape[0], w.shape[1], 1, 1), bias, sn, g, packs, False, "cl",
+                      "cl", relu, None)
     return y.view(B, g.Cy)
 
 
@@ -368,17 +401,18 @@ def linear(x2d, w, bias, packs: WeightPacks, relu=False, sn=None, training=True,
 class _NormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, idx, running_mean, running_var, mode, training, relu, residual, rows_per_seg,
-                num_classes):
+                num_classes, groups):
         shape = x.shape
         C = shape[-1]
         x2 = x.reshape(-1, C)
         if training:
-            mean, var = _lib.K.bn_stats(x2, running_mean, running_var, BN_MOMENTUM)
+            mean, var = _lib.K.bn_stats(x2, running_mean, running_var, BN_MOMENTUM, groups)
         else:
-            mean, var = running_mean, running_var
+            mean, var, groups = running_mean, running_var, 1
+        ctx.groups = groups
         g2 = gamma.reshape(-1, 2 * C) if mode == MODE_SPADE else gamma
         r2 = residual.reshape(-1, C) if residual is not None else None
-        y = _lib.K.norm_fwd(x2, mean, var, BN_EPS, mode, g2, beta, idx, rows_per_seg, r2, relu)
+        y = _lib.K.norm_fwd(x2, mean, var, BN_EPS, mode, g2, beta, idx, rows_per_seg, r2, relu, groups)
         ctx.mode, ctx.relu, ctx.rows_per_seg, ctx.num_classes, ctx.training = mode, relu, rows_per_seg, num_classes, training
         ctx.has_residual = residual is not None
         ctx.save_for_backward(x2, y if relu else None, mean, var, g2, idx)
@@ -393,7 +427,7 @@ class _NormFn(torch.autograd.Function):
         C = x2.shape[1]
         dy2 = dy.contiguous().reshape(-1, C)
         dx, dgamma, dbeta, dtable, dgb = _lib.K.norm_bwd(dy2, x2, y, mean, var, BN_EPS, ctx.mode, g2, idx,
-                                                         ctx.rows_per_seg, ctx.relu, ctx.num_classes)
+                                                         ctx.rows_per_seg, ctx.relu, ctx.num_classes, ctx.groups)
         dres = None
         if ctx.has_residual:
             dres = _lib.K.relu_bwd(dy2, y).view(ctx.shape) if ctx.relu else dy
@@ -405,24 +439,25 @@ class _NormFn(torch.autograd.Function):
             gg, gb = dgb.view(ctx.shape[:-1] + (2 * C,)), None
         else:
             gg, gb = None, None
-        return dx.view(ctx.shape), gg, gb, None, None, None, None, None, None, dres, None, None
+        return dx.view(ctx.shape), gg, gb, None, None, None, None, None, None, dres, None, None, None
 
 
-def batch_norm(x, weight, bias, running_mean, running_var, training, relu=False, residual=None):
+def batch_norm(x, weight, bias, running_mean, running_var, training, relu=False, residual=None, groups=1):
+    """groups > 1: `groups` calls of the layer batched along dim 0, each with its own batch statistics"""
     mode = MODE_AFFINE if weight is not None else MODE_PLAIN
-    return _NormFn.apply(x, weight, bias, None, running_mean, running_var, mode, training, relu, residual, 1, 0)
+    return _NormFn.apply(x, weight, bias, None, running_mean, running_var, mode, training, relu, residual, 1, 0, groups)
 
 
-def cond_batch_norm(x, table, idx_i32, running_mean, running_var, training, relu=False):
+def cond_batch_norm(x, table, idx_i32, running_mean, running_var, training, relu=False, groups=1):
     """x (O,H,W,C); table (num_classes, 2C) = [gamma | beta]; idx_i32 (O,)"""
     rows_per_seg = x.shape[1] * x.shape[2]
     return _NormFn.apply(x, table, None, idx_i32, running_mean, running_var, MODE_CBN, training, relu, None,
-                         rows_per_seg, table.shape[0])
+                         rows_per_seg, table.shape[0], groups)
 
 
-def spade_norm(x, gb, running_mean, running_var, training, relu=False):
+def spade_norm(x, gb, running_mean, running_var, training, relu=False, groups=1):
     """x (N,H,W,C); gb (N,H,W,2C) = fused [gamma | beta] conv output"""
-    return _NormFn.apply(x, gb, None, None, running_mean, running_var, MODE_SPADE, training, relu, None, 1, 0)
+    return _NormFn.apply(x, gb, None, None, running_mean, running_var, MODE_SPADE, training, relu, None, 1, 0, groups)
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -51,6 +51,15 @@ def bce_const(logits, value: float):
     return F.binary_cross_entropy_with_logits(logits, torch.full_like(logits, value))
 
 
+def bce_const_groups(logits, value: float, groups: int):
+    """per-call means of a batched call: (groups,)"""
+    l = F.binary_cross_entropy_with_logits(logits, torch.full_like(logits, value), reduction="none")
+    return l.view(groups, -1).mean(1)
+
+
+FAKE_W = (0.4, 0.4, 0.2)          # rec, rand, shift weights (train64.py:199-201, 219-221, 298-349)
+
+
 def estimate_attributes(att_logits, attribute):
     """train64.py:155-166 (intended semantics): un-annotated objects get their arg-max attribute switched on."""
     none = (attribute.sum(dim=1, keepdim=True) == 0).to(attribute.dtype)
@@ -70,6 +79,7 @@ class TrainStep:
         self.netG, self.netD_image, self.netD_object, self.netD_att = [n.to(self.device) for n in
                                                                        build_networks(image_size)]
         self.pos_weight = (default_pos_weight() if pos_weight is None else pos_weight).to(self.device)
+        self.fake_w = torch.tensor(FAKE_W, device=self.device)
         self.skip_dead_work = skip_dead_work
         kw = dict(lr=lr, betas=(0.5, 0.999))
         if self.device.type == "cuda":
@@ -97,22 +107,28 @@ class TrainStep:
         return b
 
     def generator(self, b, attribute_est):
-        return self.netG(b["imgs"], b["objs"], b["boxes"], b["masks"], b["obj_to_img"], b["z"], b["attribute"],
-                         b["masks_shift"], b["boxes_shift"], attribute_est)
+        return self.netG.forward_batched(b["imgs"], b["objs"], b["boxes"], b["masks"], b["obj_to_img"], b["z"],
+                                         b["attribute"], b["masks_shift"], b["boxes_shift"], attribute_est)
 
     # ---- losses (train64.py:195-252, 284-364) ----------------------------------------------------------------
+    # Calls of one discriminator on different inputs are batched along dim 0 as `groups` (in the reference's call order):
+    # every spectral-normalised layer then runs `groups` power iterations and scales call g's rows by its own 1/sigma_g.
     def d_loss(self, b, fake):
-        crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift = [t.detach() for t in fake[:7]]
         D_i, D_o, D_a = self.d_nets
         objs = b["objs"]
+        N, O = b["imgs"].shape[0], objs.shape[0]
+        crops_input = fake["outputs"][0].detach()
+        w = self.fake_w
         l = {}
-        l["d_img_fake"] = 0.4 * bce_const(D_i(img_rec), 0) + 0.4 * bce_const(D_i(img_rand), 0) + 0.2 * bce_const(D_i(img_shift), 0)
-        l["d_img_real"] = bce_const(D_i(b["imgs"]), 1)
-        l["d_obj_fake"] = 0.4 * bce_const(D_o(crops_input_rec, objs)[0], 0) + 0.4 * bce_const(D_o(crops_rand, objs)[0], 0) \
-            + 0.2 * bce_const(D_o(crops_shift, objs)[0], 0)
-        src, cls = D_o(crops_input, objs)
-        l["d_obj_real"] = bce_const(src, 1)
-        l["d_obj_cls"] = F.cross_entropy(cls, objs)
+        # D_image on img_rec, img_rand, img_shift (fake, detached), then the real images   (train64.py:195-212)
+        src = D_i(torch.cat([fake["imgs_fake"].detach(), b["imgs"]]), groups=4)
+        l["d_img_fake"] = (w * bce_const_groups(src[:3 * N], 0, 3)).sum()
+        l["d_img_real"] = bce_const(src[3 * N:], 1)
+        # D_object on crops_input_rec, crops_rand, crops_shift, then the real crops   (train64.py:215-238)
+        src, cls = D_o(torch.cat([fake["crops_fake"].detach(), crops_input]), objs, groups=4)
+        l["d_obj_fake"] = (w * bce_const_groups(src[:3 * O], 0, 3)).sum()
+        l["d_obj_real"] = bce_const(src[3 * O:], 1)
+        l["d_obj_cls"] = F.cross_entropy(cls[3 * O:], objs)
         att_cls = D_a(crops_input)
         idx = b["att_idx"]
         l["d_att"] = F.binary_cross_entropy_with_logits(att_cls.index_select(0, idx), b["attribute_GT"].index_select(0, idx),
@@ -122,32 +138,33 @@ class TrainStep:
             + lam["obj_cls"] * l["d_obj_cls"] + lam["att_cls"] * l["d_att"]
         return total, l
 
-    def g_loss(self, b, out):
+    def g_loss(self, b, fake):
         (crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift, mu, logvar, z_rand_rec,
-         z_rand_shift) = out
+         z_rand_shift) = fake["outputs"]
         D_i, D_o, D_a = self.d_nets
         imgs, z, objs, attribute = b["imgs"], b["z"], b["objs"], b["attribute"]
-        N = imgs.shape[0]
+        N, O = imgs.shape[0], objs.shape[0]
         n_change = math.floor(N / 3)
         rec_mask = torch.ones(N, device=imgs.device)
         rec_mask[:n_change] = 0
+        w = self.fake_w
         l = {}
         l["g_img_rec"] = (rec_mask * (img_rec - imgs).abs().view(N, -1).mean(1)).sum() / (N - n_change)
         l["g_z_rec"] = 0.5 * (z_rand_rec - z).abs().mean() + 0.5 * (z_rand_shift - z).abs().mean()
         l["g_kl"] = -0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp())
-        l["g_img_adv"] = 0.4 * bce_const(D_i(img_rec), 1) + 0.4 * bce_const(D_i(img_rand), 1) + 0.2 * bce_const(D_i(img_shift), 1)
+        l["g_img_adv"] = (w * bce_const_groups(D_i(fake["imgs_fake"], groups=3), 1, 3)).sum()
+        # D_object / D_att on crops_input_rec, crops_rand, crops_shift   (train64.py:298-349)
+        src, cls = D_o(fake["crops_fake"], objs, groups=3)
+        att = D_a(fake["crops_fake"], groups=3)
         idx = b["att_idx"]
+        n_idx = idx.numel()
+        idx3 = torch.cat([idx, idx + O, idx + 2 * O])
         att_t = attribute.index_select(0, idx)
-        adv, cls, att = [], [], []
-        for crops in (crops_input_rec, crops_rand, crops_shift):
-            src, c = D_o(crops, objs)
-            adv.append(bce_const(src, 1))
-            cls.append(F.cross_entropy(c, objs))
-            att.append(F.binary_cross_entropy_with_logits(D_a(crops).index_select(0, idx), att_t, pos_weight=self.pos_weight))
-        w = (0.4, 0.4, 0.2)
-        l["g_obj_adv"] = sum(wi * v for wi, v in zip(w, adv))
-        l["g_obj_cls"] = sum(wi * v for wi, v in zip(w, cls))
-        l["g_obj_att"] = sum(wi * v for wi, v in zip(w, att))
+        l["g_obj_adv"] = (w * bce_const_groups(src, 1, 3)).sum()
+        l["g_obj_cls"] = (w * F.cross_entropy(cls, objs.repeat(3), reduction="none").view(3, O).mean(1)).sum()
+        bce = F.binary_cross_entropy_with_logits(att.index_select(0, idx3), att_t.repeat(3, 1), pos_weight=self.pos_weight,
+                                                 reduction="none")
+        l["g_obj_att"] = (w * bce.view(3, n_idx * bce.shape[1]).mean(1)).sum()
         lam = self.lam
         total = lam["img_rec"] * l["g_img_rec"] + lam["z_rec"] * l["g_z_rec"] + lam["img_adv"] * l["g_img_adv"] \
             + lam["obj_adv"] * l["g_obj_adv"] + lam["obj_cls"] * l["g_obj_cls"] + lam["att_cls"] * l["g_obj_att"] \
@@ -209,5 +226,5 @@ class TrainStep:
         if optimizer_step:
             self.opt_G.step()
         return dict(d_loss=d_total.detach(), g_loss=g_total.detach(), d_terms={k: v.detach() for k, v in d_terms.items()},
-                    g_terms={k: v.detach() for k, v in g_terms.items()}, out_g=[t.detach() for t in out],
+                    g_terms={k: v.detach() for k, v in g_terms.items()}, out_g=[t.detach() for t in out["outputs"]],
                     attribute_est=attribute_est)

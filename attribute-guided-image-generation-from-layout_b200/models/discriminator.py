@@ -26,14 +26,14 @@ class OptimizedBlock(nn.Module):
         if self.learnable_sc:
             self.sc = bnn.Conv2d(dim_in, dim_out, kernel_size=1, padding=0, bias=True)
 
-    def forward(self, x):
-        h = self.resi[0](x, x_layout="nchw", relu=True)
-        h = self.resi[2](h)
+    def forward(self, x, groups=1):
+        h = self.resi[0](x, x_layout="nchw", relu=True, groups=groups)
+        h = self.resi[2](h, groups=groups)
         s = x
         if self.downsample:
             h = ops.avg_pool2(h)
             s = ops.pool_nchw(x, 2, 0.25)
-        return ops.add(h, self.sc(s, x_layout="nchw"))
+        return ops.add(h, self.sc(s, x_layout="nchw", groups=groups))
 
 
 class ResidualBlock(nn.Module):
@@ -52,17 +52,22 @@ class ResidualBlock(nn.Module):
         if self.learnable_sc:
             self.sc = bnn.Conv2d(dim_in, dim_out, kernel_size=1, padding=0, bias=True)
 
-    def forward(self, x):
+    def forward(self, x, groups=1):
         r = ops.relu(x)
-        h = self.resi[1](r, relu=True)
-        h = self.resi[3](h)
-        s = self.sc(r) if self.learnable_sc else r
+        h = self.resi[1](r, relu=True, groups=groups)
+        h = self.resi[3](h, groups=groups)
+        s = self.sc(r, groups=groups) if self.learnable_sc else r
         out = ops.add(h, s)
         return ops.avg_pool2(out) if self.downsample else out
 
 
-def _trunk(main, relu_sum_input):
-    h = main(relu_sum_input)
+def _trunk(net, x, groups):
+    """`groups` calls of the network batched along dim 0: every spectral-normalised layer runs `groups` power
+    iterations first (in call order) and call g's rows are scaled by its own 1/sigma_g."""
+    bnn.sn_prepare(net, groups)
+    h = x
+    for blk in net.main:
+        h = blk(h, groups=groups)
     h = ops.relu(h)
     N, H, W, C = h.shape
     return ops.pool(h, H, 1.0).view(N, C)     # in-place ReLU then sum over (H, W) (discriminator.py:224-226)
@@ -82,8 +87,8 @@ class AttributeDiscriminator128(nn.Module):
             ResidualBlock(conv_dim * 16, conv_dim * 16, downsample=True))
         self.classifier_att = bnn.Linear(conv_dim * 16, n_attribute)
 
-    def forward(self, x):
-        return self.classifier_att(_trunk(self.main, x))
+    def forward(self, x, groups=1):
+        return self.classifier_att(_trunk(self, x, groups), groups=groups)
 
 
 class AttributeDiscriminator(nn.Module):
@@ -99,8 +104,8 @@ class AttributeDiscriminator(nn.Module):
             ResidualBlock(conv_dim * 8, conv_dim * 16, downsample=True))
         self.classifier_att = bnn.Linear(conv_dim * 16, n_attribute)
 
-    def forward(self, x):
-        return self.classifier_att(_trunk(self.main, x))
+    def forward(self, x, groups=1):
+        return self.classifier_att(_trunk(self, x, groups), groups=groups)
 
 
 class ImageDiscriminator(nn.Module):
@@ -117,8 +122,8 @@ class ImageDiscriminator(nn.Module):
             ResidualBlock(self.ch * 8, self.ch * 16, downsample=True))
         self.classifier = bnn.Linear(self.ch * 16, 1, bias=False)
 
-    def forward(self, x):
-        return self.classifier(_trunk(self.main, x)).view(-1)
+    def forward(self, x, groups=1):
+        return self.classifier(_trunk(self, x, groups), groups=groups).view(-1)
 
 
 class ObjectDiscriminator(nn.Module):
@@ -135,6 +140,6 @@ class ObjectDiscriminator(nn.Module):
         self.classifier_src = bnn.Linear(conv_dim * 16, 1)
         self.classifier_cls = bnn.Linear(conv_dim * 16, n_class)
 
-    def forward(self, x, y=None):
-        h = _trunk(self.main, x)
-        return self.classifier_src(h).view(-1), self.classifier_cls(h)
+    def forward(self, x, y=None, groups=1):
+        h = _trunk(self, x, groups)
+        return self.classifier_src(h, groups=groups).view(-1), self.classifier_cls(h, groups=groups)

@@ -36,11 +36,11 @@ class ConditionalBatchNorm2d(nn.Module):
         self.embed.weight.data[:, :num_features].normal_(1, 0.02)
         self.embed.weight.data[:, num_features:].zero_()
 
-    def forward(self, x, y, relu=False):
+    def forward(self, x, y, relu=False, groups=1):
         if self.bn.training:
-            self.bn.num_batches_tracked.add_(1)
+            self.bn.num_batches_tracked.add_(groups)
         return ops.cond_batch_norm(x, self.embed.weight, y, self.bn.running_mean, self.bn.running_var, self.bn.training,
-                                   relu)
+                                   relu, groups)
 
 
 class ResidualBlock(nn.Module):
@@ -55,11 +55,11 @@ class ResidualBlock(nn.Module):
             bnn.Conv2d(dim_out, dim_out, kernel_size=3, stride=1, padding=1, bias=False),
             bnn.BatchNorm2d(dim_out, affine=True, track_running_stats=True))
 
-    def forward(self, x):
+    def forward(self, x, groups=1):
         h = self.main[0](x)
-        h = self.main[1](h, relu=True)
+        h = self.main[1](h, relu=True, groups=groups)
         h = self.main[3](h)
-        return self.main[4](h, residual=x)
+        return self.main[4](h, residual=x, groups=groups)
 
 
 class ConvLSTMCell(nn.Module):
@@ -119,20 +119,24 @@ class CropEncoder(nn.Module):
         self.fc_logvar = bnn.Linear(conv_dim * 16, z_dim)
         self.eps_source = None   # optional callable(O, z_dim, device) -> device tensor (CUDA-graph friendly)
 
-    def forward(self, imgs, objs):
-        x = self.bn1(self.c1(imgs, x_layout="nchw"), objs, relu=True)
-        x = self.bn2(self.c2(x), objs, relu=True)
-        x = self.bn3(self.c3(x), objs, relu=True)
-        x = self.bn4(self.c4(x), objs, relu=True)
-        x = self.bn5(self.conv5(x), objs, relu=True)
+    def forward(self, imgs, objs, groups=1):
+        """groups > 1: that many calls batched along dim 0 (imgs (groups*O,3,S,S), objs (groups*O,)); batch statistics,
+        running-statistics updates and the noise draws stay per call, in call order."""
+        x = self.bn1(self.c1(imgs, x_layout="nchw"), objs, relu=True, groups=groups)
+        x = self.bn2(self.c2(x), objs, relu=True, groups=groups)
+        x = self.bn3(self.c3(x), objs, relu=True, groups=groups)
+        x = self.bn4(self.c4(x), objs, relu=True, groups=groups)
+        x = self.bn5(self.conv5(x), objs, relu=True, groups=groups)
         O, H, W, C = x.shape
         x = ops.pool(x, H, 1.0 / (H * W)).view(O, C)
         mu = self.fc_mu(x)
         logvar = self.fc_logvar(x)
         if self.eps_source is not None:
             eps = self.eps_source(O, mu.size(1), mu.device)
-        else:
+        elif groups == 1:
             eps = get_z_random(O, mu.size(1)).to(mu.device)
+        else:
+            eps = torch.cat([get_z_random(O // groups, mu.size(1)) for _ in range(groups)]).to(mu.device)
         z = ops.reparameterize(mu, logvar, eps)
         return z, mu, logvar
 
@@ -146,8 +150,8 @@ class GlobalEncoder(nn.Module):
         self.bn1 = bnn.BatchNorm2d(128)
         self.c2 = bnn.Conv2d(128, 128, kernel_size=4, stride=2, padding=1, bias=False)
 
-    def forward(self, h):
-        h = self.bn1(self.c1(h), relu=True)
+    def forward(self, h, groups=1):
+        h = self.bn1(self.c1(h), relu=True, groups=groups)
         h = self.c2(h)
         N, H, W, C = h.shape
         return ops.pool(h, H, 1.0).view(N, C)
@@ -177,20 +181,24 @@ class LayoutEncoder(nn.Module):
         self._pool_to_8 = pool_to_8
         self._c0_packs = ops.WeightPacks()
 
-    def forward(self, objs_att, masks, obj_to_img, z, objs):
+    def forward(self, objs_att, masks, obj_to_img, z, objs, groups=1):
+        """groups > 1: that many calls batched along dim 0; obj_to_img must then number the images of call g from
+        g * N on, so every call keeps its own ConvLSTM sequences."""
         e = ops.concat_channels(objs_att, z)                                       # (O, att + z)
         w0 = self.c0.weight
         v = ops.linear(e, w0.view(w0.shape[0], w0.shape[1]), None, self._c0_packs)   # W0 e  (rank-1 form of c0)
         h = ops.mask_outer(v, masks)                                               # (O,H+2,W+2,64), zero ring = padding 1
-        h = self.bn1(h, objs, relu=True)
-        h = self.bn2(self.c2(h), objs, relu=True)
-        h = self.bn3(self.c3(h), objs, relu=True)
-        h = self.bn4(self.c4(h), objs)
+        h = self.bn1(h, objs, relu=True, groups=groups)
+        h = self.bn2(self.c2(h), objs, relu=True, groups=groups)
+        h = self.bn3(self.c3(h), objs, relu=True, groups=groups)
+        h = self.bn4(self.c4(h), objs, groups=groups)
         if self._pool_to_8:
             f = h.shape[1] // 8
             h = ops.pool(h, f, 1.0 / (f * f))
         h = self.clstm(h, obj_to_img)
-        return self.residual(h)
+        for blk in self.residual:
+            h = blk(h, groups=groups)
+        return h
 
 
 class Decoder(nn.Module):
@@ -216,23 +224,23 @@ class Decoder(nn.Module):
             self.spade_5 = SPADE(conv_dim * 2, self.h_dim)
             self.c7 = bnn.Conv2d(conv_dim * 2, 3, kernel_size=7, stride=1, padding=3, bias=True)
 
-    def forward(self, hidden, global_h, z=None):
+    def forward(self, hidden, global_h, z=None, groups=1):
         """hidden (N,8,8,64) channel-last, global_h (N,128) -> image (N,3,S,S) NCHW (no tanh, as the reference)"""
         N, H, W, C = hidden.shape
         seg = hidden
         x = ops.concat_channels(hidden.view(N * H * W, C), global_h, 1, H * W).view(N, H, W, C + global_h.shape[1])
         h = self.c0_new(x)
-        h = self.spade_0.forward_cl(h, seg, relu=True)
-        h = self.spade_1.forward_cl(self.dc1(h), seg, relu=True)
-        h = self.spade_2.forward_cl(self.dc2(h), seg, relu=True)
-        h = self.spade_3.forward_cl(self.dc3(h), seg, relu=True)
+        h = self.spade_0.forward_cl(h, seg, relu=True, groups=groups)
+        h = self.spade_1.forward_cl(self.dc1(h), seg, relu=True, groups=groups)
+        h = self.spade_2.forward_cl(self.dc2(h), seg, relu=True, groups=groups)
+        h = self.spade_3.forward_cl(self.dc3(h), seg, relu=True, groups=groups)
         img = self.c4(h, out_layout="nchw")
         if not self._refine:
             return img
         up = ops.upsample_nearest_nchw(img, 2)
         h = self.c5(up, x_layout="nchw")
-        h = self.spade_4.forward_cl(h, seg, relu=True)
-        h = self.spade_5.forward_cl(self.c6(h), seg, relu=True)
+        h = self.spade_4.forward_cl(h, seg, relu=True, groups=groups)
+        h = self.spade_5.forward_cl(self.c6(h), seg, relu=True, groups=groups)
         return self.c7(h, out_layout="nchw")
 
 
@@ -248,10 +256,10 @@ class AttributeEncoder(nn.Module):
         self.bn1 = bnn.BatchNorm1d(64)
         self.c2 = bnn.Linear(64, 64)
 
-    def forward(self, objs, attribute):
+    def forward(self, objs, attribute, groups=1):
         a = ops.concat_channels(self.embedding(objs), attribute.contiguous())
-        a = self.bn0(self.c0(a), relu=True)
-        a = self.bn1(self.c1(a), relu=True)
+        a = self.bn0(self.c0(a), relu=True, groups=groups)
+        a = self.bn1(self.c1(a), relu=True, groups=groups)
         return self.c2(a)
 
 
@@ -272,34 +280,46 @@ class Generator(nn.Module):
                                                   class_num=num_embeddings)
 
     def forward(self, imgs, objs, boxes, masks, obj_to_img, z_rand, attribute, masks_shift, boxes_shift, attribute_est):
+        return self.forward_batched(imgs, objs, boxes, masks, obj_to_img, z_rand, attribute, masks_shift, boxes_shift,
+                                    attribute_est)["outputs"]
+
+    def forward_batched(self, imgs, objs, boxes, masks, obj_to_img, z_rand, attribute, masks_shift, boxes_shift,
+                        attribute_est):
+        """generator_obj_att.py:618-647 with the three passes (rec, rand, shift) of every sub-network batched along
+        dim 0 as three groups: one launch serves all three, while batch statistics, running-statistics updates, noise
+        draws and ConvLSTM sequences stay per pass and in the reference's call order.  Returns the reference's 11-tuple
+        ("outputs") plus the batched tensors the training step feeds to the discriminators:
+        "imgs_fake" (3N,3,H,W) = [img_rec; img_rand; img_shift], "crops_fake" (3O,3,S,S) = [crops_input_rec; crops_rand;
+        crops_shift]."""
         o2i = obj_to_img.cpu() if obj_to_img.is_cuda else obj_to_img
+        N, O = imgs.shape[0], objs.shape[0]
         objs32 = objs.to(torch.int32)
+        objs32x3 = objs32.repeat(3)
+        o2i3 = torch.cat([o2i, o2i + N, o2i + 2 * N])
         z_rand = z_rand.contiguous()
         crops_input = crop_bbox_batch(imgs, boxes, o2i, self.obj_size)
         z_rec, mu, logvar = self.crop_encoder(crops_input, objs32)
 
-        objs_att = self.attribute_encoder(objs32, attribute)
-        objs_att_est = self.attribute_encoder(objs32, attribute_est)
+        # attribute_encoder(objs, attribute) then attribute_encoder(objs, attribute_est)  (generator_obj_att.py:622-623)
+        att2 = self.attribute_encoder(objs32x3[:2 * O], torch.cat([attribute, attribute_est]), groups=2)
+        objs_att, objs_att_est = att2[:O], att2[O:]
 
-        h_rec = self.layout_encoder(objs_att_est, masks, o2i, z_rec, objs32)
-        h_rand = self.layout_encoder(objs_att, masks, o2i, z_rand, objs32)
-        h_shift = self.layout_encoder(objs_att, masks_shift, o2i, z_rand, objs32)
+        # layout_encoder x3: (att_est, masks, z_rec), (att, masks, z_rand), (att, masks_shift, z_rand)   (:626-628)
+        att3 = torch.cat([objs_att_est, objs_att, objs_att])
+        z3 = torch.cat([z_rec, z_rand, z_rand])
+        masks3 = torch.cat([masks, masks, masks_shift])
+        h3 = self.layout_encoder(att3, masks3, o2i3, z3, objs32x3, groups=3)          # (3N,8,8,64)
+        g3 = self.global_encoder(h3, groups=3)                                       # (3N,128)
+        imgs_fake = self.decoder(h3, g3, groups=3)                                   # (3N,3,H,W): rec, rand, shift
+        img_rec, img_rand, img_shift = imgs_fake[:N], imgs_fake[N:2 * N], imgs_fake[2 * N:]
 
-        h_rec_global = self.global_encoder(h_rec)
-        h_rand_global = self.global_encoder(h_rand)
-        h_shift_global = self.global_encoder(h_shift)
-
-        img_rec = self.decoder(h_rec, h_rec_global)
-        img_rand = self.decoder(h_rand, h_rand_global)
-        img_shift = self.decoder(h_shift, h_shift_global)
-
-        crops_rand = crop_bbox_batch(img_rand, boxes, o2i, self.obj_size)
-        _, z_rand_rec, _ = self.crop_encoder(crops_rand, objs32)
-
-        crops_input_rec = crop_bbox_batch(img_rec, boxes, o2i, self.obj_size)
-
-        crops_shift = crop_bbox_batch(img_shift, boxes_shift, o2i, self.obj_size)
-        _, z_rand_shift, _ = self.crop_encoder(crops_shift, objs32)
-
-        return (crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift, mu, logvar,
-                z_rand_rec, z_rand_shift)
+        # crops of (img_rec, boxes), (img_rand, boxes), (img_shift, boxes_shift)   (:639-644)
+        boxes3 = torch.cat([boxes, boxes, boxes_shift])
+        crops_fake = crop_bbox_batch(imgs_fake, boxes3, o2i3, self.obj_size)
+        crops_input_rec, crops_rand, crops_shift = crops_fake[:O], crops_fake[O:2 * O], crops_fake[2 * O:]
+        # crop_encoder(crops_rand) then crop_encoder(crops_shift)   (:640, 645)
+        _, mu2, _ = self.crop_encoder(crops_fake[O:], objs32x3[:2 * O], groups=2)
+        z_rand_rec, z_rand_shift = mu2[:O], mu2[O:]
+        outputs = (crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift, mu, logvar,
+                   z_rand_rec, z_rand_shift)
+        return dict(outputs=outputs, imgs_fake=imgs_fake, crops_fake=crops_fake)

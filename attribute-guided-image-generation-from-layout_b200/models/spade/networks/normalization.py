@@ -23,7 +23,7 @@ class SPADE(nn.Module):
         self._gb_geom = ConvGeom(nhidden, 2 * norm_nc, 3, 3, 1, 1)
         self._gb_packs = None
 
-    def forward_cl(self, x, seg, relu=False):
+    def forward_cl(self, x, seg, relu=False, groups=1):
         """x (N,H,W,C), seg (N,h,w,label_nc) channel-last; H must be an integer multiple of h."""
         f = x.shape[1] // seg.shape[1]
         if f > 1:
@@ -36,8 +36,8 @@ class SPADE(nn.Module):
         gb = ops.conv2d(actv, w, b, self._gb_geom, self._gb_packs)
         bn = self.param_free_norm
         if bn.training:
-            bn.num_batches_tracked.add_(1)
-        return ops.spade_norm(x, gb, bn.running_mean, bn.running_var, bn.training, relu)
+            bn.num_batches_tracked.add_(groups)
+        return ops.spade_norm(x, gb, bn.running_mean, bn.running_var, bn.training, relu, groups)
 
     def forward(self, x, segmap):
         """reference signature: NCHW in, NCHW out"""

@@ -208,7 +208,7 @@ def test_linear_and_spectral_norm(K):
     v = F.normalize(torch.randn(170, generator=g), dim=0)
     xd, wd, bd = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
     ud, vd = u.cuda(), v.cuda()
-    y = ops.linear(xd, wd, bd, ops.WeightPacks(), sn=(ud, vd), training=True)
+    y = ops.linear(xd, wd, bd, ops.WeightPacks(), sn=ops.sn_iterate(wd, ud, vd, 1, True))
     st = {"l.weight_orig": w.clone().requires_grad_(True), "l.weight_u": u.clone(), "l.weight_v": v.clone(), "l.bias": b.clone().requires_grad_(True)}
     xr = x.clone().requires_grad_(True)
     yr = F.linear(xr, O.sn_weight(st, "l", True), st["l.bias"])
@@ -221,6 +221,47 @@ def test_linear_and_spectral_norm(K):
     close(xd.grad, xr.grad, 1e-5, "sn dgrad")
     close(wd.grad, st["l.weight_orig"].grad, 2e-5, "sn wgrad")
     close(bd.grad, st["l.bias"].grad, 1e-5, "bias")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_batched_spectral_norm_conv(K, precision):
+    """three calls of a spectral-normalised conv batched along dim 0 == three sequential calls of the reference hook:
+    per-call sigma in the epilogue / dgrad, per-call gradient through sigma, u / v advanced three times."""
+    g = torch.Generator().manual_seed(5)
+    groups, n, Cin, Cout, H = 3, 2, 64, 128, 8
+    x = torch.randn(groups * n, Cin, H, H, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.05
+    b = torch.randn(Cout, generator=g)
+    u = F.normalize(torch.randn(Cout, generator=g), dim=0)
+    v = F.normalize(torch.randn(Cin * 9, generator=g), dim=0)
+    gy = torch.randn(groups * n, Cout, H, H, generator=g)
+    tol = 2e-2 if precision == "bf16" else 2e-5          # bf16: tcgen05 operands rounded to bf16, reference kept in fp32
+    relu = precision == "fp32"                           # (a fused ReLU would flip near-zero mask bits under bf16 rounding)
+    ops.set_precision(precision)
+    try:
+        xd = _to_layout(x, "cl").cuda().requires_grad_(True)
+        wd, bd, ud, vd = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True), u.cuda(), v.cuda()
+        geom = ops.ConvGeom(Cin, Cout, 3, 3, 1, 1)
+        y = ops.conv2d(xd, wd, bd, geom, ops.WeightPacks(), "cl", "cl", relu=relu, sn=ops.sn_iterate(wd, ud, vd, groups, True))
+        y.backward(_to_layout(gy, "cl").cuda())
+    finally:
+        ops.set_precision("fp32")
+    st = {"l.weight_orig": w.clone().requires_grad_(True), "l.weight_u": u.clone(), "l.weight_v": v.clone()}
+    bias = b.clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ys = []
+    for gi in range(groups):
+        wn = O.sn_weight(st, "l", True)
+        yg = F.conv2d(xr[gi * n:(gi + 1) * n], wn, bias, padding=1)
+        ys.append(F.relu(yg) if relu else yg)
+    yr = torch.cat(ys)
+    yr.backward(gy)
+    close(_from_layout(y, "cl"), yr, tol, "batched sn conv fwd")
+    close(ud, st["l.weight_u"], 1e-5, "u after 3 iterations")
+    close(vd, st["l.weight_v"], 1e-5, "v after 3 iterations")
+    close(_from_layout(xd.grad, "cl"), xr.grad, tol, "batched sn dgrad")
+    close(wd.grad, st["l.weight_orig"].grad, tol if precision == "bf16" else 5e-5, "batched sn wgrad")
+    close(bd.grad, bias.grad, 1e-5, "bias")
 
 
 @pytest.mark.parametrize("h,w", [(64, 27), (1, 1024), (179, 1024), (1024, 9216)])

@@ -91,7 +91,7 @@ def test_full_size_properties_config2():
     ts = TrainStep(64, device="cuda")
     b = ts.to_device(batch)
     with torch.no_grad():
-        out = ts.generator(b, b["attribute"])
+        out = ts.generator(b, b["attribute"])["outputs"]
         from models.bilinear import crop_bbox_batch
         again = crop_bbox_batch(out[5], b["boxes"], b["obj_to_img"], 32)
         assert torch.equal(again, out[2])
