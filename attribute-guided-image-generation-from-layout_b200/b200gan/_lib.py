@@ -39,6 +39,12 @@ class ConvDesc(C.Structure):
     ]
 
 
+class SNLayer(C.Structure):
+    """Mirror of b200_sn_layer (include/b200gan.h)."""
+    _fields_ = [("W", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("ws", C.c_void_p), ("inv", C.c_void_p),
+                ("u_hist", C.c_void_p), ("v_hist", C.c_void_p), ("h", C.c_int), ("w", C.c_int)]
+
+
 class B200Error(RuntimeError):
     pass
 
@@ -49,6 +55,27 @@ def _ptr(t: Optional[torch.Tensor]):
     if not t.is_cuda:
         raise B200Error("b200gan kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
     return C.c_void_p(t.data_ptr())
+
+
+F32, BF16 = 0, 1
+
+
+def _dt(t: torch.Tensor) -> int:
+    """storage type code of an activation tensor (B200_F32 / B200_BF16)"""
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise B200Error("activation tensors are fp32 or bf16, got %s" % t.dtype)
+
+
+def _same_dt(*ts):
+    ts = [t for t in ts if t is not None]
+    d = _dt(ts[0])
+    for t in ts[1:]:
+        if _dt(t) != d:
+            raise B200Error("mixed activation storage types in one call: %s" % [str(t.dtype) for t in ts])
+    return d
 
 
 def _stream():
@@ -116,8 +143,8 @@ class Kernels:
 
     def conv_gemm(self, desc: ConvDesc, inp, wmat, bias, scale, out, tc: bool):
         if not tc:
-            self._check(self.lib.b200_conv_gemm_f32(C.byref(desc), _ptr(inp), _ptr(wmat), _ptr(bias), _ptr(scale),
-                                                    _ptr(out), _stream()), "b200_conv_gemm_f32")
+            self._check(self.lib.b200_conv_gemm_f32(C.byref(desc), _ptr(inp), _dt(inp), _ptr(wmat), _ptr(bias), _ptr(scale),
+                                                    _ptr(out), _dt(out), _stream()), "b200_conv_gemm_f32")
             return
         if inp.dtype != torch.bfloat16:
             raise B200Error("conv_gemm(tc): the activation operand must be bf16 (use cast_bf16)")
@@ -140,9 +167,12 @@ class Kernels:
     def wgrad_gemm(self, desc: ConvDesc, P, G, ws, splits: int, tc: bool):
         if tc and (P.dtype != torch.bfloat16 or G.dtype != torch.bfloat16):
             raise B200Error("wgrad_gemm(tc): both operands must be bf16 (use cast_bf16)")
-        fn = self.lib.b200_wgrad_gemm_tc if tc else self.lib.b200_wgrad_gemm_f32
-        self._check(fn(C.byref(desc), _ptr(P), _ptr(G), _ptr(ws), int(splits), _stream()),
-                    "b200_wgrad_gemm_tc" if tc else "b200_wgrad_gemm_f32")
+        if tc:
+            self._check(self.lib.b200_wgrad_gemm_tc(C.byref(desc), _ptr(P), _ptr(G), _ptr(ws), int(splits), _stream()),
+                        "b200_wgrad_gemm_tc")
+        else:
+            self._check(self.lib.b200_wgrad_gemm_f32(C.byref(desc), _ptr(P), _dt(P), _ptr(G), _dt(G), _ptr(ws), int(splits),
+                                                     _stream()), "b200_wgrad_gemm_f32")
 
     def wgrad_reduce(self, ws, splits, M, Th, Tw, Cc, dst, dst_offset, s_m, s_ty, s_tx, s_c, scale=None,
                      accumulate=False, ws_row_offset=0, ws_rows=None):
@@ -181,7 +211,7 @@ class Kernels:
         mean = torch.empty((groups, Cc), dtype=torch.float32, device=dev)
         var = torch.empty((groups, Cc), dtype=torch.float32, device=dev)
         ws = torch.empty((2 * Cc * groups * self.bn_chunks(rows // groups, Cc),), dtype=torch.float64, device=dev)
-        self._check(self.lib.b200_bn_stats(_ptr(x2d), C.c_int64(rows), Cc, int(groups), _ptr(mean), _ptr(var),
+        self._check(self.lib.b200_bn_stats(_ptr(x2d), _dt(x2d), C.c_int64(rows), Cc, int(groups), _ptr(mean), _ptr(var),
                                            _ptr(running_mean), _ptr(running_var), C.c_float(momentum), _ptr(ws),
                                            _stream()), "b200_bn_stats")
         return mean, var
@@ -189,7 +219,8 @@ class Kernels:
     def norm_fwd(self, x2d, mean, var, eps, mode, gamma, beta, idx, rows_per_seg, residual, relu, groups=1):
         rows, Cc = x2d.shape
         y = torch.empty_like(x2d)
-        self._check(self.lib.b200_norm_fwd(_ptr(x2d), _ptr(y), C.c_int64(rows), Cc, int(groups), _ptr(mean), _ptr(var),
+        dt = _same_dt(x2d, residual, gamma if mode == MODE_SPADE else None)
+        self._check(self.lib.b200_norm_fwd(_ptr(x2d), _ptr(y), dt, C.c_int64(rows), Cc, int(groups), _ptr(mean), _ptr(var),
                                            C.c_float(eps), int(mode), _ptr(gamma), _ptr(beta), _ptr(idx),
                                            int(rows_per_seg), _ptr(residual), int(bool(relu)), _stream()),
                     "b200_norm_fwd")
@@ -200,6 +231,7 @@ class Kernels:
         rows, Cc = x2d.shape
         dev = x2d.device
         rpg = rows // groups
+        dt = _same_dt(dy, x2d, y, gamma if mode == MODE_SPADE else None)
         if mode == MODE_CBN:
             seg = int(rows_per_seg)
         else:
@@ -207,7 +239,7 @@ class Kernels:
             seg = (rpg + nchunks - 1) // nchunks
         nseg = groups * ((rpg + seg - 1) // seg)
         seg_sums = torch.empty((nseg * Cc * 2,), dtype=torch.float64, device=dev)
-        self._check(self.lib.b200_norm_bwd_reduce(_ptr(dy), _ptr(x2d), _ptr(y), C.c_int64(rows), Cc, int(groups),
+        self._check(self.lib.b200_norm_bwd_reduce(_ptr(dy), _ptr(x2d), _ptr(y), dt, C.c_int64(rows), Cc, int(groups),
                                                   _ptr(mean), _ptr(var), C.c_float(eps), int(mode), _ptr(gamma),
                                                   _ptr(idx), seg, int(bool(relu)), _ptr(seg_sums), _stream()),
                     "b200_norm_bwd_reduce")
@@ -223,8 +255,8 @@ class Kernels:
                                                     _ptr(dtable), _stream()), "b200_norm_bwd_finalize")
         dx = torch.empty_like(x2d)
         if mode == MODE_SPADE:
-            dgb = torch.empty((rows, 2 * Cc), dtype=torch.float32, device=dev)
-        self._check(self.lib.b200_norm_bwd_apply(_ptr(dy), _ptr(x2d), _ptr(y), _ptr(dx), C.c_int64(rows), Cc,
+            dgb = torch.empty((rows, 2 * Cc), dtype=x2d.dtype, device=dev)
+        self._check(self.lib.b200_norm_bwd_apply(_ptr(dy), _ptr(x2d), _ptr(y), _ptr(dx), dt, C.c_int64(rows), Cc,
                                                  int(groups), _ptr(mean), _ptr(var), C.c_float(eps), int(mode),
                                                  _ptr(gamma), _ptr(idx), int(rows_per_seg) if mode == MODE_CBN else 1,
                                                  int(bool(relu)), _ptr(s), _ptr(dgb), _stream()), "b200_norm_bwd_apply")
@@ -233,43 +265,47 @@ class Kernels:
     # ---- elementwise / pooling / layout ------------------------------------------------------------------------
     def relu_fwd(self, x):
         y = torch.empty_like(x)
-        self._check(self.lib.b200_relu_fwd(_ptr(x), _ptr(y), C.c_int64(x.numel()), _stream()), "b200_relu_fwd")
+        self._check(self.lib.b200_relu_fwd(_ptr(x), _ptr(y), C.c_int64(x.numel()), _dt(x), _stream()), "b200_relu_fwd")
         return y
 
     def relu_bwd(self, dy, y):
         dx = torch.empty_like(dy)
-        self._check(self.lib.b200_relu_bwd(_ptr(dy), _ptr(y), _ptr(dx), C.c_int64(dy.numel()), _stream()), "b200_relu_bwd")
+        self._check(self.lib.b200_relu_bwd(_ptr(dy), _ptr(y), _ptr(dx), C.c_int64(dy.numel()), _same_dt(dy, y), _stream()),
+                    "b200_relu_bwd")
         return dx
 
     def add(self, a, b, out=None):
         if out is None:
             out = torch.empty_like(a)
-        self._check(self.lib.b200_add(_ptr(a), _ptr(b), _ptr(out), C.c_int64(a.numel()), _stream()), "b200_add")
+        self._check(self.lib.b200_add(_ptr(a), _ptr(b), _ptr(out), C.c_int64(a.numel()), _same_dt(a, b, out), _stream()),
+                    "b200_add")
         return out
 
     def pool_fwd(self, x, N, H, W, Cc, f, scale):
-        y = torch.empty((N, H // f, W // f, Cc), dtype=torch.float32, device=x.device)
-        self._check(self.lib.b200_pool_fwd(_ptr(x), _ptr(y), N, H, W, Cc, f, C.c_float(scale), _stream()), "b200_pool_fwd")
+        y = torch.empty((N, H // f, W // f, Cc), dtype=x.dtype, device=x.device)
+        self._check(self.lib.b200_pool_fwd(_ptr(x), _ptr(y), N, H, W, Cc, f, C.c_float(scale), _dt(x), _stream()),
+                    "b200_pool_fwd")
         return y
 
     def unpool_fwd(self, x, N, H, W, Cc, f, scale):
-        y = torch.empty((N, H * f, W * f, Cc), dtype=torch.float32, device=x.device)
-        self._check(self.lib.b200_unpool_fwd(_ptr(x), _ptr(y), N, H, W, Cc, f, C.c_float(scale), _stream()),
+        y = torch.empty((N, H * f, W * f, Cc), dtype=x.dtype, device=x.device)
+        self._check(self.lib.b200_unpool_fwd(_ptr(x), _ptr(y), N, H, W, Cc, f, C.c_float(scale), _dt(x), _stream()),
                     "b200_unpool_fwd")
         return y
 
     def concat_fwd(self, a, Ca, a_div, b, Cb, b_div, rows):
-        out = torch.empty((rows, Ca + Cb), dtype=torch.float32, device=a.device)
-        self._check(self.lib.b200_concat_fwd(_ptr(a), Ca, a_div, _ptr(b), Cb, b_div, _ptr(out), C.c_int64(rows), _stream()),
+        out = torch.empty((rows, Ca + Cb), dtype=a.dtype, device=a.device)
+        self._check(self.lib.b200_concat_fwd(_ptr(a), Ca, a_div, _ptr(b), Cb, b_div, _ptr(out), C.c_int64(rows),
+                                             _same_dt(a, b), _stream()),
                     "b200_concat_fwd")
         return out
 
     def concat_bwd(self, dout, Ca, a_div, Cb, b_div, rows, need_a=True, need_b=True):
         dev = dout.device
-        da = torch.empty((rows // a_div, Ca), dtype=torch.float32, device=dev) if need_a else None
-        db = torch.empty((rows // b_div, Cb), dtype=torch.float32, device=dev) if need_b else None
+        da = torch.empty((rows // a_div, Ca), dtype=dout.dtype, device=dev) if need_a else None
+        db = torch.empty((rows // b_div, Cb), dtype=dout.dtype, device=dev) if need_b else None
         self._check(self.lib.b200_concat_bwd(_ptr(dout), Ca, a_div, _ptr(da), Cb, b_div, _ptr(db), C.c_int64(rows),
-                                             _stream()), "b200_concat_bwd")
+                                             _dt(dout), _stream()), "b200_concat_bwd")
         return da, db
 
     def gather_rows(self, table, idx):
@@ -287,20 +323,20 @@ class Kernels:
 
     def permute_rows(self, x, src_row, rowlen):
         rows = src_row.shape[0]
-        out = torch.empty((rows, rowlen), dtype=torch.float32, device=x.device)
-        self._check(self.lib.b200_permute_rows(_ptr(x), _ptr(src_row), _ptr(out), rows, rowlen, _stream()),
-                    "b200_permute_rows")
+        out = torch.empty((rows, rowlen), dtype=x.dtype, device=x.device)
+        self._check(self.lib.b200_permute_rows(_ptr(x), _ptr(src_row), _ptr(out), rows,
+                                               C.c_int64(rowlen * x.element_size()), _stream()), "b200_permute_rows")
         return out
 
-    def mask_outer_fwd(self, v, mask, O, H, W, Cc):
-        out = torch.empty((O, H + 2, W + 2, Cc), dtype=torch.float32, device=v.device)
-        self._check(self.lib.b200_mask_outer_fwd(_ptr(v), _ptr(mask), _ptr(out), O, H, W, Cc, _stream()),
+    def mask_outer_fwd(self, v, mask, O, H, W, Cc, out_dtype=torch.float32):
+        out = torch.empty((O, H + 2, W + 2, Cc), dtype=out_dtype, device=v.device)
+        self._check(self.lib.b200_mask_outer_fwd(_ptr(v), _ptr(mask), _ptr(out), O, H, W, Cc, _dt(out), _stream()),
                     "b200_mask_outer_fwd")
         return out
 
     def mask_outer_bwd(self, dout, mask, O, H, W, Cc):
         dv = torch.empty((O, Cc), dtype=torch.float32, device=dout.device)
-        self._check(self.lib.b200_mask_outer_bwd(_ptr(dout), _ptr(mask), _ptr(dv), O, H, W, Cc, _stream()),
+        self._check(self.lib.b200_mask_outer_bwd(_ptr(dout), _ptr(mask), _ptr(dv), O, H, W, Cc, _dt(dout), _stream()),
                     "b200_mask_outer_bwd")
         return dv
 
@@ -309,19 +345,21 @@ class Kernels:
         if gates is None:
             gates = torch.empty((rows, 4 * hid), dtype=torch.float32, device=dev)
             c_out = torch.empty((rows, hid), dtype=torch.float32, device=dev)
-            h_out = torch.empty((rows, hid), dtype=torch.float32, device=dev)
+            h_out = torch.empty((rows, hid), dtype=pre_x.dtype, device=dev)
         self._check(self.lib.b200_lstm_gates_fwd(_ptr(pre_x), _ptr(pre_h), _ptr(c_prev), _ptr(gates), _ptr(c_out),
-                                                 _ptr(h_out), C.c_int64(rows), hid, _stream()), "b200_lstm_gates_fwd")
+                                                 _ptr(h_out), C.c_int64(rows), hid, _same_dt(pre_x, pre_h, h_out),
+                                                 _stream()), "b200_lstm_gates_fwd")
         return gates, c_out, h_out
 
     def lstm_gates_bwd(self, dh, dc_next, gates, c_prev, c_out, rows, hid, dpre=None, dc_prev=None):
         dev = dh.device
         if dpre is None:
-            dpre = torch.empty((rows, 4 * hid), dtype=torch.float32, device=dev)
+            dpre = torch.empty((rows, 4 * hid), dtype=dh.dtype, device=dev)
         if dc_prev is None:
             dc_prev = torch.empty((rows, hid), dtype=torch.float32, device=dev)
         self._check(self.lib.b200_lstm_gates_bwd(_ptr(dh), _ptr(dc_next), _ptr(gates), _ptr(c_prev), _ptr(c_out),
-                                                 _ptr(dpre), _ptr(dc_prev), C.c_int64(rows), hid, _stream()),
+                                                 _ptr(dpre), _ptr(dc_prev), C.c_int64(rows), hid, _same_dt(dh, dpre),
+                                                 _stream()),
                     "b200_lstm_gates_bwd")
         return dpre, dc_prev
 
@@ -347,7 +385,8 @@ class Kernels:
         rows, Cc = x2d.shape
         out = torch.empty((Cc,), dtype=torch.float32, device=x2d.device)
         ws = torch.empty((Cc * self.bn_chunks(rows, Cc),), dtype=torch.float64, device=x2d.device)
-        self._check(self.lib.b200_colsum(_ptr(x2d), C.c_int64(rows), Cc, _ptr(out), _ptr(ws), _stream()), "b200_colsum")
+        self._check(self.lib.b200_colsum(_ptr(x2d), C.c_int64(rows), Cc, _dt(x2d), _ptr(out), _ptr(ws), _stream()),
+                    "b200_colsum")
         return out
 
     # ---- spectral norm --------------------------------------------------------------------------------------
@@ -369,6 +408,25 @@ class Kernels:
         self._check(self.lib.b200_sn_grad(_ptr(g), _ptr(W), _ptr(u), _ptr(v), _ptr(inv_sigma), _ptr(dW), h, w,
                                           int(bool(accumulate)), _ptr(ws), _stream()), "b200_sn_grad")
         return dW
+
+    def sn_table(self, layers, stage, ws, iters):
+        """device array of b200_sn_layer for `layers` = [(W, u, v, h, w, stage_off, ws_off)]; per layer the stage buffer
+        holds [inv (iters) | u_hist (iters*h) | v_hist (iters*w)] at stage_off (floats)"""
+        arr = (SNLayer * len(layers))()
+        for i, (W, u, v, h, w, so, wo) in enumerate(layers):
+            base = stage.data_ptr() + 4 * so
+            arr[i] = SNLayer(W.data_ptr(), u.data_ptr(), v.data_ptr(), ws.data_ptr() + 4 * wo, base, base + 4 * iters,
+                             base + 4 * (iters + iters * h), h, w)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        return host.to(stage.device)
+
+    def sn_power_iter_multi(self, table, layers, stage, ws, iters, do_iter, eps):
+        """`iters` power iterations of every layer in `table` (built by sn_table from `layers`), 4 launches each"""
+        max_h = max(l[3] for l in layers)
+        max_w = max(l[4] for l in layers)
+        self._check(self.lib.b200_sn_power_iter_multi(_ptr(table), len(layers), max_h, max_w, int(iters),
+                                                      int(bool(do_iter)), C.c_float(eps), _stream()),
+                    "b200_sn_power_iter_multi")
 
     def copy_into(self, dst, dst_row, src):
         """dst[dst_row : dst_row + src.shape[0]] = src (contiguous tensors of equal row size and dtype)"""

@@ -28,8 +28,15 @@ def sn_prepare(net, groups=1):
     if layers is None:
         layers = [m for m in net.modules() if getattr(m, "_b200_sn", False)]
         net.__dict__["_sn_layers"] = layers
-    for m in layers:
-        m.__dict__["_sn_staged"] = ops.sn_iterate(m.weight_orig, m.weight_u, m.weight_v, groups, m.training)
+        net.__dict__["_sn_plans"] = {}
+    if not layers:
+        return
+    plans = net.__dict__["_sn_plans"]
+    plan = plans.get(groups)
+    if plan is None or not plan.valid_for(layers):
+        plan = plans[groups] = ops.SNPlan(layers, groups)
+    for m, call in zip(layers, plan.run(net.training)):
+        m.__dict__["_sn_staged"] = call
 
 
 def _weight(m):
@@ -45,10 +52,11 @@ class Conv2d(nn.Conv2d):
                               self.stride[0], self.padding[0])
         self._packs = WeightPacks()
 
-    def forward(self, x, x_layout="cl", out_layout="cl", relu=False, groups=1):
-        """groups: number of independent calls batched along dim 0 (each gets its own spectral-norm iteration)"""
+    def forward(self, x, x_layout="cl", out_layout="cl", relu=False, groups=1, out_dtype=None):
+        """groups: number of independent calls batched along dim 0 (each gets its own spectral-norm iteration);
+        out_dtype: storage type of a channel-last output (default: that of a channel-last input, else ops.act_dtype())"""
         return ops.conv2d(x, _weight(self), self.bias, self._geom, self._packs, x_layout, out_layout, relu,
-                          _sn_call(self, groups))
+                          _sn_call(self, groups), out_dtype)
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):
@@ -72,8 +80,8 @@ class Linear(nn.Linear):
         super().__init__(*a, **kw)
         self._packs = WeightPacks()
 
-    def forward(self, x, relu=False, groups=1):
-        return ops.linear(x, _weight(self), self.bias, self._packs, relu, _sn_call(self, groups))
+    def forward(self, x, relu=False, groups=1, out_dtype=None):
+        return ops.linear(x, _weight(self), self.bias, self._packs, relu, _sn_call(self, groups), None, out_dtype)
 
 
 class BatchNorm2d(nn.BatchNorm2d):

@@ -36,6 +36,12 @@ def get_precision() -> str:
     return _PRECISION
 
 
+def act_dtype() -> torch.dtype:
+    """storage type of channel-last activations (and their gradients) created by this package: bf16 in the bf16 mode,
+    fp32 otherwise.  NCHW boundary tensors, statistics, parameters and parameter gradients are always fp32."""
+    return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
+
+
 def bump_weight_epoch():
     """Invalidate every packed-weight cache entry (call after weights change behind autograd's back, e.g. a CUDA
     graph replay that contains the optimizer step)."""
@@ -63,10 +69,18 @@ def _dims(x: torch.Tensor, layout: str):
     return N, H, W, C, nchw_strides(C, H, W)
 
 
-def _empty(N, H, W, C, layout, device):
+def _empty(N, H, W, C, layout, device, dtype=torch.float32):
     if layout == "cl":
-        return torch.empty((N, H, W, C), dtype=torch.float32, device=device), cl_strides(H, W, C)
+        return torch.empty((N, H, W, C), dtype=dtype, device=device), cl_strides(H, W, C)
     return torch.empty((N, C, H, W), dtype=torch.float32, device=device), nchw_strides(C, H, W)
+
+
+def _out_dtype(x: torch.Tensor, x_layout: str, out_dtype: Optional[torch.dtype]) -> torch.dtype:
+    """channel-last outputs keep the storage type of a channel-last input; an NCHW (boundary) input starts a network,
+    whose activations take act_dtype()"""
+    if out_dtype is not None:
+        return out_dtype
+    return x.dtype if x_layout == "cl" else act_dtype()
 
 
 class ConvGeom:
@@ -164,12 +178,6 @@ def as_bf16(x: torch.Tensor) -> torch.Tensor:
     return _lib.K.cast_bf16(x.contiguous())
 
 
-def _need_f32(x: torch.Tensor) -> torch.Tensor:
-    if x.dtype != torch.float32:
-        raise _lib.B200Error("fp32 gather-GEMM received a %s operand" % x.dtype)
-    return x
-
-
 def _scale_rows(scale, rows: int) -> int:
     """rows of the GEMM that share one entry of `scale` (0 = a single scalar): batched spectral-norm calls"""
     if scale is None or scale.numel() == 1:
@@ -178,15 +186,18 @@ def _scale_rows(scale, rows: int) -> int:
     return rows // scale.numel()
 
 
-def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bias=None, scale=None, relu=False):
-    """Y = epilogue(conv(X, W)); on the tcgen05 path x may be passed already cast (as_bf16)"""
+def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bias=None, scale=None, relu=False,
+                 out_dtype=None):
+    """Y = epilogue(conv(X, W)); the tcgen05 path takes a bf16 activation (cast here if it is not), the fp32 path either"""
     N, Hx, Wx, Cx, xs = _dims(x, x_layout)
     assert Cx == g.Cx, (Cx, g.Cx)
     Hy, Wy = g.out_hw(Hx, Wx)
     tc = _tc_fwd_ok(g, x_layout)
-    x = as_bf16(x) if tc else _need_f32(x)
+    odt = _out_dtype(x, x_layout, out_dtype)
+    if tc:
+        x = as_bf16(x)
     wmat, ldw = packs.get(("fwd", tc) + g.key(), w, lambda: _pack_fwd(g, w, tc))
-    y, ys = _empty(N, Hy, Wy, g.Cy, out_layout, x.device)
+    y, ys = _empty(N, Hy, Wy, g.Cy, out_layout, x.device, odt)
     d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=g.Cx, Cout=g.Cy, Th=g.kh, Tw=g.kw, in_sy=g.s, in_sx=g.s, tap_sy=1, tap_sx=1,
                  tap_oy=-g.p, tap_ox=-g.p, Hi=Hx, Wi=Wx, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3],
                  out_sy=1, out_sx=1, out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ys[0], out_sh=ys[1], out_sw=ys[2],
@@ -195,16 +206,18 @@ def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bi
     return y
 
 
-def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layout, scale=None):
+def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layout, scale=None, out_dtype=None):
     """dX = conv^T(dY, W)  (also the forward of nn.ConvTranspose2d)"""
     N, Hy, Wy, Cy, ds = _dims(dy, dy_layout)
     assert Cy == g.Cy, (Cy, g.Cy)
     Hx, Wx = x_hw
     tc = _tc_dgrad_ok(g, dy_layout)
-    dy = as_bf16(dy) if tc else _need_f32(dy)
+    odt = _out_dtype(dy, dy_layout, out_dtype)
+    if tc:
+        dy = as_bf16(dy)
     phase_packs = packs.get(("dgrad", tc) + g.key(), w, lambda: _pack_dgrad(g, w, tc))
     phases = _dgrad_phases(g)
-    dx, xs = _empty(N, Hx, Wx, g.Cx, out_layout, dy.device)
+    dx, xs = _empty(N, Hx, Wx, g.Cx, out_layout, dy.device, odt)
     if any(p is None for p in phase_packs):
         dx.zero_()
     for (py, px, ky0, kx0, Th, Tw), pk in zip(phases, phase_packs):
@@ -240,7 +253,8 @@ def conv_wgrad(g: ConvGeom, x, x_layout, dy, dy_layout, dw: torch.Tensor, accumu
     _, Hy, Wy, Cy, ds = _dims(dy, dy_layout)
     assert Cx == g.Cx and Cy == g.Cy
     tc = _tc_wgrad_ok(g, x_layout, dy_layout)
-    x, dy = (as_bf16(x), as_bf16(dy)) if tc else (_need_f32(x), _need_f32(dy))
+    if tc:
+        x, dy = as_bf16(x), as_bf16(dy)
     kk = g.kh * g.kw
     if not tc and g.Cy <= 8 and g.Cx > 8 and g.s == 1:
         # skinny OUTPUT side (the 64->3 image convolutions): swap the roles so the 3-channel tensor is the gathered,
@@ -309,11 +323,54 @@ def sn_iterate(w, u, v, groups: int, training: bool) -> SNCall:
     return SNCall(groups, inv, u_hist, v_hist)
 
 
+class SNPlan:
+    """Whole-network power iteration (b200_sn_power_iter_multi): the device descriptor table, scratch and staging buffers
+    for the spectral-normalised layers of one network and one number of batched calls."""
+
+    def __init__(self, mods, groups: int):
+        self.groups = groups
+        self.mods = list(mods)
+        self.stamp = self._stamp(self.mods)
+        dev = self.mods[0].weight_orig.device
+        layers, so, wo = [], 0, 0
+        for m in self.mods:
+            W = m.weight_orig
+            h, wd = W.shape[0], W[0].numel()
+            layers.append((W, m.weight_u, m.weight_v, h, wd, so, wo))
+            so += groups * (1 + h + wd)
+            wo += 8 * wd + h
+        self.layers = layers
+        self.stage = torch.empty((so,), dtype=torch.float32, device=dev)
+        self.ws = torch.empty((wo,), dtype=torch.float32, device=dev)
+        self.table = _lib.K.sn_table(layers, self.stage, self.ws, groups)
+
+    @staticmethod
+    def _stamp(mods):
+        return tuple((m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr()) for m in mods)
+
+    def valid_for(self, mods) -> bool:
+        return self._stamp(mods) == self.stamp
+
+    def run(self, training: bool) -> List[SNCall]:
+        """`groups` iterations of every layer (4 launches per iteration), then one copy of the staged results into a
+        buffer this call owns (so a later call of the network cannot overwrite what this call's backward needs)."""
+        g = self.groups
+        _lib.K.sn_power_iter_multi(self.table, self.layers, self.stage, self.ws, g, training, SN_EPS)
+        own = torch.empty_like(self.stage)
+        _lib.K.copy_into(own.view(1, -1), 0, self.stage.view(1, -1))
+        calls = []
+        for (_, _, _, h, wd, so, _) in self.layers:
+            calls.append(SNCall(g, own[so:so + g], own[so + g:so + g + g * h].view(g, h),
+                                own[so + g + g * h:so + g + g * h + g * wd].view(g, wd)))
+        return calls
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, sn: Optional[SNCall], g: ConvGeom, packs: WeightPacks, transposed: bool, x_layout: str,
-                out_layout: str, relu: bool, out_hw):
+                out_layout: str, relu: bool, out_hw, out_dtype):
         scale = sn.inv if sn is not None else None
+        ctx.x_dtype = x.dtype
         ctx.sn = sn
         if not transposed:
             fwd_tc, wgrad_tc = _tc_fwd_ok(g, x_layout), _tc_wgrad_ok(g, x_layout, out_layout)
@@ -321,10 +378,10 @@ class _ConvFn(torch.autograd.Function):
             fwd_tc, wgrad_tc = _tc_dgrad_ok(g, x_layout), _tc_wgrad_ok(g, out_layout, x_layout)
         x_op = as_bf16(x) if fwd_tc else x      # cast once; the bf16 copy is also what a tcgen05 weight gradient consumes
         if not transposed:
-            y = conv_forward(g, packs, w, x_op, x_layout, out_layout, bias, scale, relu)
+            y = conv_forward(g, packs, w, x_op, x_layout, out_layout, bias, scale, relu, _out_dtype(x, x_layout, out_dtype))
         else:
             assert bias is None and not relu
-            y = conv_dgrad(g, packs, w, x_op, x_layout, out_hw, out_layout, scale)
+            y = conv_dgrad(g, packs, w, x_op, x_layout, out_hw, out_layout, scale, _out_dtype(x, x_layout, out_dtype))
         ctx.g, ctx.packs, ctx.transposed = g, packs, transposed
         ctx.x_layout, ctx.out_layout, ctx.relu = x_layout, out_layout, relu
         ctx.has_bias = bias is not None
@@ -351,9 +408,9 @@ class _ConvFn(torch.autograd.Function):
             dy_op = dyb if dgrad_tc else dy
             if not ctx.transposed:
                 _, Hx, Wx, _ = ctx.x_dims
-                dx = conv_dgrad(g, packs, w, dy_op, ctx.out_layout, (Hx, Wx), ctx.x_layout, scale)
+                dx = conv_dgrad(g, packs, w, dy_op, ctx.out_layout, (Hx, Wx), ctx.x_layout, scale, ctx.x_dtype)
             else:
-                dx = conv_forward(g, packs, w, dy_op, ctx.out_layout, ctx.x_layout, None, scale, False)
+                dx = conv_forward(g, packs, w, dy_op, ctx.out_layout, ctx.x_layout, None, scale, False, ctx.x_dtype)
         if need_dw:
             gw = torch.empty_like(w)
             dy_op = dyb if wgrad_tc else dy
@@ -374,24 +431,25 @@ class _ConvFn(torch.autograd.Function):
                     _lib.K.sn_grad(gw, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = bias_grad(dy, ctx.out_layout)
-        return dx, dw, db, None, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None, None
 
 
 def conv2d(x, w, bias, g: ConvGeom, packs: WeightPacks, x_layout="cl", out_layout="cl", relu=False,
-           sn: Optional[SNCall] = None):
-    return _ConvFn.apply(x, w, bias, sn, g, packs, False, x_layout, out_layout, relu, None)
+           sn: Optional[SNCall] = None, out_dtype=None):
+    return _ConvFn.apply(x, w, bias, sn, g, packs, False, x_layout, out_layout, relu, None, out_dtype)
 
 
 def conv_transpose2d(x, w, g: ConvGeom, packs: WeightPacks, out_hw, x_layout="cl", out_layout="cl"):
     """x plays dY of the conv-orientation geometry g (g.Cy = x channels, g.Cx = output channels)."""
-    return _ConvFn.apply(x, w, None, None, g, packs, True, x_layout, out_layout, False, out_hw)
+    return _ConvFn.apply(x, w, None, None, g, packs, True, x_layout, out_layout, False, out_hw, None)
 
 
-def linear(x2d, w, bias, packs: WeightPacks, relu=False, sn: Optional[SNCall] = None, geom: Optional[ConvGeom] = None):
+def linear(x2d, w, bias, packs: WeightPacks, relu=False, sn: Optional[SNCall] = None, geom: Optional[ConvGeom] = None,
+           out_dtype=None):
     B, Cin = x2d.shape
     g = geom if geom is not None else ConvGeom(Cin, w.shape[0], 1, 1, 1, 0)
     y = _ConvFn.apply(x2d.view(B, 1, 1, Cin), w.view(w.shape[0], w.shape[1], 1, 1), bias, sn, g, packs, False, "cl",
-                      "cl", relu, None)
+                      "cl", relu, None, out_dtype)
     return y.view(B, g.Cy)
 
 
@@ -613,7 +671,7 @@ class _MaskOuterFn(torch.autograd.Function):
         O, H, W = mask.shape[0], mask.shape[-2], mask.shape[-1]
         ctx.save_for_backward(mask)
         ctx.dims = (O, H, W, v.shape[1])
-        return _lib.K.mask_outer_fwd(v.contiguous(), mask, O, H, W, v.shape[1])
+        return _lib.K.mask_outer_fwd(v.contiguous(), mask, O, H, W, v.shape[1], act_dtype())
 
     @staticmethod
     def backward(ctx, dout):
@@ -794,7 +852,7 @@ class _ConvLSTMFn(torch.autograd.Function):
             w, b = params[2 * li], params[2 * li + 1]
             hid = L.hid
             pre_x = conv_forward(L.gx, L.packs, w, xin, "cl", "cl", b, None, False)        # (P,H,W,4h)
-            h_all = torch.empty((P, H, W, hid), dtype=torch.float32, device=dev)
+            h_all = torch.empty((P, H, W, hid), dtype=x.dtype, device=dev)      # activations; cell state and gates fp32
             c_all = torch.empty((P, H, W, hid), dtype=torch.float32, device=dev)
             gates = torch.empty((P, H, W, 4 * hid), dtype=torch.float32, device=dev)
             for t in range(plan.T):
@@ -829,7 +887,7 @@ class _ConvLSTMFn(torch.autograd.Function):
             w = params[2 * li]
             hid = L.hid
             xin, h_all, c_all, gates = saved[li]
-            dpre = torch.empty((P, H, W, 4 * hid), dtype=torch.float32, device=dout.device)
+            dpre = torch.empty((P, H, W, 4 * hid), dtype=dout.dtype, device=dout.device)
             dc_next = None
             n_next = 0
             for t in range(plan.T - 1, -1, -1):
@@ -845,7 +903,7 @@ class _ConvLSTMFn(torch.autograd.Function):
                                           c_all[a:bnd], (n - n_next) * hw, hid, dpre[a:bnd], dc_prev[n_next:n])
                 if t > 0:
                     op = plan.offs[t - 1]
-                    dh_rec = conv_dgrad(L.gh, L.packs, w, dpre[o:o + n], "cl", (H, W), "cl", None)
+                    dh_rec = conv_dgrad(L.gh, L.packs, w, dpre[o:o + n], "cl", (H, W), "cl", None, dout.dtype)
                     _lib.K.add(dH[op:op + n], dh_rec, out=dH[op:op + n])
                 dc_next, n_next = dc_prev, n
             gw = torch.empty_like(w)
@@ -855,7 +913,7 @@ class _ConvLSTMFn(torch.autograd.Function):
             conv_wgrad(L.gh, hprev, "cl", dpre_op, "cl", gw)
             grads[2 * li] = gw
             grads[2 * li + 1] = _lib.K.colsum(dpre.view(P * hw, 4 * hid))
-            dxin = conv_dgrad(L.gx, L.packs, w, dpre_op, "cl", (H, W), "cl", None)
+            dxin = conv_dgrad(L.gx, L.packs, w, dpre_op, "cl", (H, W), "cl", None, dout.dtype)
             dH = dxin
         dx = _lib.K.permute_rows(dH.view(P, hw * C0), plan.unpack_src, hw * C0).view(O, H, W, C0)
         return (dx, None, None) + tuple(grads)

@@ -38,11 +38,12 @@ __device__ __forceinline__ int64_t out_offset(const b200_conv_desc& d, int64_t m
 // forward-type gather GEMM: out[m, co] = sum_k A[m, k] * wmat[co, k]
 // VEC: Cin % 16 == 0, in_sc == 1, 16-byte aligned rows -> one tap per K step and float4 gathers
 // ----------------------------------------------------------------------------------------------------------
-template <bool VEC>
-__global__ void __launch_bounds__(256) conv_gemm_f32_kernel(b200_conv_desc d, const float* __restrict__ in,
+// TI / TO: storage types of the gathered input and of the output (float or bf16); fp32 arithmetic
+template <bool VEC, typename TI, typename TO>
+__global__ void __launch_bounds__(256) conv_gemm_f32_kernel(b200_conv_desc d, const TI* __restrict__ in,
                                                             const float* __restrict__ wmat,
                                                             const float* __restrict__ bias,
-                                                            const float* __restrict__ scale, float* __restrict__ out) {
+                                                            const float* __restrict__ scale, TO* __restrict__ out) {
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     __shared__ int64_t row_out[BM];
@@ -78,9 +79,9 @@ __global__ void __launch_bounds__(256) conv_gemm_f32_kernel(b200_conv_desc d, co
             int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
             int iy = rg.iy0 + tyy * d.tap_sy, ix = rg.ix0 + txx * d.tap_sx;
             if (rg.valid && iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi) {
-                const float* p = in + rg.in_base + (int64_t)(iy >> d.up_shift) * d.in_sh +
-                                 (int64_t)(ix >> d.up_shift) * d.in_sw + c0 + lk;
-                float4 v = *reinterpret_cast<const float4*>(p);
+                const TI* p = in + rg.in_base + (int64_t)(iy >> d.up_shift) * d.in_sh +
+                              (int64_t)(ix >> d.up_shift) * d.in_sw + c0 + lk;
+                float4 v = ld4(p);
                 a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
             }
         } else {
@@ -92,8 +93,8 @@ __global__ void __launch_bounds__(256) conv_gemm_f32_kernel(b200_conv_desc d, co
                     int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
                     int iy = rg.iy0 + tyy * d.tap_sy, ix = rg.ix0 + txx * d.tap_sx;
                     if (iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi)
-                        a[e] = in[rg.in_base + (int64_t)(iy >> d.up_shift) * d.in_sh +
-                                  (int64_t)(ix >> d.up_shift) * d.in_sw + (int64_t)c * d.in_sc];
+                        a[e] = ldf(in + rg.in_base + (int64_t)(iy >> d.up_shift) * d.in_sh +
+                                   (int64_t)(ix >> d.up_shift) * d.in_sw + (int64_t)c * d.in_sc);
                 }
             }
         }
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) conv_gemm_f32_kernel(b200_conv_desc d, co
             if (co >= d.Cout) continue;
             float v = acc[i][j] * alpha + (bias ? bias[co] : 0.f);
             if (d.relu) v = fmaxf(v, 0.f);
-            out[ro + (int64_t)co * d.out_sc] = v;
+            stf(out + ro + (int64_t)co * d.out_sc, v);
         }
     }
 }
@@ -150,8 +151,9 @@ __global__ void __launch_bounds__(256) conv_gemm_f32_kernel(b200_conv_desc d, co
 // weight-gradient gather GEMM: R[m, tap*Cin + c] = sum_q P[q, m] * G_tap[q, c]
 // grid: (ceil(Cout/64), taps * ceil(Cin/64), splits)
 // ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) wgrad_gemm_f32_kernel(b200_conv_desc d, const float* __restrict__ P,
-                                                             const float* __restrict__ G, float* __restrict__ ws,
+template <typename TP, typename TG>
+__global__ void __launch_bounds__(256) wgrad_gemm_f32_kernel(b200_conv_desc d, const TP* __restrict__ P,
+                                                             const TG* __restrict__ G, float* __restrict__ ws,
                                                              int64_t rows_per_split) {
     __shared__ __align__(16) float Ps[BK][BM + 4];
     __shared__ __align__(16) float Gs[BK][BN + 4];
@@ -184,18 +186,18 @@ __global__ void __launch_bounds__(256) wgrad_gemm_f32_kernel(b200_conv_desc d, c
             int64_t n = q / ((int64_t)d.Qw * d.Qh);
             int oy = qy * d.out_sy + d.out_oy, ox = qx * d.out_sx + d.out_ox;
             if (oy >= 0 && oy < d.Ho && ox >= 0 && ox < d.Wo) {
-                const float* pp = P + n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
+                const TP* pp = P + n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (m0 + lc + e < d.Cout) p[e] = pp[(int64_t)(m0 + lc + e) * d.out_sc];
+                    if (m0 + lc + e < d.Cout) p[e] = ldf(pp + (int64_t)(m0 + lc + e) * d.out_sc);
             }
             int iy = qy * d.in_sy + d.tap_oy + tyy * d.tap_sy, ix = qx * d.in_sx + d.tap_ox + txx * d.tap_sx;
             if (iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi) {
-                const float* gp = G + n * d.in_sn + (int64_t)(iy >> d.up_shift) * d.in_sh +
-                                  (int64_t)(ix >> d.up_shift) * d.in_sw;
+                const TG* gp = G + n * d.in_sn + (int64_t)(iy >> d.up_shift) * d.in_sh +
+                               (int64_t)(ix >> d.up_shift) * d.in_sw;
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (c0 + lc + e < d.Cin) g[e] = gp[(int64_t)(c0 + lc + e) * d.in_sc];
+                    if (c0 + lc + e < d.Cin) g[e] = ldf(gp + (int64_t)(c0 + lc + e) * d.in_sc);
             }
         }
         __syncthreads();
@@ -234,8 +236,9 @@ __global__ void __launch_bounds__(256) wgrad_gemm_f32_kernel(b200_conv_desc d, c
 // runs over the flattened (tap, channel) index instead of one tap's channels, so a 7x7x3 layer needs 3 column tiles
 // instead of 49 nearly empty ones.  grid: (ceil(Cout/64), ceil(Th*Tw*Cin/64), splits)
 // ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) wgrad_gemm_f32_flatk_kernel(b200_conv_desc d, const float* __restrict__ P,
-                                                                   const float* __restrict__ G, float* __restrict__ ws,
+template <typename TP, typename TG>
+__global__ void __launch_bounds__(256) wgrad_gemm_f32_flatk_kernel(b200_conv_desc d, const TP* __restrict__ P,
+                                                                   const TG* __restrict__ G, float* __restrict__ ws,
                                                                    int64_t rows_per_split) {
     __shared__ __align__(16) float Ps[BK][BM + 4];
     __shared__ __align__(16) float Gs[BK][BN + 4];
@@ -280,24 +283,24 @@ __global__ void __launch_bounds__(256) wgrad_gemm_f32_flatk_kernel(b200_conv_des
             int64_t n = q / ((int64_t)d.Qw * d.Qh);
             int oy = qy * d.out_sy + d.out_oy, ox = qx * d.out_sx + d.out_ox;
             if (oy >= 0 && oy < d.Ho && ox >= 0 && ox < d.Wo) {
-                const float* pp = P + n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
+                const TP* pp = P + n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
                 if (d.out_sc == 1 && m0 + lc + 3 < d.Cout && ((d.out_sn | d.out_sh | d.out_sw) & 3) == 0 &&
                     (reinterpret_cast<uintptr_t>(P) & 15) == 0) {
-                    float4 v = *reinterpret_cast<const float4*>(pp + m0 + lc);
+                    float4 v = ld4(pp + m0 + lc);
                     p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
                 } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        if (m0 + lc + e < d.Cout) p[e] = pp[(int64_t)(m0 + lc + e) * d.out_sc];
+                        if (m0 + lc + e < d.Cout) p[e] = ldf(pp + (int64_t)(m0 + lc + e) * d.out_sc);
                 }
             }
-            const float* gb = G + n * d.in_sn;
+            const TG* gb = G + n * d.in_sn;
             const int by = qy * d.in_sy, bx = qx * d.in_sx;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 int iy = by + goy[e], ix = bx + gox[e];
                 if (gok[e] && iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi)
-                    g[e] = __ldg(gb + (int64_t)(iy >> d.up_shift) * d.in_sh + (int64_t)(ix >> d.up_shift) * d.in_sw + gco[e]);
+                    g[e] = ldf(gb + (int64_t)(iy >> d.up_shift) * d.in_sh + (int64_t)(ix >> d.up_shift) * d.in_sw + gco[e]);
             }
         }
         __syncthreads();
@@ -334,40 +337,63 @@ __global__ void __launch_bounds__(256) wgrad_gemm_f32_flatk_kernel(b200_conv_des
 
 using namespace b200;
 
-extern "C" int b200_conv_gemm_f32(const b200_conv_desc* d, const float* in, const float* wmat, const float* bias,
-                                  const float* scale, float* out, b200_stream_t stream) {
+template <typename TI, typename TO>
+static void launch_conv_f32(const b200_conv_desc* d, const void* in, const float* wmat, const float* bias,
+                            const float* scale, void* out, dim3 grid, cudaStream_t st) {
+    // 4-element vector gathers need 4-element-aligned strides and base (16 B for fp32, 8 B for bf16)
+    bool vec = d->Cin % 16 == 0 && d->in_sc == 1 && d->in_sn % 4 == 0 && d->in_sh % 4 == 0 && d->in_sw % 4 == 0 &&
+               (reinterpret_cast<uintptr_t>(in) & (4 * sizeof(TI) - 1)) == 0;
+    if (vec)
+        conv_gemm_f32_kernel<true, TI, TO><<<grid, 256, 0, st>>>(*d, (const TI*)in, wmat, bias, scale, (TO*)out);
+    else
+        conv_gemm_f32_kernel<false, TI, TO><<<grid, 256, 0, st>>>(*d, (const TI*)in, wmat, bias, scale, (TO*)out);
+}
+
+extern "C" int b200_conv_gemm_f32(const b200_conv_desc* d, const void* in, int in_dt, const float* wmat,
+                                  const float* bias, const float* scale, void* out, int out_dt, b200_stream_t stream) {
     int64_t M = (int64_t)d->B * d->Qh * d->Qw;
     if (M == 0 || d->Cout == 0) return 0;
     B200_REQUIRE(d->Cin > 0 && d->Th > 0 && d->Tw > 0, "conv_gemm_f32: bad descriptor");
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((d->Cout + BN - 1) / BN));
     B200_REQUIRE(grid.y < 65536, "conv_gemm_f32: Cout too large");
-    bool vec = d->Cin % 16 == 0 && d->in_sc == 1 && d->in_sn % 4 == 0 && d->in_sh % 4 == 0 && d->in_sw % 4 == 0 &&
-               (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-    if (vec)
-        conv_gemm_f32_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(*d, in, wmat, bias, scale, out);
-    else
-        conv_gemm_f32_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(*d, in, wmat, bias, scale, out);
+    cudaStream_t st = as_stream(stream);
+    B200_DISPATCH_DT(in_dt, TI, {
+        if (out_dt == B200_BF16) launch_conv_f32<TI, bf16>(d, in, wmat, bias, scale, out, grid, st);
+        else launch_conv_f32<TI, float>(d, in, wmat, bias, scale, out, grid, st);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_wgrad_gemm_f32(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
-                                   b200_stream_t stream) {
+template <typename TP, typename TG>
+static int launch_wgrad_f32(const b200_conv_desc* d, const void* P, const void* G, float* ws, int splits, int64_t rps,
+                            cudaStream_t st) {
+    if (d->Cin <= 8) {
+        dim3 grid((unsigned)((d->Cout + BM - 1) / BM), (unsigned)((d->Th * d->Tw * d->Cin + BN - 1) / BN), (unsigned)splits);
+        wgrad_gemm_f32_flatk_kernel<TP, TG><<<grid, 256, 0, st>>>(*d, (const TP*)P, (const TG*)G, ws, rps);
+        return 0;
+    }
+    int ctiles = (d->Cin + BN - 1) / BN;
+    dim3 grid((unsigned)((d->Cout + BM - 1) / BM), (unsigned)(d->Th * d->Tw * ctiles), (unsigned)splits);
+    if (grid.y >= 65536) return set_error("wgrad_gemm_f32: too many tap tiles");
+    wgrad_gemm_f32_kernel<TP, TG><<<grid, 256, 0, st>>>(*d, (const TP*)P, (const TG*)G, ws, rps);
+    return 0;
+}
+
+extern "C" int b200_wgrad_gemm_f32(const b200_conv_desc* d, const void* P, int p_dt, const void* G, int g_dt, float* ws,
+                                   int splits, b200_stream_t stream) {
     int64_t Q = (int64_t)d->B * d->Qh * d->Qw;
     B200_REQUIRE(splits >= 1 && splits < 65536, "wgrad_gemm_f32: bad splits");
     int64_t rps = (Q + splits - 1) / splits;
     rps = (rps + BK - 1) / BK * BK;
     if (rps < BK) rps = BK;
-    if (d->Cin <= 8) {
-        dim3 grid((unsigned)((d->Cout + BM - 1) / BM), (unsigned)((d->Th * d->Tw * d->Cin + BN - 1) / BN), (unsigned)splits);
-        wgrad_gemm_f32_flatk_kernel<<<grid, 256, 0, as_stream(stream)>>>(*d, P, G, ws, rps);
-        B200_CHECK_LAUNCH();
-        return 0;
-    }
-    int ctiles = (d->Cin + BN - 1) / BN;
-    dim3 grid((unsigned)((d->Cout + BM - 1) / BM), (unsigned)(d->Th * d->Tw * ctiles), (unsigned)splits);
-    B200_REQUIRE(grid.y < 65536, "wgrad_gemm_f32: too many tap tiles");
-    wgrad_gemm_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(*d, P, G, ws, rps);
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    B200_DISPATCH_DT(p_dt, TP, {
+        if (g_dt == B200_BF16) rc = launch_wgrad_f32<TP, bf16>(d, P, G, ws, splits, rps, st);
+        else rc = launch_wgrad_f32<TP, float>(d, P, G, ws, splits, rps, st);
+    });
+    if (rc) return rc;
     B200_CHECK_LAUNCH();
     return 0;
 }

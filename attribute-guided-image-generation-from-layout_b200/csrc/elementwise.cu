@@ -1,4 +1,4 @@
-// elementwise.cu — HBM-bound pointwise / pooling / layout kernels of the G+D step (all channel-last fp32).
+// elementwise.cu — HBM-bound pointwise / pooling / layout kernels of the G+D step (channel-last activations stored as fp32 or bf16, fp32 arithmetic).
 // Reference call sites are cited per entry point in include/b200gan.h.
 #include "common.cuh"
 
@@ -7,38 +7,46 @@ namespace b200 {
 #define GRID_STRIDE(i, n) \
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
 
-__global__ void relu_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4, const float* xt,
-                                float* yt, int tail) {
+// T = storage type of the channel-last activations (float or bf16); arithmetic is fp32 throughout.
+template <typename T>
+__global__ void relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n4, int tail) {
     GRID_STRIDE(i, n4) {
-        float4 v = x[i];
+        float4 v = ld4(x + i * 4);
         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-        y[i] = v;
+        st4(y + i * 4, v);
     }
-    if (blockIdx.x == 0 && threadIdx.x < tail) yt[threadIdx.x] = fmaxf(xt[threadIdx.x], 0.f);
+    if (blockIdx.x == 0 && threadIdx.x < tail) stf(y + n4 * 4 + threadIdx.x, fmaxf(ldf(x + n4 * 4 + threadIdx.x), 0.f));
 }
 
-__global__ void relu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float4* __restrict__ dx,
-                                int64_t n4, const float* dyt, const float* yt, float* dxt, int tail) {
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t n4,
+                                int tail) {
     GRID_STRIDE(i, n4) {
-        float4 g = dy[i], v = y[i];
+        float4 g = ld4(dy + i * 4), v = ld4(y + i * 4);
         g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f; g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
-        dx[i] = g;
+        st4(dx + i * 4, g);
     }
-    if (blockIdx.x == 0 && threadIdx.x < tail) dxt[threadIdx.x] = yt[threadIdx.x] > 0.f ? dyt[threadIdx.x] : 0.f;
+    if (blockIdx.x == 0 && threadIdx.x < tail) {
+        const int64_t t = n4 * 4 + threadIdx.x;
+        stf(dx + t, ldf(y + t) > 0.f ? ldf(dy + t) : 0.f);
+    }
 }
 
-__global__ void add_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ o,
-                           int64_t n4, const float* at, const float* bt, float* ot, int tail) {
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, int64_t n4, int tail) {
     GRID_STRIDE(i, n4) {
-        float4 u = a[i], v = b[i];
-        o[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+        float4 u = ld4(a + i * 4), v = ld4(b + i * 4);
+        st4(o + i * 4, make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w));
     }
-    if (blockIdx.x == 0 && threadIdx.x < tail) ot[threadIdx.x] = at[threadIdx.x] + bt[threadIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x < tail) {
+        const int64_t t = n4 * 4 + threadIdx.x;
+        stf(o + t, ldf(a + t) + ldf(b + t));
+    }
 }
 
 // y[n,qy,qx,c] = scale * sum_{dy,dx<f} x[n,qy*f+dy,qx*f+dx,c];  V = channels per thread (4 when C % 4 == 0)
-template <int V>
-__global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int f,
+template <typename T, int V>
+__global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f,
                                 float scale) {
     const int Ho = H / f, Wo = W / f, Cv = C / V;
     const int64_t total = (int64_t)N * Ho * Wo * Cv;
@@ -47,26 +55,26 @@ __global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__
         const int qx = (int)((t / Cv) % Wo);
         const int qy = (int)((t / ((int64_t)Cv * Wo)) % Ho);
         const int n = (int)(t / ((int64_t)Cv * Wo * Ho));
-        const float* p = x + (((int64_t)n * H + (int64_t)qy * f) * W + (int64_t)qx * f) * C + c;
+        const T* p = x + (((int64_t)n * H + (int64_t)qy * f) * W + (int64_t)qx * f) * C + c;
         if (V == 4) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int dy = 0; dy < f; ++dy)
                 for (int dx = 0; dx < f; ++dx) {
-                    const float4 v = *reinterpret_cast<const float4*>(p + ((int64_t)dy * W + dx) * C);
+                    const float4 v = ld4(p + ((int64_t)dy * W + dx) * C);
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                 }
-            *reinterpret_cast<float4*>(y + t * 4) = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+            st4(y + t * 4, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
         } else {
             float acc = 0.f;
             for (int dy = 0; dy < f; ++dy)
-                for (int dx = 0; dx < f; ++dx) acc += p[((int64_t)dy * W + dx) * C];
-            y[t] = acc * scale;
+                for (int dx = 0; dx < f; ++dx) acc += ldf(p + ((int64_t)dy * W + dx) * C);
+            stf(y + t, acc * scale);
         }
     }
 }
 
-template <int V>
-__global__ void unpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int f,
+template <typename T, int V>
+__global__ void unpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f,
                                   float scale) {
     const int Ho = H * f, Wo = W * f, Cv = C / V;
     const int64_t total = (int64_t)N * Ho * Wo * Cv;
@@ -75,18 +83,19 @@ __global__ void unpool_fwd_kernel(const float* __restrict__ x, float* __restrict
         const int ox = (int)((t / Cv) % Wo);
         const int oy = (int)((t / ((int64_t)Cv * Wo)) % Ho);
         const int n = (int)(t / ((int64_t)Cv * Wo * Ho));
-        const float* p = x + (((int64_t)n * H + oy / f) * W + ox / f) * C + c;
+        const T* p = x + (((int64_t)n * H + oy / f) * W + ox / f) * C + c;
         if (V == 4) {
-            const float4 v = *reinterpret_cast<const float4*>(p);
-            *reinterpret_cast<float4*>(y + t * 4) = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+            const float4 v = ld4(p);
+            st4(y + t * 4, make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale));
         } else {
-            y[t] = scale * p[0];
+            stf(y + t, scale * ldf(p));
         }
     }
 }
 
-__global__ void concat_fwd_kernel(const float* __restrict__ a, int Ca, int a_div, const float* __restrict__ b, int Cb,
-                                  int b_div, float* __restrict__ out, int64_t rows) {
+template <typename T>
+__global__ void concat_fwd_kernel(const T* __restrict__ a, int Ca, int a_div, const T* __restrict__ b, int Cb,
+                                  int b_div, T* __restrict__ out, int64_t rows) {
     int Ct = Ca + Cb;
     int64_t total = rows * Ct;
     GRID_STRIDE(t, total) {
@@ -97,8 +106,9 @@ __global__ void concat_fwd_kernel(const float* __restrict__ a, int Ca, int a_div
 }
 
 // adjoint of concat: da[ra][c] = sum_{r in [ra*a_div, (ra+1)*a_div)} dout[r][c] (ascending r), same for b
-__global__ void concat_bwd_kernel(const float* __restrict__ dout, int Ca, int a_div, float* __restrict__ da, int Cb,
-                                  int b_div, float* __restrict__ db, int64_t rows) {
+template <typename T>
+__global__ void concat_bwd_kernel(const T* __restrict__ dout, int Ca, int a_div, T* __restrict__ da, int Cb,
+                                  int b_div, T* __restrict__ db, int64_t rows) {
     int Ct = Ca + Cb;
     int64_t na = da ? (rows / a_div) * Ca : 0;
     int64_t nb = db ? (rows / b_div) * Cb : 0;
@@ -107,15 +117,15 @@ __global__ void concat_bwd_kernel(const float* __restrict__ dout, int Ca, int a_
             int c = (int)(t % Ca);
             int64_t r0 = (t / Ca) * a_div;
             float acc = 0.f;
-            for (int k = 0; k < a_div; ++k) acc += dout[(r0 + k) * Ct + c];
-            da[t] = acc;
+            for (int k = 0; k < a_div; ++k) acc += ldf(dout + (r0 + k) * Ct + c);
+            stf(da + t, acc);
         } else {
             int64_t u = t - na;
             int c = (int)(u % Cb);
             int64_t r0 = (u / Cb) * b_div;
             float acc = 0.f;
-            for (int k = 0; k < b_div; ++k) acc += dout[(r0 + k) * Ct + Ca + c];
-            db[u] = acc;
+            for (int k = 0; k < b_div; ++k) acc += ldf(dout + (r0 + k) * Ct + Ca + c);
+            stf(db + u, acc);
         }
     }
 }
@@ -143,19 +153,21 @@ __global__ void scatter_rows_kernel(const float* __restrict__ dout, const int32_
     }
 }
 
-__global__ void permute_rows_kernel(const float4* __restrict__ x, const int32_t* __restrict__ src_row,
-                                    float4* __restrict__ out, int rows, int rowlen4) {
-    int64_t total = (int64_t)rows * rowlen4;
+// rows of 16-byte units (any element type)
+__global__ void permute_rows_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ src_row,
+                                    uint4* __restrict__ out, int rows, int rowlen16) {
+    int64_t total = (int64_t)rows * rowlen16;
     GRID_STRIDE(t, total) {
-        int c = (int)(t % rowlen4);
-        int r = (int)(t / rowlen4);
+        int c = (int)(t % rowlen16);
+        int r = (int)(t / rowlen16);
         int s = src_row[r];
-        out[t] = s >= 0 ? x[(int64_t)s * rowlen4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        out[t] = s >= 0 ? x[(int64_t)s * rowlen16 + c] : make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
+template <typename T>
 __global__ void mask_outer_fwd_kernel(const float* __restrict__ v, const float* __restrict__ mask,
-                                      float* __restrict__ out, int O, int H, int W, int C) {
+                                      T* __restrict__ out, int O, int H, int W, int C) {
     const int Hp = H + 2, Wp = W + 2, C4 = C >> 2;
     const int64_t total = (int64_t)O * Hp * Wp * C4;
     GRID_STRIDE(t, total) {
@@ -171,12 +183,13 @@ __global__ void mask_outer_fwd_kernel(const float* __restrict__ v, const float* 
                 r = make_float4(m * q.x, m * q.y, m * q.z, m * q.w);
             }
         }
-        *reinterpret_cast<float4*>(out + t * 4) = r;
+        st4(out + t * 4, r);
     }
 }
 
 // dv[o,c] = sum_{y,x} mask[o,y,x] * dout[o,y+1,x+1,c]; one block per (o, 32-channel group), fixed-order tree
-__global__ void mask_outer_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ mask,
+template <typename T>
+__global__ void mask_outer_bwd_kernel(const T* __restrict__ dout, const float* __restrict__ mask,
                                       float* __restrict__ dv, int O, int H, int W, int C) {
     __shared__ float red[8][32];
     int o = blockIdx.x;
@@ -187,7 +200,7 @@ __global__ void mask_outer_bwd_kernel(const float* __restrict__ dout, const floa
         for (int p = threadIdx.y; p < H * W; p += 8) {
             int y = p / W, x = p % W;
             float m = mask[((int64_t)o * H + y) * W + x];
-            if (m != 0.f) acc += m * dout[(((int64_t)o * (H + 2) + (y + 1)) * Wp + (x + 1)) * C + c];
+            if (m != 0.f) acc += m * ldf(dout + (((int64_t)o * (H + 2) + (y + 1)) * Wp + (x + 1)) * C + c);
         }
     }
     red[threadIdx.y][threadIdx.x] = acc;
@@ -201,28 +214,35 @@ __global__ void mask_outer_bwd_kernel(const float* __restrict__ dout, const floa
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-__global__ void lstm_gates_fwd_kernel(const float* __restrict__ pre_x, const float* __restrict__ pre_h,
+// pre-activations and the hidden state are activations (T); the cell state and the saved gates stay fp32
+template <typename T>
+__global__ void lstm_gates_fwd_kernel(const T* __restrict__ pre_x, const T* __restrict__ pre_h,
                                       const float* __restrict__ c_prev, float* __restrict__ gates,
-                                      float* __restrict__ c_out, float* __restrict__ h_out, int64_t rows, int hid) {
+                                      float* __restrict__ c_out, T* __restrict__ h_out, int64_t rows, int hid) {
     int64_t total = rows * hid;
     GRID_STRIDE(t, total) {
         int k = (int)(t % hid);
         int64_t r = t / hid;
         int64_t base = r * 4 * hid + k;
-        float pi = pre_x[base], pf = pre_x[base + hid], po = pre_x[base + 2 * hid], pg = pre_x[base + 3 * hid];
-        if (pre_h) { pi += pre_h[base]; pf += pre_h[base + hid]; po += pre_h[base + 2 * hid]; pg += pre_h[base + 3 * hid]; }
+        float pi = ldf(pre_x + base), pf = ldf(pre_x + base + hid), po = ldf(pre_x + base + 2 * hid),
+              pg = ldf(pre_x + base + 3 * hid);
+        if (pre_h) {
+            pi += ldf(pre_h + base); pf += ldf(pre_h + base + hid); po += ldf(pre_h + base + 2 * hid);
+            pg += ldf(pre_h + base + 3 * hid);
+        }
         float i = sigmoidf_(pi), f = sigmoidf_(pf), o = sigmoidf_(po), g = tanhf(pg);
         float cp = c_prev ? c_prev[t] : 0.f;
         float cn = f * cp + i * g;
         gates[base] = i; gates[base + hid] = f; gates[base + 2 * hid] = o; gates[base + 3 * hid] = g;
         c_out[t] = cn;
-        h_out[t] = o * tanhf(cn);
+        stf(h_out + t, o * tanhf(cn));
     }
 }
 
-__global__ void lstm_gates_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dc_next,
+template <typename T>
+__global__ void lstm_gates_bwd_kernel(const T* __restrict__ dh, const float* __restrict__ dc_next,
                                       const float* __restrict__ gates, const float* __restrict__ c_prev,
-                                      const float* __restrict__ c_out, float* __restrict__ dpre,
+                                      const float* __restrict__ c_out, T* __restrict__ dpre,
                                       float* __restrict__ dc_prev, int64_t rows, int hid) {
     int64_t total = rows * hid;
     GRID_STRIDE(t, total) {
@@ -231,13 +251,13 @@ __global__ void lstm_gates_bwd_kernel(const float* __restrict__ dh, const float*
         int64_t base = r * 4 * hid + k;
         float i = gates[base], f = gates[base + hid], o = gates[base + 2 * hid], g = gates[base + 3 * hid];
         float tc = tanhf(c_out[t]);
-        float dhv = dh[t];
+        float dhv = ldf(dh + t);
         float dc = (dc_next ? dc_next[t] : 0.f) + dhv * o * (1.f - tc * tc);
         float cp = c_prev ? c_prev[t] : 0.f;
-        dpre[base] = dc * g * i * (1.f - i);
-        dpre[base + hid] = dc * cp * f * (1.f - f);
-        dpre[base + 2 * hid] = dhv * tc * o * (1.f - o);
-        dpre[base + 3 * hid] = dc * i * (1.f - g * g);
+        stf(dpre + base, dc * g * i * (1.f - i));
+        stf(dpre + base + hid, dc * cp * f * (1.f - f));
+        stf(dpre + base + 2 * hid, dhv * tc * o * (1.f - o));
+        stf(dpre + base + 3 * hid, dc * i * (1.f - g * g));
         dc_prev[t] = dc * f;
     }
 }
@@ -255,7 +275,8 @@ __global__ void reparam_bwd_kernel(const float* dz, const float* logvar, const f
 }
 
 // column sums: stage 1 per-chunk partial (double), stage 2 fixed-order combine
-__global__ void colsum_partial_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t rows_per_chunk,
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int C, int64_t rows_per_chunk,
                                       double* __restrict__ ws) {
     __shared__ double red[8][33];
     int c = blockIdx.y * 32 + threadIdx.x;
@@ -263,7 +284,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ x, int64_t rows,
     int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
     double acc = 0.0;
     if (c < C)
-        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += (double)x[r * C + c];
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += (double)ldf(x + r * C + c);
     red[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
@@ -353,80 +374,95 @@ using namespace b200;
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-extern "C" int b200_relu_fwd(const float* x, float* y, int64_t n, b200_stream_t stream) {
+template <typename T>
+static inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & (4 * sizeof(T) - 1)) == 0; }
+
+extern "C" int b200_relu_fwd(const void* x, void* y, int64_t n, int dt, b200_stream_t stream) {
     if (n == 0) return 0;
-    int64_t n4 = (aligned16(x) && aligned16(y)) ? n / 4 : 0;
-    int tail = (int)(n - n4 * 4);
-    B200_REQUIRE(tail < 256, "relu_fwd: unaligned large tensor");
-    relu_fwd_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const float4*)x, (float4*)y, n4,
-                                                                                   x + n4 * 4, y + n4 * 4, tail);
+    B200_DISPATCH_DT(dt, T, {
+        int64_t n4 = (aligned4<T>(x) && aligned4<T>(y)) ? n / 4 : 0;
+        int tail = (int)(n - n4 * 4);
+        B200_REQUIRE(tail < 256, "relu_fwd: unaligned large tensor");
+        relu_fwd_kernel<T><<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, n4, tail);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, b200_stream_t stream) {
+extern "C" int b200_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, int dt, b200_stream_t stream) {
     if (n == 0) return 0;
-    int64_t n4 = (aligned16(dy) && aligned16(y) && aligned16(dx)) ? n / 4 : 0;
-    int tail = (int)(n - n4 * 4);
-    B200_REQUIRE(tail < 256, "relu_bwd: unaligned large tensor");
-    relu_bwd_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>(
-        (const float4*)dy, (const float4*)y, (float4*)dx, n4, dy + n4 * 4, y + n4 * 4, dx + n4 * 4, tail);
+    B200_DISPATCH_DT(dt, T, {
+        int64_t n4 = (aligned4<T>(dy) && aligned4<T>(y) && aligned4<T>(dx)) ? n / 4 : 0;
+        int tail = (int)(n - n4 * 4);
+        B200_REQUIRE(tail < 256, "relu_bwd: unaligned large tensor");
+        relu_bwd_kernel<T><<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const T*)dy, (const T*)y, (T*)dx,
+                                                                                      n4, tail);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_add(const float* a, const float* b, float* out, int64_t n, b200_stream_t stream) {
+extern "C" int b200_add(const void* a, const void* b, void* out, int64_t n, int dt, b200_stream_t stream) {
     if (n == 0) return 0;
-    int64_t n4 = (aligned16(a) && aligned16(b) && aligned16(out)) ? n / 4 : 0;
-    int tail = (int)(n - n4 * 4);
-    B200_REQUIRE(tail < 256, "add: unaligned large tensor");
-    add_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const float4*)a, (const float4*)b,
-                                                                              (float4*)out, n4, a + n4 * 4, b + n4 * 4,
-                                                                              out + n4 * 4, tail);
+    B200_DISPATCH_DT(dt, T, {
+        int64_t n4 = (aligned4<T>(a) && aligned4<T>(b) && aligned4<T>(out)) ? n / 4 : 0;
+        int tail = (int)(n - n4 * 4);
+        B200_REQUIRE(tail < 256, "add: unaligned large tensor");
+        add_kernel<T><<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (T*)out, n4,
+                                                                                 tail);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_pool_fwd(const float* x, float* y, int N, int H, int W, int C, int f, float scale,
+extern "C" int b200_pool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt,
                              b200_stream_t stream) {
     B200_REQUIRE(f >= 1 && H % f == 0 && W % f == 0, "pool_fwd: H=%d W=%d not divisible by f=%d", H, W, f);
     int64_t total = (int64_t)N * (H / f) * (W / f) * C;
     if (total == 0) return 0;
-    if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
-        pool_fwd_kernel<4><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
-    else
-        pool_fwd_kernel<1><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
+    B200_DISPATCH_DT(dt, T, {
+        if (C % 4 == 0 && aligned4<T>(x) && aligned4<T>(y))
+            pool_fwd_kernel<T, 4><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+        else
+            pool_fwd_kernel<T, 1><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_unpool_fwd(const float* x, float* y, int N, int H, int W, int C, int f, float scale,
+extern "C" int b200_unpool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt,
                                b200_stream_t stream) {
     int64_t total = (int64_t)N * H * f * W * f * C;
     if (total == 0) return 0;
-    if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
-        unpool_fwd_kernel<4><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
-    else
-        unpool_fwd_kernel<1><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, f, scale);
+    B200_DISPATCH_DT(dt, T, {
+        if (C % 4 == 0 && aligned4<T>(x) && aligned4<T>(y))
+            unpool_fwd_kernel<T, 4><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+        else
+            unpool_fwd_kernel<T, 1><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_concat_fwd(const float* a, int Ca, int a_div, const float* b, int Cb, int b_div, float* out,
-                               int64_t rows, b200_stream_t stream) {
+extern "C" int b200_concat_fwd(const void* a, int Ca, int a_div, const void* b, int Cb, int b_div, void* out,
+                               int64_t rows, int dt, b200_stream_t stream) {
     if (rows == 0) return 0;
-    concat_fwd_kernel<<<grid_for(rows * (Ca + Cb), 256), 256, 0, as_stream(stream)>>>(a, Ca, a_div, b, Cb, b_div, out,
-                                                                                      rows);
+    B200_DISPATCH_DT(dt, T, {
+        concat_fwd_kernel<T><<<grid_for(rows * (Ca + Cb), 256), 256, 0, as_stream(stream)>>>((const T*)a, Ca, a_div, (const T*)b,
+                                                                                         Cb, b_div, (T*)out, rows);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_concat_bwd(const float* dout, int Ca, int a_div, float* da, int Cb, int b_div, float* db,
-                               int64_t rows, b200_stream_t stream) {
+extern "C" int b200_concat_bwd(const void* dout, int Ca, int a_div, void* da, int Cb, int b_div, void* db,
+                               int64_t rows, int dt, b200_stream_t stream) {
     if (rows == 0) return 0;
     B200_REQUIRE(rows % a_div == 0 && rows % b_div == 0, "concat_bwd: rows not divisible by broadcast factors");
-    concat_bwd_kernel<<<grid_for(rows * (Ca + Cb), 256), 256, 0, as_stream(stream)>>>(dout, Ca, a_div, da, Cb, b_div,
-                                                                                      db, rows);
+    B200_DISPATCH_DT(dt, T, {
+        concat_bwd_kernel<T><<<grid_for(rows * (Ca + Cb), 256), 256, 0, as_stream(stream)>>>((const T*)dout, Ca, a_div, (T*)da,
+                                                                                         Cb, b_div, (T*)db, rows);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -447,50 +483,58 @@ extern "C" int b200_scatter_rows(const float* dout, const int32_t* idx, float* d
     return 0;
 }
 
-extern "C" int b200_permute_rows(const float* x, const int32_t* src_row, float* out, int rows, int rowlen,
+extern "C" int b200_permute_rows(const void* x, const int32_t* src_row, void* out, int rows, int64_t row_bytes,
                                  b200_stream_t stream) {
     if (rows == 0) return 0;
-    B200_REQUIRE(rowlen % 4 == 0 && aligned16(x) && aligned16(out), "permute_rows: rowlen %% 4 != 0 or unaligned");
-    permute_rows_kernel<<<grid_for((int64_t)rows * (rowlen / 4), 256), 256, 0, as_stream(stream)>>>(
-        (const float4*)x, src_row, (float4*)out, rows, rowlen / 4);
+    B200_REQUIRE(row_bytes % 16 == 0 && aligned16(x) && aligned16(out), "permute_rows: row_bytes %% 16 != 0 or unaligned");
+    permute_rows_kernel<<<grid_for((int64_t)rows * (row_bytes / 16), 256), 256, 0, as_stream(stream)>>>(
+        (const uint4*)x, src_row, (uint4*)out, rows, (int)(row_bytes / 16));
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_mask_outer_fwd(const float* v, const float* mask, float* out, int O, int H, int W, int C,
+extern "C" int b200_mask_outer_fwd(const float* v, const float* mask, void* out, int O, int H, int W, int C, int dt,
                                    b200_stream_t stream) {
     if (O == 0) return 0;
     B200_REQUIRE(C % 4 == 0, "mask_outer_fwd: C=%d must be a multiple of 4", C);
     int64_t total = (int64_t)O * (H + 2) * (W + 2) * (C / 4);
-    mask_outer_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(v, mask, out, O, H, W, C);
+    B200_DISPATCH_DT(dt, T, {
+        mask_outer_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(v, mask, (T*)out, O, H, W, C);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_mask_outer_bwd(const float* dout, const float* mask, float* dv, int O, int H, int W, int C,
+extern "C" int b200_mask_outer_bwd(const void* dout, const float* mask, float* dv, int O, int H, int W, int C, int dt,
                                    b200_stream_t stream) {
     if (O == 0) return 0;
     dim3 grid(O, (C + 31) / 32), block(32, 8);
-    mask_outer_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(dout, mask, dv, O, H, W, C);
+    B200_DISPATCH_DT(dt, T, {
+        mask_outer_bwd_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)dout, mask, dv, O, H, W, C);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_lstm_gates_fwd(const float* pre_x, const float* pre_h, const float* c_prev, float* gates,
-                                   float* c_out, float* h_out, int64_t rows, int hid, b200_stream_t stream) {
+extern "C" int b200_lstm_gates_fwd(const void* pre_x, const void* pre_h, const float* c_prev, float* gates,
+                                   float* c_out, void* h_out, int64_t rows, int hid, int dt, b200_stream_t stream) {
     if (rows == 0) return 0;
-    lstm_gates_fwd_kernel<<<grid_for(rows * hid, 256), 256, 0, as_stream(stream)>>>(pre_x, pre_h, c_prev, gates, c_out,
-                                                                                    h_out, rows, hid);
+    B200_DISPATCH_DT(dt, T, {
+        lstm_gates_fwd_kernel<T><<<grid_for(rows * hid, 256), 256, 0, as_stream(stream)>>>(
+            (const T*)pre_x, (const T*)pre_h, c_prev, gates, c_out, (T*)h_out, rows, hid);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_lstm_gates_bwd(const float* dh, const float* dc_next, const float* gates, const float* c_prev,
-                                   const float* c_out, float* dpre, float* dc_prev, int64_t rows, int hid,
+extern "C" int b200_lstm_gates_bwd(const void* dh, const float* dc_next, const float* gates, const float* c_prev,
+                                   const float* c_out, void* dpre, float* dc_prev, int64_t rows, int hid, int dt,
                                    b200_stream_t stream) {
     if (rows == 0) return 0;
-    lstm_gates_bwd_kernel<<<grid_for(rows * hid, 256), 256, 0, as_stream(stream)>>>(dh, dc_next, gates, c_prev, c_out,
-                                                                                    dpre, dc_prev, rows, hid);
+    B200_DISPATCH_DT(dt, T, {
+        lstm_gates_bwd_kernel<T><<<grid_for(rows * hid, 256), 256, 0, as_stream(stream)>>>(
+            (const T*)dh, dc_next, gates, c_prev, c_out, (T*)dpre, dc_prev, rows, hid);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -522,12 +566,12 @@ extern "C" int b200_bn_chunks(int64_t rows, int C) {
     return (int)n;
 }
 
-extern "C" int b200_colsum(const float* x, int64_t rows, int C, float* out, double* ws, b200_stream_t stream) {
+extern "C" int b200_colsum(const void* x, int64_t rows, int C, int dt, float* out, double* ws, b200_stream_t stream) {
     int nchunks = b200_bn_chunks(rows, C);
     int64_t rpc = (rows + nchunks - 1) / nchunks;
     if (rpc < 1) rpc = 1;
     dim3 grid(nchunks, (C + 31) / 32), block(32, 8);
-    colsum_partial_kernel<<<grid, block, 0, as_stream(stream)>>>(x, rows, C, rpc, ws);
+    B200_DISPATCH_DT(dt, T, { colsum_partial_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, rows, C, rpc, ws); });
     B200_CHECK_LAUNCH();
     colsum_final_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, nchunks, C, out);
     B200_CHECK_LAUNCH();

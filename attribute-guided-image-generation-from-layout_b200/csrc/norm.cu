@@ -11,7 +11,8 @@ namespace b200 {
 // statistics.  `groups` independent calls batched along the row dimension (rows = groups * rows_per_group) keep
 // separate statistics: grid.z = group, chunks never straddle a group.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void bn_stats_partial_kernel(const float* __restrict__ x, int64_t rows_per_group, int C,
+template <typename T>
+__global__ void bn_stats_partial_kernel(const T* __restrict__ x, int64_t rows_per_group, int C,
                                         int64_t rows_per_chunk, double* __restrict__ ws) {
     __shared__ double r1[8][33], r2[8][33];
     int c = blockIdx.y * 32 + threadIdx.x;
@@ -22,7 +23,7 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ x, int64_t row
     double s1 = 0.0, s2 = 0.0;
     if (c < C) {
         for (int64_t r = a + threadIdx.y; r < b; r += 8) {
-            double v = (double)x[r * C + c];
+            double v = (double)ldf(x + r * C + c);
             s1 += v;
             s2 += v * v;
         }
@@ -75,18 +76,21 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ ws, int nchunks
 // ---------------------------------------------------------------------------------------------------------
 // forward apply
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void norm_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t rows, int C,
+// T: storage type of x, y, residual and (SPADE) the gamma|beta activation; parameter tables are fp32
+template <typename T, int MODE>
+__global__ void norm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int C,
                                 const float* __restrict__ mean, const float* __restrict__ var, float eps,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const int32_t* __restrict__ idx, int rows_per_seg, const float4* __restrict__ residual,
+                                const void* __restrict__ gamma_v, const float* __restrict__ beta,
+                                const int32_t* __restrict__ idx, int rows_per_seg, const T* __restrict__ residual,
                                 int relu, int64_t rows_per_group) {
+    const float* gamma = reinterpret_cast<const float*>(gamma_v);
+    const T* gb = reinterpret_cast<const T*>(gamma_v);
     int C4 = C >> 2;
     int64_t total = rows * C4;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)(t % C4) << 2;
         int64_t r = t / C4;
-        float4 v = x[t];
+        float4 v = ld4(x + t * 4);
         const int64_t go = (r / rows_per_group) * C;
         float4 m = *reinterpret_cast<const float4*>(mean + go + c);
         float4 vv = *reinterpret_cast<const float4*>(var + go + c);
@@ -105,28 +109,28 @@ __global__ void norm_fwd_kernel(const float4* __restrict__ x, float4* __restrict
             float4 b = *reinterpret_cast<const float4*>(row + C + c);
             o.x = g.x * o.x + b.x; o.y = g.y * o.y + b.y; o.z = g.z * o.z + b.z; o.w = g.w * o.w + b.w;
         } else if (MODE == B200_NORM_SPADE) {
-            const float* row = gamma + r * 2 * C;
-            float4 g = *reinterpret_cast<const float4*>(row + c);
-            float4 b = *reinterpret_cast<const float4*>(row + C + c);
+            const T* row = gb + r * 2 * C;
+            float4 g = ld4(row + c);
+            float4 b = ld4(row + C + c);
             o.x = o.x * (1.f + g.x) + b.x; o.y = o.y * (1.f + g.y) + b.y;
             o.z = o.z * (1.f + g.z) + b.z; o.w = o.w * (1.f + g.w) + b.w;
         }
         if (residual) {
-            float4 q = residual[t];
+            float4 q = ld4(residual + t * 4);
             o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
         }
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        y[t] = o;
+        st4(y + t * 4, o);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // backward stage 1: per-segment sums
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void norm_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                       const float* __restrict__ y, int64_t rows, int C, const float* __restrict__ mean,
-                                       const float* __restrict__ var, float eps, const float* __restrict__ gamma,
+template <typename T, int MODE>
+__global__ void norm_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                       const T* __restrict__ y, int64_t rows, int C, const float* __restrict__ mean,
+                                       const float* __restrict__ var, float eps, const void* __restrict__ gamma,
                                        int rows_per_seg, int relu, double* __restrict__ seg_sums,
                                        int64_t rows_per_group, int segs_per_group) {
     __shared__ double r1[8][33], r2[8][33];
@@ -140,10 +144,10 @@ __global__ void norm_bwd_reduce_kernel(const float* __restrict__ dy, const float
     if (c < C) {
         float m = mean[(int64_t)g * C + c], rstd = 1.f / sqrtf(var[(int64_t)g * C + c] + eps);
         for (int64_t r = a + threadIdx.y; r < b; r += 8) {
-            float g = dy[r * C + c];
-            if (relu && !(y[r * C + c] > 0.f)) g = 0.f;
-            float xh = (x[r * C + c] - m) * rstd;
-            if (MODE == B200_NORM_SPADE) g *= 1.f + gamma[r * 2 * C + c];
+            float g = ldf(dy + r * C + c);
+            if (relu && !(ldf(y + r * C + c) > 0.f)) g = 0.f;
+            float xh = (ldf(x + r * C + c) - m) * rstd;
+            if (MODE == B200_NORM_SPADE) g *= 1.f + ldf(reinterpret_cast<const T*>(gamma) + r * 2 * C + c);
             s1 += (double)g;
             s2 += (double)g * (double)xh;
         }
@@ -219,25 +223,26 @@ __global__ void cbn_dtable_kernel(const double* __restrict__ seg, int nseg, int 
 }
 
 // stage 3 (4 channels per thread)
-template <int MODE>
-__global__ void norm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                      const float* __restrict__ y, float* __restrict__ dx, int64_t rows, int C,
+template <typename T, int MODE>
+__global__ void norm_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                      const T* __restrict__ y, T* __restrict__ dx, int64_t rows, int C,
                                       const float* __restrict__ mean, const float* __restrict__ var, float eps,
-                                      const float* __restrict__ gamma, const int32_t* __restrict__ idx,
-                                      int rows_per_seg, int relu, const float* __restrict__ s, float* __restrict__ dgb,
+                                      const void* __restrict__ gamma_v, const int32_t* __restrict__ idx,
+                                      int rows_per_seg, int relu, const float* __restrict__ s, T* __restrict__ dgb,
                                       int64_t rows_per_group) {
+    const float* gamma = reinterpret_cast<const float*>(gamma_v);
     const int C4 = C >> 2;
     const int64_t total = rows * C4;
     const float inv_rows = 1.f / (float)rows_per_group;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(t % C4) << 2;
         const int64_t r = t / C4;
-        const float4 g4 = *reinterpret_cast<const float4*>(dy + t * 4);
-        const float4 x4 = *reinterpret_cast<const float4*>(x + t * 4);
+        const float4 g4 = ld4(dy + t * 4);
+        const float4 x4 = ld4(x + t * 4);
         float g[4] = {g4.x, g4.y, g4.z, g4.w};
         const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
         if (relu) {
-            const float4 y4 = *reinterpret_cast<const float4*>(y + t * 4);
+            const float4 y4 = ld4(y + t * 4);
             if (!(y4.x > 0.f)) g[0] = 0.f;
             if (!(y4.y > 0.f)) g[1] = 0.f;
             if (!(y4.z > 0.f)) g[2] = 0.f;
@@ -256,7 +261,7 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ dy, const float*
             const float4 q = *reinterpret_cast<const float4*>(gamma + (int64_t)idx[r / rows_per_seg] * 2 * C + c);
             ga[0] = q.x; ga[1] = q.y; ga[2] = q.z; ga[3] = q.w;
         } else if (MODE == B200_NORM_SPADE) {
-            const float4 q = *reinterpret_cast<const float4*>(gamma + r * 2 * C + c);
+            const float4 q = ld4(reinterpret_cast<const T*>(gamma_v) + r * 2 * C + c);
             ga[0] = 1.f + q.x; ga[1] = 1.f + q.y; ga[2] = 1.f + q.z; ga[3] = 1.f + q.w;
         }
         float o[4], gx[4];
@@ -269,10 +274,10 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ dy, const float*
             o[e] = rstd * (dxh - s[(go + c + e) * 2] * inv_rows - xh * s[(go + c + e) * 2 + 1] * inv_rows);
         }
         if (MODE == B200_NORM_SPADE) {
-            *reinterpret_cast<float4*>(dgb + r * 2 * C + c) = make_float4(gx[0], gx[1], gx[2], gx[3]);
-            *reinterpret_cast<float4*>(dgb + r * 2 * C + C + c) = make_float4(g[0], g[1], g[2], g[3]);
+            st4(dgb + r * 2 * C + c, make_float4(gx[0], gx[1], gx[2], gx[3]));
+            st4(dgb + r * 2 * C + C + c, make_float4(g[0], g[1], g[2], g[3]));
         }
-        *reinterpret_cast<float4*>(dx + t * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        st4(dx + t * 4, make_float4(o[0], o[1], o[2], o[3]));
     }
 }
 
@@ -280,7 +285,7 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ dy, const float*
 
 using namespace b200;
 
-extern "C" int b200_bn_stats(const float* x, int64_t rows, int C, int groups, float* mean, float* var,
+extern "C" int b200_bn_stats(const void* x, int dt, int64_t rows, int C, int groups, float* mean, float* var,
                              float* running_mean, float* running_var, float momentum, double* ws,
                              b200_stream_t stream) {
     B200_REQUIRE(rows > 0 && C > 0 && groups >= 1 && rows % groups == 0, "bn_stats: bad rows=%lld groups=%d", (long long)rows, groups);
@@ -289,7 +294,7 @@ extern "C" int b200_bn_stats(const float* x, int64_t rows, int C, int groups, fl
     int nchunks = b200_bn_chunks(rpg, C);
     int64_t rpc = (rpg + nchunks - 1) / nchunks;
     dim3 grid(nchunks, (C + 31) / 32, groups), block(32, 8);
-    bn_stats_partial_kernel<<<grid, block, 0, as_stream(stream)>>>(x, rpg, C, rpc, ws);
+    B200_DISPATCH_DT(dt, T, { bn_stats_partial_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, rpg, C, rpc, ws); });
     B200_CHECK_LAUNCH();
     bn_stats_final_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, nchunks, C, groups, rpg, mean, var, running_mean,
                                                                       running_var, momentum);
@@ -297,43 +302,51 @@ extern "C" int b200_bn_stats(const float* x, int64_t rows, int C, int groups, fl
     return 0;
 }
 
-extern "C" int b200_norm_fwd(const float* x, float* y, int64_t rows, int C, int groups, const float* mean,
-                             const float* var, float eps, int mode, const float* gamma, const float* beta,
-                             const int32_t* idx, int rows_per_seg, const float* residual, int relu,
+template <typename T>
+static int norm_fwd_launch(const void* x, void* y, int64_t rows, int C, int64_t rpg, const float* mean, const float* var,
+                           float eps, int mode, const void* gamma, const float* beta, const int32_t* idx, int rows_per_seg,
+                           const void* residual, int relu, cudaStream_t st) {
+    const int g = grid_for(rows * (C / 4), 256);
+    const T* xp = (const T*)x;
+    T* yp = (T*)y;
+    const T* rp = (const T*)residual;
+    switch (mode) {
+        case B200_NORM_PLAIN:
+            norm_fwd_kernel<T, B200_NORM_PLAIN><<<g, 256, 0, st>>>(xp, yp, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, rp, relu, rpg);
+            break;
+        case B200_NORM_AFFINE:
+            norm_fwd_kernel<T, B200_NORM_AFFINE><<<g, 256, 0, st>>>(xp, yp, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, rp, relu, rpg);
+            break;
+        case B200_NORM_CBN:
+            norm_fwd_kernel<T, B200_NORM_CBN><<<g, 256, 0, st>>>(xp, yp, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, rp, relu, rpg);
+            break;
+        case B200_NORM_SPADE:
+            norm_fwd_kernel<T, B200_NORM_SPADE><<<g, 256, 0, st>>>(xp, yp, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, rp, relu, rpg);
+            break;
+        default:
+            return set_error("norm_fwd: bad mode %d", mode);
+    }
+    return 0;
+}
+
+extern "C" int b200_norm_fwd(const void* x, void* y, int dt, int64_t rows, int C, int groups, const float* mean,
+                             const float* var, float eps, int mode, const void* gamma, const float* beta,
+                             const int32_t* idx, int rows_per_seg, const void* residual, int relu,
                              b200_stream_t stream) {
     B200_REQUIRE(C % 4 == 0, "norm_fwd: C=%d must be a multiple of 4", C);
     if (rows == 0) return 0;
     B200_REQUIRE(groups >= 1 && rows % groups == 0, "norm_fwd: rows %% groups != 0");
     const int64_t rpg = rows / groups;
-    int64_t total = rows * (C / 4);
-    int g = grid_for(total, 256);
-    cudaStream_t st = as_stream(stream);
-    const float4* x4 = (const float4*)x;
-    float4* y4 = (float4*)y;
-    const float4* r4 = (const float4*)residual;
     if (rows_per_seg < 1) rows_per_seg = 1;
-    switch (mode) {
-        case B200_NORM_PLAIN:
-            norm_fwd_kernel<B200_NORM_PLAIN><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu, rpg);
-            break;
-        case B200_NORM_AFFINE:
-            norm_fwd_kernel<B200_NORM_AFFINE><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu, rpg);
-            break;
-        case B200_NORM_CBN:
-            norm_fwd_kernel<B200_NORM_CBN><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu, rpg);
-            break;
-        case B200_NORM_SPADE:
-            norm_fwd_kernel<B200_NORM_SPADE><<<g, 256, 0, st>>>(x4, y4, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, r4, relu, rpg);
-            break;
-        default:
-            return set_error("norm_fwd: bad mode %d", mode);
-    }
+    int rc;
+    B200_DISPATCH_DT(dt, T, { rc = norm_fwd_launch<T>(x, y, rows, C, rpg, mean, var, eps, mode, gamma, beta, idx, rows_per_seg, residual, relu, as_stream(stream)); });
+    if (rc) return rc;
     B200_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int b200_norm_bwd_reduce(const float* dy, const float* x, const float* y, int64_t rows, int C, int groups,
-                                    const float* mean, const float* var, float eps, int mode, const float* gamma,
+extern "C" int b200_norm_bwd_reduce(const void* dy, const void* x, const void* y, int dt, int64_t rows, int C, int groups,
+                                    const float* mean, const float* var, float eps, int mode, const void* gamma,
                                     const int32_t* idx, int rows_per_seg, int relu, double* seg_sums,
                                     b200_stream_t stream) {
     (void)idx;
@@ -342,10 +355,12 @@ extern "C" int b200_norm_bwd_reduce(const float* dy, const float* x, const float
     const int spg = (int)((rpg + rows_per_seg - 1) / rows_per_seg);
     dim3 grid(spg * groups, (C + 31) / 32), block(32, 8);
     cudaStream_t st = as_stream(stream);
-    if (mode == B200_NORM_SPADE)
-        norm_bwd_reduce_kernel<B200_NORM_SPADE><<<grid, block, 0, st>>>(dy, x, y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg);
-    else
-        norm_bwd_reduce_kernel<B200_NORM_PLAIN><<<grid, block, 0, st>>>(dy, x, y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg);
+    B200_DISPATCH_DT(dt, T, {
+        if (mode == B200_NORM_SPADE)
+            norm_bwd_reduce_kernel<T, B200_NORM_SPADE><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg);
+        else
+            norm_bwd_reduce_kernel<T, B200_NORM_PLAIN><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -364,34 +379,46 @@ extern "C" int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, i
     return 0;
 }
 
-extern "C" int b200_norm_bwd_apply(const float* dy, const float* x, const float* y, float* dx, int64_t rows, int C,
-                                   int groups, const float* mean, const float* var, float eps, int mode,
-                                   const float* gamma, const int32_t* idx, int rows_per_seg, int relu, const float* s,
-                                   float* dgb, b200_stream_t stream) {
-    if (rows == 0) return 0;
-    B200_REQUIRE(C % 4 == 0, "norm_bwd_apply: C=%d must be a multiple of 4", C);
-    B200_REQUIRE(groups >= 1 && rows % groups == 0, "norm_bwd_apply: rows %% groups != 0");
-    const int64_t rpg = rows / groups;
-    int g = grid_for(rows * (C / 4), 256);
-    cudaStream_t st = as_stream(stream);
-    if (rows_per_seg < 1) rows_per_seg = 1;
+template <typename T>
+static int norm_bwd_apply_launch(const void* dy, const void* x, const void* y, void* dx, int64_t rows, int C, int64_t rpg,
+                                 const float* mean, const float* var, float eps, int mode, const void* gamma,
+                                 const int32_t* idx, int rows_per_seg, int relu, const float* s, void* dgb,
+                                 cudaStream_t st) {
+    const int g = grid_for(rows * (C / 4), 256);
+    const T *dyp = (const T*)dy, *xp = (const T*)x, *yp = (const T*)y;
+    T *dxp = (T*)dx, *dgbp = (T*)dgb;
     switch (mode) {
         case B200_NORM_PLAIN:
-            norm_bwd_apply_kernel<B200_NORM_PLAIN><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb, rpg);
+            norm_bwd_apply_kernel<T, B200_NORM_PLAIN><<<g, 256, 0, st>>>(dyp, xp, yp, dxp, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgbp, rpg);
             break;
         case B200_NORM_AFFINE:
-            norm_bwd_apply_kernel<B200_NORM_AFFINE><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb, rpg);
+            norm_bwd_apply_kernel<T, B200_NORM_AFFINE><<<g, 256, 0, st>>>(dyp, xp, yp, dxp, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgbp, rpg);
             break;
         case B200_NORM_CBN:
-            norm_bwd_apply_kernel<B200_NORM_CBN><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb, rpg);
+            norm_bwd_apply_kernel<T, B200_NORM_CBN><<<g, 256, 0, st>>>(dyp, xp, yp, dxp, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgbp, rpg);
             break;
         case B200_NORM_SPADE:
-            B200_REQUIRE(dgb != nullptr, "norm_bwd_apply: SPADE needs dgb");
-            norm_bwd_apply_kernel<B200_NORM_SPADE><<<g, 256, 0, st>>>(dy, x, y, dx, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgb, rpg);
+            if (dgb == nullptr) return set_error("norm_bwd_apply: SPADE needs dgb");
+            norm_bwd_apply_kernel<T, B200_NORM_SPADE><<<g, 256, 0, st>>>(dyp, xp, yp, dxp, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgbp, rpg);
             break;
         default:
             return set_error("norm_bwd_apply: bad mode %d", mode);
     }
+    return 0;
+}
+
+extern "C" int b200_norm_bwd_apply(const void* dy, const void* x, const void* y, void* dx, int dt, int64_t rows, int C,
+                                   int groups, const float* mean, const float* var, float eps, int mode,
+                                   const void* gamma, const int32_t* idx, int rows_per_seg, int relu, const float* s,
+                                   void* dgb, b200_stream_t stream) {
+    if (rows == 0) return 0;
+    B200_REQUIRE(C % 4 == 0, "norm_bwd_apply: C=%d must be a multiple of 4", C);
+    B200_REQUIRE(groups >= 1 && rows % groups == 0, "norm_bwd_apply: rows %% groups != 0");
+    const int64_t rpg = rows / groups;
+    if (rows_per_seg < 1) rows_per_seg = 1;
+    int rc;
+    B200_DISPATCH_DT(dt, T, { rc = norm_bwd_apply_launch<T>(dy, x, y, dx, rows, C, rpg, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, s, dgb, as_stream(stream)); });
+    if (rc) return rc;
     B200_CHECK_LAUNCH();
     return 0;
 }

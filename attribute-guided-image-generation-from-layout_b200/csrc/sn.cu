@@ -122,6 +122,77 @@ __global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* _
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// whole-network power iteration: every spectral-normalised layer of a discriminator in one launch sequence
+// (blockIdx.z / blockIdx.y = layer; blocks beyond a layer's extent exit).  Same arithmetic and reduction order
+// per layer as the single-layer kernels above.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void snm_wtu_kernel(const b200_sn_layer* __restrict__ layers) {
+    const b200_sn_layer l = layers[blockIdx.z];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= l.w) return;
+    const int nch = l.h < 64 ? 1 : kSnRowChunks;
+    if ((int)blockIdx.y >= nch) return;
+    const int rpc = (l.h + nch - 1) / nch;
+    const int i0 = blockIdx.y * rpc;
+    const int i1 = i0 + rpc < l.h ? i0 + rpc : l.h;
+    float acc = 0.f;
+    for (int i = i0; i < i1; ++i) acc += l.W[(int64_t)i * l.w + j] * l.u[i];
+    l.ws[(int64_t)blockIdx.y * l.w + j] = acc;
+}
+
+__global__ void snm_norm_v_kernel(const b200_sn_layer* __restrict__ layers, float eps, int it) {
+    __shared__ float red[33];
+    const b200_sn_layer l = layers[blockIdx.x];
+    const int nch = l.h < 64 ? 1 : kSnRowChunks;
+    float ss = 0.f;
+    for (int j = threadIdx.x; j < l.w; j += 1024) {
+        float t = 0.f;
+        for (int k = 0; k < nch; ++k) t += l.ws[(int64_t)k * l.w + j];
+        l.v[j] = t;
+        ss += t * t;
+    }
+    float tot = block_sum_1024(ss, red);
+    float inv = 1.f / fmaxf(sqrtf(tot), eps);
+    for (int j = threadIdx.x; j < l.w; j += 1024) l.v[j] *= inv;
+    (void)it;
+}
+
+__global__ void snm_wv_kernel(const b200_sn_layer* __restrict__ layers) {
+    const b200_sn_layer l = layers[blockIdx.y];
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= l.h) return;
+    const float* Wr = l.W + (int64_t)row * l.w;
+    float acc = 0.f;
+    for (int j = lane; j < l.w; j += 32) acc += Wr[j] * l.v[j];
+    acc = warp_sum(acc);
+    if (lane == 0) l.ws[(int64_t)kSnRowChunks * l.w + row] = acc;
+}
+
+// u update, sigma, and the per-iteration record: inv[it], u_hist[it], v_hist[it]
+__global__ void snm_norm_u_kernel(const b200_sn_layer* __restrict__ layers, float eps, int do_iter, int it) {
+    __shared__ float red[33];
+    const b200_sn_layer l = layers[blockIdx.x];
+    const float* wv = l.ws + (int64_t)kSnRowChunks * l.w;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < l.h; i += 1024) ss += wv[i] * wv[i];
+    float tot = block_sum_1024(ss, red);
+    float inv = 1.f / fmaxf(sqrtf(tot), eps);
+    float dot = 0.f;
+    for (int i = threadIdx.x; i < l.h; i += 1024) {
+        float un = do_iter ? wv[i] * inv : l.u[i];
+        if (do_iter) l.u[i] = un;
+        if (l.u_hist) l.u_hist[(int64_t)it * l.h + i] = un;
+        dot += un * wv[i];
+    }
+    if (l.v_hist)
+        for (int j = threadIdx.x; j < l.w; j += 1024) l.v_hist[(int64_t)it * l.w + j] = l.v[j];
+    float sigma = block_sum_1024(dot, red);
+    if (threadIdx.x == 0) l.inv[it] = 1.f / sigma;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -159,5 +230,25 @@ extern "C" int b200_sn_grad(const float* g, const float* W, const float* u, cons
     B200_CHECK_LAUNCH();
     sn_grad_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(g, u, v, inv_sigma, ws, dW, h, w, accumulate);
     B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_sn_power_iter_multi(const b200_sn_layer* layers, int n_layers, int max_h, int max_w, int iters,
+                                        int do_iter, float eps, b200_stream_t stream) {
+    if (n_layers <= 0 || iters <= 0) return 0;
+    B200_REQUIRE(n_layers < 65536 && max_h > 0 && max_w > 0, "sn_power_iter_multi: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    for (int it = 0; it < iters; ++it) {
+        if (do_iter) {
+            snm_wtu_kernel<<<dim3((max_w + 127) / 128, kSnRowChunks, n_layers), 128, 0, st>>>(layers);
+            B200_CHECK_LAUNCH();
+            snm_norm_v_kernel<<<n_layers, 1024, 0, st>>>(layers, eps, it);
+            B200_CHECK_LAUNCH();
+        }
+        snm_wv_kernel<<<dim3((max_h + 7) / 8, n_layers), 256, 0, st>>>(layers);
+        B200_CHECK_LAUNCH();
+        snm_norm_u_kernel<<<n_layers, 1024, 0, st>>>(layers, eps, do_iter, it);
+        B200_CHECK_LAUNCH();
+    }
     return 0;
 }

@@ -88,7 +88,7 @@ class AttributeDiscriminator128(nn.Module):
         self.classifier_att = bnn.Linear(conv_dim * 16, n_attribute)
 
     def forward(self, x, groups=1):
-        return self.classifier_att(_trunk(self, x, groups), groups=groups)
+        return self.classifier_att(_trunk(self, x, groups), groups=groups, out_dtype=torch.float32)
 
 
 class AttributeDiscriminator(nn.Module):
@@ -105,7 +105,7 @@ class AttributeDiscriminator(nn.Module):
         self.classifier_att = bnn.Linear(conv_dim * 16, n_attribute)
 
     def forward(self, x, groups=1):
-        return self.classifier_att(_trunk(self, x, groups), groups=groups)
+        return self.classifier_att(_trunk(self, x, groups), groups=groups, out_dtype=torch.float32)
 
 
 class ImageDiscriminator(nn.Module):
@@ -123,7 +123,7 @@ class ImageDiscriminator(nn.Module):
         self.classifier = bnn.Linear(self.ch * 16, 1, bias=False)
 
     def forward(self, x, groups=1):
-        return self.classifier(_trunk(self, x, groups), groups=groups).view(-1)
+        return self.classifier(_trunk(self, x, groups), groups=groups, out_dtype=torch.float32).view(-1)
 
 
 class ObjectDiscriminator(nn.Module):
@@ -142,4 +142,5 @@ class ObjectDiscriminator(nn.Module):
 
     def forward(self, x, y=None, groups=1):
         h = _trunk(self, x, groups)
-        return self.classifier_src(h, groups=groups).view(-1), self.classifier_cls(h, groups=groups)
+        return (self.classifier_src(h, groups=groups, out_dtype=torch.float32).view(-1),
+                self.classifier_cls(h, groups=groups, out_dtype=torch.float32))

@@ -129,8 +129,8 @@ class CropEncoder(nn.Module):
         x = self.bn5(self.conv5(x), objs, relu=True, groups=groups)
         O, H, W, C = x.shape
         x = ops.pool(x, H, 1.0 / (H * W)).view(O, C)
-        mu = self.fc_mu(x)
-        logvar = self.fc_logvar(x)
+        mu = self.fc_mu(x, out_dtype=torch.float32)              # the VAE head and everything after it stay fp32
+        logvar = self.fc_logvar(x, out_dtype=torch.float32)
         if self.eps_source is not None:
             eps = self.eps_source(O, mu.size(1), mu.device)
         elif groups == 1:

@@ -25,6 +25,12 @@ extern "C" {
 
 typedef void* b200_stream_t; /* cudaStream_t */
 
+/* Storage type of a channel-last ACTIVATION tensor (and of its gradient): fp32, or bf16 in the bf16 training mode.
+ * Wherever an entry point takes `void*` activations it also takes their type code `dt`; arithmetic, statistics,
+ * reductions, parameters and parameter gradients are always fp32 (or wider).  NCHW boundary tensors (images, crops)
+ * are always fp32. */
+enum { B200_F32 = 0, B200_BF16 = 1 };
+
 const char* b200_last_error(void);
 int b200_version(void);
 /* number of kernel launches issued through this library by the calling process (for bench.py's gpu_launches) */
@@ -80,9 +86,10 @@ typedef struct {
     int scale_rows;                /* 0: one scalar *scale; > 0: scale[m / scale_rows] (per-group 1/sigma of batched calls) */
 } b200_conv_desc;
 
-/* fp32 CUDA-core path (bit-tight parity mode). wmat fp32 [Cout][ldw]. */
-int b200_conv_gemm_f32(const b200_conv_desc* d, const float* in, const float* wmat, const float* bias,
-                       const float* scale, float* out, b200_stream_t stream);
+/* fp32 CUDA-core path (bit-tight parity mode; also the 3-channel layers and Linear heads). wmat fp32 [Cout][ldw];
+ * in / out stored as in_dt / out_dt, strides in elements of that type. */
+int b200_conv_gemm_f32(const b200_conv_desc* d, const void* in, int in_dt, const float* wmat, const float* bias,
+                       const float* scale, void* out, int out_dt, b200_stream_t stream);
 /* tcgen05 path: bf16 operands, fp32 accumulate in TMEM.  `in_bf16` is the channel-last activation stored as bf16
  * (b200_cast_bf16 produces it from an fp32 tensor); the descriptor's input strides are in bf16 elements and must be
  * multiples of 8 (16-byte rows).  wmat bf16 [Cout_pad][ldw] with Cout_pad a multiple of the N tile
@@ -107,7 +114,7 @@ int b200_cast_bf16(const float* x, void* y_bf16, int64_t n, b200_stream_t stream
  * where `d` describes the gather of G exactly as above (d->Cin = Cg) and P is addressed with d's out_* fields
  * (d->Cout = number of P channels m).  Split over the row range into `splits` partial results written to
  * ws ([splits][Cout][Th*Tw*Cin] fp32); b200_wgrad_reduce sums them in fixed order into the parameter layout. */
-int b200_wgrad_gemm_f32(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+int b200_wgrad_gemm_f32(const b200_conv_desc* d, const void* P, int p_dt, const void* G, int g_dt, float* ws, int splits,
                         b200_stream_t stream);
 /* tcgen05 variant: P and G are bf16 channel-last tensors (strides in bf16 elements, multiples of 8) */
 int b200_wgrad_gemm_tc(const b200_conv_desc* d, const void* P_bf16, const void* G_bf16, float* ws, int splits,
@@ -128,7 +135,8 @@ int b200_pack_weight(const float* src, void* dst, int dst_bf16, int M, int Mpad,
 /* ------------------------------------------------------------------------------------------------
  * Normalisation family — replaces nn.BatchNorm1d/2d, ConditionalBatchNorm2d (generator_obj_att.py:31-44),
  * SPADE's param-free BN + modulation (normalization.py:94-108), fused with ReLU / residual add.
- * x, y: (rows, C) channel-last fp32.
+ * x, y, residual, dy, dx (rows, C) and SPADE's gamma|beta activation gb / its gradient dgb (rows, 2C) are channel-last
+ * activations of storage type dt; statistics, parameter tables and parameter gradients are fp32.
  */
 /* `groups`: several independent calls of the same layer batched along the row dimension (rows = groups *
  * rows_per_group, group g = rows [g*rows_per_group, (g+1)*rows_per_group)) keep SEPARATE batch statistics — this is how
@@ -138,20 +146,20 @@ int b200_pack_weight(const float* src, void* dst, int dst_bf16, int M, int Mpad,
  * batch statistics (biased var) + running-stat update (momentum, unbiased var) — F.batch_norm training semantics.
  * ws: 2*C*groups*b200_bn_chunks(rows/groups, C) doubles. running_* may be NULL. */
 int b200_bn_chunks(int64_t rows, int C);
-int b200_bn_stats(const float* x, int64_t rows, int C, int groups, float* mean, float* var, float* running_mean,
+int b200_bn_stats(const void* x, int dt, int64_t rows, int C, int groups, float* mean, float* var, float* running_mean,
                   float* running_var, float momentum, double* ws, b200_stream_t stream);
 enum { B200_NORM_PLAIN = 0, B200_NORM_AFFINE = 1, B200_NORM_CBN = 2, B200_NORM_SPADE = 3 };
 /* y = relu?( residual? + (x-mean)*rsqrt(var+eps) * g + b ):
  *   PLAIN g=1,b=0 | AFFINE g=gamma[c], b=beta[c] | CBN g=table[idx[row/rows_per_seg]][c], b=table[..][C+c]
  *   | SPADE g=1+gb[row][c], b=gb[row][C+c]  (gb = the fused gamma|beta conv output, (rows,2C)) */
-int b200_norm_fwd(const float* x, float* y, int64_t rows, int C, int groups, const float* mean, const float* var,
-                  float eps, int mode, const float* gamma, const float* beta, const int32_t* idx, int rows_per_seg,
-                  const float* residual, int relu, b200_stream_t stream);
+int b200_norm_fwd(const void* x, void* y, int dt, int64_t rows, int C, int groups, const float* mean, const float* var,
+                  float eps, int mode, const void* gamma, const float* beta, const int32_t* idx, int rows_per_seg,
+                  const void* residual, int relu, b200_stream_t stream);
 /* backward, stage 1: per-segment sums of (dyr*g, dyr*g*xhat) [and for CBN the raw (dyr, dyr*xhat)] where dyr = dy masked by
  * y>0 when relu; segments never straddle a group: seg_sums is (groups * ceil(rows_per_group / rows_per_seg), C, 2)
  * doubles.  For CBN pass rows_per_seg = H*W. */
-int b200_norm_bwd_reduce(const float* dy, const float* x, const float* y, int64_t rows, int C, int groups,
-                         const float* mean, const float* var, float eps, int mode, const float* gamma,
+int b200_norm_bwd_reduce(const void* dy, const void* x, const void* y, int dt, int64_t rows, int C, int groups,
+                         const float* mean, const float* var, float eps, int mode, const void* gamma,
                          const int32_t* idx, int rows_per_seg, int relu, double* seg_sums, b200_stream_t stream);
 /* stage 2: combine segments in fixed order -> s (groups, C, 2) floats = (sum dxhat, sum dxhat*xhat); parameter gradients
  * (summed over groups): AFFINE: dgamma[c], dbeta[c]; CBN: dtable (num_classes, 2C) deterministic segmented sum by class
@@ -161,9 +169,9 @@ int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, int groups, 
                            b200_stream_t stream);
 /* stage 3: dx = rstd*(dxhat - s1/rows_per_group - xhat*s2/rows_per_group); SPADE additionally writes dgb (rows,2C) =
  * (dyr*xhat | dyr). */
-int b200_norm_bwd_apply(const float* dy, const float* x, const float* y, float* dx, int64_t rows, int C, int groups,
-                        const float* mean, const float* var, float eps, int mode, const float* gamma,
-                        const int32_t* idx, int rows_per_seg, int relu, const float* s, float* dgb,
+int b200_norm_bwd_apply(const void* dy, const void* x, const void* y, void* dx, int dt, int64_t rows, int C, int groups,
+                        const float* mean, const float* var, float eps, int mode, const void* gamma,
+                        const int32_t* idx, int rows_per_seg, int relu, const float* s, void* dgb,
                         b200_stream_t stream);
 /* eval-mode normalisation uses b200_norm_fwd with mean/var = running stats. */
 
@@ -174,44 +182,47 @@ int b200_norm_bwd_apply(const float* dy, const float* x, const float* y, float* 
  * (generator_obj_att.py:102-112), the VAE reparameterisation (generator_obj_att.py:417-420) and the
  * embedding (x) mask broadcast of LayoutEncoder (generator_obj_att.py:489-490).
  */
-int b200_relu_fwd(const float* x, float* y, int64_t n, b200_stream_t stream);
-int b200_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, b200_stream_t stream);
-int b200_add(const float* a, const float* b, float* out, int64_t n, b200_stream_t stream);
+int b200_relu_fwd(const void* x, void* y, int64_t n, int dt, b200_stream_t stream);
+int b200_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, int dt, b200_stream_t stream);
+int b200_add(const void* a, const void* b, void* out, int64_t n, int dt, b200_stream_t stream);
 /* y[n, qy, qx, c] = scale * sum_{f x f block} x[n, qy*f+dy, qx*f+dx, c]  (x: (N,H,W,C), H%f==0) */
-int b200_pool_fwd(const float* x, float* y, int N, int H, int W, int C, int f, float scale, b200_stream_t stream);
+int b200_pool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt, b200_stream_t stream);
 /* y[n, iy, ix, c] = scale * x[n, iy/f, ix/f, c]  (x: (N,H,W,C) -> y: (N,H*f,W*f,C)) */
-int b200_unpool_fwd(const float* x, float* y, int N, int H, int W, int C, int f, float scale, b200_stream_t stream);
+int b200_unpool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt, b200_stream_t stream);
 /* out[row] = [ a[row / a_div][0:Ca] | b[row / b_div][0:Cb] ] and its adjoint (sums over the broadcast rows, fixed order) */
-int b200_concat_fwd(const float* a, int Ca, int a_div, const float* b, int Cb, int b_div, float* out, int64_t rows,
-                    b200_stream_t stream);
-int b200_concat_bwd(const float* dout, int Ca, int a_div, float* da, int Cb, int b_div, float* db, int64_t rows,
-                    b200_stream_t stream);
+int b200_concat_fwd(const void* a, int Ca, int a_div, const void* b, int Cb, int b_div, void* out, int64_t rows,
+                    int dt, b200_stream_t stream);
+int b200_concat_bwd(const void* dout, int Ca, int a_div, void* da, int Cb, int b_div, void* db, int64_t rows,
+                    int dt, b200_stream_t stream);
 int b200_gather_rows(const float* table, const int32_t* idx, float* out, int rows, int D, b200_stream_t stream);
 /* dtable[k] = sum over rows with idx==k, ascending row order (deterministic); dtable (num_classes, D) overwritten */
 int b200_scatter_rows(const float* dout, const int32_t* idx, float* dtable, int rows, int D, int num_classes,
                       b200_stream_t stream);
-/* out[o, y+1, x+1, c] = mask[o,y,x] * v[o,c], zero ring (1x1 conv with padding 1 of a rank-1 tensor) */
-int b200_mask_outer_fwd(const float* v, const float* mask, float* out, int O, int H, int W, int C,
+/* out[o, y+1, x+1, c] = mask[o,y,x] * v[o,c], zero ring (1x1 conv with padding 1 of a rank-1 tensor); v, mask, dv fp32,
+ * out / dout activations of type dt */
+int b200_mask_outer_fwd(const float* v, const float* mask, void* out, int O, int H, int W, int C, int dt,
                         b200_stream_t stream);
-int b200_mask_outer_bwd(const float* dout, const float* mask, float* dv, int O, int H, int W, int C,
+int b200_mask_outer_bwd(const void* dout, const float* mask, float* dv, int O, int H, int W, int C, int dt,
                         b200_stream_t stream);
 /* ConvLSTM cell pointwise part; pre = pre_x + pre_h, channels ordered [i|f|o|g] each `hid` wide; rows = n*H*W.
  * gates (rows,4*hid) receives the activated gates for the backward. pre_h / c_prev may be NULL (t = 0). */
-int b200_lstm_gates_fwd(const float* pre_x, const float* pre_h, const float* c_prev, float* gates, float* c_out,
-                        float* h_out, int64_t rows, int hid, b200_stream_t stream);
+/* pre_x, pre_h, h_out, dh, dpre are activations of type dt; the cell state c and the saved gates stay fp32 */
+int b200_lstm_gates_fwd(const void* pre_x, const void* pre_h, const float* c_prev, float* gates, float* c_out,
+                        void* h_out, int64_t rows, int hid, int dt, b200_stream_t stream);
 /* dpre (rows,4*hid), dc_prev (rows,hid) from dh, dc_next (NULL = 0), saved gates, c_prev (NULL = 0), c_out */
-int b200_lstm_gates_bwd(const float* dh, const float* dc_next, const float* gates, const float* c_prev,
-                        const float* c_out, float* dpre, float* dc_prev, int64_t rows, int hid,
+int b200_lstm_gates_bwd(const void* dh, const float* dc_next, const float* gates, const float* c_prev,
+                        const float* c_out, void* dpre, float* dc_prev, int64_t rows, int hid, int dt,
                         b200_stream_t stream);
 int b200_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, int64_t n, b200_stream_t stream);
 int b200_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu_add, float* dlogvar_add,
                      int64_t n, b200_stream_t stream);
 /* out[c] = sum_rows x[row][c] (bias gradients), deterministic; ws: C*b200_bn_chunks(rows,C) doubles */
-int b200_colsum(const float* x, int64_t rows, int C, float* out, double* ws, b200_stream_t stream);
+int b200_colsum(const void* x, int64_t rows, int C, int dt, float* out, double* ws, b200_stream_t stream);
 /* y[b][c][r] = x[b][r][c]: batched (R x C) transpose, i.e. NCHW <-> channel-last at module boundaries */
 int b200_transpose(const float* x, float* y, int B, int R, int C, b200_stream_t stream);
-/* row gather / scatter-overwrite for the time-major packing of ConvLSTM sequences: out[r] = x[src_row[r]] (rowlen floats) */
-int b200_permute_rows(const float* x, const int32_t* src_row, float* out, int rows, int rowlen, b200_stream_t stream);
+/* row gather / scatter-overwrite for the time-major packing of ConvLSTM sequences: out[r] = x[src_row[r]] (rows of
+ * row_bytes bytes, a multiple of 16; src_row < 0 writes zeros) */
+int b200_permute_rows(const void* x, const int32_t* src_row, void* out, int rows, int64_t row_bytes, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Spectral normalisation — replaces torch.nn.utils.spectral_norm's pre-forward hook installed by add_sn
@@ -224,6 +235,23 @@ int b200_sn_power_iter(const float* W, int h, int w, float* u, float* v, int do_
                        float* inv_sigma_out, float* ws, b200_stream_t stream);
 int b200_sn_grad(const float* g, const float* W, const float* u, const float* v, const float* inv_sigma, float* dW, int h,
                  int w, int accumulate, double* ws, b200_stream_t stream);
+
+/* The same power iteration for EVERY spectral-normalised layer of a network at once (4 launches per iteration instead
+ * of 4 per layer), `iters` times in sequence — one per batched call of the network.  `layers` is a DEVICE array of
+ * n_layers descriptors; iteration `it` of layer l records inv[it] = 1/sigma, u_hist[it*h ..], v_hist[it*w ..] (the
+ * vectors that sigma was computed with; either history pointer may be NULL).  ws: 8*w + h floats per layer. */
+typedef struct {
+    const float* W;     /* (h, w) row-major view of weight_orig */
+    float* u;           /* (h,)  updated in place */
+    float* v;           /* (w,)  updated in place */
+    float* ws;          /* 8*w + h floats of scratch */
+    float* inv;         /* (iters,) */
+    float* u_hist;      /* (iters, h) or NULL */
+    float* v_hist;      /* (iters, w) or NULL */
+    int h, w;
+} b200_sn_layer;
+int b200_sn_power_iter_multi(const b200_sn_layer* layers, int n_layers, int max_h, int max_w, int iters, int do_iter,
+                             float eps, b200_stream_t stream);
 
 /* plain device-to-device copy on the stream (row concatenation of batched calls) */
 int b200_copy(void* dst, const void* src, size_t bytes, b200_stream_t stream);

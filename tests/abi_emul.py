@@ -131,8 +131,8 @@ class EmulKernels:
 
     def conv_gemm(self, d, inp, wmat, bias, scale, out, tc):
         self.launches += 1
-        assert (inp.dtype == torch.bfloat16) == bool(tc), "tcgen05 path takes bf16 operands, the fp32 path fp32"
-        A = self._gather(d, inp.float() if tc else inp)
+        assert inp.dtype == torch.bfloat16 or not tc, "the tcgen05 path takes bf16 operands"
+        A = self._gather(d, inp).float()
         K = d.Th * d.Tw * d.Cin
         Wm = wmat.float()[:d.Cout, :K]
         A2 = A.reshape(A.shape[0], K)
@@ -150,21 +150,21 @@ class EmulKernels:
         if d.relu:
             y = F.relu(y)
         off, ok = self._out_index(d)
-        flat = torch.as_strided(out, (out.untyped_storage().nbytes() // 4 - out.storage_offset(),), (1,), out.storage_offset())
+        flat = torch.as_strided(out, (out.untyped_storage().nbytes() // out.element_size() - out.storage_offset(),), (1,),
+                                out.storage_offset())
         co = torch.arange(d.Cout) * d.out_sc
         idx = (off[ok][:, None] + co[None]).reshape(-1)
-        flat[idx] = y[ok].reshape(-1)
+        flat[idx] = y[ok].reshape(-1).to(out.dtype)
 
     def wgrad_gemm(self, d, P, G, ws, splits, tc):
         self.launches += 1
-        assert (P.dtype == torch.bfloat16) == bool(tc) and (G.dtype == torch.bfloat16) == bool(tc)
-        if tc:
-            P, G = P.float(), G.float()
-        A = self._gather(d, G)                                   # (Q, T, Cin)
+        assert (P.dtype == torch.bfloat16 and G.dtype == torch.bfloat16) or not tc
+        A = self._gather(d, G).float()                           # (Q, T, Cin)
         off, ok = self._out_index(d)
-        flatP = torch.as_strided(P, (P.untyped_storage().nbytes() // 4 - P.storage_offset(),), (1,), P.storage_offset())
+        flatP = torch.as_strided(P, (P.untyped_storage().nbytes() // P.element_size() - P.storage_offset(),), (1,),
+                                 P.storage_offset())
         co = torch.arange(d.Cout) * d.out_sc
-        Pm = flatP[(off.clamp(min=0)[:, None] + co[None])] * ok[:, None].to(P.dtype)
+        Pm = flatP[(off.clamp(min=0)[:, None] + co[None])].float() * ok[:, None].float()
         if tc:
             A = A.to(torch.bfloat16).float()
             Pm = Pm.to(torch.bfloat16).float()
@@ -200,6 +200,7 @@ class EmulKernels:
     # ---- normalisation --------------------------------------------------------------------------------------
     def bn_stats(self, x2d, running_mean, running_var, momentum, groups=1):
         self.launches += 2
+        x2d = x2d.float()
         rows, C = x2d.shape
         rpg = rows // groups
         xd = x2d.double().view(groups, rpg, C)
@@ -225,6 +226,11 @@ class EmulKernels:
 
     def norm_fwd(self, x2d, mean, var, eps, mode, gamma, beta, idx, rows_per_seg, residual, relu, groups=1):
         self.launches += 1
+        dt = x2d.dtype
+        assert residual is None or residual.dtype == dt
+        assert mode != MODE_SPADE or gamma.dtype == dt
+        x2d, gamma = x2d.float(), (gamma.float() if gamma is not None else None)
+        residual = residual.float() if residual is not None else None
         rows, C = x2d.shape
         rpg = rows // groups
         mean_r = mean.view(groups, C).repeat_interleave(rpg, dim=0)
@@ -234,10 +240,14 @@ class EmulKernels:
         y = xh if g is None else xh * g + b
         if residual is not None:
             y = y + residual
-        return F.relu(y) if relu else y
+        return (F.relu(y) if relu else y).to(dt)
 
     def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes, groups=1):
         self.launches += 4
+        dt = x2d.dtype
+        assert dy.dtype == dt and (y is None or y.dtype == dt) and (mode != MODE_SPADE or gamma.dtype == dt)
+        dy, x2d, y = dy.float(), x2d.float(), (y.float() if y is not None else None)
+        gamma = gamma.float() if gamma is not None else None
         rows, C = x2d.shape
         rpg = rows // groups
         mean_r = mean.view(groups, C).repeat_interleave(rpg, dim=0)
@@ -260,8 +270,8 @@ class EmulKernels:
             dtable = torch.zeros(num_classes, 2 * C)
             dtable.index_add_(0, idx.long(), torch.cat([a, b], dim=1))
         elif mode == MODE_SPADE:
-            dgb = torch.cat([g * xh, g], dim=1)
-        return dx, dgamma, dbeta, dtable, dgb
+            dgb = torch.cat([g * xh, g], dim=1).to(dt)
+        return dx.to(dt), dgamma, dbeta, dtable, dgb
 
     # ---- elementwise ----------------------------------------------------------------------------------------
     def relu_fwd(self, x):
@@ -270,35 +280,39 @@ class EmulKernels:
 
     def relu_bwd(self, dy, y):
         self.launches += 1
+        assert dy.dtype == y.dtype
         return dy * (y > 0).to(dy.dtype)
 
     def add(self, a, b, out=None):
         self.launches += 1
+        assert a.dtype == b.dtype
+        r = (a.float() + b.float()).to(a.dtype)
         if out is None:
-            return a + b
-        out.copy_(a + b)
+            return r
+        out.copy_(r)
         return out
 
     def pool_fwd(self, x, N, H, W, C, f, scale):
         self.launches += 1
-        return x.reshape(N, H // f, f, W // f, f, C).sum(dim=(2, 4)) * scale
+        return (x.float().reshape(N, H // f, f, W // f, f, C).sum(dim=(2, 4)) * scale).to(x.dtype)
 
     def unpool_fwd(self, x, N, H, W, C, f, scale):
         self.launches += 1
-        v = x.reshape(N, H, 1, W, 1, C).expand(N, H, f, W, f, C)
-        return (v * scale).reshape(N, H * f, W * f, C).contiguous()
+        v = x.float().reshape(N, H, 1, W, 1, C).expand(N, H, f, W, f, C)
+        return (v * scale).reshape(N, H * f, W * f, C).contiguous().to(x.dtype)
 
     def concat_fwd(self, a, Ca, a_div, b, Cb, b_div, rows):
         self.launches += 1
+        assert a.dtype == b.dtype
         aa = a.reshape(-1, Ca).repeat_interleave(a_div, dim=0)
         bb = b.reshape(-1, Cb).repeat_interleave(b_div, dim=0)
         return torch.cat([aa, bb], dim=1)
 
     def concat_bwd(self, dout, Ca, a_div, Cb, b_div, rows, need_a=True, need_b=True):
         self.launches += 1
-        d = dout.reshape(rows, Ca + Cb)
-        da = d[:, :Ca].reshape(rows // a_div, a_div, Ca).sum(1) if need_a else None
-        db = d[:, Ca:].reshape(rows // b_div, b_div, Cb).sum(1) if need_b else None
+        d = dout.float().reshape(rows, Ca + Cb)
+        da = d[:, :Ca].reshape(rows // a_div, a_div, Ca).sum(1).to(dout.dtype) if need_a else None
+        db = d[:, Ca:].reshape(rows // b_div, b_div, Cb).sum(1).to(dout.dtype) if need_b else None
         return da, db
 
     def gather_rows(self, table, idx):
@@ -318,21 +332,23 @@ class EmulKernels:
         out = xv[src.clamp(min=0)] * (src >= 0).to(x.dtype)[:, None]
         return out
 
-    def mask_outer_fwd(self, v, mask, O, H, W, C):
+    def mask_outer_fwd(self, v, mask, O, H, W, C, out_dtype=torch.float32):
         self.launches += 1
         out = torch.zeros(O, H + 2, W + 2, C)
         out[:, 1:H + 1, 1:W + 1] = mask.reshape(O, H, W, 1) * v.reshape(O, 1, 1, C)
-        return out
+        return out.to(out_dtype)
 
     def mask_outer_bwd(self, dout, mask, O, H, W, C):
         self.launches += 1
-        return (dout[:, 1:H + 1, 1:W + 1] * mask.reshape(O, H, W, 1)).sum(dim=(1, 2))
+        return (dout.float()[:, 1:H + 1, 1:W + 1] * mask.reshape(O, H, W, 1)).sum(dim=(1, 2))
 
     def lstm_gates_fwd(self, pre_x, pre_h, c_prev, rows, hid, gates=None, c_out=None, h_out=None):
         self.launches += 1
-        pre = pre_x.reshape(rows, 4 * hid)
+        dt = pre_x.dtype
+        assert (pre_h is None or pre_h.dtype == dt) and (h_out is None or h_out.dtype == dt)
+        pre = pre_x.float().reshape(rows, 4 * hid)
         if pre_h is not None:
-            pre = pre + pre_h.reshape(rows, 4 * hid)
+            pre = pre + pre_h.float().reshape(rows, 4 * hid)
         i, f, o, g = torch.split(pre, hid, dim=1)
         i, f, o, g = torch.sigmoid(i), torch.sigmoid(f), torch.sigmoid(o), torch.tanh(g)
         cp = c_prev.reshape(rows, hid) if c_prev is not None else 0
@@ -340,7 +356,7 @@ class EmulKernels:
         hn = o * torch.tanh(cn)
         gt = torch.cat([i, f, o, g], dim=1)
         if gates is None:
-            return gt, cn, hn
+            return gt, cn, hn.to(dt)
         gates.copy_(gt.view(gates.shape))
         c_out.copy_(cn.view(c_out.shape))
         h_out.copy_(hn.view(h_out.shape))
@@ -350,7 +366,8 @@ class EmulKernels:
         self.launches += 1
         i, f, o, g = torch.split(gates.reshape(rows, 4 * hid), hid, dim=1)
         tc = torch.tanh(c_out.reshape(rows, hid))
-        dhv = dh.reshape(rows, hid)
+        assert dpre is None or dpre.dtype == dh.dtype
+        dhv = dh.float().reshape(rows, hid)
         dc = dhv * o * (1 - tc * tc)
         if dc_next is not None:
             dc = dc + dc_next.reshape(rows, hid)
@@ -358,7 +375,7 @@ class EmulKernels:
         dp = torch.cat([dc * g * i * (1 - i), dc * cp * f * (1 - f), dhv * tc * o * (1 - o), dc * i * (1 - g * g)], dim=1)
         dcp = dc * f
         if dpre is None:
-            return dp, dcp
+            return dp.to(dh.dtype), dcp
         dpre.copy_(dp.view(dpre.shape))
         dc_prev.copy_(dcp.view(dc_prev.shape))
         return dpre, dc_prev
@@ -409,6 +426,19 @@ class EmulKernels:
         else:
             dW.copy_(val)
         return dW
+
+    def sn_table(self, layers, stage, ws, iters):
+        return None
+
+    def sn_power_iter_multi(self, table, layers, stage, ws, iters, do_iter, eps):
+        self.launches += 4 * iters
+        for (W, u, v, h, w, so, wo) in layers:
+            for it in range(iters):
+                inv = stage[so + it:so + it + 1]
+                self.launches -= 4
+                self.sn_power_iter(W, h, w, u, v, do_iter, eps, inv_out=inv)
+                stage[so + iters + it * h:so + iters + (it + 1) * h] = u
+                stage[so + iters + iters * h + it * w:so + iters + iters * h + (it + 1) * w] = v
 
     def copy_into(self, dst, dst_row, src):
         self.launches += 1

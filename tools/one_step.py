@@ -13,7 +13,10 @@ ts.netG.crop_encoder.eps_source = lambda o, z, d: torch.randn(o, z, device=d)
 b = ts.to_device(O.synth_batch(batch, size, 8, 10))
 for i in range(steps):
     torch.cuda.synchronize(); t = time.time()
+    if i == steps - 1:
+        torch.cuda.profiler.start()          # ncu --profile-from-start off: only the last step is captured
     n0 = _lib.K.launch_count()
     r = ts.step(b, optimizer_step=True)
     torch.cuda.synchronize()
     print("step %d: %.1f ms wall, %d library launches, d_loss %.4f g_loss %.4f" % (i, (time.time() - t) * 1e3, _lib.K.launch_count() - n0, float(r["d_loss"]), float(r["g_loss"])), flush=True)
+torch.cuda.profiler.stop()
