@@ -161,6 +161,12 @@ class Kernels:
     def conv_tc_set_im2col(self, enable: bool) -> bool:
         return bool(self.lib.b200_conv_tc_set_im2col(int(bool(enable))))
 
+    def conv_tc_set_persistent(self, enable: bool) -> bool:
+        return bool(self.lib.b200_conv_tc_set_persistent(int(bool(enable))))
+
+    def conv_tc_set_halo(self, enable: bool) -> bool:
+        return bool(self.lib.b200_conv_tc_set_halo(int(bool(enable))))
+
     def conv_tc_ntile(self, cout: int) -> int:
         return int(self.lib.b200_conv_tc_ntile(int(cout)))
 

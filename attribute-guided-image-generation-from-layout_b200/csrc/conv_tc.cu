@@ -383,6 +383,497 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
     if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// persistent forward-type kernel (TMA im2col operands, no split-K): one CTA per SM walks the output tiles
+// t = blockIdx.x, blockIdx.x + gridDim.x, ... (N tile fastest, so concurrently running CTAs share the activation tile
+// in L2).  The operand ring runs ahead across tile boundaries and two TMEM accumulators alternate, so the epilogue of
+// tile j (warps 0-3: tcgen05.ld, scale / bias / ReLU, store) overlaps the loads and MMAs of tile j+1.
+//   warp 4 lane 0 : producer — per k-block one im2col TMA (A, 128 pixels x 64 channels) + one tiled TMA (B, BN x 64)
+//   warp 5 lane 0 : tcgen05.mma issuer; tcgen05.commit frees the stage / publishes the accumulator
+//   warps 0-3     : epilogue
+// ------------------------------------------------------------------------------------------------------------
+struct PersistTail {
+    uint64_t full[8];
+    uint64_t empty[8];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                      const __grid_constant__ CUtensorMap tmap_a,
+                                                                      b200_conv_desc d, const float* __restrict__ bias,
+                                                                      const float* __restrict__ scale,
+                                                                      void* __restrict__ out_v, int out_bf16,
+                                                                      int num_n_tiles, int num_tiles) {
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int ACC_COLS = BN < 16 ? 16 : BN;
+    constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+    constexpr int CW = BN >= 32 ? 32 : 16;      // accumulator columns per tcgen05.ld
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_BYTES;
+    PersistTail* tail = reinterpret_cast<PersistTail*>(smem_b + STAGES * B_BYTES);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int64_t M = (int64_t)d.B * d.Qh * d.Qw;
+    const int cpb = d.Cin / BK;
+    const int num_kb = d.Th * d.Tw * cpb;
+
+    if (warp == 4 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    }
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(smem_u32(&tail->full[s]), 1);
+                mbar_init(smem_u32(&tail->empty[s]), 1);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(smem_u32(&tail->tmem_full[b]), 1);
+                mbar_init(smem_u32(&tail->tmem_empty[b]), 4);      // one arrival per epilogue warp
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(&tail->tmem_base), TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+
+    if (warp < 4) {
+        // ===================== epilogue =====================
+        const int row = warp * 32 + lane;
+        float* out = reinterpret_cast<float*>(out_v);
+        __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(out_v);
+        const bool vec = d.out_sc == 1 && (d.Cout & 7) == 0 &&
+                         (out_bf16 ? (((d.out_sn | d.out_sh | d.out_sw) & 7) == 0 && (reinterpret_cast<uintptr_t>(out_v) & 15) == 0)
+                                   : (((d.out_sn | d.out_sh | d.out_sw) & 3) == 0 && (reinterpret_cast<uintptr_t>(out_v) & 15) == 0));
+        int j = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
+            const int buf = j & 1;
+            const int n0 = (t % num_n_tiles) * BN;
+            const int64_t m = (int64_t)(t / num_n_tiles) * BM + row;
+            int64_t ro = -1;
+            float alpha = 1.f;
+            if (m < M) {
+                const int qx = (int)(m % d.Qw);
+                const int qy = (int)((m / d.Qw) % d.Qh);
+                const int64_t n = m / ((int64_t)d.Qw * d.Qh);
+                const int oy = qy * d.out_sy + d.out_oy, ox = qx * d.out_sx + d.out_ox;
+                if (oy >= 0 && oy < d.Ho && ox >= 0 && ox < d.Wo)
+                    ro = n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
+                if (scale) alpha = scale[d.scale_rows > 0 ? m / d.scale_rows : 0];
+            }
+            mbar_wait(smem_u32(&tail->tmem_full[buf]), (uint32_t)(j >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * ACC_COLS);
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += CW) {
+                uint32_t r[CW];
+                if constexpr (CW == 32) tmem_ld32(tacc + (uint32_t)cb, r);
+                else tmem_ld16(tacc + (uint32_t)cb, r);
+                if (ro >= 0) {
+#pragma unroll
+                    for (int h = 0; h < CW; h += 16) {
+                        float o[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const int co = n0 + cb + h + e;
+                            const float val = __uint_as_float(r[h + e]) * alpha + ((bias && co < d.Cout) ? bias[co] : 0.f);
+                            o[e] = d.relu ? fmaxf(val, 0.f) : val;
+                        }
+                        const int c0 = n0 + cb + h;
+                        if (vec && c0 + 16 <= d.Cout) {
+                            if (out_bf16) {
+                                st_bf16x8(outh + ro + c0, o);
+                                st_bf16x8(outh + ro + c0 + 8, o + 8);
+                            } else {
+                                float4* p = reinterpret_cast<float4*>(out + ro + c0);
+                                p[0] = make_float4(o[0], o[1], o[2], o[3]);
+                                p[1] = make_float4(o[4], o[5], o[6], o[7]);
+                                p[2] = make_float4(o[8], o[9], o[10], o[11]);
+                                p[3] = make_float4(o[12], o[13], o[14], o[15]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                const int co = c0 + e;
+                                if (co < d.Cout) {
+                                    if (out_bf16) outh[ro + (int64_t)co * d.out_sc] = __float2bfloat16_rn(o[e]);
+                                    else out[ro + (int64_t)co * d.out_sc] = o[e];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // the accumulator has been read: hand the TMEM buffer back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tail->tmem_empty[buf]));
+        }
+    } else if (warp == 4) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int n0 = (t % num_n_tiles) * BN;
+                const int64_t m0 = (int64_t)(t / num_n_tiles) * BM;
+                const int qx = (int)(m0 % d.Qw);
+                const int qy = (int)((m0 / d.Qw) % d.Qh);
+                const int an = (int)(m0 / ((int64_t)d.Qw * d.Qh));
+                const int aw = qx * d.in_sx + (d.tap_sx > 0 ? d.tap_ox : d.tap_ox - (d.Tw - 1));
+                const int ah = qy * d.in_sy + (d.tap_sy > 0 ? d.tap_oy : d.tap_oy - (d.Th - 1));
+                int tap = 0, cc = 0;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = (int)(it % STAGES);
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
+                    const uint32_t bar = smem_u32(&tail->full[s]);
+                    mbar_arrive_expect_tx(bar, A_BYTES + B_BYTES);
+                    const int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
+                    const uint16_t ow = (uint16_t)(d.tap_sx > 0 ? txx : d.Tw - 1 - txx);
+                    const uint16_t oh = (uint16_t)(d.tap_sy > 0 ? tyy : d.Th - 1 - tyy);
+                    tma_load_im2col_4d(smem_u32(smem_a + s * A_BYTES), &tmap_a, cc * BK, aw, ah, an, ow, oh, bar);
+                    tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tmap, kb * BK, n0, bar);
+                    if (++cc == cpb) { cc = 0; ++tap; }
+                }
+            }
+        }
+    } else {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        uint32_t it = 0;
+        int j = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
+            const int buf = j & 1;
+            mbar_wait(smem_u32(&tail->tmem_empty[buf]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = (int)(it % STAGES);
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(smem_u32(&tail->full[s]), ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t adesc = make_desc(smem_u32(smem_a + s * A_BYTES), 16, 1024);
+                    const uint64_t bdesc = make_desc(smem_u32(smem_b + s * B_BYTES), 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(smem_u32(&tail->empty[s]));
+                    if (kb == num_kb - 1) umma_commit(smem_u32(&tail->tmem_full[buf]));
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// shifted-window kernel for stride-1 k x k convolutions (forward and their dgrad): the activation is read ONCE.
+//
+// Output pixels of one image are numbered along PADDED rows of width Wp = Qw + Tw - 1: v = qy * Wp + qxv (columns
+// qxv >= Qw are dummies, dropped by the epilogue).  For tap (ty, tx) the input pixel of output v is then
+// u = v + dy * Wp + dx — a constant row offset — in the zero-padded input plane P (rows of Wp pixels).  So a tile of 128
+// consecutive v needs, for ALL taps, one contiguous slab of P rows [r0, r0 + RB): a single tiled TMA box
+// {64 channels, Wp pixels, RB rows} with hardware zero fill outside the image, written to shared memory in the K-major
+// SWIZZLE_128B layout (one 128-byte row per pixel).  The A operand of tap (ty, tx) is that slab read from row
+// voff + dy*Wp + dx on: tcgen05.mma applies the swizzle to absolute shared-memory addresses, so a descriptor whose
+// start address is shifted by whole 128-byte rows addresses the shifted window directly (tools/probes/
+// umma_rowshift_probe.cu verifies this on the hardware).  Per tile the activation traffic drops from
+// taps x 16 KB to one slab (e.g. 144 KB -> 35 KB for a 3x3 layer at 32x32) — these layers are L2->SM bandwidth
+// bound, not tensor bound.  Persistent CTAs, weights streamed through a TMA ring, double-buffered slab and TMEM.
+// ------------------------------------------------------------------------------------------------------------
+struct HaloTail {
+    uint64_t a_full[4];
+    uint64_t a_empty[4];
+    uint64_t b_full[8];
+    uint64_t b_empty[8];
+    uint64_t b_res_full;
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tmap, int c, int w, int h, int n,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+        : "memory");
+}
+
+struct HaloGeom {
+    int Wp, RB;             // padded row width, slab rows
+    int lw, lh;             // input coordinates of P[0][0]
+    int slab_bytes;         // RB * Wp * 128 rounded up to 1024
+    int slab_tx;            // RB * Wp * 128
+    int na;                 // slab buffers (2..4)
+    int b_stages;           // weight ring stages (streaming mode)
+    int b_resident;         // 1: the CTA keeps its N tile's whole weight matrix in shared memory
+    int tiles_per_img;
+    int num_n_tiles, num_m_tiles;
+};
+
+// tile i of CTA b: streaming mode walks t = b + i*G with the N tile fastest; resident mode pins the CTA to N tile
+// b % NT and walks the M tiles b / NT + i * (G / NT)   (G % NT == 0)
+__device__ __forceinline__ bool halo_tile(const HaloGeom& hg, int i, int& mt, int& nt) {
+    if (hg.b_resident) {
+        nt = (int)blockIdx.x % hg.num_n_tiles;
+        mt = (int)blockIdx.x / hg.num_n_tiles + i * ((int)gridDim.x / hg.num_n_tiles);
+    } else {
+        const int64_t t = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+        nt = (int)(t % hg.num_n_tiles);
+        const int64_t m = t / hg.num_n_tiles;
+        mt = m > 0x7fffffff ? 0x7fffffff : (int)m;
+    }
+    return mt < hg.num_m_tiles;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                              const __grid_constant__ CUtensorMap tmap_in,
+                                                              b200_conv_desc d, HaloGeom hg,
+                                                              const float* __restrict__ bias,
+                                                              const float* __restrict__ scale,
+                                                              void* __restrict__ out_v, int out_bf16) {
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int ACC_COLS = BN < 16 ? 16 : BN;
+    constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+    constexpr int CW = BN >= 32 ? 32 : 16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int cpb = d.Cin / BK;
+    const int taps = d.Th * d.Tw;
+    const int num_kb = taps * cpb;
+    uint8_t* smem_a = smem;                                   // na slabs
+    uint8_t* smem_b = smem + hg.na * hg.slab_bytes;           // ring (b_stages) or resident (num_kb) x B_BYTES
+    HaloTail* tail = reinterpret_cast<HaloTail*>(smem_b + (hg.b_resident ? num_kb : hg.b_stages) * B_BYTES);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t SB = (uint32_t)hg.b_stages, NA = (uint32_t)hg.na;
+
+    if (warp == 4 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_in)) : "memory");
+    }
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int b = 0; b < 4; ++b) {
+                mbar_init(smem_u32(&tail->a_full[b]), 1);
+                mbar_init(smem_u32(&tail->a_empty[b]), 1);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(smem_u32(&tail->tmem_full[b]), 1);
+                mbar_init(smem_u32(&tail->tmem_empty[b]), 4);
+            }
+            for (int s = 0; s < 8; ++s) {
+                mbar_init(smem_u32(&tail->b_full[s]), 1);
+                mbar_init(smem_u32(&tail->b_empty[s]), 1);
+            }
+            mbar_init(smem_u32(&tail->b_res_full), 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(&tail->tmem_base), TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+
+    if (warp < 4) {
+        // ===================== epilogue =====================
+        const int row = warp * 32 + lane;
+        float* out = reinterpret_cast<float*>(out_v);
+        __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(out_v);
+        const bool vec = d.out_sc == 1 && (d.Cout & 7) == 0 &&
+                         (out_bf16 ? (((d.out_sn | d.out_sh | d.out_sw) & 7) == 0 && (reinterpret_cast<uintptr_t>(out_v) & 15) == 0)
+                                   : (((d.out_sn | d.out_sh | d.out_sw) & 3) == 0 && (reinterpret_cast<uintptr_t>(out_v) & 15) == 0));
+        int mt, nt;
+        for (int j = 0; halo_tile(hg, j, mt, nt); ++j) {
+            const int buf = j & 1;
+            const int n0 = nt * BN;
+            const int img = mt / hg.tiles_per_img;
+            const int v = (mt - img * hg.tiles_per_img) * BM + row;
+            const int qy = v / hg.Wp, qx = v - qy * hg.Wp;
+            int64_t ro = -1;
+            float alpha = 1.f;
+            if (qy < d.Qh && qx < d.Qw) {
+                ro = (int64_t)img * d.out_sn + (int64_t)qy * d.out_sh + (int64_t)qx * d.out_sw;
+                if (scale) {
+                    const int64_t m = ((int64_t)img * d.Qh + qy) * d.Qw + qx;
+                    alpha = scale[d.scale_rows > 0 ? m / d.scale_rows : 0];
+                }
+            }
+            mbar_wait(smem_u32(&tail->tmem_full[buf]), (uint32_t)(j >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * ACC_COLS);
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += CW) {
+                uint32_t r[CW];
+                if constexpr (CW == 32) tmem_ld32(tacc + (uint32_t)cb, r);
+                else tmem_ld16(tacc + (uint32_t)cb, r);
+                if (ro >= 0) {
+#pragma unroll
+                    for (int h = 0; h < CW; h += 16) {
+                        float o[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const int co = n0 + cb + h + e;
+                            const float val = __uint_as_float(r[h + e]) * alpha + ((bias && co < d.Cout) ? bias[co] : 0.f);
+                            o[e] = d.relu ? fmaxf(val, 0.f) : val;
+                        }
+                        const int c0 = n0 + cb + h;
+                        if (vec && c0 + 16 <= d.Cout) {
+                            if (out_bf16) {
+                                st_bf16x8(outh + ro + c0, o);
+                                st_bf16x8(outh + ro + c0 + 8, o + 8);
+                            } else {
+                                float4* p = reinterpret_cast<float4*>(out + ro + c0);
+                                p[0] = make_float4(o[0], o[1], o[2], o[3]);
+                                p[1] = make_float4(o[4], o[5], o[6], o[7]);
+                                p[2] = make_float4(o[8], o[9], o[10], o[11]);
+                                p[3] = make_float4(o[12], o[13], o[14], o[15]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                const int co = c0 + e;
+                                if (co < d.Cout) {
+                                    if (out_bf16) outh[ro + (int64_t)co * d.out_sc] = __float2bfloat16_rn(o[e]);
+                                    else out[ro + (int64_t)co * d.out_sc] = o[e];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tail->tmem_empty[buf]));
+        }
+    } else if (warp == 4) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            uint32_t ia = 0, ib = 0;
+            int mt, nt;
+            if (hg.b_resident && halo_tile(hg, 0, mt, nt)) {
+                const uint32_t bbar = smem_u32(&tail->b_res_full);
+                mbar_arrive_expect_tx(bbar, (uint32_t)(num_kb * B_BYTES));
+                for (int kb = 0; kb < num_kb; ++kb)
+                    tma_load_2d(smem_u32(smem_b + kb * B_BYTES), &tmap, kb * BK, nt * BN, bbar);
+            }
+            for (int i = 0; halo_tile(hg, i, mt, nt); ++i) {
+                const int n0 = nt * BN;
+                const int img = mt / hg.tiles_per_img;
+                const int v0 = (mt - img * hg.tiles_per_img) * BM;
+                const int r0 = v0 / hg.Wp;
+                for (int cc = 0; cc < cpb; ++cc, ++ia) {
+                    const int ab = (int)(ia % NA);
+                    mbar_wait(smem_u32(&tail->a_empty[ab]), ((ia / NA) & 1u) ^ 1u);
+                    const uint32_t abar = smem_u32(&tail->a_full[ab]);
+                    mbar_arrive_expect_tx(abar, (uint32_t)hg.slab_tx);
+                    tma_load_4d(smem_u32(smem_a + ab * hg.slab_bytes), &tmap_in, cc * BK, hg.lw, hg.lh + r0, img, abar);
+                    if (!hg.b_resident) {
+                        for (int tap = 0; tap < taps; ++tap, ++ib) {
+                            const int s = (int)(ib % SB);
+                            mbar_wait(smem_u32(&tail->b_empty[s]), ((ib / SB) & 1u) ^ 1u);
+                            const uint32_t bbar = smem_u32(&tail->b_full[s]);
+                            mbar_arrive_expect_tx(bbar, B_BYTES);
+                            tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tmap, (tap * cpb + cc) * BK, n0, bbar);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        uint32_t ia = 0, ib = 0;
+        int mt, nt;
+        if (hg.b_resident && halo_tile(hg, 0, mt, nt)) {
+            mbar_wait(smem_u32(&tail->b_res_full), 0);
+            tc_fence_after();
+        }
+        for (int j = 0; halo_tile(hg, j, mt, nt); ++j) {
+            const int buf = j & 1;
+            const int img = mt / hg.tiles_per_img;
+            const int v0 = (mt - img * hg.tiles_per_img) * BM;
+            const int voff = v0 % hg.Wp;
+            mbar_wait(smem_u32(&tail->tmem_empty[buf]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
+            for (int cc = 0; cc < cpb; ++cc, ++ia) {
+                const int ab = (int)(ia % NA);
+                mbar_wait(smem_u32(&tail->a_full[ab]), (ia / NA) & 1u);
+                tc_fence_after();
+                const uint32_t slab = smem_u32(smem_a + ab * hg.slab_bytes);
+                int ty = 0, tx = 0;
+                for (int tap = 0; tap < taps; ++tap, ++ib) {
+                    uint32_t b_addr;
+                    int s = 0;
+                    if (hg.b_resident) {
+                        b_addr = smem_u32(smem_b + (tap * cpb + cc) * B_BYTES);
+                    } else {
+                        s = (int)(ib % SB);
+                        mbar_wait(smem_u32(&tail->b_full[s]), (ib / SB) & 1u);
+                        tc_fence_after();
+                        b_addr = smem_u32(smem_b + s * B_BYTES);
+                    }
+                    if (lane == 0) {
+                        const int dy = ty * d.tap_sy + d.tap_oy - hg.lh;
+                        const int dx = tx * d.tap_sx + d.tap_ox - hg.lw;
+                        const uint32_t a0 = slab + (uint32_t)(voff + dy * hg.Wp + dx) * 128u;
+                        const uint64_t adesc = make_desc(a0, 16, 1024);
+                        const uint64_t bdesc = make_desc(b_addr, 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cc | tap | k) != 0);
+                        if (!hg.b_resident) umma_commit(smem_u32(&tail->b_empty[s]));
+                        if (tap == taps - 1) {
+                            umma_commit(smem_u32(&tail->a_empty[ab]));
+                            if (cc == cpb - 1) umma_commit(smem_u32(&tail->tmem_full[buf]));
+                        }
+                    }
+                    __syncwarp();
+                    if (++tx == d.Tw) { tx = 0; ++ty; }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // split-K second pass: out = epilogue( sum_z ws[z][m][co] ), fixed summation order
 __global__ void conv_splitk_reduce_kernel(b200_conv_desc d, const float* __restrict__ ws, int splits, int ldo,
                                           const float* __restrict__ bias, const float* __restrict__ scale,
@@ -631,6 +1122,8 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
+static int g_use_persist = 1;
+static int g_use_halo = 1;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -706,6 +1199,113 @@ static int encode_im2col(const b200_conv_desc* d, const void* in, CUtensorMap* t
     return 0;
 }
 
+// shifted-window plan: stride-1 window walk with unit tap steps onto a dense output at a resolution where the
+// dummy-column / last-tile waste is small, slabs small enough to keep >= 2 in flight.  If the N tile's whole weight
+// matrix fits next to the slabs it stays RESIDENT (BN = 64 is tried first for that), else it streams through a ring.
+static bool halo_plan(const b200_conv_desc* d, int BN, bool allow_stream, HaloGeom* hg) {
+    if (!g_use_halo) return false;
+    if (d->up_shift != 0 || d->in_sy != 1 || d->in_sx != 1) return false;
+    if ((d->tap_sy != 1 && d->tap_sy != -1) || (d->tap_sx != 1 && d->tap_sx != -1)) return false;
+    if (d->out_sy != 1 || d->out_sx != 1 || d->out_oy != 0 || d->out_ox != 0 || d->Ho != d->Qh || d->Wo != d->Qw) return false;
+    const int taps = d->Th * d->Tw;
+    if (taps < 2) return false;
+    const int Wp = d->Qw + d->Tw - 1;
+    const int RB = (Wp - 1 + 127 + d->Tw - 1) / Wp + 1 + (d->Th - 1);
+    if (Wp > 256 || RB > 256) return false;
+    const int slab_tx = RB * Wp * 128;
+    const int slab_bytes = (slab_tx + 1023) & ~1023;
+    const int b_bytes = BN * BK * 2;
+    const int cpb = d->Cin / BK;
+    const int num_kb = taps * cpb;
+    const int total = 226 * 1024 - 1024 - (int)sizeof(HaloTail);
+    const int tiles_per_img = (d->Qh * Wp + BM - 1) / BM;
+    // waste of the padded-row tiling against the dense M = Qh*Qw tiling of the im2col kernels
+    const double waste = (double)tiles_per_img * BM / ((double)d->Qh * d->Qw);
+    if (waste > 1.25) return false;
+    int na, stages = 0, resident = 0;
+    if (2 * slab_bytes + num_kb * b_bytes <= total) {
+        resident = 1;
+        na = (total - num_kb * b_bytes) / slab_bytes;
+    } else {
+        if (!allow_stream) return false;
+        stages = 4;
+        na = (total - stages * b_bytes) / slab_bytes;
+        if (na < 2) return false;
+        if (na > 4) na = 4;
+        stages = (total - na * slab_bytes) / b_bytes;
+        if (stages > 8) stages = 8;
+        // streaming only pays when the activation re-read dominates the weight traffic
+        const double K = (double)taps * d->Cin;
+        const double bytes_halo = waste * (cpb * (double)slab_tx + BN * K * 2.0);
+        const double bytes_im2col = K / BK * A_BYTES + BN * K * 2.0;
+        if (bytes_halo > 0.75 * bytes_im2col) return false;
+    }
+    if (na > 4) na = 4;
+    hg->Wp = Wp; hg->RB = RB;
+    hg->lw = d->tap_sx > 0 ? d->tap_ox : d->tap_ox - (d->Tw - 1);
+    hg->lh = d->tap_sy > 0 ? d->tap_oy : d->tap_oy - (d->Th - 1);
+    hg->slab_bytes = slab_bytes; hg->slab_tx = slab_tx; hg->na = na; hg->b_stages = stages; hg->b_resident = resident;
+    hg->tiles_per_img = tiles_per_img;
+    return true;
+}
+
+template <int BN>
+static int launch_halo(const b200_conv_desc* d, const HaloGeom& hg_in, const void* wmat, const void* in,
+                       const float* bias, const float* scale, void* out, int out_bf16, cudaStream_t st) {
+    EncodeTiledFn enc = get_encode_fn();
+    HaloGeom hg = hg_in;
+    const int pad_tile = b200_conv_tc_ntile(d->Cout);                       // rows of the packed weight matrix
+    const int rows = (d->Cout + pad_tile - 1) / pad_tile * pad_tile;
+    const int ntiles = (d->Cout + BN - 1) / BN;
+    CUtensorMap tmap_w, tmap_in;
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)d->ldw, (cuuint64_t)rows};
+        cuuint64_t gstr[1] = {(cuuint64_t)d->ldw * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wmat), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm_tc: cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
+    }
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->B};
+        cuuint64_t gstr[3] = {(cuuint64_t)d->in_sw * 2, (cuuint64_t)d->in_sh * 2, (cuuint64_t)d->in_sn * 2};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)hg.Wp, (cuuint32_t)hg.RB, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmap_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm_tc: cuTensorMapEncodeTiled(4D slab) failed (%d)", (int)r);
+    }
+    const int num_kb = d->Th * d->Tw * (d->Cin / BK);
+    const int smem_bytes = 1024 + hg.na * hg.slab_bytes + (hg.b_resident ? num_kb : hg.b_stages) * BN * BK * 2 +
+                           (int)sizeof(HaloTail);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute(halo): %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int64_t mtiles = (int64_t)d->B * hg.tiles_per_img;
+    B200_REQUIRE(mtiles * ntiles < (1ll << 31), "conv_gemm_tc: too many tiles");
+    hg.num_n_tiles = ntiles;
+    hg.num_m_tiles = (int)mtiles;
+    int grid;
+    if (hg.b_resident) {
+        int per_n = kNumSMs / ntiles;
+        if (per_n < 1) return set_error("conv_gemm_tc: too many N tiles for the resident shifted-window kernel");
+        if (per_n > mtiles) per_n = (int)mtiles;
+        grid = per_n * ntiles;
+    } else {
+        const int64_t tiles = mtiles * ntiles;
+        grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    }
+    conv_halo_tc_kernel<BN><<<grid, 192, smem_bytes, st>>>(tmap_w, tmap_in, *d, hg, bias, scale, out, out_bf16);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
 template <int BN, int STAGES>
 static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const void* wmat, const float* bias,
                       const float* scale, void* out, int out_bf16, float* split_ws, int splits, int use_im2col,
@@ -723,6 +1323,13 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    HaloGeom hg;
+    if (use_im2col && splits == 1) {
+        // resident weights with a 64-wide N tile first (fits for Cin = 64 3x3 layers of any Cout), then the native tile
+        if (BN == 128 && d->Cout / 64 <= kNumSMs && halo_plan(d, 64, false, &hg))
+            return launch_halo<64>(d, hg, wmat, in, bias, scale, out, out_bf16, st);
+        if (halo_plan(d, BN, true, &hg)) return launch_halo<BN>(d, hg, wmat, in, bias, scale, out, out_bf16, st);
+    }
     const bool atma = use_im2col && im2col_eligible(d);
     if (atma) {
         if (encode_im2col(d, in, &tmap_a) != 0) return -1;
@@ -743,6 +1350,26 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
     const int num_kb = d->Th * d->Tw * (d->Cin / BK);
     int kbps = (num_kb + splits - 1) / splits;
     splits = (num_kb + kbps - 1) / kbps;          // no empty split
+    if (atma && splits == 1 && g_use_persist && BN >= 64 && num_kb <= 24) {
+        // persistent path: one CTA per SM, deep operand ring, double-buffered TMEM accumulator
+        constexpr int PSTAGES = BN == 128 ? 6 : 8;
+        constexpr int psmem = 1024 + PSTAGES * (A_BYTES + BN * BK * 2) + (int)sizeof(PersistTail);
+        static bool pconfigured = false;
+        if (!pconfigured) {
+            cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<BN, PSTAGES>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+            B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute(persist): %s", cudaGetErrorString(e));
+            pconfigured = true;
+        }
+        const int64_t mtiles = (M + BM - 1) / BM;
+        const int64_t tiles = mtiles * ntiles;
+        B200_REQUIRE(tiles < (1ll << 31), "conv_gemm_tc: too many tiles");
+        const int grid_p = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+        conv_gemm_tc_persist_kernel<BN, PSTAGES><<<grid_p, 192, psmem, st>>>(tmap, tmap_a, *d, bias, scale, out, out_bf16,
+                                                                           ntiles, (int)tiles);
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles, (unsigned)splits);
     if (atma)
         conv_gemm_tc_kernel<BN, STAGES, true><<<grid, 192, smem_bytes, st>>>(tmap, tmap_a, *d, in, bias, scale, out,
@@ -862,6 +1489,18 @@ extern "C" int b200_conv_tc_set_im2col(int enable) {
     int old = g_use_im2col;
     g_use_im2col = enable ? 1 : 0;
     return old;
+}
+
+extern "C" int b200_conv_tc_set_persistent(int enable) {
+    int prev = tc::g_use_persist;
+    tc::g_use_persist = enable ? 1 : 0;
+    return prev;
+}
+
+extern "C" int b200_conv_tc_set_halo(int enable) {
+    int prev = tc::g_use_halo;
+    tc::g_use_halo = enable ? 1 : 0;
+    return prev;
 }
 
 extern "C" int b200_conv_tc_ntile(int Cout) { return Cout >= 128 ? 128 : (Cout >= 64 ? 64 : 16); }

@@ -106,6 +106,17 @@ int b200_conv_tc_ntile(int Cout);
  * cp.async gathers.  b200_conv_tc_set_im2col(0) forces the cp.async path (parity tests compare the two); returns the
  * previous setting. */
 int b200_conv_tc_set_im2col(int enable);
+/* im2col-eligible, unsplit launches run the PERSISTENT kernel (one CTA per SM walking the output tiles, operand ring
+ * running ahead across tiles, double-buffered TMEM accumulator so the epilogue overlaps the next tile's MMAs).
+ * b200_conv_tc_set_persistent(0) forces the one-tile-per-CTA kernel (parity tests compare the two); returns the
+ * previous setting. */
+int b200_conv_tc_set_persistent(int enable);
+/* Stride-1 k x k window walks (conv forward and its dgrad) whose activation slab fits shared memory run the
+ * SHIFTED-WINDOW kernel: one tiled TMA box per 64-channel slab brings the zero-padded input rows of a 128-pixel output
+ * tile into shared memory once, and every tap's A operand is that slab addressed from a row-shifted start (UMMA
+ * descriptors swizzle on absolute shared-memory addresses), instead of one im2col load per tap.
+ * b200_conv_tc_set_halo(0) disables it (parity tests compare with the im2col kernels); returns the previous setting. */
+int b200_conv_tc_set_halo(int enable);
 int b200_conv_tc_splits(const b200_conv_desc* d);
 /* y[i] = bf16(x[i]) (round to nearest even), n % 4 == 0 */
 int b200_cast_bf16(const float* x, void* y_bf16, int64_t n, b200_stream_t stream);

@@ -19,6 +19,8 @@ for _ in range(2):
     ts.step(b, optimizer_step=True)
 torch.cuda.synchronize()
 K = _lib._K
+if os.environ.get("B200_NO_PERSIST"):
+    K.conv_tc_set_persistent(False)
 recs = []
 names = [n for n in dir(K) if not n.startswith("_") and callable(getattr(K, n)) and n not in ("launch_count", "version", "bn_chunks", "conv_tc_ntile")]
 orig = {n: getattr(K, n) for n in names}
