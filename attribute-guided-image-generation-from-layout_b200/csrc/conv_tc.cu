@@ -53,6 +53,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > kSpinLimit) __trap();   // a broken pipeline must not hang the GPU
     }
 }
+// one lane of a converged warp (the tcgen05 / TMA issue instructions take their operands from uniform registers: the
+// issuing roles run warp-uniform code and predicate only the issue itself, so no per-instruction broadcast is needed)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }
+__device__ __forceinline__ int uniform(int x) { return __shfl_sync(0xffffffffu, x, 0); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -176,7 +185,7 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
     int* row_ix = row_iy + BM;
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = uniform(tid >> 5), lane = tid & 31;
     const int64_t M = (int64_t)d.B * d.Qh * d.Qw;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
@@ -330,52 +339,59 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
         }
     } else if (warp == 4) {
         // ===================== B producer (TMA), and the A producer on the im2col path =====================
-        if (lane == 0) {
-            // im2col base coordinates of the tile's first output pixel (tap (0,0) in the tensor map's offset convention)
-            int aw = 0, ah = 0, an = 0, tap = 0, cc = 0;
-            if (ATMA) {
-                const int qx = (int)(m0 % d.Qw);
-                const int qy = (int)((m0 / d.Qw) % d.Qh);
-                an = (int)(m0 / ((int64_t)d.Qw * d.Qh));
-                aw = qx * d.in_sx + (d.tap_sx > 0 ? d.tap_ox : d.tap_ox - (d.Tw - 1));
-                ah = qy * d.in_sy + (d.tap_sy > 0 ? d.tap_oy : d.tap_oy - (d.Th - 1));
-                tap = kb_begin / cpb;
-                cc = kb_begin - tap * cpb;
-            }
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
-                const uint32_t bar = smem_u32(&tail->full[s]);
+        // warp-uniform; one elected lane issues the TMA requests
+        const uint32_t bar0 = smem_u32(tail);
+        const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b);
+        // im2col base coordinates of the tile's first output pixel (tap (0,0) in the tensor map's offset convention)
+        int aw = 0, ah = 0, an = 0, tap = 0, cc = 0, tyy = 0, txx = 0;
+        if (ATMA) {
+            const int qx = (int)(m0 % d.Qw);
+            const int qy = (int)((m0 / d.Qw) % d.Qh);
+            an = (int)(m0 / ((int64_t)d.Qw * d.Qh));
+            aw = qx * d.in_sx + (d.tap_sx > 0 ? d.tap_ox : d.tap_ox - (d.Tw - 1));
+            ah = qy * d.in_sy + (d.tap_sy > 0 ? d.tap_oy : d.tap_oy - (d.Th - 1));
+            tap = kb_begin / cpb;
+            cc = kb_begin - tap * cpb;
+            tyy = tap / d.Tw;
+            txx = tap - tyy * d.Tw;
+        }
+        uint32_t s = 0, ph = 0;
+        for (int i = 0; i < num_kb; ++i) {
+            mbar_wait(bar0 + (uint32_t)offsetof(SmemTail, empty) + 8u * s, ph ^ 1u);
+            const uint16_t ow = (uint16_t)(d.tap_sx > 0 ? txx : d.Tw - 1 - txx);
+            const uint16_t oh = (uint16_t)(d.tap_sy > 0 ? tyy : d.Th - 1 - tyy);
+            if (elect_one()) {
+                const uint32_t bar = bar0 + (uint32_t)offsetof(SmemTail, full) + 8u * s;
                 mbar_arrive_expect_tx(bar, ATMA ? A_BYTES + B_BYTES : B_BYTES);
-                if (ATMA) {
-                    const int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
-                    const uint16_t ow = (uint16_t)(d.tap_sx > 0 ? txx : d.Tw - 1 - txx);
-                    const uint16_t oh = (uint16_t)(d.tap_sy > 0 ? tyy : d.Th - 1 - tyy);
-                    tma_load_im2col_4d(smem_u32(smem_a + s * A_BYTES), &tmap_a, cc * BK, aw, ah, an, ow, oh, bar);
-                    if (++cc == cpb) { cc = 0; ++tap; }
-                }
-                tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tmap, (kb_begin + i) * BK, n0, bar);
+                if (ATMA) tma_load_im2col_4d(a0 + s * A_BYTES, &tmap_a, cc * BK, aw, ah, an, ow, oh, bar);
+                tma_load_2d(b0 + s * B_BYTES, &tmap, (kb_begin + i) * BK, n0, bar);
             }
+            if (ATMA && ++cc == cpb) {
+                cc = 0;
+                if (++txx == d.Tw) { txx = 0; ++tyy; }
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
     } else {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
         constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        const uint64_t desc_hi = make_desc(0, 16, 1024);
+        const uint32_t bar0 = smem_u32(tail);
+        const uint32_t a0 = smem_u32(smem_a) >> 4, b0 = smem_u32(smem_b) >> 4;
+        uint32_t s = 0, ph = 0;
         for (int i = 0; i < num_kb; ++i) {
-            const int s = i % STAGES;
-            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-            mbar_wait(smem_u32(&tail->full[s]), ph);
+            mbar_wait(bar0 + (uint32_t)offsetof(SmemTail, full) + 8u * s, ph);
             tc_fence_after();
-            if (lane == 0) {
-                const uint64_t adesc = make_desc(smem_u32(smem_a + s * A_BYTES), 16, 1024);
-                const uint64_t bdesc = make_desc(smem_u32(smem_b + s * B_BYTES), 16, 1024);
+            const uint64_t adesc = desc_hi | (uint64_t)((a0 + s * (A_BYTES >> 4)) & 0x3FFFu);
+            const uint64_t bdesc = desc_hi | (uint64_t)((b0 + s * (B_BYTES >> 4)) & 0x3FFFu);
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) != 0);
-                umma_commit(smem_u32(&tail->empty[s]));
-                if (i == num_kb - 1) umma_commit(smem_u32(&tail->tmem_full));
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)(i | k));
+                umma_commit(bar0 + (uint32_t)offsetof(SmemTail, empty) + 8u * s);
+                if (i == num_kb - 1) umma_commit(bar0 + (uint32_t)offsetof(SmemTail, tmem_full));
             }
-            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
     }
     tc_fence_before();
@@ -432,7 +448,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_persist_kernel(const __gr
     PersistTail* tail = reinterpret_cast<PersistTail*>(smem_b + STAGES * B_BYTES);
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = uniform(tid >> 5), lane = tid & 31;
     const int64_t M = (int64_t)d.B * d.Qh * d.Qw;
     const int cpb = d.Cin / BK;
     const int num_kb = d.Th * d.Tw * cpb;
@@ -534,58 +550,64 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_persist_kernel(const __gr
             if (lane == 0) mbar_arrive(smem_u32(&tail->tmem_empty[buf]));
         }
     } else if (warp == 4) {
-        // ===================== producer =====================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int n0 = (t % num_n_tiles) * BN;
-                const int64_t m0 = (int64_t)(t / num_n_tiles) * BM;
-                const int qx = (int)(m0 % d.Qw);
-                const int qy = (int)((m0 / d.Qw) % d.Qh);
-                const int an = (int)(m0 / ((int64_t)d.Qw * d.Qh));
-                const int aw = qx * d.in_sx + (d.tap_sx > 0 ? d.tap_ox : d.tap_ox - (d.Tw - 1));
-                const int ah = qy * d.in_sy + (d.tap_sy > 0 ? d.tap_oy : d.tap_oy - (d.Th - 1));
-                int tap = 0, cc = 0;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = (int)(it % STAGES);
-                    const uint32_t ph = (it / STAGES) & 1u;
-                    mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
-                    const uint32_t bar = smem_u32(&tail->full[s]);
-                    mbar_arrive_expect_tx(bar, A_BYTES + B_BYTES);
-                    const int tyy = tap / d.Tw, txx = tap - tyy * d.Tw;
-                    const uint16_t ow = (uint16_t)(d.tap_sx > 0 ? txx : d.Tw - 1 - txx);
-                    const uint16_t oh = (uint16_t)(d.tap_sy > 0 ? tyy : d.Th - 1 - tyy);
-                    tma_load_im2col_4d(smem_u32(smem_a + s * A_BYTES), &tmap_a, cc * BK, aw, ah, an, ow, oh, bar);
-                    tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tmap, kb * BK, n0, bar);
-                    if (++cc == cpb) { cc = 0; ++tap; }
+        // ===================== producer (warp-uniform; one elected lane issues the TMA requests) =====================
+        const uint32_t bar0 = smem_u32(tail);
+        const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b);
+        const int lw = d.tap_sx > 0 ? d.tap_ox : d.tap_ox - (d.Tw - 1);
+        const int lh = d.tap_sy > 0 ? d.tap_oy : d.tap_oy - (d.Th - 1);
+        uint32_t s = 0, ph = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int n0 = (t % num_n_tiles) * BN;
+            const int64_t m0 = (int64_t)(t / num_n_tiles) * BM;
+            const int qx = (int)(m0 % d.Qw);
+            const int qy = (int)((m0 / d.Qw) % d.Qh);
+            const int an = (int)(m0 / ((int64_t)d.Qw * d.Qh));
+            const int aw = qx * d.in_sx + lw;
+            const int ah = qy * d.in_sy + lh;
+            int kb = 0;
+            for (int ty = 0; ty < d.Th; ++ty) {
+                const uint16_t oh = (uint16_t)(d.tap_sy > 0 ? ty : d.Th - 1 - ty);
+                for (int tx = 0; tx < d.Tw; ++tx) {
+                    const uint16_t ow = (uint16_t)(d.tap_sx > 0 ? tx : d.Tw - 1 - tx);
+                    for (int cc = 0; cc < cpb; ++cc, ++kb) {
+                        mbar_wait(bar0 + (uint32_t)offsetof(PersistTail, empty) + 8u * s, ph ^ 1u);
+                        if (elect_one()) {
+                            const uint32_t bar = bar0 + (uint32_t)offsetof(PersistTail, full) + 8u * s;
+                            mbar_arrive_expect_tx(bar, A_BYTES + B_BYTES);
+                            tma_load_im2col_4d(a0 + s * A_BYTES, &tmap_a, cc * BK, aw, ah, an, ow, oh, bar);
+                            tma_load_2d(b0 + s * B_BYTES, &tmap, kb * BK, n0, bar);
+                        }
+                        if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    }
                 }
             }
         }
     } else {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
         constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-        uint32_t it = 0;
+        const uint64_t desc_hi = make_desc(0, 16, 1024);
+        const uint32_t bar0 = smem_u32(tail);
+        const uint32_t a0 = smem_u32(smem_a) >> 4, b0 = smem_u32(smem_b) >> 4;
+        uint32_t s = 0, ph = 0;
         int j = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
             const int buf = j & 1;
-            mbar_wait(smem_u32(&tail->tmem_empty[buf]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+            mbar_wait(bar0 + (uint32_t)offsetof(PersistTail, tmem_empty) + 8u * buf, ((uint32_t)(j >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = (int)(it % STAGES);
-                const uint32_t ph = (it / STAGES) & 1u;
-                mbar_wait(smem_u32(&tail->full[s]), ph);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(bar0 + (uint32_t)offsetof(PersistTail, full) + 8u * s, ph);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint64_t adesc = make_desc(smem_u32(smem_a + s * A_BYTES), 16, 1024);
-                    const uint64_t bdesc = make_desc(smem_u32(smem_b + s * B_BYTES), 16, 1024);
+                const uint64_t adesc = desc_hi | (uint64_t)((a0 + s * (A_BYTES >> 4)) & 0x3FFFu);
+                const uint64_t bdesc = desc_hi | (uint64_t)((b0 + s * (B_BYTES >> 4)) & 0x3FFFu);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                    umma_commit(smem_u32(&tail->empty[s]));
-                    if (kb == num_kb - 1) umma_commit(smem_u32(&tail->tmem_full[buf]));
+                        umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)(kb | k));
+                    umma_commit(bar0 + (uint32_t)offsetof(PersistTail, empty) + 8u * s);
+                    if (kb == num_kb - 1) umma_commit(bar0 + (uint32_t)offsetof(PersistTail, tmem_full) + 8u * buf);
                 }
-                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
     }
@@ -677,7 +699,7 @@ __global__ void __launch_bounds__(192, 1) conv_halo_tc_kernel(const __grid_const
     HaloTail* tail = reinterpret_cast<HaloTail*>(smem_b + (hg.b_resident ? num_kb : hg.b_stages) * B_BYTES);
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = uniform(tid >> 5), lane = tid & 31;
     const uint32_t SB = (uint32_t)hg.b_stages, NA = (uint32_t)hg.na;
 
     if (warp == 4 && lane == 0) {
@@ -781,46 +803,59 @@ __global__ void __launch_bounds__(192, 1) conv_halo_tc_kernel(const __grid_const
             if (lane == 0) mbar_arrive(smem_u32(&tail->tmem_empty[buf]));
         }
     } else if (warp == 4) {
-        // ===================== producer =====================
-        if (lane == 0) {
-            uint32_t ia = 0, ib = 0;
-            int mt, nt;
-            if (hg.b_resident && halo_tile(hg, 0, mt, nt)) {
-                const uint32_t bbar = smem_u32(&tail->b_res_full);
+        // ===================== producer (warp-uniform; one elected lane issues the TMA requests) =====================
+        const uint32_t bar0 = smem_u32(tail);
+        const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
+        uint32_t ab = 0, aph = 0, bs = 0, bph = 0;
+        int mt, nt;
+        if (hg.b_resident && halo_tile(hg, 0, mt, nt)) {
+            if (elect_one()) {
+                const uint32_t bbar = bar0 + (uint32_t)offsetof(HaloTail, b_res_full);
                 mbar_arrive_expect_tx(bbar, (uint32_t)(num_kb * B_BYTES));
-                for (int kb = 0; kb < num_kb; ++kb)
-                    tma_load_2d(smem_u32(smem_b + kb * B_BYTES), &tmap, kb * BK, nt * BN, bbar);
+                for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sb0 + kb * B_BYTES, &tmap, kb * BK, nt * BN, bbar);
             }
-            for (int i = 0; halo_tile(hg, i, mt, nt); ++i) {
-                const int n0 = nt * BN;
-                const int img = mt / hg.tiles_per_img;
-                const int v0 = (mt - img * hg.tiles_per_img) * BM;
-                const int r0 = v0 / hg.Wp;
-                for (int cc = 0; cc < cpb; ++cc, ++ia) {
-                    const int ab = (int)(ia % NA);
-                    mbar_wait(smem_u32(&tail->a_empty[ab]), ((ia / NA) & 1u) ^ 1u);
-                    const uint32_t abar = smem_u32(&tail->a_full[ab]);
+            __syncwarp();
+        }
+        for (int i = 0; halo_tile(hg, i, mt, nt); ++i) {
+            const int n0 = nt * BN;
+            const int img = mt / hg.tiles_per_img;
+            const int v0 = (mt - img * hg.tiles_per_img) * BM;
+            const int r0 = v0 / hg.Wp;
+            for (int cc = 0; cc < cpb; ++cc) {
+                mbar_wait(bar0 + (uint32_t)offsetof(HaloTail, a_empty) + 8u * ab, aph ^ 1u);
+                if (elect_one()) {
+                    const uint32_t abar = bar0 + (uint32_t)offsetof(HaloTail, a_full) + 8u * ab;
                     mbar_arrive_expect_tx(abar, (uint32_t)hg.slab_tx);
-                    tma_load_4d(smem_u32(smem_a + ab * hg.slab_bytes), &tmap_in, cc * BK, hg.lw, hg.lh + r0, img, abar);
-                    if (!hg.b_resident) {
-                        for (int tap = 0; tap < taps; ++tap, ++ib) {
-                            const int s = (int)(ib % SB);
-                            mbar_wait(smem_u32(&tail->b_empty[s]), ((ib / SB) & 1u) ^ 1u);
-                            const uint32_t bbar = smem_u32(&tail->b_full[s]);
+                    tma_load_4d(sa0 + ab * (uint32_t)hg.slab_bytes, &tmap_in, cc * BK, hg.lw, hg.lh + r0, img, abar);
+                }
+                if (++ab == NA) { ab = 0; aph ^= 1u; }
+                if (!hg.b_resident) {
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(bar0 + (uint32_t)offsetof(HaloTail, b_empty) + 8u * bs, bph ^ 1u);
+                        if (elect_one()) {
+                            const uint32_t bbar = bar0 + (uint32_t)offsetof(HaloTail, b_full) + 8u * bs;
                             mbar_arrive_expect_tx(bbar, B_BYTES);
-                            tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tmap, (tap * cpb + cc) * BK, n0, bbar);
+                            tma_load_2d(sb0 + bs * B_BYTES, &tmap, (tap * cpb + cc) * BK, n0, bbar);
                         }
+                        if (++bs == SB) { bs = 0; bph ^= 1u; }
                     }
                 }
             }
         }
     } else {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
         constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-        uint32_t ia = 0, ib = 0;
+        const uint64_t desc_hi = make_desc(0, 16, 1024);
+        const uint32_t slab0 = smem_u32(smem_a) >> 4, slab_step = (uint32_t)hg.slab_bytes >> 4;
+        const uint32_t b0 = smem_u32(smem_b) >> 4;
+        const uint32_t bar0 = smem_u32(tail);
+        // 16-byte units: one pixel row of the slab = 8
+        const int row_step = d.tap_sy * hg.Wp * 8, col_step = d.tap_sx * 8;
+        const int off00 = ((d.tap_oy - hg.lh) * hg.Wp + (d.tap_ox - hg.lw)) * 8;
+        uint32_t ab = 0, aph = 0, bs = 0, bph = 0;
         int mt, nt;
         if (hg.b_resident && halo_tile(hg, 0, mt, nt)) {
-            mbar_wait(smem_u32(&tail->b_res_full), 0);
+            mbar_wait(bar0 + (uint32_t)offsetof(HaloTail, b_res_full), 0);
             tc_fence_after();
         }
         for (int j = 0; halo_tile(hg, j, mt, nt); ++j) {
@@ -828,44 +863,45 @@ __global__ void __launch_bounds__(192, 1) conv_halo_tc_kernel(const __grid_const
             const int img = mt / hg.tiles_per_img;
             const int v0 = (mt - img * hg.tiles_per_img) * BM;
             const int voff = v0 % hg.Wp;
-            mbar_wait(smem_u32(&tail->tmem_empty[buf]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+            mbar_wait(bar0 + (uint32_t)offsetof(HaloTail, tmem_empty) + 8u * buf, ((uint32_t)(j >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
-            for (int cc = 0; cc < cpb; ++cc, ++ia) {
-                const int ab = (int)(ia % NA);
-                mbar_wait(smem_u32(&tail->a_full[ab]), (ia / NA) & 1u);
+            uint32_t acc = 0;
+            for (int cc = 0; cc < cpb; ++cc) {
+                mbar_wait(bar0 + (uint32_t)offsetof(HaloTail, a_full) + 8u * ab, aph);
                 tc_fence_after();
-                const uint32_t slab = smem_u32(smem_a + ab * hg.slab_bytes);
-                int ty = 0, tx = 0;
-                for (int tap = 0; tap < taps; ++tap, ++ib) {
-                    uint32_t b_addr;
-                    int s = 0;
-                    if (hg.b_resident) {
-                        b_addr = smem_u32(smem_b + (tap * cpb + cc) * B_BYTES);
-                    } else {
-                        s = (int)(ib % SB);
-                        mbar_wait(smem_u32(&tail->b_full[s]), (ib / SB) & 1u);
-                        tc_fence_after();
-                        b_addr = smem_u32(smem_b + s * B_BYTES);
-                    }
-                    if (lane == 0) {
-                        const int dy = ty * d.tap_sy + d.tap_oy - hg.lh;
-                        const int dx = tx * d.tap_sx + d.tap_ox - hg.lw;
-                        const uint32_t a0 = slab + (uint32_t)(voff + dy * hg.Wp + dx) * 128u;
-                        const uint64_t adesc = make_desc(a0, 16, 1024);
-                        const uint64_t bdesc = make_desc(b_addr, 16, 1024);
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cc | tap | k) != 0);
-                        if (!hg.b_resident) umma_commit(smem_u32(&tail->b_empty[s]));
-                        if (tap == taps - 1) {
-                            umma_commit(smem_u32(&tail->a_empty[ab]));
-                            if (cc == cpb - 1) umma_commit(smem_u32(&tail->tmem_full[buf]));
+                const uint32_t a_base = slab0 + ab * slab_step + (uint32_t)(voff * 8 + off00);
+                uint32_t b_res = b0 + (uint32_t)cc * (B_BYTES >> 4);
+                int row_off = 0;
+                for (int ty = 0; ty < d.Th; ++ty, row_off += row_step) {
+                    int off = row_off;
+                    for (int tx = 0; tx < d.Tw; ++tx, off += col_step) {
+                        uint32_t b_lo;
+                        if (hg.b_resident) {
+                            b_lo = b_res;
+                            b_res += (uint32_t)cpb * (B_BYTES >> 4);
+                        } else {
+                            mbar_wait(bar0 + (uint32_t)offsetof(HaloTail, b_full) + 8u * bs, bph);
+                            tc_fence_after();
+                            b_lo = b0 + bs * (B_BYTES >> 4);
                         }
+                        const uint64_t adesc = desc_hi | (uint64_t)((a_base + (uint32_t)off) & 0x3FFFu);
+                        const uint64_t bdesc = desc_hi | (uint64_t)(b_lo & 0x3FFFu);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc | (uint32_t)k);
+                            if (!hg.b_resident) umma_commit(bar0 + (uint32_t)offsetof(HaloTail, b_empty) + 8u * bs);
+                        }
+                        acc = 1;
+                        if (!hg.b_resident && ++bs == SB) { bs = 0; bph ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++tx == d.Tw) { tx = 0; ++ty; }
                 }
+                if (elect_one()) {
+                    umma_commit(bar0 + (uint32_t)offsetof(HaloTail, a_empty) + 8u * ab);
+                    if (cc == cpb - 1) umma_commit(bar0 + (uint32_t)offsetof(HaloTail, tmem_full) + 8u * buf);
+                }
+                if (++ab == NA) { ab = 0; aph ^= 1u; }
             }
         }
     }
@@ -934,7 +970,7 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(const __grid_constan
     PixInfo* pix = reinterpret_cast<PixInfo*>(tail + 1);   // [STAGES][64]
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = uniform(tid >> 5), lane = tid & 31;
     const int64_t Q = (int64_t)d.B * d.Qh * d.Qw;
     const int ctiles = (d.Cin + BNW - 1) / BNW;
     const int tap = blockIdx.y / ctiles;
@@ -1068,50 +1104,69 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(const __grid_constan
         }
     } else if (warp == 4) {
         // ===================== TMA producer (im2col maps of dY and of the gathered activation) =====================
-        if (WTMA && lane == 0) {
+        // warp-uniform; one elected lane issues the TMA requests; pixel coordinates advance incrementally
+        if (WTMA) {
             const uint16_t ow = (uint16_t)(d.tap_sx > 0 ? txx : d.Tw - 1 - txx);
             const uint16_t oh = (uint16_t)(d.tap_sy > 0 ? tyy : d.Th - 1 - tyy);
             const int lw = d.tap_sx > 0 ? d.tap_ox : d.tap_ox - (d.Tw - 1);
             const int lh = d.tap_sy > 0 ? d.tap_oy : d.tap_oy - (d.Th - 1);
+            const uint32_t bar0 = smem_u32(tail);
+            const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b);
+            int qx = (int)(q_begin % d.Qw);
+            int qy = (int)((q_begin / d.Qw) % d.Qh);
+            int n = (int)(q_begin / ((int64_t)d.Qw * d.Qh));
+            uint32_t s = 0, ph = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
-                const uint32_t bar = smem_u32(&tail->full[s]);
-                mbar_arrive_expect_tx(bar, PA_BYTES + GB_BYTES);
-                const int64_t q = q_begin + (int64_t)kb * 64;
-                const int qx = (int)(q % d.Qw);
-                const int qy = (int)((q / d.Qw) % d.Qh);
-                const int n = (int)(q / ((int64_t)d.Qw * d.Qh));
-                const uint32_t a_dst = smem_u32(smem_a + s * PA_BYTES);
-                const int pw = qx * d.out_sx + d.out_ox, phh = qy * d.out_sy + d.out_oy;
-                tma_load_im2col_4d(a_dst, &tmap_p, m0, pw, phh, n, 0, 0, bar);
-                tma_load_im2col_4d(a_dst + 8192, &tmap_p, m0 + 64, pw, phh, n, 0, 0, bar);
-                const uint32_t b_dst = smem_u32(smem_b + s * GB_BYTES);
-                const int gw = qx * d.in_sx + lw, gh = qy * d.in_sy + lh;
-                tma_load_im2col_4d(b_dst, &tmap_g, c0, gw, gh, n, ow, oh, bar);
-                if (BNW == 128) tma_load_im2col_4d(b_dst + 8192, &tmap_g, c0 + 64, gw, gh, n, ow, oh, bar);
+                mbar_wait(bar0 + (uint32_t)offsetof(SmemTail, empty) + 8u * s, ph ^ 1u);
+                if (elect_one()) {
+                    const uint32_t bar = bar0 + (uint32_t)offsetof(SmemTail, full) + 8u * s;
+                    mbar_arrive_expect_tx(bar, PA_BYTES + GB_BYTES);
+                    const uint32_t a_dst = a0 + s * PA_BYTES;
+                    const int pw = qx * d.out_sx + d.out_ox, phh = qy * d.out_sy + d.out_oy;
+                    tma_load_im2col_4d(a_dst, &tmap_p, m0, pw, phh, n, 0, 0, bar);
+                    tma_load_im2col_4d(a_dst + 8192, &tmap_p, m0 + 64, pw, phh, n, 0, 0, bar);
+                    const uint32_t b_dst = b0 + s * GB_BYTES;
+                    const int gw = qx * d.in_sx + lw, gh = qy * d.in_sy + lh;
+                    tma_load_im2col_4d(b_dst, &tmap_g, c0, gw, gh, n, ow, oh, bar);
+                    if (BNW == 128) tma_load_im2col_4d(b_dst + 8192, &tmap_g, c0 + 64, gw, gh, n, ow, oh, bar);
+                }
+                // advance 64 pixels
+                qx += 64;
+                if (qx >= d.Qw) {
+                    const int cy = qx / d.Qw;
+                    qx -= cy * d.Qw;
+                    qy += cy;
+                    if (qy >= d.Qh) {
+                        const int cn = qy / d.Qh;
+                        qy -= cn * d.Qh;
+                        n += cn;
+                    }
+                }
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 5) {
+        // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
         constexpr uint32_t idesc = make_idesc(BNW, 1, 1);
+        // MN-major SWIZZLE_128B: LBO = stride between 64-element MN atoms (8192 B), SBO = stride between
+        // 8-row K groups (1024 B); each UMMA (K = 16 pixels) advances 16 rows = 2048 B
+        const uint64_t desc_hi = make_desc(0, 8192, 1024);
+        const uint32_t bar0 = smem_u32(tail);
+        const uint32_t a0 = smem_u32(smem_a) >> 4, b0 = smem_u32(smem_b) >> 4;
+        uint32_t s = 0, ph = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-            mbar_wait(smem_u32(&tail->full[s]), ph);
+            mbar_wait(bar0 + (uint32_t)offsetof(SmemTail, full) + 8u * s, ph);
             tc_fence_after();
-            if (lane == 0) {
-                // MN-major SWIZZLE_128B: LBO = stride between 64-element MN atoms (8192 B), SBO = stride between
-                // 8-row K groups (1024 B); each UMMA (K = 16 pixels) advances 16 rows = 2048 B
-                const uint64_t adesc = make_desc(smem_u32(smem_a + s * PA_BYTES), 8192, 1024);
-                const uint64_t bdesc = make_desc(smem_u32(smem_b + s * GB_BYTES), 8192, 1024);
+            const uint64_t adesc = desc_hi | (uint64_t)((a0 + s * (PA_BYTES >> 4)) & 0x3FFFu);
+            const uint64_t bdesc = desc_hi | (uint64_t)((b0 + s * (GB_BYTES >> 4)) & 0x3FFFu);
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
-                umma_commit(smem_u32(&tail->empty[s]));
-                if (kb == num_kb - 1) umma_commit(smem_u32(&tail->tmem_full));
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (uint32_t)(kb | k));
+                umma_commit(bar0 + (uint32_t)offsetof(SmemTail, empty) + 8u * s);
+                if (kb == num_kb - 1) umma_commit(bar0 + (uint32_t)offsetof(SmemTail, tmem_full));
             }
-            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
     }
     tc_fence_before();
@@ -1123,7 +1178,7 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(const __grid_constan
 // host side
 // ------------------------------------------------------------------------------------------------------------
 static int g_use_persist = 1;
-static int g_use_halo = 1;
+static int g_use_halo = 0;     // measured slower than the persistent im2col kernel on every step shape (profiles/r01e_bench_conv.md)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
