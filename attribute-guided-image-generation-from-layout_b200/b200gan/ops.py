@@ -186,6 +186,59 @@ def _scale_rows(scale, rows: int) -> int:
     return rows // scale.numel()
 
 
+def _packed_ok(g: ConvGeom) -> bool:
+    """few-channel inputs (the 3-channel image / crop convolutions) reach the tcgen05 GEMMs through an explicit bf16
+    im2col matrix: K = Cx*kh*kw per output pixel, zero padded to a multiple of 64"""
+    return (_PRECISION == "bf16" and g.Cx < 16 and g.Cy % 64 == 0 and g.cx_offset == 0 and g.cx_total == g.Cx
+            and _rup(g.Cx * g.kh * g.kw, 64) <= 256)
+
+
+def im2col_pack(g: ConvGeom, x, x_layout):
+    """(N*Hy*Wy, Kp) bf16 im2col matrix of x; column (ky*kw+kx)*Cx + c — the column order of _pack_fwd"""
+    N, Hx, Wx, Cx, xs = _dims(x, x_layout)
+    assert Cx == g.Cx
+    Hy, Wy = g.out_hw(Hx, Wx)
+    Kp = _rup(g.Cx * g.kh * g.kw, 64)
+    return _lib.K.im2col_pack(x.contiguous(), xs, N, Hx, Wx, Cx, g.kh, g.kw, g.s, g.p, Hy, Wy, Kp)
+
+
+def conv_forward_packed(g: ConvGeom, packs: WeightPacks, w, P, N, Hy, Wy, out_layout, bias=None, scale=None, relu=False,
+                        out_dtype=torch.bfloat16):
+    """Y = epilogue(P @ Wmat^T): the convolution as a 1x1 tcgen05 gather-GEMM over the im2col matrix P"""
+    Kp = P.shape[1]
+    wmat, ldw = packs.get(("fwd", True) + g.key(), w, lambda: _pack_fwd(g, w, True))
+    assert ldw == Kp
+    y, ys = _empty(N, Hy, Wy, g.Cy, out_layout, P.device, out_dtype)
+    xs = cl_strides(Hy, Wy, Kp)
+    d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=Kp, Cout=g.Cy, Th=1, Tw=1, in_sy=1, in_sx=1, tap_sy=1, tap_sx=1, tap_oy=0,
+                 tap_ox=0, Hi=Hy, Wi=Wy, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3], out_sy=1, out_sx=1,
+                 out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ys[0], out_sh=ys[1], out_sw=ys[2], out_sc=ys[3], ldw=ldw,
+                 relu=int(relu), scale_rows=_scale_rows(scale, N * Hy * Wy))
+    _lib.K.conv_gemm(d, P, wmat, bias, scale, y, True)
+    return y
+
+
+def conv_wgrad_packed(g: ConvGeom, P, N, Hy, Wy, dy, dy_layout, dw: torch.Tensor):
+    """dW = dY^T @ P on the tcgen05 weight-gradient kernel (T = 1, Kp "channels"), unpacked into the parameter layout"""
+    Kp = P.shape[1]
+    _, _, _, Cy, ds = _dims(dy, dy_layout)
+    assert Cy == g.Cy and dy.dtype == torch.bfloat16
+    g1 = ConvGeom(Kp, g.Cy, 1, 1, 1, 0)
+    Q = N * Hy * Wy
+    splits = _wgrad_splits(g1, Q, True)
+    ws = torch.empty((splits * g.Cy * Kp,), dtype=torch.float32, device=P.device)
+    xs = cl_strides(Hy, Wy, Kp)
+    d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=Kp, Cout=g.Cy, Th=1, Tw=1, in_sy=1, in_sx=1, tap_sy=1, tap_sx=1, tap_oy=0,
+                 tap_ox=0, Hi=Hy, Wi=Wy, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3], out_sy=1, out_sx=1,
+                 out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ds[0], out_sh=ds[1], out_sw=ds[2], out_sc=ds[3], ldw=Kp, relu=0)
+    _lib.K.wgrad_gemm(d, dy, P, ws, splits, True)
+    tmp = torch.empty((g.Cy, Kp), dtype=torch.float32, device=P.device)
+    _lib.K.wgrad_reduce(ws, splits, g.Cy, 1, 1, Kp, tmp, 0, Kp, 0, 0, 1)
+    K = g.kh * g.kw * g.Cx
+    dw.copy_(tmp[:, :K].view(g.Cy, g.kh, g.kw, g.Cx).permute(0, 3, 1, 2))
+    return dw
+
+
 def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bias=None, scale=None, relu=False,
                  out_dtype=None):
     """Y = epilogue(conv(X, W)); the tcgen05 path takes a bf16 activation (cast here if it is not), the fp32 path either"""
@@ -377,7 +430,16 @@ class _ConvFn(torch.autograd.Function):
         else:
             fwd_tc, wgrad_tc = _tc_dgrad_ok(g, x_layout), _tc_wgrad_ok(g, out_layout, x_layout)
         x_op = as_bf16(x) if fwd_tc else x      # cast once; the bf16 copy is also what a tcgen05 weight gradient consumes
-        if not transposed:
+        ctx.packed = (not transposed) and _packed_ok(g) and out_layout == "cl"
+        if ctx.packed:
+            # few-channel input: explicit bf16 im2col matrix, kept for the weight gradient
+            N, Hx, Wx, _, _ = _dims(x, x_layout)
+            Hy, Wy = g.out_hw(Hx, Wx)
+            x_op = im2col_pack(g, x, x_layout)
+            ctx.y_dims = (N, Hy, Wy)
+            y = conv_forward_packed(g, packs, w, x_op, N, Hy, Wy, out_layout, bias, scale, relu,
+                                    _out_dtype(x, x_layout, out_dtype))
+        elif not transposed:
             y = conv_forward(g, packs, w, x_op, x_layout, out_layout, bias, scale, relu, _out_dtype(x, x_layout, out_dtype))
         else:
             assert bias is None and not relu
@@ -386,7 +448,7 @@ class _ConvFn(torch.autograd.Function):
         ctx.x_layout, ctx.out_layout, ctx.relu = x_layout, out_layout, relu
         ctx.has_bias = bias is not None
         ctx.x_dims = _dims(x, x_layout)[:4]
-        ctx.save_for_backward(x_op if (fwd_tc and wgrad_tc) else x, w, y if relu else None)
+        ctx.save_for_backward(x_op if ((fwd_tc and wgrad_tc) or ctx.packed) else x, w, y if relu else None)
         return y
 
     @staticmethod
@@ -403,7 +465,8 @@ class _ConvFn(torch.autograd.Function):
             dgrad_tc, wgrad_tc = _tc_dgrad_ok(g, ctx.out_layout), _tc_wgrad_ok(g, ctx.x_layout, ctx.out_layout)
         else:
             dgrad_tc, wgrad_tc = _tc_fwd_ok(g, ctx.out_layout), _tc_wgrad_ok(g, ctx.out_layout, ctx.x_layout)
-        dyb = as_bf16(dy) if ((need_dx and dgrad_tc) or (need_dw and wgrad_tc)) else None   # one cast for both GEMMs
+        packed = ctx.packed
+        dyb = as_bf16(dy) if ((need_dx and dgrad_tc) or (need_dw and (wgrad_tc or packed))) else None   # one cast for both GEMMs
         if need_dx:
             dy_op = dyb if dgrad_tc else dy
             if not ctx.transposed:
@@ -413,8 +476,21 @@ class _ConvFn(torch.autograd.Function):
                 dx = conv_forward(g, packs, w, dy_op, ctx.out_layout, ctx.x_layout, None, scale, False, ctx.x_dtype)
         if need_dw:
             gw = torch.empty_like(w)
-            dy_op = dyb if wgrad_tc else dy
-            if sn is None:
+            dy_op = dyb if (wgrad_tc or packed) else dy
+            if packed:
+                N, Hy, Wy = ctx.y_dims
+                if sn is None:
+                    dw = conv_wgrad_packed(g, x, N, Hy, Wy, dy_op, ctx.out_layout, gw)
+                else:
+                    n = N // sn.groups
+                    rows = n * Hy * Wy
+                    h, wd = w.shape[0], w[0].numel()
+                    dw = torch.empty_like(w)
+                    for gi in range(sn.groups):
+                        conv_wgrad_packed(g, x[gi * rows:(gi + 1) * rows], n, Hy, Wy, dy_op[gi * n:(gi + 1) * n],
+                                          ctx.out_layout, gw)
+                        _lib.K.sn_grad(gw, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
+            elif sn is None:
                 if not ctx.transposed:
                     conv_wgrad(g, x, ctx.x_layout, dy_op, ctx.out_layout, gw)
                 else:

@@ -350,6 +350,60 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// im2col packing of a FEW-channel convolution input (the 3-channel image / crop convolutions): row m = output pixel
+// (n, qy, qx), column k = (ky*kw + kx)*Cx + c, bf16, zero padded to Kp (a multiple of 64).  The packed matrix is the
+// channel-last activation of an equivalent 1x1 convolution with Kp input channels, which runs on the tcgen05
+// gather-GEMMs (forward and weight gradient) — K = Cx*kh*kw is far too small per tap to feed them directly.
+// blockDim = (Kp/8, rows per block): a thread owns 8 consecutive columns (fixed taps), 16-byte stores.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_pack_kernel(const T* __restrict__ x, int64_t M, int Hx, int Wx, int Cx, int64_t sn, int64_t sh,
+                                   int64_t sw, int64_t sc, int kh, int kw, int stride, int pad, int Hy, int Wy, int Kp,
+                                   bf16* __restrict__ out) {
+    const int kg = threadIdx.x;
+    int64_t off[8];
+    int dy[8], dx[8];
+    const int K = Cx * kh * kw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = kg * 8 + j;
+        if (k < K) {
+            const int tap = k / Cx, c = k - tap * Cx;
+            const int ky = tap / kw, kx = tap - ky * kw;
+            dy[j] = ky - pad;
+            dx[j] = kx - pad;
+            off[j] = (int64_t)c * sc;
+        } else {
+            dy[j] = -(1 << 28);          // always out of bounds -> zero
+            dx[j] = 0;
+            off[j] = 0;
+        }
+    }
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; m < M; m += (int64_t)gridDim.x * blockDim.y) {
+        const int mi = (int)m;
+        const int qx = mi % Wy;
+        const int t = mi / Wy;
+        const int qy = t % Hy;
+        const int n = t / Hy;
+        const T* xb = x + (int64_t)n * sn;
+        const int iy0 = qy * stride, ix0 = qx * stride;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int iy = iy0 + dy[j], ix = ix0 + dx[j];
+            const bool ok = iy >= 0 && iy < Hx && ix >= 0 && ix < Wx;
+            v[j] = ok ? ldf(xb + off[j] + (int64_t)iy * sh + (int64_t)ix * sw) : 0.f;
+        }
+        uint4 u;
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]),
+                       c2 = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+        u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+        u.z = *reinterpret_cast<uint32_t*>(&c2); u.w = *reinterpret_cast<uint32_t*>(&d);
+        *reinterpret_cast<uint4*>(out + m * Kp + kg * 8) = u;
+    }
+}
+
 // y[b][c][r] = x[b][r][c]  (batched R x C -> C x R transpose; NCHW <-> channel-last)
 __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
     __shared__ float tile[32][33];
@@ -597,6 +651,25 @@ extern "C" int b200_wgrad_reduce(const float* ws, int splits, int64_t split_stri
     if (total == 0) return 0;
     wgrad_reduce_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(ws, splits, split_stride, M, Th, Tw, C, dst,
                                                                              s_m, s_ty, s_tx, s_c, scale, accumulate);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_im2col_pack(const void* x, int x_dt, int64_t N, int Hx, int Wx, int Cx, int64_t sn, int64_t sh,
+                                int64_t sw, int64_t sc, int kh, int kw, int stride, int pad, int Hy, int Wy, int Kp,
+                                void* out_bf16, b200_stream_t stream) {
+    const int64_t M = N * Hy * Wy;
+    if (M == 0) return 0;
+    B200_REQUIRE(Kp % 64 == 0 && Kp >= Cx * kh * kw && Kp <= 2048, "im2col_pack: Kp=%d must be a multiple of 64 covering K=%d", Kp, Cx * kh * kw);
+    B200_REQUIRE(M < (1ll << 31), "im2col_pack: too many output pixels");
+    const int G = Kp / 8;
+    const int rows = 256 / G > 0 ? 256 / G : 1;
+    dim3 block(G, rows);
+    const int grid = grid_for((M + rows - 1) / rows, 1, 16);
+    B200_DISPATCH_DT(x_dt, T, {
+        im2col_pack_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, M, Hx, Wx, Cx, sn, sh, sw, sc, kh, kw, stride,
+                                                                  pad, Hy, Wy, Kp, (bf16*)out_bf16);
+    });
     B200_CHECK_LAUNCH();
     return 0;
 }

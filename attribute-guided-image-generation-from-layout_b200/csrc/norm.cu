@@ -8,6 +8,57 @@
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------------------------
+// 16-byte vector access: V = 4 fp32 or 8 bf16 consecutive channels per thread
+// ---------------------------------------------------------------------------------------------------------
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+    static constexpr int V = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct VecIO<bf16> {
+    static constexpr int V = 8;
+    static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {            // bf16 -> fp32 is a 16-bit shift
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+        uint4 q;
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]),
+                       c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+        q.x = *reinterpret_cast<uint32_t*>(&a); q.y = *reinterpret_cast<uint32_t*>(&b);
+        q.z = *reinterpret_cast<uint32_t*>(&c); q.w = *reinterpret_cast<uint32_t*>(&d);
+        *reinterpret_cast<uint4*>(p) = q;
+    }
+};
+template <int V>
+__device__ __forceinline__ void ldp(const float* p, float (&v)[V]) {       // V fp32 parameters (16-byte aligned)
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(p + i);
+        v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+    }
+}
+// the vector kernels take layouts where a 256-thread block covers whole rows: C/V threads per row, a power of two <= 256
+template <typename T>
+static inline bool vec_ok(int64_t rows, int C) {
+    constexpr int V = VecIO<T>::V;
+    if (C % V != 0 || rows >= (1ll << 31)) return false;
+    const int tpr = C / V;
+    return tpr >= 1 && tpr <= 256 && (tpr & (tpr - 1)) == 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // statistics.  `groups` independent calls batched along the row dimension (rows = groups * rows_per_group) keep
 // separate statistics: grid.z = group, chunks never straddle a group.
 // ---------------------------------------------------------------------------------------------------------
@@ -124,6 +175,74 @@ __global__ void norm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int6
     }
 }
 
+// vector variant: a thread owns V consecutive channels (16 bytes) of a fixed channel slot and walks rows; no 64-bit
+// divisions, per-row parameters (group statistics, CBN table row) resolved once per row
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) norm_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int rows, int C,
+                                                          const float* __restrict__ mean,
+                                                          const float* __restrict__ var, float eps,
+                                                          const void* __restrict__ gamma_v,
+                                                          const float* __restrict__ beta,
+                                                          const int32_t* __restrict__ idx, int rows_per_seg,
+                                                          const T* __restrict__ residual, int relu,
+                                                          int rows_per_group) {
+    constexpr int V = VecIO<T>::V;
+    const float* gamma = reinterpret_cast<const float*>(gamma_v);
+    const T* gb = reinterpret_cast<const T*>(gamma_v);
+    const int tpr = C / V;
+    const int c = (threadIdx.x % tpr) * V;
+    const int rpb = blockDim.x / tpr;
+    float ga[V], be[V];
+    if (MODE == B200_NORM_AFFINE) { ldp<V>(gamma + c, ga); ldp<V>(beta + c, be); }
+    int g_cur = -1;
+    float m[V], rs[V];
+#pragma unroll 2
+    for (int r = blockIdx.x * rpb + threadIdx.x / tpr; r < rows; r += gridDim.x * rpb) {
+        const int64_t o = (int64_t)r * C + c;
+        float v[V];
+        VecIO<T>::load(x + o, v);
+        const int g = r / rows_per_group;
+        if (g != g_cur) {
+            g_cur = g;
+            float vv[V];
+            ldp<V>(mean + (int64_t)g * C + c, m);
+            ldp<V>(var + (int64_t)g * C + c, vv);
+#pragma unroll
+            for (int e = 0; e < V; ++e) rs[e] = 1.f / sqrtf(vv[e] + eps);
+        }
+        float out[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) out[e] = (v[e] - m[e]) * rs[e];
+        if (MODE == B200_NORM_AFFINE) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) out[e] = out[e] * ga[e] + be[e];
+        } else if (MODE == B200_NORM_CBN) {
+            const float* row = gamma + (int64_t)idx[r / rows_per_seg] * 2 * C;
+            ldp<V>(row + c, ga);
+            ldp<V>(row + C + c, be);
+#pragma unroll
+            for (int e = 0; e < V; ++e) out[e] = ga[e] * out[e] + be[e];
+        } else if (MODE == B200_NORM_SPADE) {
+            const T* row = gb + (int64_t)r * 2 * C;
+            VecIO<T>::load(row + c, ga);
+            VecIO<T>::load(row + C + c, be);
+#pragma unroll
+            for (int e = 0; e < V; ++e) out[e] = out[e] * (1.f + ga[e]) + be[e];
+        }
+        if (residual) {
+            float q[V];
+            VecIO<T>::load(residual + o, q);
+#pragma unroll
+            for (int e = 0; e < V; ++e) out[e] += q[e];
+        }
+        if (relu) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) out[e] = fmaxf(out[e], 0.f);
+        }
+        VecIO<T>::store(y + o, out);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // backward stage 1: per-segment sums
 // ---------------------------------------------------------------------------------------------------------
@@ -161,6 +280,132 @@ __global__ void norm_bwd_reduce_kernel(const T* __restrict__ dy, const T* __rest
         seg_sums[((int64_t)blockIdx.x * C + c) * 2 + 0] = t1;
         seg_sums[((int64_t)blockIdx.x * C + c) * 2 + 1] = t2;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// vector reductions over rows (statistics, backward segment sums): a block covers CT*V channels (CT = channel
+// threads, a power of two <= 16) x 256/CT rows per pass; per-thread fp64 accumulation, then a fixed-order tree:
+// lanes of a warp that share a channel slot (shuffle), then the 8 warps (shared memory).  Deterministic.
+// ---------------------------------------------------------------------------------------------------------
+template <int V>
+__device__ __forceinline__ void block_reduce_rows(double (&s1)[V], double (&s2)[V], int ct, double* sm /* [8][16*V*2] */,
+                                                  double* out1, double* out2, int64_t stride, bool valid) {
+    // lanes l and l ^ o with o >= ct hold the same channel slot, different rows
+    for (int o = 16; o >= ct; o >>= 1) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+            s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < ct) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            sm[(warp * 16 + lane) * V * 2 + e * 2] = s1[e];
+            sm[(warp * 16 + lane) * V * 2 + e * 2 + 1] = s2[e];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < ct * V && valid) {
+        const int slot = threadIdx.x / V, e = threadIdx.x % V;
+        double t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            t1 += sm[(w * 16 + slot) * V * 2 + e * 2];
+            t2 += sm[(w * 16 + slot) * V * 2 + e * 2 + 1];
+        }
+        out1[(int64_t)threadIdx.x * stride] = t1;
+        out2[(int64_t)threadIdx.x * stride] = t2;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_partial_vec_kernel(const T* __restrict__ x, int64_t rows_per_group, int C,
+                                                                  int64_t rows_per_chunk, int ct,
+                                                                  double* __restrict__ ws) {
+    constexpr int V = VecIO<T>::V;
+    __shared__ double sm[8 * 16 * V * 2];
+    const int c0 = blockIdx.y * ct * V;
+    const int c = c0 + (threadIdx.x % ct) * V;
+    const int rstep = 256 / ct;
+    const int64_t g0 = (int64_t)blockIdx.z * rows_per_group;
+    const int64_t a = g0 + (int64_t)blockIdx.x * rows_per_chunk;
+    const int64_t e = g0 + rows_per_group;
+    const int64_t b = a + rows_per_chunk < e ? a + rows_per_chunk : e;
+    double s1[V], s2[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.0;
+#pragma unroll 2
+    for (int64_t r = a + threadIdx.x / ct; r < b; r += rstep) {
+        float v[V];
+        VecIO<T>::load(x + r * C + c, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const double d = (double)v[i];
+            s1[i] += d;
+            s2[i] += d * d;
+        }
+    }
+    const int64_t chunk = (int64_t)blockIdx.z * gridDim.x + blockIdx.x;
+    double* o = ws + (chunk * C + c0) * 2;
+    block_reduce_rows<V>(s1, s2, ct, sm, o, o + 1, 2, true);
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) norm_bwd_reduce_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                 const T* __restrict__ y, int C,
+                                                                 const float* __restrict__ mean,
+                                                                 const float* __restrict__ var, float eps,
+                                                                 const void* __restrict__ gamma, int rows_per_seg,
+                                                                 int relu, double* __restrict__ seg_sums,
+                                                                 int64_t rows_per_group, int segs_per_group, int ct) {
+    constexpr int V = VecIO<T>::V;
+    __shared__ double sm[8 * 16 * V * 2];
+    const int c0 = blockIdx.y * ct * V;
+    const int c = c0 + (threadIdx.x % ct) * V;
+    const int rstep = 256 / ct;
+    const int g = blockIdx.x / segs_per_group;
+    const int64_t gend = (int64_t)(g + 1) * rows_per_group;
+    const int64_t a = (int64_t)g * rows_per_group + (int64_t)(blockIdx.x - g * segs_per_group) * rows_per_seg;
+    const int64_t b = a + rows_per_seg < gend ? a + rows_per_seg : gend;
+    float m[V], rs[V];
+    {
+        float vv[V];
+        ldp<V>(mean + (int64_t)g * C + c, m);
+        ldp<V>(var + (int64_t)g * C + c, vv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) rs[i] = 1.f / sqrtf(vv[i] + eps);
+    }
+    double s1[V], s2[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.0;
+#pragma unroll 2
+    for (int64_t r = a + threadIdx.x / ct; r < b; r += rstep) {
+        float gv[V], xv[V];
+        VecIO<T>::load(dy + r * C + c, gv);
+        VecIO<T>::load(x + r * C + c, xv);
+        if (relu) {
+            float yv[V];
+            VecIO<T>::load(y + r * C + c, yv);
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                if (!(yv[i] > 0.f)) gv[i] = 0.f;
+        }
+        if (MODE == B200_NORM_SPADE) {
+            float q[V];
+            VecIO<T>::load(reinterpret_cast<const T*>(gamma) + r * 2 * C + c, q);
+#pragma unroll
+            for (int i = 0; i < V; ++i) gv[i] *= 1.f + q[i];
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float xh = (xv[i] - m[i]) * rs[i];
+            s1[i] += (double)gv[i];
+            s2[i] += (double)gv[i] * (double)xh;
+        }
+    }
+    double* o = seg_sums + ((int64_t)blockIdx.x * C + c0) * 2;
+    block_reduce_rows<V>(s1, s2, ct, sm, o, o + 1, 2, true);
 }
 
 // stage 2: s[g][c] = (sum dxhat, sum dxhat*xhat) per group; parameter gradients summed over the groups.
@@ -281,6 +526,80 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ dy, const T* __restr
     }
 }
 
+
+// stage 3, vector variant (V channels of a fixed slot per thread, rows walked; see norm_fwd_vec_kernel)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) norm_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                const T* __restrict__ y, T* __restrict__ dx, int rows,
+                                                                int C, const float* __restrict__ mean,
+                                                                const float* __restrict__ var, float eps,
+                                                                const void* __restrict__ gamma_v,
+                                                                const int32_t* __restrict__ idx, int rows_per_seg,
+                                                                int relu, const float* __restrict__ s,
+                                                                T* __restrict__ dgb, int rows_per_group) {
+    constexpr int V = VecIO<T>::V;
+    const float* gamma = reinterpret_cast<const float*>(gamma_v);
+    const int tpr = C / V;
+    const int c = (threadIdx.x % tpr) * V;
+    const int rpb = blockDim.x / tpr;
+    const float inv_rows = 1.f / (float)rows_per_group;
+    float ga[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) ga[e] = 1.f;
+    if (MODE == B200_NORM_AFFINE) ldp<V>(gamma + c, ga);
+    int g_cur = -1;
+    float m[V], rs[V], sa[V], sb[V];
+#pragma unroll 2
+    for (int r = blockIdx.x * rpb + threadIdx.x / tpr; r < rows; r += gridDim.x * rpb) {
+        const int64_t o = (int64_t)r * C + c;
+        float g[V], xv[V];
+        VecIO<T>::load(dy + o, g);
+        VecIO<T>::load(x + o, xv);
+        if (relu) {
+            float yv[V];
+            VecIO<T>::load(y + o, yv);
+#pragma unroll
+            for (int e = 0; e < V; ++e)
+                if (!(yv[e] > 0.f)) g[e] = 0.f;
+        }
+        const int grp = r / rows_per_group;
+        if (grp != g_cur) {
+            g_cur = grp;
+            float vv[V], s2[2 * V];
+            ldp<V>(mean + (int64_t)grp * C + c, m);
+            ldp<V>(var + (int64_t)grp * C + c, vv);
+            ldp<2 * V>(s + ((int64_t)grp * C + c) * 2, s2);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                rs[e] = 1.f / sqrtf(vv[e] + eps);
+                sa[e] = s2[2 * e] * inv_rows;
+                sb[e] = s2[2 * e + 1] * inv_rows;
+            }
+        }
+        if (MODE == B200_NORM_CBN) {
+            ldp<V>(gamma + (int64_t)idx[r / rows_per_seg] * 2 * C + c, ga);
+        } else if (MODE == B200_NORM_SPADE) {
+            float q[V];
+            VecIO<T>::load(reinterpret_cast<const T*>(gamma_v) + (int64_t)r * 2 * C + c, q);
+#pragma unroll
+            for (int e = 0; e < V; ++e) ga[e] = 1.f + q[e];
+        }
+        float out[V], gx[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const float xh = (xv[e] - m[e]) * rs[e];
+            const float dxh = g[e] * ga[e];
+            gx[e] = g[e] * xh;
+            out[e] = rs[e] * (dxh - sa[e] - xh * sb[e]);
+        }
+        if (MODE == B200_NORM_SPADE) {
+            VecIO<T>::store(dgb + (int64_t)r * 2 * C + c, gx);
+            VecIO<T>::store(dgb + (int64_t)r * 2 * C + C + c, g);
+        }
+        VecIO<T>::store(dx + o, out);
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -294,7 +613,15 @@ extern "C" int b200_bn_stats(const void* x, int dt, int64_t rows, int C, int gro
     int nchunks = b200_bn_chunks(rpg, C);
     int64_t rpc = (rpg + nchunks - 1) / nchunks;
     dim3 grid(nchunks, (C + 31) / 32, groups), block(32, 8);
-    B200_DISPATCH_DT(dt, T, { bn_stats_partial_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, rpg, C, rpc, ws); });
+    B200_DISPATCH_DT(dt, T, {
+        if (vec_ok<T>(rows, C)) {
+            const int tpr = C / VecIO<T>::V, ct = tpr < 16 ? tpr : 16;
+            dim3 vgrid(nchunks, tpr / ct, groups);
+            bn_stats_partial_vec_kernel<T><<<vgrid, 256, 0, as_stream(stream)>>>((const T*)x, rpg, C, rpc, ct, ws);
+        } else {
+            bn_stats_partial_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, rpg, C, rpc, ws);
+        }
+    });
     B200_CHECK_LAUNCH();
     bn_stats_final_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, nchunks, C, groups, rpg, mean, var, running_mean,
                                                                       running_var, momentum);
@@ -306,10 +633,32 @@ template <typename T>
 static int norm_fwd_launch(const void* x, void* y, int64_t rows, int C, int64_t rpg, const float* mean, const float* var,
                            float eps, int mode, const void* gamma, const float* beta, const int32_t* idx, int rows_per_seg,
                            const void* residual, int relu, cudaStream_t st) {
-    const int g = grid_for(rows * (C / 4), 256);
     const T* xp = (const T*)x;
     T* yp = (T*)y;
     const T* rp = (const T*)residual;
+    if (vec_ok<T>(rows, C) && rpg < (1ll << 31)) {
+        const int rpb = 256 / (C / VecIO<T>::V);
+        const int vg = grid_for((rows + rpb - 1) / rpb, 1, 8);
+        const int ri = (int)rows, gi = (int)rpg;
+        switch (mode) {
+            case B200_NORM_PLAIN:
+                norm_fwd_vec_kernel<T, B200_NORM_PLAIN><<<vg, 256, 0, st>>>(xp, yp, ri, C, mean, var, eps, gamma, beta, idx, rows_per_seg, rp, relu, gi);
+                break;
+            case B200_NORM_AFFINE:
+                norm_fwd_vec_kernel<T, B200_NORM_AFFINE><<<vg, 256, 0, st>>>(xp, yp, ri, C, mean, var, eps, gamma, beta, idx, rows_per_seg, rp, relu, gi);
+                break;
+            case B200_NORM_CBN:
+                norm_fwd_vec_kernel<T, B200_NORM_CBN><<<vg, 256, 0, st>>>(xp, yp, ri, C, mean, var, eps, gamma, beta, idx, rows_per_seg, rp, relu, gi);
+                break;
+            case B200_NORM_SPADE:
+                norm_fwd_vec_kernel<T, B200_NORM_SPADE><<<vg, 256, 0, st>>>(xp, yp, ri, C, mean, var, eps, gamma, beta, idx, rows_per_seg, rp, relu, gi);
+                break;
+            default:
+                return set_error("norm_fwd: bad mode %d", mode);
+        }
+        return 0;
+    }
+    const int g = grid_for(rows * (C / 4), 256);
     switch (mode) {
         case B200_NORM_PLAIN:
             norm_fwd_kernel<T, B200_NORM_PLAIN><<<g, 256, 0, st>>>(xp, yp, rows, C, mean, var, eps, gamma, beta, idx, rows_per_seg, rp, relu, rpg);
@@ -356,6 +705,14 @@ extern "C" int b200_norm_bwd_reduce(const void* dy, const void* x, const void* y
     dim3 grid(spg * groups, (C + 31) / 32), block(32, 8);
     cudaStream_t st = as_stream(stream);
     B200_DISPATCH_DT(dt, T, {
+        if (vec_ok<T>(rows, C)) {
+            const int tpr = C / VecIO<T>::V, ct = tpr < 16 ? tpr : 16;
+            dim3 vgrid(spg * groups, tpr / ct);
+            if (mode == B200_NORM_SPADE)
+                norm_bwd_reduce_vec_kernel<T, B200_NORM_SPADE><<<vgrid, 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg, ct);
+            else
+                norm_bwd_reduce_vec_kernel<T, B200_NORM_PLAIN><<<vgrid, 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg, ct);
+        } else
         if (mode == B200_NORM_SPADE)
             norm_bwd_reduce_kernel<T, B200_NORM_SPADE><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg);
         else
@@ -384,9 +741,32 @@ static int norm_bwd_apply_launch(const void* dy, const void* x, const void* y, v
                                  const float* mean, const float* var, float eps, int mode, const void* gamma,
                                  const int32_t* idx, int rows_per_seg, int relu, const float* s, void* dgb,
                                  cudaStream_t st) {
-    const int g = grid_for(rows * (C / 4), 256);
     const T *dyp = (const T*)dy, *xp = (const T*)x, *yp = (const T*)y;
     T *dxp = (T*)dx, *dgbp = (T*)dgb;
+    if (vec_ok<T>(rows, C) && rpg < (1ll << 31)) {
+        const int rpb = 256 / (C / VecIO<T>::V);
+        const int vg = grid_for((rows + rpb - 1) / rpb, 1, 8);
+        const int ri = (int)rows, gi = (int)rpg;
+        switch (mode) {
+            case B200_NORM_PLAIN:
+                norm_bwd_apply_vec_kernel<T, B200_NORM_PLAIN><<<vg, 256, 0, st>>>(dyp, xp, yp, dxp, ri, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgbp, gi);
+                break;
+            case B200_NORM_AFFINE:
+                norm_bwd_apply_vec_kernel<T, B200_NORM_AFFINE><<<vg, 256, 0, st>>>(dyp, xp, yp, dxp, ri, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgbp, gi);
+                break;
+            case B200_NORM_CBN:
+                norm_bwd_apply_vec_kernel<T, B200_NORM_CBN><<<vg, 256, 0, st>>>(dyp, xp, yp, dxp, ri, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgbp, gi);
+                break;
+            case B200_NORM_SPADE:
+                if (dgb == nullptr) return set_error("norm_bwd_apply: SPADE needs dgb");
+                norm_bwd_apply_vec_kernel<T, B200_NORM_SPADE><<<vg, 256, 0, st>>>(dyp, xp, yp, dxp, ri, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgbp, gi);
+                break;
+            default:
+                return set_error("norm_bwd_apply: bad mode %d", mode);
+        }
+        return 0;
+    }
+    const int g = grid_for(rows * (C / 4), 256);
     switch (mode) {
         case B200_NORM_PLAIN:
             norm_bwd_apply_kernel<T, B200_NORM_PLAIN><<<g, 256, 0, st>>>(dyp, xp, yp, dxp, rows, C, mean, var, eps, gamma, idx, rows_per_seg, relu, s, dgbp, rpg);

@@ -188,10 +188,9 @@ def run_b200(args):
     n_obj = n_img * OBJS_PER_IMAGE
 
     torch.manual_seed(1234)
-    ts = TrainStep(args.size, device=dev, capturable=(not args.no_graph) and world == 1)
+    ts = TrainStep(args.size, device=dev, capturable=not args.no_graph)
     if world > 1:
-        ts.enable_data_parallel()
-        args.no_graph = True       # NCCL work is issued from autograd hooks; the multi-GPU step runs eagerly
+        ts.enable_data_parallel()  # the bucketed all-reduces issued from the autograd hooks are captured with the step
     torch.cuda.manual_seed(100 + rank)
     ts.netG.crop_encoder.eps_source = lambda o, z, d: torch.randn(o, z, device=d)
 
@@ -200,6 +199,12 @@ def run_b200(args):
     h2d_bytes = sum(v.numel() * v.element_size() for k, v in host.items() if k != "obj_to_img")
     b = ts.to_device(pinned)
     torch.cuda.synchronize()
+
+    t_start = time.time()
+
+    def note(msg):
+        if os.environ.get("B200_BENCH_VERBOSE", "1") != "0":
+            print("[bench r%d +%.1fs] %s" % (rank, time.time() - t_start, msg), file=sys.stderr, flush=True)
 
     def sync_all():
         if world > 1:
@@ -217,6 +222,7 @@ def run_b200(args):
     res = eager_step(b)
     torch.cuda.synchronize()
     launches_per_step = _lib.K.launch_count() - launches_before
+    note("eager warm-up done (%d launches/step)" % launches_per_step)
 
     graph = None
     static_out = None
@@ -232,7 +238,8 @@ def run_b200(args):
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: the NCCL watchdog thread may query events while the step (with its all-reduces) is captured
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
                 r = eager_step(b)
                 static_out = (r["d_loss"], r["g_loss"])
             ops.bump_weight_epoch()
@@ -245,6 +252,8 @@ def run_b200(args):
             graph = None
             ops.bump_weight_epoch()
             torch.cuda.synchronize()
+
+    note("graph captured" if graph is not None else "no graph: eager steps")
 
     def run_step():
         if graph is not None:
@@ -266,6 +275,7 @@ def run_b200(args):
     sync_all()
     ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    note("device-resident timing done: %.2f ms/step" % ms)
     assert all(torch.isfinite(l).all() for l in losses), "non-finite loss in the timed region"
 
     # ---- end-to-end timing: pinned host batch -> device every step, losses read back every step ----------------
@@ -283,6 +293,7 @@ def run_b200(args):
     f1.record()
     sync_all()
     ms_e2e = f0.elapsed_time(f1) / args.steps
+    note("end-to-end timing done: %.2f ms/step" % ms_e2e)
     assert torch.isfinite(host_losses).all()
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -294,6 +305,7 @@ def run_b200(args):
     roof = None
     if rank == 0:
         roof = kernel_roofline(ts, b, args)
+        note("kernel roofline done")
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -324,45 +336,61 @@ def run_b200(args):
 
 
 def kernel_roofline(ts, b, args):
-    """Time every launch of the dominant kernel family inside one eager step with CUDA events on the launching stream
-    and divide the algorithmic FLOPs of those launches (2*M*N*K of the convolution each launch computes) by the summed
-    duration.  Peak = MEASURED_PEAKS.json bf16 sustained figure (kernel timed inside a long step), else the
+    """Device time of every launch of the dominant kernel family (the tcgen05 gather-GEMMs) in one step, measured live
+    with CUDA events on the launching stream: each distinct launch (descriptor + kernel path) met during one eager step
+    is captured into a CUDA graph of R back-to-back launches on its real operands and replayed between two events, so
+    the figure is kernel time without host launch gaps (events around single eager launches measure the host).  The
+    algorithmic FLOPs of those launches (2*M*N*K of the convolution each computes) divided by the summed durations is
+    `achieved`.  Peak = MEASURED_PEAKS.json bf16 sustained figure (kernels timed inside a long step), else the
     B200_PROFILING.md fallback."""
     from b200gan import _lib, ops
-    K = _lib.K
     real = _lib._K if _lib._K is not None else None
     if real is None:
         return None
-    records = []
+    R = 4
+    records = []          # (tc, flops, ms per launch)
+    per_key = {}
     orig_conv, orig_wgrad = real.conv_gemm, real.wgrad_gemm
 
-    def flops_of(d, wgrad):
-        rows = d.B * d.Qh * d.Qw
-        return 2.0 * rows * d.Cout * d.Th * d.Tw * d.Cin
+    def flops_of(d):
+        return 2.0 * d.B * d.Qh * d.Qw * d.Cout * d.Th * d.Tw * d.Cin
 
     def timed(fn, wgrad):
         def wrapper(desc, *a, **kw):
-            tc = a[-1] if not kw else kw.get("tc", a[-1])
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            fn(desc, *a, **kw)
-            e.record()
-            records.append((bool(tc), wgrad, flops_of(desc, wgrad), s, e))
+            tc = bool(a[-1] if "tc" not in kw else kw["tc"])
+            fn(desc, *a, **kw)                                   # the step's own launch
+            key = (wgrad, tc, bytes(desc)) + tuple(int(x) for x in a if isinstance(x, int))
+            if key not in per_key:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(R):
+                        fn(desc, *a, **kw)
+                g.replay()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                g.replay()
+                e.record()
+                e.synchronize()
+                per_key[key] = s.elapsed_time(e) / R
+                del g
+            records.append((tc, flops_of(desc), per_key[key]))
         return wrapper
 
     real.conv_gemm = timed(orig_conv, False)
     real.wgrad_gemm = timed(orig_wgrad, True)
+    ddp = (ts.ddp_d, ts.ddp_g)
+    ts.ddp_d = ts.ddp_g = None        # rank 0 alone runs this step: no gradient exchange
     try:
         ops.bump_weight_epoch()
         ts.step(b, optimizer_step=False)
         torch.cuda.synchronize()
     finally:
         real.conv_gemm, real.wgrad_gemm = orig_conv, orig_wgrad
-    tc_t = sum(s.elapsed_time(e) for tc, _, _, s, e in records if tc) / 1e3
-    tc_f = sum(f for tc, _, f, _, _ in records if tc)
-    simt_t = sum(s.elapsed_time(e) for tc, _, _, s, e in records if not tc) / 1e3
-    simt_f = sum(f for tc, _, f, _, _ in records if not tc)
-    peak, src = 1390.5, "fallback"
+        ts.ddp_d, ts.ddp_g = ddp
+    tc_t = sum(t for tc, _, t in records if tc) / 1e3
+    tc_f = sum(f for tc, f, _ in records if tc)
+    simt_t = sum(t for tc, _, t in records if not tc) / 1e3
+    simt_f = sum(f for tc, f, _ in records if not tc)
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peak, src = float(mp["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
@@ -376,6 +404,8 @@ def kernel_roofline(ts, b, args):
         name = "conv_gemm_f32_kernel + wgrad_gemm_f32_kernel (fp32 CUDA-core gather-GEMMs)"
     return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "peak_source": src, "traffic": None, "launches": len([1 for r in records if r[0]]) if tc_t > 0 else len(records),
+            "distinct_launch_shapes": len(per_key),
+            "timing": "CUDA events around a graph of %d back-to-back launches per distinct launch shape" % R,
             "kernel_time_ms_per_step": (tc_t if tc_t > 0 else simt_t) * 1e3,
             "other_gemm_ms_per_step": (simt_t if tc_t > 0 else 0.0) * 1e3,
             "algorithmic_tflop_per_step": (tc_f if tc_t > 0 else simt_f) / 1e12}

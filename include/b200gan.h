@@ -229,6 +229,15 @@ int b200_reparam_bwd(const float* dz, const float* logvar, const float* eps, flo
                      int64_t n, b200_stream_t stream);
 /* out[c] = sum_rows x[row][c] (bias gradients), deterministic; ws: C*b200_bn_chunks(rows,C) doubles */
 int b200_colsum(const void* x, int64_t rows, int C, int dt, float* out, double* ws, b200_stream_t stream);
+/* im2col packing of a few-channel convolution input (the 3-channel image / crop convolutions; replaces the first
+ * conv of CropEncoder generator_obj_att.py:371, OptimizedBlock discriminator.py:29-60 in the tcgen05 precision mode):
+ * out[m][k] (bf16, row length Kp, a multiple of 64) = x[n, c, qy*stride + ky - pad, qx*stride + kx - pad] (0 outside the
+ * image) with m = (n*Hy + qy)*Wy + qx and k = (ky*kw + kx)*Cx + c; columns k >= Cx*kh*kw are zero.  x is addressed with
+ * element strides (sn, sh, sw, sc), storage type x_dt.  The result is the channel-last activation of an equivalent 1x1
+ * convolution with Kp input channels. */
+int b200_im2col_pack(const void* x, int x_dt, int64_t N, int Hx, int Wx, int Cx, int64_t sn, int64_t sh, int64_t sw,
+                     int64_t sc, int kh, int kw, int stride, int pad, int Hy, int Wy, int Kp, void* out_bf16,
+                     b200_stream_t stream);
 /* y[b][c][r] = x[b][r][c]: batched (R x C) transpose, i.e. NCHW <-> channel-last at module boundaries */
 int b200_transpose(const float* x, float* y, int B, int R, int C, b200_stream_t stream);
 /* row gather / scatter-overwrite for the time-major packing of ConvLSTM sequences: out[r] = x[src_row[r]] (rows of

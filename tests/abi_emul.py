@@ -129,6 +129,16 @@ class EmulKernels:
         self.launches += 1
         return x.to(torch.bfloat16)
 
+    def im2col_pack(self, x, x_strides, N, Hx, Wx, Cx, kh, kw, stride, pad, Hy, Wy, Kp):
+        self.launches += 1
+        sn, sh, sw, sc = x_strides
+        xv = torch.as_strided(x, (N, Cx, Hx, Wx), (sn, sc, sh, sw)).float()
+        cols = F.unfold(xv, (kh, kw), padding=pad, stride=stride)              # (N, Cx*kh*kw, Hy*Wy), row = c*kh*kw + tap
+        cols = cols.view(N, Cx, kh * kw, Hy * Wy).permute(0, 3, 2, 1).reshape(N * Hy * Wy, kh * kw * Cx)
+        out = torch.zeros((N * Hy * Wy, Kp), dtype=torch.bfloat16)
+        out[:, :kh * kw * Cx] = cols.to(torch.bfloat16)
+        return out
+
     def conv_gemm(self, d, inp, wmat, bias, scale, out, tc):
         self.launches += 1
         assert inp.dtype == torch.bfloat16 or not tc, "the tcgen05 path takes bf16 operands"

@@ -93,6 +93,8 @@ CONV_CASES = [
     # Cx, Cy, k, s, p, H, N, x_layout, out_layout, bias
     (3, 64, 7, 1, 3, 32, 3, "nchw", "cl", False),
     (3, 64, 3, 1, 1, 16, 2, "nchw", "cl", True),
+    (3, 64, 1, 1, 0, 16, 5, "nchw", "cl", False),       # OptimizedBlock shortcut on the pooled image
+    (3, 128, 3, 2, 1, 17, 3, "nchw", "cl", False),      # strided, odd extent (im2col-packed path)
     (64, 128, 4, 2, 1, 32, 3, "cl", "cl", False),
     (64, 128, 4, 2, 1, 33, 2, "cl", "cl", False),       # odd extent (LayoutEncoder 66 -> 33 -> 16)
     (128, 64, 3, 1, 1, 8, 5, "cl", "cl", True),
@@ -154,10 +156,11 @@ def test_conv_fwd_bwd(K, case, precision):
             yr.backward(gy)
             dxr, dwr, dbr = xr.grad, wr.grad, (br.grad if has_b else None)
         else:
-            tf = 1e-4 if ops._tc_fwd_ok(geom, xl) else 2e-2
+            packed = ops._packed_ok(geom) and ol == "cl"     # few-channel input: im2col-packed tcgen05 path, bf16 output
+            tf = 1e-4 if ops._tc_fwd_ok(geom, xl) else (4e-3 if packed else 2e-2)
             td = 1e-4 if ops._tc_dgrad_ok(geom, ol) else 2e-2
-            tw = 1e-4 if ops._tc_wgrad_ok(geom, xl, ol) else 2e-2
-            xq, wq = (_bf(x), _bf(w)) if ops._tc_fwd_ok(geom, xl) else (x, w)
+            tw = 1e-4 if (ops._tc_wgrad_ok(geom, xl, ol) or packed) else 2e-2
+            xq, wq = (_bf(x), _bf(w)) if (ops._tc_fwd_ok(geom, xl) or packed) else (x, w)
             yr = _conv_ref(xq, wq, b, s, p, False, None)
             gy = torch.randn(yr.shape, generator=g)
             dxr = torch.nn.grad.conv2d_input(x.shape, _bf(w), _bf(gy), stride=s, padding=p)
@@ -171,6 +174,23 @@ def test_conv_fwd_bwd(K, case, precision):
             close(bd.grad, dbr, 1e-5 if y.dtype == torch.float32 else 4e-3, "bias grad")
     finally:
         ops.set_precision("fp32")
+
+
+@pytest.mark.parametrize("case", [(3, 7, 1, 3, 32, 5, "nchw"), (3, 3, 1, 1, 16, 2, "nchw"), (3, 1, 1, 0, 9, 4, "nchw"),
+                                  (3, 3, 2, 1, 17, 3, "nchw"), (3, 4, 2, 1, 8, 3, "cl")])
+def test_im2col_pack_bit_exact(K, case):
+    """the packed bf16 im2col matrix of a few-channel input equals the CPU restatement (unfold) bit for bit"""
+    Cx, k, s, p, H, N, layout = case
+    g = torch.Generator().manual_seed(Cx + k + H)
+    x = torch.randn(N, Cx, H, H + 3, generator=g)
+    geom = ops.ConvGeom(Cx, 64, k, k, s, p)
+    Hy, Wy = geom.out_hw(H, H + 3)
+    Kp = (Cx * k * k + 63) // 64 * 64
+    xd = _to_layout(x, layout)
+    strides = ops.nchw_strides(Cx, H, H + 3) if layout == "nchw" else ops.cl_strides(H, H + 3, Cx)
+    got = K.im2col_pack(xd.cuda(), strides, N, H, H + 3, Cx, k, k, s, p, Hy, Wy, Kp)
+    want = E.im2col_pack(xd, strides, N, H, H + 3, Cx, k, k, s, p, Hy, Wy, Kp)
+    assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
