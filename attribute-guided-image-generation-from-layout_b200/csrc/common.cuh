@@ -74,6 +74,48 @@ __device__ __forceinline__ void st4(bf16* p, float4 v) {
     *reinterpret_cast<uint2*>(p) = u;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// 16-byte vector access: V = 4 fp32 or 8 bf16 consecutive channels per thread
+// ---------------------------------------------------------------------------------------------------------
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+    static constexpr int V = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct VecIO<bf16> {
+    static constexpr int V = 8;
+    static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {            // bf16 -> fp32 is a 16-bit shift
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+        uint4 q;
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]),
+                       c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+        q.x = *reinterpret_cast<uint32_t*>(&a); q.y = *reinterpret_cast<uint32_t*>(&b);
+        q.z = *reinterpret_cast<uint32_t*>(&c); q.w = *reinterpret_cast<uint32_t*>(&d);
+        *reinterpret_cast<uint4*>(p) = q;
+    }
+};
+template <int V>
+__device__ __forceinline__ void ldp(const float* p, float (&v)[V]) {       // V fp32 parameters (16-byte aligned)
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(p + i);
+        v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+    }
+}
 // dispatch helper: run `BODY` with `T` bound to the storage type selected by an int dtype code
 #define B200_DISPATCH_DT(dt, T, ...)                          \
     do {                                                      \

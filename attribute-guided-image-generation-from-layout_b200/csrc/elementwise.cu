@@ -9,86 +9,115 @@ namespace b200 {
 
 // T = storage type of the channel-last activations (float or bf16); arithmetic is fp32 throughout.
 template <typename T>
-__global__ void relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n4, int tail) {
-    GRID_STRIDE(i, n4) {
-        float4 v = ld4(x + i * 4);
-        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-        st4(y + i * 4, v);
+__global__ void relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t nv, int tail) {
+    constexpr int V = VecIO<T>::V;
+    GRID_STRIDE(i, nv) {
+        float v[V];
+        VecIO<T>::load(x + i * V, v);
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = fmaxf(v[e], 0.f);
+        VecIO<T>::store(y + i * V, v);
     }
-    if (blockIdx.x == 0 && threadIdx.x < tail) stf(y + n4 * 4 + threadIdx.x, fmaxf(ldf(x + n4 * 4 + threadIdx.x), 0.f));
+    if (blockIdx.x == 0 && threadIdx.x < tail) stf(y + nv * V + threadIdx.x, fmaxf(ldf(x + nv * V + threadIdx.x), 0.f));
 }
 
 template <typename T>
-__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t n4,
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t nv,
                                 int tail) {
-    GRID_STRIDE(i, n4) {
-        float4 g = ld4(dy + i * 4), v = ld4(y + i * 4);
-        g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f; g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
-        st4(dx + i * 4, g);
+    constexpr int V = VecIO<T>::V;
+    GRID_STRIDE(i, nv) {
+        float g[V], v[V];
+        VecIO<T>::load(dy + i * V, g);
+        VecIO<T>::load(y + i * V, v);
+#pragma unroll
+        for (int e = 0; e < V; ++e) g[e] = v[e] > 0.f ? g[e] : 0.f;
+        VecIO<T>::store(dx + i * V, g);
     }
     if (blockIdx.x == 0 && threadIdx.x < tail) {
-        const int64_t t = n4 * 4 + threadIdx.x;
+        const int64_t t = nv * V + threadIdx.x;
         stf(dx + t, ldf(y + t) > 0.f ? ldf(dy + t) : 0.f);
     }
 }
 
 template <typename T>
-__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, int64_t n4, int tail) {
-    GRID_STRIDE(i, n4) {
-        float4 u = ld4(a + i * 4), v = ld4(b + i * 4);
-        st4(o + i * 4, make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w));
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, int64_t nv, int tail) {
+    constexpr int V = VecIO<T>::V;
+    GRID_STRIDE(i, nv) {
+        float u[V], v[V];
+        VecIO<T>::load(a + i * V, u);
+        VecIO<T>::load(b + i * V, v);
+#pragma unroll
+        for (int e = 0; e < V; ++e) u[e] += v[e];
+        VecIO<T>::store(o + i * V, u);
     }
     if (blockIdx.x == 0 && threadIdx.x < tail) {
-        const int64_t t = n4 * 4 + threadIdx.x;
+        const int64_t t = nv * V + threadIdx.x;
         stf(o + t, ldf(a + t) + ldf(b + t));
     }
 }
 
-// y[n,qy,qx,c] = scale * sum_{dy,dx<f} x[n,qy*f+dy,qx*f+dx,c];  V = channels per thread (4 when C % 4 == 0)
-template <typename T, int V>
+// y[n,qy,qx,c] = scale * sum_{dy,dx<f} x[n,qy*f+dy,qx*f+dx,c];  V = channels per thread (16 bytes when C % V == 0, else
+// 1); I = index type (32-bit when the element count fits: no 64-bit divisions)
+template <typename T, int V, typename I>
 __global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f,
                                 float scale) {
     const int Ho = H / f, Wo = W / f, Cv = C / V;
-    const int64_t total = (int64_t)N * Ho * Wo * Cv;
-    GRID_STRIDE(t, total) {
+    const I total = (I)N * Ho * Wo * Cv;
+    for (I t = blockIdx.x * (I)blockDim.x + threadIdx.x; t < total; t += (I)gridDim.x * blockDim.x) {
         const int c = (int)(t % Cv) * V;
-        const int qx = (int)((t / Cv) % Wo);
-        const int qy = (int)((t / ((int64_t)Cv * Wo)) % Ho);
-        const int n = (int)(t / ((int64_t)Cv * Wo * Ho));
+        I q = t / Cv;
+        const int qx = (int)(q % Wo);
+        q /= Wo;
+        const int qy = (int)(q % Ho);
+        const int n = (int)(q / Ho);
         const T* p = x + (((int64_t)n * H + (int64_t)qy * f) * W + (int64_t)qx * f) * C + c;
-        if (V == 4) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (V > 1) {
+            static_assert(V == VecIO<T>::V, "vector width");
+            float acc[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] = 0.f;
             for (int dy = 0; dy < f; ++dy)
                 for (int dx = 0; dx < f; ++dx) {
-                    const float4 v = ld4(p + ((int64_t)dy * W + dx) * C);
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    float v[V];
+                    VecIO<T>::load(p + ((int64_t)dy * W + dx) * C, v);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) acc[e] += v[e];
                 }
-            st4(y + t * 4, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] *= scale;
+            VecIO<T>::store(y + (int64_t)t * V, acc);
         } else {
             float acc = 0.f;
             for (int dy = 0; dy < f; ++dy)
                 for (int dx = 0; dx < f; ++dx) acc += ldf(p + ((int64_t)dy * W + dx) * C);
-            stf(y + t, acc * scale);
+            stf(y + (int64_t)t, acc * scale);
         }
     }
 }
 
-template <typename T, int V>
+// y[n,oy,ox,c] = scale * x[n,oy/f,ox/f,c]  (nearest upsampling; the adjoint of pool_fwd)
+template <typename T, int V, typename I>
 __global__ void unpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f,
                                   float scale) {
     const int Ho = H * f, Wo = W * f, Cv = C / V;
-    const int64_t total = (int64_t)N * Ho * Wo * Cv;
-    GRID_STRIDE(t, total) {
+    const I total = (I)N * Ho * Wo * Cv;
+    for (I t = blockIdx.x * (I)blockDim.x + threadIdx.x; t < total; t += (I)gridDim.x * blockDim.x) {
         const int c = (int)(t % Cv) * V;
-        const int ox = (int)((t / Cv) % Wo);
-        const int oy = (int)((t / ((int64_t)Cv * Wo)) % Ho);
-        const int n = (int)(t / ((int64_t)Cv * Wo * Ho));
+        I q = t / Cv;
+        const int ox = (int)(q % Wo);
+        q /= Wo;
+        const int oy = (int)(q % Ho);
+        const int n = (int)(q / Ho);
         const T* p = x + (((int64_t)n * H + oy / f) * W + ox / f) * C + c;
-        if (V == 4) {
-            const float4 v = ld4(p);
-            st4(y + t * 4, make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale));
+        if constexpr (V > 1) {
+            static_assert(V == VecIO<T>::V, "vector width");
+            float v[V];
+            VecIO<T>::load(p, v);
+#pragma unroll
+            for (int e = 0; e < V; ++e) v[e] *= scale;
+            VecIO<T>::store(y + (int64_t)t * V, v);
         } else {
-            stf(y + t, scale * ldf(p));
+            stf(y + (int64_t)t, scale * ldf(p));
         }
     }
 }
@@ -168,22 +197,30 @@ __global__ void permute_rows_kernel(const uint4* __restrict__ x, const int32_t* 
 template <typename T>
 __global__ void mask_outer_fwd_kernel(const float* __restrict__ v, const float* __restrict__ mask,
                                       T* __restrict__ out, int O, int H, int W, int C) {
-    const int Hp = H + 2, Wp = W + 2, C4 = C >> 2;
-    const int64_t total = (int64_t)O * Hp * Wp * C4;
+    constexpr int V = VecIO<T>::V;
+    const int Hp = H + 2, Wp = W + 2, Cv = C / V;
+    const int64_t total = (int64_t)O * Hp * Wp * Cv;
     GRID_STRIDE(t, total) {
-        const int c = (int)(t % C4) << 2;
-        const int x = (int)((t / C4) % Wp);
-        const int y = (int)((t / ((int64_t)C4 * Wp)) % Hp);
-        const int o = (int)(t / ((int64_t)C4 * Wp * Hp));
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        // total < 2^31 is checked by the launcher: 32-bit divisions
+        const uint32_t u = (uint32_t)t;
+        const int c = (int)(u % Cv) * V;
+        uint32_t q = u / Cv;
+        const int x = (int)(q % Wp);
+        q /= Wp;
+        const int y = (int)(q % Hp);
+        const int o = (int)(q / Hp);
+        float r[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) r[e] = 0.f;
         if (y >= 1 && y <= H && x >= 1 && x <= W) {
             const float m = mask[((int64_t)o * H + (y - 1)) * W + (x - 1)];
             if (m != 0.f) {
-                const float4 q = *reinterpret_cast<const float4*>(v + (int64_t)o * C + c);
-                r = make_float4(m * q.x, m * q.y, m * q.z, m * q.w);
+                ldp<V>(v + (int64_t)o * C + c, r);
+#pragma unroll
+                for (int e = 0; e < V; ++e) r[e] *= m;
             }
         }
-        st4(out + t * 4, r);
+        VecIO<T>::store(out + t * V, r);
     }
 }
 
@@ -434,8 +471,8 @@ static inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>
 extern "C" int b200_relu_fwd(const void* x, void* y, int64_t n, int dt, b200_stream_t stream) {
     if (n == 0) return 0;
     B200_DISPATCH_DT(dt, T, {
-        int64_t n4 = (aligned4<T>(x) && aligned4<T>(y)) ? n / 4 : 0;
-        int tail = (int)(n - n4 * 4);
+        int64_t n4 = (aligned16(x) && aligned16(y)) ? n / VecIO<T>::V : 0;
+        int tail = (int)(n - n4 * VecIO<T>::V);
         B200_REQUIRE(tail < 256, "relu_fwd: unaligned large tensor");
         relu_fwd_kernel<T><<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, n4, tail);
     });
@@ -446,8 +483,8 @@ extern "C" int b200_relu_fwd(const void* x, void* y, int64_t n, int dt, b200_str
 extern "C" int b200_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, int dt, b200_stream_t stream) {
     if (n == 0) return 0;
     B200_DISPATCH_DT(dt, T, {
-        int64_t n4 = (aligned4<T>(dy) && aligned4<T>(y) && aligned4<T>(dx)) ? n / 4 : 0;
-        int tail = (int)(n - n4 * 4);
+        int64_t n4 = (aligned16(dy) && aligned16(y) && aligned16(dx)) ? n / VecIO<T>::V : 0;
+        int tail = (int)(n - n4 * VecIO<T>::V);
         B200_REQUIRE(tail < 256, "relu_bwd: unaligned large tensor");
         relu_bwd_kernel<T><<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const T*)dy, (const T*)y, (T*)dx,
                                                                                       n4, tail);
@@ -459,8 +496,8 @@ extern "C" int b200_relu_bwd(const void* dy, const void* y, void* dx, int64_t n,
 extern "C" int b200_add(const void* a, const void* b, void* out, int64_t n, int dt, b200_stream_t stream) {
     if (n == 0) return 0;
     B200_DISPATCH_DT(dt, T, {
-        int64_t n4 = (aligned4<T>(a) && aligned4<T>(b) && aligned4<T>(out)) ? n / 4 : 0;
-        int tail = (int)(n - n4 * 4);
+        int64_t n4 = (aligned16(a) && aligned16(b) && aligned16(out)) ? n / VecIO<T>::V : 0;
+        int tail = (int)(n - n4 * VecIO<T>::V);
         B200_REQUIRE(tail < 256, "add: unaligned large tensor");
         add_kernel<T><<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (T*)out, n4,
                                                                                  tail);
@@ -475,10 +512,15 @@ extern "C" int b200_pool_fwd(const void* x, void* y, int N, int H, int W, int C,
     int64_t total = (int64_t)N * (H / f) * (W / f) * C;
     if (total == 0) return 0;
     B200_DISPATCH_DT(dt, T, {
-        if (C % 4 == 0 && aligned4<T>(x) && aligned4<T>(y))
-            pool_fwd_kernel<T, 4><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
-        else
-            pool_fwd_kernel<T, 1><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+        constexpr int V = VecIO<T>::V;
+        const bool small = (int64_t)N * H * W * C < (1ll << 31);
+        if (C % V == 0 && aligned16(x) && aligned16(y)) {
+            if (small) pool_fwd_kernel<T, V, uint32_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+            else pool_fwd_kernel<T, V, int64_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+        } else {
+            if (small) pool_fwd_kernel<T, 1, uint32_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+            else pool_fwd_kernel<T, 1, int64_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+        }
     });
     B200_CHECK_LAUNCH();
     return 0;
@@ -489,10 +531,15 @@ extern "C" int b200_unpool_fwd(const void* x, void* y, int N, int H, int W, int 
     int64_t total = (int64_t)N * H * f * W * f * C;
     if (total == 0) return 0;
     B200_DISPATCH_DT(dt, T, {
-        if (C % 4 == 0 && aligned4<T>(x) && aligned4<T>(y))
-            unpool_fwd_kernel<T, 4><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
-        else
-            unpool_fwd_kernel<T, 1><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+        constexpr int V = VecIO<T>::V;
+        const bool small = total < (1ll << 31);
+        if (C % V == 0 && aligned16(x) && aligned16(y)) {
+            if (small) unpool_fwd_kernel<T, V, uint32_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+            else unpool_fwd_kernel<T, V, int64_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+        } else {
+            if (small) unpool_fwd_kernel<T, 1, uint32_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+            else unpool_fwd_kernel<T, 1, int64_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+        }
     });
     B200_CHECK_LAUNCH();
     return 0;
@@ -550,9 +597,11 @@ extern "C" int b200_permute_rows(const void* x, const int32_t* src_row, void* ou
 extern "C" int b200_mask_outer_fwd(const float* v, const float* mask, void* out, int O, int H, int W, int C, int dt,
                                    b200_stream_t stream) {
     if (O == 0) return 0;
-    B200_REQUIRE(C % 4 == 0, "mask_outer_fwd: C=%d must be a multiple of 4", C);
-    int64_t total = (int64_t)O * (H + 2) * (W + 2) * (C / 4);
+    B200_REQUIRE(C % 8 == 0, "mask_outer_fwd: C=%d must be a multiple of 8", C);
+    B200_REQUIRE((int64_t)O * (H + 2) * (W + 2) * (C / 4) < (1ll << 31), "mask_outer_fwd: tensor too large");
+    B200_REQUIRE(aligned16(v) && aligned16(out), "mask_outer_fwd: operands must be 16-byte aligned");
     B200_DISPATCH_DT(dt, T, {
+        int64_t total = (int64_t)O * (H + 2) * (W + 2) * (C / VecIO<T>::V);
         mask_outer_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(v, mask, (T*)out, O, H, W, C);
     });
     B200_CHECK_LAUNCH();

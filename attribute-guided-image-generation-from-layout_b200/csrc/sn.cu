@@ -107,17 +107,43 @@ __global__ void sn_dot_final_kernel(double* part, int nblocks) {
     s = warp_sum(s);
     if (threadIdx.x == 0) part[0] = s;
 }
+// dW = g / sigma - <g, W> / sigma^2 * u v^T.  Every block first sums the partial dot products itself (one warp, lanes
+// stride over the block partials, shuffle tree — the fixed order sn_dot_final_kernel uses), so no separate launch.
 __global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* __restrict__ u,
                                      const float* __restrict__ v, const float* __restrict__ inv_sigma,
-                                     const double* __restrict__ part, float* __restrict__ dW, int h, int w,
+                                     const double* __restrict__ part, int nblocks, float* __restrict__ dW, int h, int w,
                                      int accumulate) {
-    int64_t n = (int64_t)h * w;
-    float inv = *inv_sigma;
-    float coef = (float)(part[0]) * inv * inv;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-        int j = (int)(t % w);
-        int i = (int)(t / w);
-        float val = g[t] * inv - coef * u[i] * v[j];
+    __shared__ float coef_s;
+    const float inv = *inv_sigma;
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int k = threadIdx.x; k < nblocks; k += 32) s += part[1 + k];
+        s = warp_sum(s);
+        if (threadIdx.x == 0) coef_s = (float)s * inv * inv;
+    }
+    __syncthreads();
+    const float coef = coef_s;
+    const uint32_t n = (uint32_t)h * (uint32_t)w;
+    if ((w & 3) == 0) {
+        const uint32_t n4 = n >> 2, w4 = (uint32_t)w >> 2;
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += gridDim.x * blockDim.x) {
+            const uint32_t i = t / w4, j = (t - i * w4) << 2;
+            const float4 gv = *reinterpret_cast<const float4*>(g + (size_t)t * 4);
+            const float4 vv = *reinterpret_cast<const float4*>(v + j);
+            const float cu = coef * u[i];
+            float4 o = make_float4(gv.x * inv - cu * vv.x, gv.y * inv - cu * vv.y, gv.z * inv - cu * vv.z, gv.w * inv - cu * vv.w);
+            float4* dst = reinterpret_cast<float4*>(dW + (size_t)t * 4);
+            if (accumulate) {
+                const float4 p = *dst;
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            *dst = o;
+        }
+        return;
+    }
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t i = t / (uint32_t)w, j = t - i * (uint32_t)w;
+        const float val = g[t] * inv - coef * u[i] * v[j];
         dW[t] = accumulate ? dW[t] + val : val;
     }
 }
@@ -130,16 +156,31 @@ __global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* _
 // ---------------------------------------------------------------------------------------------------------
 __global__ void snm_wtu_kernel(const b200_sn_layer* __restrict__ layers) {
     const b200_sn_layer l = layers[blockIdx.z];
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= l.w) return;
     const int nch = l.h < 64 ? 1 : kSnRowChunks;
     if ((int)blockIdx.y >= nch) return;
     const int rpc = (l.h + nch - 1) / nch;
     const int i0 = blockIdx.y * rpc;
     const int i1 = i0 + rpc < l.h ? i0 + rpc : l.h;
-    float acc = 0.f;
-    for (int i = i0; i < i1; ++i) acc += l.W[(int64_t)i * l.w + j] * l.u[i];
-    l.ws[(int64_t)blockIdx.y * l.w + j] = acc;
+    if ((l.w & 3) == 0 && ((reinterpret_cast<uintptr_t>(l.W) | reinterpret_cast<uintptr_t>(l.ws)) & 15) == 0) {
+        // 4 columns per thread (16-byte loads), the same per-column summation order as the scalar path
+        const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (j >= l.w) return;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* Wp = l.W + j;
+#pragma unroll 4
+        for (int i = i0; i < i1; ++i) {
+            const float4 q = *reinterpret_cast<const float4*>(Wp + (int64_t)i * l.w);
+            const float ui = l.u[i];
+            acc.x += q.x * ui; acc.y += q.y * ui; acc.z += q.z * ui; acc.w += q.w * ui;
+        }
+        *reinterpret_cast<float4*>(l.ws + (int64_t)blockIdx.y * l.w + j) = acc;
+        return;
+    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l.w; j += gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int i = i0; i < i1; ++i) acc += l.W[(int64_t)i * l.w + j] * l.u[i];
+        l.ws[(int64_t)blockIdx.y * l.w + j] = acc;
+    }
 }
 
 __global__ void snm_norm_v_kernel(const b200_sn_layer* __restrict__ layers, float eps, int it) {
@@ -166,7 +207,16 @@ __global__ void snm_wv_kernel(const b200_sn_layer* __restrict__ layers) {
     if (row >= l.h) return;
     const float* Wr = l.W + (int64_t)row * l.w;
     float acc = 0.f;
-    for (int j = lane; j < l.w; j += 32) acc += Wr[j] * l.v[j];
+    if ((l.w & 3) == 0 && (reinterpret_cast<uintptr_t>(l.W) & 15) == 0 && (reinterpret_cast<uintptr_t>(l.v) & 15) == 0) {
+#pragma unroll 4
+        for (int j = lane * 4; j < l.w; j += 128) {
+            const float4 q = *reinterpret_cast<const float4*>(Wr + j);
+            const float4 p = *reinterpret_cast<const float4*>(l.v + j);
+            acc += q.x * p.x + q.y * p.y + q.z * p.z + q.w * p.w;
+        }
+    } else {
+        for (int j = lane; j < l.w; j += 32) acc += Wr[j] * l.v[j];
+    }
     acc = warp_sum(acc);
     if (lane == 0) l.ws[(int64_t)kSnRowChunks * l.w + row] = acc;
 }
@@ -224,11 +274,10 @@ extern "C" int b200_sn_grad(const float* g, const float* W, const float* u, cons
     int64_t n = (int64_t)h * w;
     int nblocks = grid_for(n, 256, 4);
     if (nblocks > 1023) nblocks = 1023;
+    B200_REQUIRE(n < (1ll << 32), "sn_grad: weight too large");
     sn_dot_partial_kernel<<<nblocks, 256, 0, st>>>(g, W, n, ws);
     B200_CHECK_LAUNCH();
-    sn_dot_final_kernel<<<1, 32, 0, st>>>(ws, nblocks);
-    B200_CHECK_LAUNCH();
-    sn_grad_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(g, u, v, inv_sigma, ws, dW, h, w, accumulate);
+    sn_grad_apply_kernel<<<grid_for((w & 3) == 0 ? n / 4 : n, 256), 256, 0, st>>>(g, u, v, inv_sigma, ws, nblocks, dW, h, w, accumulate);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -240,7 +289,7 @@ extern "C" int b200_sn_power_iter_multi(const b200_sn_layer* layers, int n_layer
     cudaStream_t st = as_stream(stream);
     for (int it = 0; it < iters; ++it) {
         if (do_iter) {
-            snm_wtu_kernel<<<dim3((max_w + 127) / 128, kSnRowChunks, n_layers), 128, 0, st>>>(layers);
+            snm_wtu_kernel<<<dim3((max_w / 4 + 127) / 128 + 1, kSnRowChunks, n_layers), 128, 0, st>>>(layers);
             B200_CHECK_LAUNCH();
             snm_norm_v_kernel<<<n_layers, 1024, 0, st>>>(layers, eps, it);
             B200_CHECK_LAUNCH();

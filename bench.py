@@ -350,6 +350,7 @@ def kernel_roofline(ts, b, args):
     R = 4
     records = []          # (tc, flops, ms per launch)
     per_key = {}
+    by_shape = {}
     orig_conv, orig_wgrad = real.conv_gemm, real.wgrad_gemm
 
     def flops_of(d):
@@ -374,6 +375,10 @@ def kernel_roofline(ts, b, args):
                 per_key[key] = s.elapsed_time(e) / R
                 del g
             records.append((tc, flops_of(desc), per_key[key]))
+            shape = (("wgrad" if wgrad else "conv"), tc, desc.B * desc.Qh * desc.Qw, desc.Cin, desc.Cout, desc.Th * desc.Tw,
+                     desc.in_sy, desc.out_sy)
+            a = by_shape.setdefault(shape, [0, 0.0, 0.0])
+            a[0] += 1; a[1] += per_key[key]; a[2] += flops_of(desc)
         return wrapper
 
     real.conv_gemm = timed(orig_conv, False)
@@ -387,6 +392,11 @@ def kernel_roofline(ts, b, args):
     finally:
         real.conv_gemm, real.wgrad_gemm = orig_conv, orig_wgrad
         ts.ddp_d, ts.ddp_g = ddp
+    if os.environ.get("B200_BENCH_SHAPES"):
+        for shape, (n, ms_, fl) in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:60]:
+            print("[shape] %-5s tc=%d M=%8d Cin=%4d Cout=%4d T=%2d s_in=%d s_out=%d | n=%3d %8.3f ms %7.1f TFLOP/s" %
+                  (shape[0], shape[1], shape[2], shape[3], shape[4], shape[5], shape[6], shape[7], n, ms_, fl / ms_ / 1e9),
+                  file=sys.stderr)
     tc_t = sum(t for tc, _, t in records if tc) / 1e3
     tc_f = sum(f for tc, f, _ in records if tc)
     simt_t = sum(t for tc, _, t in records if not tc) / 1e3
