@@ -52,15 +52,34 @@ __global__ void sn_norm_v_kernel(const float* __restrict__ partial, int nchunks,
     for (int j = threadIdx.x; j < w; j += 1024) v[j] *= inv;
 }
 
+// one warp: sum_j Wr[j] * v[j]; 4 consecutive columns per lane (16-byte loads) when the row layout allows it.
+// The single-layer and the whole-network kernels share this order (their results are compared bit for bit).
+__device__ __forceinline__ float warp_row_dot(const float* __restrict__ Wr, const float* __restrict__ v, int w, int lane,
+                                              bool vec) {
+    float acc = 0.f;
+    if (vec) {
+#pragma unroll 4
+        for (int j = lane * 4; j < w; j += 128) {
+            const float4 q = *reinterpret_cast<const float4*>(Wr + j);
+            const float4 p = *reinterpret_cast<const float4*>(v + j);
+            acc += q.x * p.x + q.y * p.y + q.z * p.z + q.w * p.w;
+        }
+    } else {
+        for (int j = lane; j < w; j += 32) acc += Wr[j] * v[j];
+    }
+    return warp_sum(acc);
+}
+__device__ __forceinline__ bool row_vec_ok(const float* W, const float* v, int w) {
+    return (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+}
+
 // wv[i] = sum_j W[i][j] v[j]; one warp per row
 __global__ void sn_wv_kernel(const float* __restrict__ W, const float* __restrict__ v, int h, int w,
                              float* __restrict__ wv) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= h) return;
-    float acc = 0.f;
-    for (int j = lane; j < w; j += 32) acc += W[(int64_t)row * w + j] * v[j];
-    acc = warp_sum(acc);
+    const float acc = warp_row_dot(W + (int64_t)row * w, v, w, lane, row_vec_ok(W, v, w));
     if (lane == 0) wv[row] = acc;
 }
 
@@ -124,12 +143,12 @@ __global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* _
     __syncthreads();
     const float coef = coef_s;
     const uint32_t n = (uint32_t)h * (uint32_t)w;
-    if ((w & 3) == 0) {
+    if ((w & 3) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dW)) & 15) == 0) {
         const uint32_t n4 = n >> 2, w4 = (uint32_t)w >> 2;
         for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += gridDim.x * blockDim.x) {
             const uint32_t i = t / w4, j = (t - i * w4) << 2;
             const float4 gv = *reinterpret_cast<const float4*>(g + (size_t)t * 4);
-            const float4 vv = *reinterpret_cast<const float4*>(v + j);
+            const float4 vv = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);      // history rows: 4-byte aligned only
             const float cu = coef * u[i];
             float4 o = make_float4(gv.x * inv - cu * vv.x, gv.y * inv - cu * vv.y, gv.z * inv - cu * vv.z, gv.w * inv - cu * vv.w);
             float4* dst = reinterpret_cast<float4*>(dW + (size_t)t * 4);
@@ -205,19 +224,7 @@ __global__ void snm_wv_kernel(const b200_sn_layer* __restrict__ layers) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= l.h) return;
-    const float* Wr = l.W + (int64_t)row * l.w;
-    float acc = 0.f;
-    if ((l.w & 3) == 0 && (reinterpret_cast<uintptr_t>(l.W) & 15) == 0 && (reinterpret_cast<uintptr_t>(l.v) & 15) == 0) {
-#pragma unroll 4
-        for (int j = lane * 4; j < l.w; j += 128) {
-            const float4 q = *reinterpret_cast<const float4*>(Wr + j);
-            const float4 p = *reinterpret_cast<const float4*>(l.v + j);
-            acc += q.x * p.x + q.y * p.y + q.z * p.z + q.w * p.w;
-        }
-    } else {
-        for (int j = lane; j < l.w; j += 32) acc += Wr[j] * l.v[j];
-    }
-    acc = warp_sum(acc);
+    const float acc = warp_row_dot(l.W + (int64_t)row * l.w, l.v, l.w, lane, row_vec_ok(l.W, l.v, l.w));
     if (lane == 0) l.ws[(int64_t)kSnRowChunks * l.w + row] = acc;
 }
 
