@@ -170,8 +170,9 @@ class Kernels:
     def conv_tc_set_im2col(self, enable: bool) -> bool:
         return bool(self.lib.b200_conv_tc_set_im2col(int(bool(enable))))
 
-    def conv_tc_set_persistent(self, enable: bool) -> bool:
-        return bool(self.lib.b200_conv_tc_set_persistent(int(bool(enable))))
+    def conv_tc_set_persistent(self, mode) -> int:
+        """0 off, 1 one CTA per SM, 2 two CTAs per SM, 3 two CTAs per SM for short K loops; returns the previous mode"""
+        return int(self.lib.b200_conv_tc_set_persistent(int(mode)))
 
     def conv_tc_set_halo(self, enable: bool) -> bool:
         return bool(self.lib.b200_conv_tc_set_halo(int(bool(enable))))

@@ -431,7 +431,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1) conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(192, 2) conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                       const __grid_constant__ CUtensorMap tmap_a,
                                                                       b200_conv_desc d, const float* __restrict__ bias,
                                                                       const float* __restrict__ scale,
@@ -489,17 +489,18 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_persist_kernel(const __gr
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
             const int buf = j & 1;
             const int n0 = (t % num_n_tiles) * BN;
-            const int64_t m = (int64_t)(t / num_n_tiles) * BM + row;
+            const uint32_t m = (uint32_t)(t / num_n_tiles) * BM + (uint32_t)row;      // M < 2^31 (checked at launch)
             int64_t ro = -1;
             float alpha = 1.f;
-            if (m < M) {
-                const int qx = (int)(m % d.Qw);
-                const int qy = (int)((m / d.Qw) % d.Qh);
-                const int64_t n = m / ((int64_t)d.Qw * d.Qh);
+            if (m < (uint32_t)M) {
+                const uint32_t q = m / (uint32_t)d.Qw;
+                const int qx = (int)(m - q * (uint32_t)d.Qw);
+                const uint32_t n = q / (uint32_t)d.Qh;
+                const int qy = (int)(q - n * (uint32_t)d.Qh);
                 const int oy = qy * d.out_sy + d.out_oy, ox = qx * d.out_sx + d.out_ox;
                 if (oy >= 0 && oy < d.Ho && ox >= 0 && ox < d.Wo)
-                    ro = n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
-                if (scale) alpha = scale[d.scale_rows > 0 ? m / d.scale_rows : 0];
+                    ro = (int64_t)n * d.out_sn + (int64_t)oy * d.out_sh + (int64_t)ox * d.out_sw;
+                if (scale) alpha = scale[d.scale_rows > 0 ? m / (uint32_t)d.scale_rows : 0];
             }
             mbar_wait(smem_u32(&tail->tmem_full[buf]), (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
@@ -1177,7 +1178,8 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-static int g_use_persist = 1;
+static int g_use_persist = 2;      // 0 off, 1 one CTA per SM, 2 two CTAs per SM, 3 two CTAs per SM for short K loops
+static int g_two_cta_max_kb = 4;
 static int g_use_halo = 0;     // measured slower than the persistent im2col kernel on every step shape (profiles/r01e_bench_conv.md)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1406,22 +1408,40 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
     int kbps = (num_kb + splits - 1) / splits;
     splits = (num_kb + kbps - 1) / kbps;          // no empty split
     if (atma && splits == 1 && g_use_persist && BN >= 64 && num_kb <= 24) {
-        // persistent path: one CTA per SM, deep operand ring, double-buffered TMEM accumulator
-        constexpr int PSTAGES = BN == 128 ? 6 : 8;
-        constexpr int psmem = 1024 + PSTAGES * (A_BYTES + BN * BK * 2) + (int)sizeof(PersistTail);
-        static bool pconfigured = false;
-        if (!pconfigured) {
-            cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<BN, PSTAGES>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
-            B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute(persist): %s", cudaGetErrorString(e));
-            pconfigured = true;
-        }
+        // persistent path: operand ring running ahead across tiles, double-buffered TMEM accumulator.  Two co-resident
+        // CTAs per SM with a shallower ring each (g_use_persist == 2, short K loops: two epilogue warp sets interleave)
+        // or one CTA per SM with a deep ring.
         const int64_t mtiles = (M + BM - 1) / BM;
         const int64_t tiles = mtiles * ntiles;
         B200_REQUIRE(tiles < (1ll << 31), "conv_gemm_tc: too many tiles");
-        const int grid_p = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-        conv_gemm_tc_persist_kernel<BN, PSTAGES><<<grid_p, 192, psmem, st>>>(tmap, tmap_a, *d, bias, scale, out, out_bf16,
-                                                                           ntiles, (int)tiles);
+        const bool two = g_use_persist == 2 || (g_use_persist == 3 && num_kb <= g_two_cta_max_kb);
+        if (two) {
+            constexpr int PSTAGES = BN == 128 ? 3 : 4;
+            constexpr int psmem = 1024 + PSTAGES * (A_BYTES + BN * BK * 2) + (int)sizeof(PersistTail);
+            static bool pconfigured = false;
+            if (!pconfigured) {
+                cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<BN, PSTAGES>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+                B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute(persist): %s", cudaGetErrorString(e));
+                pconfigured = true;
+            }
+            const int grid_p = (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+            conv_gemm_tc_persist_kernel<BN, PSTAGES><<<grid_p, 192, psmem, st>>>(tmap, tmap_a, *d, bias, scale, out,
+                                                                               out_bf16, ntiles, (int)tiles);
+        } else {
+            constexpr int PSTAGES = BN == 128 ? 6 : 8;
+            constexpr int psmem = 1024 + PSTAGES * (A_BYTES + BN * BK * 2) + (int)sizeof(PersistTail);
+            static bool pconfigured = false;
+            if (!pconfigured) {
+                cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<BN, PSTAGES>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+                B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute(persist): %s", cudaGetErrorString(e));
+                pconfigured = true;
+            }
+            const int grid_p = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+            conv_gemm_tc_persist_kernel<BN, PSTAGES><<<grid_p, 192, psmem, st>>>(tmap, tmap_a, *d, bias, scale, out,
+                                                                               out_bf16, ntiles, (int)tiles);
+        }
         B200_CHECK_LAUNCH();
         return 0;
     }
@@ -1548,7 +1568,7 @@ extern "C" int b200_conv_tc_set_im2col(int enable) {
 
 extern "C" int b200_conv_tc_set_persistent(int enable) {
     int prev = tc::g_use_persist;
-    tc::g_use_persist = enable ? 1 : 0;
+    tc::g_use_persist = enable < 0 ? 0 : (enable > 3 ? 3 : enable);
     return prev;
 }
 
@@ -1562,14 +1582,24 @@ extern "C" int b200_conv_tc_ntile(int Cout) { return Cout >= 128 ? 128 : (Cout >
 
 /* split-K plan: enough CTAs to fill the 148 SMs twice when the output tile grid alone cannot */
 extern "C" int b200_conv_tc_splits(const b200_conv_desc* d) {
+    static int forced = []() {
+        const char* e = getenv("B200_TC_SPLITS");      // experiments only: force the split-K factor
+        return e ? atoi(e) : 0;
+    }();
+    if (forced > 0) {
+        const int nkb = d->Th * d->Tw * (d->Cin / 64);
+        return forced < nkb ? forced : (nkb > 0 ? nkb : 1);
+    }
     int64_t M = (int64_t)d->B * d->Qh * d->Qw;
     int bn = b200_conv_tc_ntile(d->Cout);
     int64_t tiles = ((M + 127) / 128) * ((d->Cout + bn - 1) / bn);
     int num_kb = d->Th * d->Tw * (d->Cin / 64);
-    if (tiles >= 148 || num_kb < 8) return 1;
-    int64_t s = (296 + tiles - 1) / tiles;
-    if (s > num_kb / 4) s = num_kb / 4;
-    if (s > 32) s = 32;
+    // measured (tools/bench_conv.py, B200_TC_SPLITS): the fp32 partials' round trip plus the reduce launch cost more
+    // than idle SMs unless fewer than half of them have a tile and the K loop is long
+    if (tiles * 2 > kNumSMs || num_kb < 16) return 1;
+    int64_t s = kNumSMs / tiles;
+    if (s > num_kb / 8) s = num_kb / 8;
+    if (s > 8) s = 8;
     return s < 1 ? 1 : (int)s;
 }
 

@@ -108,8 +108,9 @@ int b200_conv_tc_ntile(int Cout);
 int b200_conv_tc_set_im2col(int enable);
 /* im2col-eligible, unsplit launches run the PERSISTENT kernel (one CTA per SM walking the output tiles, operand ring
  * running ahead across tiles, double-buffered TMEM accumulator so the epilogue overlaps the next tile's MMAs).
- * b200_conv_tc_set_persistent(0) forces the one-tile-per-CTA kernel (parity tests compare the two); returns the
- * previous setting. */
+ * b200_conv_tc_set_persistent(mode): 0 forces the one-tile-per-CTA kernel (parity tests compare the two), 1 = one
+ * persistent CTA per SM with a deep operand ring, 2 = two co-resident CTAs per SM with shallower rings, 3 = two CTAs per
+ * SM for short K loops only; returns the previous mode. */
 int b200_conv_tc_set_persistent(int enable);
 /* Stride-1 k x k window walks (conv forward and its dgrad) whose activation slab fits shared memory run the
  * SHIFTED-WINDOW kernel: one tiled TMA box per 64-channel slab brings the zero-padded input rows of a 128-pixel output

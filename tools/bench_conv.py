@@ -12,6 +12,9 @@ from b200gan import _lib, ops
 
 # (Cx, Cy, k, s, p, H, N)  — dominant shapes of the 64x64 step at batch 32 / 256 objects
 SHAPES = [
+    (64, 64, 1, 1, 0, 32, 768),      # 1x1 shortcuts / im2col-packed 3-channel convolutions
+    (64, 128, 1, 1, 0, 32, 768),
+    (128, 256, 1, 1, 0, 16, 768),
     (64, 64, 3, 1, 1, 32, 768),      # D_obj / D_att blocks at 32x32 (3 batched calls)
     (64, 64, 3, 1, 1, 64, 256),      # D_img block at 64x64, SPADE_3 shared conv
     (64, 128, 3, 1, 1, 32, 768),
@@ -31,9 +34,12 @@ SHAPES = [
     (64, 3, 7, 1, 3, 64, 96),        # decoder c4
     (192, 256, 3, 1, 1, 8, 96),
     (64, 64, 3, 1, 1, 8, 96),        # G residual blocks
+    (256, 64, 5, 1, 2, 8, 96),
+    (512, 128, 5, 1, 2, 8, 96),
+    (256, 256, 4, 2, 1, 16, 96),
 ]
-MODES = {"cpasync": (False, False, False), "im2col": (True, False, False), "persist": (True, True, False),
-         "halo": (True, True, True)}
+MODES = {"cpasync": (False, 0, False), "im2col": (True, 0, False), "persist": (True, 1, False),
+         "persist2": (True, 2, False), "halo": (True, 1, True)}
 
 
 def timeit(fn, R=10, reps=5):
@@ -58,7 +64,7 @@ def timeit(fn, R=10, reps=5):
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     filt = sys.argv[2] if len(sys.argv) > 2 else ""
-    modes = os.environ.get("MODES", "cpasync,im2col,persist,halo").split(",")
+    modes = os.environ.get("MODES", "im2col,persist,persist2").split(",")
     ops.set_precision("bf16")
     K = _lib.K
     print("%-34s %-6s " % ("shape (Cx,Cy,k,s,p,H,N)", "op") + " ".join("%16s" % m for m in modes))
@@ -91,7 +97,7 @@ def main():
                     elif op == "dgrad":
                         fn = lambda: ops.conv_dgrad(geom, packs, w, dy, "cl", (H, H), "cl")
                     else:
-                        if m in ("persist", "halo"):
+                        if m in ("persist", "persist2", "halo"):
                             cells.append("%16s" % "-"); continue
                         fn = lambda: ops.conv_wgrad(geom, x, "cl", dy, "cl", dw)
                     us = timeit(fn)
