@@ -141,13 +141,21 @@ class Kernels:
         self._check(self.lib.b200_cast_bf16(_ptr(x), _ptr(y), C.c_int64(x.numel()), _stream()), "b200_cast_bf16")
         return y
 
-    def im2col_pack(self, x, x_strides, N, Hx, Wx, Cx, kh, kw, stride, pad, Hy, Wy, Kp):
-        """bf16 [N*Hy*Wy, Kp] im2col matrix of a few-channel input (column = (ky*kw+kx)*Cx + c, zero padded to Kp)"""
+    def im2col_pack(self, x, x_strides, N, Hx, Wx, Cx, kh, kw, stride, pad, Hy, Wy, Kp, flip=False):
+        """bf16 [N*Hy*Wy, Kp] im2col matrix of a few-channel input (column = (ky*kw+kx)*Cx + c, zero padded to Kp);
+        flip: the transposed window walk (stride 1) over an output gradient"""
         out = torch.empty((N * Hy * Wy, Kp), dtype=torch.bfloat16, device=x.device)
         sn, sh, sw, sc = x_strides
         self._check(self.lib.b200_im2col_pack(_ptr(x), _dt(x), C.c_int64(N), Hx, Wx, Cx, C.c_int64(sn), C.c_int64(sh),
-                                              C.c_int64(sw), C.c_int64(sc), kh, kw, stride, pad, Hy, Wy, Kp, _ptr(out),
-                                              _stream()), "b200_im2col_pack")
+                                              C.c_int64(sw), C.c_int64(sc), kh, kw, stride, pad, Hy, Wy, Kp,
+                                              int(bool(flip)), _ptr(out), _stream()), "b200_im2col_pack")
+        return out
+
+    def rowsum(self, x2d):
+        rows, L = x2d.shape
+        out = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
+        self._check(self.lib.b200_rowsum(_ptr(x2d), _dt(x2d), C.c_int64(rows), C.c_int64(L), _ptr(out), _stream()),
+                    "b200_rowsum")
         return out
 
     def conv_gemm(self, desc: ConvDesc, inp, wmat, bias, scale, out, tc: bool):

@@ -239,6 +239,52 @@ def conv_wgrad_packed(g: ConvGeom, P, N, Hy, Wy, dy, dy_layout, dw: torch.Tensor
     return dw
 
 
+def _packed_out_ok(g: ConvGeom, x_layout: str) -> bool:
+    """few OUTPUT channels (the 64 -> 3 image convolution): its data and weight gradients share one bf16 im2col matrix of
+    the output gradient (transposed window walk) and run on the tcgen05 GEMMs"""
+    return (_PRECISION == "bf16" and x_layout == "cl" and g.Cy < 16 and g.Cx % 64 == 0 and g.s == 1 and g.cx_offset == 0
+            and g.cx_total == g.Cx and _rup(g.Cy * g.kh * g.kw, 64) <= 256)
+
+
+def conv_backward_packed_out(g: ConvGeom, packs: WeightPacks, w, x, x_dims, dy, dy_layout, need_dx, need_dw, scale,
+                             x_dtype):
+    """(dX, dW) of a stride-1 convolution with few output channels through P = im2col(dY) (flipped window):
+    dX = P @ Wd^T (a 1x1 tcgen05 gather-GEMM, Wd = the data-gradient weight pack) and dW = X^T @ P (tcgen05 weight-gradient
+    kernel with X as the pixel-major M operand and P as the gathered operand, T = 1)."""
+    N, Hx, Wx, Cx = x_dims
+    _, Hy, Wy, Cy, ds = _dims(dy, dy_layout)
+    K = g.kh * g.kw * Cy
+    Kp = _rup(K, 64)
+    P = _lib.K.im2col_pack(dy, ds, N, Hy, Wy, Cy, g.kh, g.kw, 1, g.p, Hx, Wx, Kp, flip=True)
+    ps = cl_strides(Hx, Wx, Kp)
+    dx = dw = None
+    if need_dx:
+        wmat, ldw = packs.get(("dgrad", True) + g.key(), w, lambda: _pack_dgrad(g, w, True))[0]
+        assert ldw == Kp
+        dx, xs = _empty(N, Hx, Wx, Cx, "cl", dy.device, x_dtype)
+        d = ConvDesc(B=N, Qh=Hx, Qw=Wx, Cin=Kp, Cout=Cx, Th=1, Tw=1, in_sy=1, in_sx=1, tap_sy=1, tap_sx=1, tap_oy=0,
+                     tap_ox=0, Hi=Hx, Wi=Wx, up_shift=0, in_sn=ps[0], in_sh=ps[1], in_sw=ps[2], in_sc=ps[3], out_sy=1,
+                     out_sx=1, out_oy=0, out_ox=0, Ho=Hx, Wo=Wx, out_sn=xs[0], out_sh=xs[1], out_sw=xs[2], out_sc=xs[3],
+                     ldw=ldw, relu=0, scale_rows=_scale_rows(scale, N * Hx * Wx))
+        _lib.K.conv_gemm(d, P, wmat, None, scale, dx, True)
+    if need_dw:
+        xb = as_bf16(x)
+        xs = cl_strides(Hx, Wx, Cx)
+        g1 = ConvGeom(Kp, Cx, 1, 1, 1, 0)
+        splits = _wgrad_splits(g1, N * Hx * Wx, True)
+        ws = torch.empty((splits * Cx * Kp,), dtype=torch.float32, device=dy.device)
+        d = ConvDesc(B=N, Qh=Hx, Qw=Wx, Cin=Kp, Cout=Cx, Th=1, Tw=1, in_sy=1, in_sx=1, tap_sy=1, tap_sx=1, tap_oy=0,
+                     tap_ox=0, Hi=Hx, Wi=Wx, up_shift=0, in_sn=ps[0], in_sh=ps[1], in_sw=ps[2], in_sc=ps[3], out_sy=1,
+                     out_sx=1, out_oy=0, out_ox=0, Ho=Hx, Wo=Wx, out_sn=xs[0], out_sh=xs[1], out_sw=xs[2], out_sc=xs[3],
+                     ldw=Kp, relu=0)
+        _lib.K.wgrad_gemm(d, xb, P, ws, splits, True)
+        tmp = torch.empty((Cx, Kp), dtype=torch.float32, device=dy.device)
+        _lib.K.wgrad_reduce(ws, splits, Cx, 1, 1, Kp, tmp, 0, Kp, 0, 0, 1)
+        dw = torch.empty_like(w)
+        dw.copy_(tmp[:, :K].view(Cx, g.kh, g.kw, Cy).permute(3, 0, 1, 2))     # [ci][(ky,kx,co)] -> (co, ci, ky, kx)
+    return dx, dw
+
+
 def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bias=None, scale=None, relu=False,
                  out_dtype=None):
     """Y = epilogue(conv(X, W)); the tcgen05 path takes a bf16 activation (cast here if it is not), the fp32 path either"""
@@ -343,10 +389,8 @@ def bias_grad(dy: torch.Tensor, layout: str) -> torch.Tensor:
     if layout == "cl":
         return _lib.K.colsum(dy.reshape(-1, dy.shape[-1]))
     N, C, H, W = dy.shape
-    per = _lib.K.pool_fwd(dy, N * C, H, W, 1, H, 1.0) if H == W else None
-    if per is None:
-        raise _lib.B200Error("bias_grad: non-square NCHW output")
-    return _lib.K.colsum(per.reshape(N, C))
+    per = _lib.K.rowsum(dy.contiguous().view(N * C, H * W))          # per-(n, c) sums, then over n
+    return _lib.K.colsum(per.view(N, C))
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -466,6 +510,12 @@ class _ConvFn(torch.autograd.Function):
         else:
             dgrad_tc, wgrad_tc = _tc_fwd_ok(g, ctx.out_layout), _tc_wgrad_ok(g, ctx.out_layout, ctx.x_layout)
         packed = ctx.packed
+        if (not ctx.transposed) and sn is None and _packed_out_ok(g, ctx.x_layout) and (need_dx or need_dw):
+            dx, dw = conv_backward_packed_out(g, packs, w, x, ctx.x_dims, dy, ctx.out_layout, need_dx, need_dw, scale,
+                                              ctx.x_dtype)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = bias_grad(dy, ctx.out_layout)
+            return dx, dw, db, None, None, None, None, None, None, None, None, None
         dyb = as_bf16(dy) if ((need_dx and dgrad_tc) or (need_dw and (wgrad_tc or packed))) else None   # one cast for both GEMMs
         if need_dx:
             dy_op = dyb if dgrad_tc else dy

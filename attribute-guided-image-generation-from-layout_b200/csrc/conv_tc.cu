@@ -1407,7 +1407,11 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
     const int num_kb = d->Th * d->Tw * (d->Cin / BK);
     int kbps = (num_kb + splits - 1) / splits;
     splits = (num_kb + kbps - 1) / kbps;          // no empty split
-    if (atma && splits == 1 && g_use_persist && BN >= 64 && num_kb <= 24) {
+    static const int persist_max_kb = []() {
+        const char* e = getenv("B200_TC_PERSIST_MAXKB");      // experiments only
+        return e ? atoi(e) : (1 << 30);       // measured: the persistent kernel wins for every K-loop length
+    }();
+    if (atma && splits == 1 && g_use_persist && BN >= 64 && num_kb <= persist_max_kb) {
         // persistent path: operand ring running ahead across tiles, double-buffered TMEM accumulator.  Two co-resident
         // CTAs per SM with a shallower ring each (g_use_persist == 2, short K loops: two epilogue warp sets interleave)
         // or one CTA per SM with a deep ring.

@@ -330,6 +330,65 @@ __global__ void colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int
         ws[(int64_t)blockIdx.x * C + c] = s;
     }
 }
+// vector variant of the column sums: a block covers CT*V channels (CT channel threads, a power of two <= 16) x 256/CT
+// rows per pass; per-thread fp64 accumulation, fixed-order tree (warp shuffles across the lanes sharing a channel slot,
+// then the 8 warps through shared memory)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const T* __restrict__ x, int64_t rows, int C,
+                                                                int64_t rows_per_chunk, int ct,
+                                                                double* __restrict__ ws) {
+    constexpr int V = VecIO<T>::V;
+    __shared__ double sm[8 * 16 * V];
+    const int c0 = blockIdx.y * ct * V;
+    const int c = c0 + (threadIdx.x % ct) * V;
+    const int rstep = 256 / ct;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
+    const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+    double s[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) s[i] = 0.0;
+#pragma unroll 2
+    for (int64_t r = r0 + threadIdx.x / ct; r < r1; r += rstep) {
+        float v[V];
+        VecIO<T>::load(x + r * C + c, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) s[i] += (double)v[i];
+    }
+    for (int o = 16; o >= ct; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < ct) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) sm[(warp * 16 + lane) * V + i] = s[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < ct * V) {
+        const int slot = threadIdx.x / V, i = threadIdx.x % V;
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sm[(w * 16 + slot) * V + i];
+        ws[(int64_t)blockIdx.x * C + c0 + threadIdx.x] = t;
+    }
+}
+
+// out[r] = sum_l x[r*L + l]: one block per row (bias gradient of an NCHW output: rows = (n, c), L = H*W), fixed order
+template <typename T>
+__global__ void __launch_bounds__(256) rowsum_kernel(const T* __restrict__ x, int64_t L, float* __restrict__ out) {
+    __shared__ double red[8];
+    const T* p = x + (int64_t)blockIdx.x * L;
+    double acc = 0.0;
+    for (int64_t l = threadIdx.x; l < L; l += 256) acc += (double)ldf(p + l);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < 8; ++k) s += red[k];
+        out[blockIdx.x] = (float)s;
+    }
+}
+
 // one warp per column: lanes stride over the chunks, fixed-order shuffle tree
 __global__ void colsum_final_kernel(const double* __restrict__ ws, int nchunks, int C, float* __restrict__ out) {
     int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -387,6 +446,40 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
     }
 }
 
+// 4 consecutive channels per thread (16-byte loads of the partials, 8 in flight): C % 4 == 0, total < 2^31.
+// Per element the splits are summed in the same order as the scalar kernel (bit-identical results).
+__global__ void wgrad_reduce_vec_kernel(const float* __restrict__ ws, int splits, int64_t split_stride, int M, int Th, int Tw,
+                                        int C, float* __restrict__ dst, int64_t s_m, int64_t s_ty, int64_t s_tx,
+                                        int64_t s_c, const float* __restrict__ scale, int accumulate) {
+    const uint32_t K = (uint32_t)(Th * Tw * C);
+    const uint32_t total4 = (uint32_t)M * K / 4;
+    const float alpha = scale ? *scale : 1.f;
+    for (uint32_t t4 = blockIdx.x * blockDim.x + threadIdx.x; t4 < total4; t4 += gridDim.x * blockDim.x) {
+        const uint32_t t = t4 * 4;
+        const uint32_t m = t / K, k = t - m * K;
+        const uint32_t tap = k / (uint32_t)C, c = k - tap * (uint32_t)C;
+        const uint32_t ty = tap / (uint32_t)Tw, tx = tap - ty * (uint32_t)Tw;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* p = ws + t;
+        int s = 0;
+        for (; s + 8 <= splits; s += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(p + (int64_t)(s + u) * split_stride);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        for (; s < splits; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(p + (int64_t)s * split_stride);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float* q = dst + (int64_t)m * s_m + (int64_t)ty * s_ty + (int64_t)tx * s_tx + (int64_t)c * s_c;
+        const float o[4] = {alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[e * s_c] = accumulate ? q[e * s_c] + o[e] : o[e];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // im2col packing of a FEW-channel convolution input (the 3-channel image / crop convolutions): row m = output pixel
 // (n, qy, qx), column k = (ky*kw + kx)*Cx + c, bf16, zero padded to Kp (a multiple of 64).  The packed matrix is the
@@ -397,7 +490,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
 template <typename T>
 __global__ void im2col_pack_kernel(const T* __restrict__ x, int64_t M, int Hx, int Wx, int Cx, int64_t sn, int64_t sh,
                                    int64_t sw, int64_t sc, int kh, int kw, int stride, int pad, int Hy, int Wy, int Kp,
-                                   bf16* __restrict__ out) {
+                                   int flip, bf16* __restrict__ out) {
     const int kg = threadIdx.x;
     int64_t off[8];
     int dy[8], dx[8];
@@ -408,8 +501,8 @@ __global__ void im2col_pack_kernel(const T* __restrict__ x, int64_t M, int Hx, i
         if (k < K) {
             const int tap = k / Cx, c = k - tap * Cx;
             const int ky = tap / kw, kx = tap - ky * kw;
-            dy[j] = ky - pad;
-            dx[j] = kx - pad;
+            dy[j] = flip ? pad - ky : ky - pad;      // flip: the transposed (data-gradient) window walk
+            dx[j] = flip ? pad - kx : kx - pad;
             off[j] = (int64_t)c * sc;
         } else {
             dy[j] = -(1 << 28);          // always out of bounds -> zero
@@ -674,9 +767,26 @@ extern "C" int b200_colsum(const void* x, int64_t rows, int C, int dt, float* ou
     int64_t rpc = (rows + nchunks - 1) / nchunks;
     if (rpc < 1) rpc = 1;
     dim3 grid(nchunks, (C + 31) / 32), block(32, 8);
-    B200_DISPATCH_DT(dt, T, { colsum_partial_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, rows, C, rpc, ws); });
+    B200_DISPATCH_DT(dt, T, {
+        constexpr int V = VecIO<T>::V;
+        const int tpr = C / V;
+        if (C % V == 0 && tpr <= 256 && (tpr & (tpr - 1)) == 0 && aligned16(x)) {
+            const int ct = tpr < 16 ? tpr : 16;
+            colsum_partial_vec_kernel<T><<<dim3(nchunks, tpr / ct), 256, 0, as_stream(stream)>>>((const T*)x, rows, C, rpc, ct, ws);
+        } else {
+            colsum_partial_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, rows, C, rpc, ws);
+        }
+    });
     B200_CHECK_LAUNCH();
     colsum_final_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, nchunks, C, out);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_rowsum(const void* x, int dt, int64_t rows, int64_t L, float* out, b200_stream_t stream) {
+    if (rows == 0) return 0;
+    B200_REQUIRE(rows < (1ll << 31) && L > 0, "rowsum: bad sizes");
+    B200_DISPATCH_DT(dt, T, { rowsum_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>((const T*)x, L, out); });
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -698,15 +808,19 @@ extern "C" int b200_wgrad_reduce(const float* ws, int splits, int64_t split_stri
                                  int accumulate, b200_stream_t stream) {
     int64_t total = (int64_t)M * Th * Tw * C;
     if (total == 0) return 0;
-    wgrad_reduce_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(ws, splits, split_stride, M, Th, Tw, C, dst,
-                                                                             s_m, s_ty, s_tx, s_c, scale, accumulate);
+    if ((C & 3) == 0 && (split_stride & 3) == 0 && total < (1ll << 31) && aligned16(ws))
+        wgrad_reduce_vec_kernel<<<grid_for(total / 4, 128, 16), 128, 0, as_stream(stream)>>>(ws, splits, split_stride, M, Th, Tw, C,
+                                                                                        dst, s_m, s_ty, s_tx, s_c, scale, accumulate);
+    else
+        wgrad_reduce_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(ws, splits, split_stride, M, Th, Tw, C, dst,
+                                                                                 s_m, s_ty, s_tx, s_c, scale, accumulate);
     B200_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int b200_im2col_pack(const void* x, int x_dt, int64_t N, int Hx, int Wx, int Cx, int64_t sn, int64_t sh,
                                 int64_t sw, int64_t sc, int kh, int kw, int stride, int pad, int Hy, int Wy, int Kp,
-                                void* out_bf16, b200_stream_t stream) {
+                                int flip, void* out_bf16, b200_stream_t stream) {
     const int64_t M = N * Hy * Wy;
     if (M == 0) return 0;
     B200_REQUIRE(Kp % 64 == 0 && Kp >= Cx * kh * kw && Kp <= 2048, "im2col_pack: Kp=%d must be a multiple of 64 covering K=%d", Kp, Cx * kh * kw);
@@ -717,7 +831,7 @@ extern "C" int b200_im2col_pack(const void* x, int x_dt, int64_t N, int Hx, int 
     const int grid = grid_for((M + rows - 1) / rows, 1, 16);
     B200_DISPATCH_DT(x_dt, T, {
         im2col_pack_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, M, Hx, Wx, Cx, sn, sh, sw, sc, kh, kw, stride,
-                                                                  pad, Hy, Wy, Kp, (bf16*)out_bf16);
+                                                                  pad, Hy, Wy, Kp, flip, (bf16*)out_bf16);
     });
     B200_CHECK_LAUNCH();
     return 0;

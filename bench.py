@@ -332,7 +332,13 @@ def run_b200(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # every rank leaves together and hard-exits: tearing down NCCL communicators that captured CUDA graphs still
+        # reference can block at interpreter shutdown, and the result line is already out
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def kernel_roofline(ts, b, args):

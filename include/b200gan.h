@@ -235,10 +235,14 @@ int b200_colsum(const void* x, int64_t rows, int C, int dt, float* out, double* 
  * out[m][k] (bf16, row length Kp, a multiple of 64) = x[n, c, qy*stride + ky - pad, qx*stride + kx - pad] (0 outside the
  * image) with m = (n*Hy + qy)*Wy + qx and k = (ky*kw + kx)*Cx + c; columns k >= Cx*kh*kw are zero.  x is addressed with
  * element strides (sn, sh, sw, sc), storage type x_dt.  The result is the channel-last activation of an equivalent 1x1
- * convolution with Kp input channels. */
+ * convolution with Kp input channels.  flip != 0 walks the transposed window, x[n, c, qy + pad - ky, qx + pad - kx]
+ * (stride 1): the im2col matrix of an output gradient, shared by the data gradient and the weight gradient of a
+ * convolution with few OUTPUT channels (Decoder c4, generator_obj_att.py:572). */
 int b200_im2col_pack(const void* x, int x_dt, int64_t N, int Hx, int Wx, int Cx, int64_t sn, int64_t sh, int64_t sw,
-                     int64_t sc, int kh, int kw, int stride, int pad, int Hy, int Wy, int Kp, void* out_bf16,
+                     int64_t sc, int kh, int kw, int stride, int pad, int Hy, int Wy, int Kp, int flip, void* out_bf16,
                      b200_stream_t stream);
+/* out[r] = sum_l x[r*L + l] (fixed order; the per-(n, c) sums of an NCHW output gradient: bias gradients) */
+int b200_rowsum(const void* x, int dt, int64_t rows, int64_t L, float* out, b200_stream_t stream);
 /* y[b][c][r] = x[b][r][c]: batched (R x C) transpose, i.e. NCHW <-> channel-last at module boundaries */
 int b200_transpose(const float* x, float* y, int B, int R, int C, b200_stream_t stream);
 /* row gather / scatter-overwrite for the time-major packing of ConvLSTM sequences: out[r] = x[src_row[r]] (rows of

@@ -129,15 +129,26 @@ class EmulKernels:
         self.launches += 1
         return x.to(torch.bfloat16)
 
-    def im2col_pack(self, x, x_strides, N, Hx, Wx, Cx, kh, kw, stride, pad, Hy, Wy, Kp):
+    def im2col_pack(self, x, x_strides, N, Hx, Wx, Cx, kh, kw, stride, pad, Hy, Wy, Kp, flip=False):
         self.launches += 1
         sn, sh, sw, sc = x_strides
         xv = torch.as_strided(x, (N, Cx, Hx, Wx), (sn, sc, sh, sw)).float()
-        cols = F.unfold(xv, (kh, kw), padding=pad, stride=stride)              # (N, Cx*kh*kw, Hy*Wy), row = c*kh*kw + tap
-        cols = cols.view(N, Cx, kh * kw, Hy * Wy).permute(0, 3, 2, 1).reshape(N * Hy * Wy, kh * kw * Cx)
-        out = torch.zeros((N * Hy * Wy, Kp), dtype=torch.bfloat16)
-        out[:, :kh * kw * Cx] = cols.to(torch.bfloat16)
-        return out
+        out = torch.zeros((N, Hy, Wy, Kp), dtype=torch.float32)
+        qy = torch.arange(Hy)[:, None]
+        qx = torch.arange(Wy)[None, :]
+        for ky in range(kh):
+            for kx in range(kw):
+                iy = qy * stride + (pad - ky if flip else ky - pad)
+                ix = qx * stride + (pad - kx if flip else kx - pad)
+                ok = (iy >= 0) & (iy < Hx) & (ix >= 0) & (ix < Wx)                            # (Hy, Wy)
+                g = xv[:, :, iy.clamp(0, Hx - 1).expand(Hy, Wy), ix.clamp(0, Wx - 1).expand(Hy, Wy)]   # (N, Cx, Hy, Wy)
+                k0 = (ky * kw + kx) * Cx
+                out[..., k0:k0 + Cx] = torch.where(ok, g, torch.zeros(())).permute(0, 2, 3, 1)
+        return out.reshape(N * Hy * Wy, Kp).to(torch.bfloat16)
+
+    def rowsum(self, x2d):
+        self.launches += 1
+        return x2d.double().sum(1).float()
 
     def conv_gemm(self, d, inp, wmat, bias, scale, out, tc):
         self.launches += 1

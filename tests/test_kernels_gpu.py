@@ -191,6 +191,14 @@ def test_im2col_pack_bit_exact(K, case):
     got = K.im2col_pack(xd.cuda(), strides, N, H, H + 3, Cx, k, k, s, p, Hy, Wy, Kp)
     want = E.im2col_pack(xd, strides, N, H, H + 3, Cx, k, k, s, p, Hy, Wy, Kp)
     assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
+    if s == 1:      # transposed window walk (the im2col matrix of an output gradient), rows over the conv INPUT grid
+        Hi, Wi = H + 2 * p - k + 1, H + 3 + 2 * p - k + 1
+        dyv = torch.randn(N, Cx, Hi, Wi, generator=g)
+        dyd = _to_layout(dyv, layout)
+        st = ops.nchw_strides(Cx, Hi, Wi) if layout == "nchw" else ops.cl_strides(Hi, Wi, Cx)
+        got = K.im2col_pack(dyd.cuda(), st, N, Hi, Wi, Cx, k, k, 1, p, H, H + 3, Kp, flip=True)
+        want = E.im2col_pack(dyd, st, N, Hi, Wi, Cx, k, k, 1, p, H, H + 3, Kp, flip=True)
+        assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
