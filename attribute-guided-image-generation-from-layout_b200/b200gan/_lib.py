@@ -419,7 +419,7 @@ class Kernels:
         dev = u.device
         if inv_out is None:
             inv_out = torch.empty((1,), dtype=torch.float32, device=dev)
-        ws = torch.empty((8 * w + h,), dtype=torch.float32, device=dev)
+        ws = torch.empty((32 * w + h,), dtype=torch.float32, device=dev)
         self._check(self.lib.b200_sn_power_iter(_ptr(W2d_param), h, w, _ptr(u), _ptr(v), int(bool(do_iter)),
                                                 C.c_float(eps), _ptr(sigma_out), _ptr(inv_out), _ptr(ws), _stream()),
                     "b200_sn_power_iter")

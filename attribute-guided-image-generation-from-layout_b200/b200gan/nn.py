@@ -84,12 +84,49 @@ class Linear(nn.Linear):
         return ops.linear(x, _weight(self), self.bias, self._packs, relu, _sn_call(self, groups), None, out_dtype)
 
 
+# ---- num_batches_tracked bookkeeping -----------------------------------------------------------------------------
+# Every training-mode BN forward increments its int64 counter (nn.BatchNorm semantics).  Inside a training step the ~70
+# one-element increments are deferred and applied with ONE multi-tensor add when the step ends (count_batches / flush).
+_DEFER_COUNTS = False
+_PENDING_COUNTS = {}
+
+
+def count_batches(counter: torch.Tensor, n: int):
+    if _DEFER_COUNTS:
+        key = id(counter)
+        ent = _PENDING_COUNTS.get(key)
+        if ent is None:
+            _PENDING_COUNTS[key] = [counter, n]
+        else:
+            ent[1] += n
+    else:
+        counter.add_(n)
+
+
+class deferred_batch_counts:
+    """with deferred_batch_counts(): ...  — the counters are brought up to date on exit"""
+
+    def __enter__(self):
+        global _DEFER_COUNTS
+        self.prev, _DEFER_COUNTS = _DEFER_COUNTS, True
+        return self
+
+    def __exit__(self, *exc):
+        global _DEFER_COUNTS
+        _DEFER_COUNTS = self.prev
+        if not _DEFER_COUNTS and _PENDING_COUNTS:
+            ents = list(_PENDING_COUNTS.values())
+            _PENDING_COUNTS.clear()
+            torch._foreach_add_([e[0] for e in ents], [e[1] for e in ents])
+        return False
+
+
 class BatchNorm2d(nn.BatchNorm2d):
     """Works on (..., C) channel-last tensors (also serves BatchNorm1d's (B, C) case)."""
 
     def forward(self, x, relu=False, residual=None, groups=1):
         if self.training and self.track_running_stats:
-            self.num_batches_tracked.add_(groups)
+            count_batches(self.num_batches_tracked, groups)
         w = self.weight if self.affine else None
         b = self.bias if self.affine else None
         return ops.batch_norm(x, w, b, self.running_mean, self.running_var, self.training, relu, residual, groups)
@@ -98,7 +135,7 @@ class BatchNorm2d(nn.BatchNorm2d):
 class BatchNorm1d(nn.BatchNorm1d):
     def forward(self, x, relu=False, groups=1):
         if self.training and self.track_running_stats:
-            self.num_batches_tracked.add_(groups)
+            count_batches(self.num_batches_tracked, groups)
         return ops.batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var, self.training, relu, None,
                               groups)
 

@@ -435,7 +435,7 @@ class SNPlan:
             h, wd = W.shape[0], W[0].numel()
             layers.append((W, m.weight_u, m.weight_v, h, wd, so, wo))
             so += groups * (1 + h + wd)
-            wo += _rup(8 * wd + h, 4)          # 16-byte aligned scratch per layer (vector stores)
+            wo += _rup(32 * wd + h, 4)          # 16-byte aligned scratch per layer (vector stores)
         self.layers = layers
         self.stage = torch.empty((so,), dtype=torch.float32, device=dev)
         self.ws = torch.empty((wo,), dtype=torch.float32, device=dev)

@@ -175,6 +175,11 @@ class TrainStep:
     def step(self, b: Dict[str, torch.Tensor], optimizer_step: bool = True, seeds=None):
         """b: device batch from to_device().  seeds: optional (seed_d, seed_g) for torch.manual_seed before each generator
         forward (pins the CropEncoder noise like the parity harness of the oracle)."""
+        from . import nn as bnn
+        with bnn.deferred_batch_counts():
+            return self._step(b, optimizer_step, seeds)
+
+    def _step(self, b, optimizer_step, seeds):
         from models.bilinear import crop_bbox_batch
         D_i, D_o, D_a = self.d_nets
         b = dict(b)

@@ -753,7 +753,7 @@ extern "C" int b200_reparam_bwd(const float* dz, const float* logvar, const floa
 
 extern "C" int b200_bn_chunks(int64_t rows, int C) {
     int cblocks = (C + 31) / 32;
-    int64_t target = (int64_t)kNumSMs * 8 / cblocks;
+    int64_t target = (int64_t)kNumSMs * 4 / cblocks;      // 256-thread vector blocks: ~4 per SM saturate HBM
     if (target < 1) target = 1;
     int64_t by_rows = (rows + 31) / 32;
     int64_t n = by_rows < target ? by_rows : target;

@@ -6,7 +6,7 @@
 
 namespace b200 {
 
-constexpr int kSnRowChunks = 8;
+constexpr int kSnRowChunks = 32;     // row chunks of the W^T u pass (partial sums per chunk, summed in order)
 
 // partial[chunk][j] = sum_{i in chunk} W[i][j] * u[i]
 __global__ void sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u, int h, int w, int rows_per_chunk,

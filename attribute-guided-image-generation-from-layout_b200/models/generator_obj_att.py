@@ -38,7 +38,7 @@ class ConditionalBatchNorm2d(nn.Module):
 
     def forward(self, x, y, relu=False, groups=1):
         if self.bn.training:
-            self.bn.num_batches_tracked.add_(groups)
+            bnn.count_batches(self.bn.num_batches_tracked, groups)
         return ops.cond_batch_norm(x, self.embed.weight, y, self.bn.running_mean, self.bn.running_var, self.bn.training,
                                    relu, groups)
 

@@ -36,7 +36,7 @@ class SPADE(nn.Module):
         gb = ops.conv2d(actv, w, b, self._gb_geom, self._gb_packs)
         bn = self.param_free_norm
         if bn.training:
-            bn.num_batches_tracked.add_(groups)
+            bnn.count_batches(bn.num_batches_tracked, groups)
         return ops.spade_norm(x, gb, bn.running_mean, bn.running_var, bn.training, relu, groups)
 
     def forward(self, x, segmap):

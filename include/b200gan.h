@@ -252,7 +252,7 @@ int b200_permute_rows(const void* x, const int32_t* src_row, void* out, int rows
 /* ------------------------------------------------------------------------------------------------
  * Spectral normalisation — replaces torch.nn.utils.spectral_norm's pre-forward hook installed by add_sn
  * (discriminator.py:15-22): one power iteration in place on u (h) and v (w), sigma = u.(W v); W (h,w) row-major
- * view of weight_orig.  *sigma_out = sigma, *inv_sigma_out = 1/sigma.  ws: 8*w + h floats.
+ * view of weight_orig.  *sigma_out = sigma, *inv_sigma_out = 1/sigma.  ws: 32*w + h floats.
  * b200_sn_grad: dW = g*inv_sigma - (<g, W> * inv_sigma^2) * u v^T  (gradient through W/sigma with u, v constant),
  * g = gradient w.r.t. the normalised weight, same layout as W.  ws: 1024 doubles.
  */
@@ -264,12 +264,12 @@ int b200_sn_grad(const float* g, const float* W, const float* u, const float* v,
 /* The same power iteration for EVERY spectral-normalised layer of a network at once (4 launches per iteration instead
  * of 4 per layer), `iters` times in sequence — one per batched call of the network.  `layers` is a DEVICE array of
  * n_layers descriptors; iteration `it` of layer l records inv[it] = 1/sigma, u_hist[it*h ..], v_hist[it*w ..] (the
- * vectors that sigma was computed with; either history pointer may be NULL).  ws: 8*w + h floats per layer. */
+ * vectors that sigma was computed with; either history pointer may be NULL).  ws: 32*w + h floats per layer. */
 typedef struct {
     const float* W;     /* (h, w) row-major view of weight_orig */
     float* u;           /* (h,)  updated in place */
     float* v;           /* (w,)  updated in place */
-    float* ws;          /* 8*w + h floats of scratch */
+    float* ws;          /* 32*w + h floats of scratch */
     float* inv;         /* (iters,) */
     float* u_hist;      /* (iters, h) or NULL */
     float* v_hist;      /* (iters, w) or NULL */
