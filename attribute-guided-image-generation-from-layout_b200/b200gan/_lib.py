@@ -69,6 +69,17 @@ def _dt(t: torch.Tensor) -> int:
     raise B200Error("activation tensors are fp32 or bf16, got %s" % t.dtype)
 
 
+def vec_layout_ok(x2d: torch.Tensor) -> bool:
+    """(rows, C) activation layouts the 16-byte vector normalisation kernels take: C/V threads per row, a power of two
+    <= 256 (V = 8 bf16 / 4 fp32 channels) — mirrors vec_ok() in csrc/norm.cu"""
+    rows, Cc = x2d.shape
+    v = 8 if x2d.dtype == torch.bfloat16 else 4
+    if Cc % v or rows >= 2 ** 31:
+        return False
+    tpr = Cc // v
+    return 1 <= tpr <= 256 and (tpr & (tpr - 1)) == 0
+
+
 def _same_dt(*ts):
     ts = [t for t in ts if t is not None]
     d = _dt(ts[0])
@@ -265,7 +276,7 @@ class Kernels:
         seg_sums = torch.empty((nseg * Cc * 2,), dtype=torch.float64, device=dev)
         self._check(self.lib.b200_norm_bwd_reduce(_ptr(dy), _ptr(x2d), _ptr(y), dt, C.c_int64(rows), Cc, int(groups),
                                                   _ptr(mean), _ptr(var), C.c_float(eps), int(mode), _ptr(gamma),
-                                                  _ptr(idx), seg, int(bool(relu)), _ptr(seg_sums), _stream()),
+                                                  _ptr(idx), seg, int(relu), _ptr(seg_sums), _stream()),
                     "b200_norm_bwd_reduce")
         s = torch.empty((groups * Cc * 2,), dtype=torch.float32, device=dev)
         dgamma = dbeta = dtable = dgb = None
@@ -283,7 +294,7 @@ class Kernels:
         self._check(self.lib.b200_norm_bwd_apply(_ptr(dy), _ptr(x2d), _ptr(y), _ptr(dx), dt, C.c_int64(rows), Cc,
                                                  int(groups), _ptr(mean), _ptr(var), C.c_float(eps), int(mode),
                                                  _ptr(gamma), _ptr(idx), int(rows_per_seg) if mode == MODE_CBN else 1,
-                                                 int(bool(relu)), _ptr(s), _ptr(dgb), _stream()), "b200_norm_bwd_apply")
+                                                 int(relu), _ptr(s), _ptr(dgb), _stream()), "b200_norm_bwd_apply")
         return dx, dgamma, dbeta, dtable, dgb
 
     # ---- elementwise / pooling / layout ------------------------------------------------------------------------
@@ -419,7 +430,7 @@ class Kernels:
         dev = u.device
         if inv_out is None:
             inv_out = torch.empty((1,), dtype=torch.float32, device=dev)
-        ws = torch.empty((32 * w + h,), dtype=torch.float32, device=dev)
+        ws = torch.empty((8 * w + h,), dtype=torch.float32, device=dev)
         self._check(self.lib.b200_sn_power_iter(_ptr(W2d_param), h, w, _ptr(u), _ptr(v), int(bool(do_iter)),
                                                 C.c_float(eps), _ptr(sigma_out), _ptr(inv_out), _ptr(ws), _stream()),
                     "b200_sn_power_iter")
@@ -431,6 +442,18 @@ class Kernels:
         ws = torch.empty((1024,), dtype=torch.float64, device=W.device)
         self._check(self.lib.b200_sn_grad(_ptr(g), _ptr(W), _ptr(u), _ptr(v), _ptr(inv_sigma), _ptr(dW), h, w,
                                           int(bool(accumulate)), _ptr(ws), _stream()), "b200_sn_grad")
+        return dW
+
+    def sn_wgrad_finish(self, ws, groups, spg, Cy, T, Cx, W, u_hist, v_hist, inv, dW):
+        """dW of `groups` batched calls of a spectral-normalised layer from the group-aligned partials of one wgrad launch"""
+        dev = W.device
+        n = Cy * Cx * T
+        Gbuf = torch.empty((groups * n,), dtype=torch.float32, device=dev)
+        parts = int(self.lib.b200_sn_wgrad_parts(int(Cy), int(Cx)))
+        dot = torch.empty((groups * parts,), dtype=torch.float64, device=dev)
+        self._check(self.lib.b200_sn_wgrad_finish(_ptr(ws), int(groups), int(spg), C.c_int64(Cy * T * Cx), int(Cy), int(T),
+                                                  int(Cx), _ptr(W), _ptr(u_hist), _ptr(v_hist), _ptr(inv), _ptr(Gbuf),
+                                                  _ptr(dot), _ptr(dW), _stream()), "b200_sn_wgrad_finish")
         return dW
 
     def sn_table(self, layers, stage, ws, iters):

@@ -8,6 +8,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import torch
 
 from . import _lib
@@ -342,7 +344,10 @@ def _wgrad_splits(g: ConvGeom, Q: int, tc: bool, rows=None, cols=None) -> int:
         tiles = -(-rows // 64) * -(-cols // 64)
     else:
         tiles = -(-g.Cy // 64) * g.kh * g.kw * -(-g.Cx // 64)
-    splits = max(1, min(-(-592 // tiles), max(1, Q // 256), 256 if rows is not None else 64))
+    # tcgen05 kernel: one wave of two co-resident CTAs per SM; more splits only add partial-result traffic (every split
+    # writes and the reduction re-reads a full fp32 copy of the gradient)
+    target = int(os.environ.get("B200_WGRAD_TARGET", "296")) if tc else 592
+    splits = max(1, min(-(-target // tiles), max(1, Q // 256), 256 if rows is not None else 64))
     return splits
 
 
@@ -383,6 +388,42 @@ def conv_wgrad(g: ConvGeom, x, x_layout, dy, dy_layout, dw: torch.Tensor, accumu
     _lib.K.wgrad_reduce(ws, splits, g.Cy, g.kh, g.kw, g.Cx, dw, g.cx_offset * kk, g.cx_total * kk, g.kw, 1, kk,
                         accumulate=accumulate)
     return dw
+
+
+GROUPED_SN_WGRAD = True      # one weight-gradient GEMM for all batched calls of a spectral-normalised layer
+
+
+def _sn_group_splits(g: ConvGeom, Q: int, groups: int) -> int:
+    """pixel splits PER CALL for the grouped spectral-norm weight gradient (0 = not applicable): the calls' row ranges must
+    be whole numbers of 64-pixel k-blocks of equal size"""
+    if not GROUPED_SN_WGRAD or groups < 2 or groups > 8 or Q % groups:
+        return 0
+    Qg = Q // groups
+    kk = g.kh * g.kw
+    if kk > 64 or g.Cy >= 65536 or g.Cy * g.Cx * kk >= 2 ** 31 or g.cx_offset != 0 or g.cx_total != g.Cx:
+        return 0
+    spg = max(1, _wgrad_splits(g, Q, True) // groups)
+    while spg > 1 and Qg % (64 * spg):
+        spg -= 1
+    return spg if Qg % (64 * spg) == 0 else 0
+
+
+def conv_wgrad_sn_grouped(g: ConvGeom, x, dy, sn: "SNCall", w, spg: int) -> torch.Tensor:
+    """dW through W / sigma_g for sn.groups batched calls (x, dy: bf16 channel-last, rows of call g contiguous): one
+    tcgen05 weight-gradient launch with call-aligned pixel splits, then b200_sn_wgrad_finish"""
+    N, Hx, Wx, Cx, xs = _dims(x, "cl")
+    _, Hy, Wy, Cy, ds = _dims(dy, "cl")
+    kk = g.kh * g.kw
+    K = kk * g.Cx
+    splits = sn.groups * spg
+    ws = torch.empty((splits * g.Cy * K,), dtype=torch.float32, device=x.device)
+    d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=g.Cx, Cout=g.Cy, Th=g.kh, Tw=g.kw, in_sy=g.s, in_sx=g.s, tap_sy=1, tap_sx=1,
+                 tap_oy=-g.p, tap_ox=-g.p, Hi=Hx, Wi=Wx, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3],
+                 out_sy=1, out_sx=1, out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ds[0], out_sh=ds[1], out_sw=ds[2],
+                 out_sc=ds[3], ldw=K, relu=0)
+    _lib.K.wgrad_gemm(d, dy, x, ws, splits, True)
+    dw = torch.empty_like(w)
+    return _lib.K.sn_wgrad_finish(ws, sn.groups, spg, g.Cy, kk, g.Cx, w, sn.u_hist, sn.v_hist, sn.inv, dw)
 
 
 def bias_grad(dy: torch.Tensor, layout: str) -> torch.Tensor:
@@ -435,7 +476,7 @@ class SNPlan:
             h, wd = W.shape[0], W[0].numel()
             layers.append((W, m.weight_u, m.weight_v, h, wd, so, wo))
             so += groups * (1 + h + wd)
-            wo += _rup(32 * wd + h, 4)          # 16-byte aligned scratch per layer (vector stores)
+            wo += _rup(8 * wd + h, 4)          # 16-byte aligned scratch per layer (vector stores)
         self.layers = layers
         self.stage = torch.empty((so,), dtype=torch.float32, device=dev)
         self.ws = torch.empty((wo,), dtype=torch.float32, device=dev)
@@ -546,6 +587,10 @@ class _ConvFn(torch.autograd.Function):
                 else:
                     conv_wgrad(g, dy_op, ctx.out_layout, x, ctx.x_layout, gw)
                 dw = gw
+            elif wgrad_tc and _sn_group_splits(g, dy_op.shape[0] * dy_op.shape[1] * dy_op.shape[2], sn.groups) > 0:
+                assert not ctx.transposed
+                spg = _sn_group_splits(g, dy_op.shape[0] * dy_op.shape[1] * dy_op.shape[2], sn.groups)
+                dw = conv_wgrad_sn_grouped(g, x, dy_op, sn, w, spg)
             else:
                 # batched calls have their own sigma, u, v: gradient through W / sigma_g per group of rows
                 assert not ctx.transposed
@@ -597,9 +642,13 @@ class _NormFn(torch.autograd.Function):
         g2 = gamma.reshape(-1, 2 * C) if mode == MODE_SPADE else gamma
         r2 = residual.reshape(-1, C) if residual is not None else None
         y = _lib.K.norm_fwd(x2, mean, var, BN_EPS, mode, g2, beta, idx, rows_per_seg, r2, relu, groups)
-        ctx.mode, ctx.relu, ctx.rows_per_seg, ctx.num_classes, ctx.training = mode, relu, rows_per_seg, num_classes, training
+        # conditional batch norm + ReLU: the backward recomputes the ReLU mask from x (gamma * xhat + beta > 0) instead of
+        # reading the saved output (relu flag 2; one activation read less per backward pass, y is not kept alive)
+        recompute = bool(relu) and mode == MODE_CBN and residual is None and _lib.vec_layout_ok(x2)
+        relu_flag = 2 if recompute else int(bool(relu))
+        ctx.mode, ctx.relu, ctx.rows_per_seg, ctx.num_classes, ctx.training = mode, relu_flag, rows_per_seg, num_classes, training
         ctx.has_residual = residual is not None
-        ctx.save_for_backward(x2, y if relu else None, mean, var, g2, idx)
+        ctx.save_for_backward(x2, y if relu_flag == 1 else None, mean, var, g2, idx)
         ctx.shape = shape
         return y.view(shape)
 

@@ -67,6 +67,22 @@ __global__ void crop_fwd_kernel(const float* __restrict__ feats, const float* __
     }
 }
 
+// The sampling coordinate of crop row i (column j) is monotone in i: only the few rows whose floor lands on y - 1 or y
+// contribute to image row y.  [lo, hi) is a conservative superset of them from the linear end points (one extra index
+// either side, the whole range for degenerate / non-increasing boxes); the exact floor predicate below still decides,
+// so the contributing set and its ascending summation order are those of the full scan.
+__device__ __forceinline__ void tap_range(float c_first, float c_last, int S, int target, int& lo, int& hi) {
+    lo = 0;
+    hi = S;
+    const float step = S > 1 ? (c_last - c_first) / (float)(S - 1) : 0.f;
+    if (step > 1e-3f) {
+        const float a = ((float)target - 1.f - c_first) / step, b = ((float)target + 1.f - c_first) / step;
+        const int l = (int)floorf(a) - 1, h = (int)ceilf(b) + 2;
+        lo = l < 0 ? 0 : (l > S ? S : l);
+        hi = h < 0 ? 0 : (h > S ? S : h);
+    }
+}
+
 // pass 1: T[b,c,y,j] = sum_i wy(i -> y) * dcrops[b,c,i,j]   (rows of the crop that touch image row y, ascending i)
 __global__ void crop_bwd_rows_kernel(const float* __restrict__ dcrops, const float* __restrict__ boxes,
                                      const float* __restrict__ wy, float* __restrict__ T, int C, int H, int B, int HH,
@@ -79,8 +95,11 @@ __global__ void crop_bwd_rows_kernel(const float* __restrict__ dcrops, const flo
         int b = (int)(t / ((int64_t)WW * H * C));
         const float* bx = boxes + b * 4;
         const float* d = dcrops + ((int64_t)b * C + c) * HH * WW + j;
+        int lo, hi;
+        tap_range(crop_coord(bx[1], bx[3], wy[0], wy[HH], H), crop_coord(bx[1], bx[3], wy[HH - 1], wy[2 * HH - 1], H), HH, y,
+                  lo, hi);
         float acc = 0.f;
-        for (int i = 0; i < HH; ++i) {
+        for (int i = lo; i < hi; ++i) {
             float iy = crop_coord(bx[1], bx[3], wy[i], wy[HH + i], H);
             float y0f = floorf(iy);
             int y0 = (int)y0f;
@@ -107,7 +126,10 @@ __global__ void crop_bwd_cols_kernel(const float* __restrict__ T, const float* _
             int b = box_order[k];
             const float* bx = boxes + b * 4;
             const float* row = T + (((int64_t)b * C + c) * H + y) * WW;
-            for (int j = 0; j < WW; ++j) {
+            int lo, hi;
+            tap_range(crop_coord(bx[0], bx[2], wx[0], wx[WW], W), crop_coord(bx[0], bx[2], wx[WW - 1], wx[2 * WW - 1], W), WW,
+                      x, lo, hi);
+            for (int j = lo; j < hi; ++j) {
                 float ix = crop_coord(bx[0], bx[2], wx[j], wx[WW + j], W);
                 float x0f = floorf(ix);
                 int x0 = (int)x0f;

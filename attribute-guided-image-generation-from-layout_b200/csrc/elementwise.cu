@@ -249,6 +249,51 @@ __global__ void mask_outer_bwd_kernel(const T* __restrict__ dout, const float* _
     }
 }
 
+// vector variant: one block per object; a thread owns V channels (16 bytes) of a fixed slot and walks the pixels with
+// stride 256 / (C / V); fixed-order tree over the pixel lanes (warp shuffles, then the 8 warps).  C / V a power of two <= 32.
+template <typename T>
+__global__ void __launch_bounds__(256) mask_outer_bwd_vec_kernel(const T* __restrict__ dout, const float* __restrict__ mask,
+                                                                float* __restrict__ dv, int H, int W, int C) {
+    constexpr int V = VecIO<T>::V;
+    __shared__ float sm[8][32 * V];
+    const int o = blockIdx.x;
+    const int ct = C / V;
+    const int slot = threadIdx.x % ct;
+    const int pstep = 256 / ct;
+    const int Wp = W + 2;
+    const T* base = dout + (int64_t)o * (H + 2) * Wp * C + slot * V;
+    const float* mk = mask + (int64_t)o * H * W;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+#pragma unroll 4
+    for (int p = threadIdx.x / ct; p < H * W; p += pstep) {
+        const float m = mk[p];
+        if (m != 0.f) {
+            const int y = p / W, x = p - y * W;
+            float v[V];
+            VecIO<T>::load(base + ((int64_t)(y + 1) * Wp + (x + 1)) * C, v);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] += m * v[e];
+        }
+    }
+    for (int off = 16; off >= ct; off >>= 1) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < ct) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) sm[warp][lane * V + e] = acc[e];
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += sm[w][threadIdx.x];
+        dv[(int64_t)o * C + threadIdx.x] = s;
+    }
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // pre-activations and the hidden state are activations (T); the cell state and the saved gates stay fp32
@@ -347,7 +392,7 @@ __global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const T* __rest
     double s[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) s[i] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int64_t r = r0 + threadIdx.x / ct; r < r1; r += rstep) {
         float v[V];
         VecIO<T>::load(x + r * C + c, v);
@@ -446,38 +491,111 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
     }
 }
 
-// 4 consecutive channels per thread (16-byte loads of the partials, 8 in flight): C % 4 == 0, total < 2^31.
-// Per element the splits are summed in the same order as the scalar kernel (bit-identical results).
+// 4 consecutive channels per thread (16-byte loads of the partials) and 4 split lanes per element: lane = (element e =
+// lane & 7, split lane sl = lane >> 3); split lane sl sums splits sl, sl + 4, ... in order, the four partial sums are
+// combined as (p0 + p2) + (p1 + p3) by two shuffles — a fixed order.  C % 4 == 0, total < 2^31.
 __global__ void wgrad_reduce_vec_kernel(const float* __restrict__ ws, int splits, int64_t split_stride, int M, int Th, int Tw,
                                         int C, float* __restrict__ dst, int64_t s_m, int64_t s_ty, int64_t s_tx,
                                         int64_t s_c, const float* __restrict__ scale, int accumulate) {
     const uint32_t K = (uint32_t)(Th * Tw * C);
     const uint32_t total4 = (uint32_t)M * K / 4;
     const float alpha = scale ? *scale : 1.f;
-    for (uint32_t t4 = blockIdx.x * blockDim.x + threadIdx.x; t4 < total4; t4 += gridDim.x * blockDim.x) {
-        const uint32_t t = t4 * 4;
-        const uint32_t m = t / K, k = t - m * K;
-        const uint32_t tap = k / (uint32_t)C, c = k - tap * (uint32_t)C;
-        const uint32_t ty = tap / (uint32_t)Tw, tx = tap - ty * (uint32_t)Tw;
+    const int lane = threadIdx.x & 31, e = lane & 7, sl = lane >> 3;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t groups = (total4 + 7) / 8;                 // 8 elements per warp pass
+    for (uint32_t gidx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); gidx < groups; gidx += warps) {
+        const uint32_t t4 = gidx * 8 + e;
+        const bool live = t4 < total4;
+        const uint32_t t = (live ? t4 : 0) * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float* p = ws + t;
-        int s = 0;
-        for (; s + 8 <= splits; s += 8) {
-            float4 v[8];
+        int s = sl;
+        for (; s + 12 < splits; s += 16) {
+            float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(p + (int64_t)(s + u) * split_stride);
+            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(p + (int64_t)(s + 4 * u) * split_stride);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+            for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
         }
-        for (; s < splits; ++s) {
+        for (; s < splits; s += 4) {
             const float4 v = *reinterpret_cast<const float4*>(p + (int64_t)s * split_stride);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        float* q = dst + (int64_t)m * s_m + (int64_t)ty * s_ty + (int64_t)tx * s_tx + (int64_t)c * s_c;
-        const float o[4] = {alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) q[e * s_c] = accumulate ? q[e * s_c] + o[e] : o[e];
+        for (int o = 16; o >= 8; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        if (live && sl == 0) {
+            const uint32_t m = t / K, k = t - m * K;
+            const uint32_t tap = k / (uint32_t)C, c = k - tap * (uint32_t)C;
+            const uint32_t ty = tap / (uint32_t)Tw, tx = tap - ty * (uint32_t)Tw;
+            float* q = dst + (int64_t)m * s_m + (int64_t)ty * s_ty + (int64_t)tx * s_tx + (int64_t)c * s_c;
+            const float o4[4] = {alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i * s_c] = accumulate ? q[i * s_c] + o4[i] : o4[i];
+        }
     }
+}
+
+// Transposing variant for the parameter layout (M, C, Th, Tw) (s_c = Th*Tw, s_ty = Tw, s_tx = 1): the partial results are
+// (M, tap, C).  A block owns 32 channels of one row m: it sums the splits with 16-byte loads along C (4 split lanes per
+// element, combined (p0 + p1) + (p2 + p3) by two shuffles — a fixed order), transposes through shared memory, and writes
+// the 32 x T block — contiguous in the destination — with coalesced stores.
+__global__ void __launch_bounds__(256) wgrad_reduce_tr_kernel(const float* __restrict__ ws, int splits, int64_t split_stride,
+                                                             int M, int T, int C, float* __restrict__ dst, int64_t s_m,
+                                                             const float* __restrict__ scale, int accumulate) {
+    __shared__ float tile[32 * 64];
+    const int c0 = blockIdx.x * 32;
+    const float alpha = scale ? *scale : 1.f;
+    const int nvalid = C - c0 < 32 ? C - c0 : 32;                 // a multiple of 4
+    const int items = T * 8;                                       // (tap, channel quad)
+    const int work = items * 4;                                    // x 4 split lanes
+    const int bound = (work + 31) & ~31;
+  for (int m = blockIdx.y; m < M; m += gridDim.y) {               // rows walked by the block (few, fat blocks)
+    const float* base = ws + (int64_t)m * T * C + c0;
+    for (int w = threadIdx.x; w < bound; w += 256) {
+        const int item = w >> 2, sl = w & 3;
+        const int tap = item >> 3, q = item & 7;
+        const bool live = w < work && q * 4 < nvalid;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            const float* p = base + (int64_t)tap * C + q * 4;
+            int s = sl;
+            for (; s + 12 < splits; s += 16) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(p + (int64_t)(s + 4 * u) * split_stride);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+            }
+            for (; s < splits; s += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(p + (int64_t)s * split_stride);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        if (live && sl == 0) {
+            float* t = tile + (q * 4) * T + tap;
+            t[0] = acc.x; t[T] = acc.y; t[2 * T] = acc.z; t[3 * T] = acc.w;
+        }
+    }
+    __syncthreads();
+    float* out = dst + (int64_t)m * s_m + (int64_t)c0 * T;
+    for (int i = threadIdx.x; i < nvalid * T; i += 256) {
+        const float v = alpha * tile[i];
+        out[i] = accumulate ? out[i] + v : v;
+    }
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -531,6 +649,58 @@ __global__ void im2col_pack_kernel(const T* __restrict__ x, int64_t M, int Hx, i
         u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
         u.z = *reinterpret_cast<uint32_t*>(&c2); u.w = *reinterpret_cast<uint32_t*>(&d);
         *reinterpret_cast<uint4*>(out + m * Kp + kg * 8) = u;
+    }
+}
+
+// Staged variant (unit input x-stride, i.e. NCHW inputs): one warp packs a strip of 32 consecutive output pixels.
+// Phase 1: lane = pixel, loop over the K columns (warp-uniform tap / channel): consecutive lanes read consecutive input
+// columns (coalesced), results go to shared memory as bf16 [32][Kp + 8].  Phase 2: the strip's 32 x Kp block is
+// contiguous in the output: 16-byte shared loads, fully coalesced 16-byte stores.
+template <typename T>
+__global__ void __launch_bounds__(128) im2col_pack_staged_kernel(const T* __restrict__ x, int64_t M, int Hx, int Wx, int Cx,
+                                                                int64_t sn, int64_t sh, int64_t sw, int64_t sc, int kh,
+                                                                int kw, int stride, int pad, int Hy, int Wy, int Kp,
+                                                                int flip, bf16* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t pack_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ld = Kp + 8;                                   // row pitch in bf16: 16-byte aligned rows, spread banks
+    bf16* tile = reinterpret_cast<bf16*>(pack_smem) + (size_t)warp * 32 * ld;
+    const int64_t strips = (M + 31) / 32;
+    for (int64_t sidx = (int64_t)blockIdx.x * 4 + warp; sidx < strips; sidx += (int64_t)gridDim.x * 4) {
+        const int64_t m = sidx * 32 + lane;
+        const bool live = m < M;
+        int qx = 0, qy = 0, n = 0;
+        if (live) {
+            const int mi = (int)m;
+            qx = mi % Wy;
+            const int t = mi / Wy;
+            qy = t % Hy;
+            n = t / Hy;
+        }
+        const T* xb = x + (int64_t)n * sn;
+        const int iy0 = qy * stride + (flip ? pad : -pad), ix0 = qx * stride + (flip ? pad : -pad);
+        bf16* row = tile + lane * ld;
+        int k = 0;
+        for (int ky = 0; ky < kh; ++ky) {
+            const int iy = flip ? iy0 - ky : iy0 + ky;
+            const bool oky = live && iy >= 0 && iy < Hx;
+            for (int kx = 0; kx < kw; ++kx) {
+                const int ix = flip ? ix0 - kx : ix0 + kx;
+                const bool ok = oky && ix >= 0 && ix < Wx;
+                const T* p = xb + (int64_t)iy * sh + (int64_t)ix * sw;
+                for (int c = 0; c < Cx; ++c, ++k) row[k] = __float2bfloat16_rn(ok ? ldf(p + (int64_t)c * sc) : 0.f);
+            }
+        }
+        for (; k < Kp; ++k) row[k] = __float2bfloat16_rn(0.f);
+        __syncwarp();
+        const int cpr = Kp / 8;                               // 16-byte chunks per row
+        const int64_t m0 = sidx * 32;
+        const int rows = (int)(M - m0 < 32 ? M - m0 : 32);
+        for (int j = lane; j < rows * cpr; j += 32) {
+            const int r = j / cpr, q = j - r * cpr;
+            *reinterpret_cast<uint4*>(out + (m0 + r) * Kp + q * 8) = *reinterpret_cast<const uint4*>(tile + r * ld + q * 8);
+        }
+        __syncwarp();
     }
 }
 
@@ -706,7 +876,12 @@ extern "C" int b200_mask_outer_bwd(const void* dout, const float* mask, float* d
     if (O == 0) return 0;
     dim3 grid(O, (C + 31) / 32), block(32, 8);
     B200_DISPATCH_DT(dt, T, {
-        mask_outer_bwd_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)dout, mask, dv, O, H, W, C);
+        constexpr int V = VecIO<T>::V;
+        const int ct = C / V;
+        if (C % V == 0 && ct >= 1 && ct <= 32 && (ct & (ct - 1)) == 0 && aligned16(dout))
+            mask_outer_bwd_vec_kernel<T><<<O, 256, 0, as_stream(stream)>>>((const T*)dout, mask, dv, H, W, C);
+        else
+            mask_outer_bwd_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)dout, mask, dv, O, H, W, C);
     });
     B200_CHECK_LAUNCH();
     return 0;
@@ -753,7 +928,7 @@ extern "C" int b200_reparam_bwd(const float* dz, const float* logvar, const floa
 
 extern "C" int b200_bn_chunks(int64_t rows, int C) {
     int cblocks = (C + 31) / 32;
-    int64_t target = (int64_t)kNumSMs * 4 / cblocks;      // 256-thread vector blocks: ~4 per SM saturate HBM
+    int64_t target = (int64_t)kNumSMs * 8 / cblocks;
     if (target < 1) target = 1;
     int64_t by_rows = (rows + 31) / 32;
     int64_t n = by_rows < target ? by_rows : target;
@@ -808,8 +983,16 @@ extern "C" int b200_wgrad_reduce(const float* ws, int splits, int64_t split_stri
                                  int accumulate, b200_stream_t stream) {
     int64_t total = (int64_t)M * Th * Tw * C;
     if (total == 0) return 0;
-    if ((C & 3) == 0 && (split_stride & 3) == 0 && total < (1ll << 31) && aligned16(ws))
-        wgrad_reduce_vec_kernel<<<grid_for(total / 4, 128, 16), 128, 0, as_stream(stream)>>>(ws, splits, split_stride, M, Th, Tw, C,
+    const int T = Th * Tw;
+    if ((C & 3) == 0 && (split_stride & 3) == 0 && aligned16(ws) && T > 1 && T <= 64 && s_tx == 1 && s_ty == Tw && s_c == T &&
+        M < 65536) {
+        const int cb = (C + 31) / 32;
+        int rows = (kNumSMs * 8 + cb - 1) / cb;              // ~8 blocks per SM in total, each walking M / rows rows
+        if (rows > M) rows = M;
+        wgrad_reduce_tr_kernel<<<dim3(cb, rows), 256, 0, as_stream(stream)>>>(ws, splits, split_stride, M, T, C, dst, s_m,
+                                                                            scale, accumulate);
+    } else if ((C & 3) == 0 && (split_stride & 3) == 0 && total < (1ll << 31) && aligned16(ws))
+        wgrad_reduce_vec_kernel<<<grid_for(total / 4 * 4, 128, 16), 128, 0, as_stream(stream)>>>(ws, splits, split_stride, M, Th, Tw, C,
                                                                                         dst, s_m, s_ty, s_tx, s_c, scale, accumulate);
     else
         wgrad_reduce_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(ws, splits, split_stride, M, Th, Tw, C, dst,
@@ -823,8 +1006,26 @@ extern "C" int b200_im2col_pack(const void* x, int x_dt, int64_t N, int Hx, int 
                                 int flip, void* out_bf16, b200_stream_t stream) {
     const int64_t M = N * Hy * Wy;
     if (M == 0) return 0;
-    B200_REQUIRE(Kp % 64 == 0 && Kp >= Cx * kh * kw && Kp <= 2048, "im2col_pack: Kp=%d must be a multiple of 64 covering K=%d", Kp, Cx * kh * kw);
+    B200_REQUIRE(Kp % 64 == 0 && Kp >= Cx * kh * kw && Kp <= 512, "im2col_pack: Kp=%d must be a multiple of 64 covering K=%d", Kp, Cx * kh * kw);
     B200_REQUIRE(M < (1ll << 31), "im2col_pack: too many output pixels");
+    if (sw == 1) {
+        // NCHW-style input (unit stride along x): staged kernel, coalesced on both sides
+        const int smem = 4 * 32 * (Kp + 8) * 2;
+        const int64_t strips = (M + 31) / 32;
+        const int grid = grid_for((strips + 3) / 4, 1, 4);
+        B200_DISPATCH_DT(x_dt, T, {
+            static bool configured = false;
+            if (!configured) {
+                cudaError_t e = cudaFuncSetAttribute(im2col_pack_staged_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32 * (512 + 8) * 2);
+                if (e != cudaSuccess) return set_error("im2col_pack: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                configured = true;
+            }
+            im2col_pack_staged_kernel<T><<<grid, 128, smem, as_stream(stream)>>>((const T*)x, M, Hx, Wx, Cx, sn, sh, sw, sc, kh, kw,
+                                                                              stride, pad, Hy, Wy, Kp, flip, (bf16*)out_bf16);
+        });
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
     const int G = Kp / 8;
     const int rows = 256 / G > 0 ? 256 / G : 1;
     dim3 block(G, rows);

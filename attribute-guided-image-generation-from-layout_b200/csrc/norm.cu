@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_vec_kernel(const T* __res
                                                                  const T* __restrict__ y, int C,
                                                                  const float* __restrict__ mean,
                                                                  const float* __restrict__ var, float eps,
-                                                                 const void* __restrict__ gamma, int rows_per_seg,
+                                                                 const void* __restrict__ gamma,
+                                                                 const int32_t* __restrict__ idx, int rows_per_seg,
                                                                  int relu, double* __restrict__ seg_sums,
                                                                  int64_t rows_per_group, int segs_per_group, int ct) {
     constexpr int V = VecIO<T>::V;
@@ -337,12 +338,24 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_vec_kernel(const T* __res
     double s1[V], s2[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.0;
+    // relu == 2 (CBN): the ReLU mask is recomputed from x (one segment = one object = one table row) instead of
+    // reading the saved output: gamma * xhat + beta > 0, the exact fp32 expression of the forward kernel
+    float cg[V], cb[V];
+    if (MODE == B200_NORM_CBN && relu == 2) {
+        const float* row = reinterpret_cast<const float*>(gamma) + (int64_t)idx[a / rows_per_seg] * 2 * C;
+        ldp<V>(row + c, cg);
+        ldp<V>(row + C + c, cb);
+    }
 #pragma unroll 2
     for (int64_t r = a + threadIdx.x / ct; r < b; r += rstep) {
         float gv[V], xv[V];
         VecIO<T>::load(dy + r * C + c, gv);
         VecIO<T>::load(x + r * C + c, xv);
-        if (relu) {
+        if (MODE == B200_NORM_CBN && relu == 2) {
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                if (!(cg[i] * ((xv[i] - m[i]) * rs[i]) + cb[i] > 0.f)) gv[i] = 0.f;
+        } else if (relu) {
             float yv[V];
             VecIO<T>::load(y + r * C + c, yv);
 #pragma unroll
@@ -513,7 +526,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_vec_kernel(const T* __rest
         float g[V], xv[V];
         VecIO<T>::load(dy + o, g);
         VecIO<T>::load(x + o, xv);
-        if (relu) {
+        if (relu == 1) {
             float yv[V];
             VecIO<T>::load(y + o, yv);
 #pragma unroll
@@ -535,7 +548,15 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_vec_kernel(const T* __rest
             }
         }
         if (MODE == B200_NORM_CBN) {
-            ldp<V>(gamma + (int64_t)idx[r / rows_per_seg] * 2 * C + c, ga);
+            const float* row = gamma + (int64_t)idx[r / rows_per_seg] * 2 * C;
+            ldp<V>(row + c, ga);
+            if (relu == 2) {      // recomputed ReLU mask: gamma * xhat + beta > 0 (the forward kernel's fp32 expression)
+                float be[V];
+                ldp<V>(row + C + c, be);
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+                    if (!(ga[e] * ((xv[e] - m[e]) * rs[e]) + be[e] > 0.f)) g[e] = 0.f;
+            }
         } else if (MODE == B200_NORM_SPADE) {
             float q[V];
             VecIO<T>::load(reinterpret_cast<const T*>(gamma_v) + (int64_t)r * 2 * C + c, q);
@@ -556,6 +577,10 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_vec_kernel(const T* __rest
         }
         VecIO<T>::store(dx + o, out);
     }
+}
+
+static inline bool vec_ok_dt(int dt, int64_t rows, int C) {
+    return dt == B200_BF16 ? vec_ok<bf16>(rows, C) : vec_ok<float>(rows, C);
 }
 
 }  // namespace b200
@@ -656,8 +681,9 @@ extern "C" int b200_norm_bwd_reduce(const void* dy, const void* x, const void* y
                                     const float* mean, const float* var, float eps, int mode, const void* gamma,
                                     const int32_t* idx, int rows_per_seg, int relu, double* seg_sums,
                                     b200_stream_t stream) {
-    (void)idx;
     B200_REQUIRE(rows > 0 && rows_per_seg > 0 && groups >= 1 && rows % groups == 0, "norm_bwd_reduce: bad sizes");
+    B200_REQUIRE(relu != 2 || (mode == B200_NORM_CBN && idx != nullptr && vec_ok_dt(dt, rows, C) && (rows / groups) % rows_per_seg == 0),
+                 "norm_bwd_reduce: relu = 2 (recomputed mask) needs conditional batch norm on a vector-kernel layout");
     const int64_t rpg = rows / groups;
     const int spg = (int)((rpg + rows_per_seg - 1) / rows_per_seg);
     dim3 grid(spg * groups, (C + 31) / 32), block(32, 8);
@@ -667,9 +693,11 @@ extern "C" int b200_norm_bwd_reduce(const void* dy, const void* x, const void* y
             const int tpr = C / VecIO<T>::V, ct = tpr < 16 ? tpr : 16;
             dim3 vgrid(spg * groups, tpr / ct);
             if (mode == B200_NORM_SPADE)
-                norm_bwd_reduce_vec_kernel<T, B200_NORM_SPADE><<<vgrid, 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg, ct);
+                norm_bwd_reduce_vec_kernel<T, B200_NORM_SPADE><<<vgrid, 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, C, mean, var, eps, gamma, idx, rows_per_seg, relu, seg_sums, rpg, spg, ct);
+            else if (mode == B200_NORM_CBN && relu == 2)
+                norm_bwd_reduce_vec_kernel<T, B200_NORM_CBN><<<vgrid, 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, C, mean, var, eps, gamma, idx, rows_per_seg, relu, seg_sums, rpg, spg, ct);
             else
-                norm_bwd_reduce_vec_kernel<T, B200_NORM_PLAIN><<<vgrid, 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg, ct);
+                norm_bwd_reduce_vec_kernel<T, B200_NORM_PLAIN><<<vgrid, 256, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, C, mean, var, eps, gamma, idx, rows_per_seg, relu, seg_sums, rpg, spg, ct);
         } else
         if (mode == B200_NORM_SPADE)
             norm_bwd_reduce_kernel<T, B200_NORM_SPADE><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, rows, C, mean, var, eps, gamma, rows_per_seg, relu, seg_sums, rpg, spg);
@@ -752,6 +780,8 @@ extern "C" int b200_norm_bwd_apply(const void* dy, const void* x, const void* y,
     if (rows == 0) return 0;
     B200_REQUIRE(C % 4 == 0, "norm_bwd_apply: C=%d must be a multiple of 4", C);
     B200_REQUIRE(groups >= 1 && rows % groups == 0, "norm_bwd_apply: rows %% groups != 0");
+    B200_REQUIRE(relu != 2 || (mode == B200_NORM_CBN && vec_ok_dt(dt, rows, C) && rows / groups < (1ll << 31)),
+                 "norm_bwd_apply: relu = 2 (recomputed mask) needs conditional batch norm on a vector-kernel layout");
     const int64_t rpg = rows / groups;
     if (rows_per_seg < 1) rows_per_seg = 1;
     int rc;

@@ -6,18 +6,53 @@
 
 namespace b200 {
 
-constexpr int kSnRowChunks = 32;     // row chunks of the W^T u pass (partial sums per chunk, summed in order)
+constexpr int kSnRowChunks = 8;      // row chunks of the W^T u pass (partial sums per chunk, summed in order)
+
+// partial[j] = sum_{i in [i0, i1)} W[i][j] * u[i] for the 128 columns of block column `bx`; blockDim.x = 128.
+// Vector layout (w % 4 == 0, 16-byte aligned): lane = column quad (a warp reads 512 contiguous bytes of a row), the 4
+// warps take rows i0 + warp, step 4, and their sums are added in warp order through shared memory.  The single-layer and
+// the whole-network kernels share this function (their results are compared bit for bit).
+__device__ __forceinline__ void wtu_chunk(const float* __restrict__ W, const float* __restrict__ u, int w, int i0, int i1,
+                                          int bx, float* __restrict__ partial) {
+    __shared__ float4 red[3][32];
+    if ((w & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0) {
+        const int q = threadIdx.x & 31, rl = threadIdx.x >> 5;
+        const int j = (bx * 32 + q) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < w) {
+            const float* Wp = W + j;
+#pragma unroll 4
+            for (int i = i0 + rl; i < i1; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(Wp + (int64_t)i * w);
+                const float ui = u[i];
+                acc.x += v.x * ui; acc.y += v.y * ui; acc.z += v.z * ui; acc.w += v.w * ui;
+            }
+        }
+        if (rl > 0) red[rl - 1][q] = acc;
+        __syncthreads();
+        if (rl == 0 && j < w) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 o = red[k][q];
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+            *reinterpret_cast<float4*>(partial + j) = acc;
+        }
+        return;
+    }
+    const int j = bx * 128 + threadIdx.x;
+    if (j >= w) return;
+    float acc = 0.f;
+    for (int i = i0; i < i1; ++i) acc += W[(int64_t)i * w + j] * u[i];
+    partial[j] = acc;
+}
 
 // partial[chunk][j] = sum_{i in chunk} W[i][j] * u[i]
 __global__ void sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u, int h, int w, int rows_per_chunk,
                               float* __restrict__ partial) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= w) return;
     int i0 = blockIdx.y * rows_per_chunk;
     int i1 = i0 + rows_per_chunk < h ? i0 + rows_per_chunk : h;
-    float acc = 0.f;
-    for (int i = i0; i < i1; ++i) acc += W[(int64_t)i * w + j] * u[i];
-    partial[(int64_t)blockIdx.y * w + j] = acc;
+    wtu_chunk(W, u, w, i0, i1, blockIdx.x, partial + (int64_t)blockIdx.y * w);
 }
 
 __device__ float block_sum_1024(float v, float* red) {
@@ -169,6 +204,113 @@ __global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* _
 
 
 // ---------------------------------------------------------------------------------------------------------
+// Grouped weight gradient through W / sigma_g: `groups` calls of a spectral-normalised layer batched along dim 0 share
+// ONE weight-gradient GEMM whose pixel splits are aligned with the call boundaries (splits [g*spg, (g+1)*spg) belong to
+// call g).  Phase A sums each call's splits into G_g (parameter layout (M, C, T); the partials are (M, tap, C)) and
+// accumulates the partial dot products <G_g, W>; phase B forms
+//     dW = sum_g ( G_g / sigma_g - <G_g, W> / sigma_g^2 * u_g v_g^T ).
+// Replaces, per call, wgrad + wgrad_reduce + sn_dot_partial + sn_grad_apply.  All sums in a fixed order.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSnMaxGroups = 8;
+
+// grid (ceil(C/32), rows, groups), 256 threads: 32 channels of the rows m = blockIdx.y, + gridDim.y, ... of call g
+__global__ void __launch_bounds__(256) sn_wgrad_reduce_kernel(const float* __restrict__ ws, int spg, int64_t split_stride,
+                                                             int M, int T, int C, const float* __restrict__ W,
+                                                             float* __restrict__ Gbuf, double* __restrict__ dot_part) {
+    __shared__ float tile[32 * 64];
+    __shared__ double red[8];
+    const int g = blockIdx.z;
+    const int c0 = blockIdx.x * 32;
+    const int nvalid = C - c0 < 32 ? C - c0 : 32;                 // a multiple of 4
+    const int items = T * 8;                                       // (tap, channel quad)
+    const int work = items * 4;                                    // x 4 split lanes
+    const int bound = (work + 31) & ~31;
+    const int64_t n = (int64_t)M * C * T;
+    const float* wsg = ws + (int64_t)g * spg * split_stride;
+    float* Gg = Gbuf + (int64_t)g * n;
+    double dot = 0.0;
+    for (int m = blockIdx.y; m < M; m += gridDim.y) {
+        const float* base = wsg + (int64_t)m * T * C + c0;
+        for (int w = threadIdx.x; w < bound; w += 256) {
+            const int item = w >> 2, sl = w & 3;
+            const int tap = item >> 3, q = item & 7;
+            const bool live = w < work && q * 4 < nvalid;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                const float* p = base + (int64_t)tap * C + q * 4;
+                for (int sidx = sl; sidx < spg; sidx += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(p + (int64_t)sidx * split_stride);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            }
+            if (live && sl == 0) {
+                float* t = tile + (q * 4) * T + tap;
+                t[0] = acc.x; t[T] = acc.y; t[2 * T] = acc.z; t[3 * T] = acc.w;
+            }
+        }
+        __syncthreads();
+        const int64_t o0 = ((int64_t)m * C + c0) * T;
+        for (int i = threadIdx.x; i < nvalid * T; i += 256) {
+            const float v = tile[i];
+            Gg[o0 + i] = v;
+            dot += (double)v * (double)W[o0 + i];
+        }
+        __syncthreads();
+    }
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        dot_part[(int64_t)g * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) sn_grad_groups_kernel(const float* __restrict__ Gbuf, int groups,
+                                                            const float* __restrict__ u_hist,
+                                                            const float* __restrict__ v_hist,
+                                                            const float* __restrict__ inv, const double* __restrict__ dot_part,
+                                                            int nparts, float* __restrict__ dW, int h, int w) {
+    __shared__ float coef[kSnMaxGroups], invs[kSnMaxGroups];
+    for (int g = threadIdx.x >> 5; g < groups; g += 8) {          // warp g: fixed-order sum of call g's partial dots
+        double sdot = 0.0;
+        for (int k = threadIdx.x & 31; k < nparts; k += 32) sdot += dot_part[(int64_t)g * nparts + k];
+        sdot = warp_sum(sdot);
+        if ((threadIdx.x & 31) == 0) {
+            const float iv = inv[g];
+            invs[g] = iv;
+            coef[g] = (float)sdot * iv * iv;
+        }
+    }
+    __syncthreads();
+    const uint32_t n = (uint32_t)h * (uint32_t)w;
+    const uint32_t n4 = n >> 2, w4 = (uint32_t)w >> 2;             // w % 4 == 0
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += gridDim.x * blockDim.x) {
+        const uint32_t i = t / w4, j = (t - i * w4) << 2;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < groups; ++g) {
+            const float4 gv = *reinterpret_cast<const float4*>(Gbuf + (size_t)g * n + (size_t)t * 4);
+            const float* v = v_hist + (size_t)g * w + j;
+            const float cu = coef[g] * u_hist[(size_t)g * h + i];
+            const float iv = invs[g];
+            o.x += gv.x * iv - cu * v[0];
+            o.y += gv.y * iv - cu * v[1];
+            o.z += gv.z * iv - cu * v[2];
+            o.w += gv.w * iv - cu * v[3];
+        }
+        *reinterpret_cast<float4*>(dW + (size_t)t * 4) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // whole-network power iteration: every spectral-normalised layer of a discriminator in one launch sequence
 // (blockIdx.z / blockIdx.y = layer; blocks beyond a layer's extent exit).  Same arithmetic and reduction order
 // per layer as the single-layer kernels above.
@@ -176,30 +318,11 @@ __global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* _
 __global__ void snm_wtu_kernel(const b200_sn_layer* __restrict__ layers) {
     const b200_sn_layer l = layers[blockIdx.z];
     const int nch = l.h < 64 ? 1 : kSnRowChunks;
-    if ((int)blockIdx.y >= nch) return;
+    if ((int)blockIdx.y >= nch || (int)blockIdx.x * 128 >= l.w) return;
     const int rpc = (l.h + nch - 1) / nch;
     const int i0 = blockIdx.y * rpc;
     const int i1 = i0 + rpc < l.h ? i0 + rpc : l.h;
-    if ((l.w & 3) == 0 && ((reinterpret_cast<uintptr_t>(l.W) | reinterpret_cast<uintptr_t>(l.ws)) & 15) == 0) {
-        // 4 columns per thread (16-byte loads), the same per-column summation order as the scalar path
-        const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-        if (j >= l.w) return;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* Wp = l.W + j;
-#pragma unroll 4
-        for (int i = i0; i < i1; ++i) {
-            const float4 q = *reinterpret_cast<const float4*>(Wp + (int64_t)i * l.w);
-            const float ui = l.u[i];
-            acc.x += q.x * ui; acc.y += q.y * ui; acc.z += q.z * ui; acc.w += q.w * ui;
-        }
-        *reinterpret_cast<float4*>(l.ws + (int64_t)blockIdx.y * l.w + j) = acc;
-        return;
-    }
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l.w; j += gridDim.x * blockDim.x) {
-        float acc = 0.f;
-        for (int i = i0; i < i1; ++i) acc += l.W[(int64_t)i * l.w + j] * l.u[i];
-        l.ws[(int64_t)blockIdx.y * l.w + j] = acc;
-    }
+    wtu_chunk(l.W, l.u, l.w, i0, i1, blockIdx.x, l.ws + (int64_t)blockIdx.y * l.w);
 }
 
 __global__ void snm_norm_v_kernel(const b200_sn_layer* __restrict__ layers, float eps, int it) {
@@ -289,6 +412,35 @@ extern "C" int b200_sn_grad(const float* g, const float* W, const float* u, cons
     return 0;
 }
 
+extern "C" int b200_sn_wgrad_parts(int M, int C) {
+    const int cb = (C + 31) / 32;
+    int rows = (kNumSMs * 8 + cb - 1) / cb;
+    if (rows > M) rows = M;
+    if (rows < 1) rows = 1;
+    return cb * rows;
+}
+
+extern "C" int b200_sn_wgrad_finish(const float* ws, int groups, int splits_per_group, int64_t split_stride, int M, int T,
+                                    int C, const float* W, const float* u_hist, const float* v_hist, const float* inv,
+                                    float* Gbuf, double* dot_part, float* dW, b200_stream_t stream) {
+    cudaStream_t st = as_stream(stream);
+    B200_REQUIRE(groups >= 1 && groups <= kSnMaxGroups && splits_per_group >= 1, "sn_wgrad_finish: bad groups / splits");
+    B200_REQUIRE((C & 3) == 0 && T >= 1 && T <= 64 && M >= 1 && M < 65536 && (split_stride & 3) == 0 &&
+                     (int64_t)M * C * T < (1ll << 31),
+                 "sn_wgrad_finish: needs C %% 4 == 0, T <= 64, M < 65536");
+    B200_REQUIRE(((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(Gbuf) | reinterpret_cast<uintptr_t>(dW)) & 15) == 0,
+                 "sn_wgrad_finish: buffers must be 16-byte aligned");
+    const int cb = (C + 31) / 32;
+    const int nparts = b200_sn_wgrad_parts(M, C);
+    const int rows = nparts / cb;
+    sn_wgrad_reduce_kernel<<<dim3(cb, rows, groups), 256, 0, st>>>(ws, splits_per_group, split_stride, M, T, C, W, Gbuf, dot_part);
+    B200_CHECK_LAUNCH();
+    const int64_t n = (int64_t)M * C * T;
+    sn_grad_groups_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(Gbuf, groups, u_hist, v_hist, inv, dot_part, nparts, dW, M, C * T);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int b200_sn_power_iter_multi(const b200_sn_layer* layers, int n_layers, int max_h, int max_w, int iters,
                                         int do_iter, float eps, b200_stream_t stream) {
     if (n_layers <= 0 || iters <= 0) return 0;
@@ -296,7 +448,7 @@ extern "C" int b200_sn_power_iter_multi(const b200_sn_layer* layers, int n_layer
     cudaStream_t st = as_stream(stream);
     for (int it = 0; it < iters; ++it) {
         if (do_iter) {
-            snm_wtu_kernel<<<dim3((max_w / 4 + 127) / 128 + 1, kSnRowChunks, n_layers), 128, 0, st>>>(layers);
+            snm_wtu_kernel<<<dim3((max_w + 127) / 128, kSnRowChunks, n_layers), 128, 0, st>>>(layers);
             B200_CHECK_LAUNCH();
             snm_norm_v_kernel<<<n_layers, 1024, 0, st>>>(layers, eps, it);
             B200_CHECK_LAUNCH();

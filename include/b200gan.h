@@ -169,7 +169,8 @@ int b200_norm_fwd(const void* x, void* y, int dt, int64_t rows, int C, int group
                   const void* residual, int relu, b200_stream_t stream);
 /* backward, stage 1: per-segment sums of (dyr*g, dyr*g*xhat) [and for CBN the raw (dyr, dyr*xhat)] where dyr = dy masked by
  * y>0 when relu; segments never straddle a group: seg_sums is (groups * ceil(rows_per_group / rows_per_seg), C, 2)
- * doubles.  For CBN pass rows_per_seg = H*W. */
+ * doubles.  For CBN pass rows_per_seg = H*W.  relu = 2 (CBN on a 16-byte vector layout only): the mask is recomputed as
+ * g * xhat + b > 0 — the forward kernel's fp32 expression — and y may be NULL (one activation read less per pass). */
 int b200_norm_bwd_reduce(const void* dy, const void* x, const void* y, int dt, int64_t rows, int C, int groups,
                          const float* mean, const float* var, float eps, int mode, const void* gamma,
                          const int32_t* idx, int rows_per_seg, int relu, double* seg_sums, b200_stream_t stream);
@@ -252,7 +253,7 @@ int b200_permute_rows(const void* x, const int32_t* src_row, void* out, int rows
 /* ------------------------------------------------------------------------------------------------
  * Spectral normalisation — replaces torch.nn.utils.spectral_norm's pre-forward hook installed by add_sn
  * (discriminator.py:15-22): one power iteration in place on u (h) and v (w), sigma = u.(W v); W (h,w) row-major
- * view of weight_orig.  *sigma_out = sigma, *inv_sigma_out = 1/sigma.  ws: 32*w + h floats.
+ * view of weight_orig.  *sigma_out = sigma, *inv_sigma_out = 1/sigma.  ws: 8*w + h floats.
  * b200_sn_grad: dW = g*inv_sigma - (<g, W> * inv_sigma^2) * u v^T  (gradient through W/sigma with u, v constant),
  * g = gradient w.r.t. the normalised weight, same layout as W.  ws: 1024 doubles.
  */
@@ -261,15 +262,26 @@ int b200_sn_power_iter(const float* W, int h, int w, float* u, float* v, int do_
 int b200_sn_grad(const float* g, const float* W, const float* u, const float* v, const float* inv_sigma, float* dW, int h,
                  int w, int accumulate, double* ws, b200_stream_t stream);
 
+/* Weight gradient of `groups` (<= 8) batched calls of one spectral-normalised layer, each with its own sigma_g, u_g, v_g:
+ * ws holds the fp32 partial results ([groups*splits_per_group][M][T*C], split_stride elements apart) of ONE
+ * b200_wgrad_gemm_* launch whose pixel splits are aligned with the call boundaries (splits [g*spg, (g+1)*spg) = call g).
+ *   G_g = sum of call g's splits, transposed to the parameter layout (M, C, T);
+ *   dW  = sum_g ( G_g * inv[g] - <G_g, W> * inv[g]^2 * u_hist[g] v_hist[g]^T ),  W viewed (M, C*T).
+ * Gbuf: groups*M*C*T floats, dot_part: groups*b200_sn_wgrad_parts(M, C) doubles (scratch).  C % 4 == 0, T <= 64. */
+int b200_sn_wgrad_parts(int M, int C);
+int b200_sn_wgrad_finish(const float* ws, int groups, int splits_per_group, int64_t split_stride, int M, int T, int C,
+                         const float* W, const float* u_hist, const float* v_hist, const float* inv, float* Gbuf,
+                         double* dot_part, float* dW, b200_stream_t stream);
+
 /* The same power iteration for EVERY spectral-normalised layer of a network at once (4 launches per iteration instead
  * of 4 per layer), `iters` times in sequence — one per batched call of the network.  `layers` is a DEVICE array of
  * n_layers descriptors; iteration `it` of layer l records inv[it] = 1/sigma, u_hist[it*h ..], v_hist[it*w ..] (the
- * vectors that sigma was computed with; either history pointer may be NULL).  ws: 32*w + h floats per layer. */
+ * vectors that sigma was computed with; either history pointer may be NULL).  ws: 8*w + h floats per layer. */
 typedef struct {
     const float* W;     /* (h, w) row-major view of weight_orig */
     float* u;           /* (h,)  updated in place */
     float* v;           /* (w,)  updated in place */
-    float* ws;          /* 32*w + h floats of scratch */
+    float* ws;          /* 8*w + h floats of scratch */
     float* inv;         /* (iters,) */
     float* u_hist;      /* (iters, h) or NULL */
     float* v_hist;      /* (iters, w) or NULL */

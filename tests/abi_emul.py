@@ -190,10 +190,14 @@ class EmulKernels:
             A = A.to(torch.bfloat16).float()
             Pm = Pm.to(torch.bfloat16).float()
         K = d.Th * d.Tw * d.Cin
-        R = Pm.t() @ A.reshape(A.shape[0], K)
+        A2 = A.reshape(A.shape[0], K)
         wsv = ws.view(splits, d.Cout, K)
-        wsv.zero_()
-        wsv[0] = R
+        # the kernels split the pixel range into `splits` chunks of rows_per_split = ceil(Q / splits) rounded up to 64
+        Q = A2.shape[0]
+        rps = max(64, (-(-Q // splits) + 63) // 64 * 64)
+        for z in range(splits):
+            a, b = z * rps, min(Q, (z + 1) * rps)
+            wsv[z] = Pm[a:b].t() @ A2[a:b] if b > a else 0.0
 
     def wgrad_reduce(self, ws, splits, M, Th, Tw, C, dst, dst_offset, s_m, s_ty, s_tx, s_c, scale=None, accumulate=False,
                      ws_row_offset=0, ws_rows=None):
@@ -274,7 +278,12 @@ class EmulKernels:
         mean_r = mean.view(groups, C).repeat_interleave(rpg, dim=0)
         rstd_r = (1.0 / torch.sqrt(var.view(groups, C) + eps)).repeat_interleave(rpg, dim=0)
         xh = (x2d - mean_r) * rstd_r
-        g = dy * (y > 0).to(dy.dtype) if relu else dy
+        if relu == 2:        # recomputed mask (conditional batch norm): gamma * xhat + beta > 0
+            assert mode == MODE_CBN and y is None
+            gm2, bm2 = self._g_b(mode, gamma, None, idx, rows_per_seg, rows, C)
+            g = dy * ((gm2 * xh + bm2) > 0).to(dy.dtype)
+        else:
+            g = dy * (y > 0).to(dy.dtype) if relu else dy
         gm, _ = self._g_b(mode, gamma, gamma if mode == MODE_AFFINE else None, idx, rows_per_seg, rows, C)
         dxh = g if gm is None else g * gm
         s1 = dxh.double().view(groups, rpg, C).sum(1).float().repeat_interleave(rpg, dim=0)
@@ -446,6 +455,18 @@ class EmulKernels:
             dW += val
         else:
             dW.copy_(val)
+        return dW
+
+    def sn_wgrad_finish(self, ws, groups, spg, Cy, T, Cx, W, u_hist, v_hist, inv, dW):
+        self.launches += 2
+        part = ws.view(groups, spg, Cy, T, Cx).sum(1)                     # (groups, Cy, tap, Cx)
+        G = part.permute(0, 1, 3, 2).reshape(groups, Cy, Cx * T)           # parameter layout (Cy, Cx, T)
+        Wm = W.detach().reshape(Cy, Cx * T)
+        out = torch.zeros(Cy, Cx * T)
+        for g in range(groups):
+            dot = (G[g].double() * Wm.double()).sum().float()
+            out += G[g] * inv[g] - dot * inv[g] * inv[g] * torch.outer(u_hist[g], v_hist[g])
+        dW.copy_(out.reshape(dW.shape))
         return dW
 
     def sn_table(self, layers, stage, ws, iters):

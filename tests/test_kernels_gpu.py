@@ -320,6 +320,42 @@ def test_whole_network_power_iteration(K):
         close(m.__dict__["_sn_staged"].inv, (1.0 / sigma).reshape(1), 1e-5, "eval sigma")
 
 
+@pytest.mark.parametrize("case", [(64, 64, 3, 1, 1, 16, 3), (64, 128, 3, 1, 1, 8, 4), (128, 64, 1, 1, 0, 16, 4),
+                                  (256, 512, 3, 1, 1, 4, 4)])
+def test_grouped_sn_weight_gradient(K, case):
+    """`groups` batched calls of a spectral-normalised conv: ONE weight-gradient GEMM with call-aligned splits +
+    b200_sn_wgrad_finish must equal the per-call loop (wgrad + reduce + b200_sn_grad per call) up to summation order, and
+    the emulation of the entry point."""
+    Cx, Cy, k, s, p, H, groups = case
+    n = 16                                                   # images per call
+    g = torch.Generator().manual_seed(Cx + Cy + groups)
+    geom = ops.ConvGeom(Cx, Cy, k, k, s, p)
+    Hy = geom.out_hw(H, H)[0]
+    x = torch.randn(groups * n, H, H, Cx, generator=g)
+    dy = torch.randn(groups * n, Hy, Hy, Cy, generator=g)
+    w = (torch.randn(Cy, Cx, k, k, generator=g) / (Cx * k * k) ** 0.5)
+    u = F.normalize(torch.randn(Cy, generator=g), dim=0)
+    v = F.normalize(torch.randn(Cx * k * k, generator=g), dim=0)
+    ops.set_precision("bf16")
+    try:
+        outs = []
+        for grouped in (True, False):
+            prev, ops.GROUPED_SN_WGRAD = ops.GROUPED_SN_WGRAD, grouped
+            try:
+                wd = w.cuda().requires_grad_(True)
+                sn = ops.sn_iterate(wd.detach(), u.cuda(), v.cuda(), groups, True)
+                if grouped:
+                    assert ops._sn_group_splits(geom, groups * n * Hy * Hy, groups) > 0
+                y = ops.conv2d(x.cuda().bfloat16(), wd, None, geom, ops.WeightPacks(), sn=sn)
+                y.backward(dy.cuda().bfloat16())
+                outs.append(wd.grad.clone())
+            finally:
+                ops.GROUPED_SN_WGRAD = prev
+        close(outs[0], outs[1], 2e-5, "grouped vs per-call spectral-norm weight gradient")
+    finally:
+        ops.set_precision("fp32")
+
+
 @pytest.mark.parametrize("h,w", [(64, 27), (1, 1024), (179, 1024), (1024, 9216)])
 def test_sn_power_iteration(K, h, w):
     g = torch.Generator().manual_seed(h + w)
@@ -381,6 +417,28 @@ def test_norm_fwd_bwd(K, mode, relu, groups):
         assert (d is None) == (c is None), name
         if d is not None:
             close(d, c, 2e-5, name)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cbn_recomputed_relu_mask(K, dtype):
+    """relu = 2: conditional batch norm's backward recomputes the ReLU mask from x (gamma * xhat + beta > 0) instead of
+    reading y; it must equal the y-based mask path EXACTLY (same fp32 expression as the forward kernel)."""
+    g = torch.Generator().manual_seed(3)
+    groups, O_, hw, C, ncls = 3, 12, 36, 128, 9
+    rows = O_ * hw
+    x = (torch.randn(rows, C, generator=g) * 2 + 0.5).to(dtype)
+    idx = torch.randint(0, ncls, (O_,), generator=g).to(torch.int32)
+    table = torch.randn(ncls, 2 * C, generator=g)
+    dy = torch.randn(rows, C, generator=g).to(dtype)
+    xd, dyd, td, idd = cu(x, dy, table, idx)
+    mean, var = K.bn_stats(xd, None, None, 0.1, groups)
+    y = K.norm_fwd(xd, mean, var, 1e-5, 2, td, None, idd, hw, None, True, groups)
+    a = K.norm_bwd(dyd, xd, y, mean, var, 1e-5, 2, td, idd, hw, 1, ncls, groups)
+    b = K.norm_bwd(dyd, xd, None, mean, var, 1e-5, 2, td, idd, hw, 2, ncls, groups)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]), "recomputed mask differs from the saved-output mask"
+    c = E.norm_bwd(dy, x, None, mean.cpu(), var.cpu(), 1e-5, 2, table, idx, hw, 2, ncls, groups)
+    close(b[0], c[0], 2e-5 if dtype == torch.float32 else 1e-2, "dx")
+    close(b[3], c[3], 2e-5 if dtype == torch.float32 else 1e-2, "dtable")
 
 
 def test_bn_stats_shapes(K):
