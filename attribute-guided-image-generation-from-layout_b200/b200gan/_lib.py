@@ -322,6 +322,13 @@ class Kernels:
                     "b200_pool_fwd")
         return y
 
+    def pool_add_fwd(self, a, b, N, H, W, Cc, f, scale):
+        _same_dt(a, b)
+        y = torch.empty((N, H // f, W // f, Cc), dtype=a.dtype, device=a.device)
+        self._check(self.lib.b200_pool_add_fwd(_ptr(a), _ptr(b), _ptr(y), N, H, W, Cc, f, C.c_float(scale), _dt(a), _stream()),
+                    "b200_pool_add_fwd")
+        return y
+
     def unpool_fwd(self, x, N, H, W, Cc, f, scale):
         y = torch.empty((N, H * f, W * f, Cc), dtype=x.dtype, device=x.device)
         self._check(self.lib.b200_unpool_fwd(_ptr(x), _ptr(y), N, H, W, Cc, f, C.c_float(scale), _dt(x), _stream()),

@@ -734,6 +734,27 @@ class _PoolFn(torch.autograd.Function):
         return _lib.K.unpool_fwd(dy.contiguous(), N, H, W, C, ctx.f, ctx.scale), None, None
 
 
+class _PoolAddFn(torch.autograd.Function):
+    """y = scale * (f x f block sums of a + b); both inputs receive the same gradient tensor"""
+
+    @staticmethod
+    def forward(ctx, a, b, f, scale):
+        N, H, W, C = a.shape
+        ctx.f, ctx.scale = f, scale
+        return _lib.K.pool_add_fwd(a.contiguous(), b.contiguous(), N, H, W, C, f, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, C = dy.shape
+        g = _lib.K.unpool_fwd(dy.contiguous(), N, H, W, C, ctx.f, ctx.scale)
+        return g, g, None, None
+
+
+def avg_pool2_sum(a, b):
+    """avg_pool2(a + b) in one pass"""
+    return _PoolAddFn.apply(a, b, 2, 0.25)
+
+
 class _UnpoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, f, scale):

@@ -59,8 +59,8 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* 
 // y[n,qy,qx,c] = scale * sum_{dy,dx<f} x[n,qy*f+dy,qx*f+dx,c];  V = channels per thread (16 bytes when C % V == 0, else
 // 1); I = index type (32-bit when the element count fits: no 64-bit divisions)
 template <typename T, int V, typename I>
-__global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f,
-                                float scale) {
+__global__ void pool_fwd_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y, int N, int H, int W,
+                                int C, int f, float scale) {
     const int Ho = H / f, Wo = W / f, Cv = C / V;
     const I total = (I)N * Ho * Wo * Cv;
     for (I t = blockIdx.x * (I)blockDim.x + threadIdx.x; t < total; t += (I)gridDim.x * blockDim.x) {
@@ -82,6 +82,11 @@ __global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int 
                     VecIO<T>::load(p + ((int64_t)dy * W + dx) * C, v);
 #pragma unroll
                     for (int e = 0; e < V; ++e) acc[e] += v[e];
+                    if (x2) {           // pooled SUM of two tensors (residual branch + shortcut of a downsampling block)
+                        VecIO<T>::load(x2 + (p - x) + ((int64_t)dy * W + dx) * C, v);
+#pragma unroll
+                        for (int e = 0; e < V; ++e) acc[e] += v[e];
+                    }
                 }
 #pragma unroll
             for (int e = 0; e < V; ++e) acc[e] *= scale;
@@ -89,7 +94,10 @@ __global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int 
         } else {
             float acc = 0.f;
             for (int dy = 0; dy < f; ++dy)
-                for (int dx = 0; dx < f; ++dx) acc += ldf(p + ((int64_t)dy * W + dx) * C);
+                for (int dx = 0; dx < f; ++dx) {
+                    acc += ldf(p + ((int64_t)dy * W + dx) * C);
+                    if (x2) acc += ldf(x2 + (p - x) + ((int64_t)dy * W + dx) * C);
+                }
             stf(y + (int64_t)t, acc * scale);
         }
     }
@@ -440,6 +448,7 @@ __global__ void colsum_final_kernel(const double* __restrict__ ws, int nchunks, 
     if (c >= C) return;
     int lane = threadIdx.x & 31;
     double s = 0.0;
+#pragma unroll 4
     for (int k = lane; k < nchunks; k += 32) s += ws[(int64_t)k * C + c];
     s = warp_sum(s);
     if (lane == 0) out[c] = (float)s;
@@ -769,24 +778,37 @@ extern "C" int b200_add(const void* a, const void* b, void* out, int64_t n, int 
     return 0;
 }
 
-extern "C" int b200_pool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt,
-                             b200_stream_t stream) {
+static int pool_launch(const void* x, const void* x2, void* y, int N, int H, int W, int C, int f, float scale, int dt,
+                       b200_stream_t stream) {
     B200_REQUIRE(f >= 1 && H % f == 0 && W % f == 0, "pool_fwd: H=%d W=%d not divisible by f=%d", H, W, f);
     int64_t total = (int64_t)N * (H / f) * (W / f) * C;
     if (total == 0) return 0;
     B200_DISPATCH_DT(dt, T, {
         constexpr int V = VecIO<T>::V;
         const bool small = (int64_t)N * H * W * C < (1ll << 31);
-        if (C % V == 0 && aligned16(x) && aligned16(y)) {
-            if (small) pool_fwd_kernel<T, V, uint32_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
-            else pool_fwd_kernel<T, V, int64_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+        const T* a = (const T*)x;
+        const T* b = (const T*)x2;
+        if (C % V == 0 && aligned16(x) && aligned16(y) && (x2 == nullptr || aligned16(x2))) {
+            if (small) pool_fwd_kernel<T, V, uint32_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale);
+            else pool_fwd_kernel<T, V, int64_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale);
         } else {
-            if (small) pool_fwd_kernel<T, 1, uint32_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
-            else pool_fwd_kernel<T, 1, int64_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+            if (small) pool_fwd_kernel<T, 1, uint32_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale);
+            else pool_fwd_kernel<T, 1, int64_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale);
         }
     });
     B200_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int b200_pool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt,
+                             b200_stream_t stream) {
+    return pool_launch(x, nullptr, y, N, H, W, C, f, scale, dt, stream);
+}
+
+extern "C" int b200_pool_add_fwd(const void* a, const void* b, void* y, int N, int H, int W, int C, int f, float scale,
+                                 int dt, b200_stream_t stream) {
+    B200_REQUIRE(a != nullptr && b != nullptr, "pool_add_fwd: two inputs required");
+    return pool_launch(a, b, y, N, H, W, C, f, scale, dt, stream);
 }
 
 extern "C" int b200_unpool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt,

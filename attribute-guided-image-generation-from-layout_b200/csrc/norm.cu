@@ -61,6 +61,7 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ ws, int nchunks
     if (running_mean && lane == 0) { rm = running_mean[c]; rv = running_var[c]; }
     for (int g = 0; g < groups; ++g) {
         double s1 = 0.0, s2 = 0.0;
+#pragma unroll 4
         for (int k = lane; k < nchunks; k += 32) {
             const double* p = ws + (((int64_t)g * nchunks + k) * C + c) * 2;
             s1 += p[0];
@@ -392,12 +393,14 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ seg, int nse
     for (int g = 0; g < groups; ++g) {
         double s1 = 0.0, s2 = 0.0;
         if (mode == B200_NORM_CBN) {
+#pragma unroll 4
             for (int k = g * spg + lane; k < (g + 1) * spg; k += 32) {
                 double w = (double)gamma[(int64_t)idx[k] * 2 * C + c];
                 s1 += w * seg[((int64_t)k * C + c) * 2];
                 s2 += w * seg[((int64_t)k * C + c) * 2 + 1];
             }
         } else {
+#pragma unroll 4
             for (int k = g * spg + lane; k < (g + 1) * spg; k += 32) {
                 s1 += seg[((int64_t)k * C + c) * 2];
                 s2 += seg[((int64_t)k * C + c) * 2 + 1];

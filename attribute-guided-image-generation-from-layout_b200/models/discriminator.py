@@ -57,8 +57,7 @@ class ResidualBlock(nn.Module):
         h = self.resi[1](r, relu=True, groups=groups)
         h = self.resi[3](h, groups=groups)
         s = self.sc(r, groups=groups) if self.learnable_sc else r
-        out = ops.add(h, s)
-        return ops.avg_pool2(out) if self.downsample else out
+        return ops.avg_pool2_sum(h, s) if self.downsample else ops.add(h, s)
 
 
 def _trunk(net, x, groups):

@@ -326,6 +326,10 @@ class EmulKernels:
         self.launches += 1
         return (x.float().reshape(N, H // f, f, W // f, f, C).sum(dim=(2, 4)) * scale).to(x.dtype)
 
+    def pool_add_fwd(self, a, b, N, H, W, C, f, scale):
+        self.launches += 1
+        return ((a.float() + b.float()).reshape(N, H // f, f, W // f, f, C).sum(dim=(2, 4)) * scale).to(a.dtype)
+
     def unpool_fwd(self, x, N, H, W, C, f, scale):
         self.launches += 1
         v = x.float().reshape(N, H, 1, W, 1, C).expand(N, H, f, W, f, C)
