@@ -31,6 +31,16 @@ import torch  # noqa: E402
 
 OBJS_PER_IMAGE = 8
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at communicator creation),
+# so file descriptor 1 is pointed at stderr for the lifetime of the process and the result line goes to a private
+# duplicate of the original stdout.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
+
 
 # ------------------------------------------------------------------------------------------------------------
 # FLOP model (FlopCounterMode fit of the reference autograd): per G+D step
@@ -154,7 +164,7 @@ def run_reference(args):
                                    "reference on %d host threads" % (args.steps, args.size, args.size, n, OBJS_PER_IMAGE, threads)},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n_per_gpu, note=""):
@@ -330,7 +340,7 @@ def run_b200(args):
             "cpu_baseline": cpu_base,
             "step_tflops": step_flops(args.size, n_img, n_obj) / (ms / 1e3) / 1e12,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # every rank leaves together and hard-exits: tearing down NCCL communicators that captured CUDA graphs still
         # reference can block at interpreter shutdown, and the result line is already out
