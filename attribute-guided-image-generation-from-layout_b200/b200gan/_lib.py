@@ -116,6 +116,24 @@ class Kernels:
     def version(self) -> int:
         return int(self.lib.b200_version())
 
+    # ---- box -> layout integer work ------------------------------------------------------------------------
+    def rasterize_boxes(self, boxes, H, W):
+        if not boxes.is_cuda or boxes.dtype != torch.float32:
+            raise B200Error("rasterize_boxes: fp32 CUDA boxes required")
+        boxes = boxes.contiguous()
+        O_ = boxes.shape[0]
+        masks = torch.empty((O_, 1, H, W), dtype=torch.float32, device=boxes.device)
+        self._check(self.lib.b200_rasterize_boxes(_ptr(boxes), O_, H, W, _ptr(masks), _stream()), "b200_rasterize_boxes")
+        return masks
+
+    def shift_boxes(self, boxes):
+        if not boxes.is_cuda or boxes.dtype != torch.float32:
+            raise B200Error("shift_boxes: fp32 CUDA boxes required")
+        boxes = boxes.contiguous()
+        out = torch.empty_like(boxes)
+        self._check(self.lib.b200_shift_boxes(_ptr(boxes), boxes.shape[0], _ptr(out), _stream()), "b200_shift_boxes")
+        return out
+
     # ---- crops ----------------------------------------------------------------------------------------
     def crop_fwd(self, feats, boxes, box_to_img, wx, wy, HH, WW):
         N, Cc, H, W = feats.shape
@@ -139,7 +157,7 @@ class Kernels:
     def crop_bwd(self, dcrops, boxes, img_box_start, box_order, wx, wy, N, H, W):
         B, Cc, HH, WW = dcrops.shape
         dfeats = torch.empty((N, Cc, H, W), dtype=torch.float32, device=dcrops.device)
-        ws = torch.empty((max(1, B * Cc * H * WW),), dtype=torch.float32, device=dcrops.device)
+        ws = torch.empty(((B * Cc * H * WW + 3) // 4 * 4 + 4 * max(1, B),), dtype=torch.float32, device=dcrops.device)
         self._check(self.lib.b200_crop_bwd(_ptr(dcrops), _ptr(boxes), _ptr(img_box_start), _ptr(box_order), _ptr(wx),
                                            _ptr(wy), _ptr(dfeats), _ptr(ws), N, Cc, H, W, B, HH, WW, _stream()),
                     "b200_crop_bwd")

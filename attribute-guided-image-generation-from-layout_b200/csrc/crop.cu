@@ -40,11 +40,12 @@ __global__ void crop_fwd_kernel(const float* __restrict__ feats, const float* __
                                 const int32_t* __restrict__ box_to_img, const float* __restrict__ wx,
                                 const float* __restrict__ wy, float* __restrict__ crops, int C, int H, int W, int B,
                                 int HH, int WW) {
-    int64_t total = (int64_t)B * HH * WW;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        int j = (int)(t % WW);
-        int i = (int)((t / WW) % HH);
-        int b = (int)(t / ((int64_t)WW * HH));
+    const uint32_t total = (uint32_t)B * HH * WW;               // < 2^31, checked by the launcher
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const uint32_t q = t / (uint32_t)WW;
+        const int j = (int)(t - q * (uint32_t)WW);
+        const int i = (int)(q % (uint32_t)HH);
+        const int b = (int)(q / (uint32_t)HH);
         const float* bx = boxes + b * 4;
         float ix = crop_coord(bx[0], bx[2], wx[j], wx[WW + j], W);
         float iy = crop_coord(bx[1], bx[3], wy[i], wy[HH + i], H);
@@ -83,21 +84,43 @@ __device__ __forceinline__ void tap_range(float c_first, float c_last, int S, in
     }
 }
 
-// pass 1: T[b,c,y,j] = sum_i wy(i -> y) * dcrops[b,c,i,j]   (rows of the crop that touch image row y, ascending i)
+// pixel footprint of box b: rows / columns of the image any bilinear tap of the crop can touch (one pixel of slack),
+// ext[b] = {ylo, yhi, xlo, xhi} inclusive, clamped to the image.  Pixels outside it receive nothing from the box.
+__global__ void crop_extents_kernel(const float* __restrict__ boxes, const float* __restrict__ wx,
+                                    const float* __restrict__ wy, int4* __restrict__ ext, int B, int H, int W, int HH,
+                                    int WW) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* bx = boxes + b * 4;
+    const float ya = crop_coord(bx[1], bx[3], wy[0], wy[HH], H), yb = crop_coord(bx[1], bx[3], wy[HH - 1], wy[2 * HH - 1], H);
+    const float xa = crop_coord(bx[0], bx[2], wx[0], wx[WW], W), xb = crop_coord(bx[0], bx[2], wx[WW - 1], wx[2 * WW - 1], W);
+    int ylo = (int)floorf(fminf(ya, yb)) - 1, yhi = (int)floorf(fmaxf(ya, yb)) + 2;
+    int xlo = (int)floorf(fminf(xa, xb)) - 1, xhi = (int)floorf(fmaxf(xa, xb)) + 2;
+    ylo = ylo < 0 ? 0 : ylo; xlo = xlo < 0 ? 0 : xlo;
+    yhi = yhi > H - 1 ? H - 1 : yhi; xhi = xhi > W - 1 ? W - 1 : xhi;
+    ext[b] = make_int4(ylo, yhi, xlo, xhi);
+}
+
+// pass 1: T[b,c,y,j] = sum_i wy(i -> y) * dcrops[b,c,i,j]   (rows of the crop that touch image row y, ascending i);
+// one block per (box, channel) walks only the rows of the box's footprint (pass 2 reads no others)
 __global__ void crop_bwd_rows_kernel(const float* __restrict__ dcrops, const float* __restrict__ boxes,
-                                     const float* __restrict__ wy, float* __restrict__ T, int C, int H, int B, int HH,
-                                     int WW) {
-    int64_t total = (int64_t)B * C * H * WW;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        int j = (int)(t % WW);
-        int y = (int)((t / WW) % H);
-        int c = (int)((t / ((int64_t)WW * H)) % C);
-        int b = (int)(t / ((int64_t)WW * H * C));
-        const float* bx = boxes + b * 4;
-        const float* d = dcrops + ((int64_t)b * C + c) * HH * WW + j;
+                                     const float* __restrict__ wy, const int4* __restrict__ ext, float* __restrict__ T,
+                                     int C, int H, int B, int HH, int WW) {
+    const int b = blockIdx.x / C, c = blockIdx.x - b * C;
+    (void)B;
+    const int4 e = ext[b];
+    const float* bx = boxes + b * 4;
+    const float c_first = crop_coord(bx[1], bx[3], wy[0], wy[HH], H);
+    const float c_last = crop_coord(bx[1], bx[3], wy[HH - 1], wy[2 * HH - 1], H);
+    const float* dbase = dcrops + ((int64_t)b * C + c) * HH * WW;
+    float* Tb = T + ((int64_t)b * C + c) * H * WW;
+    const int n = (e.y - e.x + 1) * WW;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int r = idx / WW, j = idx - r * WW;
+        const int y = e.x + r;
+        const float* d = dbase + j;
         int lo, hi;
-        tap_range(crop_coord(bx[1], bx[3], wy[0], wy[HH], H), crop_coord(bx[1], bx[3], wy[HH - 1], wy[2 * HH - 1], H), HH, y,
-                  lo, hi);
+        tap_range(c_first, c_last, HH, y, lo, hi);
         float acc = 0.f;
         for (int i = lo; i < hi; ++i) {
             float iy = crop_coord(bx[1], bx[3], wy[i], wy[HH + i], H);
@@ -106,24 +129,28 @@ __global__ void crop_bwd_rows_kernel(const float* __restrict__ dcrops, const flo
             if (y0 == y) acc += ((y0f + 1.f) - iy) * d[(int64_t)i * WW];
             else if (y0 + 1 == y) acc += (iy - y0f) * d[(int64_t)i * WW];
         }
-        T[t] = acc;
+        Tb[(int64_t)y * WW + j] = acc;
     }
 }
 
 // pass 2: dfeats[n,c,y,x] = sum_{b in image n, ascending} sum_j wx(j -> x) * T[b,c,y,j]
 __global__ void crop_bwd_cols_kernel(const float* __restrict__ T, const float* __restrict__ boxes,
                                      const int32_t* __restrict__ img_box_start, const int32_t* __restrict__ box_order,
-                                     const float* __restrict__ wx, float* __restrict__ dfeats, int N, int C, int H,
-                                     int W, int WW) {
-    int64_t total = (int64_t)N * C * H * W;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        int x = (int)(t % W);
-        int y = (int)((t / W) % H);
-        int c = (int)((t / ((int64_t)W * H)) % C);
-        int n = (int)(t / ((int64_t)W * H * C));
+                                     const float* __restrict__ wx, const int4* __restrict__ ext,
+                                     float* __restrict__ dfeats, int N, int C, int H, int W, int WW) {
+    const uint32_t total = (uint32_t)N * C * H * W;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        uint32_t q = t / (uint32_t)W;
+        const int x = (int)(t - q * (uint32_t)W);
+        const int y = (int)(q % (uint32_t)H);
+        q /= (uint32_t)H;
+        const int c = (int)(q % (uint32_t)C);
+        const int n = (int)(q / (uint32_t)C);
         float acc = 0.f;
         for (int k = img_box_start[n]; k < img_box_start[n + 1]; ++k) {
             int b = box_order[k];
+            const int4 e = ext[b];
+            if (y < e.x || y > e.y || x < e.z || x > e.w) continue;      // outside the box's footprint
             const float* bx = boxes + b * 4;
             const float* row = T + (((int64_t)b * C + c) * H + y) * WW;
             int lo, hi;
@@ -151,6 +178,7 @@ extern "C" int b200_crop_fwd(const float* feats, const float* boxes, const int32
     (void)N;
     if (B == 0) return 0;
     int64_t total = (int64_t)B * HH * WW;
+    B200_REQUIRE(total < (1ll << 31), "crop_fwd: too many crop pixels");
     crop_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(feats, boxes, box_to_img, wx, wy, crops, C, H,
                                                                          W, B, HH, WW);
     B200_CHECK_LAUNCH();
@@ -169,13 +197,19 @@ extern "C" int b200_crop_taps(const float* boxes, const float* wx, const float* 
 extern "C" int b200_crop_bwd(const float* dcrops, const float* boxes, const int32_t* img_box_start,
                              const int32_t* box_order, const float* wx, const float* wy, float* dfeats, float* ws,
                              int N, int C, int H, int W, int B, int HH, int WW, b200_stream_t stream) {
+    // ws: B*C*H*WW floats (pass-1 rows) followed by B int4 footprints (16-byte aligned: the float count is rounded up)
+    const int64_t t1 = (int64_t)B * C * H * WW;
+    int4* ext = reinterpret_cast<int4*>(ws + (t1 + 3) / 4 * 4);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "crop_bwd: workspace must be 16-byte aligned");
+    B200_REQUIRE(t1 < (1ll << 31) && (int64_t)N * C * H * W < (1ll << 31), "crop_bwd: tensors too large");
     if (B > 0) {
-        int64_t t1 = (int64_t)B * C * H * WW;
-        crop_bwd_rows_kernel<<<grid_for(t1, 256), 256, 0, as_stream(stream)>>>(dcrops, boxes, wy, ws, C, H, B, HH, WW);
+        crop_extents_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(boxes, wx, wy, ext, B, H, W, HH, WW);
+        B200_CHECK_LAUNCH();
+        crop_bwd_rows_kernel<<<B * C, 256, 0, as_stream(stream)>>>(dcrops, boxes, wy, ext, ws, C, H, B, HH, WW);
         B200_CHECK_LAUNCH();
     }
     int64_t t2 = (int64_t)N * C * H * W;
-    crop_bwd_cols_kernel<<<grid_for(t2, 256), 256, 0, as_stream(stream)>>>(ws, boxes, img_box_start, box_order, wx,
+    crop_bwd_cols_kernel<<<grid_for(t2, 256), 256, 0, as_stream(stream)>>>(ws, boxes, img_box_start, box_order, wx, ext,
                                                                            dfeats, N, C, H, W, WW);
     B200_CHECK_LAUNCH();
     return 0;

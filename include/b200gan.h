@@ -37,13 +37,25 @@ int b200_version(void);
 int64_t b200_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
+ * Box -> layout integer work (bit-exact contract): the rasterised box masks the LayoutEncoder broadcasts the object
+ * embedding into (generator_obj_att.py:489-490) and the shifted boxes of the "shift" pass.
+ * b200_rasterize_boxes: masks (O,1,H,W) fp32 = 1 inside [round(y0*H), round(y1*H)) x [round(x0*W), round(x1*W)), else 0,
+ *   with Python's round (half to even, on double) and Python slice-bound semantics (data/vg_custom_mask.py:120,136,157);
+ *   boxes (O,4) fp32 [x0,y0,x1,y1].
+ * b200_shift_boxes: data/vg_custom_mask.py:139-158 — boxes narrower than 0.5 move 0.8x of the distance to the farther
+ *   horizontal border (double arithmetic, fp32 result). */
+int b200_rasterize_boxes(const float* boxes, int O, int H, int W, float* masks, b200_stream_t stream);
+int b200_shift_boxes(const float* boxes, int O, float* out, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Box crops — replaces models/bilinear.py:26-41,67-104,107-136 (crop_bbox_batch -> F.grid_sample,
  * bilinear, zeros padding, align_corners=False) and its autograd backward.
  * feats (N,C,H,W) NCHW; boxes (B,4) [x0,y0,x1,y1] in [0,1]; box_to_img (B) int32;
  * wx (2*WW) = [linspace(1,0,WW) | linspace(0,1,WW)] and wy (2*HH) built on the HOST in fp32 exactly
  * as bilinear.py:272-275 does; crops (B,C,HH,WW).
  * b200_crop_taps exports the integer part (floor indices) for the bit-exact index contract.
- * b200_crop_bwd is a deterministic two-pass gather: ws needs B*C*H*WW floats; img_box_start (N+1) int32
+ * b200_crop_bwd is a deterministic two-pass gather restricted to each box's pixel footprint: ws needs B*C*H*WW floats
+ * (rounded up to a multiple of 4) + 4*B more (the footprints), 16-byte aligned; img_box_start (N+1) int32
  * are offsets into box_order (B) int32 = box ids grouped by image (ascending box id inside an image).
  */
 int b200_crop_fwd(const float* feats, const float* boxes, const int32_t* box_to_img, const float* wx, const float* wy,

@@ -1,0 +1,139 @@
+"""-m gpu: the box -> layout integer work (bit-exact), BASELINE config 4 (eval-mode generator forward, test64.py style) and
+config 5 (layout microbench shapes: rasterise + broadcast + crops at 128x128 with 8..30 boxes per image)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from b200gan import _lib, layout, ops  # noqa: E402
+from b200gan.step import TrainStep  # noqa: E402
+from helpers import load_states, rel  # noqa: E402
+from oracle import gan_oracle as O  # noqa: E402
+
+
+def _edge_boxes(seed=0, n=300):
+    g = torch.Generator().manual_seed(seed)
+    xy0 = torch.rand(n, 2, generator=g) * 0.7
+    wh = torch.rand(n, 2, generator=g) * 0.5
+    boxes = torch.cat([xy0, (xy0 + wh).clamp(max=1.0)], 1)
+    # products that land exactly on .5 (Python round is half-to-even): k/128 * 64 = k/2
+    k = torch.randint(0, 129, (n // 3, 4), generator=g).float() / 128.0
+    k = torch.cat([torch.minimum(k[:, :2], k[:, 2:]), torch.maximum(k[:, :2], k[:, 2:])], 1)
+    special = torch.tensor([[0.0, 0.0, 1.0, 1.0], [0.5, 0.5, 0.5, 0.5], [0.9, 0.9, 0.1, 0.1], [0.2578125, 0.0, 0.5078125, 1.0],
+                            [0.0078125, 0.0234375, 0.0390625, 0.0546875], [-0.05, 0.1, 0.4, 1.2], [0.3, -0.2, 1.3, 0.6],
+                            [0.49, 0.0, 0.51, 1.0], [0.0, 0.3, 0.49999, 0.31]])
+    return torch.cat([boxes, k, special]).float().contiguous()
+
+
+@pytest.mark.parametrize("H,W", [(64, 64), (128, 128), (66, 30), (7, 5)])
+def test_rasterize_boxes_bit_exact(H, W):
+    """round-half-even on double + Python slice semantics, against the loader restatement (oracle), bit for bit"""
+    boxes = _edge_boxes(H)
+    got = layout.rasterize_boxes(boxes.cuda(), H, W)
+    want = O.rasterize_boxes(boxes, H, W)
+    assert got.shape == want.shape and torch.equal(got.cpu(), want)
+
+
+def test_shift_boxes_bit_exact():
+    boxes = _edge_boxes(3)
+    got = layout.shift_boxes(boxes.cuda())
+    want = O.shift_boxes(boxes)
+    assert torch.equal(got.cpu(), want)
+    m, bs, ms = layout.layout_inputs(boxes.cuda(), 64)
+    assert torch.equal(ms.cpu(), O.rasterize_boxes(want, 64, 64)) and torch.equal(bs.cpu(), want)
+
+
+def test_rasterize_empty_and_requires_cuda():
+    assert layout.rasterize_boxes(torch.zeros(0, 4).cuda(), 64, 64).shape == (0, 1, 64, 64)
+    with pytest.raises(_lib.B200Error):
+        layout.rasterize_boxes(torch.zeros(2, 4), 64, 64)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 5: layout microbench shapes at 128x128
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("per_image", [8, 12, 16, 20, 24, 30])
+def test_config5_layout_and_crops_128(per_image):
+    """128x128, `per_image` boxes per image: device rasteriser == loader masks; the embedding (x) mask broadcast
+    (LayoutEncoder c0 as rank-1 outer product) and the 64x64 crops forward / backward against the oracle."""
+    N, H, S = 4, 128, 64
+    b = O.synth_batch(N, H, per_image, seed=per_image)
+    boxes, o2i = b["boxes"], b["obj_to_img"]
+    On = boxes.shape[0]
+    masks = layout.rasterize_boxes(boxes.cuda(), H, H)
+    assert torch.equal(masks.cpu(), b["masks"])
+    # broadcast: v (O, C) (x) mask with a zero ring  ==  (v.view(O,C,1,1) * mask) zero-padded by 1   (generator_obj_att.py:489-490, c0 pad 1)
+    g = torch.Generator().manual_seed(1)
+    v = torch.randn(On, 64, generator=g)
+    out = _lib.K.mask_outer_fwd(v.cuda(), masks, On, H, H, 64)
+    want = torch.nn.functional.pad(v.view(On, 64, 1, 1) * b["masks"], (1, 1, 1, 1)).permute(0, 2, 3, 1)
+    assert torch.equal(out.cpu(), want.contiguous())
+    # crops: forward values, bit-exact tap indices, deterministic backward
+    feats = torch.randn(N, 3, H, H, generator=g)
+    fr = feats.clone().requires_grad_(True)
+    want_c = O.crop_bbox_batch(fr, boxes, o2i, S)
+    fd = feats.cuda().requires_grad_(True)
+    got_c = ops.crop_bbox_batch(fd, boxes.cuda(), o2i, S)
+    assert float((got_c.detach().cpu() - want_c.detach()).abs().max()) < 2e-6
+    wgt = torch.randn(want_c.shape, generator=g)
+    (want_c * wgt).sum().backward()
+    (got_c * wgt.cuda()).sum().backward()
+    assert rel(fd.grad, fr.grad) < 1e-5
+    ix0, iy0, _, _ = _lib.K.crop_taps(boxes.cuda(), ops.crop_weights(S, "cuda"), ops.crop_weights(S, "cuda"), H, H, S, S)
+    rx0, ry0, _, _ = O.crop_taps(boxes, H, H, S, S)
+    assert torch.equal(ix0.cpu(), rx0) and torch.equal(iy0.cpu(), ry0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 4: eval-mode generator forward (test64.py:114-198 style)
+# ---------------------------------------------------------------------------------------------------------
+def test_config4_eval_generator_matches_oracle():
+    """netG.eval(): running-statistics BN / CBN / SPADE, no running-stat updates; all 11 outputs against the oracle in
+    eval mode with the same CropEncoder noise (fp32 kernels, 1e-4)."""
+    ops.set_precision("fp32")
+    states = O.make_states(64, 2)
+    batch = O.synth_batch(3, 64, None, 21)
+    ts = TrainStep(64, device="cuda")
+    load_states(ts, states)
+    ts.netG.eval()
+    before = {k: v.clone() for k, v in ts.netG.state_dict().items() if "running" in k or "num_batches" in k}
+    b = ts.to_device(batch)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        got = ts.netG(b["imgs"], b["objs"], b["boxes"], b["masks"], b["obj_to_img"], b["z"], b["attribute"], b["masks_shift"],
+                      b["boxes_shift"], b["attribute"])
+    torch.manual_seed(77)
+    with torch.no_grad():
+        want = O.generator_forward(states["G"], batch["imgs"], batch["objs"], batch["boxes"], batch["masks"],
+                                   batch["obj_to_img"], batch["z"], batch["attribute"], batch["masks_shift"],
+                                   batch["boxes_shift"], batch["attribute"], training=False, image_size=64)
+    for i, (a, r) in enumerate(zip(got, want)):
+        assert rel(a, r) < 1e-4, "eval-mode generator output %d: %.3e" % (i, rel(a, r))
+    after = ts.netG.state_dict()
+    for k, v in before.items():
+        assert torch.equal(after[k], v), "eval mode must not touch %s" % k
+
+
+def test_config4_full_size_properties():
+    """BASELINE config 4 shape: batch 256, 8 objects/image, generator-only eval forward in bf16 — finite images, generated
+    crops equal crops of the generated images, and images are independent of the rest of the batch (eval mode)."""
+    ops.set_precision("bf16")
+    try:
+        ts = TrainStep(64, device="cuda")
+        ts.netG.eval()
+        ts.netG.crop_encoder.eps_source = lambda o, z, d: torch.zeros(o, z, device=d)
+        batch = O.synth_batch(256, 64, 8, 5)
+        b = ts.to_device(batch)
+        with torch.no_grad():
+            out = ts.netG(b["imgs"], b["objs"], b["boxes"], b["masks"], b["obj_to_img"], b["z"], b["attribute"],
+                          b["masks_shift"], b["boxes_shift"], b["attribute"])
+            assert out[5].shape == (256, 3, 64, 64) and all(torch.isfinite(t).all() for t in out)
+            again = ops.crop_bbox_batch(out[5], b["boxes"], b["obj_to_img"], 32)
+            assert torch.equal(again, out[2])
+            sub = {k: (v[:64 * 8] if v.shape[0] == 2048 else v[:64]) for k, v in batch.items()}
+            bs = ts.to_device(sub)
+            part = ts.netG(bs["imgs"], bs["objs"], bs["boxes"], bs["masks"], bs["obj_to_img"], bs["z"], bs["attribute"],
+                           bs["masks_shift"], bs["boxes_shift"], bs["attribute"])
+            assert rel(part[5], out[5][:64]) < 2e-2       # bf16 tiles differ with the batch size; eval BN is per sample
+    finally:
+        ops.set_precision("fp32")
