@@ -500,6 +500,11 @@ class Kernels:
                                                       int(bool(do_iter)), C.c_float(eps), _stream()),
                     "b200_sn_power_iter_multi")
 
+    def adam_multi(self, table, n_entries, step, lr, beta1, beta2, eps):
+        """one Adam update of every chunk in the device table (b200_adam_entry[]); `step` is a 0-dim fp32 CUDA tensor"""
+        self._check(self.lib.b200_adam_multi(_ptr(table), int(n_entries), _ptr(step), C.c_double(lr), C.c_double(beta1),
+                                             C.c_double(beta2), C.c_double(eps), _stream()), "b200_adam_multi")
+
     def copy_into(self, dst, dst_row, src):
         """dst[dst_row : dst_row + src.shape[0]] = src (contiguous tensors of equal row size and dtype)"""
         if not (dst.is_cuda and src.is_cuda):

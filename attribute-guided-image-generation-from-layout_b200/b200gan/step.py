@@ -72,7 +72,7 @@ def estimate_attributes(att_logits, attribute):
 class TrainStep:
     def __init__(self, image_size: int = 64, device="cuda", lr: float = 2e-4, lambdas: Optional[Dict[str, float]] = None,
                  pos_weight: Optional[torch.Tensor] = None, skip_dead_work: bool = True, fused_adam: bool = True,
-                 capturable: bool = False):
+                 capturable: bool = False, optimizer: str = "b200"):
         self.image_size, self.obj_size = image_size, image_size // 2
         self.device = torch.device(device)
         self.lam = dict(LAMBDAS if lambdas is None else lambdas)
@@ -82,10 +82,14 @@ class TrainStep:
         self.fake_w = torch.tensor(FAKE_W, device=self.device)
         self.skip_dead_work = skip_dead_work
         kw = dict(lr=lr, betas=(0.5, 0.999))
-        if self.device.type == "cuda":
-            kw.update(fused=fused_adam, capturable=capturable)
-        self.opt_G = torch.optim.Adam(self.netG.parameters(), **kw)                  # train64.py:111-114
-        self.opt_D = [torch.optim.Adam(n.parameters(), **kw) for n in (self.netD_image, self.netD_object, self.netD_att)]
+        if self.device.type == "cuda" and optimizer == "b200":
+            from .optim import Adam                                                  # multi-tensor kernel, device step counter
+        else:
+            Adam = torch.optim.Adam
+            if self.device.type == "cuda":
+                kw.update(fused=fused_adam, capturable=capturable)
+        self.opt_G = Adam(self.netG.parameters(), **kw)                              # train64.py:111-114
+        self.opt_D = [Adam(n.parameters(), **kw) for n in (self.netD_image, self.netD_object, self.netD_att)]
         self.d_nets = (self.netD_image, self.netD_object, self.netD_att)
         self.ddp_d = self.ddp_g = None
 

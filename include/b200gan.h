@@ -306,6 +306,22 @@ typedef struct {
 int b200_sn_power_iter_multi(const b200_sn_layer* layers, int n_layers, int max_h, int max_w, int iters, int do_iter,
                              float eps, b200_stream_t stream);
 
+/* Multi-tensor Adam (torch.optim.Adam(params, lr, betas) as train64.py:111-114 builds it: no weight decay, no amsgrad):
+ * ONE launch updates every chunk listed in the DEVICE array `entries` (a tensor is split into chunks of <= 65536 elements by
+ * the host so that blocks are balanced).  *step_dev (float, on the device) is incremented first and supplies the bias
+ * corrections, so the update can be captured in a CUDA graph.
+ *   m = m + (g - m)*(1-b1);  v = v*b2 + (1-b2)*g*g;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) */
+typedef struct {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int32_t n;
+    int32_t pad;
+} b200_adam_entry;
+int b200_adam_multi(const b200_adam_entry* entries_dev, int n_entries, float* step_dev, double lr, double beta1,
+                    double beta2, double eps, b200_stream_t stream);
+
 /* plain device-to-device copy on the stream (row concatenation of batched calls) */
 int b200_copy(void* dst, const void* src, size_t bytes, b200_stream_t stream);
 

@@ -486,6 +486,9 @@ class EmulKernels:
                 stage[so + iters + it * h:so + iters + (it + 1) * h] = u
                 stage[so + iters + iters * h + it * w:so + iters + iters * h + (it + 1) * w] = v
 
+    def adam_multi(self, table, n_entries, step, lr, beta1, beta2, eps):
+        raise NotImplementedError("adam_multi takes raw device pointers; the CPU wiring tests use torch.optim.Adam")
+
     def copy_into(self, dst, dst_row, src):
         self.launches += 1
         dst[dst_row:dst_row + src.shape[0]].copy_(src)
