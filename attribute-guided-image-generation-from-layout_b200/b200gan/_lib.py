@@ -340,11 +340,24 @@ class Kernels:
                     "b200_pool_fwd")
         return y
 
-    def pool_add_fwd(self, a, b, N, H, W, Cc, f, scale):
+    def pool_add_fwd(self, a, b, N, H, W, Cc, f, scale, relu=False):
         _same_dt(a, b)
         y = torch.empty((N, H // f, W // f, Cc), dtype=a.dtype, device=a.device)
-        self._check(self.lib.b200_pool_add_fwd(_ptr(a), _ptr(b), _ptr(y), N, H, W, Cc, f, C.c_float(scale), _dt(a), _stream()),
-                    "b200_pool_add_fwd")
+        self._check(self.lib.b200_pool_add_fwd(_ptr(a), _ptr(b), _ptr(y), N, H, W, Cc, f, C.c_float(scale), int(bool(relu)),
+                                               _dt(a), _stream()), "b200_pool_add_fwd")
+        return y
+
+    def add_relu(self, a, b):
+        dt = _same_dt(a, b)
+        out = torch.empty_like(a)
+        self._check(self.lib.b200_add_relu(_ptr(a), _ptr(b), _ptr(out), C.c_int64(a.numel()), dt, _stream()), "b200_add_relu")
+        return out
+
+    def unpool_masked_fwd(self, x, mask, N, H, W, Cc, f, scale):
+        _same_dt(x, mask)
+        y = torch.empty((N, H * f, W * f, Cc), dtype=x.dtype, device=x.device)
+        self._check(self.lib.b200_unpool_masked_fwd(_ptr(x), _ptr(mask), _ptr(y), N, H, W, Cc, f, C.c_float(scale), _dt(x),
+                                                    _stream()), "b200_unpool_masked_fwd")
         return y
 
     def unpool_fwd(self, x, N, H, W, Cc, f, scale):

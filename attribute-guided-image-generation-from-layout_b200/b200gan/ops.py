@@ -735,24 +735,49 @@ class _PoolFn(torch.autograd.Function):
 
 
 class _PoolAddFn(torch.autograd.Function):
-    """y = scale * (f x f block sums of a + b); both inputs receive the same gradient tensor"""
+    """y = [relu](scale * (f x f block sums of a + b)); both inputs receive the same gradient tensor"""
 
     @staticmethod
-    def forward(ctx, a, b, f, scale):
+    def forward(ctx, a, b, f, scale, relu):
         N, H, W, C = a.shape
-        ctx.f, ctx.scale = f, scale
-        return _lib.K.pool_add_fwd(a.contiguous(), b.contiguous(), N, H, W, C, f, scale)
+        ctx.f, ctx.scale, ctx.relu = f, scale, relu
+        y = _lib.K.pool_add_fwd(a.contiguous(), b.contiguous(), N, H, W, C, f, scale, relu)
+        if relu:
+            ctx.save_for_backward(y)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
         N, H, W, C = dy.shape
-        g = _lib.K.unpool_fwd(dy.contiguous(), N, H, W, C, ctx.f, ctx.scale)
-        return g, g, None, None
+        if ctx.relu:
+            (y,) = ctx.saved_tensors
+            g = _lib.K.unpool_masked_fwd(dy.contiguous(), y, N, H, W, C, ctx.f, ctx.scale)
+        else:
+            g = _lib.K.unpool_fwd(dy.contiguous(), N, H, W, C, ctx.f, ctx.scale)
+        return g, g, None, None, None
 
 
-def avg_pool2_sum(a, b):
-    """avg_pool2(a + b) in one pass"""
-    return _PoolAddFn.apply(a, b, 2, 0.25)
+def avg_pool2_sum(a, b, relu=False):
+    """[relu](avg_pool2(a + b)) in one pass"""
+    return _PoolAddFn.apply(a, b, 2, 0.25, relu)
+
+
+class _AddReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        y = _lib.K.add_relu(a.contiguous(), b.contiguous())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        g = _lib.K.relu_bwd(dy.contiguous(), y)
+        return g, g
+
+
+def add_relu(a, b):
+    return _AddReluFn.apply(a, b)
 
 
 class _UnpoolFn(torch.autograd.Function):

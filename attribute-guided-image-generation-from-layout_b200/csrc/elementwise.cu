@@ -40,19 +40,24 @@ __global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ 
 }
 
 template <typename T>
-__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, int64_t nv, int tail) {
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, int64_t nv, int tail,
+                           int relu) {
     constexpr int V = VecIO<T>::V;
     GRID_STRIDE(i, nv) {
         float u[V], v[V];
         VecIO<T>::load(a + i * V, u);
         VecIO<T>::load(b + i * V, v);
 #pragma unroll
-        for (int e = 0; e < V; ++e) u[e] += v[e];
+        for (int e = 0; e < V; ++e) {
+            u[e] += v[e];
+            if (relu) u[e] = fmaxf(u[e], 0.f);
+        }
         VecIO<T>::store(o + i * V, u);
     }
     if (blockIdx.x == 0 && threadIdx.x < tail) {
         const int64_t t = nv * V + threadIdx.x;
-        stf(o + t, ldf(a + t) + ldf(b + t));
+        const float s = ldf(a + t) + ldf(b + t);
+        stf(o + t, relu ? fmaxf(s, 0.f) : s);
     }
 }
 
@@ -60,7 +65,7 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* 
 // 1); I = index type (32-bit when the element count fits: no 64-bit divisions)
 template <typename T, int V, typename I>
 __global__ void pool_fwd_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y, int N, int H, int W,
-                                int C, int f, float scale) {
+                                int C, int f, float scale, int relu) {
     const int Ho = H / f, Wo = W / f, Cv = C / V;
     const I total = (I)N * Ho * Wo * Cv;
     for (I t = blockIdx.x * (I)blockDim.x + threadIdx.x; t < total; t += (I)gridDim.x * blockDim.x) {
@@ -89,7 +94,10 @@ __global__ void pool_fwd_kernel(const T* __restrict__ x, const T* __restrict__ x
                     }
                 }
 #pragma unroll
-            for (int e = 0; e < V; ++e) acc[e] *= scale;
+            for (int e = 0; e < V; ++e) {
+                acc[e] *= scale;
+                if (relu) acc[e] = fmaxf(acc[e], 0.f);
+            }
             VecIO<T>::store(y + (int64_t)t * V, acc);
         } else {
             float acc = 0.f;
@@ -98,15 +106,15 @@ __global__ void pool_fwd_kernel(const T* __restrict__ x, const T* __restrict__ x
                     acc += ldf(p + ((int64_t)dy * W + dx) * C);
                     if (x2) acc += ldf(x2 + (p - x) + ((int64_t)dy * W + dx) * C);
                 }
-            stf(y + (int64_t)t, acc * scale);
+            stf(y + (int64_t)t, relu ? fmaxf(acc * scale, 0.f) : acc * scale);
         }
     }
 }
 
 // y[n,oy,ox,c] = scale * x[n,oy/f,ox/f,c]  (nearest upsampling; the adjoint of pool_fwd)
 template <typename T, int V, typename I>
-__global__ void unpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f,
-                                  float scale) {
+__global__ void unpool_fwd_kernel(const T* __restrict__ x, const T* __restrict__ mask, T* __restrict__ y, int N, int H,
+                                  int W, int C, int f, float scale) {
     const int Ho = H * f, Wo = W * f, Cv = C / V;
     const I total = (I)N * Ho * Wo * Cv;
     for (I t = blockIdx.x * (I)blockDim.x + threadIdx.x; t < total; t += (I)gridDim.x * blockDim.x) {
@@ -121,11 +129,20 @@ __global__ void unpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, in
             static_assert(V == VecIO<T>::V, "vector width");
             float v[V];
             VecIO<T>::load(p, v);
+            if (mask) {          // gradient of relu(pool(.)): zero where the pooled output was not positive
+                float mk[V];
+                VecIO<T>::load(mask + (p - x), mk);
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+                    if (!(mk[e] > 0.f)) v[e] = 0.f;
+            }
 #pragma unroll
             for (int e = 0; e < V; ++e) v[e] *= scale;
             VecIO<T>::store(y + (int64_t)t * V, v);
         } else {
-            stf(y + (int64_t)t, scale * ldf(p));
+            float v = ldf(p);
+            if (mask && !(ldf(mask + (p - x)) > 0.f)) v = 0.f;
+            stf(y + (int64_t)t, scale * v);
         }
     }
 }
@@ -765,21 +782,29 @@ extern "C" int b200_relu_bwd(const void* dy, const void* y, void* dx, int64_t n,
     return 0;
 }
 
-extern "C" int b200_add(const void* a, const void* b, void* out, int64_t n, int dt, b200_stream_t stream) {
+static int add_launch(const void* a, const void* b, void* out, int64_t n, int dt, int relu, b200_stream_t stream) {
     if (n == 0) return 0;
     B200_DISPATCH_DT(dt, T, {
         int64_t n4 = (aligned16(a) && aligned16(b) && aligned16(out)) ? n / VecIO<T>::V : 0;
         int tail = (int)(n - n4 * VecIO<T>::V);
         B200_REQUIRE(tail < 256, "add: unaligned large tensor");
         add_kernel<T><<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (T*)out, n4,
-                                                                                 tail);
+                                                                                 tail, relu);
     });
     B200_CHECK_LAUNCH();
     return 0;
 }
 
+extern "C" int b200_add(const void* a, const void* b, void* out, int64_t n, int dt, b200_stream_t stream) {
+    return add_launch(a, b, out, n, dt, 0, stream);
+}
+
+extern "C" int b200_add_relu(const void* a, const void* b, void* out, int64_t n, int dt, b200_stream_t stream) {
+    return add_launch(a, b, out, n, dt, 1, stream);
+}
+
 static int pool_launch(const void* x, const void* x2, void* y, int N, int H, int W, int C, int f, float scale, int dt,
-                       b200_stream_t stream) {
+                       int relu, b200_stream_t stream) {
     B200_REQUIRE(f >= 1 && H % f == 0 && W % f == 0, "pool_fwd: H=%d W=%d not divisible by f=%d", H, W, f);
     int64_t total = (int64_t)N * (H / f) * (W / f) * C;
     if (total == 0) return 0;
@@ -789,11 +814,11 @@ static int pool_launch(const void* x, const void* x2, void* y, int N, int H, int
         const T* a = (const T*)x;
         const T* b = (const T*)x2;
         if (C % V == 0 && aligned16(x) && aligned16(y) && (x2 == nullptr || aligned16(x2))) {
-            if (small) pool_fwd_kernel<T, V, uint32_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale);
-            else pool_fwd_kernel<T, V, int64_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale);
+            if (small) pool_fwd_kernel<T, V, uint32_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale, relu);
+            else pool_fwd_kernel<T, V, int64_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale, relu);
         } else {
-            if (small) pool_fwd_kernel<T, 1, uint32_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale);
-            else pool_fwd_kernel<T, 1, int64_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale);
+            if (small) pool_fwd_kernel<T, 1, uint32_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale, relu);
+            else pool_fwd_kernel<T, 1, int64_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(a, b, (T*)y, N, H, W, C, f, scale, relu);
         }
     });
     B200_CHECK_LAUNCH();
@@ -802,32 +827,45 @@ static int pool_launch(const void* x, const void* x2, void* y, int N, int H, int
 
 extern "C" int b200_pool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt,
                              b200_stream_t stream) {
-    return pool_launch(x, nullptr, y, N, H, W, C, f, scale, dt, stream);
+    return pool_launch(x, nullptr, y, N, H, W, C, f, scale, dt, 0, stream);
 }
 
 extern "C" int b200_pool_add_fwd(const void* a, const void* b, void* y, int N, int H, int W, int C, int f, float scale,
-                                 int dt, b200_stream_t stream) {
+                                 int relu, int dt, b200_stream_t stream) {
     B200_REQUIRE(a != nullptr && b != nullptr, "pool_add_fwd: two inputs required");
-    return pool_launch(a, b, y, N, H, W, C, f, scale, dt, stream);
+    return pool_launch(a, b, y, N, H, W, C, f, scale, dt, relu, stream);
 }
 
-extern "C" int b200_unpool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt,
-                               b200_stream_t stream) {
+static int unpool_launch(const void* x, const void* mask, void* y, int N, int H, int W, int C, int f, float scale, int dt,
+                         b200_stream_t stream) {
     int64_t total = (int64_t)N * H * f * W * f * C;
     if (total == 0) return 0;
     B200_DISPATCH_DT(dt, T, {
         constexpr int V = VecIO<T>::V;
         const bool small = total < (1ll << 31);
-        if (C % V == 0 && aligned16(x) && aligned16(y)) {
-            if (small) unpool_fwd_kernel<T, V, uint32_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
-            else unpool_fwd_kernel<T, V, int64_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+        const T* xp = (const T*)x;
+        const T* mp = (const T*)mask;
+        if (C % V == 0 && aligned16(x) && aligned16(y) && (mask == nullptr || aligned16(mask))) {
+            if (small) unpool_fwd_kernel<T, V, uint32_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>(xp, mp, (T*)y, N, H, W, C, f, scale);
+            else unpool_fwd_kernel<T, V, int64_t><<<grid_for(total / V, 256), 256, 0, as_stream(stream)>>>(xp, mp, (T*)y, N, H, W, C, f, scale);
         } else {
-            if (small) unpool_fwd_kernel<T, 1, uint32_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
-            else unpool_fwd_kernel<T, 1, int64_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, f, scale);
+            if (small) unpool_fwd_kernel<T, 1, uint32_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(xp, mp, (T*)y, N, H, W, C, f, scale);
+            else unpool_fwd_kernel<T, 1, int64_t><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(xp, mp, (T*)y, N, H, W, C, f, scale);
         }
     });
     B200_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int b200_unpool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt,
+                               b200_stream_t stream) {
+    return unpool_launch(x, nullptr, y, N, H, W, C, f, scale, dt, stream);
+}
+
+extern "C" int b200_unpool_masked_fwd(const void* x, const void* mask, void* y, int N, int H, int W, int C, int f, float scale,
+                                      int dt, b200_stream_t stream) {
+    B200_REQUIRE(mask != nullptr, "unpool_masked_fwd: mask required");
+    return unpool_launch(x, mask, y, N, H, W, C, f, scale, dt, stream);
 }
 
 extern "C" int b200_concat_fwd(const void* a, int Ca, int a_div, const void* b, int Cb, int b_div, void* out,

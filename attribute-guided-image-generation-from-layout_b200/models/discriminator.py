@@ -26,14 +26,17 @@ class OptimizedBlock(nn.Module):
         if self.learnable_sc:
             self.sc = bnn.Conv2d(dim_in, dim_out, kernel_size=1, padding=0, bias=True)
 
-    def forward(self, x, groups=1):
+    def forward(self, x, groups=1, out_relu=False):
+        """out_relu: return relu(block output) — every consumer of a discriminator block applies ReLU first (the next
+        ResidualBlock's in-place ReLU, or the trunk's final one), so the trunk asks for the activated tensor directly"""
         h = self.resi[0](x, x_layout="nchw", relu=True, groups=groups)
         h = self.resi[2](h, groups=groups)
         s = x
         if self.downsample:
             h = ops.avg_pool2(h)
             s = ops.pool_nchw(x, 2, 0.25)
-        return ops.add(h, self.sc(s, x_layout="nchw", groups=groups))
+        s = self.sc(s, x_layout="nchw", groups=groups)
+        return ops.add_relu(h, s) if out_relu else ops.add(h, s)
 
 
 class ResidualBlock(nn.Module):
@@ -52,12 +55,15 @@ class ResidualBlock(nn.Module):
         if self.learnable_sc:
             self.sc = bnn.Conv2d(dim_in, dim_out, kernel_size=1, padding=0, bias=True)
 
-    def forward(self, x, groups=1):
-        r = ops.relu(x)
+    def forward(self, x, groups=1, in_relu=False, out_relu=False):
+        """in_relu: x already is relu(previous block output); out_relu: return relu(block output) (see OptimizedBlock)"""
+        r = x if in_relu else ops.relu(x)
         h = self.resi[1](r, relu=True, groups=groups)
         h = self.resi[3](h, groups=groups)
         s = self.sc(r, groups=groups) if self.learnable_sc else r
-        return ops.avg_pool2_sum(h, s) if self.downsample else ops.add(h, s)
+        if self.downsample:
+            return ops.avg_pool2_sum(h, s, relu=out_relu)
+        return ops.add_relu(h, s) if out_relu else ops.add(h, s)
 
 
 def _trunk(net, x, groups):
@@ -65,9 +71,10 @@ def _trunk(net, x, groups):
     iterations first (in call order) and call g's rows are scaled by its own 1/sigma_g."""
     bnn.sn_prepare(net, groups)
     h = x
-    for blk in net.main:
-        h = blk(h, groups=groups)
-    h = ops.relu(h)
+    for i, blk in enumerate(net.main):
+        # block outputs are consumed only through ReLU (the next block's in-place ReLU, the final one below):
+        # each block hands over the activated tensor, fused into its last kernel
+        h = blk(h, groups=groups, out_relu=True) if i == 0 else blk(h, groups=groups, in_relu=True, out_relu=True)
     N, H, W, C = h.shape
     return ops.pool(h, H, 1.0).view(N, C)     # in-place ReLU then sum over (H, W) (discriminator.py:224-226)
 

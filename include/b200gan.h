@@ -213,9 +213,16 @@ int b200_add(const void* a, const void* b, void* out, int64_t n, int dt, b200_st
 /* y[n, qy, qx, c] = scale * sum_{f x f block} x[n, qy*f+dy, qx*f+dx, c]  (x: (N,H,W,C), H%f==0) */
 int b200_pool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt, b200_stream_t stream);
 /* y = scale * pooled sum of (a + b): the residual branch and the shortcut of a downsampling discriminator block
- * (discriminator.py:98-99: pool(resi(x)) + pool(sc(x)), pooling being linear) in one pass */
-int b200_pool_add_fwd(const void* a, const void* b, void* y, int N, int H, int W, int C, int f, float scale, int dt,
-                      b200_stream_t stream);
+ * (discriminator.py:98-99: pool(resi(x)) + pool(sc(x)), pooling being linear) in one pass; relu != 0 applies the ReLU every
+ * consumer of the block output starts with */
+int b200_pool_add_fwd(const void* a, const void* b, void* y, int N, int H, int W, int C, int f, float scale, int relu,
+                      int dt, b200_stream_t stream);
+/* out = relu(a + b) (a block's output when every consumer applies ReLU first, discriminator.py:70-74,224) */
+int b200_add_relu(const void* a, const void* b, void* out, int64_t n, int dt, b200_stream_t stream);
+/* y = scale * x[.., iy/f, ix/f, ..] where mask[.., iy/f, ix/f, ..] > 0, else 0 (mask shaped like x): the gradient of
+ * relu(pool(.)) in one pass */
+int b200_unpool_masked_fwd(const void* x, const void* mask, void* y, int N, int H, int W, int C, int f, float scale, int dt,
+                           b200_stream_t stream);
 /* y[n, iy, ix, c] = scale * x[n, iy/f, ix/f, c]  (x: (N,H,W,C) -> y: (N,H*f,W*f,C)) */
 int b200_unpool_fwd(const void* x, void* y, int N, int H, int W, int C, int f, float scale, int dt, b200_stream_t stream);
 /* out[row] = [ a[row / a_div][0:Ca] | b[row / b_div][0:Cb] ] and its adjoint (sums over the broadcast rows, fixed order) */

@@ -326,9 +326,19 @@ class EmulKernels:
         self.launches += 1
         return (x.float().reshape(N, H // f, f, W // f, f, C).sum(dim=(2, 4)) * scale).to(x.dtype)
 
-    def pool_add_fwd(self, a, b, N, H, W, C, f, scale):
+    def pool_add_fwd(self, a, b, N, H, W, C, f, scale, relu=False):
         self.launches += 1
-        return ((a.float() + b.float()).reshape(N, H // f, f, W // f, f, C).sum(dim=(2, 4)) * scale).to(a.dtype)
+        y = (a.float() + b.float()).reshape(N, H // f, f, W // f, f, C).sum(dim=(2, 4)) * scale
+        return (F.relu(y) if relu else y).to(a.dtype)
+
+    def add_relu(self, a, b):
+        self.launches += 1
+        return F.relu(a.float() + b.float()).to(a.dtype)
+
+    def unpool_masked_fwd(self, x, mask, N, H, W, C, f, scale):
+        self.launches += 1
+        v = (x.float() * (mask.float() > 0)).reshape(N, H, 1, W, 1, C).expand(N, H, f, W, f, C)
+        return (v * scale).reshape(N, H * f, W * f, C).to(x.dtype)
 
     def unpool_fwd(self, x, N, H, W, C, f, scale):
         self.launches += 1
