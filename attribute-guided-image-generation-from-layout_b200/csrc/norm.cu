@@ -49,38 +49,56 @@ __global__ void bn_stats_partial_kernel(const T* __restrict__ x, int64_t rows_pe
     }
 }
 
-// one warp per channel: lanes stride over the chunks, fixed-order shuffle tree (deterministic); the groups' running
-// statistics updates are applied one after the other, as the separate calls would have
-__global__ void bn_stats_final_kernel(const double* __restrict__ ws, int nchunks, int C, int groups,
-                                      int64_t rows_per_group, float* mean, float* var, float* running_mean,
-                                      float* running_var, float momentum) {
-    int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= C) return;
-    int lane = threadIdx.x & 31;
+// one block (128 threads) per channel: threads stride over the chunks of every group at once (all loads independent), then
+// a fixed-order tree (warp shuffles, 4 warps through shared memory); the groups' running-statistics updates are applied
+// one after the other, as the separate calls would have.  groups <= 8 per pass.
+__global__ void __launch_bounds__(128) bn_stats_final_kernel(const double* __restrict__ ws, int nchunks, int C, int groups,
+                                                            int64_t rows_per_group, float* mean, float* var,
+                                                            float* running_mean, float* running_var, float momentum) {
+    constexpr int GB = 8;
+    __shared__ double red[4][GB][2];
+    const int c = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float rm = 0.f, rv = 0.f;
-    if (running_mean && lane == 0) { rm = running_mean[c]; rv = running_var[c]; }
-    for (int g = 0; g < groups; ++g) {
-        double s1 = 0.0, s2 = 0.0;
-#pragma unroll 4
-        for (int k = lane; k < nchunks; k += 32) {
-            const double* p = ws + (((int64_t)g * nchunks + k) * C + c) * 2;
-            s1 += p[0];
-            s2 += p[1];
+    if (running_mean && threadIdx.x == 0) { rm = running_mean[c]; rv = running_var[c]; }
+    for (int g0 = 0; g0 < groups; g0 += GB) {
+        double s1[GB], s2[GB];
+#pragma unroll
+        for (int u = 0; u < GB; ++u) s1[u] = s2[u] = 0.0;
+        for (int k = threadIdx.x; k < nchunks; k += 128) {
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                if (g0 + u < groups) {
+                    const double* p = ws + (((int64_t)(g0 + u) * nchunks + k) * C + c) * 2;
+                    s1[u] += p[0];
+                    s2[u] += p[1];
+                }
+            }
         }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (lane == 0) {
-            double m = s1 / (double)rows_per_group;
-            double v = s2 / (double)rows_per_group - m * m;
-            if (v < 0.0) v = 0.0;
-            mean[(int64_t)g * C + c] = (float)m;
-            var[(int64_t)g * C + c] = (float)v;
-            double unb = rows_per_group > 1 ? v * (double)rows_per_group / (double)(rows_per_group - 1) : v;
-            rm = (1.f - momentum) * rm + momentum * (float)m;
-            rv = (1.f - momentum) * rv + momentum * (float)unb;
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+            const double t1 = warp_sum(s1[u]), t2 = warp_sum(s2[u]);
+            if (lane == 0) { red[warp][u][0] = t1; red[warp][u][1] = t2; }
         }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int u = 0; u < GB && g0 + u < groups; ++u) {
+                const int g = g0 + u;
+                const double t1 = (red[0][u][0] + red[1][u][0]) + (red[2][u][0] + red[3][u][0]);
+                const double t2 = (red[0][u][1] + red[1][u][1]) + (red[2][u][1] + red[3][u][1]);
+                double m = t1 / (double)rows_per_group;
+                double v = t2 / (double)rows_per_group - m * m;
+                if (v < 0.0) v = 0.0;
+                mean[(int64_t)g * C + c] = (float)m;
+                var[(int64_t)g * C + c] = (float)v;
+                double unb = rows_per_group > 1 ? v * (double)rows_per_group / (double)(rows_per_group - 1) : v;
+                rm = (1.f - momentum) * rm + momentum * (float)m;
+                rv = (1.f - momentum) * rv + momentum * (float)unb;
+            }
+        }
+        __syncthreads();
     }
-    if (running_mean && lane == 0) { running_mean[c] = rm; running_var[c] = rv; }
+    if (running_mean && threadIdx.x == 0) { running_mean[c] = rm; running_var[c] = rv; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -609,8 +627,8 @@ extern "C" int b200_bn_stats(const void* x, int dt, int64_t rows, int C, int gro
         }
     });
     B200_CHECK_LAUNCH();
-    bn_stats_final_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, nchunks, C, groups, rpg, mean, var, running_mean,
-                                                                      running_var, momentum);
+    bn_stats_final_kernel<<<C, 128, 0, as_stream(stream)>>>(ws, nchunks, C, groups, rpg, mean, var, running_mean, running_var,
+                                                            momentum);
     B200_CHECK_LAUNCH();
     return 0;
 }
