@@ -36,6 +36,7 @@ class ConvDesc(C.Structure):
         ("ldw", C.c_int64),
         ("relu", C.c_int),
         ("scale_rows", C.c_int),
+        ("relu_mask", C.c_void_p),
     ]
 
 
@@ -187,7 +188,14 @@ class Kernels:
                     "b200_rowsum")
         return out
 
-    def conv_gemm(self, desc: ConvDesc, inp, wmat, bias, scale, out, tc: bool):
+    def conv_gemm(self, desc: ConvDesc, inp, wmat, bias, scale, out, tc: bool, mask=None):
+        """mask (tcgen05 path only): tensor laid out like `out`; outputs are zeroed where it is not > 0"""
+        if mask is not None:
+            if not tc or mask.dtype != out.dtype or mask.shape != out.shape or not mask.is_contiguous():
+                raise B200Error("conv_gemm: relu mask must match the output (tcgen05 path)")
+            desc.relu_mask = mask.data_ptr()
+        else:
+            desc.relu_mask = None
         if not tc:
             self._check(self.lib.b200_conv_gemm_f32(C.byref(desc), _ptr(inp), _dt(inp), _ptr(wmat), _ptr(bias), _ptr(scale),
                                                     _ptr(out), _dt(out), _stream()), "b200_conv_gemm_f32")

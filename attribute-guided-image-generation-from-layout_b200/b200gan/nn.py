@@ -52,11 +52,14 @@ class Conv2d(nn.Conv2d):
                               self.stride[0], self.padding[0])
         self._packs = WeightPacks()
 
-    def forward(self, x, x_layout="cl", out_layout="cl", relu=False, groups=1, out_dtype=None):
+    def forward(self, x, x_layout="cl", out_layout="cl", relu=False, groups=1, out_dtype=None, mask_input_grad=False,
+                grad_premasked=False):
         """groups: number of independent calls batched along dim 0 (each gets its own spectral-norm iteration);
-        out_dtype: storage type of a channel-last output (default: that of a channel-last input, else ops.act_dtype())"""
+        out_dtype: storage type of a channel-last output (default: that of a channel-last input, else ops.act_dtype());
+        relu + grad_premasked on a producer and mask_input_grad on its ONLY consumer fuse the ReLU backward into the
+        consumer's data-gradient GEMM (see ops._ConvFn)"""
         return ops.conv2d(x, _weight(self), self.bias, self._geom, self._packs, x_layout, out_layout, relu,
-                          _sn_call(self, groups), out_dtype)
+                          _sn_call(self, groups), out_dtype, mask_input_grad, grad_premasked)
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):

@@ -307,8 +307,9 @@ def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bi
     return y
 
 
-def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layout, scale=None, out_dtype=None):
-    """dX = conv^T(dY, W)  (also the forward of nn.ConvTranspose2d)"""
+def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layout, scale=None, out_dtype=None, mask=None):
+    """dX = conv^T(dY, W)  (also the forward of nn.ConvTranspose2d).  mask: the layer input X when X is a ReLU output whose
+    producer expects the masked gradient — dX is zeroed where X <= 0 (in the GEMM epilogue on the tcgen05 path)"""
     N, Hy, Wy, Cy, ds = _dims(dy, dy_layout)
     assert Cy == g.Cy, (Cy, g.Cy)
     Hx, Wx = x_hw
@@ -333,7 +334,9 @@ def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layo
                      in_sn=ds[0], in_sh=ds[1], in_sw=ds[2], in_sc=ds[3], out_sy=g.s, out_sx=g.s, out_oy=py, out_ox=px,
                      Ho=Hx, Wo=Wx, out_sn=xs[0], out_sh=xs[1], out_sw=xs[2], out_sc=xs[3], ldw=ldw, relu=0,
                      scale_rows=_scale_rows(scale, N * Qh * Qw))
-        _lib.K.conv_gemm(d, dy, wmat, None, scale, dx, tc)
+        _lib.K.conv_gemm(d, dy, wmat, None, scale, dx, tc, mask if (tc and mask is not None and mask.dtype == dx.dtype) else None)
+    if mask is not None and not (tc and mask.dtype == dx.dtype):
+        dx = _lib.K.relu_bwd(dx, mask.to(dx.dtype) if mask.dtype != dx.dtype else mask)
     return dx
 
 
@@ -506,7 +509,11 @@ class SNPlan:
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, sn: Optional[SNCall], g: ConvGeom, packs: WeightPacks, transposed: bool, x_layout: str,
-                out_layout: str, relu: bool, out_hw, out_dtype):
+                out_layout: str, relu: bool, out_hw, out_dtype, mask_input_grad: bool = False, grad_premasked: bool = False):
+        # mask_input_grad: x is the ReLU output of a producer that set grad_premasked — this layer's data gradient is
+        # returned already multiplied by (x > 0); grad_premasked: the incoming gradient of a fused-ReLU layer is already
+        # masked by its (single) consumer, so the separate relu_bwd pass is skipped
+        ctx.mask_input_grad, ctx.grad_premasked = bool(mask_input_grad), bool(grad_premasked)
         scale = sn.inv if sn is not None else None
         ctx.x_dtype = x.dtype
         ctx.sn = sn
@@ -541,7 +548,7 @@ class _ConvFn(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         g, packs, sn = ctx.g, ctx.packs, ctx.sn
         dy = dy.contiguous()
-        if ctx.relu:
+        if ctx.relu and not ctx.grad_premasked:
             dy = _lib.K.relu_bwd(dy, y)
         scale = sn.inv if sn is not None else None
         dx = dw = db = None
@@ -556,13 +563,14 @@ class _ConvFn(torch.autograd.Function):
                                               ctx.x_dtype)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = bias_grad(dy, ctx.out_layout)
-            return dx, dw, db, None, None, None, None, None, None, None, None, None
+            return dx, dw, db, None, None, None, None, None, None, None, None, None, None, None
         dyb = as_bf16(dy) if ((need_dx and dgrad_tc) or (need_dw and (wgrad_tc or packed))) else None   # one cast for both GEMMs
         if need_dx:
             dy_op = dyb if dgrad_tc else dy
             if not ctx.transposed:
                 _, Hx, Wx, _ = ctx.x_dims
-                dx = conv_dgrad(g, packs, w, dy_op, ctx.out_layout, (Hx, Wx), ctx.x_layout, scale, ctx.x_dtype)
+                dx = conv_dgrad(g, packs, w, dy_op, ctx.out_layout, (Hx, Wx), ctx.x_layout, scale, ctx.x_dtype,
+                                mask=x if (ctx.mask_input_grad and not ctx.packed) else None)
             else:
                 dx = conv_forward(g, packs, w, dy_op, ctx.out_layout, ctx.x_layout, None, scale, False, ctx.x_dtype)
         if need_dw:
@@ -602,12 +610,13 @@ class _ConvFn(torch.autograd.Function):
                     _lib.K.sn_grad(gw, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = bias_grad(dy, ctx.out_layout)
-        return dx, dw, db, None, None, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None, None, None, None
 
 
 def conv2d(x, w, bias, g: ConvGeom, packs: WeightPacks, x_layout="cl", out_layout="cl", relu=False,
-           sn: Optional[SNCall] = None, out_dtype=None):
-    return _ConvFn.apply(x, w, bias, sn, g, packs, False, x_layout, out_layout, relu, None, out_dtype)
+           sn: Optional[SNCall] = None, out_dtype=None, mask_input_grad=False, grad_premasked=False):
+    return _ConvFn.apply(x, w, bias, sn, g, packs, False, x_layout, out_layout, relu, None, out_dtype, mask_input_grad,
+                         grad_premasked)
 
 
 def conv_transpose2d(x, w, g: ConvGeom, packs: WeightPacks, out_hw, x_layout="cl", out_layout="cl"):

@@ -351,6 +351,7 @@ static void launch_conv_f32(const b200_conv_desc* d, const void* in, const float
 
 extern "C" int b200_conv_gemm_f32(const b200_conv_desc* d, const void* in, int in_dt, const float* wmat,
                                   const float* bias, const float* scale, void* out, int out_dt, b200_stream_t stream) {
+    B200_REQUIRE(d->relu_mask == nullptr, "conv_gemm_f32: relu_mask is a tcgen05-path epilogue");
     int64_t M = (int64_t)d->B * d->Qh * d->Qw;
     if (M == 0 || d->Cout == 0) return 0;
     B200_REQUIRE(d->Cin > 0 && d->Th > 0 && d->Tw > 0, "conv_gemm_f32: bad descriptor");

@@ -164,6 +164,37 @@ __device__ __forceinline__ void st_bf16x8(void* p, const float* o) {
     *reinterpret_cast<uint4*>(p) = u;
 }
 
+// fused ReLU backward of the layer input: zero the 16 outputs whose mask value (same address as the output) is not > 0
+__device__ __forceinline__ void relu_mask16(float (&o)[16], const void* mask, int64_t off, int out_bf16) {
+    if (out_bf16) {
+        const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(mask) + off);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint4 q = p[h];
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!(__uint_as_float(w[i] << 16) > 0.f)) o[h * 8 + 2 * i] = 0.f;
+                if (!(__uint_as_float(w[i] & 0xFFFF0000u) > 0.f)) o[h * 8 + 2 * i + 1] = 0.f;
+            }
+        }
+    } else {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(mask) + off);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float4 q = p[h];
+            if (!(q.x > 0.f)) o[h * 4] = 0.f;
+            if (!(q.y > 0.f)) o[h * 4 + 1] = 0.f;
+            if (!(q.z > 0.f)) o[h * 4 + 2] = 0.f;
+            if (!(q.w > 0.f)) o[h * 4 + 3] = 0.f;
+        }
+    }
+}
+__device__ __forceinline__ bool relu_mask1(const void* mask, int64_t off, int out_bf16) {
+    return out_bf16 ? (__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(mask)[off]) > 0.f)
+                    : (reinterpret_cast<const float*>(mask)[off] > 0.f);
+}
+
 template <int BN, int STAGES, bool ATMA>
 __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                            const __grid_constant__ CUtensorMap tmap_a, b200_conv_desc d,
@@ -314,6 +345,7 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
                         o[e] = d.relu ? fmaxf(val, 0.f) : val;
                     }
                     if (vec && n0 + cb + 16 <= d.Cout) {
+                        if (d.relu_mask) relu_mask16(o, d.relu_mask, ro + n0 + cb, out_bf16);
                         if (out_bf16) {
                             st_bf16x8(outh + ro + n0 + cb, o);
                             st_bf16x8(outh + ro + n0 + cb + 8, o + 8);
@@ -329,8 +361,10 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
                         for (int e = 0; e < 16; ++e) {
                             int co = n0 + cb + e;
                             if (co < d.Cout) {
-                                if (out_bf16) outh[ro + (int64_t)co * d.out_sc] = __float2bfloat16_rn(o[e]);
-                                else out[ro + (int64_t)co * d.out_sc] = o[e];
+                                const int64_t oo = ro + (int64_t)co * d.out_sc;
+                                const float val = (d.relu_mask && !relu_mask1(d.relu_mask, oo, out_bf16)) ? 0.f : o[e];
+                                if (out_bf16) outh[oo] = __float2bfloat16_rn(val);
+                                else out[oo] = val;
                             }
                         }
                     }
@@ -522,6 +556,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_tc_persist_kernel(const __gr
                         }
                         const int c0 = n0 + cb + h;
                         if (vec && c0 + 16 <= d.Cout) {
+                            if (d.relu_mask) relu_mask16(o, d.relu_mask, ro + c0, out_bf16);
                             if (out_bf16) {
                                 st_bf16x8(outh + ro + c0, o);
                                 st_bf16x8(outh + ro + c0 + 8, o + 8);
@@ -537,8 +572,10 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_tc_persist_kernel(const __gr
                             for (int e = 0; e < 16; ++e) {
                                 const int co = c0 + e;
                                 if (co < d.Cout) {
-                                    if (out_bf16) outh[ro + (int64_t)co * d.out_sc] = __float2bfloat16_rn(o[e]);
-                                    else out[ro + (int64_t)co * d.out_sc] = o[e];
+                                    const int64_t oo = ro + (int64_t)co * d.out_sc;
+                                    const float val = (d.relu_mask && !relu_mask1(d.relu_mask, oo, out_bf16)) ? 0.f : o[e];
+                                    if (out_bf16) outh[oo] = __float2bfloat16_rn(val);
+                                    else out[oo] = val;
                                 }
                             }
                         }
@@ -776,6 +813,7 @@ __global__ void __launch_bounds__(192, 1) conv_halo_tc_kernel(const __grid_const
                         }
                         const int c0 = n0 + cb + h;
                         if (vec && c0 + 16 <= d.Cout) {
+                            if (d.relu_mask) relu_mask16(o, d.relu_mask, ro + c0, out_bf16);
                             if (out_bf16) {
                                 st_bf16x8(outh + ro + c0, o);
                                 st_bf16x8(outh + ro + c0 + 8, o + 8);
@@ -791,8 +829,10 @@ __global__ void __launch_bounds__(192, 1) conv_halo_tc_kernel(const __grid_const
                             for (int e = 0; e < 16; ++e) {
                                 const int co = c0 + e;
                                 if (co < d.Cout) {
-                                    if (out_bf16) outh[ro + (int64_t)co * d.out_sc] = __float2bfloat16_rn(o[e]);
-                                    else out[ro + (int64_t)co * d.out_sc] = o[e];
+                                    const int64_t oo = ro + (int64_t)co * d.out_sc;
+                                    const float val = (d.relu_mask && !relu_mask1(d.relu_mask, oo, out_bf16)) ? 0.f : o[e];
+                                    if (out_bf16) outh[oo] = __float2bfloat16_rn(val);
+                                    else out[oo] = val;
                                 }
                             }
                         }
@@ -941,8 +981,10 @@ __global__ void conv_splitk_reduce_kernel(b200_conv_desc d, const float* __restr
             if (co + e >= d.Cout) break;
             float v = o[e] * alpha + (bias ? bias[co + e] : 0.f);
             if (d.relu) v = fmaxf(v, 0.f);
-            if (out_bf16) outh[ro + (int64_t)(co + e) * d.out_sc] = __float2bfloat16_rn(v);
-            else out[ro + (int64_t)(co + e) * d.out_sc] = v;
+            const int64_t oo = ro + (int64_t)(co + e) * d.out_sc;
+            if (d.relu_mask && !relu_mask1(d.relu_mask, oo, out_bf16)) v = 0.f;
+            if (out_bf16) outh[oo] = __float2bfloat16_rn(v);
+            else out[oo] = v;
         }
     }
 }
@@ -1628,6 +1670,7 @@ extern "C" int b200_conv_gemm_tc(const b200_conv_desc* d, const void* in_bf16, c
     B200_REQUIRE(d->ldw % 64 == 0 && d->ldw >= (int64_t)d->Th * d->Tw * d->Cin, "conv_gemm_tc: bad ldw");
     B200_REQUIRE((reinterpret_cast<uintptr_t>(wmat_bf16) & 15) == 0, "conv_gemm_tc: wmat must be 16-byte aligned");
     B200_REQUIRE(splits >= 1 && (splits == 1 || split_ws != nullptr), "conv_gemm_tc: split-K needs a workspace");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(d->relu_mask) & 15) == 0, "conv_gemm_tc: relu_mask must be 16-byte aligned");
     B200_REQUIRE(splits == 1 || (reinterpret_cast<uintptr_t>(split_ws) & 15) == 0, "conv_gemm_tc: unaligned workspace");
     cudaStream_t st = as_stream(stream);
     const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(in_bf16);

@@ -29,8 +29,8 @@ class OptimizedBlock(nn.Module):
     def forward(self, x, groups=1, out_relu=False):
         """out_relu: return relu(block output) — every consumer of a discriminator block applies ReLU first (the next
         ResidualBlock's in-place ReLU, or the trunk's final one), so the trunk asks for the activated tensor directly"""
-        h = self.resi[0](x, x_layout="nchw", relu=True, groups=groups)
-        h = self.resi[2](h, groups=groups)
+        h = self.resi[0](x, x_layout="nchw", relu=True, groups=groups, grad_premasked=True)
+        h = self.resi[2](h, groups=groups, mask_input_grad=True)      # the only consumer of the ReLU output above
         s = x
         if self.downsample:
             h = ops.avg_pool2(h)
@@ -58,8 +58,8 @@ class ResidualBlock(nn.Module):
     def forward(self, x, groups=1, in_relu=False, out_relu=False):
         """in_relu: x already is relu(previous block output); out_relu: return relu(block output) (see OptimizedBlock)"""
         r = x if in_relu else ops.relu(x)
-        h = self.resi[1](r, relu=True, groups=groups)
-        h = self.resi[3](h, groups=groups)
+        h = self.resi[1](r, relu=True, groups=groups, grad_premasked=True)
+        h = self.resi[3](h, groups=groups, mask_input_grad=True)      # the only consumer of the ReLU output above
         s = self.sc(r, groups=groups) if self.learnable_sc else r
         if self.downsample:
             return ops.avg_pool2_sum(h, s, relu=out_relu)

@@ -96,6 +96,9 @@ typedef struct {
     int64_t ldw;                   /* row stride (elements) of wmat */
     int relu;
     int scale_rows;                /* 0: one scalar *scale; > 0: scale[m / scale_rows] (per-group 1/sigma of batched calls) */
+    const void* relu_mask;         /* tcgen05 path only, may be NULL: tensor with out's type and strides; outputs are zeroed
+                                      where it is not > 0 — the ReLU backward of a layer whose INPUT is a ReLU output, fused
+                                      into that layer's data-gradient GEMM (out = dX, relu_mask = X) */
 } b200_conv_desc;
 
 /* fp32 CUDA-core path (bit-tight parity mode; also the 3-channel layers and Linear heads). wmat fp32 [Cout][ldw];

@@ -150,8 +150,9 @@ class EmulKernels:
         self.launches += 1
         return x2d.double().sum(1).float()
 
-    def conv_gemm(self, d, inp, wmat, bias, scale, out, tc):
+    def conv_gemm(self, d, inp, wmat, bias, scale, out, tc, mask=None):
         self.launches += 1
+        assert mask is None or (tc and mask.shape == out.shape and mask.dtype == out.dtype)
         assert inp.dtype == torch.bfloat16 or not tc, "the tcgen05 path takes bf16 operands"
         A = self._gather(d, inp).float()
         K = d.Th * d.Tw * d.Cin
@@ -175,7 +176,11 @@ class EmulKernels:
                                 out.storage_offset())
         co = torch.arange(d.Cout) * d.out_sc
         idx = (off[ok][:, None] + co[None]).reshape(-1)
-        flat[idx] = y[ok].reshape(-1).to(out.dtype)
+        vals = y[ok].reshape(-1)
+        if mask is not None:
+            mflat = torch.as_strided(mask, flat.shape, (1,), mask.storage_offset())
+            vals = torch.where(mflat[idx].float() > 0, vals, torch.zeros(()))
+        flat[idx] = vals.to(out.dtype)
 
     def wgrad_gemm(self, d, P, G, ws, splits, tc):
         self.launches += 1
