@@ -465,7 +465,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 2) conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(192, 3) conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                       const __grid_constant__ CUtensorMap tmap_a,
                                                                       b200_conv_desc d, const float* __restrict__ bias,
                                                                       const float* __restrict__ scale,
@@ -1462,7 +1462,10 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
         B200_REQUIRE(tiles < (1ll << 31), "conv_gemm_tc: too many tiles");
         const bool two = g_use_persist == 2 || (g_use_persist == 3 && num_kb <= g_two_cta_max_kb);
         if (two) {
-            constexpr int PSTAGES = BN == 128 ? 3 : 4;
+            // BN = 128: two CTAs per SM (3 x 32 KB stages each); BN <= 64: three CTAs per SM (3 x 24 KB stages each) — the
+            // short-K, epilogue-heavy launches gain from a third epilogue warp set
+            constexpr int PSTAGES = 3;
+            constexpr int PER_SM = BN == 128 ? 2 : 3;
             constexpr int psmem = 1024 + PSTAGES * (A_BYTES + BN * BK * 2) + (int)sizeof(PersistTail);
             static bool pconfigured = false;
             if (!pconfigured) {
@@ -1471,7 +1474,7 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
                 B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute(persist): %s", cudaGetErrorString(e));
                 pconfigured = true;
             }
-            const int grid_p = (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+            const int grid_p = (int)(tiles < PER_SM * kNumSMs ? tiles : PER_SM * kNumSMs);
             conv_gemm_tc_persist_kernel<BN, PSTAGES><<<grid_p, 192, psmem, st>>>(tmap, tmap_a, *d, bias, scale, out,
                                                                                out_bf16, ntiles, (int)tiles);
         } else {
