@@ -373,8 +373,10 @@ def kernel_roofline(ts, b, args):
         return 2.0 * d.B * d.Qh * d.Qw * d.Cout * d.Th * d.Tw * d.Cin
 
     def timed(fn, wgrad):
+        tc_pos = 4 if wgrad else 5          # wgrad_gemm(desc, P, G, ws, splits, tc) / conv_gemm(desc, inp, wmat, bias, scale, out, tc, mask)
+
         def wrapper(desc, *a, **kw):
-            tc = bool(a[-1] if "tc" not in kw else kw["tc"])
+            tc = bool(kw["tc"] if "tc" in kw else a[tc_pos])
             fn(desc, *a, **kw)                                   # the step's own launch
             key = (wgrad, tc, bytes(desc)) + tuple(int(x) for x in a if isinstance(x, int))
             if key not in per_key:
