@@ -1,18 +1,22 @@
 // conv_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM convolutions for sm_100a (K1/K2 forward-type, K3 weight gradient).
 //
-// Forward-type kernel (conv fwd, dgrad, ConvTranspose phases): one CTA computes a 128 x BN output tile.
-//   warps 0-3 : A producers — gather the im2col rows of the tile straight from the channel-last bf16 activation with
-//               16-byte cp.async (LDGSTS, zero fill for padding / tile tails) into the canonical K-major
-//               SWIZZLE_128B layout; completion is signalled on the stage's mbarrier by
-//               cp.async.mbarrier.arrive.noinc, so STAGES k-blocks are in flight per CTA and no register staging
-//               exists; afterwards the same warps run the epilogue (tcgen05.ld from TMEM, scale / bias / ReLU,
-//               strided fp32 or bf16 store, or raw fp32 partials when the K range is split over gridDim.z).
-//   warp 4    : B producer — TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) loads of the packed bf16 weight matrix.
-//   warp 5    : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM).
-//   smem ring : STAGES x (A 128x64 bf16 = 16 KB, B BNx64 bf16), mbarrier full/empty pairs, tcgen05.commit releases.
+// Forward-type GEMMs (conv fwd, dgrad, ConvTranspose phases, 1x1 GEMMs over im2col-packed matrices): a 128 x BN output
+// tile per accumulator, operands in the canonical K-major SWIZZLE_128B layout, bf16 x bf16 -> fp32 in TMEM.
+//   conv_gemm_tc_persist_kernel (default): persistent CTAs (2 per SM at BN = 128, 3 at BN = 64) walk the tiles; warp 4
+//       issues one TMA im2col load (A: 128 pixels x 64 channels of one tap) and one tiled TMA load (B: BN x 64 weights) per
+//       k-block into a 3-stage ring that runs ahead across tiles; warp 5 issues the tcgen05.mma instructions into one of
+//       two TMEM accumulators; warps 0-3 run the epilogue (tcgen05.ld, 1/sigma scale, bias, ReLU, optional ReLU mask of
+//       the layer input, strided stores) of tile j while tile j+1 is being accumulated.
+//   conv_gemm_tc_kernel: one tile per CTA; split-K launches (fp32 partials + conv_splitk_reduce_kernel) and gathers the
+//       im2col tensor map cannot express (fused nearest upsampling: warps 0-3 gather with 16-byte cp.async instead).
+//   conv_halo_tc_kernel: shifted-window experiment (one zero-padded slab per tile, taps as row-shifted descriptors);
+//       correct but slower, disabled by default.
+// The TMA / MMA issuing roles run warp-uniform code with one elected lane issuing (descriptors stay in uniform registers);
+// every mbarrier wait is bounded.
 // Weight-gradient kernel: R[m, c] = sum_pixels P[pix, m] * G[pix, c]; both operands are pixel-major tiles
-//   (64 pixels x 128 B of channels) = the canonical MN-major SWIZZLE_128B layout, so the same producer code feeds
-//   them; split over the pixel range with fp32 partials reduced by b200_wgrad_reduce (deterministic).
+//   (64 pixels x 128 B of channels) = the canonical MN-major SWIZZLE_128B layout, loaded by two TMA im2col maps (or
+//   cp.async gathers); split over the pixel range with fp32 partials reduced by b200_wgrad_reduce / b200_sn_wgrad_finish
+//   (deterministic).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
