@@ -189,6 +189,15 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU for --impl b200 (there is no CPU fallback)"
+    import __graft_entry__ as ge
+    if not os.path.exists(ge.LIB):          # the in-tree library did not travel: local rank 0 builds it, the others wait
+        if local == 0:
+            ge.build()
+        else:
+            t_wait = time.time()
+            while not os.path.exists(ge.LIB) and time.time() - t_wait < 600:
+                time.sleep(2.0)
+            time.sleep(2.0)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

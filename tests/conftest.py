@@ -12,6 +12,16 @@ for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # on a GPU box the CUDA library must exist before the first kernel call (the product has no fallback): build it if
+    # the in-tree .so did not travel with the sources
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import __graft_entry__ as ge
+            if not os.path.exists(ge.LIB):
+                ge.build()
+    except Exception as e:          # the tests themselves will report a missing library loudly
+        print("conftest: could not build libb200gan.so: %s" % e, file=sys.stderr)
 
 
 @pytest.fixture
