@@ -91,3 +91,13 @@ def test_step_wiring_bf16_operand_routing(emul):
         assert rel(res["out_g"][i], ref["out_g"][i]) < 6e-2
     assert abs(float(res["d_loss"]) - float(ref["d_loss"])) < 5e-2 * abs(float(ref["d_loss"]))
     assert abs(float(res["g_loss"]) - float(ref["g_loss"])) < 5e-2 * abs(float(ref["g_loss"]))
+    # gradients through the bf16-mode host paths (im2col-packed 3-channel layers, grouped spectral-norm weight gradient,
+    # fused ReLU masks): discriminators tight, generator within the stated bf16 bound (chaotic at the 1e-3 level, F12)
+    cos = torch.nn.functional.cosine_similarity
+    for name, net in (("D_img", ts.netD_image), ("D_obj", ts.netD_object), ("D_att", ts.netD_att)):
+        a = torch.cat([p.grad.reshape(-1) for _, p in net.named_parameters()]).double()
+        r = torch.cat([ref["d_grads"][name][k].reshape(-1) for k, _ in net.named_parameters()]).double()
+        assert float(cos(a, r, dim=0)) > 0.995, name
+    a = torch.cat([p.grad.reshape(-1) for _, p in ts.netG.named_parameters()]).double()
+    r = torch.cat([ref["g_grads"][k].reshape(-1) for k, _ in ts.netG.named_parameters()]).double()
+    assert float(cos(a, r, dim=0)) > 0.85
