@@ -444,16 +444,47 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ seg, int nse
     }
 }
 
-// CBN embedding gradient: dtable[k][c] = sum_{o: idx[o]==k} sum(dyr*xhat); dtable[k][C+c] = sum_{o} sum(dyr)
-__global__ void cbn_dtable_kernel(const double* __restrict__ seg, int nseg, int C, const int32_t* __restrict__ idx,
-                                  int num_classes, float* __restrict__ dtable) {
-    int64_t total = (int64_t)num_classes * C;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(t % C);
-        int k = (int)(t / C);
+// CBN embedding gradient: dtable[k][c] = sum_{o: idx[o]==k} sum(dyr*xhat); dtable[k][C+c] = sum_{o} sum(dyr).
+// One block per class k: warp 0 compacts the segments of that class into shared memory in ascending order (ballot
+// prefix), then the threads walk that short list per channel — the summation order of the plain scan, without every
+// (class, channel) thread scanning all segments.
+constexpr int kCbnListMax = 2048;
+__global__ void __launch_bounds__(256) cbn_dtable_kernel(const double* __restrict__ seg, int nseg, int C,
+                                                        const int32_t* __restrict__ idx, int num_classes,
+                                                        float* __restrict__ dtable) {
+    __shared__ int list[kCbnListMax];
+    __shared__ int cnt;
+    const int k = blockIdx.x;
+    (void)num_classes;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int n = 0;
+        for (int base = 0; base < nseg; base += 32) {
+            const int o = base + lane;
+            const bool m = o < nseg && idx[o] == k;
+            const unsigned bal = __ballot_sync(0xffffffffu, m);
+            if (m) {
+                const int pos = n + __popc(bal & ((1u << lane) - 1u));
+                if (pos < kCbnListMax) list[pos] = o;
+            }
+            n += __popc(bal);
+        }
+        if (lane == 0) cnt = n;
+    }
+    __syncthreads();
+    const int n = cnt;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         double a = 0.0, b = 0.0;
-        for (int o = 0; o < nseg; ++o)
-            if (idx[o] == k) { a += seg[((int64_t)o * C + c) * 2 + 1]; b += seg[((int64_t)o * C + c) * 2]; }
+        if (n <= kCbnListMax) {
+            for (int i = 0; i < n; ++i) {
+                const int o = list[i];
+                a += seg[((int64_t)o * C + c) * 2 + 1];
+                b += seg[((int64_t)o * C + c) * 2];
+            }
+        } else {                                  // more matches than the list holds: plain ordered scan
+            for (int o = 0; o < nseg; ++o)
+                if (idx[o] == k) { a += seg[((int64_t)o * C + c) * 2 + 1]; b += seg[((int64_t)o * C + c) * 2]; }
+        }
         dtable[(int64_t)k * 2 * C + c] = (float)a;
         dtable[(int64_t)k * 2 * C + C + c] = (float)b;
     }
@@ -737,7 +768,7 @@ extern "C" int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, i
     norm_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(seg_sums, nseg, C, mode, gamma, idx, s, dgamma, dbeta, groups);
     B200_CHECK_LAUNCH();
     if (mode == B200_NORM_CBN && dtable) {
-        cbn_dtable_kernel<<<grid_for((int64_t)num_classes * C, 128), 128, 0, st>>>(seg_sums, nseg, C, idx, num_classes, dtable);
+        cbn_dtable_kernel<<<num_classes, 256, 0, st>>>(seg_sums, nseg, C, idx, num_classes, dtable);
         B200_CHECK_LAUNCH();
     }
     return 0;
