@@ -400,35 +400,42 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_vec_kernel(const T* __res
 
 // stage 2: s[g][c] = (sum dxhat, sum dxhat*xhat) per group; parameter gradients summed over the groups.
 // One warp per channel, fixed-order shuffle tree.
-__global__ void norm_bwd_finalize_kernel(const double* __restrict__ seg, int nseg, int C, int mode,
-                                         const float* __restrict__ gamma, const int32_t* __restrict__ idx, float* s,
-                                         float* dgamma, float* dbeta, int groups) {
-    int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= C) return;
-    int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(128) norm_bwd_finalize_kernel(const double* __restrict__ seg, int nseg, int C, int mode,
+                                                               const float* __restrict__ gamma,
+                                                               const int32_t* __restrict__ idx, float* s, float* dgamma,
+                                                               float* dbeta, int groups) {
+    // one block (128 threads) per channel: the segments of a group are strided over the threads (independent loads), then a
+    // fixed-order tree (warp shuffles, 4 warps through shared memory)
+    __shared__ double red[4][2];
+    const int c = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int spg = nseg / groups;
     double t1 = 0.0, t2 = 0.0;
     for (int g = 0; g < groups; ++g) {
         double s1 = 0.0, s2 = 0.0;
         if (mode == B200_NORM_CBN) {
-#pragma unroll 4
-            for (int k = g * spg + lane; k < (g + 1) * spg; k += 32) {
+#pragma unroll 2
+            for (int k = g * spg + threadIdx.x; k < (g + 1) * spg; k += 128) {
                 double w = (double)gamma[(int64_t)idx[k] * 2 * C + c];
                 s1 += w * seg[((int64_t)k * C + c) * 2];
                 s2 += w * seg[((int64_t)k * C + c) * 2 + 1];
             }
         } else {
-#pragma unroll 4
-            for (int k = g * spg + lane; k < (g + 1) * spg; k += 32) {
+#pragma unroll 2
+            for (int k = g * spg + threadIdx.x; k < (g + 1) * spg; k += 128) {
                 s1 += seg[((int64_t)k * C + c) * 2];
                 s2 += seg[((int64_t)k * C + c) * 2 + 1];
             }
         }
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
-        t1 += s1;
-        t2 += s2;
-        if (lane == 0) {
+        if (lane == 0) { red[warp][0] = s1; red[warp][1] = s2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s1 = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
+            s2 = (red[0][1] + red[1][1]) + (red[2][1] + red[3][1]);
+            t1 += s1;
+            t2 += s2;
             if (mode == B200_NORM_AFFINE) {
                 double w = (double)gamma[c];
                 s1 *= w;
@@ -437,8 +444,9 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ seg, int nse
             s[((int64_t)g * C + c) * 2] = (float)s1;
             s[((int64_t)g * C + c) * 2 + 1] = (float)s2;
         }
+        __syncthreads();
     }
-    if (lane == 0 && mode == B200_NORM_AFFINE) {
+    if (threadIdx.x == 0 && mode == B200_NORM_AFFINE) {
         if (dbeta) dbeta[c] = (float)t1;
         if (dgamma) dgamma[c] = (float)t2;
     }
@@ -765,7 +773,7 @@ extern "C" int b200_norm_bwd_finalize(const double* seg_sums, int nseg, int C, i
                                       float* dtable, b200_stream_t stream) {
     cudaStream_t st = as_stream(stream);
     B200_REQUIRE(groups >= 1 && nseg % groups == 0, "norm_bwd_finalize: nseg %% groups != 0");
-    norm_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(seg_sums, nseg, C, mode, gamma, idx, s, dgamma, dbeta, groups);
+    norm_bwd_finalize_kernel<<<C, 128, 0, st>>>(seg_sums, nseg, C, mode, gamma, idx, s, dgamma, dbeta, groups);
     B200_CHECK_LAUNCH();
     if (mode == B200_NORM_CBN && dtable) {
         cbn_dtable_kernel<<<num_classes, 256, 0, st>>>(seg_sums, nseg, C, idx, num_classes, dtable);
