@@ -46,6 +46,17 @@ class SNLayer(C.Structure):
                 ("u_hist", C.c_void_p), ("v_hist", C.c_void_p), ("h", C.c_int), ("w", C.c_int)]
 
 
+PACK_CHUNK = 8192
+
+
+class PackEntry(C.Structure):
+    """Mirror of b200_pack_entry (include/b200gan.h)."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("ldw", C.c_int64), ("s_m", C.c_int64), ("s_ky", C.c_int64),
+                ("s_kx", C.c_int64), ("s_c", C.c_int64), ("dst_bf16", C.c_int32), ("M", C.c_int32), ("Th", C.c_int32),
+                ("Tw", C.c_int32), ("C", C.c_int32), ("C_dst", C.c_int32), ("c_off", C.c_int32), ("ky0", C.c_int32),
+                ("kx0", C.c_int32), ("kstep", C.c_int32), ("chunk_begin", C.c_int32), ("pad", C.c_int32)]
+
+
 class B200Error(RuntimeError):
     pass
 
@@ -251,7 +262,7 @@ class Kernels:
                     "b200_wgrad_reduce")
 
     def pack_weight(self, src, src_offset, dst, dst_row_offset, bf16, M, Mpad, Th, Tw, Cc, ldw, s_m, s_ky, s_kx, s_c,
-                    ky0=0, kx0=0, kstep=1):
+                    ky0=0, kx0=0, kstep=1, C_dst=0, c_off=0):
         esz = 2 if bf16 else 4
         sptr = C.c_void_p(src.data_ptr() + 4 * int(src_offset))
         dptr = C.c_void_p(dst.data_ptr() + esz * int(dst_row_offset) * int(ldw))
@@ -259,8 +270,32 @@ class Kernels:
             raise B200Error("pack_weight: CUDA tensors required")
         self._check(self.lib.b200_pack_weight(sptr, dptr, int(bool(bf16)), int(M), int(Mpad), int(Th), int(Tw), int(Cc),
                                               C.c_int64(ldw), C.c_int64(s_m), C.c_int64(s_ky), C.c_int64(s_kx),
-                                              C.c_int64(s_c), int(ky0), int(kx0), int(kstep), _stream()),
-                    "b200_pack_weight")
+                                              C.c_int64(s_c), int(ky0), int(kx0), int(kstep), int(C_dst), int(c_off),
+                                              _stream()), "b200_pack_weight")
+
+    def pack_table(self, recipes, device):
+        """(pinned host image, device copy, n_entries, total_chunks) of the b200_pack_entry table for `recipes` (objects
+        with the attributes of ops.PackRecipe); the copy is an asynchronous pinned copy (capturable)"""
+        arr = (PackEntry * len(recipes))()
+        chunks = 0
+        for i, r in enumerate(recipes):
+            esz = 2 if r.bf16 else 4
+            cd = r.C_dst if r.C_dst > 0 else r.C
+            arr[i] = PackEntry(r.src.data_ptr() + 4 * int(r.src_offset),
+                               r.dst.data_ptr() + esz * int(r.dst_row_offset) * int(r.ldw), r.ldw, r.s_m, r.s_ky, r.s_kx,
+                               r.s_c, int(bool(r.bf16)), r.M, r.Th, r.Tw, r.C, cd, r.c_off if r.C_dst > 0 else 0, r.ky0,
+                               r.kx0, r.kstep, chunks, 0)
+            chunks += -(-(r.M * r.Th * r.Tw * r.C) // PACK_CHUNK)
+        nbytes = C.sizeof(arr)
+        host = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
+        C.memmove(host.data_ptr(), C.addressof(arr), nbytes)
+        dev = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        dev.copy_(host, non_blocking=True)
+        return host, dev, len(recipes), chunks
+
+    def pack_weight_multi(self, table_dev, n_entries, total_chunks):
+        self._check(self.lib.b200_pack_weight_multi(_ptr(table_dev), int(n_entries), int(total_chunks), _stream()),
+                    "b200_pack_weight_multi")
 
     # ---- normalisation --------------------------------------------------------------------------------------
     def bn_chunks(self, rows, Cc):

@@ -19,6 +19,8 @@ def broadcast_module(module: torch.nn.Module, src: int = 0, group=None):
     """Make every rank start from rank `src`'s parameters and buffers."""
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+    from . import ops
+    ops.bump_weight_epoch()        # `.data` writes do not move tensor versions: invalidate the packed GEMM operands
 
 
 def shard_images(n_images: int, rank: int, world: int):

@@ -9,6 +9,7 @@ from __future__ import annotations
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import os
+import weakref
 
 import torch
 
@@ -102,23 +103,122 @@ class ConvGeom:
         return (self.Cx, self.Cy, self.kh, self.kw, self.s, self.p, self.cx_offset, self.cx_total)
 
 
-class WeightPacks:
-    """Packed GEMM operands of one parameter tensor, rebuilt when the parameter's version changes."""
+class PackRecipe:
+    """One b200_pack_weight call: how a GEMM operand matrix (or a row / channel slice of it) is produced from a parameter.
+    Kept with the cached matrix so that the whole set can be re-packed in place by ONE launch after an optimizer step
+    (refresh_packs -> b200_pack_weight_multi)."""
+    __slots__ = ("src", "src_offset", "dst", "dst_row_offset", "bf16", "M", "Mpad", "Th", "Tw", "C", "ldw", "s_m", "s_ky",
+                 "s_kx", "s_c", "ky0", "kx0", "kstep", "C_dst", "c_off")
 
-    def __init__(self, stamp_src=None):
-        self.store: Dict[tuple, tuple] = {}
-        # tensors whose (data_ptr, version) identify the weights when `w` is a per-call temporary (fused gamma|beta)
-        self.stamp_src = stamp_src
+    def __init__(self, src, src_offset, dst, dst_row_offset, bf16, M, Mpad, Th, Tw, C, ldw, s_m, s_ky, s_kx, s_c, ky0=0,
+                 kx0=0, kstep=1, C_dst=0, c_off=0):
+        (self.src, self.src_offset, self.dst, self.dst_row_offset, self.bf16, self.M, self.Mpad, self.Th, self.Tw, self.C,
+         self.ldw, self.s_m, self.s_ky, self.s_kx, self.s_c, self.ky0, self.kx0, self.kstep, self.C_dst, self.c_off) = (
+            src, src_offset, dst, dst_row_offset, bool(bf16), M, Mpad, Th, Tw, C, ldw, s_m, s_ky, s_kx, s_c, ky0, kx0,
+            kstep, C_dst, c_off)
+
+    def run(self):
+        _lib.K.pack_weight(self.src, self.src_offset, self.dst, self.dst_row_offset, self.bf16, self.M, self.Mpad, self.Th,
+                           self.Tw, self.C, self.ldw, self.s_m, self.s_ky, self.s_kx, self.s_c, self.ky0, self.kx0,
+                           self.kstep, self.C_dst, self.c_off)
+
+
+_PACK_REGISTRY = weakref.WeakSet()      # every live WeightPacks
+_PACK_GEN = 0                            # bumped whenever a cached operand is (re)built into a new buffer
+_REFRESH_TABLES: Dict[object, tuple] = {}
+
+
+class WeightPacks:
+    """Packed GEMM operands of one layer's weights.
+
+    Validity: an entry is rebuilt lazily when its source parameters' (data_ptr, _version) or the global epoch changed
+    (in-place autograd-visible updates: load_state_dict, foreach/single-tensor optimizers, init code), and ALL entries
+    derived from an optimizer's parameters are re-packed eagerly, in place, by one launch right after every
+    Optimizer.step() (refresh_packs, installed as a global optimizer post-step hook by the package) — which covers
+    updates that do not touch `_version` (b200gan.optim.Adam's raw-pointer kernel, torch's fused Adam, a CUDA-graph
+    replay containing the update).  Anything else that writes weights behind autograd's back (`.data`, raw pointers)
+    must call bump_weight_epoch()."""
+
+    def __init__(self, sources=None):
+        self.store: Dict[tuple, list] = {}
+        # parameters whose concatenation along dim 0 is the weight `w` handed to get() (SPADE's fused gamma|beta
+        # convolution): the operand is packed from them directly and `w` itself may be a per-call temporary
+        self.sources = tuple(sources) if sources is not None else None
+        _PACK_REGISTRY.add(self)
+
+    @staticmethod
+    def _stamp(src):
+        return tuple((t.data_ptr(), t._version) for t in src) + (_CACHE_EPOCH,)
 
     def get(self, key, w: torch.Tensor, builder):
-        src = self.stamp_src if self.stamp_src is not None else (w,)
-        stamp = tuple((t.data_ptr(), t._version) for t in src) + (_CACHE_EPOCH,)
+        """builder(sources, recipes) -> value; appends one PackRecipe per b200_pack_weight call it made"""
+        global _PACK_GEN
+        src = self.sources if self.sources is not None else (w,)
+        stamp = self._stamp(src)
         hit = self.store.get(key)
         if hit is not None and hit[0] == stamp:
             return hit[1]
-        val = builder()
-        self.store[key] = (stamp, val)
+        if hit is not None and all(a[0] == b[0] for a, b in zip(hit[0][:-1], stamp[:-1])) and len(hit[3]) == len(src):
+            for r in hit[2]:                       # same parameter storage, new values: re-pack in place
+                r.run()
+            hit[0] = stamp
+            return hit[1]
+        recipes: List[PackRecipe] = []
+        val = builder(src, recipes)
+        self.store[key] = [stamp, val, recipes, src]
+        _PACK_GEN += 1
         return val
+
+
+def _storage_ptr(t: torch.Tensor) -> int:
+    return t.untyped_storage().data_ptr()
+
+
+def refresh_packs(params=None, owner=None):
+    """Re-pack, in place and with ONE launch, every cached GEMM operand derived from `params` (all cached operands when
+    None) and mark them valid for the parameters' current versions.  Called after every optimizer step (see
+    WeightPacks); CUDA-graph capturable (the device table is cached per `owner` — the optimizer — and operand-set
+    generation, so no host-to-device copy happens in steady state)."""
+    ent = _REFRESH_TABLES.get(id(owner)) if owner is not None else None
+    if ent is None or ent[0] != _PACK_GEN or ent[3]() is not owner:
+        ptrs = None if params is None else {_storage_ptr(p) for p in params}
+        items = []
+        for wp in list(_PACK_REGISTRY):
+            for e in wp.store.values():
+                if ptrs is None or any(_storage_ptr(t) in ptrs for t in e[3]):
+                    items.append(e)
+        recipes = [r for e in items for r in e[2]]
+        table = _lib.K.pack_table(recipes, recipes[0].src.device) if recipes else None
+        ent = (_PACK_GEN, items, table, weakref.ref(owner) if owner is not None else None)
+        if owner is not None:
+            if len(_REFRESH_TABLES) > 64:
+                _REFRESH_TABLES.clear()
+            _REFRESH_TABLES[id(owner)] = ent
+    _, items, table, _ = ent
+    if table is None:
+        return 0
+    _host, dev, n, chunks = table
+    _lib.K.pack_weight_multi(dev, n, chunks)
+    for e in items:
+        e[0] = WeightPacks._stamp(e[3])
+    return n
+
+
+def _optimizer_post_step(optimizer, args, kwargs):
+    """global torch.optim post-step hook: the packed operands follow every parameter update (see WeightPacks)"""
+    if not any(len(wp.store) for wp in _PACK_REGISTRY):
+        return
+    refresh_packs([p for g in optimizer.param_groups for p in g["params"]], owner=optimizer)
+
+
+_HOOK_HANDLE = None
+
+
+def install_optimizer_hook():
+    global _HOOK_HANDLE
+    if _HOOK_HANDLE is None:
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+        _HOOK_HANDLE = register_optimizer_step_post_hook(_optimizer_post_step)
 
 
 def _tc_fwd_ok(g: ConvGeom, x_layout: str) -> bool:
@@ -133,14 +233,23 @@ def _tc_wgrad_ok(g: ConvGeom, x_layout: str, dy_layout: str) -> bool:
     return _PRECISION == "bf16" and x_layout == "cl" and dy_layout == "cl" and g.Cx % 64 == 0 and g.Cy % 64 == 0
 
 
-def _pack_fwd(g: ConvGeom, w: torch.Tensor, tc: bool):
-    """wmat[co][(ky*kw+kx)*Cx + c] = w[co, cx_offset+c, ky, kx]"""
+def _pack_fwd(g: ConvGeom, srcs, tc: bool, recipes: List[PackRecipe]):
+    """wmat[co][(ky*kw+kx)*Cx + c] = w[co, cx_offset+c, ky, kx]; w = srcs concatenated along dim 0"""
     K = g.kh * g.kw * g.Cx
     ldw = _rup(K, 64) if tc else _rup(K, 4)
     mpad = _rup(g.Cy, _lib.K.conv_tc_ntile(g.Cy)) if tc else g.Cy
-    dst = torch.empty((mpad, ldw), dtype=torch.bfloat16 if tc else torch.float32, device=w.device)
+    dst = torch.zeros((mpad, ldw), dtype=torch.bfloat16 if tc else torch.float32, device=srcs[0].device)
     kk = g.kh * g.kw
-    _lib.K.pack_weight(w, g.cx_offset * kk, dst, 0, tc, g.Cy, mpad, g.kh, g.kw, g.Cx, ldw, g.cx_total * kk, g.kw, 1, kk)
+    row = 0
+    for i, w in enumerate(srcs):
+        rows = w.shape[0]
+        last = i == len(srcs) - 1
+        r = PackRecipe(w, g.cx_offset * kk, dst, row, tc, rows, (mpad - row) if last else rows, g.kh, g.kw, g.Cx, ldw,
+                       g.cx_total * kk, g.kw, 1, kk)
+        r.run()
+        recipes.append(r)
+        row += rows
+    assert row == g.Cy, (row, g.Cy)
     return dst, ldw
 
 
@@ -155,8 +264,9 @@ def _dgrad_phases(g: ConvGeom):
     return out
 
 
-def _pack_dgrad(g: ConvGeom, w: torch.Tensor, tc: bool):
-    """per output phase: wmat[ci][(j*Tw+i)*Cy + co] = w[co, cx_offset+ci, ky0+s*j, kx0+s*i]"""
+def _pack_dgrad(g: ConvGeom, srcs, tc: bool, recipes: List[PackRecipe]):
+    """per output phase: wmat[ci][(j*Tw+i)*Cy + co] = w[co, cx_offset+ci, ky0+s*j, kx0+s*i]; w = srcs concatenated along
+    dim 0 (each source fills its own slice of the co axis)"""
     packs = []
     kk = g.kh * g.kw
     for (py, px, ky0, kx0, Th, Tw) in _dgrad_phases(g):
@@ -166,9 +276,17 @@ def _pack_dgrad(g: ConvGeom, w: torch.Tensor, tc: bool):
         K = Th * Tw * g.Cy
         ldw = _rup(K, 64) if tc else _rup(K, 4)
         mpad = _rup(g.Cx, _lib.K.conv_tc_ntile(g.Cx)) if tc else g.Cx
-        dst = torch.empty((mpad, ldw), dtype=torch.bfloat16 if tc else torch.float32, device=w.device)
-        _lib.K.pack_weight(w, g.cx_offset * kk, dst, 0, tc, g.Cx, mpad, Th, Tw, g.Cy, ldw, kk, g.kw, 1, g.cx_total * kk,
-                           ky0, kx0, g.s)
+        dst = torch.zeros((mpad, ldw), dtype=torch.bfloat16 if tc else torch.float32, device=srcs[0].device)
+        co = 0
+        for w in srcs:
+            rows = w.shape[0]
+            whole = len(srcs) == 1
+            r = PackRecipe(w, g.cx_offset * kk, dst, 0, tc, g.Cx, mpad, Th, Tw, rows, ldw, kk, g.kw, 1, g.cx_total * kk,
+                           ky0, kx0, g.s, 0 if whole else g.Cy, 0 if whole else co)
+            r.run()
+            recipes.append(r)
+            co += rows
+        assert co == g.Cy, (co, g.Cy)
         packs.append((dst, ldw))
     return packs
 
@@ -208,7 +326,7 @@ def conv_forward_packed(g: ConvGeom, packs: WeightPacks, w, P, N, Hy, Wy, out_la
                         out_dtype=torch.bfloat16):
     """Y = epilogue(P @ Wmat^T): the convolution as a 1x1 tcgen05 gather-GEMM over the im2col matrix P"""
     Kp = P.shape[1]
-    wmat, ldw = packs.get(("fwd", True) + g.key(), w, lambda: _pack_fwd(g, w, True))
+    wmat, ldw = packs.get(("fwd", True) + g.key(), w, lambda src, rec: _pack_fwd(g, src, True, rec))
     assert ldw == Kp
     y, ys = _empty(N, Hy, Wy, g.Cy, out_layout, P.device, out_dtype)
     xs = cl_strides(Hy, Wy, Kp)
@@ -261,7 +379,7 @@ def conv_backward_packed_out(g: ConvGeom, packs: WeightPacks, w, x, x_dims, dy, 
     ps = cl_strides(Hx, Wx, Kp)
     dx = dw = None
     if need_dx:
-        wmat, ldw = packs.get(("dgrad", True) + g.key(), w, lambda: _pack_dgrad(g, w, True))[0]
+        wmat, ldw = packs.get(("dgrad", True) + g.key(), w, lambda src, rec: _pack_dgrad(g, src, True, rec))[0]
         assert ldw == Kp
         dx, xs = _empty(N, Hx, Wx, Cx, "cl", dy.device, x_dtype)
         d = ConvDesc(B=N, Qh=Hx, Qw=Wx, Cin=Kp, Cout=Cx, Th=1, Tw=1, in_sy=1, in_sx=1, tap_sy=1, tap_sx=1, tap_oy=0,
@@ -297,7 +415,7 @@ def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bi
     odt = _out_dtype(x, x_layout, out_dtype)
     if tc:
         x = as_bf16(x)
-    wmat, ldw = packs.get(("fwd", tc) + g.key(), w, lambda: _pack_fwd(g, w, tc))
+    wmat, ldw = packs.get(("fwd", tc) + g.key(), w, lambda src, rec: _pack_fwd(g, src, tc, rec))
     y, ys = _empty(N, Hy, Wy, g.Cy, out_layout, x.device, odt)
     d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=g.Cx, Cout=g.Cy, Th=g.kh, Tw=g.kw, in_sy=g.s, in_sx=g.s, tap_sy=1, tap_sx=1,
                  tap_oy=-g.p, tap_ox=-g.p, Hi=Hx, Wi=Wx, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3],
@@ -317,7 +435,7 @@ def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layo
     odt = _out_dtype(dy, dy_layout, out_dtype)
     if tc:
         dy = as_bf16(dy)
-    phase_packs = packs.get(("dgrad", tc) + g.key(), w, lambda: _pack_dgrad(g, w, tc))
+    phase_packs = packs.get(("dgrad", tc) + g.key(), w, lambda src, rec: _pack_dgrad(g, src, tc, rec))
     phases = _dgrad_phases(g)
     dx, xs = _empty(N, Hx, Wx, g.Cx, out_layout, dy.device, odt)
     if any(p is None for p in phase_packs):

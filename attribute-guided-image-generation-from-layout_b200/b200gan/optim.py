@@ -3,7 +3,8 @@ train64.py:111-114 (lr, betas=(0.5, 0.999), eps=1e-8, no weight decay, no amsgra
 counter lives on the device, so the whole update is CUDA-graph capturable.
 
 The class keeps torch.optim.Optimizer's surface (param_groups, state[p] = {"step", "exp_avg", "exp_avg_sq"}, zero_grad,
-state_dict / load_state_dict), so utils/model_saver_iter.py style checkpointing works unchanged.  All parameters of one
+state_dict / load_state_dict — the latter rebuilds the device step counter and tables), so utils/model_saver_iter.py
+style checkpointing works unchanged.  All parameters of one
 instance share one step counter (every parameter of a network receives a gradient in every step of the reference's loop)."""
 import ctypes as C
 
@@ -29,7 +30,8 @@ class Adam(torch.optim.Optimizer):
         """device array of b200_adam_entry for the group's chunks.  The pinned host image and the device buffer are
         allocated once; when gradient tensors move (a CUDA-graph capture allocates them from its own pool) only the image is
         rewritten and re-copied with an asynchronous pinned copy — a capturable memcpy node, no allocation under capture."""
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in items)
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr()) for p in items)
         slot = self._tables.get(group_idx)
         n_ent = sum(-(-p.numel() // CHUNK) for p in items)
         nbytes = n_ent * C.sizeof(_Entry)
@@ -52,6 +54,27 @@ class Adam(torch.optim.Optimizer):
             slot["dev"][:nbytes].copy_(slot["host"][:nbytes], non_blocking=True)
             slot["key"], slot["n"] = key, n_ent
         return slot["dev"], slot["n"]
+
+    def load_state_dict(self, state_dict):
+        """torch.optim.Optimizer.load_state_dict, then: the kernel reads ONE device step counter per group, so it is
+        rebuilt from the loaded per-parameter `step` values (bias correction continues where the checkpoint stopped), and
+        the cached device tables are dropped (the loaded exp_avg / exp_avg_sq are new tensors)."""
+        super().load_state_dict(state_dict)
+        self._tables = {}
+        self._steps = {}
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p in self.state and "step" in self.state[p]]
+            if not ps:
+                continue
+            t = max(float(self.state[p]["step"]) for p in ps)
+            step_t = torch.full((), t, dtype=torch.float32, device=ps[0].device)
+            self._steps[gi] = step_t
+            for p in ps:
+                st = self.state[p]
+                st["step"] = step_t
+                for k in ("exp_avg", "exp_avg_sq"):
+                    if st[k].device != p.device or st[k].dtype != torch.float32 or not st[k].is_contiguous():
+                        st[k] = st[k].to(device=p.device, dtype=torch.float32).contiguous()
 
     @torch.no_grad()
     def step(self, closure=None):

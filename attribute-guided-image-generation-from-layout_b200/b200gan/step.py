@@ -82,11 +82,18 @@ class TrainStep:
         self.fake_w = torch.tensor(FAKE_W, device=self.device)
         self.skip_dead_work = skip_dead_work
         kw = dict(lr=lr, betas=(0.5, 0.999))
+        # optimizer: "b200" = the multi-tensor kernel (CUDA only) | "torch_fused" = torch.optim.Adam(fused=True) |
+        # "torch" = torch.optim.Adam (on CUDA: fused=fused_adam).  Whichever updates the weights, the packed GEMM operands
+        # follow through the global post-step hook (ops.WeightPacks).
         if self.device.type == "cuda" and optimizer == "b200":
             from .optim import Adam                                                  # multi-tensor kernel, device step counter
         else:
             Adam = torch.optim.Adam
-            if self.device.type == "cuda":
+            if optimizer == "torch_fused":
+                kw.update(fused=True)
+                if self.device.type == "cuda":
+                    kw.update(capturable=capturable)
+            elif self.device.type == "cuda":
                 kw.update(fused=fused_adam, capturable=capturable)
         self.opt_G = Adam(self.netG.parameters(), **kw)                              # train64.py:111-114
         self.opt_D = [Adam(n.parameters(), **kw) for n in (self.netD_image, self.netD_object, self.netD_att)]

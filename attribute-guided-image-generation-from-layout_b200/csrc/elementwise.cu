@@ -471,30 +471,65 @@ __global__ void colsum_final_kernel(const double* __restrict__ ws, int nchunks, 
     if (lane == 0) out[c] = (float)s;
 }
 
+__device__ __forceinline__ uint16_t f32_to_bf16_rn(float v) {
+    uint32_t u = __float_as_uint(v);
+    uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+    if ((u & 0x7F800000u) == 0x7F800000u) r = u;  // inf / nan pass through
+    return (uint16_t)(r >> 16);
+}
+
+// full entry (C_dst == C, c_off == 0): every element of the Mpad x ldw matrix is written (zeros in the padding);
+// partial entry (a channel slice [c_off, c_off + C) of a wider matrix): only its valid elements are written
 __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restrict__ dst, int dst_bf16, int M, int Mpad,
                                    int Th, int Tw, int C, int64_t ldw, int64_t s_m, int64_t s_ky, int64_t s_kx,
-                                   int64_t s_c, int ky0, int kx0, int kstep) {
+                                   int64_t s_c, int ky0, int kx0, int kstep, int C_dst, int c_off) {
     int64_t total = (int64_t)Mpad * ldw;
-    int K = Th * Tw * C;
+    const int K = Th * Tw * C_dst;
+    const bool full = (C_dst == C && c_off == 0);
     GRID_STRIDE(t, total) {
         int64_t m = t / ldw;
         int k = (int)(t % ldw);
         float v = 0.f;
+        bool valid = false;
         if (m < M && k < K) {
-            int c = k % C;
-            int tap = k / C;
-            int i = tap % Tw, j = tap / Tw;
-            v = src[m * s_m + (int64_t)(ky0 + kstep * j) * s_ky + (int64_t)(kx0 + kstep * i) * s_kx + (int64_t)c * s_c];
+            int c = k % C_dst - c_off;
+            int tap = k / C_dst;
+            if (c >= 0 && c < C) {
+                int i = tap % Tw, j = tap / Tw;
+                v = src[m * s_m + (int64_t)(ky0 + kstep * j) * s_ky + (int64_t)(kx0 + kstep * i) * s_kx + (int64_t)c * s_c];
+                valid = true;
+            }
         }
-        if (dst_bf16) {
-            // round-to-nearest-even fp32 -> bf16
-            uint32_t u = __float_as_uint(v);
-            uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
-            if ((u & 0x7F800000u) == 0x7F800000u) r = u;  // inf / nan pass through
-            reinterpret_cast<uint16_t*>(dst)[t] = (uint16_t)(r >> 16);
-        } else {
-            reinterpret_cast<float*>(dst)[t] = v;
-        }
+        if (!valid && !full) continue;
+        if (dst_bf16) reinterpret_cast<uint16_t*>(dst)[t] = f32_to_bf16_rn(v);
+        else reinterpret_cast<float*>(dst)[t] = v;
+    }
+}
+
+// every packed operand of a network in one launch: block b = one B200_PACK_CHUNK-element chunk of one entry's VALID
+// elements (binary search over the chunk prefix sums), same element mapping as pack_weight_kernel
+__global__ void __launch_bounds__(256) pack_weight_multi_kernel(const b200_pack_entry* __restrict__ entries, int n_entries) {
+    const int b = blockIdx.x;
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {                                   // last entry with chunk_begin <= b
+        int mid = (lo + hi + 1) >> 1;
+        if (entries[mid].chunk_begin <= b) lo = mid; else hi = mid - 1;
+    }
+    const b200_pack_entry en = entries[lo];
+    const int TC = en.Th * en.Tw * en.C;
+    const int64_t total = (int64_t)en.M * TC;
+    const int64_t t0 = (int64_t)(b - en.chunk_begin) * B200_PACK_CHUNK;
+    const int64_t t1 = t0 + B200_PACK_CHUNK < total ? t0 + B200_PACK_CHUNK : total;
+    for (int64_t t = t0 + threadIdx.x; t < t1; t += 256) {
+        const int64_t m = t / TC;
+        const int r = (int)(t - m * TC);
+        const int tap = r / en.C, c = r - tap * en.C;
+        const int j = tap / en.Tw, i = tap - j * en.Tw;
+        const float v = en.src[m * en.s_m + (int64_t)(en.ky0 + en.kstep * j) * en.s_ky +
+                               (int64_t)(en.kx0 + en.kstep * i) * en.s_kx + (int64_t)c * en.s_c];
+        const int64_t d = m * en.ldw + (int64_t)tap * en.C_dst + en.c_off + c;
+        if (en.dst_bf16) reinterpret_cast<uint16_t*>(en.dst)[d] = f32_to_bf16_rn(v);
+        else reinterpret_cast<float*>(en.dst)[d] = v;
     }
 }
 
@@ -1028,12 +1063,24 @@ extern "C" int b200_rowsum(const void* x, int dt, int64_t rows, int64_t L, float
 
 extern "C" int b200_pack_weight(const float* src, void* dst, int dst_bf16, int M, int Mpad, int Th, int Tw, int C,
                                 int64_t ldw, int64_t s_m, int64_t s_ky, int64_t s_kx, int64_t s_c, int ky0, int kx0,
-                                int kstep, b200_stream_t stream) {
-    B200_REQUIRE(ldw >= (int64_t)Th * Tw * C && Mpad >= M, "pack_weight: ldw/Mpad too small");
+                                int kstep, int C_dst, int c_off, b200_stream_t stream) {
+    if (C_dst <= 0) { C_dst = C; c_off = 0; }
+    B200_REQUIRE(ldw >= (int64_t)Th * Tw * C_dst && Mpad >= M && c_off >= 0 && c_off + C <= C_dst,
+                 "pack_weight: ldw/Mpad too small or bad channel slice");
     int64_t total = (int64_t)Mpad * ldw;
     if (total == 0) return 0;
     pack_weight_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(src, dst, dst_bf16, M, Mpad, Th, Tw, C, ldw,
-                                                                            s_m, s_ky, s_kx, s_c, ky0, kx0, kstep);
+                                                                            s_m, s_ky, s_kx, s_c, ky0, kx0, kstep, C_dst,
+                                                                            c_off);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_pack_weight_multi(const b200_pack_entry* entries_dev, int n_entries, int total_chunks,
+                                      b200_stream_t stream) {
+    if (n_entries <= 0 || total_chunks <= 0) return 0;
+    B200_REQUIRE(entries_dev != nullptr, "pack_weight_multi: null table");
+    pack_weight_multi_kernel<<<total_chunks, 256, 0, as_stream(stream)>>>(entries_dev, n_entries);
     B200_CHECK_LAUNCH();
     return 0;
 }

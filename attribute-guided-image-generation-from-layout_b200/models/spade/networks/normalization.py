@@ -29,8 +29,8 @@ class SPADE(nn.Module):
         if f > 1:
             seg = ops.upsample_nearest(seg, f)
         actv = self.mlp_shared[0](seg, relu=True, grad_premasked=True)      # its only consumer masks the gradient (below)
-        if self._gb_packs is None or self._gb_packs.stamp_src[0] is not self.mlp_gamma.weight:
-            self._gb_packs = WeightPacks(stamp_src=(self.mlp_gamma.weight, self.mlp_beta.weight))
+        if self._gb_packs is None or self._gb_packs.sources[0] is not self.mlp_gamma.weight:
+            self._gb_packs = WeightPacks(sources=(self.mlp_gamma.weight, self.mlp_beta.weight))
         w = torch.cat([self.mlp_gamma.weight, self.mlp_beta.weight], dim=0)
         b = torch.cat([self.mlp_gamma.bias, self.mlp_beta.bias], dim=0)
         gb = ops.conv2d(actv, w, b, self._gb_geom, self._gb_packs, mask_input_grad=True)

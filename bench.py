@@ -261,7 +261,9 @@ def run_b200(args):
             with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
                 r = eager_step(b)
                 static_out = (r["d_loss"], r["g_loss"])
-            ops.bump_weight_epoch()
+            # (every optimizer step inside the captured iteration is followed by the in-place re-pack of the GEMM operands
+            # derived from its parameters — ops.refresh_packs via the optimizer post-step hook — so each replay computes
+            # with the weights the previous replay wrote)
             for _ in range(args.warmup):
                 graph.replay()
             torch.cuda.synchronize()
@@ -269,7 +271,6 @@ def run_b200(args):
             if rank == 0:
                 print("[bench] CUDA graph capture unavailable (%s: %s); timing eagerly" % (type(e).__name__, e), file=sys.stderr)
             graph = None
-            ops.bump_weight_epoch()
             torch.cuda.synchronize()
 
     note("graph captured" if graph is not None else "no graph: eager steps")
@@ -287,12 +288,18 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    traj = torch.zeros((args.steps, 2), device=dev)           # loss trajectory of the timed iterations (device-side copies)
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         losses = run_step()
+        traj[i, 0].copy_(losses[0]); traj[i, 1].copy_(losses[1])
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1) / args.steps
+    traj = traj.cpu()
+    # the timed iterations TRAIN: the same batch is replayed, so the losses must move from iteration to iteration
+    assert args.steps < 2 or (traj[1:] != traj[:-1]).any(dim=1).all(), \
+        "losses repeat across timed iterations: the optimizer update is not reaching the next iteration"
     clocks = sampler.stop() if rank == 0 else None
     note("device-resident timing done: %.2f ms/step" % ms)
     assert all(torch.isfinite(l).all() for l in losses), "non-finite loss in the timed region"
@@ -348,6 +355,10 @@ def run_b200(args):
             "roofline": roof,
             "cpu_baseline": cpu_base,
             "step_tflops": step_flops(args.size, n_img, n_obj) / (ms / 1e3) / 1e12,
+            "loss_trajectory": {"d_loss": [round(float(v), 5) for v in traj[:, 0][:8]],
+                                "g_loss": [round(float(v), 5) for v in traj[:, 1][:8]],
+                                "note": "first timed iterations on one repeated batch; they move because every iteration "
+                                        "applies the four Adam updates and re-packs the GEMM operands"},
         }
         emit(line)
     if world > 1:
@@ -413,7 +424,6 @@ def kernel_roofline(ts, b, args):
     ddp = (ts.ddp_d, ts.ddp_g)
     ts.ddp_d = ts.ddp_g = None        # rank 0 alone runs this step: no gradient exchange
     try:
-        ops.bump_weight_epoch()
         ts.step(b, optimizer_step=False)
         torch.cuda.synchronize()
     finally:

@@ -154,10 +154,27 @@ int b200_wgrad_reduce(const float* ws, int splits, int64_t split_stride, int M, 
                       b200_stream_t stream);
 /* Weight packing from the parameter layout into GEMM matrices (fp32 or bf16), taps (ky0+kstep*j, kx0+kstep*i):
  * dst[m*ldw + (j*Tw+i)*C + c] = src[m*s_m + (ky0+kstep*j)*s_ky + (kx0+kstep*i)*s_kx + c*s_c]; rows m in [M,Mpad) and
- * columns beyond Th*Tw*C are zero filled. */
+ * columns beyond Th*Tw*C are zero filled.
+ * C_dst > C: the entry is the channel slice [c_off, c_off + C) of a C_dst-channel matrix (column (j*Tw+i)*C_dst + c_off + c)
+ * and writes only its valid elements; C_dst <= 0 means C_dst = C, c_off = 0. */
 int b200_pack_weight(const float* src, void* dst, int dst_bf16, int M, int Mpad, int Th, int Tw, int C, int64_t ldw,
-                     int64_t s_m, int64_t s_ky, int64_t s_kx, int64_t s_c, int ky0, int kx0, int kstep,
-                     b200_stream_t stream);
+                     int64_t s_m, int64_t s_ky, int64_t s_kx, int64_t s_c, int ky0, int kx0, int kstep, int C_dst,
+                     int c_off, b200_stream_t stream);
+/* The same packing for MANY matrices in one launch: the refresh of every packed GEMM operand of a network after its
+ * optimizer step (train64.py:258-262 / 366-370 update the weights every iteration; the operand matrices above must follow).
+ * Entry e writes ONLY the valid elements dst[m*ldw + (j*Tw+i)*C_dst + c_off + c], m < M, c < C — padding (rows >= M,
+ * columns >= Th*Tw*C_dst) is left untouched (the caller zero-fills it once at allocation), so several entries can fill
+ * one matrix (SPADE's fused gamma|beta operand is packed from two parameters).  chunk_begin = number of
+ * B200_PACK_CHUNK-element chunks of the entries before e (a prefix sum; the kernel maps one block to one chunk). */
+#define B200_PACK_CHUNK 8192
+typedef struct {
+    const float* src;
+    void* dst;
+    int64_t ldw, s_m, s_ky, s_kx, s_c;
+    int32_t dst_bf16, M, Th, Tw, C, C_dst, c_off, ky0, kx0, kstep;
+    int32_t chunk_begin, pad;
+} b200_pack_entry;
+int b200_pack_weight_multi(const b200_pack_entry* entries_dev, int n_entries, int total_chunks, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Normalisation family — replaces nn.BatchNorm1d/2d, ConditionalBatchNorm2d (generator_obj_att.py:31-44),

@@ -219,13 +219,37 @@ class EmulKernels:
             view.copy_(R)
 
     def pack_weight(self, src, src_offset, dst, dst_row_offset, bf16, M, Mpad, Th, Tw, C, ldw, s_m, s_ky, s_kx, s_c,
-                    ky0=0, kx0=0, kstep=1):
+                    ky0=0, kx0=0, kstep=1, C_dst=0, c_off=0):
         self.launches += 1
+        self._pack(src, src_offset, dst, dst_row_offset, M, Mpad, Th, Tw, C, ldw, s_m, s_ky, s_kx, s_c, ky0, kx0, kstep,
+                   C_dst, c_off, valid_only=False)
+
+    @staticmethod
+    def _pack(src, src_offset, dst, dst_row_offset, M, Mpad, Th, Tw, C, ldw, s_m, s_ky, s_kx, s_c, ky0, kx0, kstep, C_dst,
+              c_off, valid_only):
         v = _storage_view(src.detach(), src_offset + ky0 * s_ky + kx0 * s_kx, (M, Th, Tw, C),
                           (s_m, s_ky * kstep, s_kx * kstep, s_c))
-        out = torch.zeros(Mpad, ldw)
-        out[:M, :Th * Tw * C] = v.reshape(M, -1)
-        dst[dst_row_offset:dst_row_offset + Mpad] = out.to(dst.dtype)
+        full = C_dst <= 0 or (C_dst == C and c_off == 0)
+        if C_dst <= 0:
+            C_dst, c_off = C, 0
+        with torch.no_grad():
+            if full and not valid_only:          # whole Mpad x ldw block, zero padded
+                out = torch.zeros(Mpad, ldw)
+                out[:M, :Th * Tw * C] = v.reshape(M, -1)
+                dst[dst_row_offset:dst_row_offset + Mpad] = out.to(dst.dtype)
+            else:                                # only the valid elements (of a channel slice)
+                blk = dst[dst_row_offset:dst_row_offset + M, :Th * Tw * C_dst].view(M, Th * Tw, C_dst)
+                blk[:, :, c_off:c_off + C] = v.reshape(M, Th * Tw, C).to(dst.dtype)
+
+    def pack_table(self, recipes, device):
+        return None, list(recipes), len(recipes), 0
+
+    def pack_weight_multi(self, table_dev, n_entries, total_chunks):
+        """b200_pack_weight_multi: every entry's valid elements, padding untouched"""
+        self.launches += 1
+        for r in table_dev:
+            self._pack(r.src, r.src_offset, r.dst, r.dst_row_offset, r.M, r.Mpad, r.Th, r.Tw, r.C, r.ldw, r.s_m, r.s_ky,
+                       r.s_kx, r.s_c, r.ky0, r.kx0, r.kstep, r.C_dst, r.c_off, valid_only=True)
 
     # ---- normalisation --------------------------------------------------------------------------------------
     def bn_stats(self, x2d, running_mean, running_var, momentum, groups=1):

@@ -753,3 +753,81 @@ def test_im2col_path_equals_cpasync_path(K, case):
     y32 = ops.conv_forward(geom, ops.WeightPacks(), w, x, "cl", "cl") if not transposed else \
         ops.conv_dgrad(geom, ops.WeightPacks(), w, dy, "cl", (H, H), "cl")
     close(outs[0][0], y32, 2e-2, "tc vs fp32")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# packed GEMM operands follow the weights (round-1 defect: they went stale after raw-pointer / fused optimizer updates)
+# ---------------------------------------------------------------------------------------------------------
+def _conv_operands(g, w, tc, sources=None):
+    packs = ops.WeightPacks(sources)
+    fwd = packs.get(("fwd", tc) + g.key(), w, lambda src, rec: ops._pack_fwd(g, src, tc, rec))
+    dg = packs.get(("dgrad", tc) + g.key(), w, lambda src, rec: ops._pack_dgrad(g, src, tc, rec))
+    return packs, fwd, dg
+
+
+def _emul_operands(g, w, tc, n_src=1):
+    """the same matrices through the CPU restatement of b200_pack_weight"""
+    real = _lib.K
+    _lib.K = E
+    try:
+        srcs = tuple(w.cpu().chunk(n_src, 0)) if n_src > 1 else (w.cpu(),)
+        fwd = ops._pack_fwd(g, srcs, tc, [])
+        dg = ops._pack_dgrad(g, srcs, tc, [])
+    finally:
+        _lib.K = real
+    return fwd, dg
+
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("geom", [(64, 128, 4, 4, 2, 1, 0, None), (128, 256, 3, 3, 1, 1, 0, None), (64, 256, 5, 5, 1, 2, 128, 192),
+                                  (192, 64, 1, 1, 1, 0, 0, None)])
+def test_pack_refresh_follows_raw_weight_updates(K, geom, tc):
+    """pack once, change the weights WITHOUT moving the tensor version (what b200_adam_multi and torch's fused Adam do),
+    refresh_packs() -> every operand (forward + the stride^2 data-gradient phases) equals a fresh pack, bit for bit"""
+    Cx, Cy, kh, kw, s, p, off, tot = geom
+    g = ops.ConvGeom(Cx, Cy, kh, kw, s, p, off, tot)
+    gen = torch.Generator().manual_seed(3)
+    w = torch.randn(Cy, g.cx_total, kh, kw, generator=gen).cuda()
+    packs, fwd, dg = _conv_operands(g, w, tc)
+    v0 = w._version
+    w2 = torch.randn(Cy, g.cx_total, kh, kw, generator=gen)
+    w.data.copy_(w2)          # `.data` writes do not move the tensor version (nor do raw-pointer kernels)
+    assert w._version == v0
+    stale = packs.get(("fwd", tc) + g.key(), w, None)          # cache hit: the stamp cannot see the raw update
+    assert stale[0] is fwd[0]
+    n = ops.refresh_packs([w])
+    assert n >= 1 + sum(1 for q in dg if q is not None)
+    torch.cuda.synchronize()
+    ref_fwd, ref_dg = _emul_operands(g, w2, tc)
+    assert torch.equal(fwd[0].cpu(), ref_fwd[0]) and fwd[1] == ref_fwd[1]
+    for a, r in zip(dg, ref_dg):
+        assert (a is None) == (r is None)
+        if a is not None:
+            assert torch.equal(a[0].cpu(), r[0])
+    # a version-visible update (load_state_dict, foreach optimizers) re-packs lazily into the SAME buffers
+    with torch.no_grad():
+        w.mul_(2.0)
+    again = packs.get(("fwd", tc) + g.key(), w, lambda src, rec: ops._pack_fwd(g, src, tc, rec))
+    assert again[0].data_ptr() == fwd[0].data_ptr()
+    assert torch.equal(again[0].cpu(), _emul_operands(g, w2 * 2.0, tc)[0][0])
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_pack_from_two_parameters(K, tc):
+    """SPADE's fused gamma|beta convolution (normalization.py:101-104): the 2C-output operand is packed from the two
+    parameters directly (row slices forward, channel slices in the data-gradient matrices)"""
+    g = ops.ConvGeom(128, 256, 3, 3, 1, 1)
+    gen = torch.Generator().manual_seed(4)
+    wg, wb = torch.randn(128, 128, 3, 3, generator=gen).cuda(), torch.randn(128, 128, 3, 3, generator=gen).cuda()
+    w = torch.cat([wg, wb])
+    packs, fwd, dg = _conv_operands(g, w, tc, sources=(wg, wb))
+    one, fwd1, dg1 = _conv_operands(g, w, tc)
+    assert torch.equal(fwd[0], fwd1[0])
+    for a, r in zip(dg, dg1):
+        assert torch.equal(a[0], r[0])
+    wb.data.mul_(-3.0)
+    ops.refresh_packs([wb])
+    ref_fwd, ref_dg = _emul_operands(g, torch.cat([wg, wb]), tc)
+    assert torch.equal(fwd[0].cpu(), ref_fwd[0])
+    for a, r in zip(dg, ref_dg):
+        assert torch.equal(a[0].cpu(), r[0])

@@ -175,3 +175,47 @@ def test_multi_tensor_adam_matches_torch():
     assert float(o_b.state[mine[0]]["step"]) == 6.0      # 4 + 1 eager + 1 replay (capture itself does not run)
     sd = o_b.state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_adam_save_load_step_parity():
+    """checkpoint round trip (utils/model_saver_iter.py:40-57 saves optimizer.state_dict()): a b200gan Adam that has already
+    stepped loads another optimizer's state and must continue exactly like torch.optim.Adam does after the same load —
+    bias-correction step count and moments come from the checkpoint, not from the instance's own history."""
+    import copy
+    from b200gan.optim import Adam
+    g = torch.Generator().manual_seed(1)
+    shapes = [(300, 7), (65537,), (64, 3, 3, 3)]
+    ref = [torch.randn(s, generator=g).cuda().requires_grad_(True) for s in shapes]
+    mine = [p.detach().clone().requires_grad_(True) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=2e-4, betas=(0.5, 0.999))
+    o_b = Adam(mine, lr=2e-4, betas=(0.5, 0.999))
+
+    def both(n, scale=1.0):
+        for _ in range(n):
+            for a, b in zip(ref, mine):
+                gr = torch.randn(a.shape, generator=g).cuda() * scale
+                a.grad, b.grad = gr.clone(), gr.clone()
+            o_ref.step()
+            o_b.step()
+
+    both(3)
+    ckpt_ref, ckpt_b = copy.deepcopy(o_ref.state_dict()), copy.deepcopy(o_b.state_dict())
+    assert float(ckpt_b["state"][0]["step"]) == 3.0
+    both(2, 5.0)                                           # the instances move on ...
+    with torch.no_grad():
+        for a, b in zip(ref, mine):                        # ... then weights and optimizer state are restored
+            b.copy_(a)
+    o_ref.load_state_dict(ckpt_ref)
+    o_b.load_state_dict(ckpt_b)
+    assert float(o_b.state[mine[0]]["step"]) == 3.0
+    both(2)
+    for a, b in zip(ref, mine):
+        assert rel(b, a) < 1e-6
+        assert rel(o_b.state[b]["exp_avg"], o_ref.state[a]["exp_avg"]) < 1e-6
+        assert rel(o_b.state[b]["exp_avg_sq"], o_ref.state[a]["exp_avg_sq"]) < 1e-6
+    assert float(o_b.state[mine[0]]["step"]) == 5.0
+    # loading a torch.optim.Adam checkpoint into the kernel optimizer works too (same state layout)
+    o_b.load_state_dict(copy.deepcopy(o_ref.state_dict()))
+    both(1)
+    for a, b in zip(ref, mine):
+        assert rel(b, a) < 1e-6

@@ -65,6 +65,99 @@ def test_bf16_step_within_stated_bound():
     assert cos > 0.85
 
 
+@pytest.mark.parametrize("optimizer", ["b200", "torch_fused", "torch"])
+def test_three_training_iterations_follow_oracle(optimizer):
+    """train64.py:254-262, 366-370: the weights move every iteration and every GEMM must see them.  Three full iterations
+    (D-step, 3 x Adam, G-step on the updated discriminators, Adam) in fp32; each is compared with one oracle +
+    torch.optim.Adam iteration started from the same state (helpers.SyncedOracle explains why not free-running).  The raw-
+    pointer kernel optimizer and torch's fused Adam do not move tensor versions — round 1's packed operands went stale
+    exactly there."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    from helpers import run_synced_training
+    states = O.make_states(64, 0)
+    batch = O.synth_batch(2, 64, 4, 7)
+    ops.set_precision("fp32")
+    ts = TrainStep(64, device="cuda", optimizer=optimizer)
+    load_states(ts, states)
+    log = run_synced_training(ts, batch, 64, states, 3, img_tol=1e-4, loss_tol=1e-4,
+                              cos_min=dict(G=0.97, D_img=0.999, D_obj=0.999, D_att=0.999), verbose=True)
+    assert len(log) == 3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_replays_train(precision):
+    """The bench path: ONE captured CUDA graph of the whole iteration (incl. the Adam updates and the re-pack of every GEMM
+    operand) replayed three times must train like the eager step: every replay is compared with one oracle iteration from
+    the state the replay started in.  The CropEncoder noise comes from static device buffers filled with the reference's
+    CPU-RNG draws before each replay."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    from helpers import reference_eps, run_synced_training
+    states = O.make_states(64, 0)
+    batch = O.synth_batch(2, 64, 4, 7)
+    n_obj = batch["objs"].shape[0]
+    ops.set_precision(precision)
+    try:
+        ts = TrainStep(64, device="cuda", optimizer="b200")
+        load_states(ts, states)
+        # per iteration the crop encoder is called (O) then (2O) in each of the two generator forwards
+        bufs = [torch.zeros(n_obj, 64, device="cuda"), torch.zeros(2 * n_obj, 64, device="cuda"),
+                torch.zeros(n_obj, 64, device="cuda"), torch.zeros(2 * n_obj, 64, device="cuda")]
+        calls = [0]
+
+        def eps_source(o, z, dev):
+            t = bufs[calls[0] % 4]
+            calls[0] += 1
+            assert t.shape == (o, z)
+            return t
+
+        def fill(seeds):
+            for half, seed in enumerate(seeds):
+                e = reference_eps(seed, n_obj)
+                bufs[2 * half].copy_(e[0])
+                bufs[2 * half + 1].copy_(torch.cat(e[1:]))
+
+        ts.netG.crop_encoder.eps_source = eps_source
+        b = ts.to_device(batch)
+        sd0 = {n: {k: v.clone() for k, v in net.state_dict().items()} for n, net in
+               (("G", ts.netG), ("D_img", ts.netD_image), ("D_obj", ts.netD_object), ("D_att", ts.netD_att))}
+        fill((1, 2))
+        for _ in range(2):                                  # eager warm-up: builds every packed operand and plan
+            ts.step(b, optimizer_step=True)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ts.step(b, optimizer_step=True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        calls[0] = 0
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static = ts.step(b, optimizer_step=True)
+        # back to the initial weights / statistics and fresh Adam moments, written IN PLACE (the graph holds the addresses)
+        with torch.no_grad():
+            for n, net in (("G", ts.netG), ("D_img", ts.netD_image), ("D_obj", ts.netD_object), ("D_att", ts.netD_att)):
+                for k, v in net.state_dict().items():
+                    v.copy_(sd0[n][k])
+            for o in [ts.opt_G] + ts.opt_D:
+                for st in o.state.values():
+                    st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+                for t in o._steps.values():
+                    t.zero_()
+        ops.refresh_packs()                                 # weights were written behind the optimizer's back
+
+        def replay(bb, seeds):
+            fill(seeds)
+            graph.replay()
+            torch.cuda.synchronize()
+            return static
+
+        tol = dict(img_tol=1e-4, loss_tol=1e-4, cos_min=dict(G=0.97, D_img=0.999, D_obj=0.999, D_att=0.999)) \
+            if precision == "fp32" else dict(img_tol=8e-2, loss_tol=5e-2, cos_min=dict(G=0.5, D_img=0.9, D_obj=0.9, D_att=0.9))
+        run_synced_training(ts, batch, 64, states, 3, verbose=True, step_fn=replay, **tol)
+    finally:
+        ops.set_precision("fp32")
+
+
 def test_ragged_batch_and_optimizer_steps():
     """3..9 objects per image incl. repeated steps with Adam: losses stay finite, weights move, step is deterministic"""
     batch = O.synth_batch(3, 64, None, 11)

@@ -101,3 +101,20 @@ def test_step_wiring_bf16_operand_routing(emul):
     a = torch.cat([p.grad.reshape(-1) for _, p in ts.netG.named_parameters()]).double()
     r = torch.cat([ref["g_grads"][k].reshape(-1) for k, _ in ts.netG.named_parameters()]).double()
     assert float(cos(a, r, dim=0)) > 0.85
+
+
+@pytest.mark.parametrize("optimizer", ["torch_fused", "torch"])
+def test_three_training_steps_follow_the_oracle(emul, optimizer):
+    """Multi-step parity (train64.py:254-262, 366-370): after every Adam update the GEMM operands must be the NEW weights —
+    torch's fused Adam never moves tensor versions, which is what left the packed operands stale in round 1.  Three full
+    iterations (D-step, 3x Adam, G-step on the updated discriminators, Adam), each against one oracle iteration started
+    from the same state (helpers.SyncedOracle)."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    from helpers import run_synced_training
+    from b200gan.step import TrainStep
+    states = O.make_states(64, 0)
+    batch = O.synth_batch(2, 64, 4, 7)
+    ts = TrainStep(64, device="cpu", optimizer=optimizer)
+    load_states(ts, states)
+    run_synced_training(ts, batch, 64, states, 3, img_tol=1e-4, loss_tol=1e-4,
+                        cos_min=dict(G=0.97, D_img=0.999, D_obj=0.999, D_att=0.999), verbose=True)
