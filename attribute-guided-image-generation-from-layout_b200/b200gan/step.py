@@ -69,10 +69,38 @@ def estimate_attributes(att_logits, attribute):
     return est
 
 
+def swap_attributes(attribute: torch.Tensor, objs: torch.Tensor, obj_to_img: torch.Tensor, n_images: int,
+                    matrix: torch.Tensor, rng):
+    """train64.py:169-188 ("change GT attribute"), host side like the reference: in the first floor(N/3) images the first
+    floor(n_obj/2) objects get 1-2 new attributes drawn from `matrix[obj]` (object-vs-attribute co-occurrence counts,
+    matrix_obj_vs_att.pt) with the object's current attributes excluded.  rng: a `random.Random` (the reference draws
+    randrange(1, 3) and then choices() from the global `random` module, in that order).  CPU tensors in, returns
+    (swapped attribute, LongTensor of swapped rows); the step overwrites the same rows of attribute_est
+    (train64.py:187-188) and keeps the ORIGINAL attribute as attribute_GT (train64.py:153, 241-244)."""
+    out = attribute.clone()
+    rows = []
+    n_att = attribute.shape[1]
+    for img_idx in range(n_images // 3):
+        members = torch.nonzero(obj_to_img == img_idx).view(-1).tolist()
+        for obj_idx in members[:len(members) // 2]:
+            weights = matrix[int(objs[obj_idx])].clone()
+            weights[torch.nonzero(attribute[obj_idx]).view(-1)] = 0
+            k = rng.randrange(1, 3)
+            new = rng.choices(range(n_att), weights, k=k)
+            out[obj_idx] = 0
+            out[obj_idx, torch.tensor(new, dtype=torch.long)] = 1
+            rows.append(obj_idx)
+    return out, torch.tensor(rows, dtype=torch.long)
+
+
 class TrainStep:
     def __init__(self, image_size: int = 64, device="cuda", lr: float = 2e-4, lambdas: Optional[Dict[str, float]] = None,
                  pos_weight: Optional[torch.Tensor] = None, skip_dead_work: bool = True, fused_adam: bool = True,
-                 capturable: bool = False, optimizer: str = "b200"):
+                 capturable: bool = False, optimizer: str = "b200", att_matrix: Optional[torch.Tensor] = None,
+                 swap_rng=None):
+        # att_matrix (179, 106) + swap_rng (random.Random): enable the reference's GT-attribute swap (train64.py:169-188)
+        # in to_device(); without a matrix the batch's attributes are used as they are (the parity configuration)
+        self.att_matrix, self.swap_rng = att_matrix, swap_rng
         self.image_size, self.obj_size = image_size, image_size // 2
         self.device = torch.device(device)
         self.lam = dict(LAMBDAS if lambdas is None else lambdas)
@@ -111,10 +139,24 @@ class TrainStep:
     # ---- batch handling ---------------------------------------------------------------------------------
     def to_device(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """train64.py:149-151: everything but obj_to_img moves to the device; index sets that the reference derives with
-        nonzero() on the device are derived here from the CPU copy (no device sync inside the step)."""
+        nonzero() on the device are derived here from the CPU copy (no device sync inside the step).  With an att_matrix
+        the GT-attribute swap (train64.py:169-188) is applied here, on the host as in the reference: `attribute` becomes
+        the swapped one, `attribute_GT` keeps the original, `swap_rows` lists the changed objects.  A caller that did the
+        swap itself passes `attribute_GT` (and optionally `swap_rows`) in the batch."""
+        batch = dict(batch)
+        if "attribute_GT" not in batch and self.att_matrix is not None:
+            import random
+            if self.swap_rng is None:
+                self.swap_rng = random.Random()
+            gt = batch["attribute"]
+            batch["attribute"], batch["swap_rows"] = swap_attributes(gt, batch["objs"], batch["obj_to_img"],
+                                                                     batch["imgs"].shape[0], self.att_matrix, self.swap_rng)
+            batch["attribute_GT"] = gt
         b = {k: (v if k == "obj_to_img" else v.to(self.device, non_blocking=True)) for k, v in batch.items()}
-        att = batch["attribute"]
-        b["att_idx"] = att.sum(dim=1).nonzero().view(-1).to(self.device)
+        gt = batch.get("attribute_GT", batch["attribute"])
+        b["att_idx"] = gt.sum(dim=1).nonzero().view(-1).to(self.device)                    # D-step: train64.py:241
+        if "attribute_GT" in batch:
+            b["att_idx_g"] = batch["attribute"].sum(dim=1).nonzero().view(-1).to(self.device)   # G-step: train64.py:323
         return b
 
     def generator(self, b, attribute_est):
@@ -167,7 +209,7 @@ class TrainStep:
         # D_object / D_att on crops_input_rec, crops_rand, crops_shift   (train64.py:298-349)
         src, cls = D_o(fake["crops_fake"], objs, groups=3)
         att = D_a(fake["crops_fake"], groups=3)
-        idx = b["att_idx"]
+        idx = b.get("att_idx_g", b["att_idx"])
         n_idx = idx.numel()
         idx3 = torch.cat([idx, idx + O, idx + 2 * O])
         att_t = attribute.index_select(0, idx)
@@ -194,11 +236,15 @@ class TrainStep:
         from models.bilinear import crop_bbox_batch
         D_i, D_o, D_a = self.d_nets
         b = dict(b)
-        b["attribute_GT"] = b["attribute"].clone()
+        if "attribute_GT" not in b:
+            b["attribute_GT"] = b["attribute"]                                                  # no swap: train64.py:153
         with torch.no_grad():
             crops = crop_bbox_batch(b["imgs"], b["boxes"], b["obj_to_img"], self.obj_size)     # train64.py:160
             est_logits = D_a(crops)                                                             # train64.py:161
-        attribute_est = estimate_attributes(est_logits, b["attribute"])
+        attribute_est = estimate_attributes(est_logits, b["attribute_GT"])
+        rows = b.get("swap_rows")
+        if rows is not None and rows.numel() > 0:                                               # train64.py:187-188
+            attribute_est.index_copy_(0, rows, b["attribute"].index_select(0, rows))
         # ---------------- D-step ----------------
         if seeds is not None:
             torch.manual_seed(seeds[0])

@@ -616,6 +616,34 @@ def estimate_attributes(att_logits: torch.Tensor, attribute: torch.Tensor) -> to
     return est
 
 
+def swap_attributes(attribute: torch.Tensor, attribute_est: torch.Tensor, objs: torch.Tensor, obj_to_img: torch.Tensor,
+                    n_images: int, matrix: torch.Tensor, rng):
+    """train64.py:169-188 "change GT attribute": in the first floor(N/3) images the first floor(n_obj/2) objects get 1-2
+    NEW attributes drawn from the object-vs-attribute co-occurrence row `matrix[obj]` with the object's current attributes
+    zeroed out; both `attribute` and `attribute_est` rows are replaced by the new multi-hot vector.  `rng` is a Python
+    `random.Random` (the reference uses the global `random` module: randrange(1, 3) is drawn BEFORE choices(), as Python
+    evaluates the keyword argument first).  Returns (attribute, attribute_est, swapped_rows); inputs are not modified;
+    attribute_GT of the step stays the ORIGINAL attribute (train64.py:153)."""
+    attribute, attribute_est = attribute.clone(), attribute_est.clone()
+    attribute_GT = attribute.clone()
+    rows = []
+    for img_idx in range(n_images // 3):
+        obj_indices = torch.nonzero(obj_to_img == img_idx).view(-1)
+        for changed, obj_idx in enumerate(obj_indices.tolist()):
+            if changed >= len(obj_indices) // 2:
+                break
+            old = torch.nonzero(attribute_GT[obj_idx]).view(-1)
+            weights = matrix[int(objs[obj_idx])].clone()
+            weights[old] = 0
+            k = rng.randrange(1, 3)
+            new = rng.choices(range(attribute.shape[1]), weights, k=k)
+            attribute[obj_idx] = 0
+            attribute[obj_idx, torch.tensor(new, dtype=torch.long)] = 1
+            attribute_est[obj_idx] = attribute[obj_idx]
+            rows.append(obj_idx)
+    return attribute, attribute_est, torch.tensor(rows, dtype=torch.long)
+
+
 def bce_logits(x, target_value: float):
     return F.binary_cross_entropy_with_logits(x, torch.full_like(x, target_value))
 

@@ -180,8 +180,45 @@ def make_crop():
                 dfeats=feats.grad.clone(), b2f_u=b2f_u, crops_u=crops_u.clone())
 
 
+def make_swap():
+    """The "change GT attribute" block of the training loop (train64.py:169-188) is inline code, not a function: its
+    lines are read from the reference file and executed UNMODIFIED over a prepared namespace (synthetic co-occurrence
+    matrix with the real one's shape/dtype, Python `random` seeded), and inputs + results are stored."""
+    import math
+    import random
+    import textwrap
+    lines = open("/root/reference/train64.py").read().splitlines()
+    lo = next(i for i, l in enumerate(lines) if "# change GT attribute:" in l)
+    hi = next(i for i, l in enumerate(lines) if "# Generate fake image" in l)
+    code = textwrap.dedent("\n".join(lines[lo:hi]))
+    cases = []
+    for seed, n_images in ((0, 6), (1, 7), (2, 3), (3, 2)):
+        batch = O.synth_batch(n_images, 64, objs_per_image=None, seed=40 + seed, sparse_attributes=True)
+        g = torch.Generator().manual_seed(seed)
+        matrix = torch.randint(0, 5000, (O.NUM_OBJECTS, O.NUM_ATTRIBUTES), generator=g).float()
+        matrix[0] = 0
+        attribute = batch["attribute"].clone()
+        attribute_GT = attribute.clone()
+        est_logits = torch.randn(attribute.shape, generator=g)
+        attribute_est = O.estimate_attributes(est_logits, attribute)
+        ns = dict(torch=torch, math=math, random=random, matrix=matrix, device=torch.device("cpu"), imgs=batch["imgs"],
+                  objs=batch["objs"], obj_to_img=batch["obj_to_img"], attribute=attribute.clone(),
+                  attribute_GT=attribute_GT, attribute_est=attribute_est.clone())
+        random.seed(1000 + seed)
+        exec(code, ns)
+        cases.append(dict(seed=1000 + seed, n_images=n_images, objs=batch["objs"], obj_to_img=batch["obj_to_img"],
+                          matrix=matrix, attribute_in=attribute, attribute_est_in=attribute_est,
+                          attribute_out=ns["attribute"], attribute_est_out=ns["attribute_est"]))
+        changed = int((ns["attribute"] != attribute).any(1).sum())
+        print("swap case %d: N=%d O=%d rows changed %d" % (seed, n_images, attribute.shape[0], changed))
+    return cases
+
+
 if __name__ == "__main__":
     out = os.path.dirname(os.path.abspath(__file__))
+    torch.save(make_swap(), os.path.join(out, "swap.pt"))
+    if "--swap-only" in sys.argv:
+        sys.exit(0)
     torch.save(make_crop(), os.path.join(out, "crop.pt"))
     torch.save(make_step(64, 2, 0), os.path.join(out, "step64.pt"))
     torch.save(make_step(128, 2, 0), os.path.join(out, "step128.pt"))

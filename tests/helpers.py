@@ -21,14 +21,18 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def oracle_step(model, batch, seeds=(123, 124)):
-    """train64.py:141-370 through the oracle; seeds pin the CropEncoder noise of the two generator forwards."""
+def oracle_step(model, batch, seeds=(123, 124), swap=None):
+    """train64.py:141-370 through the oracle; seeds pin the CropEncoder noise of the two generator forwards.
+    swap = (matrix, random.Random): apply the GT-attribute swap of train64.py:169-188 after the attribute estimation."""
     b = dict(batch)
     b["attribute_GT"] = b["attribute"].clone()
     nets = model.nets()
     with torch.no_grad():
         crops = O.crop_bbox_batch(b["imgs"], b["boxes"], b["obj_to_img"], model.obj_size)
     est = O.estimate_attributes(nets["att"](crops).detach(), b["attribute"])
+    if swap is not None:
+        b["attribute"], est, _ = O.swap_attributes(b["attribute"], est, b["objs"], b["obj_to_img"], b["imgs"].shape[0],
+                                                   swap[0], swap[1])
     torch.manual_seed(seeds[0])
     out_d = model.generator(b, est)
     d_loss, d_terms = O.d_step_loss(nets, b, out_d, model.pos_weight)

@@ -85,3 +85,18 @@ def test_oracle_step_matches_reference_golden(size):
                 assert abs(float(st[k].double().norm()) - v[0]) <= 1e-4 * v[0] + 1e-9, (n, k)
             else:
                 assert rel(st[k].float(), v.float()) < 1e-4 or float((st[k].float() - v.float()).abs().max()) < 1e-6, (n, k)
+
+
+def test_attribute_swap_matches_reference_lines():
+    """train64.py:169-188 executed unmodified (make_golden.make_swap) vs the oracle restatement, incl. the Python RNG
+    stream (randrange before choices), images with < 2 objects, un-annotated objects and N < 3"""
+    import random
+    cases = torch.load(os.path.join(GOLD, "swap.pt"))
+    assert len(cases) == 4
+    for c in cases:
+        rng = random.Random(c["seed"])
+        att, est, rows = O.swap_attributes(c["attribute_in"], c["attribute_est_in"], c["objs"], c["obj_to_img"],
+                                           c["n_images"], c["matrix"], rng)
+        assert torch.equal(att, c["attribute_out"]) and torch.equal(est, c["attribute_est_out"])
+        changed = (c["attribute_out"] != c["attribute_in"]).any(1).nonzero().view(-1)
+        assert set(changed.tolist()) <= set(rows.tolist())

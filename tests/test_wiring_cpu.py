@@ -118,3 +118,38 @@ def test_three_training_steps_follow_the_oracle(emul, optimizer):
     load_states(ts, states)
     run_synced_training(ts, batch, 64, states, 3, img_tol=1e-4, loss_tol=1e-4,
                         cos_min=dict(G=0.97, D_img=0.999, D_obj=0.999, D_att=0.999), verbose=True)
+
+
+def test_product_attribute_swap_matches_reference_lines():
+    """b200gan.step.swap_attributes against the golden produced by executing train64.py:169-188 unmodified"""
+    import random
+    from b200gan.step import swap_attributes
+    from helpers import GOLD
+    for c in torch.load(os.path.join(GOLD, "swap.pt")):
+        att, rows = swap_attributes(c["attribute_in"], c["objs"], c["obj_to_img"], c["n_images"], c["matrix"],
+                                    random.Random(c["seed"]))
+        assert torch.equal(att, c["attribute_out"])
+        est = c["attribute_est_in"].clone()
+        est[rows] = att[rows]                                  # what TrainStep._step does on the device
+        assert torch.equal(est, c["attribute_est_out"])
+
+
+def test_step_with_gt_attribute_swap(emul):
+    """the whole iteration with the swap enabled (3 images -> image 0 has half of its objects re-labelled): the D-step
+    attribute loss uses the ORIGINAL labels on the originally annotated rows, the G-step the swapped ones"""
+    import random
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    from b200gan.step import TrainStep
+    states = O.make_states(64, 0)
+    batch = O.synth_batch(3, 64, 4, 9, sparse_attributes=True)
+    g = torch.Generator().manual_seed(0)
+    matrix = torch.randint(0, 5000, (O.NUM_OBJECTS, O.NUM_ATTRIBUTES), generator=g).float()
+    ts = TrainStep(64, device="cpu", att_matrix=matrix, swap_rng=random.Random(77))
+    load_states(ts, states)
+    b = ts.to_device(batch)
+    assert b["swap_rows"].numel() == 2 and not torch.equal(b["attribute"], b["attribute_GT"])
+    res = ts.step(b, optimizer_step=False, seeds=(123, 124))
+    model = O.OracleModel(64, 0, states)
+    ref = oracle_step(model, batch, swap=(matrix, random.Random(77)))
+    assert torch.equal(res["attribute_est"], ref["attribute_est"])
+    check_step_against(ts, res, ref, img_tol=1e-4, loss_tol=1e-5, grad_tol=2e-2, cos_min=0.9999)
