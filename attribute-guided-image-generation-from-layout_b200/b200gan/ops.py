@@ -163,6 +163,9 @@ class WeightPacks:
                 r.run()
             hit[0] = stamp
             return hit[1]
+        # the cache outlives the iteration: hold graph-free aliases (a view of a parameter made under grad mode would keep
+        # its AccumulateGrad node — and its stream — alive across iterations, which breaks CUDA-graph capture)
+        src = tuple(t.detach() for t in src)
         recipes: List[PackRecipe] = []
         val = builder(src, recipes)
         self.store[key] = [stamp, val, recipes, src]
