@@ -72,7 +72,7 @@ def synthetic_loader_module(image_size, n_batches, seed0):
     mod = types.ModuleType("data.vg_custom_mask")
 
     def get_dataloader(batch_size=10, VG_DIR=None, VG_IMG_DIR=None, attribute_embedding=128, image_size=None):
-        return _Loader(batch_size), None
+        return _Loader(batch_size), _Loader(batch_size)
 
     mod.get_dataloader = get_dataloader
     return mod
@@ -85,14 +85,19 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--niter", type=int, default=2)
     ap.add_argument("--batch", type=int, default=3)
+    ap.add_argument("--script", default="train", choices=["train", "test"],
+                    help="train: train64/128.py main(config); test: test64.py (runs its inference / attribute-edit loop on import)")
     args = ap.parse_args()
     import torch
     torch.set_num_threads(max(1, os.cpu_count() or 1))
 
+    written = {}
     for name in ("tensorboardX", "h5py", "imageio"):
         m = types.ModuleType(name)
         if name == "tensorboardX":
             m.SummaryWriter = lambda *a, **k: None
+        if name == "imageio":                      # test64.py:13 — images the script "writes" are recorded instead
+            m.imwrite = lambda path, arr: written.__setitem__(os.path.basename(path), torch.as_tensor(arr).clone())
         sys.modules[name] = m
     # `models` first from the implementation under test, everything else (utils/, data/, attribute_*.py) from the reference
     if args.impl == "b200-emul":
@@ -113,15 +118,23 @@ def main():
     matrix[0] = 0
     torch.save(matrix, "matrix_obj_vs_att.pt")
 
-    script = __import__("train%d" % args.size)
-    import models
-    expect = PKG if args.impl == "b200-emul" else REF
-    assert os.path.abspath(models.__file__).startswith(expect), (models.__file__, expect)
     import utils.model_saver_iter as saver
     dev = "cuda:0" if (torch.cuda.is_available() and args.impl == "b200-emul") else "cpu"
     proxy = TorchProxy(torch, dev)
-    script.torch = proxy
     saver.torch = proxy
+    states = O.make_states(args.size, 0)
+
+    def check_models():
+        import models
+        expect = PKG if args.impl == "b200-emul" else REF
+        assert os.path.abspath(models.__file__).startswith(expect), (models.__file__, expect)
+
+    if args.script == "test":
+        return run_test_script(args, torch, proxy, states, written, check_models)
+
+    script = __import__("train%d" % args.size)
+    check_models()
+    script.torch = proxy
 
     cfg = argparse.Namespace(path="~", dataset="vg", vg_dir="~/vg", batch_size=args.batch, niter=args.niter,
                              image_size=args.size, object_size=args.size // 2, embedding_dim=64, z_dim=64,
@@ -130,7 +143,6 @@ def main():
                              resume_iter="l", log_step=1, tensorboard_step=100, save_step=args.niter,
                              use_tensorboard=False, exp_name="harness")
     _, model_dir, _, _ = script.prepare_dir(cfg.exp_name)
-    states = O.make_states(args.size, 0)
     for key, appendix in (("G", "netG"), ("D_img", "netD_image"), ("D_obj", "netD_object"), ("D_att", "netD_attribute")):
         torch.save({k: v.clone() for k, v in states[key].items()}, os.path.join(model_dir, "iter-0_%s.pkl" % appendix))
 
@@ -138,6 +150,41 @@ def main():
     random.seed(0)
     script.main(cfg)
     print("HARNESS_DONE model_dir=%s" % os.path.abspath(model_dir))
+
+
+def run_test_script(args, torch, proxy, states, written, check_models):
+    """test64.py:75-262 — generator in eval mode, attribute estimation, generation, attribute edit, second generation,
+    attribute-classifier precision / recall.  The script parses sys.argv and runs main() at import time (test64.py:265),
+    so the device proxy has to be what ITS `import torch` binds: the unmodified source is compiled and executed in a module
+    namespace whose `__import__` hands out the proxy for the top-level torch package (nothing else sees the proxy)."""
+    assert args.size == 64
+    os.makedirs("data", exist_ok=True)
+    if not os.path.exists("data/vocab.json"):
+        os.symlink(os.path.join(REF, "data", "vocab.json"), "data/vocab.json")       # test64.py:82 opens it relative to cwd
+    exp = "est_change_att_vg_bs%de64z64clstm3li1.0lo1.0lc1.0lz8.0lc1.0lk0.01" % args.batch    # test64.py:308-318
+    g_dir = os.path.join("~", "checkpoints", "all", "models", exp)
+    d_dir = os.path.join("~", "models", "trained_models")                             # test64.py:103
+    for d, key, appendix in ((g_dir, "G", "netG"), (d_dir, "D_att", "netD_attribute")):
+        os.makedirs(d, exist_ok=True)
+        torch.save({k: v.clone() for k, v in states[key].items()}, os.path.join(d, "iter-0_%s.pkl" % appendix))
+    sys.argv = ["test64.py", "--batch_size", str(args.batch), "--resume_iter", "l"]
+    torch.manual_seed(0)
+    random.seed(0)
+    import builtins
+    real_import = builtins.__import__
+
+    def importer(name, globals=None, locals=None, fromlist=(), level=0):
+        mod = real_import(name, globals, locals, fromlist, level)
+        return proxy if (mod is torch) else mod           # `import torch` / `import torch.x.y as z` bind through the proxy
+
+    ns_builtins = dict(vars(builtins))
+    ns_builtins["__import__"] = importer
+    path = os.path.join(REF, "test64.py")
+    code = compile(open(path).read(), path, "exec")       # the unmodified source, executed as module `test64`
+    exec(code, {"__name__": "test64", "__file__": path, "__builtins__": ns_builtins})
+    check_models()
+    torch.save(written, "written_images.pt")
+    print("HARNESS_DONE images=%d" % len(written))
 
 
 if __name__ == "__main__":

@@ -68,3 +68,32 @@ def test_unmodified_train64_runs_on_the_b200_module_surface(tmp_path):
         assert float(ur.abs().max()) > 1e-4
         cos = float(torch.nn.functional.cosine_similarity(ua, ur, dim=0))
         assert cos >= cos_min, (appendix, cos)
+
+
+def test_unmodified_test64_inference_edit_loop(tmp_path):
+    """test64.py:75-262 (eval-mode generator, attribute estimation, generation, colour-attribute edit + second generation,
+    attribute-classifier precision / recall) executed unmodified over both `models` packages from the same checkpoints —
+    loaded through the reference's own utils/model_saver_iter.load_model: every image the script writes (uint8 after
+    imagenet_deprocess_batch) must agree to 1 grey level and every printed statistic must be identical."""
+    outs, imgs = {}, {}
+    for impl in ("reference", "b200-emul"):
+        p = subprocess.Popen([sys.executable, os.path.join(HERE, "ref_harness.py"), "--impl", impl, "--script", "test",
+                              "--out", str(tmp_path / impl), "--niter", "2", "--batch", "3"], stdout=subprocess.PIPE,
+                             stderr=subprocess.STDOUT, text=True)
+        outs[impl], _ = p.communicate(timeout=1500)
+        assert p.returncode == 0 and "HARNESS_DONE images=24" in outs[impl], outs[impl][-3000:]
+        imgs[impl] = torch.load(str(tmp_path / impl / "written_images.pt"))
+
+    def stats(text):
+        lines = text.splitlines()
+        i0 = next(i for i, l in enumerate(lines) if l.startswith("average precision"))
+        return [l for l in lines[i0:] if not l.startswith("HARNESS_DONE")]
+
+    assert stats(outs["reference"]) == stats(outs["b200-emul"])
+    a, r = imgs["b200-emul"], imgs["reference"]
+    assert sorted(a) == sorted(r) and len(r) == 24
+    for k in r:
+        assert a[k].dtype == torch.uint8 and a[k].shape == r[k].shape == (64, 64, 3)
+        assert int((a[k].int() - r[k].int()).abs().max()) <= 1, k
+    assert float(r["img000000_rand.png"].float().std()) > 1.0                    # real pictures, not constants
+    assert not torch.equal(r["img000000_rand.png"], r["img000000_rec.png"])
