@@ -146,6 +146,43 @@ class Kernels:
         self._check(self.lib.b200_shift_boxes(_ptr(boxes), boxes.shape[0], _ptr(out), _stream()), "b200_shift_boxes")
         return out
 
+    # ---- masks_to_layout ---------------------------------------------------------------------------------
+    def m2l_taps(self, boxes, linx, liny, M):
+        O_, H, W = boxes.shape[0], liny.numel(), linx.numel()
+        dev = boxes.device
+        ix0 = torch.empty((O_, W), dtype=torch.int32, device=dev)
+        iy0 = torch.empty((O_, H), dtype=torch.int32, device=dev)
+        fx = torch.empty((O_, W), dtype=torch.float32, device=dev)
+        fy = torch.empty((O_, H), dtype=torch.float32, device=dev)
+        self._check(self.lib.b200_masks_to_layout_taps(_ptr(boxes), _ptr(linx), _ptr(liny), _ptr(ix0), _ptr(iy0), _ptr(fx),
+                                                       _ptr(fy), int(M), H, W, O_, _stream()), "b200_masks_to_layout_taps")
+        return ix0, iy0, fx, fy
+
+    def m2l_fwd(self, vecs, boxes, masks, img_obj_start, obj_order, linx, liny, N):
+        O_, D = vecs.shape
+        M, H, W = masks.shape[-1], liny.numel(), linx.numel()
+        for t in (vecs, boxes, masks):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise B200Error("masks_to_layout: contiguous fp32 tensors required")
+        out = torch.empty((N, D, H, W), dtype=torch.float32, device=vecs.device)
+        self._check(self.lib.b200_masks_to_layout_fwd(_ptr(vecs), _ptr(boxes), _ptr(masks), _ptr(img_obj_start),
+                                                      _ptr(obj_order), _ptr(linx), _ptr(liny), _ptr(out), int(N), O_, D, M,
+                                                      H, W, _stream()), "b200_masks_to_layout_fwd")
+        return out
+
+    def m2l_bwd(self, dout, vecs, boxes, masks, obj_to_img, linx, liny, need_vecs=True, need_masks=True):
+        O_, D = vecs.shape
+        N, _, H, W = dout.shape
+        M = masks.shape[-1]
+        dev = vecs.device
+        dvecs = torch.empty((O_, D), dtype=torch.float32, device=dev) if need_vecs else None
+        dmasks = torch.empty((O_, M, M), dtype=torch.float32, device=dev) if need_masks else None
+        ws = torch.empty((O_ * H * W,), dtype=torch.float32, device=dev) if need_masks else None
+        self._check(self.lib.b200_masks_to_layout_bwd(_ptr(dout), _ptr(vecs), _ptr(boxes), _ptr(masks), _ptr(obj_to_img),
+                                                      _ptr(linx), _ptr(liny), _ptr(dvecs), _ptr(dmasks), _ptr(ws), N, O_, D,
+                                                      M, H, W, _stream()), "b200_masks_to_layout_bwd")
+        return dvecs, dmasks
+
     # ---- crops ----------------------------------------------------------------------------------------
     def crop_fwd(self, feats, boxes, box_to_img, wx, wy, HH, WW):
         N, Cc, H, W = feats.shape

@@ -47,6 +47,25 @@ int64_t b200_launch_count(void);
 int b200_rasterize_boxes(const float* boxes, int O, int H, int W, float* masks, b200_stream_t stream);
 int b200_shift_boxes(const float* boxes, int O, float* out, b200_stream_t stream);
 
+/* masks_to_layout — the scatter-sum object layout the reference calls at utils/draw_box.py:482-483
+ * (`masks_to_layout(vecs, boxes, masks, obj_to_img, H=..., N=...)`; the definition is sg2im's layout.py, not shipped in the
+ * reference tree — see oracle/layout_oracle.py): out (N,D,H,W) fp32,
+ *   out[n,d,y,x] = sum over the objects o of image n (ascending) of vecs[o,d] * bilinear(masks[o] (M,M), grid_o(y,x)),
+ * grid_o from the box [x0,y0,x1,y1] as X = (linspace(0,1,W)[x] - x0)/(x1 - x0) (zeros padding, align_corners=False).
+ * linx (W) / liny (H): torch.linspace(0,1,.) built on the CPU by the caller (the reference's tables, bit for bit).
+ * img_obj_start (N+1) / obj_order (O): objects grouped by image, ascending inside an image; obj_to_img (O) int32.
+ * vecs (O,D) with D % 4 == 0.  Deterministic gather (no atomics); floors / in-bounds predicates bit-exact
+ * (b200_masks_to_layout_taps exposes them: ix0 (O,W), iy0 (O,H) int32 and the fractional weights).
+ * bwd: dvecs (O,D) and/or dmasks (O,M,M) (either may be NULL); ws: O*H*W floats (needed for dmasks). */
+int b200_masks_to_layout_taps(const float* boxes, const float* linx, const float* liny, int32_t* ix0, int32_t* iy0,
+                              float* fx, float* fy, int M, int H, int W, int O, b200_stream_t stream);
+int b200_masks_to_layout_fwd(const float* vecs, const float* boxes, const float* masks, const int32_t* img_obj_start,
+                             const int32_t* obj_order, const float* linx, const float* liny, float* out, int N, int O,
+                             int D, int M, int H, int W, b200_stream_t stream);
+int b200_masks_to_layout_bwd(const float* dout, const float* vecs, const float* boxes, const float* masks,
+                             const int32_t* obj_to_img, const float* linx, const float* liny, float* dvecs, float* dmasks,
+                             float* ws, int N, int O, int D, int M, int H, int W, b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Box crops — replaces models/bilinear.py:26-41,67-104,107-136 (crop_bbox_batch -> F.grid_sample,
  * bilinear, zeros padding, align_corners=False) and its autograd backward.

@@ -219,3 +219,86 @@ def test_adam_save_load_step_parity():
     both(1)
     for a, b in zip(ref, mine):
         assert rel(b, a) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# masks_to_layout (config 5; utils/draw_box.py:482-483) against oracle/layout_oracle.py
+# ---------------------------------------------------------------------------------------------------------
+def _m2l_inputs(seed, N, per_image, D, M, ragged=False):
+    from oracle import layout_oracle as LO  # noqa: F401
+    g = torch.Generator().manual_seed(seed)
+    counts = [int(torch.randint(0, per_image + 1, (1,), generator=g)) if ragged else per_image for _ in range(N)]
+    if ragged:
+        counts[0] = 0                       # an image without objects stays all zero
+        counts[-1] = max(counts[-1], 33)    # more than one 32-object pass
+    O_ = sum(counts)
+    o2i = torch.cat([torch.full((c,), i, dtype=torch.long) for i, c in enumerate(counts)]) if O_ else torch.zeros(0, dtype=torch.long)
+    xy0 = torch.rand(O_, 2, generator=g) * 0.7
+    wh = torch.rand(O_, 2, generator=g) * 0.5 + 0.05
+    boxes = torch.cat([xy0, (xy0 + wh).clamp(max=1.0)], 1)
+    if O_ > 3:
+        boxes[0] = torch.tensor([0.0, 0.0, 1.0, 1.0])
+        boxes[1] = torch.tensor([0.25, 0.5, 0.75, 1.0])
+        boxes[2] = torch.tensor([-0.1, 0.2, 0.4, 1.3])          # partly outside the canvas
+    vecs = torch.randn(O_, D, generator=g)
+    masks = torch.rand(O_, M, M, generator=g)
+    return vecs, boxes, masks, o2i
+
+
+@pytest.mark.parametrize("N,per_image,D,M,H,ragged", [(4, 8, 128, 16, 128, False), (3, 30, 64, 16, 64, False),
+                                                      (5, 12, 8, 7, 33, True), (2, 5, 4, 1, 16, False)])
+def test_masks_to_layout_matches_restatement(N, per_image, D, M, H, ragged):
+    from oracle import layout_oracle as LO
+    vecs, boxes, masks, o2i = _m2l_inputs(N * 7 + D, N, per_image, D, M, ragged)
+    W = H if H != 33 else 20
+    # index work: bit-exact
+    ix0, iy0, fx, fy = layout.masks_to_layout_taps(boxes.cuda(), M, H, W)
+    rx0, ry0, rfx, rfy = LO.layout_taps(boxes, M, H, W)
+    assert torch.equal(ix0.cpu(), rx0) and torch.equal(iy0.cpu(), ry0)
+    assert torch.equal(fx.cpu(), rfx) and torch.equal(fy.cpu(), rfy)
+    # forward + gradients w.r.t. the embeddings and the masks
+    v, m = vecs.clone().requires_grad_(True), masks.clone().requires_grad_(True)
+    want = LO.masks_to_layout(v, boxes, m, o2i, H, W, N=N)
+    gw = torch.randn(want.shape, generator=torch.Generator().manual_seed(1))
+    (want * gw).sum().backward()
+    vc, mc = vecs.cuda().requires_grad_(True), masks.cuda().requires_grad_(True)
+    got = layout.masks_to_layout(vc, boxes.cuda(), mc, o2i, H, W, N=N)
+    assert got.shape == want.shape
+    assert float((got.cpu() - want.detach()).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max()))
+    (got * gw.cuda()).sum().backward()
+    assert rel(vc.grad, v.grad) < 1e-5 and rel(mc.grad, m.grad) < 1e-5
+    # deterministic: a second evaluation is bit-identical (gather, fixed-order reductions)
+    vc2, mc2 = vecs.cuda().requires_grad_(True), masks.cuda().requires_grad_(True)
+    got2 = layout.masks_to_layout(vc2, boxes.cuda(), mc2, o2i, H, W, N=N)
+    (got2 * gw.cuda()).sum().backward()
+    assert torch.equal(got2, got) and torch.equal(vc2.grad, vc.grad) and torch.equal(mc2.grad, mc.grad)
+
+
+def test_masks_to_layout_full_size_properties():
+    """config 5 at full size (128x128, N = 32, 30 boxes per image, D = 128): the oracle would need a 32 GB (O,D,H,W)
+    intermediate, so size-independent properties: linearity in the embeddings, per-image independence, a one-hot embedding
+    reproduces the resampled mask (draw_box.py:474-484 `cropped_to_full_mask`), unsorted obj_to_img == sorted."""
+    from oracle import layout_oracle as LO
+    N, per, D, M, H = 32, 30, 128, 16, 128
+    vecs, boxes, masks, o2i = _m2l_inputs(3, N, per, D, M)
+    bc, mc = boxes.cuda(), masks.cuda()
+    a = layout.masks_to_layout(vecs.cuda(), bc, mc, o2i, H, N=N)
+    assert torch.isfinite(a).all()
+    v2 = torch.randn(vecs.shape, generator=torch.Generator().manual_seed(9))
+    b = layout.masks_to_layout(v2.cuda(), bc, mc, o2i, H, N=N)
+    ab = layout.masks_to_layout((2.0 * vecs - 0.5 * v2).cuda(), bc, mc, o2i, H, N=N)
+    assert rel(ab, 2.0 * a - 0.5 * b) < 1e-5
+    sel = o2i < 2                                                # the first two images alone give the same planes
+    part = layout.masks_to_layout(vecs[sel].cuda(), boxes[sel].cuda(), masks[sel].cuda(), o2i[sel], H, N=2)
+    assert torch.equal(part, a[:2])
+    want = LO.masks_to_layout(vecs[sel], boxes[sel], masks[sel], o2i[sel], H, N=2)
+    assert float((part.cpu() - want).abs().max()) < 1e-4
+    perm = torch.randperm(o2i.numel(), generator=torch.Generator().manual_seed(2))
+    shuf = layout.masks_to_layout(vecs[perm].cuda(), boxes[perm].cuda(), masks[perm].cuda(), o2i[perm], H, N=N)
+    assert rel(shuf, a) < 1e-6
+    eye = torch.eye(per)[:, :per]                                # one-hot "embedding" per object of image 0
+    k = int((o2i == 0).sum())
+    full = layout.masks_to_layout(torch.eye(k, 32)[:, :32].contiguous().cuda(), boxes[:k].cuda(), masks[:k].cuda(),
+                                  torch.zeros(k, dtype=torch.long), H, N=1)
+    ref = LO.masks_to_layout(torch.eye(k, 32), boxes[:k], masks[:k], torch.zeros(k, dtype=torch.long), H, N=1)
+    assert float((full.cpu() - ref).abs().max()) < 1e-5

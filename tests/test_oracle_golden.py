@@ -100,3 +100,33 @@ def test_attribute_swap_matches_reference_lines():
         assert torch.equal(att, c["attribute_out"]) and torch.equal(est, c["attribute_est_out"])
         changed = (c["attribute_out"] != c["attribute_in"]).any(1).nonzero().view(-1)
         assert set(changed.tolist()) <= set(rows.tolist())
+
+
+def test_masks_to_layout_restatement_is_self_consistent():
+    """oracle/layout_oracle.py (sg2im semantics; the reference ships only the call site, utils/draw_box.py:482-483): the
+    explicit integer/weight restatement (layout_taps) reproduces the grid_sample formulation, objects of different images do
+    not mix, and the result is the per-image sum of single-object layouts"""
+    from oracle import layout_oracle as LO
+    g = torch.Generator().manual_seed(0)
+    O_, D, M, H, W = 5, 3, 4, 9, 7
+    vecs, masks = torch.randn(O_, D, generator=g), torch.rand(O_, M, M, generator=g)
+    xy0 = torch.rand(O_, 2, generator=g) * 0.5
+    boxes = torch.cat([xy0, xy0 + 0.2 + 0.3 * torch.rand(O_, 2, generator=g)], 1)
+    o2i = torch.tensor([0, 0, 2, 2, 2])
+    out = LO.masks_to_layout(vecs, boxes, masks, o2i, H, W, N=3)
+    assert out.shape == (3, D, H, W) and float(out[1].abs().max()) == 0.0
+    ix0, iy0, fx, fy = LO.layout_taps(boxes, M, H, W)
+    want = torch.zeros(3, D, H, W)
+    for o in range(O_):
+        for y in range(H):
+            for x in range(W):
+                s = 0.0
+                for (yy, wy) in ((int(iy0[o, y]), 1 - fy[o, y]), (int(iy0[o, y]) + 1, fy[o, y])):
+                    for (xx, wx) in ((int(ix0[o, x]), 1 - fx[o, x]), (int(ix0[o, x]) + 1, fx[o, x])):
+                        if 0 <= yy < M and 0 <= xx < M:
+                            s = s + float(masks[o, yy, xx]) * float(wy * wx)
+                want[o2i[o], :, y, x] += vecs[o] * s
+    assert float((out - want).abs().max()) < 1e-5
+    single = sum(LO.masks_to_layout(vecs[o:o + 1], boxes[o:o + 1], masks[o:o + 1], torch.zeros(1, dtype=torch.long), H, W, N=1)
+                 for o in (2, 3, 4))
+    assert float((single[0] - out[2]).abs().max()) < 1e-6
