@@ -146,6 +146,25 @@ class Kernels:
         self._check(self.lib.b200_shift_boxes(_ptr(boxes), boxes.shape[0], _ptr(out), _stream()), "b200_shift_boxes")
         return out
 
+    # ---- data contract ------------------------------------------------------------------------------------
+    def one_hot_attributes(self, att_idx, n_att):
+        if not att_idx.is_cuda or att_idx.dtype != torch.int64 or att_idx.dim() != 2:
+            raise B200Error("one_hot_attributes: (O,A) int64 CUDA tensor required")
+        O_, A = att_idx.shape
+        out = torch.empty((O_, n_att), dtype=torch.float32, device=att_idx.device)
+        self._check(self.lib.b200_one_hot_attributes(_ptr(att_idx), O_, A, int(n_att), _ptr(out), _stream()),
+                    "b200_one_hot_attributes")
+        return out
+
+    def imagenet_deprocess(self, imgs, inv_std, neg_mean, rescale=True):
+        N, Cc, H, W = imgs.shape
+        out = torch.empty((N, Cc, H, W), dtype=torch.uint8, device=imgs.device)
+        ws = torch.empty((2 * max(N, 1),), dtype=torch.float32, device=imgs.device)
+        self._check(self.lib.b200_imagenet_deprocess(_ptr(imgs), N, Cc, H * W, _ptr(inv_std), _ptr(neg_mean),
+                                                     int(bool(rescale)), _ptr(out), _ptr(ws), _stream()),
+                    "b200_imagenet_deprocess")
+        return out
+
     # ---- masks_to_layout ---------------------------------------------------------------------------------
     def m2l_taps(self, boxes, linx, liny, M):
         O_, H, W = boxes.shape[0], liny.numel(), linx.numel()

@@ -368,6 +368,18 @@ typedef struct {
 int b200_adam_multi(const b200_adam_entry* entries_dev, int n_entries, float* step_dev, double lr, double beta1,
                     double beta2, double eps, b200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data contract either side of the step, bit-exact integer / fp32 restatements:
+ * b200_one_hot_attributes: data/vg_custom_mask.py:160-171 — att_idx (O,A) int64, -1 terminated per row ->
+ *   out (O,n_att) fp32 multi-hot (entries after the first -1 are ignored, as the loader's while-loop does).
+ * b200_imagenet_deprocess: data/utils.py:32-66 imagenet_deprocess_batch — imgs (N,C,H*W) fp32 normalised images ->
+ *   out uint8: v = (x / inv_std[c]) - neg_mean[c]; rescale != 0: per image (v - min) / (max - min); then *255, clamp to
+ *   [0,255], truncation.  inv_std / neg_mean (C floats, device): the caller passes fp32(1/std), fp32(-mean) as the
+ *   reference builds them on the host.  ws: 2*N floats (per-image min, max). */
+int b200_one_hot_attributes(const int64_t* att_idx, int O, int A, int n_att, float* out, b200_stream_t stream);
+int b200_imagenet_deprocess(const float* imgs, int N, int C, int HW, const float* inv_std, const float* neg_mean,
+                            int rescale, uint8_t* out, float* ws, b200_stream_t stream);
+
 /* plain device-to-device copy on the stream (row concatenation of batched calls) */
 int b200_copy(void* dst, const void* src, size_t bytes, b200_stream_t stream);
 

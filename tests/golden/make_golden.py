@@ -214,9 +214,23 @@ def make_swap():
     return cases
 
 
+def make_data():
+    """data/utils.py:47-66 imagenet_deprocess_batch (imported from the reference, unmodified) on seeded images, with and
+    without the per-image rescale; plus the loader's one-hot attribute construction (vg_custom_mask.py:160-171 restated by
+    executing its own statements is not possible without h5py — the lines are quoted in the oracle instead)."""
+    from data.utils import imagenet_deprocess_batch
+    g = torch.Generator().manual_seed(11)
+    imgs = torch.randn(5, 3, 16, 12, generator=g) * 1.3
+    imgs[1] = imgs[1] * 0.01 + 0.7          # low contrast image: the rescale stretches it
+    imgs[2, :, 0, 0] = 40.0                 # outlier: everything else lands near zero
+    return dict(imgs=imgs, out_rescale=imagenet_deprocess_batch(imgs, rescale=True),
+                out_plain=imagenet_deprocess_batch(imgs, rescale=False))
+
+
 if __name__ == "__main__":
     out = os.path.dirname(os.path.abspath(__file__))
     torch.save(make_swap(), os.path.join(out, "swap.pt"))
+    torch.save(make_data(), os.path.join(out, "data.pt"))
     if "--swap-only" in sys.argv:
         sys.exit(0)
     torch.save(make_crop(), os.path.join(out, "crop.pt"))

@@ -302,3 +302,49 @@ def test_masks_to_layout_full_size_properties():
                                   torch.zeros(k, dtype=torch.long), H, N=1)
     ref = LO.masks_to_layout(torch.eye(k, 32), boxes[:k], masks[:k], torch.zeros(k, dtype=torch.long), H, N=1)
     assert float((full.cpu() - ref).abs().max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# data contract on the device: collate + one-hot attributes + imagenet_deprocess_batch
+# ---------------------------------------------------------------------------------------------------------
+def test_imagenet_deprocess_bit_exact():
+    import os
+    from b200gan import data
+    from helpers import GOLD
+    from oracle import data_oracle as DO
+    g = torch.load(os.path.join(GOLD, "data.pt"))                      # produced by the unmodified data/utils.py
+    assert torch.equal(data.imagenet_deprocess_batch(g["imgs"].cuda(), True).cpu(), g["out_rescale"])
+    assert torch.equal(data.imagenet_deprocess_batch(g["imgs"].cuda(), False).cpu(), g["out_plain"])
+    big = torch.randn(32, 3, 128, 128, generator=torch.Generator().manual_seed(5)) * 2.0
+    got = data.imagenet_deprocess_batch(big.cuda())
+    assert got.dtype == torch.uint8 and torch.equal(got.cpu(), DO.imagenet_deprocess_batch(big))
+    assert int(got.amin()) == 0 and int(got.amax()) == 255                # every image spans the full range after rescale
+
+
+def test_collate_on_device_matches_loader_restatement():
+    from b200gan import data
+    from oracle import data_oracle as DO
+    g = torch.Generator().manual_seed(8)
+    samples = []
+    for i in range(6):
+        n = int(torch.randint(3, 10, (1,), generator=g))
+        xy0 = torch.rand(n, 2, generator=g) * 0.6
+        boxes = torch.cat([xy0, (xy0 + torch.rand(n, 2, generator=g) * 0.4 + 0.05).clamp(max=1.0)], 1)
+        att = torch.full((n, 30), -1, dtype=torch.long)
+        for r in range(n):
+            k = int(torch.randint(0, 4, (1,), generator=g))
+            att[r, :k] = torch.randperm(106, generator=g)[:k]
+        att[0, 2:6] = torch.tensor([5, -1, 9, 9])                       # entries after the first -1 are ignored
+        samples.append((torch.randn(3, 64, 64, generator=g), torch.randint(1, 179, (n,), generator=g), boxes, att))
+    got = data.collate_on_device(samples, 106, "cuda")
+    want = DO.collate(samples, 106)
+    names = ("imgs", "objs", "boxes", "masks", "obj_to_img", "attribute", "masks_shift", "boxes_shift")
+    for n_, a, r in zip(names, got, want):
+        assert a.dtype == r.dtype and a.shape == r.shape, n_
+        assert torch.equal(a.cpu(), r), n_
+    assert not got[4].is_cuda and got[3].is_cuda
+    # the collated batch drives the generator exactly like a loader batch
+    ts = TrainStep(64, device="cuda")
+    out = ts.netG(got[0], got[1], got[2], got[3], got[4], torch.randn(got[1].shape[0], 64, device="cuda"), got[5], got[6],
+                  got[7], got[5])
+    assert out[4].shape == (6, 3, 64, 64) and torch.isfinite(out[4]).all()

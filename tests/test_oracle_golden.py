@@ -130,3 +130,14 @@ def test_masks_to_layout_restatement_is_self_consistent():
     single = sum(LO.masks_to_layout(vecs[o:o + 1], boxes[o:o + 1], masks[o:o + 1], torch.zeros(1, dtype=torch.long), H, W, N=1)
                  for o in (2, 3, 4))
     assert float((single[0] - out[2]).abs().max()) < 1e-6
+
+
+def test_deprocess_restatement_matches_reference_golden():
+    """data/utils.py:47-66 (unmodified reference function, make_golden.make_data) vs oracle/data_oracle.py, bit for bit"""
+    from oracle import data_oracle as DO
+    g = torch.load(os.path.join(GOLD, "data.pt"))
+    assert torch.equal(DO.imagenet_deprocess_batch(g["imgs"], True), g["out_rescale"])
+    assert torch.equal(DO.imagenet_deprocess_batch(g["imgs"], False), g["out_plain"])
+    att = torch.tensor([[3, 5, -1, 7], [-1, 2, 2, 2], [0, 105, 4, 9]])
+    oh = DO.one_hot_attributes(att, 106)
+    assert oh[0].nonzero().view(-1).tolist() == [3, 5] and float(oh[1].sum()) == 0 and oh[2].nonzero().view(-1).tolist() == [0, 4, 9, 105]
