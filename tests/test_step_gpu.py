@@ -52,17 +52,76 @@ def test_fp32_step_matches_oracle_and_reference_golden(size):
                 assert rel(v.float(), st[k].float()) < 1e-4 or float((v.float().cpu() - st[k].float()).abs().max()) < 1e-5, (name, k)
 
 
-def test_bf16_step_within_stated_bound():
-    ts, res, model, ref = _run(64, "bf16")
+def _module_cosines(named_grads, ref_grads, depth=2):
+    groups = {}
+    for k, g in named_grads:
+        groups.setdefault(".".join(k.split(".")[:depth]), []).append((g.detach().cpu().reshape(-1).double(), ref_grads[k].reshape(-1).double()))
+    out = {}
+    for m, pairs in groups.items():
+        a, r = torch.cat([p[0] for p in pairs]), torch.cat([p[1] for p in pairs])
+        out[m] = float(torch.nn.functional.cosine_similarity(a, r, dim=0))
+    return out
+
+
+@pytest.mark.parametrize("size", [64, 128])
+def test_bf16_step_within_stated_bound(size):
+    """bf16 mode (tcgen05 operands + activation storage in bf16, everything else fp32) against the fp32 oracle, 64x64 and
+    128x128.  Stated bounds: images rel-L2 <= 6e-2, losses 5e-2; discriminator gradients (D-step): per-network cosine >= 0.995
+    and every weight tensor's cosine >= 0.97; generator gradients (G-step, through three bf16 discriminators): global
+    cosine >= 0.85 and every sub-module's cosine >= 0.80.  Reference level: the reference algorithm under torch's own bf16
+    autocast reaches 0.867 / 3.6e-2 on this step (tests/test_wiring_cpu.py::test_step_wiring_bf16_operand_routing)."""
+    ts, res, model, ref = _run(size, "bf16")
     for i in (4, 5, 6):
         assert rel(res["out_g"][i], ref["out_g"][i]) < 6e-2
+    for i in (7, 8, 9, 10):
+        assert rel(res["out_g"][i], ref["out_g"][i]) < 8e-2
     assert abs(float(res["d_loss"]) - float(ref["d_loss"])) < 5e-2 * abs(float(ref["d_loss"]))
     assert abs(float(res["g_loss"]) - float(ref["g_loss"])) < 5e-2 * abs(float(ref["g_loss"]))
+    cosf = torch.nn.functional.cosine_similarity
+    for name, net in (("D_img", ts.netD_image), ("D_obj", ts.netD_object), ("D_att", ts.netD_att)):
+        a = torch.cat([p.grad.reshape(-1).cpu() for _, p in net.named_parameters()]).double()
+        r = torch.cat([ref["d_grads"][name][k].reshape(-1) for k, _ in net.named_parameters()]).double()
+        c = float(cosf(a, r, dim=0))
+        print("bf16 %d: %s D-step gradient cosine %.5f" % (size, name, c))
+        assert c > 0.995, (name, c)
+        for k, p in net.named_parameters():
+            r = ref["d_grads"][name][k]
+            if k.endswith("weight_orig") and float(r.norm()) > 1e-6:
+                ck = float(cosf(p.grad.reshape(-1).cpu().double(), r.reshape(-1).double(), dim=0))
+                assert ck > 0.97, (name, k, ck)
     ga = torch.cat([p.grad.reshape(-1).cpu() for _, p in ts.netG.named_parameters()]).double()
     gr = torch.cat([ref["g_grads"][k].reshape(-1) for k, _ in ts.netG.named_parameters()]).double()
-    cos = float(torch.nn.functional.cosine_similarity(ga, gr, dim=0))
-    print("bf16 64: G-grad cosine %.5f" % cos)
+    cos = float(cosf(ga, gr, dim=0))
+    per = _module_cosines([(k, p.grad) for k, p in ts.netG.named_parameters()], ref["g_grads"])
+    worst = min(per.items(), key=lambda kv: kv[1])
+    print("bf16 %d: G-grad cosine %.5f; worst sub-module %s %.4f" % (size, cos, worst[0], worst[1]))
     assert cos > 0.85
+    assert worst[1] > 0.80, worst
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_config2_full_size_against_oracle(precision):
+    """BASELINE config 2 at FULL size (64x64, batch 32, 8 objects/image = 256 objects) against the CPU oracle (~25 s on the
+    host cores): outputs, losses, all parameter gradients.  fp32: images 1e-4, losses 1e-4, per-network gradient cosine >=
+    0.9999 (D) / 0.999 (G); bf16: the bounds of test_bf16_step_within_stated_bound."""
+    ts, res, model, ref = _run(64, precision, n_images=32, batch_seed=3, objs_per_image=8)
+    fp32 = precision == "fp32"
+    for i in range(11):
+        assert rel(res["out_g"][i], ref["out_g"][i]) < (1e-4 if fp32 else 8e-2), i
+    for k in ("d_loss", "g_loss"):
+        assert abs(float(res[k]) - float(ref[k])) < (1e-4 if fp32 else 5e-2) * abs(float(ref[k])), k
+    cosf = torch.nn.functional.cosine_similarity
+    for name, net in (("D_img", ts.netD_image), ("D_obj", ts.netD_object), ("D_att", ts.netD_att)):
+        a = torch.cat([p.grad.reshape(-1).cpu() for _, p in net.named_parameters()]).double()
+        r = torch.cat([ref["d_grads"][name][k].reshape(-1) for k, _ in net.named_parameters()]).double()
+        c = float(cosf(a, r, dim=0))
+        print("config 2 %s: %s gradient cosine %.6f" % (precision, name, c))
+        assert c > (0.9999 if fp32 else 0.995), (name, c)
+    ga = torch.cat([p.grad.reshape(-1).cpu() for _, p in ts.netG.named_parameters()]).double()
+    gr = torch.cat([ref["g_grads"][k].reshape(-1) for k, _ in ts.netG.named_parameters()]).double()
+    c = float(cosf(ga, gr, dim=0))
+    print("config 2 %s: G gradient cosine %.6f" % (precision, c))
+    assert c > (0.999 if fp32 else 0.85)
 
 
 @pytest.mark.parametrize("optimizer", ["b200", "torch_fused", "torch"])

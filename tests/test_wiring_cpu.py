@@ -100,7 +100,21 @@ def test_step_wiring_bf16_operand_routing(emul):
         assert float(cos(a, r, dim=0)) > 0.995, name
     a = torch.cat([p.grad.reshape(-1) for _, p in ts.netG.named_parameters()]).double()
     r = torch.cat([ref["g_grads"][k].reshape(-1) for k, _ in ts.netG.named_parameters()]).double()
-    assert float(cos(a, r, dim=0)) > 0.85
+    ours = float(cos(a, r, dim=0))
+    assert ours > 0.85
+    # What bf16 costs the REFERENCE ALGORITHM itself: the same step through the oracle under torch's CPU bf16 autocast
+    # (bf16 conv / linear operands and activations, fp32 accumulate) against the fp32 oracle.  Measured: generator-gradient
+    # cosine 0.867, images 3.6e-2 — the end-to-end gradient through three discriminators and ~60 ReLU layers is this
+    # sensitive to 8-bit mantissas (SURVEY.md App. D's 0.970 was taken on a 4-term loss).  The b200 bf16 mode (fp32
+    # statistics, modulation, 1/sigma, cell state and losses; bf16 only as GEMM operand / activation storage) must not be
+    # worse than that level.
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        ac = oracle_step(O.OracleModel(64, 0, states), batch)
+    a2 = torch.cat([ac["g_grads"][k].reshape(-1).float() for k, _ in ts.netG.named_parameters()]).double()
+    autocast = float(cos(a2, r, dim=0))
+    print("generator-gradient cosine vs fp32 oracle: b200 bf16 mode %.4f | reference under bf16 autocast %.4f" % (ours, autocast))
+    assert ours >= autocast - 0.01
+    assert rel(res["out_g"][4], ref["out_g"][4]) <= rel(ac["out_g"][4].float(), ref["out_g"][4]) + 5e-3
 
 
 @pytest.mark.parametrize("optimizer", ["torch_fused", "torch"])
