@@ -22,7 +22,7 @@ def _worker(rank, world, port, out):
     broadcast_module(net)
     unused = torch.nn.Linear(3, 3)     # a parameter that never receives a gradient
     params = list(net.parameters()) + list(unused.parameters())
-    bk = GradBucketer(params, bucket_bytes=256)
+    bk = GradBucketer(params, bucket_bytes=256, tail_bytes=200)
     assert len(bk.buckets) >= 3
     g = torch.Generator().manual_seed(42)
     x = torch.randn(8, 16, generator=g)
@@ -66,3 +66,76 @@ def test_shard_images_partition():
         spans = [shard_images(n, r, w) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _step_worker(rank, world, port, out_dir, backend="gloo"):
+    """one rank of a data-parallel G+D step: its shard of the batch, bucketed all-reduce.  gloo: the CPU emulation of the
+    kernels; nccl: the CUDA kernels on device `rank` (tests/test_ddp_gpu.py)"""
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    from b200gan import _lib
+    if backend == "gloo":
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.set_num_threads(max(1, (os.cpu_count() or 2) // world))
+        from abi_emul import EmulKernels
+        _lib.K = EmulKernels()
+        device = "cpu"
+    else:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        device = "cuda:%d" % rank
+    from b200gan.step import TrainStep
+    from helpers import load_states
+    from oracle import gan_oracle as O
+    states = O.make_states(64, 0 if rank == 0 else 5)      # rank 1 starts from OTHER weights: the broadcast must fix that
+    ts = TrainStep(64, device=device, optimizer="torch" if backend == "gloo" else "b200")
+    load_states(ts, states)
+    ts.enable_data_parallel(bucket_bytes=8 << 20)
+    batch = O.synth_batch(1, 64, 4, 20 + rank)              # one image per rank (objects travel with their image)
+    res = ts.step(ts.to_device(batch), optimizer_step=False, seeds=(123 + rank, 223 + rank))
+    grads = {n: {k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()} for n, net in
+             (("G", ts.netG), ("D_img", ts.netD_image), ("D_obj", ts.netD_object), ("D_att", ts.netD_att))}
+    torch.save(dict(grads=grads, d_loss=float(res["d_loss"]), g_loss=float(res["g_loss"])), os.path.join(out_dir, "rank%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def check_against_shard_oracles(tmp_path):
+    _check(tmp_path)
+
+
+def test_data_parallel_step_world2_matches_mean_of_shard_oracles(tmp_path):
+    """the data-parallel target is mean_r(grad_ref(shard_r)) — the CPU oracle run on each shard — for the D
+    gradients after d_loss.backward() and the G gradients after g_loss.backward(); both ranks must hold the same reduced
+    gradients.  (The G+D step itself, not a toy network: every parameter of the four networks goes through the buckets.)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_step, rel
+    from oracle import gan_oracle as O
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_step_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    _check(tmp_path)
+
+
+def _check(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_step, rel
+    from oracle import gan_oracle as O
+    r0, r1 = torch.load(str(tmp_path / "rank0.pt")), torch.load(str(tmp_path / "rank1.pt"))
+    states = O.make_states(64, 0)
+    refs = [oracle_step(O.OracleModel(64, 0, states), O.synth_batch(1, 64, 4, 20 + r), seeds=(123 + r, 223 + r)) for r in range(2)]
+    assert abs(r0["d_loss"] - float(refs[0]["d_loss"])) < 1e-4 * abs(float(refs[0]["d_loss"]))
+    assert abs(r1["g_loss"] - float(refs[1]["g_loss"])) < 1e-4 * abs(float(refs[1]["g_loss"]))
+    cosf = torch.nn.functional.cosine_similarity
+    for net in ("G", "D_img", "D_obj", "D_att"):
+        a, b, m = [], [], []
+        for k, g0 in r0["grads"][net].items():
+            assert torch.equal(g0, r1["grads"][net][k]), (net, k)            # identical on both ranks after the all-reduce
+            want = 0.5 * ((refs[0]["g_grads"][k] + refs[1]["g_grads"][k]) if net == "G" else
+                          (refs[0]["d_grads"][net][k] + refs[1]["d_grads"][net][k]))
+            a.append(g0.reshape(-1).double())
+            m.append(want.reshape(-1).double())
+        c = float(cosf(torch.cat(a), torch.cat(m), dim=0))
+        assert c > (0.9999 if net != "G" else 0.999), (net, c)
+        assert rel(torch.cat(a), torch.cat(m)) < (1e-3 if net != "G" else 5e-2), net
