@@ -255,14 +255,34 @@ class Kernels:
                     "b200_rowsum")
         return out
 
-    def conv_gemm(self, desc: ConvDesc, inp, wmat, bias, scale, out, tc: bool, mask=None):
-        """mask (tcgen05 path only): tensor laid out like `out`; outputs are zeroed where it is not > 0"""
+    def conv_gemm(self, desc: ConvDesc, inp, wmat, bias, scale, out, tc, mask=None):
+        """tc: 0 = fp32 CUDA-core kernel, 1 = tcgen05 bf16 operands, 2 = tcgen05 tf32 (fp32 tensors; falls back to the CUDA-core
+        kernel for gathers the TMA im2col mode cannot express).  mask (tcgen05 paths only): tensor laid out like `out`;
+        outputs are zeroed where it is not > 0"""
+        tc = int(tc)
         if mask is not None:
             if not tc or mask.dtype != out.dtype or mask.shape != out.shape or not mask.is_contiguous():
                 raise B200Error("conv_gemm: relu mask must match the output (tcgen05 path)")
             desc.relu_mask = mask.data_ptr()
         else:
             desc.relu_mask = None
+        if tc == 2:
+            if inp.dtype != torch.float32 or wmat.dtype != torch.float32 or out.dtype != torch.float32:
+                raise B200Error("conv_gemm(tf32): fp32 activation, weight matrix and output required")
+            if not self.lib.b200_conv_tf32_ok(C.byref(desc), 0):
+                if mask is not None:
+                    raise B200Error("conv_gemm(tf32): the fused ReLU mask needs the tcgen05 path")
+                tc = 0
+            else:
+                splits = int(self.lib.b200_conv_tf32_splits(C.byref(desc)))
+                ws = None
+                if splits > 1:
+                    nt = self.conv_tc_ntile(desc.Cout)
+                    ldo = (desc.Cout + nt - 1) // nt * nt
+                    ws = torch.empty((splits * desc.B * desc.Qh * desc.Qw * ldo,), dtype=torch.float32, device=inp.device)
+                self._check(self.lib.b200_conv_gemm_tf32(C.byref(desc), _ptr(inp), _ptr(wmat), _ptr(bias), _ptr(scale),
+                                                         _ptr(out), _ptr(ws), splits, _stream()), "b200_conv_gemm_tf32")
+                return
         if not tc:
             self._check(self.lib.b200_conv_gemm_f32(C.byref(desc), _ptr(inp), _dt(inp), _ptr(wmat), _ptr(bias), _ptr(scale),
                                                     _ptr(out), _dt(out), _stream()), "b200_conv_gemm_f32")
@@ -292,9 +312,18 @@ class Kernels:
     def conv_tc_ntile(self, cout: int) -> int:
         return int(self.lib.b200_conv_tc_ntile(int(cout)))
 
-    def wgrad_gemm(self, desc: ConvDesc, P, G, ws, splits: int, tc: bool):
-        if tc and (P.dtype != torch.bfloat16 or G.dtype != torch.bfloat16):
+    def wgrad_gemm(self, desc: ConvDesc, P, G, ws, splits: int, tc):
+        tc = int(tc)
+        if tc == 1 and (P.dtype != torch.bfloat16 or G.dtype != torch.bfloat16):
             raise B200Error("wgrad_gemm(tc): both operands must be bf16 (use cast_bf16)")
+        if tc == 2:
+            if P.dtype != torch.float32 or G.dtype != torch.float32:
+                raise B200Error("wgrad_gemm(tf32): fp32 operands required")
+            if self.lib.b200_conv_tf32_ok(C.byref(desc), 1):
+                self._check(self.lib.b200_wgrad_gemm_tf32(C.byref(desc), _ptr(P), _ptr(G), _ptr(ws), int(splits), _stream()),
+                            "b200_wgrad_gemm_tf32")
+                return
+            tc = 0
         if tc:
             self._check(self.lib.b200_wgrad_gemm_tc(C.byref(desc), _ptr(P), _ptr(G), _ptr(ws), int(splits), _stream()),
                         "b200_wgrad_gemm_tc")

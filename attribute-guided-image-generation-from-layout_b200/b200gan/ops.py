@@ -22,7 +22,9 @@ SN_EPS = 1e-12
 
 # ----------------------------------------------------------------------------------------------------------
 # precision policy: "fp32" = CUDA-core fp32 gather-GEMMs (tight parity); "bf16" = tcgen05 bf16 operands with
-# fp32 accumulation wherever the layer shape is eligible (channels % 64 == 0, channel-last), fp32 otherwise.
+# fp32 accumulation wherever the layer shape is eligible (channels % 64 == 0, channel-last), fp32 otherwise;
+# "tf32" = fp32 tensors in memory, tcgen05 kind::tf32 GEMMs (operands rounded to a 10-bit mantissa on the way into shared
+# memory, fp32 accumulation) where channels % 32 == 0 — BASELINE config 2's "fp32" half on the tensor cores.
 # ----------------------------------------------------------------------------------------------------------
 _PRECISION = "fp32"
 _CACHE_EPOCH = 0
@@ -30,8 +32,8 @@ _CACHE_EPOCH = 0
 
 def set_precision(p: str):
     global _PRECISION
-    if p not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if p not in ("fp32", "bf16", "tf32"):
+        raise ValueError("precision must be 'fp32', 'tf32' or 'bf16'")
     _PRECISION = p
 
 
@@ -224,30 +226,50 @@ def install_optimizer_hook():
         _HOOK_HANDLE = register_optimizer_step_post_hook(_optimizer_post_step)
 
 
-def _tc_fwd_ok(g: ConvGeom, x_layout: str) -> bool:
-    return _PRECISION == "bf16" and x_layout == "cl" and g.Cx % 64 == 0
+TC_NONE, TC_BF16, TC_TF32 = 0, 1, 2     # GEMM kernel family of a launch: CUDA-core fp32 | tcgen05 bf16 | tcgen05 tf32
 
 
-def _tc_dgrad_ok(g: ConvGeom, dy_layout: str) -> bool:
-    return _PRECISION == "bf16" and dy_layout == "cl" and g.Cy % 64 == 0
+def _tc_kind() -> int:
+    return TC_BF16 if _PRECISION == "bf16" else (TC_TF32 if _PRECISION == "tf32" else TC_NONE)
 
 
-def _tc_wgrad_ok(g: ConvGeom, x_layout: str, dy_layout: str) -> bool:
-    return _PRECISION == "bf16" and x_layout == "cl" and dy_layout == "cl" and g.Cx % 64 == 0 and g.Cy % 64 == 0
+def _kalign(kind: int) -> int:
+    """channels per 128-byte operand row: the K granularity of the tcgen05 kernels"""
+    return 64 if kind == TC_BF16 else 32
+
+
+def tc_operand(x: torch.Tensor, kind: int) -> torch.Tensor:
+    """the activation operand a tcgen05 GEMM of `kind` consumes: a bf16 copy (TC_BF16) or the fp32 tensor itself"""
+    return as_bf16(x) if kind == TC_BF16 else x
+
+
+def _tc_fwd_ok(g: ConvGeom, x_layout: str) -> int:
+    k = _tc_kind()
+    return k if (k and x_layout == "cl" and g.Cx % _kalign(k) == 0) else TC_NONE
+
+
+def _tc_dgrad_ok(g: ConvGeom, dy_layout: str) -> int:
+    k = _tc_kind()
+    return k if (k and dy_layout == "cl" and g.Cy % _kalign(k) == 0) else TC_NONE
+
+
+def _tc_wgrad_ok(g: ConvGeom, x_layout: str, dy_layout: str) -> int:
+    k = _tc_kind()
+    return k if (k and x_layout == "cl" and dy_layout == "cl" and g.Cx % _kalign(k) == 0 and g.Cy % _kalign(k) == 0) else TC_NONE
 
 
 def _pack_fwd(g: ConvGeom, srcs, tc: bool, recipes: List[PackRecipe]):
     """wmat[co][(ky*kw+kx)*Cx + c] = w[co, cx_offset+c, ky, kx]; w = srcs concatenated along dim 0"""
     K = g.kh * g.kw * g.Cx
-    ldw = _rup(K, 64) if tc else _rup(K, 4)
+    ldw = _rup(K, _kalign(tc)) if tc else _rup(K, 4)
     mpad = _rup(g.Cy, _lib.K.conv_tc_ntile(g.Cy)) if tc else g.Cy
-    dst = torch.zeros((mpad, ldw), dtype=torch.bfloat16 if tc else torch.float32, device=srcs[0].device)
+    dst = torch.zeros((mpad, ldw), dtype=torch.bfloat16 if tc == TC_BF16 else torch.float32, device=srcs[0].device)
     kk = g.kh * g.kw
     row = 0
     for i, w in enumerate(srcs):
         rows = w.shape[0]
         last = i == len(srcs) - 1
-        r = PackRecipe(w, g.cx_offset * kk, dst, row, tc, rows, (mpad - row) if last else rows, g.kh, g.kw, g.Cx, ldw,
+        r = PackRecipe(w, g.cx_offset * kk, dst, row, tc == TC_BF16, rows, (mpad - row) if last else rows, g.kh, g.kw, g.Cx, ldw,
                        g.cx_total * kk, g.kw, 1, kk)
         r.run()
         recipes.append(r)
@@ -277,14 +299,14 @@ def _pack_dgrad(g: ConvGeom, srcs, tc: bool, recipes: List[PackRecipe]):
             packs.append(None)
             continue
         K = Th * Tw * g.Cy
-        ldw = _rup(K, 64) if tc else _rup(K, 4)
+        ldw = _rup(K, _kalign(tc)) if tc else _rup(K, 4)
         mpad = _rup(g.Cx, _lib.K.conv_tc_ntile(g.Cx)) if tc else g.Cx
-        dst = torch.zeros((mpad, ldw), dtype=torch.bfloat16 if tc else torch.float32, device=srcs[0].device)
+        dst = torch.zeros((mpad, ldw), dtype=torch.bfloat16 if tc == TC_BF16 else torch.float32, device=srcs[0].device)
         co = 0
         for w in srcs:
             rows = w.shape[0]
             whole = len(srcs) == 1
-            r = PackRecipe(w, g.cx_offset * kk, dst, 0, tc, g.Cx, mpad, Th, Tw, rows, ldw, kk, g.kw, 1, g.cx_total * kk,
+            r = PackRecipe(w, g.cx_offset * kk, dst, 0, tc == TC_BF16, g.Cx, mpad, Th, Tw, rows, ldw, kk, g.kw, 1, g.cx_total * kk,
                            ky0, kx0, g.s, 0 if whole else g.Cy, 0 if whole else co)
             r.run()
             recipes.append(r)
@@ -329,7 +351,7 @@ def conv_forward_packed(g: ConvGeom, packs: WeightPacks, w, P, N, Hy, Wy, out_la
                         out_dtype=torch.bfloat16):
     """Y = epilogue(P @ Wmat^T): the convolution as a 1x1 tcgen05 gather-GEMM over the im2col matrix P"""
     Kp = P.shape[1]
-    wmat, ldw = packs.get(("fwd", True) + g.key(), w, lambda src, rec: _pack_fwd(g, src, True, rec))
+    wmat, ldw = packs.get(("fwd", TC_BF16) + g.key(), w, lambda src, rec: _pack_fwd(g, src, TC_BF16, rec))
     assert ldw == Kp
     y, ys = _empty(N, Hy, Wy, g.Cy, out_layout, P.device, out_dtype)
     xs = cl_strides(Hy, Wy, Kp)
@@ -337,7 +359,7 @@ def conv_forward_packed(g: ConvGeom, packs: WeightPacks, w, P, N, Hy, Wy, out_la
                  tap_ox=0, Hi=Hy, Wi=Wy, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3], out_sy=1, out_sx=1,
                  out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ys[0], out_sh=ys[1], out_sw=ys[2], out_sc=ys[3], ldw=ldw,
                  relu=int(relu), scale_rows=_scale_rows(scale, N * Hy * Wy))
-    _lib.K.conv_gemm(d, P, wmat, bias, scale, y, True)
+    _lib.K.conv_gemm(d, P, wmat, bias, scale, y, TC_BF16)
     return y
 
 
@@ -348,13 +370,13 @@ def conv_wgrad_packed(g: ConvGeom, P, N, Hy, Wy, dy, dy_layout, dw: torch.Tensor
     assert Cy == g.Cy and dy.dtype == torch.bfloat16
     g1 = ConvGeom(Kp, g.Cy, 1, 1, 1, 0)
     Q = N * Hy * Wy
-    splits = _wgrad_splits(g1, Q, True)
+    splits = _wgrad_splits(g1, Q, TC_BF16)
     ws = torch.empty((splits * g.Cy * Kp,), dtype=torch.float32, device=P.device)
     xs = cl_strides(Hy, Wy, Kp)
     d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=Kp, Cout=g.Cy, Th=1, Tw=1, in_sy=1, in_sx=1, tap_sy=1, tap_sx=1, tap_oy=0,
                  tap_ox=0, Hi=Hy, Wi=Wy, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3], out_sy=1, out_sx=1,
                  out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ds[0], out_sh=ds[1], out_sw=ds[2], out_sc=ds[3], ldw=Kp, relu=0)
-    _lib.K.wgrad_gemm(d, dy, P, ws, splits, True)
+    _lib.K.wgrad_gemm(d, dy, P, ws, splits, TC_BF16)
     tmp = torch.empty((g.Cy, Kp), dtype=torch.float32, device=P.device)
     _lib.K.wgrad_reduce(ws, splits, g.Cy, 1, 1, Kp, tmp, 0, Kp, 0, 0, 1)
     K = g.kh * g.kw * g.Cx
@@ -382,25 +404,25 @@ def conv_backward_packed_out(g: ConvGeom, packs: WeightPacks, w, x, x_dims, dy, 
     ps = cl_strides(Hx, Wx, Kp)
     dx = dw = None
     if need_dx:
-        wmat, ldw = packs.get(("dgrad", True) + g.key(), w, lambda src, rec: _pack_dgrad(g, src, True, rec))[0]
+        wmat, ldw = packs.get(("dgrad", TC_BF16) + g.key(), w, lambda src, rec: _pack_dgrad(g, src, TC_BF16, rec))[0]
         assert ldw == Kp
         dx, xs = _empty(N, Hx, Wx, Cx, "cl", dy.device, x_dtype)
         d = ConvDesc(B=N, Qh=Hx, Qw=Wx, Cin=Kp, Cout=Cx, Th=1, Tw=1, in_sy=1, in_sx=1, tap_sy=1, tap_sx=1, tap_oy=0,
                      tap_ox=0, Hi=Hx, Wi=Wx, up_shift=0, in_sn=ps[0], in_sh=ps[1], in_sw=ps[2], in_sc=ps[3], out_sy=1,
                      out_sx=1, out_oy=0, out_ox=0, Ho=Hx, Wo=Wx, out_sn=xs[0], out_sh=xs[1], out_sw=xs[2], out_sc=xs[3],
                      ldw=ldw, relu=0, scale_rows=_scale_rows(scale, N * Hx * Wx))
-        _lib.K.conv_gemm(d, P, wmat, None, scale, dx, True)
+        _lib.K.conv_gemm(d, P, wmat, None, scale, dx, TC_BF16)
     if need_dw:
         xb = as_bf16(x)
         xs = cl_strides(Hx, Wx, Cx)
         g1 = ConvGeom(Kp, Cx, 1, 1, 1, 0)
-        splits = _wgrad_splits(g1, N * Hx * Wx, True)
+        splits = _wgrad_splits(g1, N * Hx * Wx, TC_BF16)
         ws = torch.empty((splits * Cx * Kp,), dtype=torch.float32, device=dy.device)
         d = ConvDesc(B=N, Qh=Hx, Qw=Wx, Cin=Kp, Cout=Cx, Th=1, Tw=1, in_sy=1, in_sx=1, tap_sy=1, tap_sx=1, tap_oy=0,
                      tap_ox=0, Hi=Hx, Wi=Wx, up_shift=0, in_sn=ps[0], in_sh=ps[1], in_sw=ps[2], in_sc=ps[3], out_sy=1,
                      out_sx=1, out_oy=0, out_ox=0, Ho=Hx, Wo=Wx, out_sn=xs[0], out_sh=xs[1], out_sw=xs[2], out_sc=xs[3],
                      ldw=Kp, relu=0)
-        _lib.K.wgrad_gemm(d, xb, P, ws, splits, True)
+        _lib.K.wgrad_gemm(d, xb, P, ws, splits, TC_BF16)
         tmp = torch.empty((Cx, Kp), dtype=torch.float32, device=dy.device)
         _lib.K.wgrad_reduce(ws, splits, Cx, 1, 1, Kp, tmp, 0, Kp, 0, 0, 1)
         dw = torch.empty_like(w)
@@ -416,8 +438,7 @@ def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bi
     Hy, Wy = g.out_hw(Hx, Wx)
     tc = _tc_fwd_ok(g, x_layout)
     odt = _out_dtype(x, x_layout, out_dtype)
-    if tc:
-        x = as_bf16(x)
+    x = tc_operand(x, tc)
     wmat, ldw = packs.get(("fwd", tc) + g.key(), w, lambda src, rec: _pack_fwd(g, src, tc, rec))
     y, ys = _empty(N, Hy, Wy, g.Cy, out_layout, x.device, odt)
     d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=g.Cx, Cout=g.Cy, Th=g.kh, Tw=g.kw, in_sy=g.s, in_sx=g.s, tap_sy=1, tap_sx=1,
@@ -436,8 +457,7 @@ def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layo
     Hx, Wx = x_hw
     tc = _tc_dgrad_ok(g, dy_layout)
     odt = _out_dtype(dy, dy_layout, out_dtype)
-    if tc:
-        dy = as_bf16(dy)
+    dy = tc_operand(dy, tc)
     phase_packs = packs.get(("dgrad", tc) + g.key(), w, lambda src, rec: _pack_dgrad(g, src, tc, rec))
     phases = _dgrad_phases(g)
     dx, xs = _empty(N, Hx, Wx, g.Cx, out_layout, dy.device, odt)
@@ -481,8 +501,7 @@ def conv_wgrad(g: ConvGeom, x, x_layout, dy, dy_layout, dw: torch.Tensor, accumu
     _, Hy, Wy, Cy, ds = _dims(dy, dy_layout)
     assert Cx == g.Cx and Cy == g.Cy
     tc = _tc_wgrad_ok(g, x_layout, dy_layout)
-    if tc:
-        x, dy = as_bf16(x), as_bf16(dy)
+    x, dy = tc_operand(x, tc), tc_operand(dy, tc)
     kk = g.kh * g.kw
     if not tc and g.Cy <= 8 and g.Cx > 8 and g.s == 1:
         # skinny OUTPUT side (the 64->3 image convolutions): swap the roles so the 3-channel tensor is the gathered,
@@ -526,14 +545,14 @@ def _sn_group_splits(g: ConvGeom, Q: int, groups: int) -> int:
     kk = g.kh * g.kw
     if kk > 64 or g.Cy >= 65536 or g.Cy * g.Cx * kk >= 2 ** 31 or g.cx_offset != 0 or g.cx_total != g.Cx:
         return 0
-    spg = max(1, _wgrad_splits(g, Q, True) // groups)
+    spg = max(1, _wgrad_splits(g, Q, TC_BF16) // groups)
     while spg > 1 and Qg % (64 * spg):
         spg -= 1
     return spg if Qg % (64 * spg) == 0 else 0
 
 
-def conv_wgrad_sn_grouped(g: ConvGeom, x, dy, sn: "SNCall", w, spg: int) -> torch.Tensor:
-    """dW through W / sigma_g for sn.groups batched calls (x, dy: bf16 channel-last, rows of call g contiguous): one
+def conv_wgrad_sn_grouped(g: ConvGeom, x, dy, sn: "SNCall", w, spg: int, kind: int = TC_BF16) -> torch.Tensor:
+    """dW through W / sigma_g for sn.groups batched calls (x, dy: operands of `kind`, channel-last, rows of call g contiguous): one
     tcgen05 weight-gradient launch with call-aligned pixel splits, then b200_sn_wgrad_finish"""
     N, Hx, Wx, Cx, xs = _dims(x, "cl")
     _, Hy, Wy, Cy, ds = _dims(dy, "cl")
@@ -545,7 +564,7 @@ def conv_wgrad_sn_grouped(g: ConvGeom, x, dy, sn: "SNCall", w, spg: int) -> torc
                  tap_oy=-g.p, tap_ox=-g.p, Hi=Hx, Wi=Wx, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3],
                  out_sy=1, out_sx=1, out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ds[0], out_sh=ds[1], out_sw=ds[2],
                  out_sc=ds[3], ldw=K, relu=0)
-    _lib.K.wgrad_gemm(d, dy, x, ws, splits, True)
+    _lib.K.wgrad_gemm(d, dy, x, ws, splits, kind)
     dw = torch.empty_like(w)
     return _lib.K.sn_wgrad_finish(ws, sn.groups, spg, g.Cy, kk, g.Cx, w, sn.u_hist, sn.v_hist, sn.inv, dw)
 
@@ -642,7 +661,7 @@ class _ConvFn(torch.autograd.Function):
             fwd_tc, wgrad_tc = _tc_fwd_ok(g, x_layout), _tc_wgrad_ok(g, x_layout, out_layout)
         else:
             fwd_tc, wgrad_tc = _tc_dgrad_ok(g, x_layout), _tc_wgrad_ok(g, out_layout, x_layout)
-        x_op = as_bf16(x) if fwd_tc else x      # cast once; the bf16 copy is also what a tcgen05 weight gradient consumes
+        x_op = tc_operand(x, fwd_tc)            # cast once; the bf16 copy is also what a tcgen05 weight gradient consumes
         ctx.packed = (not transposed) and _packed_ok(g) and out_layout == "cl"
         if ctx.packed:
             # few-channel input: explicit bf16 im2col matrix, kept for the weight gradient
@@ -685,7 +704,9 @@ class _ConvFn(torch.autograd.Function):
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = bias_grad(dy, ctx.out_layout)
             return dx, dw, db, None, None, None, None, None, None, None, None, None, None, None
-        dyb = as_bf16(dy) if ((need_dx and dgrad_tc) or (need_dw and (wgrad_tc or packed))) else None   # one cast for both GEMMs
+        # one cast for both GEMMs (the tf32 kernels take the fp32 gradient as it is)
+        dyb = tc_operand(dy, TC_BF16 if packed else max(dgrad_tc, wgrad_tc)) \
+            if ((need_dx and dgrad_tc) or (need_dw and (wgrad_tc or packed))) else None
         if need_dx:
             dy_op = dyb if dgrad_tc else dy
             if not ctx.transposed:
@@ -719,7 +740,7 @@ class _ConvFn(torch.autograd.Function):
             elif wgrad_tc and _sn_group_splits(g, dy_op.shape[0] * dy_op.shape[1] * dy_op.shape[2], sn.groups) > 0:
                 assert not ctx.transposed
                 spg = _sn_group_splits(g, dy_op.shape[0] * dy_op.shape[1] * dy_op.shape[2], sn.groups)
-                dw = conv_wgrad_sn_grouped(g, x, dy_op, sn, w, spg)
+                dw = conv_wgrad_sn_grouped(g, x, dy_op, sn, w, spg, wgrad_tc)
             else:
                 # batched calls have their own sigma, u, v: gradient through W / sigma_g per group of rows
                 assert not ctx.transposed
@@ -1258,7 +1279,7 @@ class _ConvLSTMFn(torch.autograd.Function):
                     _lib.K.add(dH[op:op + n], dh_rec, out=dH[op:op + n])
                 dc_next, n_next = dc_prev, n
             gw = torch.empty_like(w)
-            dpre_op = as_bf16(dpre) if _tc_dgrad_ok(L.gx, "cl") else dpre     # one cast for the three GEMMs below
+            dpre_op = tc_operand(dpre, _tc_dgrad_ok(L.gx, "cl"))              # one cast for the three GEMMs below
             conv_wgrad(L.gx, xin, "cl", dpre_op, "cl", gw)
             hprev = _lib.K.permute_rows(h_all.view(P, hw * hid), plan.hprev_src, hw * hid).view(P, H, W, hid)
             conv_wgrad(L.gh, hprev, "cl", dpre_op, "cl", gw)

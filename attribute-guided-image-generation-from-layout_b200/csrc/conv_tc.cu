@@ -128,10 +128,26 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)2 << 61;
     return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor), bf16 x bf16 -> f32, M = 128
+// instruction descriptor (cute::UMMA::InstrDescriptor), M = 128, fp32 accumulate (c_format = 1 at bit 4); operand formats at
+// bits [7,10) / [10,13): kind::f16 -> 1 = bf16, kind::tf32 -> 2 = tf32.  EB = operand element size in bytes (2 or 4).
+template <int EB = 2>
 __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    return (1u << 4) | ((EB == 2 ? 1u : 2u) << 7) | ((EB == 2 ? 1u : 2u) << 10) | ((uint32_t)a_mn_major << 15) |
+           ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// one tcgen05.mma of 32 bytes of K per operand row: K = 16 bf16 (kind::f16) or K = 8 tf32 (kind::tf32)
+template <int EB>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (EB == 2) umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+    else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 
 // 16-byte LDGSTS; src_bytes = 0 zero-fills the destination (padding taps, rows beyond M)
@@ -199,7 +215,7 @@ __device__ __forceinline__ bool relu_mask1(const void* mask, int64_t off, int ou
                     : (reinterpret_cast<const float*>(mask)[off] > 0.f);
 }
 
-template <int BN, int STAGES, bool ATMA>
+template <int BN, int STAGES, bool ATMA, int EB = 2>
 __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                            const __grid_constant__ CUtensorMap tmap_a, b200_conv_desc d,
                                                            const __nv_bfloat16* __restrict__ in,
@@ -207,8 +223,10 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
                                                            const float* __restrict__ scale, void* __restrict__ out_v,
                                                            int out_bf16, float* __restrict__ split_ws,
                                                            int kb_per_split) {
-    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int BKE = 128 / EB;              // operand elements per 128-byte swizzle row (k-block = one row per pixel)
+    constexpr int B_BYTES = BN * 128;
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static_assert(EB == 2 || ATMA, "the cp.async gather exists for bf16 operands only");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -224,7 +242,7 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
     const int64_t M = (int64_t)d.B * d.Qh * d.Qw;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
-    const int cpb = d.Cin / BK;                     // channel blocks per tap
+    const int cpb = d.Cin / BKE;                    // channel blocks per tap
     const int num_kb_total = d.Th * d.Tw * cpb;
     const int kb_begin = blockIdx.z * kb_per_split;
     const int num_kb = (kb_begin + kb_per_split < num_kb_total ? kb_begin + kb_per_split : num_kb_total) - kb_begin;
@@ -401,8 +419,8 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
             if (elect_one()) {
                 const uint32_t bar = bar0 + (uint32_t)offsetof(SmemTail, full) + 8u * s;
                 mbar_arrive_expect_tx(bar, ATMA ? A_BYTES + B_BYTES : B_BYTES);
-                if (ATMA) tma_load_im2col_4d(a0 + s * A_BYTES, &tmap_a, cc * BK, aw, ah, an, ow, oh, bar);
-                tma_load_2d(b0 + s * B_BYTES, &tmap, (kb_begin + i) * BK, n0, bar);
+                if (ATMA) tma_load_im2col_4d(a0 + s * A_BYTES, &tmap_a, cc * BKE, aw, ah, an, ow, oh, bar);
+                tma_load_2d(b0 + s * B_BYTES, &tmap, (kb_begin + i) * BKE, n0, bar);
             }
             if (ATMA && ++cc == cpb) {
                 cc = 0;
@@ -412,7 +430,7 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
         }
     } else {
         // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
-        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        constexpr uint32_t idesc = make_idesc<EB>(BN, 0, 0);
         const uint64_t desc_hi = make_desc(0, 16, 1024);
         const uint32_t bar0 = smem_u32(tail);
         const uint32_t a0 = smem_u32(smem_a) >> 4, b0 = smem_u32(smem_b) >> 4;
@@ -424,8 +442,8 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
             const uint64_t bdesc = desc_hi | (uint64_t)((b0 + s * (B_BYTES >> 4)) & 0x3FFFu);
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)(i | k));
+                for (int k = 0; k < 4; ++k)         // 4 x 32 bytes of K per 128-byte row
+                    umma<EB>(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)(i | k));
                 umma_commit(bar0 + (uint32_t)offsetof(SmemTail, empty) + 8u * s);
                 if (i == num_kb - 1) umma_commit(bar0 + (uint32_t)offsetof(SmemTail, tmem_full));
             }
@@ -468,14 +486,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EB = 2>
 __global__ void __launch_bounds__(192, 3) conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                       const __grid_constant__ CUtensorMap tmap_a,
                                                                       b200_conv_desc d, const float* __restrict__ bias,
                                                                       const float* __restrict__ scale,
                                                                       void* __restrict__ out_v, int out_bf16,
                                                                       int num_n_tiles, int num_tiles) {
-    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int BKE = 128 / EB;
+    constexpr int B_BYTES = BN * 128;
     constexpr int ACC_COLS = BN < 16 ? 16 : BN;
     constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
     constexpr int CW = BN >= 32 ? 32 : 16;      // accumulator columns per tcgen05.ld
@@ -488,7 +507,7 @@ __global__ void __launch_bounds__(192, 3) conv_gemm_tc_persist_kernel(const __gr
     const int tid = threadIdx.x;
     const int warp = uniform(tid >> 5), lane = tid & 31;
     const int64_t M = (int64_t)d.B * d.Qh * d.Qw;
-    const int cpb = d.Cin / BK;
+    const int cpb = d.Cin / BKE;
     const int num_kb = d.Th * d.Tw * cpb;
 
     if (warp == 4 && lane == 0) {
@@ -616,8 +635,8 @@ __global__ void __launch_bounds__(192, 3) conv_gemm_tc_persist_kernel(const __gr
                         if (elect_one()) {
                             const uint32_t bar = bar0 + (uint32_t)offsetof(PersistTail, full) + 8u * s;
                             mbar_arrive_expect_tx(bar, A_BYTES + B_BYTES);
-                            tma_load_im2col_4d(a0 + s * A_BYTES, &tmap_a, cc * BK, aw, ah, an, ow, oh, bar);
-                            tma_load_2d(b0 + s * B_BYTES, &tmap, kb * BK, n0, bar);
+                            tma_load_im2col_4d(a0 + s * A_BYTES, &tmap_a, cc * BKE, aw, ah, an, ow, oh, bar);
+                            tma_load_2d(b0 + s * B_BYTES, &tmap, kb * BKE, n0, bar);
                         }
                         if (++s == STAGES) { s = 0; ph ^= 1u; }
                     }
@@ -626,7 +645,7 @@ __global__ void __launch_bounds__(192, 3) conv_gemm_tc_persist_kernel(const __gr
         }
     } else {
         // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
-        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        constexpr uint32_t idesc = make_idesc<EB>(BN, 0, 0);
         const uint64_t desc_hi = make_desc(0, 16, 1024);
         const uint32_t bar0 = smem_u32(tail);
         const uint32_t a0 = smem_u32(smem_a) >> 4, b0 = smem_u32(smem_b) >> 4;
@@ -644,8 +663,8 @@ __global__ void __launch_bounds__(192, 3) conv_gemm_tc_persist_kernel(const __gr
                 const uint64_t bdesc = desc_hi | (uint64_t)((b0 + s * (B_BYTES >> 4)) & 0x3FFFu);
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)(kb | k));
+                    for (int k = 0; k < 4; ++k)
+                        umma<EB>(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)(kb | k));
                     umma_commit(bar0 + (uint32_t)offsetof(PersistTail, empty) + 8u * s);
                     if (kb == num_kb - 1) umma_commit(bar0 + (uint32_t)offsetof(PersistTail, tmem_full) + 8u * buf);
                 }
@@ -1001,14 +1020,18 @@ struct PixInfo {
     int64_t g_off;   // offset of G pixel for this tap (or -1)
 };
 
-template <int BNW, int STAGES, bool WTMA>
+template <int BNW, int STAGES, bool WTMA, int EB = 2>
 __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_p,
                                                             const __grid_constant__ CUtensorMap tmap_g,
                                                             b200_conv_desc d, const __nv_bfloat16* __restrict__ P,
                                                             const __nv_bfloat16* __restrict__ G,
                                                             float* __restrict__ ws, int64_t rows_per_split) {
-    constexpr int PA_BYTES = 2 * 64 * 128;            // 128 P channels x 64 pixels (two MN atoms)
-    constexpr int GB_BYTES = (BNW / 64) * 64 * 128;   // BNW G channels x 64 pixels
+    constexpr int BKE = 128 / EB;                      // channels per MN atom row (128 bytes): 64 bf16 / 32 tf32
+    constexpr int PA_ATOMS = 128 / BKE, GB_ATOMS = BNW / BKE;
+    constexpr int PA_BYTES = PA_ATOMS * 64 * 128;      // 128 P channels x 64 pixels (one 8 KB MN atom column per BKE channels)
+    constexpr int GB_BYTES = GB_ATOMS * 64 * 128;      // BNW G channels x 64 pixels
+    constexpr int KMMA = 32 / EB;                      // pixels (K) per tcgen05.mma: 16 bf16 / 8 tf32
+    static_assert(EB == 2 || WTMA, "the cp.async gather exists for bf16 operands only");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -1170,12 +1193,14 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(const __grid_constan
                     mbar_arrive_expect_tx(bar, PA_BYTES + GB_BYTES);
                     const uint32_t a_dst = a0 + s * PA_BYTES;
                     const int pw = qx * d.out_sx + d.out_ox, phh = qy * d.out_sy + d.out_oy;
-                    tma_load_im2col_4d(a_dst, &tmap_p, m0, pw, phh, n, 0, 0, bar);
-                    tma_load_im2col_4d(a_dst + 8192, &tmap_p, m0 + 64, pw, phh, n, 0, 0, bar);
+#pragma unroll
+                    for (int a = 0; a < PA_ATOMS; ++a)
+                        tma_load_im2col_4d(a_dst + a * 8192, &tmap_p, m0 + a * BKE, pw, phh, n, 0, 0, bar);
                     const uint32_t b_dst = b0 + s * GB_BYTES;
                     const int gw = qx * d.in_sx + lw, gh = qy * d.in_sy + lh;
-                    tma_load_im2col_4d(b_dst, &tmap_g, c0, gw, gh, n, ow, oh, bar);
-                    if (BNW == 128) tma_load_im2col_4d(b_dst + 8192, &tmap_g, c0 + 64, gw, gh, n, ow, oh, bar);
+#pragma unroll
+                    for (int a = 0; a < GB_ATOMS; ++a)
+                        tma_load_im2col_4d(b_dst + a * 8192, &tmap_g, c0 + a * BKE, gw, gh, n, ow, oh, bar);
                 }
                 // advance 64 pixels
                 qx += 64;
@@ -1194,7 +1219,7 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(const __grid_constan
         }
     } else if (warp == 5) {
         // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
-        constexpr uint32_t idesc = make_idesc(BNW, 1, 1);
+        constexpr uint32_t idesc = make_idesc<EB>(BNW, 1, 1);
         // MN-major SWIZZLE_128B: LBO = stride between 64-element MN atoms (8192 B), SBO = stride between
         // 8-row K groups (1024 B); each UMMA (K = 16 pixels) advances 16 rows = 2048 B
         const uint64_t desc_hi = make_desc(0, 8192, 1024);
@@ -1208,8 +1233,9 @@ __global__ void __launch_bounds__(192) wgrad_gemm_tc_kernel(const __grid_constan
             const uint64_t bdesc = desc_hi | (uint64_t)((b0 + s * (GB_BYTES >> 4)) & 0x3FFFu);
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (uint32_t)(kb | k));
+                for (int k = 0; k < 64 / KMMA; ++k)      // each MMA advances KMMA pixel rows of 128 bytes
+                    umma<EB>(tmem_base, adesc + (uint64_t)(k * KMMA * 8), bdesc + (uint64_t)(k * KMMA * 8), idesc,
+                             (uint32_t)(kb | k));
                 umma_commit(bar0 + (uint32_t)offsetof(SmemTail, empty) + 8u * s);
                 if (kb == num_kb - 1) umma_commit(bar0 + (uint32_t)offsetof(SmemTail, tmem_full));
             }
@@ -1279,25 +1305,27 @@ static bool im2col_eligible(const b200_conv_desc* d) {
     return get_encode_im2col_fn() != nullptr;
 }
 
-static int encode_im2col(const b200_conv_desc* d, const void* in, CUtensorMap* tmap) {
+static int encode_im2col(const b200_conv_desc* d, const void* in, CUtensorMap* tmap, int eb = 2) {
     EncodeIm2colFn enc = get_encode_im2col_fn();
     const int lw = d->tap_sx > 0 ? d->tap_ox : d->tap_ox - (d->Tw - 1);
     const int lh = d->tap_sy > 0 ? d->tap_oy : d->tap_oy - (d->Th - 1);
     const int uw = lw + (d->Qw - 1) * d->in_sx + 1 - d->Wi;
     const int uh = lh + (d->Qh - 1) * d->in_sy + 1 - d->Hi;
     cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->B};
-    cuuint64_t gstr[3] = {(cuuint64_t)d->in_sw * 2, (cuuint64_t)d->in_sh * 2, (cuuint64_t)d->in_sn * 2};
+    cuuint64_t gstr[3] = {(cuuint64_t)d->in_sw * eb, (cuuint64_t)d->in_sh * eb, (cuuint64_t)d->in_sn * eb};
     int lower[2] = {lw, lh}, upper[2] = {uw, uh};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->in_sx, (cuuint32_t)d->in_sy, 1};
-    CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, lower, upper,
-                     (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // fp32 tensors feeding kind::tf32 MMAs are fetched as TFLOAT32: the TMA unit rounds to the 10-bit mantissa on the way in
+    CUresult r = enc(tmap, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4,
+                     const_cast<void*>(in), gdim, gstr, lower, upper, (cuuint32_t)(128 / eb), (cuuint32_t)BM, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm_tc: cuTensorMapEncodeIm2col failed (%d)", (int)r);
     // drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (descriptor word 1, bit 21 must be
     // clear) — the same fix-up the CUTLASS im2col traits apply
     static int drv = -1;
     if (drv < 0 && cudaDriverGetVersion(&drv) != cudaSuccess) drv = 0;
-    const uint64_t bytes = (uint64_t)d->B * (uint64_t)d->in_sn * 2;
+    const uint64_t bytes = (uint64_t)d->B * (uint64_t)d->in_sn * (uint64_t)eb;
     if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(tmap)[1] &= ~(1ull << 21);
     return 0;
 }
@@ -1409,7 +1437,7 @@ static int launch_halo(const b200_conv_desc* d, const HaloGeom& hg_in, const voi
     return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EB = 2>
 static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const void* wmat, const float* bias,
                       const float* scale, void* out, int out_bf16, float* split_ws, int splits, int use_im2col,
                       cudaStream_t st) {
@@ -1419,38 +1447,43 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
     int ntiles = (d->Cout + BN - 1) / BN;
     CUtensorMap tmap, tmap_a;
     cuuint64_t gdim[2] = {(cuuint64_t)d->ldw, (cuuint64_t)ntiles * BN};
-    cuuint64_t gstr[1] = {(cuuint64_t)d->ldw * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    constexpr int BKE = 128 / EB;
+    cuuint64_t gstr[1] = {(cuuint64_t)d->ldw * EB};
+    cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wmat), gdim, gstr, box, estr,
+    CUresult r = enc(&tmap, EB == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+                     const_cast<void*>(wmat), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
     HaloGeom hg;
-    if (use_im2col && splits == 1) {
+    if (EB == 2 && use_im2col && splits == 1) {
         // resident weights with a 64-wide N tile first (fits for Cin = 64 3x3 layers of any Cout), then the native tile
         if (BN == 128 && d->Cout / 64 <= kNumSMs && halo_plan(d, 64, false, &hg))
             return launch_halo<64>(d, hg, wmat, in, bias, scale, out, out_bf16, st);
         if (halo_plan(d, BN, true, &hg)) return launch_halo<BN>(d, hg, wmat, in, bias, scale, out, out_bf16, st);
     }
-    const bool atma = use_im2col && im2col_eligible(d);
+    const bool atma = (use_im2col || EB != 2) && im2col_eligible(d);
+    B200_REQUIRE(EB == 2 || atma, "conv_gemm_tf32: the gather is not expressible as a TMA im2col walk");
     if (atma) {
-        if (encode_im2col(d, in, &tmap_a) != 0) return -1;
+        if (encode_im2col(d, in, &tmap_a, EB) != 0) return -1;
     } else {
         tmap_a = tmap;
     }
-    constexpr int smem_bytes = 1024 + STAGES * (A_BYTES + BN * BK * 2) + (int)sizeof(SmemTail) + BM * 24;
+    constexpr int smem_bytes = 1024 + STAGES * (A_BYTES + BN * 128) + (int)sizeof(SmemTail) + BM * 24;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaSuccess;
+        if constexpr (EB == 2)
+            e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, false, 2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, true, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      smem_bytes);
         B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    const int num_kb = d->Th * d->Tw * (d->Cin / BK);
+    const int num_kb = d->Th * d->Tw * (d->Cin / BKE);
     int kbps = (num_kb + splits - 1) / splits;
     splits = (num_kb + kbps - 1) / kbps;          // no empty split
     static const int persist_max_kb = []() {
@@ -1470,41 +1503,43 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
             // short-K, epilogue-heavy launches gain from a third epilogue warp set
             constexpr int PSTAGES = 3;
             constexpr int PER_SM = BN == 128 ? 2 : 3;
-            constexpr int psmem = 1024 + PSTAGES * (A_BYTES + BN * BK * 2) + (int)sizeof(PersistTail);
+            constexpr int psmem = 1024 + PSTAGES * (A_BYTES + BN * 128) + (int)sizeof(PersistTail);
             static bool pconfigured = false;
             if (!pconfigured) {
-                cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<BN, PSTAGES>,
+                cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<BN, PSTAGES, EB>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
                 B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute(persist): %s", cudaGetErrorString(e));
                 pconfigured = true;
             }
             const int grid_p = (int)(tiles < PER_SM * kNumSMs ? tiles : PER_SM * kNumSMs);
-            conv_gemm_tc_persist_kernel<BN, PSTAGES><<<grid_p, 192, psmem, st>>>(tmap, tmap_a, *d, bias, scale, out,
+            conv_gemm_tc_persist_kernel<BN, PSTAGES, EB><<<grid_p, 192, psmem, st>>>(tmap, tmap_a, *d, bias, scale, out,
                                                                                out_bf16, ntiles, (int)tiles);
         } else {
             constexpr int PSTAGES = BN == 128 ? 6 : 8;
-            constexpr int psmem = 1024 + PSTAGES * (A_BYTES + BN * BK * 2) + (int)sizeof(PersistTail);
+            constexpr int psmem = 1024 + PSTAGES * (A_BYTES + BN * 128) + (int)sizeof(PersistTail);
             static bool pconfigured = false;
             if (!pconfigured) {
-                cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<BN, PSTAGES>,
+                cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<BN, PSTAGES, EB>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
                 B200_REQUIRE(e == cudaSuccess, "conv_gemm_tc: cudaFuncSetAttribute(persist): %s", cudaGetErrorString(e));
                 pconfigured = true;
             }
             const int grid_p = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-            conv_gemm_tc_persist_kernel<BN, PSTAGES><<<grid_p, 192, psmem, st>>>(tmap, tmap_a, *d, bias, scale, out,
+            conv_gemm_tc_persist_kernel<BN, PSTAGES, EB><<<grid_p, 192, psmem, st>>>(tmap, tmap_a, *d, bias, scale, out,
                                                                                out_bf16, ntiles, (int)tiles);
         }
         B200_CHECK_LAUNCH();
         return 0;
     }
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles, (unsigned)splits);
-    if (atma)
-        conv_gemm_tc_kernel<BN, STAGES, true><<<grid, 192, smem_bytes, st>>>(tmap, tmap_a, *d, in, bias, scale, out,
-                                                                            out_bf16, split_ws, kbps);
-    else
-        conv_gemm_tc_kernel<BN, STAGES, false><<<grid, 192, smem_bytes, st>>>(tmap, tmap_a, *d, in, bias, scale, out,
-                                                                             out_bf16, split_ws, kbps);
+    if (atma) {
+        conv_gemm_tc_kernel<BN, STAGES, true, EB><<<grid, 192, smem_bytes, st>>>(tmap, tmap_a, *d, in, bias, scale, out,
+                                                                                out_bf16, split_ws, kbps);
+    } else {
+        if constexpr (EB == 2)
+            conv_gemm_tc_kernel<BN, STAGES, false, 2><<<grid, 192, smem_bytes, st>>>(tmap, tmap_a, *d, in, bias, scale, out,
+                                                                                    out_bf16, split_ws, kbps);
+    }
     B200_CHECK_LAUNCH();
     if (splits > 1) {
         int64_t total = M * ((d->Cout + 3) / 4);
@@ -1517,19 +1552,20 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
 
 // generic 4-D im2col map of a channel-last tensor walked with unit tap steps: `pixels` x 64 channels per request
 static int encode_im2col_raw(const void* base, int C, int W, int H, int N, int64_t sw, int64_t sh, int64_t sn, int lw,
-                             int lh, int uw, int uh, int step_x, int step_y, int pixels, CUtensorMap* tmap) {
+                             int lh, int uw, int uh, int step_x, int step_y, int pixels, CUtensorMap* tmap, int eb = 2) {
     EncodeIm2colFn enc = get_encode_im2col_fn();
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t gstr[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+    cuuint64_t gstr[3] = {(cuuint64_t)sw * eb, (cuuint64_t)sh * eb, (cuuint64_t)sn * eb};
     int lower[2] = {lw, lh}, upper[2] = {uw, uh};
     cuuint32_t estr[4] = {1, (cuuint32_t)step_x, (cuuint32_t)step_y, 1};
-    CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, lower, upper,
-                     (cuuint32_t)BK, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(tmap, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4,
+                     const_cast<void*>(base), gdim, gstr, lower, upper, (cuuint32_t)(128 / eb), (cuuint32_t)pixels, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "tcgen05 gather-GEMM: cuTensorMapEncodeIm2col failed (%d)", (int)r);
     static int drv = -1;
     if (drv < 0 && cudaDriverGetVersion(&drv) != cudaSuccess) drv = 0;
-    if (drv <= 13010 && (uint64_t)N * (uint64_t)sn * 2 < 131072) reinterpret_cast<uint64_t*>(tmap)[1] &= ~(1ull << 21);
+    if (drv <= 13010 && (uint64_t)N * (uint64_t)sn * (uint64_t)eb < 131072) reinterpret_cast<uint64_t*>(tmap)[1] &= ~(1ull << 21);
     return 0;
 }
 
@@ -1546,20 +1582,24 @@ static bool wgrad_im2col_eligible(const b200_conv_desc* d) {
     return true;
 }
 
-template <int BNW, int STAGES>
+template <int BNW, int STAGES, int EB = 2>
 static int launch_wgrad(const b200_conv_desc* d, const __nv_bfloat16* P, const __nv_bfloat16* G, float* ws, int splits,
                         int use_im2col, cudaStream_t st) {
     int64_t Q = (int64_t)d->B * d->Qh * d->Qw;
     int64_t rps = (Q + splits - 1) / splits;
     rps = (rps + 63) / 64 * 64;
     if (rps < 64) rps = 64;
-    constexpr int smem_bytes = 1024 + STAGES * (2 * 8192 + (BNW / 64) * 8192) + (int)sizeof(SmemTail) + STAGES * 64 * 16;
+    constexpr int BKE = 128 / EB;
+    constexpr int smem_bytes = 1024 + STAGES * ((128 / BKE) * 8192 + (BNW / BKE) * 8192) + (int)sizeof(SmemTail) + STAGES * 64 * 16;
+    static_assert(smem_bytes <= 232448, "wgrad_gemm_tc: operand ring does not fit in shared memory");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_tc_kernel<BNW, STAGES, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaSuccess;
+        if constexpr (EB == 2)
+            e = cudaFuncSetAttribute(wgrad_gemm_tc_kernel<BNW, STAGES, false, 2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(wgrad_gemm_tc_kernel<BNW, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(wgrad_gemm_tc_kernel<BNW, STAGES, true, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      smem_bytes);
         B200_REQUIRE(e == cudaSuccess, "wgrad_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
@@ -1572,23 +1612,25 @@ static int launch_wgrad(const b200_conv_desc* d, const __nv_bfloat16* P, const _
     memset(&tmap_g, 0, sizeof(tmap_g));
     // the TMA path reads whole 64-channel atoms: both channel counts must cover the tiles (zero padding comes from
     // the tensor map's channel bound, so only a partial LAST atom is fine)
-    const bool wtma = use_im2col && wgrad_im2col_eligible(d);
+    const bool wtma = (use_im2col || EB != 2) && wgrad_im2col_eligible(d);
+    B200_REQUIRE(EB == 2 || wtma, "wgrad_gemm_tf32: the gather is not expressible as a TMA im2col walk");
     if (wtma) {
         const int lw = d->tap_sx > 0 ? d->tap_ox : d->tap_ox - (d->Tw - 1);
         const int lh = d->tap_sy > 0 ? d->tap_oy : d->tap_oy - (d->Th - 1);
         const int uw = lw + (d->Qw - 1) * d->in_sx + 1 - d->Wi;
         const int uh = lh + (d->Qh - 1) * d->in_sy + 1 - d->Hi;
         if (encode_im2col_raw(G, d->Cin, d->Wi, d->Hi, d->B, d->in_sw, d->in_sh, d->in_sn, lw, lh, uw, uh, d->in_sx,
-                              d->in_sy, 64, &tmap_g) != 0)
+                              d->in_sy, 64, &tmap_g, EB) != 0)
             return -1;
         const int puw = d->out_ox + (d->Qw - 1) * d->out_sx + 1 - d->Wo;
         const int puh = d->out_oy + (d->Qh - 1) * d->out_sy + 1 - d->Ho;
         if (encode_im2col_raw(P, d->Cout, d->Wo, d->Ho, d->B, d->out_sw, d->out_sh, d->out_sn, d->out_ox, d->out_oy, puw,
-                              puh, d->out_sx, d->out_sy, 64, &tmap_p) != 0)
+                              puh, d->out_sx, d->out_sy, 64, &tmap_p, EB) != 0)
             return -1;
-        wgrad_gemm_tc_kernel<BNW, STAGES, true><<<grid, 192, smem_bytes, st>>>(tmap_p, tmap_g, *d, P, G, ws, rps);
+        wgrad_gemm_tc_kernel<BNW, STAGES, true, EB><<<grid, 192, smem_bytes, st>>>(tmap_p, tmap_g, *d, P, G, ws, rps);
     } else {
-        wgrad_gemm_tc_kernel<BNW, STAGES, false><<<grid, 192, smem_bytes, st>>>(tmap_p, tmap_g, *d, P, G, ws, rps);
+        if constexpr (EB == 2)
+            wgrad_gemm_tc_kernel<BNW, STAGES, false, 2><<<grid, 192, smem_bytes, st>>>(tmap_p, tmap_g, *d, P, G, ws, rps);
     }
     B200_CHECK_LAUNCH();
     return 0;
@@ -1634,19 +1676,22 @@ extern "C" int b200_conv_tc_set_halo(int enable) {
 extern "C" int b200_conv_tc_ntile(int Cout) { return Cout >= 128 ? 128 : (Cout >= 64 ? 64 : 16); }
 
 /* split-K plan: enough CTAs to fill the 148 SMs twice when the output tile grid alone cannot */
-extern "C" int b200_conv_tc_splits(const b200_conv_desc* d) {
+static int conv_splits_impl(const b200_conv_desc* d, int bke);
+extern "C" int b200_conv_tc_splits(const b200_conv_desc* d) { return conv_splits_impl(d, 64); }
+
+static int conv_splits_impl(const b200_conv_desc* d, int bke) {
     static int forced = []() {
         const char* e = getenv("B200_TC_SPLITS");      // experiments only: force the split-K factor
         return e ? atoi(e) : 0;
     }();
     if (forced > 0) {
-        const int nkb = d->Th * d->Tw * (d->Cin / 64);
+        const int nkb = d->Th * d->Tw * (d->Cin / bke);
         return forced < nkb ? forced : (nkb > 0 ? nkb : 1);
     }
     int64_t M = (int64_t)d->B * d->Qh * d->Qw;
     int bn = b200_conv_tc_ntile(d->Cout);
     int64_t tiles = ((M + 127) / 128) * ((d->Cout + bn - 1) / bn);
-    int num_kb = d->Th * d->Tw * (d->Cin / 64);
+    int num_kb = d->Th * d->Tw * (d->Cin / bke) * bke / 64;      // in 128-byte bf16-equivalent blocks: same work threshold
     // measured (tools/bench_conv.py, B200_TC_SPLITS): the fp32 partials' round trip plus the reduce launch cost more
     // than idle SMs unless fewer than half of them have a tile and the K loop is long
     if (tiles * 2 > kNumSMs || num_kb < 16) return 1;
@@ -1654,6 +1699,52 @@ extern "C" int b200_conv_tc_splits(const b200_conv_desc* d) {
     if (s > num_kb / 8) s = num_kb / 8;
     if (s > 8) s = 8;
     return s < 1 ? 1 : (int)s;
+}
+
+extern "C" int b200_conv_tf32_splits(const b200_conv_desc* d) { return conv_splits_impl(d, 32); }
+
+/* can the tf32 kernels (TMA im2col operands only) run this descriptor?  conv: kind 0; weight gradient: kind 1 */
+extern "C" int b200_conv_tf32_ok(const b200_conv_desc* d, int wgrad) {
+    if (d->Cin % 32 != 0 || d->in_sc != 1 || ((d->in_sn | d->in_sh | d->in_sw) & 3) != 0) return 0;
+    if (wgrad) {
+        if (d->Cout % 32 != 0 || d->out_sc != 1 || ((d->out_sn | d->out_sh | d->out_sw) & 3) != 0) return 0;
+        return tc::wgrad_im2col_eligible(d) ? 1 : 0;
+    }
+    return tc::im2col_eligible(d) ? 1 : 0;
+}
+
+extern "C" int b200_conv_gemm_tf32(const b200_conv_desc* d, const float* in, const float* wmat, const float* bias,
+                                   const float* scale, float* out, float* split_ws, int splits, b200_stream_t stream) {
+    int64_t M = (int64_t)d->B * d->Qh * d->Qw;
+    if (M == 0 || d->Cout == 0) return 0;
+    B200_REQUIRE(d->Cin % 32 == 0 && d->in_sc == 1, "conv_gemm_tf32: needs Cin %% 32 == 0 and channel-last input");
+    B200_REQUIRE(((d->in_sn | d->in_sh | d->in_sw) & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0,
+                 "conv_gemm_tf32: input rows must be 16-byte aligned");
+    B200_REQUIRE(d->ldw % 32 == 0 && d->ldw >= (int64_t)d->Th * d->Tw * d->Cin, "conv_gemm_tf32: bad ldw");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(wmat) & 15) == 0, "conv_gemm_tf32: wmat must be 16-byte aligned");
+    B200_REQUIRE(splits >= 1 && (splits == 1 || split_ws != nullptr), "conv_gemm_tf32: split-K needs a workspace");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(d->relu_mask) & 15) == 0, "conv_gemm_tf32: relu_mask must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const __nv_bfloat16* inp = reinterpret_cast<const __nv_bfloat16*>(in);      // opaque to the TMA path
+    int bn = b200_conv_tc_ntile(d->Cout);
+    if (bn == 128) return tc::launch_fwd<128, 3, 4>(d, inp, wmat, bias, scale, out, 0, split_ws, splits, 1, st);
+    if (bn == 64) return tc::launch_fwd<64, 4, 4>(d, inp, wmat, bias, scale, out, 0, split_ws, splits, 1, st);
+    return tc::launch_fwd<16, 4, 4>(d, inp, wmat, bias, scale, out, 0, split_ws, splits, 1, st);
+}
+
+extern "C" int b200_wgrad_gemm_tf32(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+                                    b200_stream_t stream) {
+    B200_REQUIRE(splits >= 1, "wgrad_gemm_tf32: bad splits");
+    B200_REQUIRE(d->Cin % 32 == 0 && d->in_sc == 1 && d->Cout % 32 == 0 && d->out_sc == 1,
+                 "wgrad_gemm_tf32: needs channel-last operands with channels %% 32 == 0");
+    B200_REQUIRE(((d->in_sn | d->in_sh | d->in_sw | d->out_sn | d->out_sh | d->out_sw) & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(P) & 15) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0,
+                 "wgrad_gemm_tf32: operand rows must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const __nv_bfloat16* Pp = reinterpret_cast<const __nv_bfloat16*>(P);
+    const __nv_bfloat16* Gp = reinterpret_cast<const __nv_bfloat16*>(G);
+    if (d->Cin >= 128) return tc::launch_wgrad<128, 3, 4>(d, Pp, Gp, ws, splits, 1, st);
+    return tc::launch_wgrad<64, 4, 4>(d, Pp, Gp, ws, splits, 1, st);
 }
 
 extern "C" int b200_cast_bf16(const float* x, void* y, int64_t n, b200_stream_t stream) {

@@ -155,6 +155,18 @@ int b200_conv_tc_set_halo(int enable);
 int b200_conv_tc_splits(const b200_conv_desc* d);
 /* y[i] = bf16(x[i]) (round to nearest even), n % 4 == 0 */
 int b200_cast_bf16(const float* x, void* y_bf16, int64_t n, b200_stream_t stream);
+/* tcgen05 kind::tf32 variants — the "fp32 on tensor cores" mode (BASELINE config 2, fp32 half): operands stay fp32 tensors in
+ * memory (strides in fp32 elements, multiples of 4), the TMA unit rounds them to tf32 (10-bit mantissa) on the way into shared
+ * memory, accumulation is fp32 in TMEM.  Same descriptor / epilogue semantics as the bf16 entry points; wmat fp32, ldw a
+ * multiple of 32, rows padded to b200_conv_tc_ntile; requires Cin % 32 == 0 (and Cout % 32 == 0 for the weight gradient) and
+ * a gather the TMA im2col mode can express — b200_conv_tf32_ok(d, wgrad) tells (callers use the fp32 CUDA-core kernels
+ * otherwise).  Stated operation-level bound: 2e-3 relative. */
+int b200_conv_tf32_ok(const b200_conv_desc* d, int wgrad);
+int b200_conv_tf32_splits(const b200_conv_desc* d);
+int b200_conv_gemm_tf32(const b200_conv_desc* d, const float* in, const float* wmat, const float* bias, const float* scale,
+                        float* out, float* split_ws, int splits, b200_stream_t stream);
+int b200_wgrad_gemm_tf32(const b200_conv_desc* d, const float* P, const float* G, float* ws, int splits,
+                         b200_stream_t stream);
 
 /* Weight-gradient gather-GEMM:  R[m, (ty*Tw+tx)*Cg + c] = sum_{n,qy,qx} P[n,qy,qx,m] * G[n, gather(qy,qx,ty,tx), c]
  * where `d` describes the gather of G exactly as above (d->Cin = Cg) and P is addressed with d's out_* fields

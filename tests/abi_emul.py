@@ -20,6 +20,12 @@ def _storage_view(t: torch.Tensor, offset: int, size, stride):
     return torch.as_strided(t, size, stride, t.storage_offset() + offset)
 
 
+def _tf32(x: torch.Tensor) -> torch.Tensor:
+    """round an fp32 tensor to tf32 (10-bit mantissa, nearest) — what the TFLOAT32 tensor maps do on the way to shared memory"""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 class EmulKernels:
     def __init__(self):
         self.launches = 0
@@ -152,14 +158,18 @@ class EmulKernels:
 
     def conv_gemm(self, d, inp, wmat, bias, scale, out, tc, mask=None):
         self.launches += 1
+        tc = int(tc)
         assert mask is None or (tc and mask.shape == out.shape and mask.dtype == out.dtype)
-        assert inp.dtype == torch.bfloat16 or not tc, "the tcgen05 path takes bf16 operands"
+        assert inp.dtype == torch.bfloat16 or tc != 1, "the tcgen05 bf16 path takes bf16 operands"
+        assert tc != 2 or (inp.dtype == torch.float32 and wmat.dtype == torch.float32 and out.dtype == torch.float32)
         A = self._gather(d, inp).float()
         K = d.Th * d.Tw * d.Cin
         Wm = wmat.float()[:d.Cout, :K]
         A2 = A.reshape(A.shape[0], K)
-        if tc:
+        if tc == 1:
             A2 = A2.to(torch.bfloat16).float()
+        elif tc == 2:
+            A2, Wm = _tf32(A2), _tf32(Wm)
         y = A2 @ Wm.t()
         if scale is not None:
             sr = getattr(d, "scale_rows", 0)
@@ -184,16 +194,20 @@ class EmulKernels:
 
     def wgrad_gemm(self, d, P, G, ws, splits, tc):
         self.launches += 1
-        assert (P.dtype == torch.bfloat16 and G.dtype == torch.bfloat16) or not tc
+        tc = int(tc)
+        assert (P.dtype == torch.bfloat16 and G.dtype == torch.bfloat16) or tc != 1
+        assert tc != 2 or (P.dtype == torch.float32 and G.dtype == torch.float32)
         A = self._gather(d, G).float()                           # (Q, T, Cin)
         off, ok = self._out_index(d)
         flatP = torch.as_strided(P, (P.untyped_storage().nbytes() // P.element_size() - P.storage_offset(),), (1,),
                                  P.storage_offset())
         co = torch.arange(d.Cout) * d.out_sc
         Pm = flatP[(off.clamp(min=0)[:, None] + co[None])].float() * ok[:, None].float()
-        if tc:
+        if tc == 1:
             A = A.to(torch.bfloat16).float()
             Pm = Pm.to(torch.bfloat16).float()
+        elif tc == 2:
+            A, Pm = _tf32(A), _tf32(Pm)
         K = d.Th * d.Tw * d.Cin
         A2 = A.reshape(A.shape[0], K)
         wsv = ws.view(splits, d.Cout, K)

@@ -831,3 +831,104 @@ def test_pack_from_two_parameters(K, tc):
     assert torch.equal(fwd[0].cpu(), ref_fwd[0])
     for a, r in zip(dg, ref_dg):
         assert torch.equal(a[0].cpu(), r[0])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 kind::tf32 — fp32 tensors on the tensor cores (BASELINE config 2, "fp32" half)
+# ---------------------------------------------------------------------------------------------------------
+TF32_CASES = [c for c in CONV_CASES if c[7] == "cl" and c[8] == "cl" and c[0] % 32 == 0 and c[1] % 32 == 0] + [
+    (96, 160, 3, 1, 1, 8, 2, "cl", "cl", True), (64, 64, 3, 1, 1, 64, 4, "cl", "cl", True), (512, 640, 1, 1, 0, 4, 3, "cl", "cl", False)]
+
+
+@pytest.mark.parametrize("case", TF32_CASES)
+def test_conv_tf32_fwd_bwd(K, case):
+    """forward, data gradient and weight gradient on the kind::tf32 kernels (TMA TFLOAT32 operands, fp32 accumulation in
+    TMEM) against F.conv2d autograd in fp32.  Stated bound: 2e-3 relative per op (10-bit operand mantissas; SURVEY.md App.
+    D); and against the same computation on tf32-ROUNDED operands the kernels must agree to 3e-4 (rounding mode of the TMA
+    conversion + summation order), which proves the error is operand rounding, not arithmetic."""
+    Cx, Cy, k, s, p, H, N, xl, ol, has_b = case
+    g = torch.Generator().manual_seed(Cx * 5 + Cy + k)
+    x = torch.randn(N, Cx, H, H, generator=g)
+    w = torch.randn(Cy, Cx, k, k, generator=g) / (Cx * k * k) ** 0.5
+    b = torch.randn(Cy, generator=g) if has_b else None
+    ops.set_precision("tf32")
+    try:
+        geom = ops.ConvGeom(Cx, Cy, k, k, s, p)
+        assert ops._tc_fwd_ok(geom, xl) == ops.TC_TF32 and ops._tc_wgrad_ok(geom, xl, ol) == ops.TC_TF32
+        xd = _to_layout(x, xl).cuda().requires_grad_(True)
+        wd = w.cuda().requires_grad_(True)
+        bd = b.cuda().requires_grad_(True) if has_b else None
+        before = K.launch_count()
+        y = ops.conv2d(xd, wd, bd, geom, ops.WeightPacks(), xl, ol, relu=False)
+        assert y.dtype == torch.float32
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        br = b.clone().requires_grad_(True) if has_b else None
+        yr = _conv_ref(xr, wr, br, s, p, False, None)
+        gy = torch.randn(yr.shape, generator=g)
+        yr.backward(gy)
+        close(_from_layout(y, ol), yr, 2e-3, "tf32 fwd")
+        y.backward(_to_layout(gy, ol).cuda())
+        close(_from_layout(xd.grad, xl), xr.grad, 2e-3, "tf32 dgrad")
+        close(wd.grad, wr.grad, 2e-3, "tf32 wgrad")
+        if has_b:
+            close(bd.grad, br.grad, 1e-5, "bias grad")
+        from abi_emul import _tf32
+        yq = _conv_ref(_tf32(x), _tf32(w), b, s, p, False, None)
+        close(_from_layout(y, ol), yq, 3e-4, "tf32 fwd vs rounded operands")
+        dxq = torch.nn.grad.conv2d_input(x.shape, _tf32(w), _tf32(gy), stride=s, padding=p)
+        close(_from_layout(xd.grad, xl), dxq, 3e-4, "tf32 dgrad vs rounded operands")
+        dwq = torch.nn.grad.conv2d_weight(_tf32(x), w.shape, _tf32(gy), stride=s, padding=p)
+        close(wd.grad, dwq, 3e-4, "tf32 wgrad vs rounded operands")
+    finally:
+        ops.set_precision("fp32")
+
+
+def test_tf32_transpose_sn_and_lstm(K):
+    """the other users of the GEMM kernels in tf32 mode: ConvTranspose2d (dgrad phases as forward), batched spectral-norm
+    convolution (grouped weight gradient through W / sigma_g) and the ConvLSTM (hoisted + recurrent GEMMs, BPTT)"""
+    g = torch.Generator().manual_seed(21)
+    ops.set_precision("tf32")
+    try:
+        x = torch.randn(2, 256, 8, 8, generator=g)
+        w = torch.randn(256, 128, 4, 4, generator=g) / (256 * 4) ** 0.5
+        geom = ops.ConvGeom(128, 256, 4, 4, 2, 1)
+        xd, wd = _to_layout(x, "cl").cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+        y = ops.conv_transpose2d(xd, wd, geom, ops.WeightPacks(), (16, 16))
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        yr = F.conv_transpose2d(xr, wr, None, stride=2, padding=1)
+        gy = torch.randn(yr.shape, generator=g)
+        yr.backward(gy)
+        y.backward(_to_layout(gy, "cl").cuda())
+        close(_from_layout(y, "cl"), yr, 2e-3, "convT fwd")
+        close(_from_layout(xd.grad, "cl"), xr.grad, 2e-3, "convT dgrad")
+        close(wd.grad, wr.grad, 2e-3, "convT wgrad")
+    finally:
+        ops.set_precision("fp32")
+    # ConvLSTM: 2 layers, ragged sequences
+    o2i = torch.tensor([0, 0, 0, 1, 2, 2])
+    x = torch.randn(6, 64, 8, 8, generator=g) * 0.5
+    sd, layers, params, cin = {}, [], [], 64
+    for i, hid in enumerate((64, 32)):
+        sd["c.cell_list.%d.conv.weight" % i] = (torch.randn(4 * hid, cin + hid, 5, 5, generator=g) / ((cin + hid) * 25) ** 0.5).requires_grad_(True)
+        sd["c.cell_list.%d.conv.bias" % i] = (torch.randn(4 * hid, generator=g) * 0.1).requires_grad_(True)
+        layers.append(ops.ConvLSTMLayer(cin, hid, 5))
+        cin = hid
+    xr = x.clone().requires_grad_(True)
+    ref = O.conv_lstm(sd, "c", xr, o2i, hidden=(64, 32))
+    gy = torch.randn(ref.shape, generator=g)
+    ref.backward(gy)
+    ops.set_precision("tf32")
+    try:
+        pd = []
+        for i in range(2):
+            pd += [sd["c.cell_list.%d.conv.weight" % i].detach().cuda().requires_grad_(True),
+                   sd["c.cell_list.%d.conv.bias" % i].detach().cuda().requires_grad_(True)]
+        xd = x.permute(0, 2, 3, 1).contiguous().cuda().requires_grad_(True)
+        out = ops.conv_lstm(xd, ops.get_plan(o2i, 3, "cuda"), layers, pd)
+        out.backward(gy.permute(0, 2, 3, 1).contiguous().cuda())
+        close(out.permute(0, 3, 1, 2), ref, 2e-3, "tf32 convlstm fwd")
+        close(xd.grad.permute(0, 3, 1, 2), xr.grad, 4e-3, "tf32 convlstm dx")
+        for i in range(2):
+            close(pd[2 * i].grad, sd["c.cell_list.%d.conv.weight" % i].grad, 4e-3, "tf32 convlstm dw%d" % i)
+    finally:
+        ops.set_precision("fp32")

@@ -167,3 +167,27 @@ def test_step_with_gt_attribute_swap(emul):
     ref = oracle_step(model, batch, swap=(matrix, random.Random(77)))
     assert torch.equal(res["attribute_est"], ref["attribute_est"])
     check_step_against(ts, res, ref, img_tol=1e-4, loss_tol=1e-5, grad_tol=2e-2, cos_min=0.9999)
+
+
+def test_step_wiring_tf32_mode(emul):
+    """tf32 mode host routing: fp32 tensors, eligible GEMMs flagged kind 2 (the emulation rounds both operands to tf32 and
+    checks the dtype contract of b200_conv_gemm_tf32 / b200_wgrad_gemm_tf32); results inside the stated tf32 bound"""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    from b200gan import ops
+    from b200gan.step import TrainStep
+    states = O.make_states(64, 0)
+    batch = O.synth_batch(2, 64, None, 7)
+    ops.set_precision("tf32")
+    try:
+        ts = TrainStep(64, device="cpu")
+        load_states(ts, states)
+        res = ts.step(ts.to_device(batch), optimizer_step=False, seeds=(123, 124))
+    finally:
+        ops.set_precision("fp32")
+    ref = oracle_step(O.OracleModel(64, 0, states), batch)
+    assert max(rel(res["out_g"][i], ref["out_g"][i]) for i in range(11)) < 5e-3
+    assert abs(float(res["g_loss"]) - float(ref["g_loss"])) < 2e-3 * abs(float(ref["g_loss"]))
+    cos = torch.nn.functional.cosine_similarity
+    a = torch.cat([p.grad.reshape(-1) for _, p in ts.netG.named_parameters()]).double()
+    r = torch.cat([ref["g_grads"][k].reshape(-1) for k, _ in ts.netG.named_parameters()]).double()
+    assert float(cos(a, r, dim=0)) > 0.98       # measured 0.988 (the bf16 mode: 0.89 on the same step)
