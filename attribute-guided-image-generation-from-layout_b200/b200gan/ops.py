@@ -28,6 +28,7 @@ SN_EPS = 1e-12
 # ----------------------------------------------------------------------------------------------------------
 _PRECISION = "fp32"
 _CACHE_EPOCH = 0
+_WGRAD_TARGET = int(os.environ.get("B200_WGRAD_TARGET", "296"))     # experiments only (read once: os.environ is slow)
 
 
 def set_precision(p: str):
@@ -254,8 +255,10 @@ def _tc_dgrad_ok(g: ConvGeom, dy_layout: str) -> int:
 
 
 def _tc_wgrad_ok(g: ConvGeom, x_layout: str, dy_layout: str) -> int:
+    """the weight gradient needs pixel-major (MN-major) operands; in the tf32 mode it runs on the bf16 kernel as three GEMMs
+    over two-term bf16 splits of the fp32 operands (conv_wgrad), hence the 64-channel granularity in both modes"""
     k = _tc_kind()
-    return k if (k and x_layout == "cl" and dy_layout == "cl" and g.Cx % _kalign(k) == 0 and g.Cy % _kalign(k) == 0) else TC_NONE
+    return k if (k and x_layout == "cl" and dy_layout == "cl" and g.Cx % 64 == 0 and g.Cy % 64 == 0) else TC_NONE
 
 
 def _pack_fwd(g: ConvGeom, srcs, tc: bool, recipes: List[PackRecipe]):
@@ -490,7 +493,7 @@ def _wgrad_splits(g: ConvGeom, Q: int, tc: bool, rows=None, cols=None) -> int:
         tiles = -(-g.Cy // 64) * g.kh * g.kw * -(-g.Cx // 64)
     # tcgen05 kernel: one wave of two co-resident CTAs per SM; more splits only add partial-result traffic (every split
     # writes and the reduction re-reads a full fp32 copy of the gradient)
-    target = int(os.environ.get("B200_WGRAD_TARGET", "296")) if tc else 592
+    target = _WGRAD_TARGET if tc else 592
     splits = max(1, min(-(-target // tiles), max(1, Q // 256), 256 if rows is not None else 64))
     return splits
 
@@ -522,12 +525,23 @@ def conv_wgrad(g: ConvGeom, x, x_layout, dy, dy_layout, dw: torch.Tensor, accumu
     Q = N * Hy * Wy
     K = kk * g.Cx
     splits = _wgrad_splits(g, Q, tc, rows=(g.Cy if (not tc and g.Cx <= 8) else None), cols=K)
-    ws = torch.empty((splits * g.Cy * K,), dtype=torch.float32, device=x.device)
     d = ConvDesc(B=N, Qh=Hy, Qw=Wy, Cin=g.Cx, Cout=g.Cy, Th=g.kh, Tw=g.kw, in_sy=g.s, in_sx=g.s, tap_sy=1, tap_sx=1,
                  tap_oy=-g.p, tap_ox=-g.p, Hi=Hx, Wi=Wx, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3],
                  out_sy=1, out_sx=1, out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ds[0], out_sh=ds[1], out_sw=ds[2],
                  out_sc=ds[3], ldw=K, relu=0)
-    _lib.K.wgrad_gemm(d, dy, x, ws, splits, tc)
+    if tc == TC_TF32:
+        # fp32 operands on the bf16 tensor-core kernel: x = xh + xl, dy = dh + dl (two-term bf16 splits, 16 mantissa bits);
+        # dY^T X ~ dh^T xh + dh^T xl + dl^T xh, three launches whose partials are summed by the same fixed-order reduction
+        n_el = g.Cy * K
+        ws = torch.empty((3 * splits * n_el,), dtype=torch.float32, device=x.device)
+        xh, xl = _lib.K.split_bf16(x.contiguous())
+        dh, dl = _lib.K.split_bf16(dy.contiguous())
+        for i, (a, b) in enumerate(((dh, xh), (dh, xl), (dl, xh))):
+            _lib.K.wgrad_gemm(d, a, b, ws[i * splits * n_el:(i + 1) * splits * n_el], splits, TC_BF16)
+        splits *= 3
+    else:
+        ws = torch.empty((splits * g.Cy * K,), dtype=torch.float32, device=x.device)
+        _lib.K.wgrad_gemm(d, dy, x, ws, splits, tc)
     _lib.K.wgrad_reduce(ws, splits, g.Cy, g.kh, g.kw, g.Cx, dw, g.cx_offset * kk, g.cx_total * kk, g.kw, 1, kk,
                         accumulate=accumulate)
     return dw
@@ -539,7 +553,7 @@ GROUPED_SN_WGRAD = True      # one weight-gradient GEMM for all batched calls of
 def _sn_group_splits(g: ConvGeom, Q: int, groups: int) -> int:
     """pixel splits PER CALL for the grouped spectral-norm weight gradient (0 = not applicable): the calls' row ranges must
     be whole numbers of 64-pixel k-blocks of equal size"""
-    if not GROUPED_SN_WGRAD or groups < 2 or groups > 8 or Q % groups:
+    if not GROUPED_SN_WGRAD or _PRECISION != "bf16" or groups < 2 or groups > 8 or Q % groups:
         return 0
     Qg = Q // groups
     kk = g.kh * g.kw

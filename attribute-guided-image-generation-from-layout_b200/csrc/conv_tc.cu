@@ -1646,6 +1646,28 @@ __global__ void cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict
     }
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits of x survive; hi*hi' + hi*lo' + lo*hi' reproduces an
+// fp32 product to ~2^-16 (the weight-gradient GEMM of the tf32 mode runs as three bf16 tensor-core GEMMs on these halves)
+__global__ void split_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, int64_t n4) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = x[t];
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        float r[4];
+        uint32_t h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat16 b = __float2bfloat16_rn(f[i]);
+            h[i] = (uint32_t)__bfloat16_as_ushort(b);
+            r[i] = f[i] - __bfloat162float(b);
+        }
+        hi[t] = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+        uint2 u;
+        u.x = pack_bf16(r[0], r[1]);
+        u.y = pack_bf16(r[2], r[3]);
+        lo[t] = u;
+    }
+}
+
 }  // namespace tc
 }  // namespace b200
 
@@ -1753,6 +1775,16 @@ extern "C" int b200_cast_bf16(const float* x, void* y, int64_t n, b200_stream_t 
                  "cast_bf16: needs n %% 4 == 0 and aligned pointers");
     tc::cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), n / 4);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_split_bf16(const float* x, void* hi, void* lo, int64_t n, b200_stream_t stream) {
+    if (n == 0) return 0;
+    B200_REQUIRE(n % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 &&
+                     (reinterpret_cast<uintptr_t>(lo) & 7) == 0, "split_bf16: needs n %% 4 == 0 and aligned pointers");
+    tc::split_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), n / 4);
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -179,10 +179,140 @@ def workload_config(args, n_per_gpu, note=""):
 # ------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------
+class Iteration:
+    """One training iteration (attribute estimation + D-step + G-step + 4 x Adam + operand re-pack) of `ts` on ONE batch
+    layout, captured into a CUDA graph (or run eagerly): `upload()` copies the pinned host batch into the static device
+    batch, `run()` replays."""
+
+    def __init__(self, ts, host, use_graph, world, rank, warm=2):
+        self.ts, self.world = ts, world
+        self.pinned = {k: (v if k == "obj_to_img" else v.pin_memory()) for k, v in host.items()}
+        self.h2d_bytes = sum(v.numel() * v.element_size() for k, v in host.items() if k != "obj_to_img")
+        self.n_images, self.n_objs = host["imgs"].shape[0], host["objs"].shape[0]
+        self.b = ts.to_device(self.pinned)
+        torch.cuda.synchronize()
+        self.graph, self.static_out = None, None
+        for _ in range(warm):
+            ts.step(self.b, optimizer_step=True)
+        torch.cuda.synchronize()
+        if use_graph:
+            import gc
+            gc.collect()
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    ts.step(self.b, optimizer_step=True)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                # thread_local: the NCCL watchdog thread may query events while the step (with its all-reduces) is captured
+                with torch.cuda.graph(g, capture_error_mode="thread_local" if world > 1 else "global"):
+                    r = ts.step(self.b, optimizer_step=True)
+                    self.static_out = (r["d_loss"], r["g_loss"])
+                # every optimizer step inside the captured iteration is followed by the in-place re-pack of the GEMM operands
+                # derived from its parameters (ops.refresh_packs, optimizer post-step hook): each replay computes with the
+                # weights the previous replay wrote
+                self.graph = g
+            except Exception as e:   # graph capture is an optimisation, never a correctness requirement
+                if rank == 0:
+                    print("[bench] CUDA graph capture unavailable (%s: %s); timing eagerly" % (type(e).__name__, e), file=sys.stderr)
+                self.graph = None
+                torch.cuda.synchronize()
+
+    def upload(self):
+        for k, v in self.pinned.items():
+            if k != "obj_to_img":
+                self.b[k].copy_(v, non_blocking=True)
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return self.static_out
+        r = self.ts.step(self.b, optimizer_step=True)
+        return r["d_loss"], r["g_loss"]
+
+
+def timed(fn, steps, sync_all):
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for i in range(steps):
+        out = fn(i)
+    e1.record()
+    sync_all()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def max_over_ranks(vals, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor(vals, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def make_step(size, precision, dev, world, graph):
+    from b200gan import ops
+    from b200gan.step import TrainStep
+    ops.set_precision(precision)
+    torch.manual_seed(1234)
+    ts = TrainStep(size, device=dev, capturable=graph)
+    if world > 1:
+        ts.enable_data_parallel()  # the bucketed all-reduces issued from the autograd hooks are captured with the step
+    # CropEncoder noise: drawn on the device (graph-safe Philox stream) instead of the reference's CPU RNG + H2D copy; the
+    # distribution is the same, and the parity tests pin the CPU-RNG variant (tests/test_step_gpu.py)
+    ts.netG.crop_encoder.eps_source = lambda o, z, d: torch.randn(o, z, device=d)
+    return ts
+
+
+def side_measurement(args, size, n_img, precision, steps, dev, world, rank, sync_all, note, label):
+    """an extra workload measured in the same process (BASELINE configs other than the headline one): device-resident and
+    end-to-end ms per iteration, max over ranks"""
+    import gc
+    from b200gan import _lib
+    from oracle import gan_oracle as O
+    try:
+        ts = make_step(size, precision, dev, world, not args.no_graph)
+        host = O.synth_batch(n_img, size, OBJS_PER_IMAGE, seed=40 + rank)
+        it = Iteration(ts, host, not args.no_graph, world, rank, warm=2)
+        for _ in range(2):
+            it.run()
+        ms, losses = timed(lambda i: it.run(), steps, sync_all)
+
+        def e2e(i):
+            it.upload()
+            l = it.run()
+            return torch.stack([l[0].reshape(()), l[1].reshape(())]).cpu()
+        ms_e2e, hl = timed(e2e, steps, sync_all)
+        ok = bool(torch.isfinite(hl).all())
+        ms, ms_e2e = max_over_ranks([ms, ms_e2e], dev, world)
+        mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+        res = {"workload": "%dx%d model, batch %d per GPU (global %d), %d objects/image, %s" %
+                           (size, size, n_img, n_img * world, OBJS_PER_IMAGE, precision),
+               "dtype": {"bf16": "bf16", "tf32": "tf32 (fp32 tensors, tcgen05 kind::tf32)", "fp32": "f32"}[precision],
+               "ms_per_step": ms, "value": n_img * world / (ms / 1e3), "unit": "images/s", "steps": steps,
+               "e2e": {"value": n_img * world / (ms_e2e / 1e3), "ms_per_step": ms_e2e,
+                       "h2d_bytes_per_step": it.h2d_bytes * world, "d2h_bytes_per_step": 8 * world},
+               "cuda_graph": it.graph is not None, "finite": ok, "peak_mem_gib": round(mem, 1),
+               "step_tflops": step_flops(size, n_img, n_img * OBJS_PER_IMAGE) * world / (ms / 1e3) / 1e12}
+        note("%s: %.2f ms/step" % (label, ms))
+        del it, ts
+    except Exception as e:          # an extra must never take the headline line down
+        res = {"workload": label, "error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        note("%s FAILED: %s" % (label, res["error"]))
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch.distributed as dist
     from b200gan import _lib, ops
-    from b200gan.step import TrainStep
     from oracle import gan_oracle as O       # synthetic batch generator + cpu_baseline leg only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,23 +332,8 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ops.set_precision(args.precision)
     n_img = args.batch
     n_obj = n_img * OBJS_PER_IMAGE
-
-    torch.manual_seed(1234)
-    ts = TrainStep(args.size, device=dev, capturable=not args.no_graph)
-    if world > 1:
-        ts.enable_data_parallel()  # the bucketed all-reduces issued from the autograd hooks are captured with the step
-    torch.cuda.manual_seed(100 + rank)
-    ts.netG.crop_encoder.eps_source = lambda o, z, d: torch.randn(o, z, device=d)
-
-    host = O.synth_batch(n_img, args.size, OBJS_PER_IMAGE, seed=10 + rank)
-    pinned = {k: (v if k == "obj_to_img" else v.pin_memory()) for k, v in host.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host.items() if k != "obj_to_img")
-    b = ts.to_device(pinned)
-    torch.cuda.synchronize()
-
     t_start = time.time()
 
     def note(msg):
@@ -230,108 +345,138 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def eager_step(batch):
-        return ts.step(batch, optimizer_step=True)
-
-    # ---- warm-up (eager) -----------------------------------------------------------------------------------
-    for _ in range(max(1, args.warmup if args.no_graph else 2)):
-        res = eager_step(b)
+    ts = make_step(args.size, args.precision, dev, world, not args.no_graph)
+    host = O.synth_batch(n_img, args.size, OBJS_PER_IMAGE, seed=10 + rank)
+    # ---- eager warm-up + launch count -------------------------------------------------------------------------
+    b0 = ts.to_device(host)
+    for _ in range(max(1, args.warmup if args.no_graph else 1)):
+        ts.step(b0, optimizer_step=True)
     torch.cuda.synchronize()
     launches_before = _lib.K.launch_count()
-    res = eager_step(b)
+    t_e = time.perf_counter()
+    ts.step(b0, optimizer_step=True)
     torch.cuda.synchronize()
+    eager_ms = (time.perf_counter() - t_e) * 1e3
     launches_per_step = _lib.K.launch_count() - launches_before
-    note("eager warm-up done (%d launches/step)" % launches_per_step)
+    note("eager warm-up done (%d launches/step, %.1f ms eager)" % (launches_per_step, eager_ms))
+    del b0
+    main = Iteration(ts, host, not args.no_graph, world, rank, warm=1)
+    for _ in range(args.warmup):
+        main.run()
+    torch.cuda.synchronize()
+    note("graph captured" if main.graph is not None else "no graph: eager steps")
 
-    graph = None
-    static_out = None
-    del res
-    import gc
-    gc.collect()
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                eager_step(b)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            # thread_local: the NCCL watchdog thread may query events while the step (with its all-reduces) is captured
-            with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
-                r = eager_step(b)
-                static_out = (r["d_loss"], r["g_loss"])
-            # (every optimizer step inside the captured iteration is followed by the in-place re-pack of the GEMM operands
-            # derived from its parameters — ops.refresh_packs via the optimizer post-step hook — so each replay computes
-            # with the weights the previous replay wrote)
-            for _ in range(args.warmup):
-                graph.replay()
-            torch.cuda.synchronize()
-        except Exception as e:   # graph capture is an optimisation, never a correctness requirement
-            if rank == 0:
-                print("[bench] CUDA graph capture unavailable (%s: %s); timing eagerly" % (type(e).__name__, e), file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
-
-    note("graph captured" if graph is not None else "no graph: eager steps")
-
-    def run_step():
-        if graph is not None:
-            graph.replay()
-            return static_out
-        r = eager_step(b)
-        return r["d_loss"], r["g_loss"]
-
-    # ---- device-resident timing -----------------------------------------------------------------------------
+    # ---- device-resident timing (inputs already in HBM) ----------------------------------------------------------
     sampler = ClockSampler(local)
+    traj = torch.zeros((args.steps, 2), device=dev)           # loss trajectory of the timed iterations (device-side copies)
+
+    def dev_step(i):
+        l = main.run()
+        traj[i, 0].copy_(l[0]); traj[i, 1].copy_(l[1])
+        return l
     sync_all()
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    traj = torch.zeros((args.steps, 2), device=dev)           # loss trajectory of the timed iterations (device-side copies)
-    e0.record()
-    for i in range(args.steps):
-        losses = run_step()
-        traj[i, 0].copy_(losses[0]); traj[i, 1].copy_(losses[1])
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms, losses = timed(dev_step, args.steps, sync_all)
+    clocks = sampler.stop() if rank == 0 else None
+    note("device-resident timing done: %.2f ms/step" % ms)
+    assert all(torch.isfinite(l).all() for l in losses), "non-finite loss in the timed region"
     traj = traj.cpu()
     # the timed iterations TRAIN: the same batch is replayed, so the losses must move from iteration to iteration
     assert args.steps < 2 or (traj[1:] != traj[:-1]).any(dim=1).all(), \
         "losses repeat across timed iterations: the optimizer update is not reaching the next iteration"
-    clocks = sampler.stop() if rank == 0 else None
-    note("device-resident timing done: %.2f ms/step" % ms)
-    assert all(torch.isfinite(l).all() for l in losses), "non-finite loss in the timed region"
 
-    # ---- end-to-end timing: pinned host batch -> device every step, losses read back every step ----------------
-    static_b = b
-    d2h_bytes = 8
-    sync_all()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        for k, v in pinned.items():
-            if k != "obj_to_img":
-                static_b[k].copy_(v, non_blocking=True)
-        losses = run_step()
-        host_losses = torch.stack([losses[0].reshape(()), losses[1].reshape(())]).cpu()
-    f1.record()
-    sync_all()
-    ms_e2e = f0.elapsed_time(f1) / args.steps
+    # ---- end-to-end: pinned host batch -> device every step, both losses read back every step ------------------------
+    def e2e_step(i):
+        main.upload()
+        l = main.run()
+        return torch.stack([l[0].reshape(()), l[1].reshape(())]).cpu()
+    ms_e2e, host_losses = timed(e2e_step, args.steps, sync_all)
     note("end-to-end timing done: %.2f ms/step" % ms_e2e)
     assert torch.isfinite(host_losses).all()
+    ms, ms_e2e = max_over_ranks([ms, ms_e2e], dev, world)
 
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    # ---- end-to-end over ROTATING RAGGED layouts (3..9 objects per image, the loader's range vg_custom_mask.py:45):
+    # every distinct layout is a different set of index plans and tensor shapes, i.e. its own captured graph ----------------
+    ragged = None
+    if not args.no_extras:
+        try:
+            n_lay = 4
+            its = [Iteration(ts, O.synth_batch(n_img, args.size, None, seed=200 + 10 * rank + j), not args.no_graph, world,
+                             rank, warm=1) for j in range(n_lay)]
+            for it in its:
+                it.run()
+
+            def rag_step(i):
+                it = its[i % n_lay]
+                it.upload()
+                l = it.run()
+                return torch.stack([l[0].reshape(()), l[1].reshape(())]).cpu()
+            k = max(args.steps, n_lay)
+            ms_rag, hl = timed(rag_step, k, sync_all)
+            (ms_rag,) = max_over_ranks([ms_rag], dev, world)
+            objs = sum(it.n_objs for it in its) / n_lay
+            # an UNSEEN layout runs eagerly once (plans built on the host, ~1700 launches issued from Python)
+            fresh = ts.to_device(O.synth_batch(n_img, args.size, None, seed=900 + rank))
+            torch.cuda.synchronize()
+            t_e = time.perf_counter()
+            ts.step(fresh, optimizer_step=True)
+            torch.cuda.synchronize()
+            first_ms = (time.perf_counter() - t_e) * 1e3
+            ragged = {"layouts": n_lay, "objects_per_image": "3..9 (mean %.2f)" % (objs / n_img), "steps": k,
+                      "ms_per_step": ms_rag, "value": n_img * world / (ms_rag / 1e3), "unit": "images/s",
+                      "objects_per_s": objs * world / (ms_rag / 1e3),
+                      "fixed_layout_objects_per_s": n_obj * world / (ms_e2e / 1e3),
+                      "first_seen_layout_eager_ms": first_ms,
+                      "note": "one captured graph per distinct layout (cache keyed by the per-image object counts); an unseen "
+                              "layout pays one eager iteration"}
+            note("ragged e2e: %.2f ms/step over %d layouts; unseen layout eager %.1f ms" % (ms_rag, n_lay, first_ms))
+            del its, fresh
+        except Exception as e:
+            ragged = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+    # ---- data parallel: what the gradient exchange costs (the same captured iteration without the all-reduces) --------------
+    dp = None
+    if world > 1 and not args.no_extras:
+        try:
+            saved = (ts.ddp_d, ts.ddp_g)
+            ts.ddp_d = ts.ddp_g = None
+            solo = Iteration(ts, host, not args.no_graph, 1, rank, warm=1)
+            solo.run()
+            ms_solo, _ = timed(lambda i: solo.run(), args.steps, sync_all)
+            ts.ddp_d, ts.ddp_g = saved
+            (ms_solo,) = max_over_ranks([ms_solo], dev, world)
+            dp = {"ms_per_step_without_allreduce": ms_solo, "exposed_allreduce_ms": ms - ms_solo,
+                  "bucket_bytes_D": saved[0].bucket_bytes(), "bucket_bytes_G": saved[1].bucket_bytes(),
+                  "note": "buckets in launch order; the LAST bucket of each backward (the networks' first layers, kept small) is "
+                          "the one whose all-reduce cannot overlap backward compute"}
+            note("without all-reduce: %.2f ms/step" % ms_solo)
+            del solo
+        except Exception as e:
+            dp = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
     # ---- roofline of the dominant kernel family (tcgen05 gather-GEMMs), timed with CUDA events per launch ------
     roof = None
     if rank == 0:
-        roof = kernel_roofline(ts, b, args)
+        roof = kernel_roofline(ts, main.b, args)
         note("kernel roofline done")
+    main_h2d, graph_used = main.h2d_bytes, main.graph is not None
+    del main, ts
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations, as extra keys of the same line ------------------------------------------------
+    extras = {}
+    if not args.no_extras and args.size == 64 and args.precision == "bf16":
+        k = max(3, min(args.steps, 5))
+        extras["config2_fp32_tensor_core"] = side_measurement(args, 64, n_img, "tf32", k, dev, world, rank, sync_all, note,
+                                                              "config 2 fp32 half (tf32 tensor cores)")
+        per_gpu = max(1, 128 // world)
+        extras["config3_128x128_global_batch_128"] = side_measurement(args, 128, per_gpu, "bf16", 3, dev, world, rank, sync_all,
+                                                                      note, "config 3 (128x128, global batch 128, strong scaling)")
+    ops.set_precision(args.precision)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -344,21 +489,26 @@ def run_b200(args):
         line = {
             "metric": "G+D train-step images/sec", "value": total_imgs / (ms / 1e3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision],
             "data": "synthetic", "config": workload_config(args, n_img),
-            "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes * world,
-                    "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": ms_e2e},
+            "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": main_h2d * world,
+                    "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
-            "cuda_graph": graph is not None,
+            "cuda_graph": graph_used,
+            "eager_ms_per_step": eager_ms,
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu_base,
-            "step_tflops": step_flops(args.size, n_img, n_obj) / (ms / 1e3) / 1e12,
+            "step_tflops": step_flops(args.size, n_img, n_obj) * world / (ms / 1e3) / 1e12,
             "loss_trajectory": {"d_loss": [round(float(v), 5) for v in traj[:, 0][:8]],
                                 "g_loss": [round(float(v), 5) for v in traj[:, 1][:8]],
                                 "note": "first timed iterations on one repeated batch; they move because every iteration "
                                         "applies the four Adam updates and re-packs the GEMM operands"},
+            "e2e_ragged_layouts": ragged,
+            "data_parallel": dp,
+            "extras": extras,
         }
         emit(line)
     if world > 1:
@@ -471,7 +621,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=64, choices=[64, 128])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only (no ragged / tf32 / 128x128 extras)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -161,6 +161,11 @@ int b200_cast_bf16(const float* x, void* y_bf16, int64_t n, b200_stream_t stream
  * multiple of 32, rows padded to b200_conv_tc_ntile; requires Cin % 32 == 0 (and Cout % 32 == 0 for the weight gradient) and
  * a gather the TMA im2col mode can express — b200_conv_tf32_ok(d, wgrad) tells (callers use the fp32 CUDA-core kernels
  * otherwise).  Stated operation-level bound: 2e-3 relative. */
+/* hi = bf16(x), lo = bf16(x - hi): the two-term bf16 split of an fp32 tensor (n % 4 == 0).  The tf32 mode's WEIGHT gradient
+ * runs as three bf16 tensor-core GEMMs on these halves (hi*hi + hi*lo + lo*hi, ~2^-16 relative — tighter than tf32): the
+ * pixel-major (MN-major) operands that GEMM needs returned all-zero accumulators with kind::tf32 on this hardware / toolchain
+ * (tools/probes/tf32_wgrad_probe.py), so b200_wgrad_gemm_tf32 is kept for probing only. */
+int b200_split_bf16(const float* x, void* hi_bf16, void* lo_bf16, int64_t n, b200_stream_t stream);
 int b200_conv_tf32_ok(const b200_conv_desc* d, int wgrad);
 int b200_conv_tf32_splits(const b200_conv_desc* d);
 int b200_conv_gemm_tf32(const b200_conv_desc* d, const float* in, const float* wmat, const float* bias, const float* scale,

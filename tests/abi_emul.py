@@ -135,6 +135,11 @@ class EmulKernels:
         self.launches += 1
         return x.to(torch.bfloat16)
 
+    def split_bf16(self, x):
+        self.launches += 1
+        hi = x.to(torch.bfloat16)
+        return hi, (x - hi.float()).to(torch.bfloat16)
+
     def im2col_pack(self, x, x_strides, N, Hx, Wx, Cx, kh, kw, stride, pad, Hy, Wy, Kp, flip=False):
         self.launches += 1
         sn, sh, sw, sc = x_strides

@@ -836,14 +836,14 @@ def test_pack_from_two_parameters(K, tc):
 # ---------------------------------------------------------------------------------------------------------
 # tcgen05 kind::tf32 — fp32 tensors on the tensor cores (BASELINE config 2, "fp32" half)
 # ---------------------------------------------------------------------------------------------------------
-TF32_CASES = [c for c in CONV_CASES if c[7] == "cl" and c[8] == "cl" and c[0] % 32 == 0 and c[1] % 32 == 0] + [
-    (96, 160, 3, 1, 1, 8, 2, "cl", "cl", True), (64, 64, 3, 1, 1, 64, 4, "cl", "cl", True), (512, 640, 1, 1, 0, 4, 3, "cl", "cl", False)]
+TF32_CASES = [c for c in CONV_CASES if c[7] == "cl" and c[8] == "cl" and c[0] % 64 == 0 and c[1] % 64 == 0] + [
+    (64, 64, 3, 1, 1, 64, 4, "cl", "cl", True), (512, 640, 1, 1, 0, 4, 3, "cl", "cl", False)]
 
 
 @pytest.mark.parametrize("case", TF32_CASES)
 def test_conv_tf32_fwd_bwd(K, case):
-    """forward, data gradient and weight gradient on the kind::tf32 kernels (TMA TFLOAT32 operands, fp32 accumulation in
-    TMEM) against F.conv2d autograd in fp32.  Stated bound: 2e-3 relative per op (10-bit operand mantissas; SURVEY.md App.
+    """forward and data gradient on the kind::tf32 kernels (TMA TFLOAT32 operands, fp32 accumulation in TMEM), weight
+    gradient as three bf16 tensor-core GEMMs over two-term bf16 splits of the fp32 operands, against F.conv2d autograd in fp32.  Stated bound: 2e-3 relative per op (10-bit operand mantissas; SURVEY.md App.
     D); and against the same computation on tf32-ROUNDED operands the kernels must agree to 3e-4 (rounding mode of the TMA
     conversion + summation order), which proves the error is operand rounding, not arithmetic."""
     Cx, Cy, k, s, p, H, N, xl, ol, has_b = case
@@ -869,7 +869,7 @@ def test_conv_tf32_fwd_bwd(K, case):
         close(_from_layout(y, ol), yr, 2e-3, "tf32 fwd")
         y.backward(_to_layout(gy, ol).cuda())
         close(_from_layout(xd.grad, xl), xr.grad, 2e-3, "tf32 dgrad")
-        close(wd.grad, wr.grad, 2e-3, "tf32 wgrad")
+        close(wd.grad, wr.grad, 1e-4, "tf32-mode wgrad (three bf16 GEMMs over two-term splits: tighter than tf32)")
         if has_b:
             close(bd.grad, br.grad, 1e-5, "bias grad")
         from abi_emul import _tf32
@@ -877,8 +877,6 @@ def test_conv_tf32_fwd_bwd(K, case):
         close(_from_layout(y, ol), yq, 3e-4, "tf32 fwd vs rounded operands")
         dxq = torch.nn.grad.conv2d_input(x.shape, _tf32(w), _tf32(gy), stride=s, padding=p)
         close(_from_layout(xd.grad, xl), dxq, 3e-4, "tf32 dgrad vs rounded operands")
-        dwq = torch.nn.grad.conv2d_weight(_tf32(x), w.shape, _tf32(gy), stride=s, padding=p)
-        close(wd.grad, dwq, 3e-4, "tf32 wgrad vs rounded operands")
     finally:
         ops.set_precision("fp32")
 
