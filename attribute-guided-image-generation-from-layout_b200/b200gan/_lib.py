@@ -46,7 +46,7 @@ class SNLayer(C.Structure):
                 ("u_hist", C.c_void_p), ("v_hist", C.c_void_p), ("h", C.c_int), ("w", C.c_int)]
 
 
-PACK_CHUNK = 8192
+PACK_MT, PACK_CT = 8, 64          # B200_PACK_MT / B200_PACK_CT (include/b200gan.h)
 
 
 class PackEntry(C.Structure):
@@ -379,7 +379,7 @@ class Kernels:
                                r.dst.data_ptr() + esz * int(r.dst_row_offset) * int(r.ldw), r.ldw, r.s_m, r.s_ky, r.s_kx,
                                r.s_c, int(bool(r.bf16)), r.M, r.Th, r.Tw, r.C, cd, r.c_off if r.C_dst > 0 else 0, r.ky0,
                                r.kx0, r.kstep, chunks, 0)
-            chunks += -(-(r.M * r.Th * r.Tw * r.C) // PACK_CHUNK)
+            chunks += -(-r.M // PACK_MT) * -(-r.C // PACK_CT)
         nbytes = C.sizeof(arr)
         host = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
         C.memmove(host.data_ptr(), C.addressof(arr), nbytes)
@@ -622,12 +622,10 @@ class Kernels:
     def sn_wgrad_finish(self, ws, groups, spg, Cy, T, Cx, W, u_hist, v_hist, inv, dW):
         """dW of `groups` batched calls of a spectral-normalised layer from the group-aligned partials of one wgrad launch"""
         dev = W.device
-        n = Cy * Cx * T
-        Gbuf = torch.empty((groups * n,), dtype=torch.float32, device=dev)
         parts = int(self.lib.b200_sn_wgrad_parts(int(Cy), int(Cx)))
         dot = torch.empty((groups * parts,), dtype=torch.float64, device=dev)
         self._check(self.lib.b200_sn_wgrad_finish(_ptr(ws), int(groups), int(spg), C.c_int64(Cy * T * Cx), int(Cy), int(T),
-                                                  int(Cx), _ptr(W), _ptr(u_hist), _ptr(v_hist), _ptr(inv), _ptr(Gbuf),
+                                                  int(Cx), _ptr(W), _ptr(u_hist), _ptr(v_hist), _ptr(inv), None,
                                                   _ptr(dot), _ptr(dW), _stream()), "b200_sn_wgrad_finish")
         return dW
 

@@ -506,9 +506,17 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restri
     }
 }
 
-// every packed operand of a network in one launch: block b = one B200_PACK_CHUNK-element chunk of one entry's VALID
-// elements (binary search over the chunk prefix sums), same element mapping as pack_weight_kernel
+// every packed operand of a network in one launch.  Work unit ("chunk") = a tile of 8 rows (m) x 64 channels (c) x all taps
+// of one entry, staged through shared memory so that BOTH sides are coalesced: the parameter is read in contiguous runs
+// (the (c, tap) plane of a row when s_c is the tap count — forward operands — or the (m, tap) plane of a channel when s_m is
+// — data-gradient operands, whose rows are the convolution's INPUT channels), the operand matrix is written in 64-element
+// row segments.  Entries with another stride pattern (none on the path) take the element-wise fallback.
+// Block b -> (entry, tile) by binary search over the chunk prefix sums; same element mapping as pack_weight_kernel.
+constexpr int kPackMT = 8, kPackCT = 64;
+constexpr int kPackSmemFloats = 12288;                       // 48 KB: 8 x 64 x 24 taps; wider kernels go in row sub-passes
+
 __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const b200_pack_entry* __restrict__ entries, int n_entries) {
+    __shared__ float tile[kPackSmemFloats];
     const int b = blockIdx.x;
     int lo = 0, hi = n_entries - 1;
     while (lo < hi) {                                   // last entry with chunk_begin <= b
@@ -516,18 +524,52 @@ __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const b200_pack_
         if (entries[mid].chunk_begin <= b) lo = mid; else hi = mid - 1;
     }
     const b200_pack_entry en = entries[lo];
-    const int TC = en.Th * en.Tw * en.C;
-    const int64_t total = (int64_t)en.M * TC;
-    const int64_t t0 = (int64_t)(b - en.chunk_begin) * B200_PACK_CHUNK;
-    const int64_t t1 = t0 + B200_PACK_CHUNK < total ? t0 + B200_PACK_CHUNK : total;
-    for (int64_t t = t0 + threadIdx.x; t < t1; t += 256) {
-        const int64_t m = t / TC;
-        const int r = (int)(t - m * TC);
-        const int tap = r / en.C, c = r - tap * en.C;
-        const int j = tap / en.Tw, i = tap - j * en.Tw;
-        const float v = en.src[m * en.s_m + (int64_t)(en.ky0 + en.kstep * j) * en.s_ky +
-                               (int64_t)(en.kx0 + en.kstep * i) * en.s_kx + (int64_t)c * en.s_c];
-        const int64_t d = m * en.ldw + (int64_t)tap * en.C_dst + en.c_off + c;
+    const int T = en.Th * en.Tw;
+    const int ctiles = (en.C + kPackCT - 1) / kPackCT;
+    const int tb = b - en.chunk_begin;
+    const int m0 = (tb / ctiles) * kPackMT, c0 = (tb % ctiles) * kPackCT;
+    const int mt = min(kPackMT, en.M - m0), ct = min(kPackCT, en.C - c0);
+    // full tap count of the parameter (the contiguous innermost run): s_c for forward operands, s_m for data-gradient ones
+    const int64_t kk = en.s_c < en.s_m ? en.s_c : en.s_m;
+    const bool inner_c = en.s_c == kk;                   // (c, tap) contiguous per row m; else (m, tap) contiguous per channel c
+    const bool staged = en.s_kx == 1 && kk * kPackCT <= kPackSmemFloats &&
+                        kk >= (int64_t)(en.ky0 + en.kstep * (en.Th - 1)) * en.s_ky + en.kx0 + en.kstep * (en.Tw - 1) + 1;
+    if (staged) {
+        const int K = (int)kk;
+        const int mp = min(mt, kPackSmemFloats / (ct * K));      // rows per sub-pass (>= 1)
+        for (int ms = 0; ms < mt; ms += mp) {
+            const int mc = min(mp, mt - ms);
+            // load: `outer` contiguous runs of `run` floats -> tile[outer][inner][K]
+            const int outer = inner_c ? mc : ct, inner = inner_c ? ct : mc, run = inner * K;
+            const int64_t s_outer = inner_c ? en.s_m : en.s_c;
+            const float* base = en.src + (int64_t)(m0 + ms) * en.s_m + (int64_t)c0 * en.s_c;
+            for (int i = threadIdx.x; i < outer * run; i += 256) {
+                const int o = i / run, r = i - o * run;
+                tile[i] = base[(int64_t)o * s_outer + r];
+            }
+            __syncthreads();
+            // store: rows (m, tap), ct contiguous channels
+            for (int i = threadIdx.x; i < mc * T * ct; i += 256) {
+                const int rw = i / ct, c = i - rw * ct;
+                const int m = rw / T, tap = rw - m * T;
+                const int j = tap / en.Tw, ii = tap - j * en.Tw;
+                const int k = (en.ky0 + en.kstep * j) * (int)en.s_ky + (en.kx0 + en.kstep * ii);
+                const float v = inner_c ? tile[(m * ct + c) * K + k] : tile[(c * mc + m) * K + k];
+                const int64_t d = (int64_t)(m0 + ms + m) * en.ldw + (int64_t)tap * en.C_dst + en.c_off + c0 + c;
+                if (en.dst_bf16) reinterpret_cast<uint16_t*>(en.dst)[d] = f32_to_bf16_rn(v);
+                else reinterpret_cast<float*>(en.dst)[d] = v;
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < mt * T * ct; i += 256) {
+        const int c = i % ct, rw = i / ct;
+        const int m = rw / T, tap = rw - m * T;
+        const int j = tap / en.Tw, ii = tap - j * en.Tw;
+        const float v = en.src[(int64_t)(m0 + m) * en.s_m + (int64_t)(en.ky0 + en.kstep * j) * en.s_ky +
+                               (int64_t)(en.kx0 + en.kstep * ii) * en.s_kx + (int64_t)(c0 + c) * en.s_c];
+        const int64_t d = (int64_t)(m0 + m) * en.ldw + (int64_t)tap * en.C_dst + en.c_off + c0 + c;
         if (en.dst_bf16) reinterpret_cast<uint16_t*>(en.dst)[d] = f32_to_bf16_rn(v);
         else reinterpret_cast<float*>(en.dst)[d] = v;
     }
@@ -602,61 +644,58 @@ __global__ void wgrad_reduce_vec_kernel(const float* __restrict__ ws, int splits
 }
 
 // Transposing variant for the parameter layout (M, C, Th, Tw) (s_c = Th*Tw, s_ty = Tw, s_tx = 1): the partial results are
-// (M, tap, C).  A block owns 32 channels of one row m: it sums the splits with 16-byte loads along C (4 split lanes per
-// element, combined (p0 + p1) + (p2 + p3) by two shuffles — a fixed order), transposes through shared memory, and writes
-// the 32 x T block — contiguous in the destination — with coalesced stores.
+// (M, tap, C).  A block owns 32 channels x R rows (m) x all taps per pass: one (row, tap, channel quad) item per thread sums
+// the splits with 16-byte loads (4 independent accumulators in flight, combined in a fixed order), the tile is transposed
+// through shared memory and written — contiguous in the destination — with coalesced stores.
 __global__ void __launch_bounds__(256) wgrad_reduce_tr_kernel(const float* __restrict__ ws, int splits, int64_t split_stride,
-                                                             int M, int T, int C, float* __restrict__ dst, int64_t s_m,
+                                                             int M, int T, int C, int R, float* __restrict__ dst, int64_t s_m,
                                                              const float* __restrict__ scale, int accumulate) {
-    __shared__ float tile[32 * 64];
+    extern __shared__ float wr_tile[];                             // [R][32][T]
     const int c0 = blockIdx.x * 32;
     const float alpha = scale ? *scale : 1.f;
     const int nvalid = C - c0 < 32 ? C - c0 : 32;                 // a multiple of 4
-    const int items = T * 8;                                       // (tap, channel quad)
-    const int work = items * 4;                                    // x 4 split lanes
-    const int bound = (work + 31) & ~31;
-  for (int m = blockIdx.y; m < M; m += gridDim.y) {               // rows walked by the block (few, fat blocks)
-    const float* base = ws + (int64_t)m * T * C + c0;
-    for (int w = threadIdx.x; w < bound; w += 256) {
-        const int item = w >> 2, sl = w & 3;
-        const int tap = item >> 3, q = item & 7;
-        const bool live = w < work && q * 4 < nvalid;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) {
-            const float* p = base + (int64_t)tap * C + q * 4;
-            int s = sl;
-            for (; s + 12 < splits; s += 16) {
-                float4 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(p + (int64_t)(s + 4 * u) * split_stride);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    const int per_row = T * 8;                                     // (tap, channel quad)
+    const int items = R * per_row, cells = R * 32 * T;
+    for (int m0 = blockIdx.y * R; m0 < M; m0 += gridDim.y * R) {
+        for (int it = threadIdx.x; it < items; it += 256) {
+            const int r = it / per_row, rem = it - r * per_row;
+            const int tap = rem >> 3, q = rem & 7;
+            const int m = m0 + r;
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+            if (m < M && q * 4 < nvalid) {
+                const float* p = ws + ((int64_t)m * T + tap) * C + c0 + q * 4;
+                int sidx = 0;
+                for (; sidx + 4 <= splits; sidx += 4) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(p + (int64_t)sidx * split_stride);
+                    const float4 v1 = *reinterpret_cast<const float4*>(p + (int64_t)(sidx + 1) * split_stride);
+                    const float4 v2 = *reinterpret_cast<const float4*>(p + (int64_t)(sidx + 2) * split_stride);
+                    const float4 v3 = *reinterpret_cast<const float4*>(p + (int64_t)(sidx + 3) * split_stride);
+                    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+                    a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+                    a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+                    a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+                }
+                for (; sidx < splits; ++sidx) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(p + (int64_t)sidx * split_stride);
+                    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+                }
+                a0.x += a1.x + (a2.x + a3.x); a0.y += a1.y + (a2.y + a3.y);
+                a0.z += a1.z + (a2.z + a3.z); a0.w += a1.w + (a2.w + a3.w);
             }
-            for (; s < splits; s += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(p + (int64_t)s * split_stride);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            float* t = wr_tile + (r * 32 + q * 4) * T + tap;
+            t[0] = a0.x; t[T] = a0.y; t[2 * T] = a0.z; t[3 * T] = a0.w;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cells; i += 256) {
+            const int r = i / (32 * T), j = i - r * 32 * T;
+            if (m0 + r < M && j < nvalid * T) {
+                float* out = dst + (int64_t)(m0 + r) * s_m + (int64_t)c0 * T + j;
+                const float v = alpha * wr_tile[i];
+                *out = accumulate ? *out + v : v;
             }
         }
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-        }
-        if (live && sl == 0) {
-            float* t = tile + (q * 4) * T + tap;
-            t[0] = acc.x; t[T] = acc.y; t[2 * T] = acc.z; t[3 * T] = acc.w;
-        }
+        __syncthreads();
     }
-    __syncthreads();
-    float* out = dst + (int64_t)m * s_m + (int64_t)c0 * T;
-    for (int i = threadIdx.x; i < nvalid * T; i += 256) {
-        const float v = alpha * tile[i];
-        out[i] = accumulate ? out[i] + v : v;
-    }
-    __syncthreads();
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -740,19 +779,25 @@ __global__ void __launch_bounds__(128) im2col_pack_staged_kernel(const T* __rest
         }
         const T* xb = x + (int64_t)n * sn;
         const int iy0 = qy * stride + (flip ? pad : -pad), ix0 = qx * stride + (flip ? pad : -pad);
-        bf16* row = tile + lane * ld;
-        int k = 0;
-        for (int ky = 0; ky < kh; ++ky) {
-            const int iy = flip ? iy0 - ky : iy0 + ky;
-            const bool oky = live && iy >= 0 && iy < Hx;
-            for (int kx = 0; kx < kw; ++kx) {
-                const int ix = flip ? ix0 - kx : ix0 + kx;
-                const bool ok = oky && ix >= 0 && ix < Wx;
-                const T* p = xb + (int64_t)iy * sh + (int64_t)ix * sw;
-                for (int c = 0; c < Cx; ++c, ++k) row[k] = __float2bfloat16_rn(ok ? ldf(p + (int64_t)c * sc) : 0.f);
+        // two consecutive K columns per step -> one 32-bit shared store (half the stores / bank conflicts of bf16 stores)
+        uint32_t* row2 = reinterpret_cast<uint32_t*>(tile + lane * ld);
+        const int K = kh * kw * Cx;
+        int ky = 0, kx = 0, c = 0;
+        for (int k = 0; k < Kp; k += 2) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                v[e] = 0.f;
+                if (k + e < K) {
+                    const int iy = flip ? iy0 - ky : iy0 + ky, ix = flip ? ix0 - kx : ix0 + kx;
+                    if (live && iy >= 0 && iy < Hx && ix >= 0 && ix < Wx)
+                        v[e] = ldf(xb + (int64_t)iy * sh + (int64_t)ix * sw + (int64_t)c * sc);
+                    if (++c == Cx) { c = 0; if (++kx == kw) { kx = 0; ++ky; } }
+                }
             }
+            __nv_bfloat162 pr = __floats2bfloat162_rn(v[0], v[1]);
+            row2[k >> 1] = *reinterpret_cast<uint32_t*>(&pr);
         }
-        for (; k < Kp; ++k) row[k] = __float2bfloat16_rn(0.f);
         __syncwarp();
         const int cpr = Kp / 8;                               // 16-byte chunks per row
         const int64_t m0 = sidx * 32;
@@ -1094,10 +1139,13 @@ extern "C" int b200_wgrad_reduce(const float* ws, int splits, int64_t split_stri
     if ((C & 3) == 0 && (split_stride & 3) == 0 && aligned16(ws) && T > 1 && T <= 64 && s_tx == 1 && s_ty == Tw && s_c == T &&
         M < 65536) {
         const int cb = (C + 31) / 32;
-        int rows = (kNumSMs * 8 + cb - 1) / cb;              // ~8 blocks per SM in total, each walking M / rows rows
-        if (rows > M) rows = M;
-        wgrad_reduce_tr_kernel<<<dim3(cb, rows), 256, 0, as_stream(stream)>>>(ws, splits, split_stride, M, T, C, dst, s_m,
-                                                                            scale, accumulate);
+        int R = 256 / (T * 8);                               // rows per pass: about one (tap, channel quad) item per thread
+        if (R < 1) R = 1;
+        if (R > M) R = M;
+        int rows = (kNumSMs * 8 + cb - 1) / cb;              // ~8 blocks per SM in total, each walking its share of the rows
+        if (rows > (M + R - 1) / R) rows = (M + R - 1) / R;
+        wgrad_reduce_tr_kernel<<<dim3(cb, rows), 256, (size_t)R * 32 * T * sizeof(float), as_stream(stream)>>>(
+            ws, splits, split_stride, M, T, C, R, dst, s_m, scale, accumulate);
     } else if ((C & 3) == 0 && (split_stride & 3) == 0 && total < (1ll << 31) && aligned16(ws))
         wgrad_reduce_vec_kernel<<<grid_for(total / 4 * 4, 128, 16), 128, 0, as_stream(stream)>>>(ws, splits, split_stride, M, Th, Tw, C,
                                                                                         dst, s_m, s_ty, s_tx, s_c, scale, accumulate);
@@ -1119,7 +1167,7 @@ extern "C" int b200_im2col_pack(const void* x, int x_dt, int64_t N, int Hx, int 
         // NCHW-style input (unit stride along x): staged kernel, coalesced on both sides
         const int smem = 4 * 32 * (Kp + 8) * 2;
         const int64_t strips = (M + 31) / 32;
-        const int grid = grid_for((strips + 3) / 4, 1, 4);
+        const int grid = grid_for((strips + 3) / 4, 1, 12);      // ~48 warps per SM: the strip loop is latency bound
         B200_DISPATCH_DT(x_dt, T, {
             static bool configured = false;
             if (!configured) {

@@ -213,80 +213,103 @@ __global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* _
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kSnMaxGroups = 8;
 
-// grid (ceil(C/32), rows, groups), 256 threads: 32 channels of the rows m = blockIdx.y, + gridDim.y, ... of call g
-__global__ void __launch_bounds__(256) sn_wgrad_reduce_kernel(const float* __restrict__ ws, int spg, int64_t split_stride,
-                                                             int M, int T, int C, const float* __restrict__ W,
-                                                             float* __restrict__ Gbuf, double* __restrict__ dot_part) {
-    __shared__ float tile[32 * 64];
+// Pass A.  grid (ceil(C/32), row blocks), 256 threads; a block owns 32 channels x R rows (m) x all taps per pass and walks
+// the calls g = 0..groups-1 itself: per call the splits are summed (16-byte loads, up to 4 independent accumulators in flight),
+// transposed through shared memory from the partials' (m, tap, c) order to the parameter's (m, c, tap) order, dotted with W and
+// accumulated as G_g / sigma_g.  Output: dW_main = sum_g G_g / sigma_g (ONE write of |W|; the per-call G_g is never stored) and
+// the per-block partial dots <G_g, W>.  Traffic: (groups * spg + 1) |W| reads + |W| write  (was (2 groups + ...) |W| more).
+__global__ void __launch_bounds__(256) sn_wgrad_reduce_kernel(const float* __restrict__ ws, int groups, int spg,
+                                                             int64_t split_stride, int M, int T, int C, int R,
+                                                             const float* __restrict__ W, const float* __restrict__ inv,
+                                                             float* __restrict__ dW, double* __restrict__ dot_part) {
+    extern __shared__ float sn_smem[];
+    float* tile = sn_smem;                        // [R][32][T]
+    float* accs = sn_smem + R * 32 * T;           // [R][32][T]
     __shared__ double red[8];
-    const int g = blockIdx.z;
     const int c0 = blockIdx.x * 32;
     const int nvalid = C - c0 < 32 ? C - c0 : 32;                 // a multiple of 4
-    const int items = T * 8;                                       // (tap, channel quad)
-    const int work = items * 4;                                    // x 4 split lanes
-    const int bound = (work + 31) & ~31;
-    const int64_t n = (int64_t)M * C * T;
-    const float* wsg = ws + (int64_t)g * spg * split_stride;
-    float* Gg = Gbuf + (int64_t)g * n;
-    double dot = 0.0;
-    for (int m = blockIdx.y; m < M; m += gridDim.y) {
-        const float* base = wsg + (int64_t)m * T * C + c0;
-        for (int w = threadIdx.x; w < bound; w += 256) {
-            const int item = w >> 2, sl = w & 3;
-            const int tap = item >> 3, q = item & 7;
-            const bool live = w < work && q * 4 < nvalid;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) {
-                const float* p = base + (int64_t)tap * C + q * 4;
-                for (int sidx = sl; sidx < spg; sidx += 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(p + (int64_t)sidx * split_stride);
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const int per_row = T * 8;                                     // (tap, channel quad) items per row
+    const int items = R * per_row;
+    const int cells = R * 32 * T;
+    const int nparts = gridDim.x * gridDim.y;
+    double dot[kSnMaxGroups];
+#pragma unroll
+    for (int g = 0; g < kSnMaxGroups; ++g) dot[g] = 0.0;
+    for (int m0 = blockIdx.y * R; m0 < M; m0 += gridDim.y * R) {
+        for (int i = threadIdx.x; i < cells; i += 256) accs[i] = 0.f;
+        for (int g = 0; g < groups; ++g) {
+            const float* wsg = ws + (int64_t)g * spg * split_stride;
+            for (int it = threadIdx.x; it < items; it += 256) {
+                const int r = it / per_row, rem = it - r * per_row;
+                const int tap = rem >> 3, q = rem & 7;
+                const int m = m0 + r;
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+                if (m < M && q * 4 < nvalid) {
+                    const float* p = wsg + ((int64_t)m * T + tap) * C + c0 + q * 4;
+                    int sidx = 0;
+                    for (; sidx + 4 <= spg; sidx += 4) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(p + (int64_t)sidx * split_stride);
+                        const float4 v1 = *reinterpret_cast<const float4*>(p + (int64_t)(sidx + 1) * split_stride);
+                        const float4 v2 = *reinterpret_cast<const float4*>(p + (int64_t)(sidx + 2) * split_stride);
+                        const float4 v3 = *reinterpret_cast<const float4*>(p + (int64_t)(sidx + 3) * split_stride);
+                        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+                        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+                        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+                        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+                    }
+                    for (; sidx < spg; ++sidx) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(p + (int64_t)sidx * split_stride);
+                        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+                    }
+                    a0.x += a1.x + (a2.x + a3.x); a0.y += a1.y + (a2.y + a3.y);
+                    a0.z += a1.z + (a2.z + a3.z); a0.w += a1.w + (a2.w + a3.w);
+                }
+                float* t = tile + (r * 32 + q * 4) * T + tap;
+                t[0] = a0.x; t[T] = a0.y; t[2 * T] = a0.z; t[3 * T] = a0.w;
+            }
+            __syncthreads();
+            const float ig = inv[g];
+            for (int i = threadIdx.x; i < cells; i += 256) {
+                const int r = i / (32 * T), j = i - r * 32 * T;
+                if (m0 + r < M && j < nvalid * T) {
+                    const float v = tile[i];
+                    dot[g] += (double)v * (double)W[((int64_t)(m0 + r) * C + c0) * T + j];
+                    accs[i] += v * ig;
                 }
             }
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-            }
-            if (live && sl == 0) {
-                float* t = tile + (q * 4) * T + tap;
-                t[0] = acc.x; t[T] = acc.y; t[2 * T] = acc.z; t[3 * T] = acc.w;
-            }
+            __syncthreads();
         }
-        __syncthreads();
-        const int64_t o0 = ((int64_t)m * C + c0) * T;
-        for (int i = threadIdx.x; i < nvalid * T; i += 256) {
-            const float v = tile[i];
-            Gg[o0 + i] = v;
-            dot += (double)v * (double)W[o0 + i];
+        for (int i = threadIdx.x; i < cells; i += 256) {
+            const int r = i / (32 * T), j = i - r * 32 * T;
+            if (m0 + r < M && j < nvalid * T) dW[((int64_t)(m0 + r) * C + c0) * T + j] = accs[i];
         }
         __syncthreads();
     }
-    dot = warp_sum(dot);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int k = 0; k < 8; ++k) t += red[k];
-        dot_part[(int64_t)g * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x] = t;
+    for (int g = 0; g < groups; ++g) {
+        const double d = warp_sum(dot[g]);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int k = 0; k < 8; ++k) t += red[k];
+            dot_part[(int64_t)g * nparts + blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(256) sn_grad_groups_kernel(const float* __restrict__ Gbuf, int groups,
-                                                            const float* __restrict__ u_hist,
+// Pass B.  dW -= sum_g (<G_g, W> / sigma_g^2) u_g v_g^T   (rank-1 corrections; one read + one write of |W|)
+__global__ void __launch_bounds__(256) sn_grad_groups_kernel(int groups, const float* __restrict__ u_hist,
                                                             const float* __restrict__ v_hist,
                                                             const float* __restrict__ inv, const double* __restrict__ dot_part,
                                                             int nparts, float* __restrict__ dW, int h, int w) {
-    __shared__ float coef[kSnMaxGroups], invs[kSnMaxGroups];
+    __shared__ float coef[kSnMaxGroups];
     for (int g = threadIdx.x >> 5; g < groups; g += 8) {          // warp g: fixed-order sum of call g's partial dots
         double sdot = 0.0;
         for (int k = threadIdx.x & 31; k < nparts; k += 32) sdot += dot_part[(int64_t)g * nparts + k];
         sdot = warp_sum(sdot);
         if ((threadIdx.x & 31) == 0) {
             const float iv = inv[g];
-            invs[g] = iv;
             coef[g] = (float)sdot * iv * iv;
         }
     }
@@ -295,16 +318,14 @@ __global__ void __launch_bounds__(256) sn_grad_groups_kernel(const float* __rest
     const uint32_t n4 = n >> 2, w4 = (uint32_t)w >> 2;             // w % 4 == 0
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += gridDim.x * blockDim.x) {
         const uint32_t i = t / w4, j = (t - i * w4) << 2;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o = *reinterpret_cast<const float4*>(dW + (size_t)t * 4);
         for (int g = 0; g < groups; ++g) {
-            const float4 gv = *reinterpret_cast<const float4*>(Gbuf + (size_t)g * n + (size_t)t * 4);
-            const float* v = v_hist + (size_t)g * w + j;
+            const float* v = v_hist + (size_t)g * w + j;          // (the staged history is only 4-byte aligned)
             const float cu = coef[g] * u_hist[(size_t)g * h + i];
-            const float iv = invs[g];
-            o.x += gv.x * iv - cu * v[0];
-            o.y += gv.y * iv - cu * v[1];
-            o.z += gv.z * iv - cu * v[2];
-            o.w += gv.w * iv - cu * v[3];
+            o.x -= cu * v[0];
+            o.y -= cu * v[1];
+            o.z -= cu * v[2];
+            o.w -= cu * v[3];
         }
         *reinterpret_cast<float4*>(dW + (size_t)t * 4) = o;
     }
@@ -430,13 +451,23 @@ extern "C" int b200_sn_wgrad_finish(const float* ws, int groups, int splits_per_
                  "sn_wgrad_finish: needs C %% 4 == 0, T <= 64, M < 65536");
     B200_REQUIRE(((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(Gbuf) | reinterpret_cast<uintptr_t>(dW)) & 15) == 0,
                  "sn_wgrad_finish: buffers must be 16-byte aligned");
+    (void)Gbuf;                                   // kept in the signature; the per-call gradients are no longer materialised
     const int cb = (C + 31) / 32;
     const int nparts = b200_sn_wgrad_parts(M, C);
     const int rows = nparts / cb;
-    sn_wgrad_reduce_kernel<<<dim3(cb, rows, groups), 256, 0, st>>>(ws, splits_per_group, split_stride, M, T, C, W, Gbuf, dot_part);
+    int R = 256 / (T * 8);                        // rows per pass: about one (tap, channel quad) item per thread
+    if (R < 1) R = 1;
+    if (R > 32) R = 32;
+    if (R > M) R = M;
+    const size_t smem = (size_t)2 * R * 32 * T * sizeof(float);
+    B200_REQUIRE(smem <= 48 * 1024, "sn_wgrad_finish: tile too large");
+    int rblocks = (rows + R - 1) / R;
+    if (rblocks < 1) rblocks = 1;
+    sn_wgrad_reduce_kernel<<<dim3(cb, rblocks), 256, smem, st>>>(ws, groups, splits_per_group, split_stride, M, T, C, R, W, inv,
+                                                                dW, dot_part);
     B200_CHECK_LAUNCH();
     const int64_t n = (int64_t)M * C * T;
-    sn_grad_groups_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(Gbuf, groups, u_hist, v_hist, inv, dot_part, nparts, dW, M, C * T);
+    sn_grad_groups_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(groups, u_hist, v_hist, inv, dot_part, cb * rblocks, dW, M, C * T);
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -200,9 +200,11 @@ int b200_pack_weight(const float* src, void* dst, int dst_bf16, int M, int Mpad,
  * optimizer step (train64.py:258-262 / 366-370 update the weights every iteration; the operand matrices above must follow).
  * Entry e writes ONLY the valid elements dst[m*ldw + (j*Tw+i)*C_dst + c_off + c], m < M, c < C — padding (rows >= M,
  * columns >= Th*Tw*C_dst) is left untouched (the caller zero-fills it once at allocation), so several entries can fill
- * one matrix (SPADE's fused gamma|beta operand is packed from two parameters).  chunk_begin = number of
- * B200_PACK_CHUNK-element chunks of the entries before e (a prefix sum; the kernel maps one block to one chunk). */
-#define B200_PACK_CHUNK 8192
+ * one matrix (SPADE's fused gamma|beta operand is packed from two parameters).  The kernel maps one block to one chunk = a
+ * tile of B200_PACK_MT rows x B200_PACK_CT channels x all taps (staged through shared memory: coalesced on both sides); entry
+ * e owns ceil(M / B200_PACK_MT) * ceil(C / B200_PACK_CT) chunks and chunk_begin = the chunks of the entries before it. */
+#define B200_PACK_MT 8
+#define B200_PACK_CT 64
 typedef struct {
     const float* src;
     void* dst;
@@ -346,7 +348,8 @@ int b200_sn_grad(const float* g, const float* W, const float* u, const float* v,
  * b200_wgrad_gemm_* launch whose pixel splits are aligned with the call boundaries (splits [g*spg, (g+1)*spg) = call g).
  *   G_g = sum of call g's splits, transposed to the parameter layout (M, C, T);
  *   dW  = sum_g ( G_g * inv[g] - <G_g, W> * inv[g]^2 * u_hist[g] v_hist[g]^T ),  W viewed (M, C*T).
- * Gbuf: groups*M*C*T floats, dot_part: groups*b200_sn_wgrad_parts(M, C) doubles (scratch).  C % 4 == 0, T <= 64. */
+ * Gbuf: unused (may be NULL; the per-call gradients are no longer materialised), dot_part: groups*b200_sn_wgrad_parts(M, C)
+ * doubles (scratch).  C % 4 == 0, T <= 64. */
 int b200_sn_wgrad_parts(int M, int C);
 int b200_sn_wgrad_finish(const float* ws, int groups, int splits_per_group, int64_t split_stride, int M, int T, int C,
                          const float* W, const float* u_hist, const float* v_hist, const float* inv, float* Gbuf,
@@ -396,6 +399,31 @@ int b200_adam_multi(const b200_adam_entry* entries_dev, int n_entries, float* st
 int b200_one_hot_attributes(const int64_t* att_idx, int O, int A, int n_att, float* out, b200_stream_t stream);
 int b200_imagenet_deprocess(const float* imgs, int N, int C, int HW, const float* inv_std, const float* neg_mean,
                             int rescale, uint8_t* out, float* ws, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step arithmetic (train64.py:195-252, 284-364): each loss term is one launch producing
+ * its partial sums (doubles, one per block, row `slot` of partials[n_terms][B200_LOSS_MAX_BLOCKS], block count in
+ * counts[slot]) AND the gradient w.r.t. its inputs; b200_loss_total sums every slot in index order into terms[slot] and the
+ * grand total into terms[n_terms].  All tensors fp32; `scale` carries the lambda of the term; `weight` (per group) the
+ * 0.4 / 0.4 / 0.2 mix of the rec / rand / shift passes (batched calls are groups of n rows).
+ *   bce_groups  : scale * sum_g weight[g] * mean_i BCE_with_logits(x[g*n+i], target[g])            grad (groups*n)
+ *   ce_groups   : scale * sum_g weight[g] * mean_r CE(x[g*n+r, :C], label[r])                      grad (groups*n, C)
+ *   bce_pw_rows : scale * sum_g weight[g] * mean_{r: sel[r] != 0, a} BCE(x[g*n+r, a], t[r, a]; pos_weight[a])   grad (groups*n, A)
+ *   l1_rows     : scale * sum_n mask[n] * mean_L |a[n,:] - b[n,:]| / denom  (b_stride_n = 0: one shared b row; mask NULL = 1)
+ *   kl          : scale * -0.5 * sum(1 + logvar - mu^2 - exp(logvar))                              dmu, dlogvar */
+#define B200_LOSS_MAX_BLOCKS 1024
+int b200_loss_bce_groups(const float* x, int n, int groups, const float* target, const float* weight, float scale,
+                         float* grad, double* partials, int* counts, int slot, b200_stream_t stream);
+int b200_loss_ce_groups(const float* x, const int64_t* label, int n, int groups, int C, const float* weight, float scale,
+                        float* grad, double* partials, int* counts, int slot, b200_stream_t stream);
+int b200_loss_bce_pw_rows(const float* x, const float* t, const float* sel, int n, int groups, int A, int n_sel,
+                          const float* pos_weight, const float* weight, float scale, float* grad, double* partials,
+                          int* counts, int slot, b200_stream_t stream);
+int b200_loss_l1_rows(const float* a, const float* b, int N, int64_t L, int64_t b_stride_n, const float* mask, float denom,
+                      float scale, float* grad, double* partials, int* counts, int slot, b200_stream_t stream);
+int b200_loss_kl(const float* mu, const float* logvar, int64_t n, float scale, float* dmu, float* dlogvar, double* partials,
+                 int* counts, int slot, b200_stream_t stream);
+int b200_loss_total(const double* partials, const int* counts, int n_terms, float* terms, b200_stream_t stream);
 
 /* plain device-to-device copy on the stream (row concatenation of batched calls) */
 int b200_copy(void* dst, const void* src, size_t bytes, b200_stream_t stream);
