@@ -653,6 +653,47 @@ class Kernels:
         self._check(self.lib.b200_adam_multi(_ptr(table), int(n_entries), _ptr(step), C.c_double(lr), C.c_double(beta1),
                                              C.c_double(beta2), C.c_double(eps), _stream()), "b200_adam_multi")
 
+    # ---- fused step arithmetic (loss.cu) ------------------------------------------------------------------------
+    def loss_bce_groups(self, x, n, groups, split_group, target, weight, scale, partials, counts, slot):
+        grad = torch.empty_like(x)
+        self._check(self.lib.b200_loss_bce_groups(_ptr(x), int(n), int(groups), int(split_group), _ptr(target), _ptr(weight),
+                                                  C.c_float(scale), _ptr(grad), _ptr(partials), _ptr(counts), int(slot),
+                                                  _stream()), "b200_loss_bce_groups")
+        return grad
+
+    def loss_ce_groups(self, x, label, n, groups, weight, scale, partials, counts, slot):
+        grad = torch.empty_like(x)
+        self._check(self.lib.b200_loss_ce_groups(_ptr(x), _ptr(label), int(n), int(groups), int(x.shape[1]), _ptr(weight),
+                                                 C.c_float(scale), _ptr(grad), _ptr(partials), _ptr(counts), int(slot),
+                                                 _stream()), "b200_loss_ce_groups")
+        return grad
+
+    def loss_bce_pw_rows(self, x, t, sel, n, groups, n_sel, pos_weight, weight, scale, partials, counts, slot):
+        grad = torch.empty_like(x)
+        self._check(self.lib.b200_loss_bce_pw_rows(_ptr(x), _ptr(t), _ptr(sel), int(n), int(groups), int(x.shape[1]), int(n_sel),
+                                                   _ptr(pos_weight), _ptr(weight), C.c_float(scale), _ptr(grad), _ptr(partials),
+                                                   _ptr(counts), int(slot), _stream()), "b200_loss_bce_pw_rows")
+        return grad
+
+    def loss_l1_rows(self, a, b, N, L, b_stride_n, mask, denom, scale, partials, counts, slot):
+        grad = torch.empty_like(a)
+        self._check(self.lib.b200_loss_l1_rows(_ptr(a), _ptr(b), int(N), C.c_int64(L), C.c_int64(b_stride_n), _ptr(mask),
+                                               C.c_float(denom), C.c_float(scale), _ptr(grad), _ptr(partials), _ptr(counts),
+                                               int(slot), _stream()), "b200_loss_l1_rows")
+        return grad
+
+    def loss_kl(self, mu, logvar, scale, partials, counts, slot):
+        dmu, dlv = torch.empty_like(mu), torch.empty_like(logvar)
+        self._check(self.lib.b200_loss_kl(_ptr(mu), _ptr(logvar), C.c_int64(mu.numel()), C.c_float(scale), _ptr(dmu), _ptr(dlv),
+                                          _ptr(partials), _ptr(counts), int(slot), _stream()), "b200_loss_kl")
+        return dmu, dlv
+
+    def loss_total(self, partials, counts, n_terms):
+        terms = torch.empty((n_terms + 1,), dtype=torch.float32, device=partials.device)
+        self._check(self.lib.b200_loss_total(_ptr(partials), _ptr(counts), int(n_terms), _ptr(terms), _stream()),
+                    "b200_loss_total")
+        return terms
+
     def copy_into(self, dst, dst_row, src):
         """dst[dst_row : dst_row + src.shape[0]] = src (contiguous tensors of equal row size and dtype)"""
         if not (dst.is_cuda and src.is_cuda):

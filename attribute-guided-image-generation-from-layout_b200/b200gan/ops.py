@@ -1307,3 +1307,108 @@ class _ConvLSTMFn(torch.autograd.Function):
 
 def conv_lstm(x, plan: BatchPlan, layers: List[ConvLSTMLayer], params: Sequence[torch.Tensor]):
     return _ConvLSTMFn.apply(x, plan, layers, *params)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fused step arithmetic (train64.py:195-252, 284-364): every loss term one launch (value partials + gradient), one launch
+# for the total — instead of ~350 elementwise / reduction launches of the PyTorch formulation
+# ----------------------------------------------------------------------------------------------------------
+LOSS_MAX_BLOCKS = 1024
+_LOSS_CONST: Dict[tuple, torch.Tensor] = {}
+
+
+def _loss_const(values, device) -> torch.Tensor:
+    key = (tuple(float(v) for v in values), str(device))
+    t = _LOSS_CONST.get(key)
+    if t is None:
+        t = _LOSS_CONST[key] = torch.tensor(key[0], dtype=torch.float32, device=device)
+    return t
+
+
+class _FusedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, acc, *inputs):
+        terms = _lib.K.loss_total(acc.partials, acc.counts, len(acc.names))
+        acc.terms = terms
+        ctx.grads = list(acc.grads)
+        return terms[len(acc.names)].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = ctx.grads
+        torch._foreach_mul_(grads, g)          # (the reference calls total.backward(): g == 1; one multi-tensor launch keeps it general)
+        return (None,) + tuple(grads)
+
+
+class FusedLoss:
+    """Accumulator of one phase's loss terms.  Each `add_*` call launches one kernel that writes the term's partial sums into
+    its slot and returns nothing; `total()` launches the combine kernel and returns the total as an autograd scalar whose
+    backward hands every registered input the gradient its kernel already computed.  Term values: `term(name)` after total()."""
+
+    def __init__(self, names, device):
+        self.names = list(names)
+        n = len(self.names)
+        self.partials = torch.empty((n, LOSS_MAX_BLOCKS), dtype=torch.float64, device=device)
+        self.counts = torch.zeros((n,), dtype=torch.int32, device=device)
+        self.inputs, self.grads, self.terms = [], [], None
+        self.device = device
+
+    def _slot(self, name):
+        return self.names.index(name)
+
+    def _reg(self, x, grad):
+        self.inputs.append(x)
+        self.grads.append(grad.view(x.shape))
+
+    @staticmethod
+    def _flat(x):
+        x = x if x.dtype == torch.float32 else x.float()
+        return x.contiguous()
+
+    def add_bce_groups(self, name, x, groups, targets, weights, scale, split_group=None):
+        """scale * sum_g weights[g] * mean BCE_with_logits(x[group g], targets[g]); groups >= split_group go to the NEXT name"""
+        xc = self._flat(x)
+        n = xc.numel() // groups
+        g = _lib.K.loss_bce_groups(xc.view(-1), n, groups, groups if split_group is None else split_group,
+                                   _loss_const(targets, self.device), _loss_const(weights, self.device), float(scale),
+                                   self.partials, self.counts, self._slot(name))
+        self._reg(x, g)
+
+    def add_ce_groups(self, name, logits, labels, groups, weights, scale):
+        xc = self._flat(logits)
+        n = xc.shape[0] // groups
+        g = _lib.K.loss_ce_groups(xc, labels.contiguous(), n, groups, _loss_const(weights, self.device), float(scale),
+                                  self.partials, self.counts, self._slot(name))
+        self._reg(logits, g)
+
+    def add_bce_pos_weight_rows(self, name, logits, targets, sel, n_sel, pos_weight, groups, weights, scale):
+        xc = self._flat(logits)
+        n = xc.shape[0] // groups
+        g = _lib.K.loss_bce_pw_rows(xc, targets.contiguous(), sel, n, groups, int(n_sel), pos_weight,
+                                    _loss_const(weights, self.device), float(scale), self.partials, self.counts, self._slot(name))
+        self._reg(logits, g)
+
+    def add_l1_rows(self, name, a, b, rows, mask, denom, scale, broadcast_b=False):
+        ac = self._flat(a)
+        L = ac.numel() // rows
+        g = _lib.K.loss_l1_rows(ac, b.contiguous(), rows, L, 0 if broadcast_b else L, mask, float(denom), float(scale),
+                                self.partials, self.counts, self._slot(name))
+        self._reg(a, g)
+
+    def add_kl(self, name, mu, logvar, scale):
+        dmu, dlv = _lib.K.loss_kl(mu.contiguous(), logvar.contiguous(), float(scale), self.partials, self.counts, self._slot(name))
+        self._reg(mu, dmu)
+        self._reg(logvar, dlv)
+
+    def total(self):
+        return _FusedLossFn.apply(self, *self.inputs)
+
+    def term_dict(self, unscale=None):
+        """{name: value} (device scalars, views of one tensor); unscale: {name: factor} divides the lambda back out"""
+        out = {}
+        for i, n in enumerate(self.names):
+            v = self.terms[i]
+            if unscale and unscale.get(n, 1.0) not in (0.0, 1.0):
+                v = v / unscale[n]
+            out[n] = v
+        return out

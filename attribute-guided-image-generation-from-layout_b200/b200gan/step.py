@@ -97,7 +97,10 @@ class TrainStep:
     def __init__(self, image_size: int = 64, device="cuda", lr: float = 2e-4, lambdas: Optional[Dict[str, float]] = None,
                  pos_weight: Optional[torch.Tensor] = None, skip_dead_work: bool = True, fused_adam: bool = True,
                  capturable: bool = False, optimizer: str = "b200", att_matrix: Optional[torch.Tensor] = None,
-                 swap_rng=None):
+                 swap_rng=None, fused_losses: bool = True):
+        # fused_losses: the step arithmetic on the loss kernels of libb200gan (one launch per term, ops.FusedLoss) instead of
+        # the PyTorch formulation kept below as `d_loss_torch` / `g_loss_torch` (same numbers; ~350 launches per iteration)
+        self.fused_losses = fused_losses
         # att_matrix (179, 106) + swap_rng (random.Random): enable the reference's GT-attribute swap (train64.py:169-188)
         # in to_device(); without a matrix the batch's attributes are used as they are (the parity configuration)
         self.att_matrix, self.swap_rng = att_matrix, swap_rng
@@ -155,8 +158,12 @@ class TrainStep:
         b = {k: (v if k == "obj_to_img" else v.to(self.device, non_blocking=True)) for k, v in batch.items()}
         gt = batch.get("attribute_GT", batch["attribute"])
         b["att_idx"] = gt.sum(dim=1).nonzero().view(-1).to(self.device)                    # D-step: train64.py:241
+        sel = (gt.sum(dim=1) != 0)
+        b["att_sel"], b["n_att_sel"] = sel.float().to(self.device), int(sel.sum())           # the same set as a 0/1 row mask
         if "attribute_GT" in batch:
             b["att_idx_g"] = batch["attribute"].sum(dim=1).nonzero().view(-1).to(self.device)   # G-step: train64.py:323
+            sel = (batch["attribute"].sum(dim=1) != 0)
+            b["att_sel_g"], b["n_att_sel_g"] = sel.float().to(self.device), int(sel.sum())
         return b
 
     def generator(self, b, attribute_est):
@@ -167,6 +174,55 @@ class TrainStep:
     # Calls of one discriminator on different inputs are batched along dim 0 as `groups` (in the reference's call order):
     # every spectral-normalised layer then runs `groups` power iterations and scales call g's rows by its own 1/sigma_g.
     def d_loss(self, b, fake):
+        return self.d_loss_fused(b, fake) if self.fused_losses else self.d_loss_torch(b, fake)
+
+    def g_loss(self, b, fake):
+        return self.g_loss_fused(b, fake) if self.fused_losses else self.g_loss_torch(b, fake)
+
+    def d_loss_fused(self, b, fake):
+        """train64.py:195-252 on the loss kernels: 4 term launches + 1 combine launch"""
+        D_i, D_o, D_a = self.d_nets
+        objs, lam = b["objs"], self.lam
+        crops_input = fake["outputs"][0].detach()
+        w4 = FAKE_W + (1.0,)
+        acc = ops.FusedLoss(["d_img_fake", "d_img_real", "d_obj_fake", "d_obj_real", "d_obj_cls", "d_att"], self.device)
+        src = D_i(torch.cat([fake["imgs_fake"].detach(), b["imgs"]]), groups=4)
+        acc.add_bce_groups("d_img_fake", src, 4, (0, 0, 0, 1), w4, lam["img_adv"], split_group=3)
+        src, cls = D_o(torch.cat([fake["crops_fake"].detach(), crops_input]), objs, groups=4)
+        acc.add_bce_groups("d_obj_fake", src, 4, (0, 0, 0, 1), w4, lam["obj_adv"], split_group=3)
+        acc.add_ce_groups("d_obj_cls", cls, objs, 4, (0, 0, 0, 1), lam["obj_cls"])
+        acc.add_bce_pos_weight_rows("d_att", D_a(crops_input), b["attribute_GT"], b["att_sel"], b["n_att_sel"], self.pos_weight,
+                                    1, (1.0,), lam["att_cls"])
+        total = acc.total()
+        return total, acc.term_dict(dict(d_img_fake=lam["img_adv"], d_img_real=lam["img_adv"], d_obj_fake=lam["obj_adv"],
+                                         d_obj_real=lam["obj_adv"], d_obj_cls=lam["obj_cls"], d_att=lam["att_cls"]))
+
+    def g_loss_fused(self, b, fake):
+        """train64.py:284-364 on the loss kernels: 7 term launches + 1 combine launch"""
+        (crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift, mu, logvar, z_rand_rec,
+         z_rand_shift) = fake["outputs"]
+        D_i, D_o, D_a = self.d_nets
+        imgs, z, objs, lam = b["imgs"], b["z"], b["objs"], self.lam
+        N = imgs.shape[0]
+        n_change = math.floor(N / 3)
+        rec_mask = ops._loss_const([0.0] * n_change + [1.0] * (N - n_change), self.device)
+        acc = ops.FusedLoss(["g_img_rec", "g_z_rec", "g_kl", "g_img_adv", "g_obj_adv", "g_obj_cls", "g_obj_att"], self.device)
+        acc.add_l1_rows("g_img_rec", img_rec, imgs, N, rec_mask, N - n_change, lam["img_rec"])
+        # 0.5 * mean|z_rand_rec - z| + 0.5 * mean|z_rand_shift - z|: the two crop-encoder passes are rows of one (2, O*z) tensor
+        acc.add_l1_rows("g_z_rec", fake["mu2"], z, 2, None, 1.0, 0.5 * lam["z_rec"], broadcast_b=True)
+        acc.add_kl("g_kl", mu, logvar, lam["kl"])
+        acc.add_bce_groups("g_img_adv", D_i(fake["imgs_fake"], groups=3), 3, (1, 1, 1), FAKE_W, lam["img_adv"])
+        src, cls = D_o(fake["crops_fake"], objs, groups=3)
+        att = D_a(fake["crops_fake"], groups=3)
+        acc.add_bce_groups("g_obj_adv", src, 3, (1, 1, 1), FAKE_W, lam["obj_adv"])
+        acc.add_ce_groups("g_obj_cls", cls, objs, 3, FAKE_W, lam["obj_cls"])
+        acc.add_bce_pos_weight_rows("g_obj_att", att, b["attribute"], b.get("att_sel_g", b["att_sel"]),
+                                    b.get("n_att_sel_g", b["n_att_sel"]), self.pos_weight, 3, FAKE_W, lam["att_cls"])
+        total = acc.total()
+        return total, acc.term_dict(dict(g_img_rec=lam["img_rec"], g_z_rec=lam["z_rec"], g_kl=lam["kl"], g_img_adv=lam["img_adv"],
+                                         g_obj_adv=lam["obj_adv"], g_obj_cls=lam["obj_cls"], g_obj_att=lam["att_cls"]))
+
+    def d_loss_torch(self, b, fake):
         D_i, D_o, D_a = self.d_nets
         objs = b["objs"]
         N, O = b["imgs"].shape[0], objs.shape[0]
@@ -191,7 +247,7 @@ class TrainStep:
             + lam["obj_cls"] * l["d_obj_cls"] + lam["att_cls"] * l["d_att"]
         return total, l
 
-    def g_loss(self, b, fake):
+    def g_loss_torch(self, b, fake):
         (crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift, mu, logvar, z_rand_rec,
          z_rand_shift) = fake["outputs"]
         D_i, D_o, D_a = self.d_nets

@@ -532,29 +532,33 @@ __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const b200_pack_
     // full tap count of the parameter (the contiguous innermost run): s_c for forward operands, s_m for data-gradient ones
     const int64_t kk = en.s_c < en.s_m ? en.s_c : en.s_m;
     const bool inner_c = en.s_c == kk;                   // (c, tap) contiguous per row m; else (m, tap) contiguous per channel c
-    const bool staged = en.s_kx == 1 && kk * kPackCT <= kPackSmemFloats &&
+    const bool staged = en.s_kx == 1 && (kk | 1) * kPackCT <= kPackSmemFloats &&
                         kk >= (int64_t)(en.ky0 + en.kstep * (en.Th - 1)) * en.s_ky + en.kx0 + en.kstep * (en.Tw - 1) + 1;
     if (staged) {
         const int K = (int)kk;
-        const int mp = min(mt, kPackSmemFloats / (ct * K));      // rows per sub-pass (>= 1)
+        const int Kp = K | 1;                                    // odd tap pitch: the transposed shared reads spread over the banks
+        const int mp = min(mt, (kPackSmemFloats - kPackCT) / (ct * Kp));     // rows per sub-pass (>= 1)
         for (int ms = 0; ms < mt; ms += mp) {
             const int mc = min(mp, mt - ms);
-            // load: `outer` contiguous runs of `run` floats -> tile[outer][inner][K]
+            // load: `outer` contiguous runs of inner * K floats -> tile[outer][inner][Kp]
             const int outer = inner_c ? mc : ct, inner = inner_c ? ct : mc, run = inner * K;
+            const int P = (inner * Kp) | 1;                      // odd pitch between outer slabs as well
             const int64_t s_outer = inner_c ? en.s_m : en.s_c;
             const float* base = en.src + (int64_t)(m0 + ms) * en.s_m + (int64_t)c0 * en.s_c;
             for (int i = threadIdx.x; i < outer * run; i += 256) {
                 const int o = i / run, r = i - o * run;
-                tile[i] = base[(int64_t)o * s_outer + r];
+                const int in = r / K, k = r - in * K;
+                tile[o * P + in * Kp + k] = base[(int64_t)o * s_outer + r];
             }
             __syncthreads();
-            // store: rows (m, tap), ct contiguous channels
-            for (int i = threadIdx.x; i < mc * T * ct; i += 256) {
-                const int rw = i / ct, c = i - rw * ct;
+            // store: rows (m, tap), ct contiguous channels per row (consecutive threads = consecutive channels)
+            for (int rw = threadIdx.x / kPackCT; rw < mc * T; rw += 256 / kPackCT) {
+                const int c = threadIdx.x % kPackCT;
+                if (c >= ct) continue;
                 const int m = rw / T, tap = rw - m * T;
                 const int j = tap / en.Tw, ii = tap - j * en.Tw;
                 const int k = (en.ky0 + en.kstep * j) * (int)en.s_ky + (en.kx0 + en.kstep * ii);
-                const float v = inner_c ? tile[(m * ct + c) * K + k] : tile[(c * mc + m) * K + k];
+                const float v = inner_c ? tile[m * P + c * Kp + k] : tile[c * P + m * Kp + k];
                 const int64_t d = (int64_t)(m0 + ms + m) * en.ldw + (int64_t)tap * en.C_dst + en.c_off + c0 + c;
                 if (en.dst_bf16) reinterpret_cast<uint16_t*>(en.dst)[d] = f32_to_bf16_rn(v);
                 else reinterpret_cast<float*>(en.dst)[d] = v;

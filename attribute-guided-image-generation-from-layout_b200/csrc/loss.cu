@@ -27,24 +27,32 @@ __device__ __forceinline__ float softplus_neg(float x) { return fmaxf(-x, 0.f) +
 __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
 
 // term = scale * sum_g weight[g] * mean_{i in group g} BCE(x_i, target[g]);  x: groups * n logits
-__global__ void __launch_bounds__(256) loss_bce_groups_kernel(const float* __restrict__ x, int n, int groups,
+// groups >= split_group are summed into the NEXT slot (the fake / real halves of a discriminator's adversarial loss are one
+// launch but two reported terms, train64.py:195-212)
+__global__ void __launch_bounds__(256) loss_bce_groups_kernel(const float* __restrict__ x, int n, int groups, int split_group,
                                                               const float* __restrict__ target,
                                                               const float* __restrict__ weight, float scale,
                                                               float* __restrict__ grad, double* __restrict__ partial,
                                                               int* __restrict__ count) {
     __shared__ double sh[8];
     const int total = n * groups;
-    double acc = 0.0;
+    double acc = 0.0, acc2 = 0.0;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
         const int g = i / n;
         const float t = target[g], w = weight[g] * scale / (float)n, v = x[i];
-        acc += (double)(w * ((1.f - t) * v + softplus_neg(v)));
+        const double l = (double)(w * ((1.f - t) * v + softplus_neg(v)));
+        if (g < split_group) acc += l; else acc2 += l;
         grad[i] = w * (sigmoidf(v) - t);
     }
     const double s = block_sum_256(acc, sh);
+    const double s2 = block_sum_256(acc2, sh);
     if (threadIdx.x == 0) {
         partial[blockIdx.x] = s;
         if (blockIdx.x == 0) *count = gridDim.x;
+        if (split_group < groups) {
+            partial[B200_LOSS_MAX_BLOCKS + blockIdx.x] = s2;
+            if (blockIdx.x == 0) count[1] = gridDim.x;
+        }
     }
 }
 
@@ -192,11 +200,11 @@ using namespace b200;
 #define SLOT_ARGS double* partials, int* counts, int slot
 #define SLOT_PTRS partials + (int64_t)slot * B200_LOSS_MAX_BLOCKS, counts + slot
 
-extern "C" int b200_loss_bce_groups(const float* x, int n, int groups, const float* target, const float* weight, float scale,
-                                    float* grad, SLOT_ARGS, b200_stream_t stream) {
+extern "C" int b200_loss_bce_groups(const float* x, int n, int groups, int split_group, const float* target,
+                                    const float* weight, float scale, float* grad, SLOT_ARGS, b200_stream_t stream) {
     B200_REQUIRE(n > 0 && groups > 0, "loss_bce_groups: empty input");
-    loss_bce_groups_kernel<<<loss_blocks((int64_t)n * groups, 1024), 256, 0, as_stream(stream)>>>(x, n, groups, target, weight,
-                                                                                                   scale, grad, SLOT_PTRS);
+    loss_bce_groups_kernel<<<loss_blocks((int64_t)n * groups, 1024), 256, 0, as_stream(stream)>>>(
+        x, n, groups, split_group, target, weight, scale, grad, SLOT_PTRS);
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -213,18 +213,20 @@ __global__ void sn_grad_apply_kernel(const float* __restrict__ g, const float* _
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kSnMaxGroups = 8;
 
-// Pass A.  grid (ceil(C/32), row blocks), 256 threads; a block owns 32 channels x R rows (m) x all taps per pass and walks
-// the calls g = 0..groups-1 itself: per call the splits are summed (16-byte loads, up to 4 independent accumulators in flight),
-// transposed through shared memory from the partials' (m, tap, c) order to the parameter's (m, c, tap) order, dotted with W and
-// accumulated as G_g / sigma_g.  Output: dW_main = sum_g G_g / sigma_g (ONE write of |W|; the per-call G_g is never stored) and
-// the per-block partial dots <G_g, W>.  Traffic: (groups * spg + 1) |W| reads + |W| write  (was (2 groups + ...) |W| more).
+// Pass A.  grid (ceil(C/32), row blocks), 256 threads; a block owns 32 channels x R rows (m) x all taps per pass.  The W tile
+// of the pass is staged in shared memory (coalesced read, parameter order).  Each thread owns one (row, tap, channel quad)
+// item: it issues the 16-byte loads of ALL calls' splits back to back (groups * spg independent loads in flight), forms
+// G_g per call in registers, accumulates <G_g, W> against the staged tile and sum_g G_g / sigma_g, and writes the latter into
+// the transposing tile; one coalesced store of the (m, c, tap)-ordered result per pass.  Two block syncs per pass.
+// Output: dW_main = sum_g G_g / sigma_g and the per-block partial dots <G_g, W>; the per-call G_g is never stored.
 __global__ void __launch_bounds__(256) sn_wgrad_reduce_kernel(const float* __restrict__ ws, int groups, int spg,
                                                              int64_t split_stride, int M, int T, int C, int R,
                                                              const float* __restrict__ W, const float* __restrict__ inv,
                                                              float* __restrict__ dW, double* __restrict__ dot_part) {
     extern __shared__ float sn_smem[];
-    float* tile = sn_smem;                        // [R][32][T]
-    float* accs = sn_smem + R * 32 * T;           // [R][32][T]
+    const int TP = T | 1;                         // odd tap pitch: conflict-free transposed access
+    float* wtile = sn_smem;                       // [R][32][TP]  W, parameter order
+    float* otile = sn_smem + R * 32 * TP;         // [R][32][TP]  sum_g G_g / sigma_g
     __shared__ double red[8];
     const int c0 = blockIdx.x * 32;
     const int nvalid = C - c0 < 32 ? C - c0 : 32;                 // a multiple of 4
@@ -232,60 +234,52 @@ __global__ void __launch_bounds__(256) sn_wgrad_reduce_kernel(const float* __res
     const int items = R * per_row;
     const int cells = R * 32 * T;
     const int nparts = gridDim.x * gridDim.y;
+    float invs[kSnMaxGroups];
     double dot[kSnMaxGroups];
 #pragma unroll
-    for (int g = 0; g < kSnMaxGroups; ++g) dot[g] = 0.0;
+    for (int g = 0; g < kSnMaxGroups; ++g) { dot[g] = 0.0; invs[g] = g < groups ? inv[g] : 0.f; }
     for (int m0 = blockIdx.y * R; m0 < M; m0 += gridDim.y * R) {
-        for (int i = threadIdx.x; i < cells; i += 256) accs[i] = 0.f;
-        for (int g = 0; g < groups; ++g) {
-            const float* wsg = ws + (int64_t)g * spg * split_stride;
-            for (int it = threadIdx.x; it < items; it += 256) {
-                const int r = it / per_row, rem = it - r * per_row;
-                const int tap = rem >> 3, q = rem & 7;
-                const int m = m0 + r;
-                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-                if (m < M && q * 4 < nvalid) {
-                    const float* p = wsg + ((int64_t)m * T + tap) * C + c0 + q * 4;
-                    int sidx = 0;
-                    for (; sidx + 4 <= spg; sidx += 4) {
-                        const float4 v0 = *reinterpret_cast<const float4*>(p + (int64_t)sidx * split_stride);
-                        const float4 v1 = *reinterpret_cast<const float4*>(p + (int64_t)(sidx + 1) * split_stride);
-                        const float4 v2 = *reinterpret_cast<const float4*>(p + (int64_t)(sidx + 2) * split_stride);
-                        const float4 v3 = *reinterpret_cast<const float4*>(p + (int64_t)(sidx + 3) * split_stride);
-                        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-                        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
-                        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
-                        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
-                    }
-                    for (; sidx < spg; ++sidx) {
-                        const float4 v0 = *reinterpret_cast<const float4*>(p + (int64_t)sidx * split_stride);
-                        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-                    }
-                    a0.x += a1.x + (a2.x + a3.x); a0.y += a1.y + (a2.y + a3.y);
-                    a0.z += a1.z + (a2.z + a3.z); a0.w += a1.w + (a2.w + a3.w);
-                }
-                float* t = tile + (r * 32 + q * 4) * T + tap;
-                t[0] = a0.x; t[T] = a0.y; t[2 * T] = a0.z; t[3 * T] = a0.w;
-            }
-            __syncthreads();
-            const float ig = inv[g];
-            for (int i = threadIdx.x; i < cells; i += 256) {
-                const int r = i / (32 * T), j = i - r * 32 * T;
-                if (m0 + r < M && j < nvalid * T) {
-                    const float v = tile[i];
-                    dot[g] += (double)v * (double)W[((int64_t)(m0 + r) * C + c0) * T + j];
-                    accs[i] += v * ig;
-                }
-            }
-            __syncthreads();
-        }
         for (int i = threadIdx.x; i < cells; i += 256) {
             const int r = i / (32 * T), j = i - r * 32 * T;
-            if (m0 + r < M && j < nvalid * T) dW[((int64_t)(m0 + r) * C + c0) * T + j] = accs[i];
+            const int c = j / T, tap = j - c * T;
+            wtile[(r * 32 + c) * TP + tap] = (m0 + r < M && c < nvalid) ? W[((int64_t)(m0 + r) * C + c0) * T + j] : 0.f;
         }
         __syncthreads();
+        for (int it = threadIdx.x; it < items; it += 256) {
+            const int r = it / per_row, rem = it - r * per_row;
+            const int tap = rem >> 3, q = rem & 7;
+            const int m = m0 + r;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && q * 4 < nvalid) {
+                const float* p = ws + ((int64_t)m * T + tap) * C + c0 + q * 4;
+                const float* wt = wtile + (r * 32 + q * 4) * TP + tap;
+                const float w0 = wt[0], w1 = wt[TP], w2 = wt[2 * TP], w3 = wt[3 * TP];
+#pragma unroll
+                for (int g = 0; g < kSnMaxGroups; ++g) {
+                    if (g < groups) {
+                        const float* pg = p + (int64_t)g * spg * split_stride;
+                        float4 a = *reinterpret_cast<const float4*>(pg);
+                        for (int sidx = 1; sidx < spg; ++sidx) {
+                            const float4 v = *reinterpret_cast<const float4*>(pg + (int64_t)sidx * split_stride);
+                            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                        }
+                        dot[g] += (double)a.x * w0 + (double)a.y * w1 + (double)a.z * w2 + (double)a.w * w3;
+                        o.x += a.x * invs[g]; o.y += a.y * invs[g]; o.z += a.z * invs[g]; o.w += a.w * invs[g];
+                    }
+                }
+            }
+            float* t = otile + (r * 32 + q * 4) * TP + tap;
+            t[0] = o.x; t[TP] = o.y; t[2 * TP] = o.z; t[3 * TP] = o.w;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cells; i += 256) {
+            const int r = i / (32 * T), j = i - r * 32 * T;
+            const int c = j / T, tap = j - c * T;
+            if (m0 + r < M && c < nvalid) dW[((int64_t)(m0 + r) * C + c0) * T + j] = otile[(r * 32 + c) * TP + tap];
+        }
     }
     for (int g = 0; g < groups; ++g) {
+        __syncthreads();
         const double d = warp_sum(dot[g]);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
         __syncthreads();
@@ -294,7 +288,6 @@ __global__ void __launch_bounds__(256) sn_wgrad_reduce_kernel(const float* __res
             for (int k = 0; k < 8; ++k) t += red[k];
             dot_part[(int64_t)g * nparts + blockIdx.y * gridDim.x + blockIdx.x] = t;
         }
-        __syncthreads();
     }
 }
 
@@ -459,7 +452,7 @@ extern "C" int b200_sn_wgrad_finish(const float* ws, int groups, int splits_per_
     if (R < 1) R = 1;
     if (R > 32) R = 32;
     if (R > M) R = M;
-    const size_t smem = (size_t)2 * R * 32 * T * sizeof(float);
+    const size_t smem = (size_t)2 * R * 32 * (T | 1) * sizeof(float);
     B200_REQUIRE(smem <= 48 * 1024, "sn_wgrad_finish: tile too large");
     int rblocks = (rows + R - 1) / R;
     if (rblocks < 1) rblocks = 1;

@@ -322,4 +322,4 @@ class Generator(nn.Module):
         z_rand_rec, z_rand_shift = mu2[:O], mu2[O:]
         outputs = (crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift, mu, logvar,
                    z_rand_rec, z_rand_shift)
-        return dict(outputs=outputs, imgs_fake=imgs_fake, crops_fake=crops_fake)
+        return dict(outputs=outputs, imgs_fake=imgs_fake, crops_fake=crops_fake, mu2=mu2)

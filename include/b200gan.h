@@ -407,13 +407,14 @@ int b200_imagenet_deprocess(const float* imgs, int N, int C, int HW, const float
  * grand total into terms[n_terms].  All tensors fp32; `scale` carries the lambda of the term; `weight` (per group) the
  * 0.4 / 0.4 / 0.2 mix of the rec / rand / shift passes (batched calls are groups of n rows).
  *   bce_groups  : scale * sum_g weight[g] * mean_i BCE_with_logits(x[g*n+i], target[g])            grad (groups*n)
+ *                 (groups >= split_group are summed into slot + 1: the fake and the real half of an adversarial loss)
  *   ce_groups   : scale * sum_g weight[g] * mean_r CE(x[g*n+r, :C], label[r])                      grad (groups*n, C)
  *   bce_pw_rows : scale * sum_g weight[g] * mean_{r: sel[r] != 0, a} BCE(x[g*n+r, a], t[r, a]; pos_weight[a])   grad (groups*n, A)
  *   l1_rows     : scale * sum_n mask[n] * mean_L |a[n,:] - b[n,:]| / denom  (b_stride_n = 0: one shared b row; mask NULL = 1)
  *   kl          : scale * -0.5 * sum(1 + logvar - mu^2 - exp(logvar))                              dmu, dlogvar */
 #define B200_LOSS_MAX_BLOCKS 1024
-int b200_loss_bce_groups(const float* x, int n, int groups, const float* target, const float* weight, float scale,
-                         float* grad, double* partials, int* counts, int slot, b200_stream_t stream);
+int b200_loss_bce_groups(const float* x, int n, int groups, int split_group, const float* target, const float* weight,
+                         float scale, float* grad, double* partials, int* counts, int slot, b200_stream_t stream);
 int b200_loss_ce_groups(const float* x, const int64_t* label, int n, int groups, int C, const float* weight, float scale,
                         float* grad, double* partials, int* counts, int slot, b200_stream_t stream);
 int b200_loss_bce_pw_rows(const float* x, const float* t, const float* sel, int n, int groups, int A, int n_sel,

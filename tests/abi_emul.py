@@ -260,6 +260,68 @@ class EmulKernels:
                 blk = dst[dst_row_offset:dst_row_offset + M, :Th * Tw * C_dst].view(M, Th * Tw, C_dst)
                 blk[:, :, c_off:c_off + C] = v.reshape(M, Th * Tw, C).to(dst.dtype)
 
+    # ---- fused step arithmetic (loss.cu): values through torch's own functional ops, gradients through autograd ------
+    @staticmethod
+    def _loss_finish(loss_terms, xs, partials, counts, slot):
+        """loss_terms: list of scalar tensors (one per slot, starting at `slot`); returns the gradients of their sum"""
+        grads = torch.autograd.grad(sum(loss_terms), xs, allow_unused=True)
+        for i, t in enumerate(loss_terms):
+            partials[slot + i].zero_()
+            partials[slot + i, 0] = float(t)
+            counts[slot + i] = 1
+        return [g if g is not None else torch.zeros_like(x) for g, x in zip(grads, xs)]
+
+    def loss_bce_groups(self, x, n, groups, split_group, target, weight, scale, partials, counts, slot):
+        self.launches += 1
+        xv = x.detach().clone().requires_grad_(True)
+        per = F.binary_cross_entropy_with_logits(xv.view(groups, n), target.view(groups, 1).expand(groups, n), reduction="none").mean(1)
+        terms = [scale * (weight[:split_group] * per[:split_group]).sum()]
+        if split_group < groups:
+            terms.append(scale * (weight[split_group:] * per[split_group:]).sum())
+        return self._loss_finish(terms, [xv], partials, counts, slot)[0].view(x.shape)
+
+    def loss_ce_groups(self, x, label, n, groups, weight, scale, partials, counts, slot):
+        self.launches += 1
+        xv = x.detach().clone().requires_grad_(True)
+        per = F.cross_entropy(xv, label.repeat(groups), reduction="none").view(groups, n).mean(1)
+        return self._loss_finish([scale * (weight * per).sum()], [xv], partials, counts, slot)[0]
+
+    def loss_bce_pw_rows(self, x, t, sel, n, groups, n_sel, pos_weight, weight, scale, partials, counts, slot):
+        self.launches += 1
+        xv = x.detach().clone().requires_grad_(True)
+        idx = sel.nonzero().view(-1)
+        if idx.numel() == 0:
+            partials[slot].zero_(); counts[slot] = 1
+            return torch.zeros_like(x)
+        term = 0.0
+        for g in range(groups):
+            term = term + weight[g] * F.binary_cross_entropy_with_logits(xv[g * n:(g + 1) * n].index_select(0, idx),
+                                                                         t.index_select(0, idx), pos_weight=pos_weight)
+        return self._loss_finish([scale * term], [xv], partials, counts, slot)[0]
+
+    def loss_l1_rows(self, a, b, N, L, b_stride_n, mask, denom, scale, partials, counts, slot):
+        self.launches += 1
+        av = a.detach().clone().requires_grad_(True)
+        bb = b.reshape(1, L).expand(N, L) if b_stride_n == 0 else b.reshape(N, L)
+        per = (av.reshape(N, L) - bb).abs().mean(1)
+        m = mask if mask is not None else torch.ones(N)
+        return self._loss_finish([scale * (m * per).sum() / denom], [av], partials, counts, slot)[0].view(a.shape)
+
+    def loss_kl(self, mu, logvar, scale, partials, counts, slot):
+        self.launches += 1
+        m, lv = mu.detach().clone().requires_grad_(True), logvar.detach().clone().requires_grad_(True)
+        term = scale * (-0.5) * torch.sum(1 + lv - m.pow(2) - lv.exp())
+        g = self._loss_finish([term], [m, lv], partials, counts, slot)
+        return g[0], g[1]
+
+    def loss_total(self, partials, counts, n_terms):
+        self.launches += 1
+        terms = torch.zeros(n_terms + 1)
+        for s_ in range(n_terms):
+            terms[s_] = float(partials[s_, :int(counts[s_])].sum())
+        terms[n_terms] = float(terms[:n_terms].double().sum())
+        return terms
+
     def pack_table(self, recipes, device):
         return None, list(recipes), len(recipes), 0
 

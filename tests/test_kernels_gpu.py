@@ -930,3 +930,71 @@ def test_tf32_transpose_sn_and_lstm(K):
             close(pd[2 * i].grad, sd["c.cell_list.%d.conv.weight" % i].grad, 4e-3, "tf32 convlstm dw%d" % i)
     finally:
         ops.set_precision("fp32")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused step arithmetic (loss.cu; train64.py:195-252, 284-364) against torch's functional losses + autograd
+# ---------------------------------------------------------------------------------------------------------
+def test_fused_loss_terms_match_torch(K):
+    g = torch.Generator().manual_seed(17)
+    O_, N, A, C = 37, 5, 106, 179
+    dev = "cuda"
+    lam = dict(adv=1.5, cls=0.7, att=2.0, rec=1.3, z=8.0, kl=0.01)
+    src4 = torch.randn(4 * N, generator=g) * 2
+    cls3 = torch.randn(3 * O_, C, generator=g) * 3
+    att3 = torch.randn(3 * O_, A, generator=g) * 2
+    labels = torch.randint(0, C, (O_,), generator=g)
+    tgt = (torch.rand(O_, A, generator=g) < 0.02).float()
+    tgt[::3] = 0                                                   # un-annotated objects
+    sel = (tgt.sum(1) != 0).float()
+    pw = torch.rand(A, generator=g) * 50 + 1
+    img_a, img_b = torch.randn(N, 3, 16, 16, generator=g), torch.randn(N, 3, 16, 16, generator=g)
+    mask = torch.tensor([0.0, 1.0, 1.0, 1.0, 1.0])
+    mu2, z = torch.randn(2 * O_, 64, generator=g), torch.randn(O_, 64, generator=g)
+    mu, lv = torch.randn(O_, 64, generator=g), torch.randn(O_, 64, generator=g) * 0.3
+    w3, w4 = (0.4, 0.4, 0.2), (0.4, 0.4, 0.2, 1.0)
+
+    def leaf(t, d):
+        return t.clone().to(d).requires_grad_(True)
+
+    # ---- reference: the PyTorch formulation of b200gan/step.py (d_loss_torch / g_loss_torch) ----
+    r = {k: leaf(v, "cpu") for k, v in dict(src4=src4, cls3=cls3, att3=att3, img=img_a, mu2=mu2, mu=mu, lv=lv).items()}
+    bce = F.binary_cross_entropy_with_logits
+    per = bce(r["src4"], torch.tensor([0.0, 0, 0, 1]).repeat_interleave(N), reduction="none").view(4, N).mean(1)
+    t_fake, t_real = lam["adv"] * (torch.tensor(w3) * per[:3]).sum(), lam["adv"] * per[3]
+    t_cls = lam["cls"] * (torch.tensor(w3) * F.cross_entropy(r["cls3"], labels.repeat(3), reduction="none").view(3, O_).mean(1)).sum()
+    idx = sel.nonzero().view(-1)
+    t_att = lam["att"] * sum(w * bce(r["att3"][i * O_:(i + 1) * O_].index_select(0, idx), tgt.index_select(0, idx), pos_weight=pw)
+                             for i, w in enumerate(w3))
+    t_rec = lam["rec"] * (mask * (r["img"] - img_b).abs().view(N, -1).mean(1)).sum() / 4.0
+    t_z = lam["z"] * (0.5 * (r["mu2"][:O_] - z).abs().mean() + 0.5 * (r["mu2"][O_:] - z).abs().mean())
+    t_kl = lam["kl"] * -0.5 * torch.sum(1 + r["lv"] - r["mu"].pow(2) - r["lv"].exp())
+    want = [t_fake, t_real, t_cls, t_att, t_rec, t_z, t_kl]
+    sum(want).backward()
+
+    # ---- kernels ----
+    d = {k: leaf(v, dev) for k, v in dict(src4=src4, cls3=cls3, att3=att3, img=img_a, mu2=mu2, mu=mu, lv=lv).items()}
+    acc = ops.FusedLoss(["fake", "real", "cls", "att", "rec", "z", "kl"], dev)
+    acc.add_bce_groups("fake", d["src4"], 4, (0, 0, 0, 1), w4, lam["adv"], split_group=3)
+    acc.add_ce_groups("cls", d["cls3"], labels.to(dev), 3, w3, lam["cls"])
+    acc.add_bce_pos_weight_rows("att", d["att3"], tgt.to(dev), sel.to(dev), int(sel.sum()), pw.to(dev), 3, w3, lam["att"])
+    acc.add_l1_rows("rec", d["img"], img_b.to(dev), N, mask.to(dev), 4.0, lam["rec"])
+    acc.add_l1_rows("z", d["mu2"], z.to(dev), 2, None, 1.0, 0.5 * lam["z"], broadcast_b=True)
+    acc.add_kl("kl", d["mu"], d["lv"], lam["kl"])
+    total = acc.total()
+    total.backward()
+    terms = acc.terms.cpu()
+    for i, t in enumerate(want):
+        assert abs(float(terms[i]) - float(t)) <= 2e-6 * max(1.0, abs(float(t))), (acc.names[i], float(terms[i]), float(t))
+    assert abs(float(total) - float(sum(want))) <= 2e-6 * abs(float(sum(want)))
+    for k in r:
+        close(d[k].grad, r[k].grad, 2e-6, "fused loss grad " + k)
+    # rows without annotation and groups with zero weight receive exactly zero gradient
+    assert float(d["att3"].grad.view(3, O_, A)[:, sel == 0].abs().max()) == 0.0
+    acc2 = ops.FusedLoss(["c"], dev)
+    c4 = leaf(torch.randn(4 * O_, C, generator=g), dev)
+    acc2.add_ce_groups("c", c4, labels.to(dev), 4, (0, 0, 0, 1), 1.0)
+    acc2.total().backward()
+    assert float(c4.grad[:3 * O_].abs().max()) == 0.0 and float(c4.grad[3 * O_:].abs().max()) > 0.0
+    want_c = F.cross_entropy(c4.detach().cpu()[3 * O_:], labels)
+    assert abs(float(acc2.terms[0]) - float(want_c)) < 2e-6 * float(want_c)

@@ -191,3 +191,29 @@ def test_step_wiring_tf32_mode(emul):
     a = torch.cat([p.grad.reshape(-1) for _, p in ts.netG.named_parameters()]).double()
     r = torch.cat([ref["g_grads"][k].reshape(-1) for k, _ in ts.netG.named_parameters()]).double()
     assert float(cos(a, r, dim=0)) > 0.98       # measured 0.988 (the bf16 mode: 0.89 on the same step)
+
+
+def test_fused_losses_equal_the_torch_formulation(emul):
+    """TrainStep(fused_losses=True) (loss kernels, ops.FusedLoss) and the PyTorch formulation of the same step arithmetic give
+    the same totals, terms and gradients (host routing of the fused path: slots, groups, masks, lambda scaling)"""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    from b200gan.step import TrainStep
+    states = O.make_states(64, 0)
+    batch = O.synth_batch(3, 64, 3, 12, sparse_attributes=True)
+    runs = []
+    for fused in (True, False):
+        ts = TrainStep(64, device="cpu", fused_losses=fused)
+        load_states(ts, states)
+        res = ts.step(ts.to_device(batch), optimizer_step=False, seeds=(3, 4))
+        runs.append((ts, res))
+    (ta, ra), (tb, rb) = runs
+    assert abs(float(ra["d_loss"]) - float(rb["d_loss"])) < 1e-5 * abs(float(rb["d_loss"]))
+    assert abs(float(ra["g_loss"]) - float(rb["g_loss"])) < 1e-5 * abs(float(rb["g_loss"]))
+    for k in rb["d_terms"]:
+        assert abs(float(ra["d_terms"][k]) - float(rb["d_terms"][k])) < 1e-5 * max(1.0, abs(float(rb["d_terms"][k]))), k
+    for k in rb["g_terms"]:
+        assert abs(float(ra["g_terms"][k]) - float(rb["g_terms"][k])) < 1e-5 * max(1.0, abs(float(rb["g_terms"][k]))), k
+    for na, nb in ((ta.netG, tb.netG), (ta.netD_image, tb.netD_image), (ta.netD_object, tb.netD_object), (ta.netD_att, tb.netD_att)):
+        a = torch.cat([p.grad.reshape(-1) for p in na.parameters()])
+        b_ = torch.cat([p.grad.reshape(-1) for p in nb.parameters()])
+        assert rel(a, b_) < 1e-4
