@@ -416,8 +416,10 @@ class Kernels:
                     "b200_norm_fwd")
         return y
 
-    def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes, groups=1):
-        """reduce -> finalize -> apply.  Returns dx, dgamma, dbeta, dtable, dgb (None where not applicable)."""
+    def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes, groups=1, sync=None):
+        """reduce -> finalize -> apply.  Returns dx, dgamma, dbeta, dtable, dgb (None where not applicable).
+        sync: optional callable applied to the (groups*C*2,) fp32 tensor of per-group (sum dxhat, sum dxhat*xhat) between
+        finalize and apply (synchronised batch norm: all-reduce over the data-parallel ranks)."""
         rows, Cc = x2d.shape
         dev = x2d.device
         rpg = rows // groups
@@ -443,6 +445,8 @@ class Kernels:
         self._check(self.lib.b200_norm_bwd_finalize(_ptr(seg_sums), nseg, Cc, int(groups), int(mode), _ptr(gamma),
                                                     _ptr(idx), int(num_classes), _ptr(s), _ptr(dgamma), _ptr(dbeta),
                                                     _ptr(dtable), _stream()), "b200_norm_bwd_finalize")
+        if sync is not None:
+            s = sync(s)
         dx = torch.empty_like(x2d)
         if mode == MODE_SPADE:
             dgb = torch.empty((rows, 2 * Cc), dtype=x2d.dtype, device=dev)

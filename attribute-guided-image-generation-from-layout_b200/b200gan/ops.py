@@ -792,6 +792,46 @@ def linear(x2d, w, bias, packs: WeightPacks, relu=False, sn: Optional[SNCall] = 
 # ----------------------------------------------------------------------------------------------------------
 # normalisation
 # ----------------------------------------------------------------------------------------------------------
+# Synchronised batch statistics (the mechanism of the reference's vendored
+# models/spade/networks/sync_batchnorm/batchnorm.py:74-145): under data parallelism every normalisation layer all-reduces its
+# per-channel (sum x, sum x^2, count) in the forward pass and its (sum dxhat, sum dxhat * xhat) in the backward pass, so the
+# sharded step computes exactly the statistics — and, with the count-weighted losses of TrainStep, exactly the gradients — of
+# the single-process global batch.  Off by default (DDP semantics: per-shard statistics).
+_SYNC_BN = None          # process group (or True for the default group) while enabled
+
+
+def set_sync_bn(group):
+    """group: a torch.distributed process group, True for the default group, None to disable"""
+    global _SYNC_BN
+    _SYNC_BN = group
+
+
+def _sync_group():
+    return None if _SYNC_BN is True else _SYNC_BN
+
+
+def _sync_moments(mean, var, n_local, running_mean, running_var):
+    """global (mean, biased var) per group from the shards' local ones; running statistics updated with the GLOBAL values in
+    call order (momentum 0.1, unbiased variance).  Returns mean, var (fp32) and n_local / n_global per group (G, 1) fp32."""
+    import torch.distributed as dist
+    G, C = mean.shape
+    buf = torch.empty((G, 2 * C + 1), dtype=torch.float64, device=mean.device)
+    m64 = mean.double()
+    buf[:, :C] = m64 * n_local
+    buf[:, C:2 * C] = (var.double() + m64 * m64) * n_local
+    buf[:, 2 * C] = float(n_local)
+    dist.all_reduce(buf, group=_sync_group())
+    n = buf[:, 2 * C:2 * C + 1]
+    gm = buf[:, :C] / n
+    gv = (buf[:, C:2 * C] / n - gm * gm).clamp_(min=0.0)
+    if running_mean is not None:
+        unb = gv * (n / (n - 1.0).clamp(min=1.0))
+        for g in range(G):
+            running_mean.mul_(1.0 - BN_MOMENTUM).add_(gm[g].float(), alpha=BN_MOMENTUM)
+            running_var.mul_(1.0 - BN_MOMENTUM).add_(unb[g].float(), alpha=BN_MOMENTUM)
+    return gm.float().contiguous(), gv.float().contiguous(), (float(n_local) / n).float()
+
+
 class _NormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, idx, running_mean, running_var, mode, training, relu, residual, rows_per_seg,
@@ -799,7 +839,11 @@ class _NormFn(torch.autograd.Function):
         shape = x.shape
         C = shape[-1]
         x2 = x.reshape(-1, C)
-        if training:
+        ctx.sync_ratio = None
+        if training and _SYNC_BN is not None:
+            mean, var = _lib.K.bn_stats(x2, None, None, BN_MOMENTUM, groups)
+            mean, var, ctx.sync_ratio = _sync_moments(mean, var, x2.shape[0] // groups, running_mean, running_var)
+        elif training:
             mean, var = _lib.K.bn_stats(x2, running_mean, running_var, BN_MOMENTUM, groups)
         else:
             mean, var, groups = running_mean, running_var, 1
@@ -824,8 +868,18 @@ class _NormFn(torch.autograd.Function):
         x2, y, mean, var, g2, idx = ctx.saved_tensors
         C = x2.shape[1]
         dy2 = dy.contiguous().reshape(-1, C)
+        sync = None
+        if ctx.sync_ratio is not None:
+            ratio, grp, G = ctx.sync_ratio, _sync_group(), ctx.groups
+
+            def sync(s_):
+                # (sum dxhat, sum dxhat * xhat) summed over the ranks; the apply kernel divides by the LOCAL row count, so the
+                # global mean is sum / n_global = (sum * n_local / n_global) / n_local
+                import torch.distributed as dist
+                dist.all_reduce(s_, group=grp)
+                return (s_.view(G, -1) * ratio).reshape(-1).contiguous()
         dx, dgamma, dbeta, dtable, dgb = _lib.K.norm_bwd(dy2, x2, y, mean, var, BN_EPS, ctx.mode, g2, idx,
-                                                         ctx.rows_per_seg, ctx.relu, ctx.num_classes, ctx.groups)
+                                                         ctx.rows_per_seg, ctx.relu, ctx.num_classes, ctx.groups, sync=sync)
         dres = None
         if ctx.has_residual:
             dres = _lib.K.relu_bwd(dy2, y).view(ctx.shape) if ctx.relu else dy

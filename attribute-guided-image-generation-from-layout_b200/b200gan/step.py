@@ -130,14 +130,43 @@ class TrainStep:
         self.opt_D = [Adam(n.parameters(), **kw) for n in (self.netD_image, self.netD_object, self.netD_att)]
         self.d_nets = (self.netD_image, self.netD_object, self.netD_att)
         self.ddp_d = self.ddp_g = None
+        self.sync_bn = False
 
-    def enable_data_parallel(self, bucket_bytes: int = 25 << 20, group=None):
-        """Shard-local step + bucketed gradient all-reduce overlapped with backward (b200gan/ddp.py)."""
+    def enable_data_parallel(self, bucket_bytes: int = 25 << 20, group=None, sync_bn: bool = False):
+        """Shard-local step + bucketed gradient all-reduce overlapped with backward (b200gan/ddp.py).
+
+        sync_bn=False: DDP semantics — batch-norm statistics and loss means are per shard.
+        sync_bn=True : exact global-batch semantics: every normalisation layer all-reduces its
+        statistics (ops.set_sync_bn) and every loss mean is weighted by world * n_local / n_global (counts exchanged once per
+        batch in to_device), so the averaged gradients equal those of the single-process step on the concatenated batch."""
+        import torch.distributed as dist
         from .ddp import GradBucketer, broadcast_module
         for n in (self.netG,) + tuple(self.d_nets):
             broadcast_module(n, group=group)
         self.ddp_d = GradBucketer([p for n in self.d_nets for p in n.parameters()], bucket_bytes, group)
         self.ddp_g = GradBucketer(list(self.netG.parameters()), bucket_bytes, group)
+        self.dp_group, self.sync_bn = group, bool(sync_bn)
+        self.dp_world, self.dp_rank = dist.get_world_size(group), dist.get_rank(group)
+        if sync_bn:
+            if not self.fused_losses:
+                raise ValueError("sync_bn needs the fused loss path (count-weighted terms)")
+            ops.set_sync_bn(group if group is not None else True)
+
+    def _global_counts(self, batch, b):
+        """per-term weights world * n_local / n_global and the global image offset of this shard (sync_bn mode)"""
+        import torch.distributed as dist
+        N, O = batch["imgs"].shape[0], batch["objs"].shape[0]
+        mine = torch.tensor([N, O, b["n_att_sel"], b.get("n_att_sel_g", b["n_att_sel"])], dtype=torch.float64, device=self.device)
+        allc = [torch.zeros_like(mine) for _ in range(self.dp_world)]
+        dist.all_gather(allc, mine, group=self.dp_group)
+        allc = torch.stack(allc).cpu()
+        tot = allc.sum(0)
+        W = float(self.dp_world)
+        n_tot, offset = int(tot[0]), int(allc[:self.dp_rank, 0].sum())
+        n_change = math.floor(n_tot / 3)
+        f = lambda i, mine_i: (W * mine_i / float(tot[i])) if float(tot[i]) > 0 else 0.0
+        return dict(img=f(0, N), obj=f(1, O), att=f(2, b["n_att_sel"]), att_g=f(3, b.get("n_att_sel_g", b["n_att_sel"])), sum=W,
+                    rec_mask=[0.0 if offset + i < n_change else 1.0 for i in range(N)], rec_denom=float(n_tot - n_change))
 
     # ---- batch handling ---------------------------------------------------------------------------------
     def to_device(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -164,6 +193,8 @@ class TrainStep:
             b["att_idx_g"] = batch["attribute"].sum(dim=1).nonzero().view(-1).to(self.device)   # G-step: train64.py:323
             sel = (batch["attribute"].sum(dim=1) != 0)
             b["att_sel_g"], b["n_att_sel_g"] = sel.float().to(self.device), int(sel.sum())
+        if self.sync_bn:
+            b["dp"] = self._global_counts(batch, b)
         return b
 
     def generator(self, b, attribute_est):
@@ -185,14 +216,15 @@ class TrainStep:
         objs, lam = b["objs"], self.lam
         crops_input = fake["outputs"][0].detach()
         w4 = FAKE_W + (1.0,)
+        dp = b.get("dp") or dict(img=1.0, obj=1.0, att=1.0, att_g=1.0, sum=1.0)     # count weights (sync_bn data parallel)
         acc = ops.FusedLoss(["d_img_fake", "d_img_real", "d_obj_fake", "d_obj_real", "d_obj_cls", "d_att"], self.device)
         src = D_i(torch.cat([fake["imgs_fake"].detach(), b["imgs"]]), groups=4)
-        acc.add_bce_groups("d_img_fake", src, 4, (0, 0, 0, 1), w4, lam["img_adv"], split_group=3)
+        acc.add_bce_groups("d_img_fake", src, 4, (0, 0, 0, 1), w4, lam["img_adv"] * dp["img"], split_group=3)
         src, cls = D_o(torch.cat([fake["crops_fake"].detach(), crops_input]), objs, groups=4)
-        acc.add_bce_groups("d_obj_fake", src, 4, (0, 0, 0, 1), w4, lam["obj_adv"], split_group=3)
-        acc.add_ce_groups("d_obj_cls", cls, objs, 4, (0, 0, 0, 1), lam["obj_cls"])
+        acc.add_bce_groups("d_obj_fake", src, 4, (0, 0, 0, 1), w4, lam["obj_adv"] * dp["obj"], split_group=3)
+        acc.add_ce_groups("d_obj_cls", cls, objs, 4, (0, 0, 0, 1), lam["obj_cls"] * dp["obj"])
         acc.add_bce_pos_weight_rows("d_att", D_a(crops_input), b["attribute_GT"], b["att_sel"], b["n_att_sel"], self.pos_weight,
-                                    1, (1.0,), lam["att_cls"])
+                                    1, (1.0,), lam["att_cls"] * dp["att"])
         total = acc.total()
         return total, acc.term_dict(dict(d_img_fake=lam["img_adv"], d_img_real=lam["img_adv"], d_obj_fake=lam["obj_adv"],
                                          d_obj_real=lam["obj_adv"], d_obj_cls=lam["obj_cls"], d_att=lam["att_cls"]))
@@ -205,19 +237,23 @@ class TrainStep:
         imgs, z, objs, lam = b["imgs"], b["z"], b["objs"], self.lam
         N = imgs.shape[0]
         n_change = math.floor(N / 3)
-        rec_mask = ops._loss_const([0.0] * n_change + [1.0] * (N - n_change), self.device)
+        dp = b.get("dp")
+        if dp is None:      # single process / DDP semantics: the first floor(N/3) images of THIS batch are excluded (train64.py:284-287)
+            dp = dict(img=1.0, obj=1.0, att=1.0, att_g=1.0, sum=1.0, rec_mask=[0.0] * n_change + [1.0] * (N - n_change),
+                      rec_denom=float(N - n_change))
+        rec_mask = ops._loss_const(dp["rec_mask"], self.device)
         acc = ops.FusedLoss(["g_img_rec", "g_z_rec", "g_kl", "g_img_adv", "g_obj_adv", "g_obj_cls", "g_obj_att"], self.device)
-        acc.add_l1_rows("g_img_rec", img_rec, imgs, N, rec_mask, N - n_change, lam["img_rec"])
+        acc.add_l1_rows("g_img_rec", img_rec, imgs, N, rec_mask, dp["rec_denom"], lam["img_rec"] * dp["sum"])
         # 0.5 * mean|z_rand_rec - z| + 0.5 * mean|z_rand_shift - z|: the two crop-encoder passes are rows of one (2, O*z) tensor
-        acc.add_l1_rows("g_z_rec", fake["mu2"], z, 2, None, 1.0, 0.5 * lam["z_rec"], broadcast_b=True)
-        acc.add_kl("g_kl", mu, logvar, lam["kl"])
-        acc.add_bce_groups("g_img_adv", D_i(fake["imgs_fake"], groups=3), 3, (1, 1, 1), FAKE_W, lam["img_adv"])
+        acc.add_l1_rows("g_z_rec", fake["mu2"], z, 2, None, 1.0, 0.5 * lam["z_rec"] * dp["obj"], broadcast_b=True)
+        acc.add_kl("g_kl", mu, logvar, lam["kl"] * dp["sum"])
+        acc.add_bce_groups("g_img_adv", D_i(fake["imgs_fake"], groups=3), 3, (1, 1, 1), FAKE_W, lam["img_adv"] * dp["img"])
         src, cls = D_o(fake["crops_fake"], objs, groups=3)
         att = D_a(fake["crops_fake"], groups=3)
-        acc.add_bce_groups("g_obj_adv", src, 3, (1, 1, 1), FAKE_W, lam["obj_adv"])
-        acc.add_ce_groups("g_obj_cls", cls, objs, 3, FAKE_W, lam["obj_cls"])
+        acc.add_bce_groups("g_obj_adv", src, 3, (1, 1, 1), FAKE_W, lam["obj_adv"] * dp["obj"])
+        acc.add_ce_groups("g_obj_cls", cls, objs, 3, FAKE_W, lam["obj_cls"] * dp["obj"])
         acc.add_bce_pos_weight_rows("g_obj_att", att, b["attribute"], b.get("att_sel_g", b["att_sel"]),
-                                    b.get("n_att_sel_g", b["n_att_sel"]), self.pos_weight, 3, FAKE_W, lam["att_cls"])
+                                    b.get("n_att_sel_g", b["n_att_sel"]), self.pos_weight, 3, FAKE_W, lam["att_cls"] * dp["att_g"])
         total = acc.total()
         return total, acc.term_dict(dict(g_img_rec=lam["img_rec"], g_z_rec=lam["z_rec"], g_kl=lam["kl"], g_img_adv=lam["img_adv"],
                                          g_obj_adv=lam["obj_adv"], g_obj_cls=lam["obj_cls"], g_obj_att=lam["att_cls"]))

@@ -377,7 +377,7 @@ class EmulKernels:
             y = y + residual
         return (F.relu(y) if relu else y).to(dt)
 
-    def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes, groups=1):
+    def norm_bwd(self, dy, x2d, y, mean, var, eps, mode, gamma, idx, rows_per_seg, relu, num_classes, groups=1, sync=None):
         self.launches += 4
         dt = x2d.dtype
         assert dy.dtype == dt and (y is None or y.dtype == dt) and (mode != MODE_SPADE or gamma.dtype == dt)
@@ -396,8 +396,12 @@ class EmulKernels:
             g = dy * (y > 0).to(dy.dtype) if relu else dy
         gm, _ = self._g_b(mode, gamma, gamma if mode == MODE_AFFINE else None, idx, rows_per_seg, rows, C)
         dxh = g if gm is None else g * gm
-        s1 = dxh.double().view(groups, rpg, C).sum(1).float().repeat_interleave(rpg, dim=0)
-        s2 = (dxh.double() * xh.double()).view(groups, rpg, C).sum(1).float().repeat_interleave(rpg, dim=0)
+        s1 = dxh.double().view(groups, rpg, C).sum(1).float()
+        s2 = (dxh.double() * xh.double()).view(groups, rpg, C).sum(1).float()
+        if sync is not None:          # b200_norm_bwd_finalize's output layout: [group][channel][2]
+            sg = sync(torch.stack([s1, s2], dim=2).reshape(-1).contiguous()).view(groups, C, 2)
+            s1, s2 = sg[:, :, 0], sg[:, :, 1]
+        s1, s2 = s1.repeat_interleave(rpg, dim=0), s2.repeat_interleave(rpg, dim=0)
         dx = rstd_r * (dxh - s1 / rpg - xh * s2 / rpg)
         dgamma = dbeta = dtable = dgb = None
         if mode == MODE_AFFINE:
