@@ -46,7 +46,7 @@ class SNLayer(C.Structure):
                 ("u_hist", C.c_void_p), ("v_hist", C.c_void_p), ("h", C.c_int), ("w", C.c_int)]
 
 
-PACK_MT, PACK_CT = 8, 64          # B200_PACK_MT / B200_PACK_CT (include/b200gan.h)
+PACK_MT, PACK_CT = 32, 64         # B200_PACK_MT / B200_PACK_CT (include/b200gan.h)
 
 
 class PackEntry(C.Structure):
@@ -372,6 +372,7 @@ class Kernels:
         with the attributes of ops.PackRecipe); the copy is an asynchronous pinned copy (capturable)"""
         arr = (PackEntry * len(recipes))()
         chunks = 0
+        owner = []
         for i, r in enumerate(recipes):
             esz = 2 if r.bf16 else 4
             cd = r.C_dst if r.C_dst > 0 else r.C
@@ -379,16 +380,22 @@ class Kernels:
                                r.dst.data_ptr() + esz * int(r.dst_row_offset) * int(r.ldw), r.ldw, r.s_m, r.s_ky, r.s_kx,
                                r.s_c, int(bool(r.bf16)), r.M, r.Th, r.Tw, r.C, cd, r.c_off if r.C_dst > 0 else 0, r.ky0,
                                r.kx0, r.kstep, chunks, 0)
-            chunks += -(-r.M // PACK_MT) * -(-r.C // PACK_CT)
+            n = -(-r.M // PACK_MT) * -(-r.C // PACK_CT)
+            owner.append(torch.full((n,), i, dtype=torch.int32))
+            chunks += n
         nbytes = C.sizeof(arr)
         host = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
         C.memmove(host.data_ptr(), C.addressof(arr), nbytes)
         dev = torch.empty((nbytes,), dtype=torch.uint8, device=device)
         dev.copy_(host, non_blocking=True)
-        return host, dev, len(recipes), chunks
+        owner_host = torch.cat(owner).pin_memory()
+        owner_dev = torch.empty_like(owner_host, device=device)
+        owner_dev.copy_(owner_host, non_blocking=True)
+        return (host, owner_host), (dev, owner_dev), len(recipes), chunks
 
     def pack_weight_multi(self, table_dev, n_entries, total_chunks):
-        self._check(self.lib.b200_pack_weight_multi(_ptr(table_dev), int(n_entries), int(total_chunks), _stream()),
+        dev, owner = table_dev
+        self._check(self.lib.b200_pack_weight_multi(_ptr(dev), int(n_entries), int(total_chunks), _ptr(owner), _stream()),
                     "b200_pack_weight_multi")
 
     # ---- normalisation --------------------------------------------------------------------------------------

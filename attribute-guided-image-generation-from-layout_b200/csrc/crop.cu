@@ -168,9 +168,174 @@ __global__ void crop_bwd_cols_kernel(const float* __restrict__ T, const float* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Shared-memory staged variants (the default): one block per (box, channel).
+// Forward: the box's source coordinates are computed ONCE per block (HH + WW evaluations instead of two per output pixel),
+// the pixel footprint of the box in the image plane is staged in shared memory with coalesced row reads, and every output
+// pixel takes its four taps from there; stores are coalesced along j.  Arithmetic (coordinates, floors, weights, tap order)
+// is exactly that of crop_fwd_kernel, so the results are bit-identical to it.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kCropMaxS = 128;                 // crop side the staged kernels take
+constexpr int kCropFootFloats = 8192;          // 32 KB footprint tile (e.g. 90 x 90 pixels); larger boxes read global memory
+
+__global__ void __launch_bounds__(256) crop_fwd_staged_kernel(const float* __restrict__ feats, const float* __restrict__ boxes,
+                                                             const int32_t* __restrict__ box_to_img,
+                                                             const float* __restrict__ wx, const float* __restrict__ wy,
+                                                             float* __restrict__ crops, int C, int H, int W, int HH, int WW) {
+    __shared__ float sx[kCropMaxS], sy[kCropMaxS];           // source coordinates per crop column / row
+    __shared__ float foot[kCropFootFloats];
+    __shared__ int ext[4];
+    const int b = blockIdx.x / C, c = blockIdx.x - b * C;
+    const float* bx = boxes + b * 4;
+    for (int t = threadIdx.x; t < WW + HH; t += 256) {
+        if (t < WW) sx[t] = crop_coord(bx[0], bx[2], wx[t], wx[WW + t], W);
+        else sy[t - WW] = crop_coord(bx[1], bx[3], wy[t - WW], wy[HH + t - WW], H);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                                    // footprint = [min floor, max floor + 1] clamped to the plane
+        float ylo = INFINITY, yhi = -INFINITY, xlo = INFINITY, xhi = -INFINITY;
+        for (int i = threadIdx.x; i < HH; i += 32) { const float f = floorf(sy[i]); ylo = fminf(ylo, f); yhi = fmaxf(yhi, f); }
+        for (int j = threadIdx.x; j < WW; j += 32) { const float f = floorf(sx[j]); xlo = fminf(xlo, f); xhi = fmaxf(xhi, f); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ylo = fminf(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = fmaxf(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+            xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+        }
+        if (threadIdx.x == 0) {
+            // NaN / huge coordinates (degenerate boxes) collapse to an empty footprint: every tap is out of bounds anyway
+            const bool ok = ylo == ylo && xlo == xlo && fabsf(ylo) < 1e8f && fabsf(yhi) < 1e8f && fabsf(xlo) < 1e8f && fabsf(xhi) < 1e8f;
+            ext[0] = ok ? max((int)ylo, 0) : 0;
+            ext[1] = ok ? min((int)yhi + 1, H - 1) : -1;
+            ext[2] = ok ? max((int)xlo, 0) : 0;
+            ext[3] = ok ? min((int)xhi + 1, W - 1) : -1;
+        }
+    }
+    __syncthreads();
+    const int y0f = ext[0], y1f = ext[1], x0f = ext[2], x1f = ext[3];
+    const int fh = y1f - y0f + 1, fw = x1f - x0f + 1;
+    const float* plane = feats + ((int64_t)box_to_img[b] * C + c) * H * W;
+    const bool staged = fh > 0 && fw > 0 && fh * fw <= kCropFootFloats;
+    if (staged) {
+        for (int t = threadIdx.x; t < fh * fw; t += 256) {
+            const int r = t / fw, q = t - r * fw;
+            foot[t] = plane[(y0f + r) * W + x0f + q];
+        }
+    }
+    __syncthreads();
+    float* out = crops + ((int64_t)b * C + c) * HH * WW;
+    for (int t = threadIdx.x; t < HH * WW; t += 256) {
+        const int i = t / WW, j = t - i * WW;
+        const float ix = sx[j], iy = sy[i];
+        const float xf = floorf(ix), yf = floorf(iy);
+        float v = 0.f;
+        if (xf >= -1.f && xf < (float)W && yf >= -1.f && yf < (float)H) {       // (also false for NaN coordinates)
+            const int x0 = (int)xf, y0 = (int)yf;
+            const float wx1 = ix - xf, wy1 = iy - yf;
+            const float wx0 = (xf + 1.f) - ix, wy0 = (yf + 1.f) - iy;
+            const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
+            const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
+            if (staged) {
+                const float* p = foot + (y0 - y0f) * fw + (x0 - x0f);
+                if (vy0 && vx0) v += p[0] * (wx0 * wy0);
+                if (vy0 && vx1) v += p[1] * (wx1 * wy0);
+                if (vy1 && vx0) v += p[fw] * (wx0 * wy1);
+                if (vy1 && vx1) v += p[fw + 1] * (wx1 * wy1);
+            } else {
+                const float* p = plane + y0 * W + x0;
+                if (vy0 && vx0) v += p[0] * (wx0 * wy0);
+                if (vy0 && vx1) v += p[1] * (wx1 * wy0);
+                if (vy1 && vx0) v += p[W] * (wx0 * wy1);
+                if (vy1 && vx1) v += p[W + 1] * (wx1 * wy1);
+            }
+        }
+        out[t] = v;
+    }
+}
+
+// Backward, staged: one block per (image, channel, row tile).  The gradient tile of the image plane is accumulated in shared
+// memory while the block walks the image's boxes in ascending order: per box the crop gradient (HH x WW) is staged with
+// coalesced reads, pass 1 folds its rows into the tile rows (T[y][j] = sum_i wy(i -> y) d[i][j], ascending i), pass 2 folds
+// the columns (acc[y][x] += sum_j wx(j -> x) T[y][j], ascending j, continuing the running sum) — the summation order of
+// crop_bwd_rows/cols_kernel, so the result is bit-identical to them; nothing but the final tile touches global memory.
+constexpr int kCropTileRows = 32;
+__global__ void __launch_bounds__(256) crop_bwd_staged_kernel(const float* __restrict__ dcrops, const float* __restrict__ boxes,
+                                                             const int32_t* __restrict__ img_box_start,
+                                                             const int32_t* __restrict__ box_order,
+                                                             const float* __restrict__ wx, const float* __restrict__ wy,
+                                                             const int4* __restrict__ ext, float* __restrict__ dfeats, int C,
+                                                             int H, int W, int HH, int WW) {
+    extern __shared__ float cb_smem[];
+    float* acc = cb_smem;                                  // [kCropTileRows][W]
+    float* dt = acc + kCropTileRows * W;                    // [HH][WW]   crop gradient of the current box
+    float* T = dt + HH * WW;                                // [kCropTileRows][WW]
+    float* sx = T + kCropTileRows * WW;                     // [WW] source x coordinate per crop column
+    float* sy = sx + WW;                                    // [HH]
+    const int n = blockIdx.x / C, c = blockIdx.x - n * C;
+    const int ty0 = blockIdx.y * kCropTileRows;
+    const int trows = min(kCropTileRows, H - ty0);
+    for (int t = threadIdx.x; t < trows * W; t += 256) acc[t] = 0.f;
+    for (int k = img_box_start[n]; k < img_box_start[n + 1]; ++k) {
+        const int b = box_order[k];
+        const int4 e = ext[b];
+        const int ya = max(e.x, ty0), yb = min(e.y, ty0 + trows - 1);
+        if (ya > yb || e.z > e.w) continue;                   // (uniform per block)
+        const float* bx = boxes + b * 4;
+        __syncthreads();
+        for (int t = threadIdx.x; t < WW + HH; t += 256) {
+            if (t < WW) sx[t] = crop_coord(bx[0], bx[2], wx[t], wx[WW + t], W);
+            else sy[t - WW] = crop_coord(bx[1], bx[3], wy[t - WW], wy[HH + t - WW], H);
+        }
+        const float* d = dcrops + ((int64_t)b * C + c) * HH * WW;
+        for (int t = threadIdx.x; t < HH * WW; t += 256) dt[t] = d[t];
+        __syncthreads();
+        const float cy0 = sy[0], cy1 = sy[HH - 1], cx0 = sx[0], cx1 = sx[WW - 1];
+        const int nr = yb - ya + 1;
+        for (int t = threadIdx.x; t < nr * WW; t += 256) {        // pass 1
+            const int r = t / WW, j = t - r * WW;
+            const int y = ya + r;
+            int lo, hi;
+            tap_range(cy0, cy1, HH, y, lo, hi);
+            float a = 0.f;
+            for (int i = lo; i < hi; ++i) {
+                const float iy = sy[i], yf = floorf(iy);
+                const int y0 = (int)yf;
+                if (y0 == y) a += ((yf + 1.f) - iy) * dt[i * WW + j];
+                else if (y0 + 1 == y) a += (iy - yf) * dt[i * WW + j];
+            }
+            T[r * WW + j] = a;
+        }
+        __syncthreads();
+        const int xa = e.z, nx = e.w - e.z + 1;
+        for (int t = threadIdx.x; t < nr * nx; t += 256) {        // pass 2
+            const int r = t / nx, x = xa + (t - r * nx);
+            int lo, hi;
+            tap_range(cx0, cx1, WW, x, lo, hi);
+            float a = acc[(ya - ty0 + r) * W + x];
+            const float* row = T + r * WW;
+            for (int j = lo; j < hi; ++j) {
+                const float ix = sx[j], xf = floorf(ix);
+                const int x0 = (int)xf;
+                if (x0 == x) a += ((xf + 1.f) - ix) * row[j];
+                else if (x0 + 1 == x) a += (ix - xf) * row[j];
+            }
+            acc[(ya - ty0 + r) * W + x] = a;
+        }
+    }
+    __syncthreads();
+    float* out = dfeats + (((int64_t)n * C + c) * H + ty0) * W;
+    for (int t = threadIdx.x; t < trows * W; t += 256) out[t] = acc[t];
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+static int g_crop_staged = 1;
+extern "C" int b200_crop_set_staged(int enable) {
+    const int prev = g_crop_staged;
+    g_crop_staged = enable ? 1 : 0;
+    return prev;
+}
 
 extern "C" int b200_crop_fwd(const float* feats, const float* boxes, const int32_t* box_to_img, const float* wx,
                              const float* wy, float* crops, int N, int C, int H, int W, int B, int HH, int WW,
@@ -179,8 +344,12 @@ extern "C" int b200_crop_fwd(const float* feats, const float* boxes, const int32
     if (B == 0) return 0;
     int64_t total = (int64_t)B * HH * WW;
     B200_REQUIRE(total < (1ll << 31), "crop_fwd: too many crop pixels");
-    crop_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(feats, boxes, box_to_img, wx, wy, crops, C, H,
-                                                                         W, B, HH, WW);
+    if (g_crop_staged && HH <= kCropMaxS && WW <= kCropMaxS && (int64_t)B * C < (1ll << 31))
+        crop_fwd_staged_kernel<<<(unsigned)(B * C), 256, 0, as_stream(stream)>>>(feats, boxes, box_to_img, wx, wy, crops, C, H,
+                                                                                W, HH, WW);
+    else
+        crop_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(feats, boxes, box_to_img, wx, wy, crops, C, H,
+                                                                             W, B, HH, WW);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -202,6 +371,21 @@ extern "C" int b200_crop_bwd(const float* dcrops, const float* boxes, const int3
     int4* ext = reinterpret_cast<int4*>(ws + (t1 + 3) / 4 * 4);
     B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "crop_bwd: workspace must be 16-byte aligned");
     B200_REQUIRE(t1 < (1ll << 31) && (int64_t)N * C * H * W < (1ll << 31), "crop_bwd: tensors too large");
+    const size_t smem = ((size_t)kCropTileRows * W + (size_t)HH * WW + (size_t)kCropTileRows * WW + WW + HH) * sizeof(float);
+    if (g_crop_staged && smem <= 200 * 1024 && (int64_t)N * C < (1ll << 31)) {
+        if (B > 0) {
+            crop_extents_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(boxes, wx, wy, ext, B, H, W, HH, WW);
+            B200_CHECK_LAUNCH();
+        }
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(crop_bwd_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            B200_REQUIRE(e == cudaSuccess, "crop_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        }
+        crop_bwd_staged_kernel<<<dim3((unsigned)(N * C), (unsigned)((H + kCropTileRows - 1) / kCropTileRows)), 256, smem,
+                                 as_stream(stream)>>>(dcrops, boxes, img_box_start, box_order, wx, wy, ext, dfeats, C, H, W, HH, WW);
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
     if (B > 0) {
         crop_extents_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(boxes, wx, wy, ext, B, H, W, HH, WW);
         B200_CHECK_LAUNCH();

@@ -512,16 +512,23 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restri
 // — data-gradient operands, whose rows are the convolution's INPUT channels), the operand matrix is written in 64-element
 // row segments.  Entries with another stride pattern (none on the path) take the element-wise fallback.
 // Block b -> (entry, tile) by binary search over the chunk prefix sums; same element mapping as pack_weight_kernel.
-constexpr int kPackMT = 8, kPackCT = 64;
+constexpr int kPackMT = B200_PACK_MT, kPackCT = B200_PACK_CT;
 constexpr int kPackSmemFloats = 12288;                       // 48 KB: 8 x 64 x 24 taps; wider kernels go in row sub-passes
 
-__global__ void __launch_bounds__(256) pack_weight_multi_kernel(const b200_pack_entry* __restrict__ entries, int n_entries) {
+__global__ void __launch_bounds__(256) pack_weight_multi_kernel(const b200_pack_entry* __restrict__ entries, int n_entries,
+                                                               const int32_t* __restrict__ chunk_entry) {
     __shared__ float tile[kPackSmemFloats];
     const int b = blockIdx.x;
-    int lo = 0, hi = n_entries - 1;
-    while (lo < hi) {                                   // last entry with chunk_begin <= b
-        int mid = (lo + hi + 1) >> 1;
-        if (entries[mid].chunk_begin <= b) lo = mid; else hi = mid - 1;
+    int lo;
+    if (chunk_entry) {
+        lo = chunk_entry[b];                            // host-built block -> entry map: one load instead of a search
+    } else {
+        lo = 0;
+        int hi = n_entries - 1;
+        while (lo < hi) {                               // last entry with chunk_begin <= b
+            int mid = (lo + hi + 1) >> 1;
+            if (entries[mid].chunk_begin <= b) lo = mid; else hi = mid - 1;
+        }
     }
     const b200_pack_entry en = entries[lo];
     const int T = en.Th * en.Tw;
@@ -1126,10 +1133,10 @@ extern "C" int b200_pack_weight(const float* src, void* dst, int dst_bf16, int M
 }
 
 extern "C" int b200_pack_weight_multi(const b200_pack_entry* entries_dev, int n_entries, int total_chunks,
-                                      b200_stream_t stream) {
+                                      const int32_t* chunk_entry_dev, b200_stream_t stream) {
     if (n_entries <= 0 || total_chunks <= 0) return 0;
     B200_REQUIRE(entries_dev != nullptr, "pack_weight_multi: null table");
-    pack_weight_multi_kernel<<<total_chunks, 256, 0, as_stream(stream)>>>(entries_dev, n_entries);
+    pack_weight_multi_kernel<<<total_chunks, 256, 0, as_stream(stream)>>>(entries_dev, n_entries, chunk_entry_dev);
     B200_CHECK_LAUNCH();
     return 0;
 }

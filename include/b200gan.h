@@ -84,6 +84,11 @@ int b200_crop_taps(const float* boxes, const float* wx, const float* wy, int32_t
 int b200_crop_bwd(const float* dcrops, const float* boxes, const int32_t* img_box_start, const int32_t* box_order,
                   const float* wx, const float* wy, float* dfeats, float* ws, int N, int C, int H, int W, int B,
                   int HH, int WW, b200_stream_t stream);
+/* The crop kernels stage each box's source footprint (forward) / the image-plane gradient tile and the crop gradient
+ * (backward) in shared memory — coalesced global traffic, coordinates computed once per box — and are bit-identical to the
+ * element-wise kernels they replace; b200_crop_set_staged(0) selects the element-wise kernels (parity tests compare the two).
+ * Returns the previous setting. */
+int b200_crop_set_staged(int enable);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolutions as gather-GEMMs — replace every nn.Conv2d / nn.ConvTranspose2d / nn.Linear forward,
@@ -203,7 +208,7 @@ int b200_pack_weight(const float* src, void* dst, int dst_bf16, int M, int Mpad,
  * one matrix (SPADE's fused gamma|beta operand is packed from two parameters).  The kernel maps one block to one chunk = a
  * tile of B200_PACK_MT rows x B200_PACK_CT channels x all taps (staged through shared memory: coalesced on both sides); entry
  * e owns ceil(M / B200_PACK_MT) * ceil(C / B200_PACK_CT) chunks and chunk_begin = the chunks of the entries before it. */
-#define B200_PACK_MT 8
+#define B200_PACK_MT 32
 #define B200_PACK_CT 64
 typedef struct {
     const float* src;
@@ -212,7 +217,9 @@ typedef struct {
     int32_t dst_bf16, M, Th, Tw, C, C_dst, c_off, ky0, kx0, kstep;
     int32_t chunk_begin, pad;
 } b200_pack_entry;
-int b200_pack_weight_multi(const b200_pack_entry* entries_dev, int n_entries, int total_chunks, b200_stream_t stream);
+/* chunk_entry_dev (optional, total_chunks int32): entry index of every chunk — saves each block the binary search */
+int b200_pack_weight_multi(const b200_pack_entry* entries_dev, int n_entries, int total_chunks,
+                           const int32_t* chunk_entry_dev, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Normalisation family — replaces nn.BatchNorm1d/2d, ConditionalBatchNorm2d (generator_obj_att.py:31-44),
