@@ -213,6 +213,10 @@ class Kernels:
                                            N, Cc, H, W, B, HH, WW, _stream()), "b200_crop_fwd")
         return out
 
+    def crop_set_staged(self, enable: bool) -> bool:
+        """shared-memory staged crop kernels (default) vs the element-wise ones; returns the previous setting"""
+        return bool(self.lib.b200_crop_set_staged(int(bool(enable))))
+
     def crop_taps(self, boxes, wx, wy, H, W, HH, WW):
         B = boxes.shape[0]
         dev = boxes.device

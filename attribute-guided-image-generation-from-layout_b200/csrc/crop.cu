@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) crop_fwd_staged_kernel(const float* __res
 // coalesced reads, pass 1 folds its rows into the tile rows (T[y][j] = sum_i wy(i -> y) d[i][j], ascending i), pass 2 folds
 // the columns (acc[y][x] += sum_j wx(j -> x) T[y][j], ascending j, continuing the running sum) — the summation order of
 // crop_bwd_rows/cols_kernel, so the result is bit-identical to them; nothing but the final tile touches global memory.
-constexpr int kCropTileRows = 32;
+constexpr int kCropTileRows = 8;        // short tiles: more blocks, and a block walks only the boxes that overlap its rows
 __global__ void __launch_bounds__(256) crop_bwd_staged_kernel(const float* __restrict__ dcrops, const float* __restrict__ boxes,
                                                              const int32_t* __restrict__ img_box_start,
                                                              const int32_t* __restrict__ box_order,

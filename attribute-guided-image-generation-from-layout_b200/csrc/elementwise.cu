@@ -513,7 +513,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restri
 // row segments.  Entries with another stride pattern (none on the path) take the element-wise fallback.
 // Block b -> (entry, tile) by binary search over the chunk prefix sums; same element mapping as pack_weight_kernel.
 constexpr int kPackMT = B200_PACK_MT, kPackCT = B200_PACK_CT;
-constexpr int kPackSmemFloats = 12288;                       // 48 KB: 8 x 64 x 24 taps; wider kernels go in row sub-passes
+constexpr int kPackSmemFloats = 11264;                       // 44 KB staging tile (+ 3.2 KB of index tables): wider kernels go in row sub-passes
 
 __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const b200_pack_entry* __restrict__ entries, int n_entries,
                                                                const int32_t* __restrict__ chunk_entry) {
@@ -539,36 +539,53 @@ __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const b200_pack_
     // full tap count of the parameter (the contiguous innermost run): s_c for forward operands, s_m for data-gradient ones
     const int64_t kk = en.s_c < en.s_m ? en.s_c : en.s_m;
     const bool inner_c = en.s_c == kk;                   // (c, tap) contiguous per row m; else (m, tap) contiguous per channel c
-    const bool staged = en.s_kx == 1 && (kk | 1) * kPackCT <= kPackSmemFloats &&
+    const bool staged = en.s_kx == 1 && kk <= 25 && T <= 32 && (kk | 1) * kPackCT <= kPackSmemFloats &&
                         kk >= (int64_t)(en.ky0 + en.kstep * (en.Th - 1)) * en.s_ky + en.kx0 + en.kstep * (en.Tw - 1) + 1;
     if (staged) {
         const int K = (int)kk;
         const int Kp = K | 1;                                    // odd tap pitch: the transposed shared reads spread over the banks
         const int mp = min(mt, (kPackSmemFloats - kPackCT) / (ct * Kp));     // rows per sub-pass (>= 1)
+        // index tables (integer divisions once per block, not per element): position of run element r inside a staged slab,
+        // and per selected tap its source offset inside the K taps of the parameter
+        __shared__ uint16_t rpos[kPackCT * 25];                  // run <= 64 channels (or <= 32 rows) x 25 taps
+        __shared__ uint8_t tapk[32];
+        const int inner_max = inner_c ? ct : min(mp, mt);
+        for (int r = threadIdx.x; r < inner_max * K; r += 256) {
+            const int in = r / K, k = r - in * K;
+            rpos[r] = (uint16_t)(in * Kp + k);
+        }
+        for (int tap = threadIdx.x; tap < T; tap += 256) {
+            const int j = tap / en.Tw, ii = tap - j * en.Tw;
+            tapk[tap] = (uint8_t)((en.ky0 + en.kstep * j) * (int)en.s_ky + (en.kx0 + en.kstep * ii));
+        }
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (int ms = 0; ms < mt; ms += mp) {
             const int mc = min(mp, mt - ms);
-            // load: `outer` contiguous runs of inner * K floats -> tile[outer][inner][Kp]
+            // load: `outer` contiguous runs of inner * K floats -> tile[outer][inner][Kp]; one warp per run, lanes along it
             const int outer = inner_c ? mc : ct, inner = inner_c ? ct : mc, run = inner * K;
             const int P = (inner * Kp) | 1;                      // odd pitch between outer slabs as well
             const int64_t s_outer = inner_c ? en.s_m : en.s_c;
             const float* base = en.src + (int64_t)(m0 + ms) * en.s_m + (int64_t)c0 * en.s_c;
-            for (int i = threadIdx.x; i < outer * run; i += 256) {
-                const int o = i / run, r = i - o * run;
-                const int in = r / K, k = r - in * K;
-                tile[o * P + in * Kp + k] = base[(int64_t)o * s_outer + r];
+            for (int o = warp; o < outer; o += 8) {
+                const float* src = base + (int64_t)o * s_outer;
+                float* dstt = tile + o * P;
+                for (int r = lane; r < run; r += 32) dstt[rpos[r]] = src[r];
             }
             __syncthreads();
-            // store: rows (m, tap), ct contiguous channels per row (consecutive threads = consecutive channels)
-            for (int rw = threadIdx.x / kPackCT; rw < mc * T; rw += 256 / kPackCT) {
-                const int c = threadIdx.x % kPackCT;
-                if (c >= ct) continue;
-                const int m = rw / T, tap = rw - m * T;
-                const int j = tap / en.Tw, ii = tap - j * en.Tw;
-                const int k = (en.ky0 + en.kstep * j) * (int)en.s_ky + (en.kx0 + en.kstep * ii);
-                const float v = inner_c ? tile[m * P + c * Kp + k] : tile[c * P + m * Kp + k];
-                const int64_t d = (int64_t)(m0 + ms + m) * en.ldw + (int64_t)tap * en.C_dst + en.c_off + c0 + c;
-                if (en.dst_bf16) reinterpret_cast<uint16_t*>(en.dst)[d] = f32_to_bf16_rn(v);
-                else reinterpret_cast<float*>(en.dst)[d] = v;
+            // store: rows (m, tap), ct contiguous channels per row: 4 rows per pass, 64 threads along the channels
+            const int c = threadIdx.x & (kPackCT - 1);
+            if (c < ct) {
+                for (int m = 0; m < mc; ++m) {
+                    const int64_t drow = (int64_t)(m0 + ms + m) * en.ldw + en.c_off + c0 + c;
+                    const float* tsrc = inner_c ? tile + m * P + c * Kp : tile + c * P + m * Kp;
+                    for (int tap = threadIdx.x >> 6; tap < T; tap += 4) {
+                        const float v = tsrc[tapk[tap]];
+                        const int64_t d = drow + (int64_t)tap * en.C_dst;
+                        if (en.dst_bf16) reinterpret_cast<uint16_t*>(en.dst)[d] = f32_to_bf16_rn(v);
+                        else reinterpret_cast<float*>(en.dst)[d] = v;
+                    }
+                }
             }
             __syncthreads();
         }

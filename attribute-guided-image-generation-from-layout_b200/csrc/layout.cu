@@ -118,6 +118,17 @@ __global__ void m2l_taps_kernel(const float* __restrict__ boxes, const float* __
     }
 }
 
+// conservative pixel footprint of object o along one axis: every output index whose source coordinate can have an
+// in-bounds tap (source index in (-1, M)  <=>  X in (-1/(2M), 1 + 1/(2M))), one pixel of slack
+__device__ __forceinline__ void m2l_extent(float lo, float hi, int M, int S, int& a, int& b) {
+    const float ext = hi - lo;
+    if (!(ext > 0.f)) { a = 0; b = S - 1; return; }
+    const float m = ext / (float)(2 * M);
+    const float fa = floorf((lo - m) * (float)(S - 1)) - 1.f, fb = ceilf((hi + m) * (float)(S - 1)) + 1.f;
+    a = fa < 0.f ? 0 : (fa > (float)(S - 1) ? S - 1 : (int)fa);
+    b = fb < 0.f ? 0 : (fb > (float)(S - 1) ? S - 1 : (int)fb);
+}
+
 constexpr int kM2LObj = 32;      // objects per pass: their per-pixel mask samples live in registers
 
 // block = 256 consecutive pixels of image blockIdx.y; the image's embeddings (<= 32 per pass) are staged in shared
@@ -143,29 +154,55 @@ __global__ void __launch_bounds__(256) m2l_fwd_kernel(const float* __restrict__ 
             for (int d = 0; d < D; ++d) obase[(int64_t)d * HW] = 0.f;
         return;
     }
+    __shared__ int sel[kM2LObj];
+    __shared__ int nsel_s;
+    const int p_last = min(blockIdx.x * 256 + 255, HW - 1);
+    const int ty0 = (blockIdx.x * 256) / W, ty1 = p_last / W;       // image rows this block's pixels lie in
+    bool first = true;
     for (int kb = k0; kb < k1; kb += kM2LObj) {
-        const int cnt = min(kM2LObj, k1 - kb);
+        const int cnt0 = min(kM2LObj, k1 - kb);
         __syncthreads();
+        // cull: only the objects whose (conservative) row footprint meets the block's rows can contribute; the survivors
+        // keep their ascending order (ballot compaction), so the summation order of the full walk is preserved
+        if (threadIdx.x < 32) {
+            bool hit = false;
+            int o = 0;
+            if ((int)threadIdx.x < cnt0) {
+                o = obj_order[kb + threadIdx.x];
+                const float4 bx = *reinterpret_cast<const float4*>(boxes + (int64_t)o * 4);
+                int ya, yb;
+                m2l_extent(bx.y, bx.w, M, H, ya, yb);
+                hit = ya <= ty1 && yb >= ty0;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (hit) sel[__popc(bal & ((1u << threadIdx.x) - 1u))] = o;
+            if (threadIdx.x == 0) nsel_s = __popc(bal);
+        }
+        __syncthreads();
+        const int cnt = nsel_s;
+        if (cnt == 0) continue;                                      // (uniform)
         for (int i = threadIdx.x; i < cnt * D4; i += 256) {
             const int j = i / D4, d4 = i - j * D4;
-            vec_s[j * D4 + d4] = reinterpret_cast<const float4*>(vecs + (int64_t)obj_order[kb + j] * D)[d4];
+            vec_s[j * D4 + d4] = reinterpret_cast<const float4*>(vecs + (int64_t)sel[j] * D)[d4];
         }
         float s[kM2LObj];
 #pragma unroll
         for (int j = 0; j < kM2LObj; ++j) {
             s[j] = 0.f;
             if (j < cnt) {
-                const int o = obj_order[kb + j];
+                const int o = sel[j];
                 const float4 bx = *reinterpret_cast<const float4*>(boxes + (int64_t)o * 4);
                 s[j] = m2l_sample(masks + (int64_t)o * M * M, M, m2l_coord(lx, bx.x, bx.z, M), m2l_coord(ly, bx.y, bx.w, M));
             }
         }
         __syncthreads();
+        const bool had = !first;
+        first = false;
         if (!live) continue;
         for (int d4 = 0; d4 < D4; ++d4) {
             float* o4 = obase + (int64_t)(4 * d4) * HW;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kb > k0) acc = make_float4(o4[0], o4[HW], o4[2 * (int64_t)HW], o4[3 * (int64_t)HW]);
+            if (had) acc = make_float4(o4[0], o4[HW], o4[2 * (int64_t)HW], o4[3 * (int64_t)HW]);
 #pragma unroll
             for (int j = 0; j < kM2LObj; ++j) {
                 if (j < cnt) {
@@ -176,17 +213,8 @@ __global__ void __launch_bounds__(256) m2l_fwd_kernel(const float* __restrict__ 
             o4[0] = acc.x; o4[HW] = acc.y; o4[2 * (int64_t)HW] = acc.z; o4[3 * (int64_t)HW] = acc.w;
         }
     }
-}
-
-// conservative pixel footprint of object o along one axis: every output index whose source coordinate can have an
-// in-bounds tap (source index in (-1, M)  <=>  X in (-1/(2M), 1 + 1/(2M))), one pixel of slack
-__device__ __forceinline__ void m2l_extent(float lo, float hi, int M, int S, int& a, int& b) {
-    const float ext = hi - lo;
-    if (!(ext > 0.f)) { a = 0; b = S - 1; return; }
-    const float m = ext / (float)(2 * M);
-    const float fa = floorf((lo - m) * (float)(S - 1)) - 1.f, fb = ceilf((hi + m) * (float)(S - 1)) + 1.f;
-    a = fa < 0.f ? 0 : (fa > (float)(S - 1) ? S - 1 : (int)fa);
-    b = fb < 0.f ? 0 : (fb > (float)(S - 1) ? S - 1 : (int)fb);
+    if (first && live)                                            // no object reaches these rows: zeros
+        for (int d = 0; d < D; ++d) obase[(int64_t)d * HW] = 0.f;
 }
 
 // backward, pass A — one block per object, restricted to the object's pixel footprint:

@@ -998,3 +998,36 @@ def test_fused_loss_terms_match_torch(K):
     assert float(c4.grad[:3 * O_].abs().max()) == 0.0 and float(c4.grad[3 * O_:].abs().max()) > 0.0
     want_c = F.cross_entropy(c4.detach().cpu()[3 * O_:], labels)
     assert abs(float(acc2.terms[0]) - float(want_c)) < 2e-6 * float(want_c)
+
+
+@pytest.mark.parametrize("N,H,S,per", [(4, 64, 32, 8), (3, 128, 64, 30), (2, 48, 16, 5)])
+def test_crop_staged_kernels_bit_identical_to_elementwise(K, N, H, S, per):
+    """the shared-memory staged crop kernels (footprint / gradient tiles staged per block, coordinates computed once per box)
+    keep the arithmetic and the summation order of the element-wise kernels: forward and backward agree bit for bit, incl.
+    boxes touching / leaving the image, a full-image box (footprint larger than the staging tile at 128x128) and a
+    degenerate box"""
+    g = torch.Generator().manual_seed(N * H + S)
+    B = N * per
+    feats = torch.randn(N, 3, H, H, generator=g).cuda()
+    xy0 = torch.rand(B, 2, generator=g) * 0.7
+    boxes = torch.cat([xy0, (xy0 + torch.rand(B, 2, generator=g) * 0.5 + 0.02)], 1)
+    boxes[0] = torch.tensor([0.0, 0.0, 1.0, 1.0])
+    boxes[1] = torch.tensor([0.5, 0.5, 0.5, 0.5])
+    boxes[2] = torch.tensor([-0.2, 0.1, 0.3, 1.4])
+    boxes[3] = torch.tensor([0.9, 0.8, 0.1, 0.2])              # inverted
+    boxes = boxes.cuda()
+    b2i = torch.sort(torch.randint(0, N, (B,), generator=g))[0]
+    plan = ops.get_plan(b2i, N, "cuda")
+    w = ops.crop_weights(S, "cuda")
+    gy = torch.randn(B, 3, S, S, generator=g).cuda()
+    outs = {}
+    for staged in (True, False):
+        prev = K.crop_set_staged(staged)
+        try:
+            outs[staged] = (K.crop_fwd(feats, boxes, plan.box_to_img, w, w, S, S),
+                            K.crop_bwd(gy, boxes, plan.img_box_start, plan.box_order, w, w, N, H, H))
+        finally:
+            K.crop_set_staged(prev)
+    assert torch.equal(outs[True][0], outs[False][0])
+    assert torch.equal(outs[True][1], outs[False][1])
+    assert torch.isfinite(outs[True][0]).all() and float(outs[True][1].abs().max()) > 0
