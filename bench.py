@@ -179,58 +179,14 @@ def workload_config(args, n_per_gpu, note=""):
 # ------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------
-class Iteration:
-    """One training iteration (attribute estimation + D-step + G-step + 4 x Adam + operand re-pack) of `ts` on ONE batch
-    layout, captured into a CUDA graph (or run eagerly): `upload()` copies the pinned host batch into the static device
-    batch, `run()` replays."""
-
-    def __init__(self, ts, host, use_graph, world, rank, warm=2):
-        self.ts, self.world = ts, world
-        self.pinned = {k: (v if k == "obj_to_img" else v.pin_memory()) for k, v in host.items()}
-        self.h2d_bytes = sum(v.numel() * v.element_size() for k, v in host.items() if k != "obj_to_img")
-        self.n_images, self.n_objs = host["imgs"].shape[0], host["objs"].shape[0]
-        self.b = ts.to_device(self.pinned)
-        torch.cuda.synchronize()
-        self.graph, self.static_out = None, None
-        for _ in range(warm):
-            ts.step(self.b, optimizer_step=True)
-        torch.cuda.synchronize()
-        if use_graph:
-            import gc
-            gc.collect()
-            try:
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    ts.step(self.b, optimizer_step=True)
-                torch.cuda.current_stream().wait_stream(side)
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                # thread_local: the NCCL watchdog thread may query events while the step (with its all-reduces) is captured
-                with torch.cuda.graph(g, capture_error_mode="thread_local" if world > 1 else "global"):
-                    r = ts.step(self.b, optimizer_step=True)
-                    self.static_out = (r["d_loss"], r["g_loss"])
-                # every optimizer step inside the captured iteration is followed by the in-place re-pack of the GEMM operands
-                # derived from its parameters (ops.refresh_packs, optimizer post-step hook): each replay computes with the
-                # weights the previous replay wrote
-                self.graph = g
-            except Exception as e:   # graph capture is an optimisation, never a correctness requirement
-                if rank == 0:
-                    print("[bench] CUDA graph capture unavailable (%s: %s); timing eagerly" % (type(e).__name__, e), file=sys.stderr)
-                self.graph = None
-                torch.cuda.synchronize()
-
-    def upload(self):
-        for k, v in self.pinned.items():
-            if k != "obj_to_img":
-                self.b[k].copy_(v, non_blocking=True)
-
-    def run(self):
-        if self.graph is not None:
-            self.graph.replay()
-            return self.static_out
-        r = self.ts.step(self.b, optimizer_step=True)
-        return r["d_loss"], r["g_loss"]
+def Iteration(ts, host, use_graph, world, rank, warm=2):
+    """one training iteration on one batch layout, captured into a CUDA graph (b200gan/graphed.py — the product's own
+    replay path): `upload()` copies the pinned host batch into the static device batch, `run()` replays"""
+    from b200gan.graphed import CapturedIteration
+    it = CapturedIteration(ts, host, use_graph, world > 1, warm=warm)
+    if it.error and rank == 0:
+        print("[bench] CUDA graph capture unavailable (%s); timing eagerly" % it.error, file=sys.stderr)
+    return it
 
 
 def timed(fn, steps, sync_all):
@@ -284,7 +240,7 @@ def side_measurement(args, size, n_img, precision, steps, dev, world, rank, sync
         def e2e(i):
             it.upload()
             l = it.run()
-            return torch.stack([l[0].reshape(()), l[1].reshape(())]).cpu()
+            return torch.stack([l["d_loss"].reshape(()), l["g_loss"].reshape(())]).cpu()
         ms_e2e, hl = timed(e2e, steps, sync_all)
         ok = bool(torch.isfinite(hl).all())
         ms, ms_e2e = max_over_ranks([ms, ms_e2e], dev, world)
@@ -349,7 +305,7 @@ def run_b200(args):
     host = O.synth_batch(n_img, args.size, OBJS_PER_IMAGE, seed=10 + rank)
     # ---- eager warm-up + launch count -------------------------------------------------------------------------
     b0 = ts.to_device(host)
-    for _ in range(max(1, args.warmup if args.no_graph else 1)):
+    for _ in range(max(2, args.warmup if args.no_graph else 2)):
         ts.step(b0, optimizer_step=True)
     torch.cuda.synchronize()
     launches_before = _lib.K.launch_count()
@@ -372,8 +328,8 @@ def run_b200(args):
 
     def dev_step(i):
         l = main.run()
-        traj[i, 0].copy_(l[0]); traj[i, 1].copy_(l[1])
-        return l
+        traj[i, 0].copy_(l["d_loss"]); traj[i, 1].copy_(l["g_loss"])
+        return l["d_loss"], l["g_loss"]
     sync_all()
     if rank == 0:
         sampler.start()
@@ -390,7 +346,7 @@ def run_b200(args):
     def e2e_step(i):
         main.upload()
         l = main.run()
-        return torch.stack([l[0].reshape(()), l[1].reshape(())]).cpu()
+        return torch.stack([l["d_loss"].reshape(()), l["g_loss"].reshape(())]).cpu()
     ms_e2e, host_losses = timed(e2e_step, args.steps, sync_all)
     note("end-to-end timing done: %.2f ms/step" % ms_e2e)
     assert torch.isfinite(host_losses).all()
@@ -411,7 +367,7 @@ def run_b200(args):
                 it = its[i % n_lay]
                 it.upload()
                 l = it.run()
-                return torch.stack([l[0].reshape(()), l[1].reshape(())]).cpu()
+                return torch.stack([l["d_loss"].reshape(()), l["g_loss"].reshape(())]).cpu()
             k = max(args.steps, n_lay)
             ms_rag, hl = timed(rag_step, k, sync_all)
             (ms_rag,) = max_over_ranks([ms_rag], dev, world)

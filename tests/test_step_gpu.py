@@ -281,3 +281,40 @@ def test_full_size_properties_config2():
         full = ts.netD_image(out[4])
         half = ts.netD_image(out[4][:16].contiguous())
         assert rel(half, full[:16]) < 1e-5
+
+
+def test_graphed_train_step_layout_cache():
+    """b200gan.graphed.GraphedTrainStep: an unseen layout runs one eager iteration and is captured; the same layout is then
+    replayed from its graph with new batch VALUES (results equal the eager step on those values, bit for bit in fp32 — the
+    kernels are deterministic); a different layout gets its own graph."""
+    from b200gan.graphed import GraphedTrainStep, layout_key
+    ops.set_precision("fp32")
+    states = O.make_states(64, 0)
+
+    def fresh():
+        ts = TrainStep(64, device="cuda")
+        load_states(ts, states)
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        ts.netG.crop_encoder.eps_source = lambda o, z, d: torch.randn(o, z, device=d, generator=gen)
+        return ts
+
+    a1 = O.synth_batch(2, 64, 4, 7)
+    a2 = O.synth_batch(2, 64, 4, 8)            # same layout (2 images x 4 objects), other values
+    c1 = O.synth_batch(3, 64, None, 9)         # another layout
+    assert layout_key(a1) == layout_key(a2) != layout_key(c1)
+    ts = fresh()
+    gts = GraphedTrainStep(ts)
+    seq = [a1, a2, c1, a1]
+    got = []
+    for hb in seq:
+        r = gts.step(hb)
+        torch.cuda.synchronize()
+        got.append((float(r["d_loss"]), float(r["g_loss"]), r["out_g"][4].detach().clone()))
+    assert gts.misses == 2 and gts.hits == 2 and all(it.graph is not None for it in gts.cache.values()), \\
+        [it.error for it in gts.cache.values()]
+    ref_ts = fresh()
+    for hb, g in zip(seq, got):
+        r = ref_ts.step(ref_ts.to_device(hb), optimizer_step=True)
+        torch.cuda.synchronize()
+        assert abs(float(r["d_loss"]) - g[0]) <= 1e-6 * abs(g[0]) and abs(float(r["g_loss"]) - g[1]) <= 1e-6 * abs(g[1])
+        assert rel(r["out_g"][4], g[2]) < 1e-6
