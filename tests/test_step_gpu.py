@@ -294,8 +294,7 @@ def test_graphed_train_step_layout_cache():
     def fresh():
         ts = TrainStep(64, device="cuda")
         load_states(ts, states)
-        gen = torch.Generator(device="cuda").manual_seed(5)
-        ts.netG.crop_encoder.eps_source = lambda o, z, d: torch.randn(o, z, device=d, generator=gen)
+        ts.netG.crop_encoder.eps_source = lambda o, z, d: torch.full((o, z), 0.25, device=d)    # no RNG in this comparison
         return ts
 
     a1 = O.synth_batch(2, 64, 4, 7)
