@@ -309,7 +309,7 @@ def test_graphed_train_step_layout_cache():
         r = gts.step(hb)
         torch.cuda.synchronize()
         got.append((float(r["d_loss"]), float(r["g_loss"]), r["out_g"][4].detach().clone()))
-    assert gts.misses == 2 and gts.hits == 2 and all(it.graph is not None for it in gts.cache.values()), \\
+    assert gts.misses == 2 and gts.hits == 2 and all(it.graph is not None for it in gts.cache.values()), \
         [it.error for it in gts.cache.values()]
     ref_ts = fresh()
     for hb, g in zip(seq, got):
