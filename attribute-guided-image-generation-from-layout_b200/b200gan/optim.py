@@ -24,24 +24,39 @@ class Adam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._tables = {}
+        self._captured = {}
         self._steps = {}
 
     def _table(self, group_idx, items):
-        """device array of b200_adam_entry for the group's chunks.  The pinned host image and the device buffer are
-        allocated once; when gradient tensors move (a CUDA-graph capture allocates them from its own pool) only the image is
-        rewritten and re-copied with an asynchronous pinned copy — a capturable memcpy node, no allocation under capture."""
+        """device array of b200_adam_entry for the group's chunks, keyed by the tensors' addresses.
+
+        Eager iterations share ONE reusable slot per group (pinned host image + device buffer; gradient tensors move from
+        step to step, so the image is rewritten and re-copied with an asynchronous pinned copy).  A table built WHILE A CUDA
+        GRAPH IS BEING CAPTURED gets its own pinned image and device buffer that are never rewritten: the captured memcpy
+        node re-reads the host image on every replay, so sharing it between captures (several batch layouts, each with its own
+        graph and its own gradient buffers) would make one graph's Adam read another graph's gradients."""
         key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
                      self.state[p]["exp_avg_sq"].data_ptr()) for p in items)
-        slot = self._tables.get(group_idx)
+        capturing = torch.cuda.is_current_stream_capturing()
         n_ent = sum(-(-p.numel() // CHUNK) for p in items)
         nbytes = n_ent * C.sizeof(_Entry)
-        if slot is None or slot["host"].numel() < nbytes:
+        if capturing:
+            slot = self._captured.get((group_idx, key))
+            if slot is not None:
+                return slot["dev"], slot["n"]
             slot = dict(key=None, n=0, host=torch.empty((nbytes,), dtype=torch.uint8).pin_memory(),
                         dev=torch.empty((nbytes,), dtype=torch.uint8, device=items[0].device))
-            self._tables[group_idx] = slot
+            self._captured[(group_idx, key)] = slot
+        else:
+            slot = self._tables.get(group_idx)
+            if slot is None or slot["host"].numel() < nbytes:
+                slot = dict(key=None, n=0, host=torch.empty((nbytes,), dtype=torch.uint8).pin_memory(),
+                            dev=torch.empty((nbytes,), dtype=torch.uint8, device=items[0].device))
+                self._tables[group_idx] = slot
         if slot["key"] != key:
-            if not torch.cuda.is_current_stream_capturing():
-                torch.cuda.current_stream().synchronize()          # an earlier copy of the image may still be in flight
+            if not capturing and slot.get("evt") is not None:
+                slot["evt"].synchronize()          # the previous copy of this image must have left the host buffer (an event
+                                                   # wait on that copy alone: a stream synchronize here stalled the host per step)
             arr = (_Entry * n_ent).from_address(slot["host"].data_ptr())
             i = 0
             for p in items:
@@ -52,6 +67,9 @@ class Adam(torch.optim.Optimizer):
                                     st["exp_avg_sq"].data_ptr() + off * 4, min(CHUNK, n - off), 0)
                     i += 1
             slot["dev"][:nbytes].copy_(slot["host"][:nbytes], non_blocking=True)
+            if not capturing:
+                slot["evt"] = torch.cuda.Event()
+                slot["evt"].record()
             slot["key"], slot["n"] = key, n_ent
         return slot["dev"], slot["n"]
 
@@ -61,6 +79,7 @@ class Adam(torch.optim.Optimizer):
         the cached device tables are dropped (the loaded exp_avg / exp_avg_sq are new tensors)."""
         super().load_state_dict(state_dict)
         self._tables = {}
+        self._captured = {}
         self._steps = {}
         for gi, group in enumerate(self.param_groups):
             ps = [p for p in group["params"] if p in self.state and "step" in self.state[p]]
