@@ -558,13 +558,16 @@ def kernel_roofline(ts, b, args):
     else:
         ach = simt_f / max(simt_t, 1e-9) / 1e12
         name = "conv_gemm_f32_kernel + wgrad_gemm_f32_kernel (fp32 CUDA-core gather-GEMMs)"
-    sample = None
-    try:        # DRAM traffic of one representative launch of the family from the committed ncu --set full capture
-        sample = json.load(open(os.path.join(ROOT, "profiles", "traffic_sample.json")))
+    traffic, traffic_src = None, None
+    try:        # measured DRAM bytes of the family's launches in one iteration: the committed ncu metrics pass of this build
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
+        if args.size == 64 and args.batch == 32 and args.precision == "bf16":
+            traffic, traffic_src = float(tr["dram_bytes"]), tr["source"]
     except Exception:
         pass
     return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "peak_source": src, "traffic": None, "traffic_sample": sample, "launches": len([1 for r in records if r[0]]) if tc_t > 0 else len(records),
+            "peak_source": src, "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per iteration, summed over the family's launches (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+            "traffic_source": traffic_src, "launches": len([1 for r in records if r[0]]) if tc_t > 0 else len(records),
             "distinct_launch_shapes": len(per_key),
             "timing": "CUDA events around a graph of %d back-to-back launches per distinct launch shape" % R,
             "kernel_time_ms_per_step": (tc_t if tc_t > 0 else simt_t) * 1e3,
