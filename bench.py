@@ -147,6 +147,57 @@ def cpu_reference_rate(size, n_images, steps, warmup, threads):
     return n_images * steps / dt, dt / steps
 
 
+def gpu_comparator(size, n_images, dev, steps=3):
+    """The honest GPU comparator: the SAME algorithm as plain functional PyTorch — the oracle
+    port, i.e. cuDNN convolutions / cuBLAS linears / ATen elementwise kernels, eager, fp32 storage with PyTorch's default cuDNN
+    TF32 convolutions — on the same B200 and the same batch.  A reported baseline like cpu_baseline, never the product."""
+    from oracle import gan_oracle as O
+    states = O.make_states(size, 0)
+    model = O.OracleModel(size, 0, states)
+    for name in ("G", "D_img", "D_obj", "D_att"):
+        st = getattr(model, name)
+        setattr(model, name, {k: v.detach().to(dev).requires_grad_(v.requires_grad) for k, v in st.items()})
+    model.pos_weight = model.pos_weight.to(dev)
+    host = O.synth_batch(n_images, size, OBJS_PER_IMAGE, 3)
+    batch = {k: (v if k == "obj_to_img" else v.to(dev)) for k, v in host.items()}
+    opts = [torch.optim.Adam([v for v in st.values() if v.requires_grad], lr=2e-4, betas=(0.5, 0.999))
+            for st in (model.G, model.D_img, model.D_obj, model.D_att)]
+
+    def one():
+        b = dict(batch)
+        b["attribute_GT"] = b["attribute"].clone()
+        nets = model.nets()
+        with torch.no_grad():
+            crops = O.crop_bbox_batch(b["imgs"], b["boxes"], b["obj_to_img"], model.obj_size)
+        est = O.estimate_attributes(nets["att"](crops).detach(), b["attribute"])
+        out = model.generator(b, est, eps=[torch.randn(b["objs"].shape[0], 64, device=dev) for _ in range(3)])
+        d_loss, _ = O.d_step_loss(nets, b, out, model.pos_weight)
+        model.zero_grad((model.D_img, model.D_obj, model.D_att))
+        d_loss.backward()
+        for o in opts[1:]:
+            o.step()
+        out = model.generator(b, est, eps=[torch.randn(b["objs"].shape[0], 64, device=dev) for _ in range(3)])
+        g_loss, _ = O.g_step_loss(nets, b, out, model.pos_weight)
+        model.zero_grad((model.G,))
+        g_loss.backward()
+        opts[0].step()
+        return d_loss.detach(), g_loss.detach()
+
+    one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        dl, gl = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"what": "the same iteration as plain functional PyTorch (oracle port: cuDNN / cuBLAS / ATen kernels, eager, fp32 tensors, "
+                    "PyTorch-default cuDNN TF32 convolutions) on the same B200, batch %d, %d objects/image" % (n_images, OBJS_PER_IMAGE),
+            "ms_per_step": ms, "value": n_images / (ms / 1e3), "unit": "images/s", "steps": steps,
+            "finite": bool(torch.isfinite(dl)) and bool(torch.isfinite(gl)), "kind": "port"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -434,6 +485,15 @@ def run_b200(args):
         per_gpu = max(1, 128 // world)
         extras["config3_128x128_global_batch_128"] = side_measurement(args, 128, per_gpu, "bf16", 3, dev, world, rank, sync_all,
                                                                       note, "config 3 (128x128, global batch 128, strong scaling)")
+        if rank == 0 and world == 1:
+            try:
+                extras["comparator_torch_cuda_eager"] = gpu_comparator(args.size, n_img, dev)
+                note("torch eager comparator: %.1f ms/step" % extras["comparator_torch_cuda_eager"]["ms_per_step"])
+            except Exception as e:
+                extras["comparator_torch_cuda_eager"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
     ops.set_precision(args.precision)
 
     cpu_base = None

@@ -393,7 +393,7 @@ def conv_lstm(sd: State, prefix: str, x: torch.Tensor, obj_to_img: torch.Tensor,
             b = sd["%s.cell_list.%d.conv.bias" % (prefix, li)]
             cin = seq.size(1)
             pre_x = F.conv2d(seq, w[:, :cin], b, padding=2)
-            h = torch.zeros(1, hid, seq.size(2), seq.size(3), dtype=x.dtype)
+            h = torch.zeros(1, hid, seq.size(2), seq.size(3), dtype=x.dtype, device=x.device)
             c = torch.zeros_like(h)
             hs = []
             for t in range(n):
