@@ -55,11 +55,17 @@ class GradBucketer:
             tail.insert(0, order.pop())
             tsize += tail[0].numel() * 4
         self.buckets: List[List[torch.nn.Parameter]] = []
+        remaining = sum(p.numel() * p.element_size() for p in order)
         cur, size = [], 0
         for p in order:
             cur.append(p)
-            size += p.numel() * p.element_size()
-            if size >= bucket_bytes:
+            nb = p.numel() * p.element_size()
+            size += nb
+            remaining -= nb
+            # graduated sizes: the buckets that complete near the END of backward have little compute left to hide behind, so
+            # the last ~bucket_bytes worth of gradients goes out in quarter-size buckets
+            target = bucket_bytes if remaining > bucket_bytes else max(bucket_bytes // 4, 1 << 20)
+            if size >= target:
                 self.buckets.append(cur)
                 cur, size = [], 0
         if cur:
