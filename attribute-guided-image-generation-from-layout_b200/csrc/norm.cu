@@ -171,10 +171,15 @@ __global__ void __launch_bounds__(256) norm_fwd_vec_kernel(const T* __restrict__
     const int rpb = blockDim.x / tpr;
     float ga[V], be[V];
     if (MODE == B200_NORM_AFFINE) { ldp<V>(gamma + c, ga); ldp<V>(beta + c, be); }
-    int g_cur = -1;
+    int g_cur = -1, seg_cur = -1;
     float m[V], rs[V];
+    // a block owns a CONTIGUOUS range of rows: the group statistics and (conditional batch norm) the object's gamma / beta
+    // table row change only every rows_per_seg rows, so they are re-loaded on change instead of once per row
+    const int rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+    const int r_begin = blockIdx.x * rows_per_block;
+    const int r_end = min(rows, r_begin + rows_per_block);
 #pragma unroll 2
-    for (int r = blockIdx.x * rpb + threadIdx.x / tpr; r < rows; r += gridDim.x * rpb) {
+    for (int r = r_begin + threadIdx.x / tpr; r < r_end; r += rpb) {
         const int64_t o = (int64_t)r * C + c;
         float v[V];
         VecIO<T>::load(x + o, v);
@@ -194,9 +199,13 @@ __global__ void __launch_bounds__(256) norm_fwd_vec_kernel(const T* __restrict__
 #pragma unroll
             for (int e = 0; e < V; ++e) out[e] = out[e] * ga[e] + be[e];
         } else if (MODE == B200_NORM_CBN) {
-            const float* row = gamma + (int64_t)idx[r / rows_per_seg] * 2 * C;
-            ldp<V>(row + c, ga);
-            ldp<V>(row + C + c, be);
+            const int seg = r / rows_per_seg;
+            if (seg != seg_cur) {
+                seg_cur = seg;
+                const float* row = gamma + (int64_t)idx[seg] * 2 * C;
+                ldp<V>(row + c, ga);
+                ldp<V>(row + C + c, be);
+            }
 #pragma unroll
             for (int e = 0; e < V; ++e) out[e] = ga[e] * out[e] + be[e];
         } else if (MODE == B200_NORM_SPADE) {
@@ -578,10 +587,13 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_vec_kernel(const T* __rest
 #pragma unroll
     for (int e = 0; e < V; ++e) ga[e] = 1.f;
     if (MODE == B200_NORM_AFFINE) ldp<V>(gamma + c, ga);
-    int g_cur = -1;
-    float m[V], rs[V], sa[V], sb[V];
+    int g_cur = -1, seg_cur = -1;
+    float m[V], rs[V], sa[V], sb[V], be[V];
+    const int rows_per_block = (rows + gridDim.x - 1) / gridDim.x;      // contiguous rows per block (see norm_fwd_vec_kernel)
+    const int r_begin = blockIdx.x * rows_per_block;
+    const int r_end = min(rows, r_begin + rows_per_block);
 #pragma unroll 2
-    for (int r = blockIdx.x * rpb + threadIdx.x / tpr; r < rows; r += gridDim.x * rpb) {
+    for (int r = r_begin + threadIdx.x / tpr; r < r_end; r += rpb) {
         const int64_t o = (int64_t)r * C + c;
         float g[V], xv[V];
         VecIO<T>::load(dy + o, g);
@@ -608,11 +620,14 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_vec_kernel(const T* __rest
             }
         }
         if (MODE == B200_NORM_CBN) {
-            const float* row = gamma + (int64_t)idx[r / rows_per_seg] * 2 * C;
-            ldp<V>(row + c, ga);
+            const int seg = r / rows_per_seg;
+            if (seg != seg_cur) {
+                seg_cur = seg;
+                const float* row = gamma + (int64_t)idx[seg] * 2 * C;
+                ldp<V>(row + c, ga);
+                if (relu == 2) ldp<V>(row + C + c, be);
+            }
             if (relu == 2) {      // recomputed ReLU mask: gamma * xhat + beta > 0 (the forward kernel's fp32 expression)
-                float be[V];
-                ldp<V>(row + C + c, be);
 #pragma unroll
                 for (int e = 0; e < V; ++e)
                     if (!(ga[e] * ((xv[e] - m[e]) * rs[e]) + be[e] > 0.f)) g[e] = 0.f;
