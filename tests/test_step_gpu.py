@@ -317,3 +317,40 @@ def test_graphed_train_step_layout_cache():
         torch.cuda.synchronize()
         assert abs(float(r["d_loss"]) - g[0]) <= 1e-6 * abs(g[0]) and abs(float(r["g_loss"]) - g[1]) <= 1e-6 * abs(g[1])
         assert rel(r["out_g"][4], g[2]) < 1e-6
+
+
+def test_attribute_classifier_training_iterations():
+    """evaluation/train_att_cls.py:196-258 (b200gan.att_cls.AttributeClassifierStep) against the oracle's attribute
+    discriminator + torch's BCE + torch.optim.Adam: three iterations on 64x64 crops of 128x128 images, each compared from the
+    same state (loss 1e-5, logits 1e-4, update direction cosine >= 0.999)."""
+    from b200gan.att_cls import AttributeClassifierStep
+    import torch.nn.functional as F
+    ops.set_precision("fp32")
+    states = O.make_states(64, 0)
+    batch = O.synth_batch(3, 128, None, 21, sparse_attributes=True)
+    st = AttributeClassifierStep(crop_size=64, device="cuda")
+    st.net.load_state_dict(states["D_att"], strict=True)
+    b = st.to_device(batch)
+    pw = O.pos_weight_vector()
+    for it in range(3):
+        sd = {k: v.detach().cpu().clone().requires_grad_(O.is_parameter(k)) for k, v in st.net.state_dict().items()}
+        before = {k: p.detach().cpu().clone() for k, p in st.net.named_parameters()}
+        opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=2e-4, betas=(0.5, 0.999))
+        for k, p in st.net.named_parameters():
+            so = st.opt.state.get(p)
+            if so:
+                opt.state[sd[k]] = dict(step=torch.tensor(float(so["step"])), exp_avg=so["exp_avg"].cpu().clone(),
+                                        exp_avg_sq=so["exp_avg_sq"].cpu().clone())
+        r = st.step(b)
+        with torch.no_grad():
+            crops = O.crop_bbox_batch(batch["imgs"], batch["boxes"], batch["obj_to_img"], 64)
+        logits = O.attribute_discriminator(sd, crops)
+        idx = batch["attribute"].sum(1).nonzero().view(-1)
+        loss = F.binary_cross_entropy_with_logits(logits.index_select(0, idx), batch["attribute"].index_select(0, idx), pos_weight=pw)
+        loss.backward()
+        opt.step()
+        assert abs(float(r["loss"]) - float(loss)) < 1e-5 * abs(float(loss)), (it, float(r["loss"]), float(loss))
+        assert rel(r["logits"], logits) < 1e-4
+        ua = torch.cat([(p.detach().cpu() - before[k]).reshape(-1) for k, p in st.net.named_parameters()]).double()
+        ur = torch.cat([(sd[k].detach() - before[k]).reshape(-1) for k, _ in st.net.named_parameters()]).double()
+        assert float(torch.nn.functional.cosine_similarity(ua, ur, dim=0)) > 0.999
