@@ -37,6 +37,8 @@ class ConvDesc(C.Structure):
         ("relu", C.c_int),
         ("scale_rows", C.c_int),
         ("relu_mask", C.c_void_p),
+        ("col_stats", C.c_void_p),
+        ("col_stats_ld", C.c_int),
     ]
 
 
@@ -268,7 +270,28 @@ class Kernels:
                     "b200_rowsum")
         return out
 
-    def conv_gemm(self, desc: ConvDesc, inp, wmat, bias, scale, out, tc, mask=None):
+    def conv_stats_ok(self, desc: ConvDesc, tc) -> bool:
+        """will this launch run on the persistent tcgen05 kernel (whose epilogue can accumulate batch-norm statistics)?"""
+        tc = int(tc)
+        return bool(tc) and bool(self.lib.b200_conv_tc_stats_ok(C.byref(desc), 4 if tc == 2 else 2))
+
+    def conv_stats_buffer(self, desc: ConvDesc, device):
+        """(slabs, ld, 2) fp32 buffer for b200_conv_desc.col_stats: one (sum, sum of squares) pair per 32-row slab and channel"""
+        M = desc.B * desc.Qh * desc.Qw
+        nt = self.conv_tc_ntile(desc.Cout)
+        ld = (desc.Cout + nt - 1) // nt * nt
+        return torch.empty(((M + 127) // 128 * 4, ld, 2), dtype=torch.float32, device=device)
+
+    def bn_stats_slabs(self, col_stats, rows, Cc, running_mean, running_var, momentum, groups=1):
+        dev = col_stats.device
+        mean = torch.empty((groups, Cc), dtype=torch.float32, device=dev)
+        var = torch.empty((groups, Cc), dtype=torch.float32, device=dev)
+        self._check(self.lib.b200_bn_stats_slabs(_ptr(col_stats), C.c_int64(col_stats.shape[0]), int(col_stats.shape[1]),
+                                                 C.c_int64(rows), int(Cc), int(groups), _ptr(mean), _ptr(var), _ptr(running_mean),
+                                                 _ptr(running_var), C.c_float(momentum), _stream()), "b200_bn_stats_slabs")
+        return mean, var
+
+    def conv_gemm(self, desc: ConvDesc, inp, wmat, bias, scale, out, tc, mask=None, stats=None):
         """tc: 0 = fp32 CUDA-core kernel, 1 = tcgen05 bf16 operands, 2 = tcgen05 tf32 (fp32 tensors; falls back to the CUDA-core
         kernel for gathers the TMA im2col mode cannot express).  mask (tcgen05 paths only): tensor laid out like `out`;
         outputs are zeroed where it is not > 0"""
@@ -279,6 +302,10 @@ class Kernels:
             desc.relu_mask = mask.data_ptr()
         else:
             desc.relu_mask = None
+        if stats is not None:            # (the caller checked conv_stats_ok: persistent tcgen05 kernel)
+            desc.col_stats, desc.col_stats_ld = stats.data_ptr(), int(stats.shape[1])
+        else:
+            desc.col_stats, desc.col_stats_ld = None, 0
         if tc == 2:
             if inp.dtype != torch.float32 or wmat.dtype != torch.float32 or out.dtype != torch.float32:
                 raise B200Error("conv_gemm(tf32): fp32 activation, weight matrix and output required")

@@ -53,13 +53,14 @@ class Conv2d(nn.Conv2d):
         self._packs = WeightPacks()
 
     def forward(self, x, x_layout="cl", out_layout="cl", relu=False, groups=1, out_dtype=None, mask_input_grad=False,
-                grad_premasked=False):
+                grad_premasked=False, stats=False):
         """groups: number of independent calls batched along dim 0 (each gets its own spectral-norm iteration);
         out_dtype: storage type of a channel-last output (default: that of a channel-last input, else ops.act_dtype());
         relu + grad_premasked on a producer and mask_input_grad on its ONLY consumer fuse the ReLU backward into the
-        consumer's data-gradient GEMM (see ops._ConvFn)"""
+        consumer's data-gradient GEMM (see ops._ConvFn); stats: the output goes straight into a batch norm — let the
+        convolution's epilogue accumulate its statistics (ops.conv2d)"""
         return ops.conv2d(x, _weight(self), self.bias, self._geom, self._packs, x_layout, out_layout, relu,
-                          _sn_call(self, groups), out_dtype, mask_input_grad, grad_premasked)
+                          _sn_call(self, groups), out_dtype, mask_input_grad, grad_premasked, stats)
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):

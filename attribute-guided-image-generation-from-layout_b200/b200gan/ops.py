@@ -350,8 +350,11 @@ def im2col_pack(g: ConvGeom, x, x_layout):
     return _lib.K.im2col_pack(x.contiguous(), xs, N, Hx, Wx, Cx, g.kh, g.kw, g.s, g.p, Hy, Wy, Kp)
 
 
+FUSE_BN_STATS = True      # batch-norm statistics accumulated in the producing convolution's epilogue (persistent tcgen05 kernel)
+
+
 def conv_forward_packed(g: ConvGeom, packs: WeightPacks, w, P, N, Hy, Wy, out_layout, bias=None, scale=None, relu=False,
-                        out_dtype=torch.bfloat16):
+                        out_dtype=torch.bfloat16, stats_box=None):
     """Y = epilogue(P @ Wmat^T): the convolution as a 1x1 tcgen05 gather-GEMM over the im2col matrix P"""
     Kp = P.shape[1]
     wmat, ldw = packs.get(("fwd", TC_BF16) + g.key(), w, lambda src, rec: _pack_fwd(g, src, TC_BF16, rec))
@@ -362,7 +365,11 @@ def conv_forward_packed(g: ConvGeom, packs: WeightPacks, w, P, N, Hy, Wy, out_la
                  tap_ox=0, Hi=Hy, Wi=Wy, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3], out_sy=1, out_sx=1,
                  out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ys[0], out_sh=ys[1], out_sw=ys[2], out_sc=ys[3], ldw=ldw,
                  relu=int(relu), scale_rows=_scale_rows(scale, N * Hy * Wy))
-    _lib.K.conv_gemm(d, P, wmat, bias, scale, y, TC_BF16)
+    st = None
+    if stats_box is not None and FUSE_BN_STATS and out_layout == "cl" and _lib.K.conv_stats_ok(d, TC_BF16):
+        st = _lib.K.conv_stats_buffer(d, P.device)
+        stats_box.append(st)
+    _lib.K.conv_gemm(d, P, wmat, bias, scale, y, TC_BF16, stats=st)
     return y
 
 
@@ -434,7 +441,7 @@ def conv_backward_packed_out(g: ConvGeom, packs: WeightPacks, w, x, x_dims, dy, 
 
 
 def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bias=None, scale=None, relu=False,
-                 out_dtype=None):
+                 out_dtype=None, stats_box=None):
     """Y = epilogue(conv(X, W)); the tcgen05 path takes a bf16 activation (cast here if it is not), the fp32 path either"""
     N, Hx, Wx, Cx, xs = _dims(x, x_layout)
     assert Cx == g.Cx, (Cx, g.Cx)
@@ -448,7 +455,11 @@ def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bi
                  tap_oy=-g.p, tap_ox=-g.p, Hi=Hx, Wi=Wx, up_shift=0, in_sn=xs[0], in_sh=xs[1], in_sw=xs[2], in_sc=xs[3],
                  out_sy=1, out_sx=1, out_oy=0, out_ox=0, Ho=Hy, Wo=Wy, out_sn=ys[0], out_sh=ys[1], out_sw=ys[2],
                  out_sc=ys[3], ldw=ldw, relu=int(relu), scale_rows=_scale_rows(scale, N * Hy * Wy))
-    _lib.K.conv_gemm(d, x, wmat, bias, scale, y, tc)
+    st = None
+    if stats_box is not None and FUSE_BN_STATS and tc and out_layout == "cl" and _lib.K.conv_stats_ok(d, tc):
+        st = _lib.K.conv_stats_buffer(d, x.device)          # (sum, sum^2) per 32-row slab and channel, filled by the epilogue
+        stats_box.append(st)
+    _lib.K.conv_gemm(d, x, wmat, bias, scale, y, tc, stats=st)
     return y
 
 
@@ -663,7 +674,8 @@ class SNPlan:
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, sn: Optional[SNCall], g: ConvGeom, packs: WeightPacks, transposed: bool, x_layout: str,
-                out_layout: str, relu: bool, out_hw, out_dtype, mask_input_grad: bool = False, grad_premasked: bool = False):
+                out_layout: str, relu: bool, out_hw, out_dtype, mask_input_grad: bool = False, grad_premasked: bool = False,
+                stats_box=None):
         # mask_input_grad: x is the ReLU output of a producer that set grad_premasked — this layer's data gradient is
         # returned already multiplied by (x > 0); grad_premasked: the incoming gradient of a fused-ReLU layer is already
         # masked by its (single) consumer, so the separate relu_bwd pass is skipped
@@ -684,9 +696,10 @@ class _ConvFn(torch.autograd.Function):
             x_op = im2col_pack(g, x, x_layout)
             ctx.y_dims = (N, Hy, Wy)
             y = conv_forward_packed(g, packs, w, x_op, N, Hy, Wy, out_layout, bias, scale, relu,
-                                    _out_dtype(x, x_layout, out_dtype))
+                                    _out_dtype(x, x_layout, out_dtype), stats_box)
         elif not transposed:
-            y = conv_forward(g, packs, w, x_op, x_layout, out_layout, bias, scale, relu, _out_dtype(x, x_layout, out_dtype))
+            y = conv_forward(g, packs, w, x_op, x_layout, out_layout, bias, scale, relu, _out_dtype(x, x_layout, out_dtype),
+                             stats_box)
         else:
             assert bias is None and not relu
             y = conv_dgrad(g, packs, w, x_op, x_layout, out_hw, out_layout, scale, _out_dtype(x, x_layout, out_dtype))
@@ -717,7 +730,7 @@ class _ConvFn(torch.autograd.Function):
                                               ctx.x_dtype)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = bias_grad(dy, ctx.out_layout)
-            return dx, dw, db, None, None, None, None, None, None, None, None, None, None, None
+            return dx, dw, db, None, None, None, None, None, None, None, None, None, None, None, None
         # one cast for both GEMMs (the tf32 kernels take the fp32 gradient as it is)
         dyb = tc_operand(dy, TC_BF16 if packed else max(dgrad_tc, wgrad_tc)) \
             if ((need_dx and dgrad_tc) or (need_dw and (wgrad_tc or packed))) else None
@@ -766,13 +779,19 @@ class _ConvFn(torch.autograd.Function):
                     _lib.K.sn_grad(gw, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = bias_grad(dy, ctx.out_layout)
-        return dx, dw, db, None, None, None, None, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def conv2d(x, w, bias, g: ConvGeom, packs: WeightPacks, x_layout="cl", out_layout="cl", relu=False,
-           sn: Optional[SNCall] = None, out_dtype=None, mask_input_grad=False, grad_premasked=False):
-    return _ConvFn.apply(x, w, bias, sn, g, packs, False, x_layout, out_layout, relu, None, out_dtype, mask_input_grad,
-                         grad_premasked)
+           sn: Optional[SNCall] = None, out_dtype=None, mask_input_grad=False, grad_premasked=False, stats=False):
+    """stats: the output feeds a batch norm — ask the kernel's epilogue for the per-slab (sum, sum of squares) pairs; when the
+    launch can provide them they ride on the returned tensor (`_b200_colstats`) and the normalisation skips its statistics pass"""
+    box = [] if stats else None
+    y = _ConvFn.apply(x, w, bias, sn, g, packs, False, x_layout, out_layout, relu, None, out_dtype, mask_input_grad,
+                      grad_premasked, box)
+    if box:
+        y._b200_colstats = box[0]
+    return y
 
 
 def conv_transpose2d(x, w, g: ConvGeom, packs: WeightPacks, out_hw, x_layout="cl", out_layout="cl"):
@@ -835,12 +854,16 @@ def _sync_moments(mean, var, n_local, running_mean, running_var):
 class _NormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, idx, running_mean, running_var, mode, training, relu, residual, rows_per_seg,
-                num_classes, groups):
+                num_classes, groups, colstats=None):
         shape = x.shape
         C = shape[-1]
         x2 = x.reshape(-1, C)
         ctx.sync_ratio = None
-        if training and _SYNC_BN is not None:
+        if (training and _SYNC_BN is None and colstats is not None and (x2.shape[0] // groups) % 32 == 0
+                and colstats.shape[0] * 32 >= x2.shape[0] and colstats.shape[1] >= C):
+            # statistics already accumulated by the producing convolution's epilogue: finish them without re-reading x
+            mean, var = _lib.K.bn_stats_slabs(colstats, x2.shape[0], C, running_mean, running_var, BN_MOMENTUM, groups)
+        elif training and _SYNC_BN is not None:
             mean, var = _lib.K.bn_stats(x2, None, None, BN_MOMENTUM, groups)
             mean, var, ctx.sync_ratio = _sync_moments(mean, var, x2.shape[0] // groups, running_mean, running_var)
         elif training:
@@ -891,25 +914,27 @@ class _NormFn(torch.autograd.Function):
             gg, gb = dgb.view(ctx.shape[:-1] + (2 * C,)), None
         else:
             gg, gb = None, None
-        return dx.view(ctx.shape), gg, gb, None, None, None, None, None, None, dres, None, None, None
+        return dx.view(ctx.shape), gg, gb, None, None, None, None, None, None, dres, None, None, None, None
 
 
 def batch_norm(x, weight, bias, running_mean, running_var, training, relu=False, residual=None, groups=1):
     """groups > 1: `groups` calls of the layer batched along dim 0, each with its own batch statistics"""
     mode = MODE_AFFINE if weight is not None else MODE_PLAIN
-    return _NormFn.apply(x, weight, bias, None, running_mean, running_var, mode, training, relu, residual, 1, 0, groups)
+    return _NormFn.apply(x, weight, bias, None, running_mean, running_var, mode, training, relu, residual, 1, 0, groups,
+                         getattr(x, "_b200_colstats", None))
 
 
 def cond_batch_norm(x, table, idx_i32, running_mean, running_var, training, relu=False, groups=1):
     """x (O,H,W,C); table (num_classes, 2C) = [gamma | beta]; idx_i32 (O,)"""
     rows_per_seg = x.shape[1] * x.shape[2]
     return _NormFn.apply(x, table, None, idx_i32, running_mean, running_var, MODE_CBN, training, relu, None,
-                         rows_per_seg, table.shape[0], groups)
+                         rows_per_seg, table.shape[0], groups, getattr(x, "_b200_colstats", None))
 
 
 def spade_norm(x, gb, running_mean, running_var, training, relu=False, groups=1):
     """x (N,H,W,C); gb (N,H,W,2C) = fused [gamma | beta] conv output"""
-    return _NormFn.apply(x, gb, None, None, running_mean, running_var, MODE_SPADE, training, relu, None, 1, 0, groups)
+    return _NormFn.apply(x, gb, None, None, running_mean, running_var, MODE_SPADE, training, relu, None, 1, 0, groups,
+                         getattr(x, "_b200_colstats", None))
 
 
 # ----------------------------------------------------------------------------------------------------------

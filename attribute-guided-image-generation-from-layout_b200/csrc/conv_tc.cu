@@ -464,6 +464,25 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
 //   warp 5 lane 0 : tcgen05.mma issuer; tcgen05.commit frees the stage / publishes the accumulator
 //   warps 0-3     : epilogue
 // ------------------------------------------------------------------------------------------------------------
+// column totals of a 32-row x 16-column register tile: v[e] = this lane's (row's) value of column e.  Four exchange rounds
+// halve the columns a lane still carries (lane bit 4 picks the upper / lower 8, bit 3 the next 4, ...), a fifth adds the two
+// lanes of a pair: afterwards v[0] of lane l is the total of column l >> 1 over the 32 rows.  16 shuffles (not 16 x 5).
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int off = 16, n = 8; n >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < n) {
+                const float send = up ? v[i] : v[i + n];
+                const float keep = up ? v[i + n] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 struct PersistTail {
     uint64_t full[8];
     uint64_t empty[8];
@@ -567,7 +586,8 @@ __global__ void __launch_bounds__(192, 3) conv_gemm_tc_persist_kernel(const __gr
                 uint32_t r[CW];
                 if constexpr (CW == 32) tmem_ld32(tacc + (uint32_t)cb, r);
                 else tmem_ld16(tacc + (uint32_t)cb, r);
-                if (ro >= 0) {
+                const bool stats = d.col_stats != nullptr;          // (uniform)
+                if (ro >= 0 || stats) {
 #pragma unroll
                     for (int h = 0; h < CW; h += 16) {
                         float o[16];
@@ -578,6 +598,25 @@ __global__ void __launch_bounds__(192, 3) conv_gemm_tc_persist_kernel(const __gr
                             o[e] = d.relu ? fmaxf(val, 0.f) : val;
                         }
                         const int c0 = n0 + cb + h;
+                        if (stats) {
+                            // batch-norm statistics of the STORED values, per 32-row slab (= this warp's rows): every lane takes
+                            // part in the shuffles; rows outside the output contribute zeros
+                            float sv[16], sq[16];
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                float q = out_bf16 ? __bfloat162float(__float2bfloat16_rn(o[e])) : o[e];
+                                if (ro < 0) q = 0.f;
+                                sv[e] = q;
+                                sq[e] = q * q;
+                            }
+                            const float ts = warp_colsum16(sv, lane), tq = warp_colsum16(sq, lane);
+                            const int col = c0 + (lane >> 1);
+                            if ((lane & 1) == 0 && col < d.col_stats_ld) {
+                                const int64_t slab = (int64_t)(t / num_n_tiles) * 4 + warp;
+                                *reinterpret_cast<float2*>(d.col_stats + (slab * d.col_stats_ld + col) * 2) = make_float2(ts, tq);
+                            }
+                        }
+                        if (ro < 0) continue;
                         if (vec && c0 + 16 <= d.Cout) {
                             if (d.relu_mask) relu_mask16(o, d.relu_mask, ro + c0, out_bf16);
                             if (out_bf16) {
@@ -1457,7 +1496,7 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
     HaloGeom hg;
-    if (EB == 2 && use_im2col && splits == 1) {
+    if (EB == 2 && use_im2col && splits == 1 && d->col_stats == nullptr) {
         // resident weights with a 64-wide N tile first (fits for Cin = 64 3x3 layers of any Cout), then the native tile
         if (BN == 128 && d->Cout / 64 <= kNumSMs && halo_plan(d, 64, false, &hg))
             return launch_halo<64>(d, hg, wmat, in, bias, scale, out, out_bf16, st);
@@ -1531,6 +1570,7 @@ static int launch_fwd(const b200_conv_desc* d, const __nv_bfloat16* in, const vo
         B200_CHECK_LAUNCH();
         return 0;
     }
+    B200_REQUIRE(d->col_stats == nullptr, "conv_gemm_tc: col_stats needs the persistent kernel (check b200_conv_tc_stats_ok)");
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles, (unsigned)splits);
     if (atma) {
         conv_gemm_tc_kernel<BN, STAGES, true, EB><<<grid, 192, smem_bytes, st>>>(tmap, tmap_a, *d, in, bias, scale, out,
@@ -1697,8 +1737,16 @@ extern "C" int b200_conv_tc_set_halo(int enable) {
 
 extern "C" int b200_conv_tc_ntile(int Cout) { return Cout >= 128 ? 128 : (Cout >= 64 ? 64 : 16); }
 
-/* split-K plan: enough CTAs to fill the 148 SMs twice when the output tile grid alone cannot */
 static int conv_splits_impl(const b200_conv_desc* d, int bke);
+extern "C" int b200_conv_tc_stats_ok(const b200_conv_desc* d, int elem_bytes) {
+    const int bke = elem_bytes == 4 ? 32 : 64;
+    if (!tc::g_use_persist || !(g_use_im2col || elem_bytes == 4) || b200_conv_tc_ntile(d->Cout) < 64) return 0;
+    if (d->Cin % bke != 0 || !tc::im2col_eligible(d)) return 0;
+    if (d->relu_mask != nullptr) return 0;
+    return conv_splits_impl(d, bke) == 1 ? 1 : 0;
+}
+
+/* split-K plan: enough CTAs to fill the 148 SMs twice when the output tile grid alone cannot */
 extern "C" int b200_conv_tc_splits(const b200_conv_desc* d) { return conv_splits_impl(d, 64); }
 
 static int conv_splits_impl(const b200_conv_desc* d, int bke) {

@@ -101,6 +101,47 @@ __global__ void __launch_bounds__(128) bn_stats_final_kernel(const double* __res
     if (running_mean && threadIdx.x == 0) { running_mean[c] = rm; running_var[c] = rv; }
 }
 
+// statistics from the per-slab (sum, sum of squares) pairs a convolution epilogue produced (32 rows per slab): one block per
+// channel, threads stride over the slabs of a group (fp64 accumulation, fixed-order tree), running statistics updated per
+// group in call order — the same outputs as bn_stats_partial + bn_stats_final without reading the activation again
+__global__ void __launch_bounds__(128) bn_stats_slabs_kernel(const float* __restrict__ cs, int64_t slabs_per_group, int ld,
+                                                            int C, int groups, int64_t rows_per_group, float* mean, float* var,
+                                                            float* running_mean, float* running_var, float momentum) {
+    __shared__ double red[4][2];
+    const int c = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float rm = 0.f, rv = 0.f;
+    if (running_mean && threadIdx.x == 0) { rm = running_mean[c]; rv = running_var[c]; }
+    for (int g = 0; g < groups; ++g) {
+        double s1 = 0.0, s2 = 0.0;
+        const float* base = cs + ((int64_t)g * slabs_per_group * ld + c) * 2;
+#pragma unroll 4
+        for (int64_t k = threadIdx.x; k < slabs_per_group; k += 128) {
+            const float2 v = *reinterpret_cast<const float2*>(base + k * ld * 2);
+            s1 += (double)v.x;
+            s2 += (double)v.y;
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) { red[warp][0] = s1; red[warp][1] = s2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double t1 = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
+            const double t2 = (red[0][1] + red[1][1]) + (red[2][1] + red[3][1]);
+            double m = t1 / (double)rows_per_group;
+            double v = t2 / (double)rows_per_group - m * m;
+            if (v < 0.0) v = 0.0;
+            mean[(int64_t)g * C + c] = (float)m;
+            var[(int64_t)g * C + c] = (float)v;
+            const double unb = rows_per_group > 1 ? v * (double)rows_per_group / (double)(rows_per_group - 1) : v;
+            rm = (1.f - momentum) * rm + momentum * (float)m;
+            rv = (1.f - momentum) * rv + momentum * (float)unb;
+        }
+        __syncthreads();
+    }
+    if (running_mean && threadIdx.x == 0) { running_mean[c] = rm; running_var[c] = rv; }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // forward apply
 // ---------------------------------------------------------------------------------------------------------
@@ -683,6 +724,19 @@ extern "C" int b200_bn_stats(const void* x, int dt, int64_t rows, int C, int gro
     B200_CHECK_LAUNCH();
     bn_stats_final_kernel<<<C, 128, 0, as_stream(stream)>>>(ws, nchunks, C, groups, rpg, mean, var, running_mean, running_var,
                                                             momentum);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_bn_stats_slabs(const float* col_stats, int64_t n_slabs, int ld, int64_t rows, int C, int groups, float* mean,
+                                   float* var, float* running_mean, float* running_var, float momentum,
+                                   b200_stream_t stream) {
+    B200_REQUIRE(rows > 0 && C > 0 && groups >= 1 && rows % groups == 0 && ld >= C, "bn_stats_slabs: bad sizes");
+    const int64_t rpg = rows / groups;
+    B200_REQUIRE(rpg % 32 == 0, "bn_stats_slabs: rows per group must be a multiple of 32 (slabs must not straddle groups)");
+    B200_REQUIRE(n_slabs >= rows / 32 && (reinterpret_cast<uintptr_t>(col_stats) & 7) == 0, "bn_stats_slabs: slab buffer too small");
+    bn_stats_slabs_kernel<<<C, 128, 0, as_stream(stream)>>>(col_stats, rpg / 32, ld, C, groups, rpg, mean, var, running_mean,
+                                                            running_var, momentum);
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -56,9 +56,9 @@ class ResidualBlock(nn.Module):
             bnn.BatchNorm2d(dim_out, affine=True, track_running_stats=True))
 
     def forward(self, x, groups=1):
-        h = self.main[0](x)
+        h = self.main[0](x, stats=True)
         h = self.main[1](h, relu=True, groups=groups)
-        h = self.main[3](h)
+        h = self.main[3](h, stats=True)
         return self.main[4](h, residual=x, groups=groups)
 
 
@@ -122,11 +122,11 @@ class CropEncoder(nn.Module):
     def forward(self, imgs, objs, groups=1):
         """groups > 1: that many calls batched along dim 0 (imgs (groups*O,3,S,S), objs (groups*O,)); batch statistics,
         running-statistics updates and the noise draws stay per call, in call order."""
-        x = self.bn1(self.c1(imgs, x_layout="nchw"), objs, relu=True, groups=groups)
-        x = self.bn2(self.c2(x), objs, relu=True, groups=groups)
-        x = self.bn3(self.c3(x), objs, relu=True, groups=groups)
-        x = self.bn4(self.c4(x), objs, relu=True, groups=groups)
-        x = self.bn5(self.conv5(x), objs, relu=True, groups=groups)
+        x = self.bn1(self.c1(imgs, x_layout="nchw", stats=True), objs, relu=True, groups=groups)
+        x = self.bn2(self.c2(x, stats=True), objs, relu=True, groups=groups)
+        x = self.bn3(self.c3(x, stats=True), objs, relu=True, groups=groups)
+        x = self.bn4(self.c4(x, stats=True), objs, relu=True, groups=groups)
+        x = self.bn5(self.conv5(x, stats=True), objs, relu=True, groups=groups)
         O, H, W, C = x.shape
         x = ops.pool(x, H, 1.0 / (H * W)).view(O, C)
         mu = self.fc_mu(x, out_dtype=torch.float32)              # the VAE head and everything after it stay fp32
@@ -151,7 +151,7 @@ class GlobalEncoder(nn.Module):
         self.c2 = bnn.Conv2d(128, 128, kernel_size=4, stride=2, padding=1, bias=False)
 
     def forward(self, h, groups=1):
-        h = self.bn1(self.c1(h), relu=True, groups=groups)
+        h = self.bn1(self.c1(h, stats=True), relu=True, groups=groups)
         h = self.c2(h)
         N, H, W, C = h.shape
         return ops.pool(h, H, 1.0).view(N, C)
@@ -189,9 +189,9 @@ class LayoutEncoder(nn.Module):
         v = ops.linear(e, w0.view(w0.shape[0], w0.shape[1]), None, self._c0_packs)   # W0 e  (rank-1 form of c0)
         h = ops.mask_outer(v, masks)                                               # (O,H+2,W+2,64), zero ring = padding 1
         h = self.bn1(h, objs, relu=True, groups=groups)
-        h = self.bn2(self.c2(h), objs, relu=True, groups=groups)
-        h = self.bn3(self.c3(h), objs, relu=True, groups=groups)
-        h = self.bn4(self.c4(h), objs, groups=groups)
+        h = self.bn2(self.c2(h, stats=True), objs, relu=True, groups=groups)
+        h = self.bn3(self.c3(h, stats=True), objs, relu=True, groups=groups)
+        h = self.bn4(self.c4(h, stats=True), objs, groups=groups)
         if self._pool_to_8:
             f = h.shape[1] // 8
             h = ops.pool(h, f, 1.0 / (f * f))
@@ -229,7 +229,7 @@ class Decoder(nn.Module):
         N, H, W, C = hidden.shape
         seg = hidden
         x = ops.concat_channels(hidden.view(N * H * W, C), global_h, 1, H * W).view(N, H, W, C + global_h.shape[1])
-        h = self.c0_new(x)
+        h = self.c0_new(x, stats=True)
         h = self.spade_0.forward_cl(h, seg, relu=True, groups=groups)
         h = self.spade_1.forward_cl(self.dc1(h), seg, relu=True, groups=groups)
         h = self.spade_2.forward_cl(self.dc2(h), seg, relu=True, groups=groups)
@@ -238,9 +238,9 @@ class Decoder(nn.Module):
         if not self._refine:
             return img
         up = ops.upsample_nearest_nchw(img, 2)
-        h = self.c5(up, x_layout="nchw")
+        h = self.c5(up, x_layout="nchw", stats=True)
         h = self.spade_4.forward_cl(h, seg, relu=True, groups=groups)
-        h = self.spade_5.forward_cl(self.c6(h), seg, relu=True, groups=groups)
+        h = self.spade_5.forward_cl(self.c6(h, stats=True), seg, relu=True, groups=groups)
         return self.c7(h, out_layout="nchw")
 
 

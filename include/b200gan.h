@@ -123,6 +123,12 @@ typedef struct {
     const void* relu_mask;         /* tcgen05 path only, may be NULL: tensor with out's type and strides; outputs are zeroed
                                       where it is not > 0 — the ReLU backward of a layer whose INPUT is a ReLU output, fused
                                       into that layer's data-gradient GEMM (out = dX, relu_mask = X) */
+    float* col_stats;              /* persistent tcgen05 kernel only (b200_conv_tc_stats_ok), may be NULL: per 32-row slab of the
+                                      output (row r = m / 32, the warp that owns those rows) and per output channel c the pair
+                                      (sum, sum of squares) of the STORED values: col_stats[(r * col_stats_ld + c) * 2 + {0,1}],
+                                      ceil(M/128)*4 slabs — batch-norm statistics accumulated in the convolution's epilogue
+                                      (b200_bn_stats_slabs finishes them), so the normalisation reads its input once */
+    int col_stats_ld;              /* channels per slab row (>= the N-tile-padded Cout) */
 } b200_conv_desc;
 
 /* fp32 CUDA-core path (bit-tight parity mode; also the 3-channel layers and Linear heads). wmat fp32 [Cout][ldw];
@@ -158,6 +164,9 @@ int b200_conv_tc_set_persistent(int enable);
  * b200_conv_tc_set_halo(0) disables it (parity tests compare with the im2col kernels); returns the previous setting. */
 int b200_conv_tc_set_halo(int enable);
 int b200_conv_tc_splits(const b200_conv_desc* d);
+/* 1 if b200_conv_gemm_tc / _tf32 (elem_bytes 2 / 4) would run this descriptor on the persistent kernel — the one whose epilogue
+ * can produce col_stats — else 0 */
+int b200_conv_tc_stats_ok(const b200_conv_desc* d, int elem_bytes);
 /* y[i] = bf16(x[i]) (round to nearest even), n % 4 == 0 */
 int b200_cast_bf16(const float* x, void* y_bf16, int64_t n, b200_stream_t stream);
 /* tcgen05 kind::tf32 variants — the "fp32 on tensor cores" mode (BASELINE config 2, fp32 half): operands stay fp32 tensors in
@@ -235,6 +244,11 @@ int b200_pack_weight_multi(const b200_pack_entry* entries_dev, int n_entries, in
  * batch statistics (biased var) + running-stat update (momentum, unbiased var) — F.batch_norm training semantics.
  * ws: 2*C*groups*b200_bn_chunks(rows/groups, C) doubles. running_* may be NULL. */
 int b200_bn_chunks(int64_t rows, int C);
+/* batch statistics from the per-slab (sum, sum of squares) pairs a convolution epilogue produced (b200_conv_desc.col_stats):
+ * same outputs and running-statistics update as b200_bn_stats; rows_per_group must be a multiple of 32 (slabs never straddle a
+ * group); n_slabs = ceil(rows / 128) * 4 (slabs beyond the last row hold zeros). */
+int b200_bn_stats_slabs(const float* col_stats, int64_t n_slabs, int ld, int64_t rows, int C, int groups, float* mean,
+                        float* var, float* running_mean, float* running_var, float momentum, b200_stream_t stream);
 int b200_bn_stats(const void* x, int dt, int64_t rows, int C, int groups, float* mean, float* var, float* running_mean,
                   float* running_var, float momentum, double* ws, b200_stream_t stream);
 enum { B200_NORM_PLAIN = 0, B200_NORM_AFFINE = 1, B200_NORM_CBN = 2, B200_NORM_SPADE = 3 };

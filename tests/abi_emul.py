@@ -161,7 +161,30 @@ class EmulKernels:
         self.launches += 1
         return x2d.double().sum(1).float()
 
-    def conv_gemm(self, d, inp, wmat, bias, scale, out, tc, mask=None):
+    def conv_stats_ok(self, d, tc):
+        """b200_conv_tc_stats_ok, approximated: a tcgen05 launch with a 64+ wide N tile and no fused ReLU mask"""
+        return bool(int(tc)) and d.Cout >= 64 and not d.relu_mask
+
+    def conv_stats_buffer(self, d, device):
+        M = d.B * d.Qh * d.Qw
+        nt = self.conv_tc_ntile(d.Cout)
+        return torch.zeros(((M + 127) // 128 * 4, (d.Cout + nt - 1) // nt * nt, 2))
+
+    def bn_stats_slabs(self, col_stats, rows, C, running_mean, running_var, momentum, groups=1):
+        self.launches += 1
+        rpg = rows // groups
+        assert rpg % 32 == 0
+        cs = col_stats[:rows // 32, :C].double().view(groups, rpg // 32, C, 2).sum(1)
+        mean = cs[..., 0] / rpg
+        var = (cs[..., 1] / rpg - mean * mean).clamp(min=0)
+        if running_mean is not None:
+            for g in range(groups):
+                unb = var[g] * rpg / (rpg - 1) if rpg > 1 else var[g]
+                running_mean.mul_(1 - momentum).add_(momentum * mean[g].float())
+                running_var.mul_(1 - momentum).add_(momentum * unb.float())
+        return mean.float(), var.float()
+
+    def conv_gemm(self, d, inp, wmat, bias, scale, out, tc, mask=None, stats=None):
         self.launches += 1
         tc = int(tc)
         assert mask is None or (tc and mask.shape == out.shape and mask.dtype == out.dtype)
@@ -196,6 +219,16 @@ class EmulKernels:
             mflat = torch.as_strided(mask, flat.shape, (1,), mask.storage_offset())
             vals = torch.where(mflat[idx].float() > 0, vals, torch.zeros(()))
         flat[idx] = vals.to(out.dtype)
+        if stats is not None:      # b200_conv_desc.col_stats: (sum, sum^2) of the STORED values per 32-row slab and channel
+            assert int(tc) and mask is None
+            M = y.shape[0]
+            q = torch.where(ok[:, None], y.to(out.dtype).float(), torch.zeros(()))
+            pad = stats.shape[0] * 32 - M
+            q = torch.cat([q, torch.zeros(pad, q.shape[1])]) if pad else q
+            q = q.view(stats.shape[0], 32, -1).double()
+            stats.zero_()
+            stats[:, :d.Cout, 0] = q.sum(1).float()
+            stats[:, :d.Cout, 1] = (q * q).sum(1).float()
 
     def wgrad_gemm(self, d, P, G, ws, splits, tc):
         self.launches += 1

@@ -1031,3 +1031,46 @@ def test_crop_staged_kernels_bit_identical_to_elementwise(K, N, H, S, per):
     assert torch.equal(outs[True][0], outs[False][0])
     assert torch.equal(outs[True][1], outs[False][1])
     assert torch.isfinite(outs[True][0]).all() and float(outs[True][1].abs().max()) > 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batch-norm statistics accumulated in the convolution epilogue (b200_conv_desc.col_stats + b200_bn_stats_slabs)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("case", [(64, 64, 3, 1, 1, 32, 6, 3), (64, 128, 4, 2, 1, 32, 6, 3), (128, 192, 3, 1, 1, 8, 7, 1),
+                                  (256, 512, 4, 2, 1, 16, 4, 2), (3, 64, 7, 1, 3, 32, 6, 2)])
+def test_conv_epilogue_statistics_match_the_statistics_pass(K, case, precision):
+    """a convolution asked for `stats` hands the normalisation the per-slab (sum, sum of squares) pairs of its STORED output:
+    mean / biased variance / running statistics from b200_bn_stats_slabs equal those of the separate statistics pass over the
+    stored tensor (b200_bn_stats) to summation order, for grouped calls, partial last tiles (M % 128 != 0) and padded channel
+    tiles; the convolution output itself is unchanged bit for bit"""
+    Cx, Cy, k, s, p, H, N, groups = case
+    if precision == "tf32" and Cx < 32:
+        pytest.skip("3-channel layers run on the CUDA-core kernels in tf32 mode")
+    g = torch.Generator().manual_seed(Cx + Cy + H)
+    xl = "nchw" if Cx == 3 else "cl"
+    x = torch.randn(N, Cx, H, H, generator=g)
+    w = torch.randn(Cy, Cx, k, k, generator=g) / (Cx * k * k) ** 0.5
+    ops.set_precision(precision)
+    try:
+        geom = ops.ConvGeom(Cx, Cy, k, k, s, p)
+        xd = _to_layout(x, xl).cuda()
+        wd = w.cuda()
+        y = ops.conv2d(xd, wd, None, geom, ops.WeightPacks(), xl, "cl", stats=True)
+        cs = getattr(y, "_b200_colstats", None)
+        rows = y.shape[0] * y.shape[1] * y.shape[2]
+        assert cs is not None and cs.shape[0] == (rows + 127) // 128 * 4, "the persistent kernel should have produced statistics"
+        y0 = ops.conv2d(xd, wd, None, geom, ops.WeightPacks(), xl, "cl", stats=False)
+        assert torch.equal(y, y0)
+        if (rows // groups) % 32:
+            pytest.skip("rows per group not slab aligned: the statistics pass is used")
+        rm_a, rv_a = torch.zeros(Cy, device="cuda"), torch.ones(Cy, device="cuda")
+        rm_b, rv_b = rm_a.clone(), rv_a.clone()
+        m_a, v_a = K.bn_stats_slabs(cs, rows, Cy, rm_a, rv_a, 0.1, groups)
+        m_b, v_b = K.bn_stats(y.reshape(rows, Cy), rm_b, rv_b, 0.1, groups)
+        assert float((m_a - m_b).abs().max()) <= 1e-6 * max(1.0, float(m_b.abs().max()))
+        close(v_a, v_b, 1e-5, "variance")
+        close(rm_a, rm_b, 1e-5, "running mean")
+        close(rv_a, rv_b, 1e-5, "running var")
+    finally:
+        ops.set_precision("fp32")
