@@ -350,7 +350,12 @@ def im2col_pack(g: ConvGeom, x, x_layout):
     return _lib.K.im2col_pack(x.contiguous(), xs, N, Hx, Wx, Cx, g.kh, g.kw, g.s, g.p, Hy, Wy, Kp)
 
 
-FUSE_BN_STATS = True      # batch-norm statistics accumulated in the producing convolution's epilogue (persistent tcgen05 kernel)
+# Batch-norm statistics accumulated in the producing convolution's epilogue (persistent tcgen05 kernel, b200_conv_desc.col_stats
+# -> b200_bn_stats_slabs).  Correct (tests/test_kernels_gpu.py::test_conv_epilogue_statistics_*), but measured SLOWER inside the
+# step (39.5 vs 38.6 ms): the 32 shuffles per 16 columns roughly double the epilogue of the short-K layers (+0.75 ms over the GEMM
+# launches) and the per-32-row partials make the finishing kernel as expensive as the statistics pass it replaces (0.73 ms).  Kept
+# as an experiment behind this switch; off by default.  
+FUSE_BN_STATS = False
 
 
 def conv_forward_packed(g: ConvGeom, packs: WeightPacks, w, P, N, Hy, Wy, out_layout, bias=None, scale=None, relu=False,
