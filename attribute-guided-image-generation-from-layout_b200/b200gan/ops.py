@@ -599,9 +599,20 @@ def conv_wgrad_sn_grouped(g: ConvGeom, x, dy, sn: "SNCall", w, spg: int, kind: i
     return _lib.K.sn_wgrad_finish(ws, sn.groups, spg, g.Cy, kk, g.Cx, w, sn.u_hist, sn.v_hist, sn.inv, dw)
 
 
+_BIAS_GRAD_MEMO = [None, None]      # (weak reference to the gradient tensor, its column sums)
+
+
 def bias_grad(dy: torch.Tensor, layout: str) -> torch.Tensor:
+    """column sums of an output gradient.  Two convolutions that receive the SAME gradient tensor (a discriminator block's
+    second convolution and its shortcut: pool(a + b) hands one tensor to both branches) share one reduction — the memo holds a
+    weak reference to the last tensor, so a hit is only possible while that very tensor object is alive."""
     if layout == "cl":
-        return _lib.K.colsum(dy.reshape(-1, dy.shape[-1]))
+        ref, val = _BIAS_GRAD_MEMO
+        if ref is not None and ref() is dy and val.shape[0] == dy.shape[-1]:
+            return val.clone()
+        val = _lib.K.colsum(dy.reshape(-1, dy.shape[-1]))
+        _BIAS_GRAD_MEMO[0], _BIAS_GRAD_MEMO[1] = weakref.ref(dy), val
+        return val
     N, C, H, W = dy.shape
     per = _lib.K.rowsum(dy.contiguous().view(N * C, H * W))          # per-(n, c) sums, then over n
     return _lib.K.colsum(per.view(N, C))
