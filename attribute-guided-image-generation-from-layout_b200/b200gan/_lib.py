@@ -661,15 +661,38 @@ class Kernels:
                                           int(bool(accumulate)), _ptr(ws), _stream()), "b200_sn_grad")
         return dW
 
-    def sn_wgrad_finish(self, ws, groups, spg, Cy, T, Cx, W, u_hist, v_hist, inv, dW):
-        """dW of `groups` batched calls of a spectral-normalised layer from the group-aligned partials of one wgrad launch"""
+    def sn_wgrad_finish(self, ws, groups, spg, Cy, T, Cx, W, u_hist, v_hist, inv, dW, pooled_taps=None):
+        """dW of `groups` batched calls of a spectral-normalised layer from the group-aligned partials of one wgrad launch.
+        pooled_taps = (Th, Tw) of the PARAMETER: `ws` are the partials of the folded (Th+1) x (Tw+1) stride-2 convolution
+        (fold_pool_weight) and T is ignored"""
         dev = W.device
         parts = int(self.lib.b200_sn_wgrad_parts(int(Cy), int(Cx)))
         dot = torch.empty((groups * parts,), dtype=torch.float64, device=dev)
+        if pooled_taps is not None:
+            th, tw = pooled_taps
+            self._check(self.lib.b200_sn_wgrad_finish_pooled(_ptr(ws), int(groups), int(spg),
+                                                             C.c_int64(Cy * (th + 1) * (tw + 1) * Cx), int(Cy), int(th), int(tw),
+                                                             int(Cx), _ptr(W), _ptr(u_hist), _ptr(v_hist), _ptr(inv),
+                                                             _ptr(dot), _ptr(dW), _stream()), "b200_sn_wgrad_finish_pooled")
+            return dW
         self._check(self.lib.b200_sn_wgrad_finish(_ptr(ws), int(groups), int(spg), C.c_int64(Cy * T * Cx), int(Cy), int(T),
                                                   int(Cx), _ptr(W), _ptr(u_hist), _ptr(v_hist), _ptr(inv), None,
                                                   _ptr(dot), _ptr(dW), _stream()), "b200_sn_wgrad_finish")
         return dW
+
+    def fold_pool_weight(self, w, w4):
+        """w (.., kh, kw) fp32 contiguous -> w4 (.., kh+1, kw+1): the weight of the stride-2 convolution equal to
+        avg_pool2(conv(x; w)) (see b200gan.h)"""
+        kh, kw = int(w.shape[-2]), int(w.shape[-1])
+        if not (w.is_cuda and w4.is_cuda and w.dtype == torch.float32 and w4.dtype == torch.float32
+                and w.is_contiguous() and w4.is_contiguous()):
+            raise B200Error("fold_pool_weight: contiguous fp32 CUDA tensors required")
+        filters = w.numel() // (kh * kw)
+        if w4.numel() != filters * (kh + 1) * (kw + 1):
+            raise B200Error("fold_pool_weight: bad destination shape")
+        self._check(self.lib.b200_fold_pool_weight(_ptr(w), _ptr(w4), C.c_int64(filters), kh, kw, _stream()),
+                    "b200_fold_pool_weight")
+        return w4
 
     def sn_table(self, layers, stage, ws, iters):
         """device array of b200_sn_layer for `layers` = [(W, u, v, h, w, stage_off, ws_off)]; per layer the stage buffer

@@ -51,15 +51,24 @@ class Conv2d(nn.Conv2d):
         self._geom = ConvGeom(self.in_channels, self.out_channels, self.kernel_size[0], self.kernel_size[1],
                               self.stride[0], self.padding[0])
         self._packs = WeightPacks()
+        self._geom_pool = None
 
     def forward(self, x, x_layout="cl", out_layout="cl", relu=False, groups=1, out_dtype=None, mask_input_grad=False,
-                grad_premasked=False, stats=False):
+                grad_premasked=False, stats=False, pool=False):
         """groups: number of independent calls batched along dim 0 (each gets its own spectral-norm iteration);
         out_dtype: storage type of a channel-last output (default: that of a channel-last input, else ops.act_dtype());
         relu + grad_premasked on a producer and mask_input_grad on its ONLY consumer fuse the ReLU backward into the
         consumer's data-gradient GEMM (see ops._ConvFn); stats: the output goes straight into a batch norm — let the
-        convolution's epilogue accumulate its statistics (ops.conv2d)"""
-        return ops.conv2d(x, _weight(self), self.bias, self._geom, self._packs, x_layout, out_layout, relu,
+        convolution's epilogue accumulate its statistics (ops.conv2d); pool: return avg_pool2d(conv(x), 2) — computed as
+        ONE stride-2 convolution with the folded weight (ops.ConvGeom.pooled), the full-resolution output never exists"""
+        geom = self._geom
+        if pool:
+            assert self.stride[0] == 1 and not relu and not stats, "pool=True: stride-1 convolution without fused ReLU"
+            if self._geom_pool is None:
+                self._geom_pool = ConvGeom.pooled(self.in_channels, self.out_channels, self.kernel_size[0],
+                                                  self.kernel_size[1], self.padding[0])
+            geom = self._geom_pool
+        return ops.conv2d(x, _weight(self), self.bias, geom, self._packs, x_layout, out_layout, relu,
                           _sn_call(self, groups), out_dtype, mask_input_grad, grad_premasked, stats)
 
 

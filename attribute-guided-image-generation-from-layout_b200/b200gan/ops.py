@@ -93,17 +93,25 @@ class ConvGeom:
     """A convolution in *conv orientation*: X (N,Hx,Wx,Cx) * W (Cy,Cx,kh,kw) -> Y (N,Hy,Wy,Cy).
     nn.ConvTranspose2d is the same geometry run backwards (its input is Y, its output X)."""
 
-    def __init__(self, Cx, Cy, kh, kw, stride, pad, cx_offset=0, cx_total=None):
+    def __init__(self, Cx, Cy, kh, kw, stride, pad, cx_offset=0, cx_total=None, fold=False):
         self.Cx, self.Cy, self.kh, self.kw, self.s, self.p = Cx, Cy, kh, kw, stride, pad
         # the parameter may hold more input channels than this op uses (ConvLSTM x / h halves)
         self.cx_offset = cx_offset
         self.cx_total = Cx if cx_total is None else cx_total
+        # fold: this is the stride-2 form of avg_pool2(conv_{(kh-1) x (kw-1), stride 1}) — the PARAMETER has (kh-1) x (kw-1)
+        # taps and the GEMM operands are packed from its folded image (ConvGeom.pooled, b200_fold_pool_weight)
+        self.fold = bool(fold)
+
+    @classmethod
+    def pooled(cls, Cx, Cy, kh, kw, pad):
+        """geometry of avg_pool2(conv_{kh x kw, stride 1, pad}(x)) as ONE (kh+1) x (kw+1) stride-2 convolution"""
+        return cls(Cx, Cy, kh + 1, kw + 1, 2, pad, fold=True)
 
     def out_hw(self, Hx, Wx):
         return (Hx + 2 * self.p - self.kh) // self.s + 1, (Wx + 2 * self.p - self.kw) // self.s + 1
 
     def key(self):
-        return (self.Cx, self.Cy, self.kh, self.kw, self.s, self.p, self.cx_offset, self.cx_total)
+        return (self.Cx, self.Cy, self.kh, self.kw, self.s, self.p, self.cx_offset, self.cx_total, self.fold)
 
 
 class PackRecipe:
@@ -125,6 +133,39 @@ class PackRecipe:
                            self.Tw, self.C, self.ldw, self.s_m, self.s_ky, self.s_kx, self.s_c, self.ky0, self.kx0,
                            self.kstep, self.C_dst, self.c_off)
 
+
+class FoldRecipe:
+    """w4 = fold(w): the weight of the stride-2 convolution equal to avg_pool2(conv(x; w)); runs BEFORE the PackRecipes that
+    read w4 (WeightPacks.get keeps it first in the entry's list; refresh_packs launches the folds, then the packing)"""
+    __slots__ = ("src", "dst")
+
+    def __init__(self, src, dst):
+        self.src, self.dst = src, dst
+
+    def run(self):
+        _lib.K.fold_pool_weight(self.src, self.dst)
+
+
+def _folded_source(g: ConvGeom, srcs, recipes):
+    """the (Cy, cx_total, kh, kw) fp32 image of a pooled convolution's parameter that the packing reads"""
+    assert len(srcs) == 1 and g.fold
+    w = srcs[0]
+    assert tuple(w.shape[2:]) == (g.kh - 1, g.kw - 1) and w.is_contiguous(), (tuple(w.shape), g.key())
+    w4 = torch.empty((w.shape[0], w.shape[1], g.kh, g.kw), dtype=torch.float32, device=w.device)
+    fr = FoldRecipe(w, w4)
+    fr.run()
+    recipes.append(fr)
+    return (w4,)
+
+
+def unfold_pool_grad(g4: torch.Tensor) -> torch.Tensor:
+    """transpose of the fold: the gradient of the (kh, kw) parameter from that of its folded (kh+1, kw+1) image"""
+    return 0.25 * ((g4[..., :-1, :-1] + g4[..., :-1, 1:]) + (g4[..., 1:, :-1] + g4[..., 1:, 1:]))
+
+
+# Discriminator blocks evaluate avg_pool2(conv(h)) as one stride-2 convolution with the folded weight and the 1x1 shortcut on
+# the pooled input (models/discriminator.py).  B200_POOLED_CONV=0 keeps the literal operation order.
+POOLED_CONV = os.environ.get("B200_POOLED_CONV", "1") != "0"
 
 _PACK_REGISTRY = weakref.WeakSet()      # every live WeightPacks
 _PACK_GEN = 0                            # bumped whenever a cached operand is (re)built into a new buffer
@@ -193,16 +234,20 @@ def refresh_packs(params=None, owner=None):
             for e in wp.store.values():
                 if ptrs is None or any(_storage_ptr(t) in ptrs for t in e[3]):
                     items.append(e)
-        recipes = [r for e in items for r in e[2]]
+        every = [r for e in items for r in e[2]]
+        folds = [r for r in every if isinstance(r, FoldRecipe)]
+        recipes = [r for r in every if not isinstance(r, FoldRecipe)]
         table = _lib.K.pack_table(recipes, recipes[0].src.device) if recipes else None
-        ent = (_PACK_GEN, items, table, weakref.ref(owner) if owner is not None else None)
+        ent = (_PACK_GEN, items, table, weakref.ref(owner) if owner is not None else None, folds)
         if owner is not None:
             if len(_REFRESH_TABLES) > 64:
                 _REFRESH_TABLES.clear()
             _REFRESH_TABLES[id(owner)] = ent
-    _, items, table, _ = ent
+    _, items, table, _, folds = ent
     if table is None:
         return 0
+    for fr in folds:                       # pooled convolutions: the folded weight images first, the packing reads them
+        fr.run()
     _host, dev, n, chunks = table
     _lib.K.pack_weight_multi(dev, n, chunks)
     for e in items:
@@ -263,6 +308,8 @@ def _tc_wgrad_ok(g: ConvGeom, x_layout: str, dy_layout: str) -> int:
 
 def _pack_fwd(g: ConvGeom, srcs, tc: bool, recipes: List[PackRecipe]):
     """wmat[co][(ky*kw+kx)*Cx + c] = w[co, cx_offset+c, ky, kx]; w = srcs concatenated along dim 0"""
+    if g.fold:
+        srcs = _folded_source(g, srcs, recipes)
     K = g.kh * g.kw * g.Cx
     ldw = _rup(K, _kalign(tc)) if tc else _rup(K, 4)
     mpad = _rup(g.Cy, _lib.K.conv_tc_ntile(g.Cy)) if tc else g.Cy
@@ -295,6 +342,8 @@ def _dgrad_phases(g: ConvGeom):
 def _pack_dgrad(g: ConvGeom, srcs, tc: bool, recipes: List[PackRecipe]):
     """per output phase: wmat[ci][(j*Tw+i)*Cy + co] = w[co, cx_offset+ci, ky0+s*j, kx0+s*i]; w = srcs concatenated along
     dim 0 (each source fills its own slice of the co axis)"""
+    if g.fold:
+        srcs = _folded_source(g, srcs, recipes)
     packs = []
     kk = g.kh * g.kw
     for (py, px, ky0, kx0, Th, Tw) in _dgrad_phases(g):
@@ -596,7 +645,8 @@ def conv_wgrad_sn_grouped(g: ConvGeom, x, dy, sn: "SNCall", w, spg: int, kind: i
                  out_sc=ds[3], ldw=K, relu=0)
     _lib.K.wgrad_gemm(d, dy, x, ws, splits, kind)
     dw = torch.empty_like(w)
-    return _lib.K.sn_wgrad_finish(ws, sn.groups, spg, g.Cy, kk, g.Cx, w, sn.u_hist, sn.v_hist, sn.inv, dw)
+    return _lib.K.sn_wgrad_finish(ws, sn.groups, spg, g.Cy, kk, g.Cx, w, sn.u_hist, sn.v_hist, sn.inv, dw,
+                                  pooled_taps=(g.kh - 1, g.kw - 1) if g.fold else None)
 
 
 _BIAS_GRAD_MEMO = [None, None]      # (weak reference to the gradient tensor, its column sums)
@@ -761,6 +811,15 @@ class _ConvFn(torch.autograd.Function):
         if need_dw:
             gw = torch.empty_like(w)
             dy_op = dyb if (wgrad_tc or packed) else dy
+
+            def wgrad(xx, xl, dd, dl):
+                """the plain weight gradient in the parameter's shape (a pooled convolution: through its folded image)"""
+                if not g.fold:
+                    return conv_wgrad(g, xx, xl, dd, dl, gw)
+                g4 = torch.empty((g.Cy, g.cx_total, g.kh, g.kw), dtype=torch.float32, device=w.device)
+                return unfold_pool_grad(conv_wgrad(g, xx, xl, dd, dl, g4))
+
+            assert not (g.fold and (packed or ctx.transposed))
             if packed:
                 N, Hy, Wy = ctx.y_dims
                 if sn is None:
@@ -776,10 +835,9 @@ class _ConvFn(torch.autograd.Function):
                         _lib.K.sn_grad(gw, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
             elif sn is None:
                 if not ctx.transposed:
-                    conv_wgrad(g, x, ctx.x_layout, dy_op, ctx.out_layout, gw)
+                    dw = wgrad(x, ctx.x_layout, dy_op, ctx.out_layout)
                 else:
-                    conv_wgrad(g, dy_op, ctx.out_layout, x, ctx.x_layout, gw)
-                dw = gw
+                    dw = wgrad(dy_op, ctx.out_layout, x, ctx.x_layout)
             elif wgrad_tc and _sn_group_splits(g, dy_op.shape[0] * dy_op.shape[1] * dy_op.shape[2], sn.groups) > 0:
                 assert not ctx.transposed
                 spg = _sn_group_splits(g, dy_op.shape[0] * dy_op.shape[1] * dy_op.shape[2], sn.groups)
@@ -791,8 +849,8 @@ class _ConvFn(torch.autograd.Function):
                 h, wd = w.shape[0], w[0].numel()
                 dw = torch.empty_like(w)
                 for gi in range(sn.groups):
-                    conv_wgrad(g, x[gi * n:(gi + 1) * n], ctx.x_layout, dy_op[gi * n:(gi + 1) * n], ctx.out_layout, gw)
-                    _lib.K.sn_grad(gw, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
+                    gg = wgrad(x[gi * n:(gi + 1) * n], ctx.x_layout, dy_op[gi * n:(gi + 1) * n], ctx.out_layout)
+                    _lib.K.sn_grad(gg, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = bias_grad(dy, ctx.out_layout)
         return dx, dw, db, None, None, None, None, None, None, None, None, None, None, None, None

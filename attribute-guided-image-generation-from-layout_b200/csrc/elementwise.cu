@@ -838,6 +838,33 @@ __global__ void __launch_bounds__(128) im2col_pack_staged_kernel(const T* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// avg_pool2(conv_{kh x kw, stride 1, pad p}(x; W)) == conv_{(kh+1) x (kw+1), stride 2, pad p}(x; W4) with
+//     W4[f][a][b] = 0.25 * sum_{i,j in {0,1}} W[f][a-i][b-j]        (terms outside the kh x kw window dropped)
+// (both are linear in x and the pooled output pixel (Y, X) averages the stride-1 outputs (2Y+i, 2X+j)).  The discriminator
+// blocks' second convolution is followed by that pooling (discriminator.py:52-57, 90-96): the folded form does 16/36 of the
+// multiply-adds of a 3x3 layer and never materialises the full-resolution output.  f = (cout, cin) filter index.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void fold_pool_weight_kernel(const float* __restrict__ w, float* __restrict__ w4, int64_t filters, int kh, int kw) {
+    const int kh4 = kh + 1, kw4 = kw + 1;
+    const int64_t n = filters * kh4 * kw4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = t / (kh4 * kw4);
+        const int r = (int)(t - f * (kh4 * kw4));
+        const int a = r / kw4, b = r - a * kw4;
+        const float* wf = w + f * kh * kw;
+        float acc = 0.f;                      // fixed order: (i, j) = (0,0), (0,1), (1,0), (1,1)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int k = a - i, l = b - j;
+                if (k >= 0 && k < kh && l >= 0 && l < kw) acc += wf[k * kw + l];
+            }
+        w4[t] = 0.25f * acc;
+    }
+}
+
 // y[b][c][r] = x[b][r][c]  (batched R x C -> C x R transpose; NCHW <-> channel-last)
 __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
     __shared__ float tile[32][33];
@@ -1217,6 +1244,15 @@ extern "C" int b200_im2col_pack(const void* x, int x_dt, int64_t N, int Hx, int 
         im2col_pack_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, M, Hx, Wx, Cx, sn, sh, sw, sc, kh, kw, stride,
                                                                   pad, Hy, Wy, Kp, flip, (bf16*)out_bf16);
     });
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200_fold_pool_weight(const float* w, float* w4, int64_t filters, int kh, int kw, b200_stream_t stream) {
+    if (filters == 0) return 0;
+    B200_REQUIRE(kh >= 1 && kw >= 1 && kh <= 15 && kw <= 15, "fold_pool_weight: bad kernel size");
+    const int64_t n = filters * (kh + 1) * (kw + 1);
+    fold_pool_weight_kernel<<<grid_for(n, 256, 4), 256, 0, as_stream(stream)>>>(w, w4, filters, kh, kw);
     B200_CHECK_LAUNCH();
     return 0;
 }

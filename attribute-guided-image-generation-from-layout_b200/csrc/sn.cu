@@ -219,10 +219,16 @@ constexpr int kSnMaxGroups = 8;
 // G_g per call in registers, accumulates <G_g, W> against the staged tile and sum_g G_g / sigma_g, and writes the latter into
 // the transposing tile; one coalesced store of the (m, c, tap)-ordered result per pass.  Two block syncs per pass.
 // Output: dW_main = sum_g G_g / sigma_g and the per-block partial dots <G_g, W>; the per-call G_g is never stored.
+//
+// FOLD (the pooled convolution, see b200_fold_pool_weight): the partials are those of the (Th+1) x (Tw+1) stride-2 convolution
+// with the folded weight; the gradient of the Th x Tw parameter tap (k, l) is 0.25 * the sum of the partials' taps
+// (k+i, l+j), i, j in {0, 1} — the transpose of the fold, applied while the splits are summed.  T = Th * Tw, Tw = fold_tw.
+template <bool FOLD>
 __global__ void __launch_bounds__(256) sn_wgrad_reduce_kernel(const float* __restrict__ ws, int groups, int spg,
                                                              int64_t split_stride, int M, int T, int C, int R,
                                                              const float* __restrict__ W, const float* __restrict__ inv,
-                                                             float* __restrict__ dW, double* __restrict__ dot_part) {
+                                                             float* __restrict__ dW, double* __restrict__ dot_part,
+                                                             int fold_tw) {
     extern __shared__ float sn_smem[];
     const int TP = T | 1;                         // odd tap pitch: conflict-free transposed access
     float* wtile = sn_smem;                       // [R][32][TP]  W, parameter order
@@ -251,17 +257,43 @@ __global__ void __launch_bounds__(256) sn_wgrad_reduce_kernel(const float* __res
             const int m = m0 + r;
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
             if (m < M && q * 4 < nvalid) {
-                const float* p = ws + ((int64_t)m * T + tap) * C + c0 + q * 4;
+                int64_t poff;                      // this item's offset inside one split's partial matrix
+                int T4 = T, tw4 = 0;
+                if (FOLD) {
+                    const int th = T / fold_tw;
+                    tw4 = fold_tw + 1;
+                    T4 = (th + 1) * tw4;
+                    const int k = tap / fold_tw, l = tap - k * fold_tw;
+                    poff = ((int64_t)m * T4 + k * tw4 + l) * C + c0 + q * 4;
+                } else {
+                    poff = ((int64_t)m * T + tap) * C + c0 + q * 4;
+                }
+                const float* p = ws + poff;
                 const float* wt = wtile + (r * 32 + q * 4) * TP + tap;
                 const float w0 = wt[0], w1 = wt[TP], w2 = wt[2 * TP], w3 = wt[3 * TP];
 #pragma unroll
                 for (int g = 0; g < kSnMaxGroups; ++g) {
                     if (g < groups) {
                         const float* pg = p + (int64_t)g * spg * split_stride;
-                        float4 a = *reinterpret_cast<const float4*>(pg);
-                        for (int sidx = 1; sidx < spg; ++sidx) {
-                            const float4 v = *reinterpret_cast<const float4*>(pg + (int64_t)sidx * split_stride);
-                            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                        float4 a;
+                        if (FOLD) {
+                            a = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int sidx = 0; sidx < spg; ++sidx) {
+                                const float* ps = pg + (int64_t)sidx * split_stride;
+                                const float4 v0 = *reinterpret_cast<const float4*>(ps);
+                                const float4 v1 = *reinterpret_cast<const float4*>(ps + C);
+                                const float4 v2 = *reinterpret_cast<const float4*>(ps + (int64_t)tw4 * C);
+                                const float4 v3 = *reinterpret_cast<const float4*>(ps + (int64_t)(tw4 + 1) * C);
+                                a.x += (v0.x + v1.x) + (v2.x + v3.x); a.y += (v0.y + v1.y) + (v2.y + v3.y);
+                                a.z += (v0.z + v1.z) + (v2.z + v3.z); a.w += (v0.w + v1.w) + (v2.w + v3.w);
+                            }
+                            a.x *= 0.25f; a.y *= 0.25f; a.z *= 0.25f; a.w *= 0.25f;
+                        } else {
+                            a = *reinterpret_cast<const float4*>(pg);
+                            for (int sidx = 1; sidx < spg; ++sidx) {
+                                const float4 v = *reinterpret_cast<const float4*>(pg + (int64_t)sidx * split_stride);
+                                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                            }
                         }
                         dot[g] += (double)a.x * w0 + (double)a.y * w1 + (double)a.z * w2 + (double)a.w * w3;
                         o.x += a.x * invs[g]; o.y += a.y * invs[g]; o.z += a.z * invs[g]; o.w += a.w * invs[g];
@@ -434,10 +466,11 @@ extern "C" int b200_sn_wgrad_parts(int M, int C) {
     return cb * rows;
 }
 
-extern "C" int b200_sn_wgrad_finish(const float* ws, int groups, int splits_per_group, int64_t split_stride, int M, int T,
-                                    int C, const float* W, const float* u_hist, const float* v_hist, const float* inv,
-                                    float* Gbuf, double* dot_part, float* dW, b200_stream_t stream) {
+static int sn_wgrad_finish_impl(const float* ws, int groups, int splits_per_group, int64_t split_stride, int M, int T,
+                                int C, const float* W, const float* u_hist, const float* v_hist, const float* inv,
+                                float* Gbuf, double* dot_part, float* dW, int fold_tw, b200_stream_t stream) {
     cudaStream_t st = as_stream(stream);
+    B200_REQUIRE(fold_tw == 0 || (fold_tw >= 1 && T % fold_tw == 0), "sn_wgrad_finish: fold_tw must divide T");
     B200_REQUIRE(groups >= 1 && groups <= kSnMaxGroups && splits_per_group >= 1, "sn_wgrad_finish: bad groups / splits");
     B200_REQUIRE((C & 3) == 0 && T >= 1 && T <= 64 && M >= 1 && M < 65536 && (split_stride & 3) == 0 &&
                      (int64_t)M * C * T < (1ll << 31),
@@ -456,13 +489,32 @@ extern "C" int b200_sn_wgrad_finish(const float* ws, int groups, int splits_per_
     B200_REQUIRE(smem <= 48 * 1024, "sn_wgrad_finish: tile too large");
     int rblocks = (rows + R - 1) / R;
     if (rblocks < 1) rblocks = 1;
-    sn_wgrad_reduce_kernel<<<dim3(cb, rblocks), 256, smem, st>>>(ws, groups, splits_per_group, split_stride, M, T, C, R, W, inv,
-                                                                dW, dot_part);
+    if (fold_tw)
+        sn_wgrad_reduce_kernel<true><<<dim3(cb, rblocks), 256, smem, st>>>(ws, groups, splits_per_group, split_stride, M, T, C,
+                                                                          R, W, inv, dW, dot_part, fold_tw);
+    else
+        sn_wgrad_reduce_kernel<false><<<dim3(cb, rblocks), 256, smem, st>>>(ws, groups, splits_per_group, split_stride, M, T, C,
+                                                                           R, W, inv, dW, dot_part, 0);
     B200_CHECK_LAUNCH();
     const int64_t n = (int64_t)M * C * T;
     sn_grad_groups_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(groups, u_hist, v_hist, inv, dot_part, cb * rblocks, dW, M, C * T);
     B200_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int b200_sn_wgrad_finish(const float* ws, int groups, int splits_per_group, int64_t split_stride, int M, int T,
+                                    int C, const float* W, const float* u_hist, const float* v_hist, const float* inv,
+                                    float* Gbuf, double* dot_part, float* dW, b200_stream_t stream) {
+    return sn_wgrad_finish_impl(ws, groups, splits_per_group, split_stride, M, T, C, W, u_hist, v_hist, inv, Gbuf, dot_part, dW,
+                                0, stream);
+}
+
+extern "C" int b200_sn_wgrad_finish_pooled(const float* ws, int groups, int splits_per_group, int64_t split_stride, int M,
+                                           int Th, int Tw, int C, const float* W, const float* u_hist, const float* v_hist,
+                                           const float* inv, double* dot_part, float* dW, b200_stream_t stream) {
+    B200_REQUIRE(Th >= 1 && Tw >= 1, "sn_wgrad_finish_pooled: bad taps");
+    return sn_wgrad_finish_impl(ws, groups, splits_per_group, split_stride, M, Th * Tw, C, W, u_hist, v_hist, inv, nullptr,
+                                dot_part, dW, Tw, stream);
 }
 
 extern "C" int b200_sn_power_iter_multi(const b200_sn_layer* layers, int n_layers, int max_h, int max_w, int iters,

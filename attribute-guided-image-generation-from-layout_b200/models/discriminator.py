@@ -30,10 +30,13 @@ class OptimizedBlock(nn.Module):
         """out_relu: return relu(block output) — every consumer of a discriminator block applies ReLU first (the next
         ResidualBlock's in-place ReLU, or the trunk's final one), so the trunk asks for the activated tensor directly"""
         h = self.resi[0](x, x_layout="nchw", relu=True, groups=groups, grad_premasked=True)
-        h = self.resi[2](h, groups=groups, mask_input_grad=True)      # the only consumer of the ReLU output above
+        # the only consumer of the ReLU output above; with downsampling the pooling is folded into the convolution
+        pooled_conv = self.downsample and ops.POOLED_CONV
+        h = self.resi[2](h, groups=groups, mask_input_grad=True, pool=pooled_conv)
         s = x
         if self.downsample:
-            h = ops.avg_pool2(h)
+            if not pooled_conv:
+                h = ops.avg_pool2(h)
             s = ops.pool_nchw(x, 2, 0.25)
         s = self.sc(s, x_layout="nchw", groups=groups)
         return ops.add_relu(h, s) if out_relu else ops.add(h, s)
@@ -41,7 +44,10 @@ class OptimizedBlock(nn.Module):
 
 class ResidualBlock(nn.Module):
     """discriminator.py:63-99.  resi[0] is an in-place ReLU evaluated before the shortcut, so BOTH branches consume
-    relu(x); avg-pool commutes with the sum of the two branches, so one pool serves both."""
+    relu(x).  Average pooling is linear, so pool(conv3(h)) + pool(sc(r)) is evaluated as
+    conv4x4/2(h; fold(W)) + sc(pool(r)): the second convolution runs as one stride-2 convolution with the folded weight
+    (16/36 of the multiply-adds, no full-resolution output) and the 1x1 shortcut on the pooled input (1/4 of its work).
+    ops.POOLED_CONV = False restores the literal order (convolutions at full resolution, one pooling pass over h + s)."""
 
     def __init__(self, dim_in, dim_out, downsample=False):
         super().__init__()
@@ -59,6 +65,12 @@ class ResidualBlock(nn.Module):
         """in_relu: x already is relu(previous block output); out_relu: return relu(block output) (see OptimizedBlock)"""
         r = x if in_relu else ops.relu(x)
         h = self.resi[1](r, relu=True, groups=groups, grad_premasked=True)
+        if self.downsample and ops.POOLED_CONV:
+            h = self.resi[3](h, groups=groups, mask_input_grad=True, pool=True)
+            s = ops.avg_pool2(r)
+            if self.learnable_sc:
+                s = self.sc(s, groups=groups)
+            return ops.add_relu(h, s) if out_relu else ops.add(h, s)
         h = self.resi[3](h, groups=groups, mask_input_grad=True)      # the only consumer of the ReLU output above
         s = self.sc(r, groups=groups) if self.learnable_sc else r
         if self.downsample:

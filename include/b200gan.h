@@ -376,6 +376,18 @@ int b200_sn_wgrad_finish(const float* ws, int groups, int splits_per_group, int6
                          const float* W, const float* u_hist, const float* v_hist, const float* inv, float* Gbuf,
                          double* dot_part, float* dW, b200_stream_t stream);
 
+/* The pooled convolution (discriminator.py:52-57, 90-96: the blocks' second convolution is followed by avg_pool2d(2)):
+ * avg_pool2(conv_{kh x kw, stride 1, pad p}(x; W)) = conv_{(kh+1) x (kw+1), stride 2, pad p}(x; W4),
+ * W4[f][a][b] = 0.25 * sum_{i,j in {0,1}} W[f][a-i][b-j] (f = filter (cout, cin); terms outside the window dropped).
+ * b200_fold_pool_weight writes W4 (filters x (kh+1) x (kw+1) fp32) from W (filters x kh x kw fp32).
+ * b200_sn_wgrad_finish_pooled is b200_sn_wgrad_finish for such a layer: `ws` holds the partials of the FOLDED convolution's
+ * weight gradient ((M, (Th+1)*(Tw+1), C) per split, split_stride = M*(Th+1)*(Tw+1)*C) and the transpose of the fold
+ * (G[m][c][k][l] = 0.25 * sum_{i,j} G4[m][k+i][l+j][c]) is applied while the splits are summed; W, dW: (M, C, Th, Tw). */
+int b200_fold_pool_weight(const float* w, float* w4, int64_t filters, int kh, int kw, b200_stream_t stream);
+int b200_sn_wgrad_finish_pooled(const float* ws, int groups, int splits_per_group, int64_t split_stride, int M, int Th,
+                                int Tw, int C, const float* W, const float* u_hist, const float* v_hist, const float* inv,
+                                double* dot_part, float* dW, b200_stream_t stream);
+
 /* The same power iteration for EVERY spectral-normalised layer of a network at once (4 launches per iteration instead
  * of 4 per layer), `iters` times in sequence — one per batched call of the network.  `layers` is a DEVICE array of
  * n_layers descriptors; iteration `it` of layer l records inv[it] = 1/sigma, u_hist[it*h ..], v_hist[it*w ..] (the

@@ -618,9 +618,28 @@ class EmulKernels:
             dW.copy_(val)
         return dW
 
-    def sn_wgrad_finish(self, ws, groups, spg, Cy, T, Cx, W, u_hist, v_hist, inv, dW):
+    def fold_pool_weight(self, w, w4):
+        """b200_fold_pool_weight: W4[f][a][b] = 0.25 * sum_{i,j in {0,1}} W[f][a-i][b-j]"""
+        self.launches += 1
+        kh, kw = w.shape[-2], w.shape[-1]
+        acc = torch.zeros_like(w4)
+        for i in (0, 1):
+            for j in (0, 1):
+                acc[..., i:i + kh, j:j + kw] += w.detach()
+        w4.copy_(0.25 * acc)
+        return w4
+
+    def sn_wgrad_finish(self, ws, groups, spg, Cy, T, Cx, W, u_hist, v_hist, inv, dW, pooled_taps=None):
         self.launches += 2
-        part = ws.view(groups, spg, Cy, T, Cx).sum(1)                     # (groups, Cy, tap, Cx)
+        if pooled_taps is not None:
+            # b200_sn_wgrad_finish_pooled: partials of the folded convolution, transposed fold while summing
+            th, tw = pooled_taps
+            T = th * tw
+            p4 = ws.view(groups, spg, Cy, th + 1, tw + 1, Cx).sum(1)
+            part = 0.25 * ((p4[:, :, :-1, :-1] + p4[:, :, :-1, 1:]) + (p4[:, :, 1:, :-1] + p4[:, :, 1:, 1:]))
+            part = part.reshape(groups, Cy, T, Cx)
+        else:
+            part = ws.view(groups, spg, Cy, T, Cx).sum(1)                 # (groups, Cy, tap, Cx)
         G = part.permute(0, 1, 3, 2).reshape(groups, Cy, Cx * T)           # parameter layout (Cy, Cx, T)
         Wm = W.detach().reshape(Cy, Cx * T)
         out = torch.zeros(Cy, Cx * T)

@@ -1079,3 +1079,71 @@ def test_conv_epilogue_statistics_match_the_statistics_pass(K, case, precision):
     finally:
         ops.FUSE_BN_STATS = prev
         ops.set_precision("fp32")
+
+
+# ---- pooled convolution: avg_pool2(conv(x)) as one stride-2 convolution with the folded weight ------------------------------
+@pytest.mark.parametrize("kh,kw", [(3, 3), (1, 1), (5, 3)])
+def test_fold_pool_weight_matches_definition(K, kh, kw):
+    """b200_fold_pool_weight against the definition in include/b200gan.h (the emulation), and the defining identity itself:
+    conv_{(kh+1)x(kw+1), stride 2}(x; W4) == avg_pool2(conv_{kh x kw}(x; W)) in torch fp64"""
+    g = torch.Generator().manual_seed(kh * 10 + kw)
+    w = torch.randn(6, 5, kh, kw, generator=g)
+    w4 = torch.empty(6, 5, kh + 1, kw + 1, device="cuda")
+    K.fold_pool_weight(w.cuda(), w4)
+    want = E.fold_pool_weight(w, torch.empty(6, 5, kh + 1, kw + 1))
+    close(w4.cpu(), want, 1e-7, "folded weight")
+    if kh == kw:
+        p = kh // 2
+        x = torch.randn(2, 5, 9, 12, generator=g).double()
+        a = F.avg_pool2d(F.conv2d(x, w.double(), padding=p), 2)
+        b = F.conv2d(x, want.double(), stride=2, padding=p)
+        close(b, a, 1e-6, "fold identity")          # (W4 above is the fp32 image)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "tf32"])
+@pytest.mark.parametrize("case", [(64, 128, 3, 1, 16, 3, 16), (64, 64, 3, 1, 32, 3, 2), (128, 256, 3, 1, 8, 1, 4),
+                                  (64, 128, 1, 0, 16, 2, 8), (128, 128, 3, 1, 6, 3, 2)])
+def test_pooled_conv_equals_conv_then_pool(K, case, precision):
+    """Conv2d(pool=True) semantics: forward, masked data gradient, spectral-norm weight gradient (grouped finish and the
+    per-call fallback) and bias gradient against torch's avg_pool2d(conv2d(x, W / sigma_g) + b) per batched call"""
+    Cx, Cy, k, p, H, groups, n = case
+    g = torch.Generator().manual_seed(Cx + Cy + H + groups)
+    x = torch.relu(torch.randn(groups * n, Cx, H, H, generator=g))          # a ReLU output: exercises mask_input_grad
+    w = torch.randn(Cy, Cx, k, k, generator=g) / (Cx * k * k) ** 0.5
+    b = torch.randn(Cy, generator=g)
+    u = F.normalize(torch.randn(Cy, generator=g), dim=0)
+    v = F.normalize(torch.randn(Cx * k * k, generator=g), dim=0)
+    gy = torch.randn(groups * n, Cy, H // 2, H // 2, generator=g)
+    tol = {"fp32": 3e-5, "tf32": 3e-3, "bf16": 2e-2}[precision]
+    ops.set_precision(precision)
+    try:
+        act = ops.act_dtype()
+        xd = _to_layout(x, "cl").cuda().to(act).requires_grad_(True)
+        wd, bd, ud, vd = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True), u.cuda(), v.cuda()
+        geom = ops.ConvGeom.pooled(Cx, Cy, k, k, p)
+        packs = ops.WeightPacks()
+        sn = ops.sn_iterate(wd.detach(), ud, vd, groups, True)
+        y = ops.conv2d(xd, wd, bd, geom, packs, "cl", "cl", sn=sn, mask_input_grad=True)
+        assert tuple(y.shape) == (groups * n, H // 2, H // 2, Cy)
+        y.backward(_to_layout(gy, "cl").cuda().to(y.dtype))
+        # the folded operands follow a raw weight update through refresh_packs (the optimizer hook's path)
+        wd.data.mul_(0.5)
+        ops.refresh_packs([wd])
+        y2 = ops.conv2d(xd.detach(), wd.detach(), None, geom, packs, "cl", "cl")
+    finally:
+        ops.set_precision("fp32")
+    st = {"l.weight_orig": w.clone().requires_grad_(True), "l.weight_u": u.clone(), "l.weight_v": v.clone()}
+    bias = b.clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ys = []
+    for gi in range(groups):
+        wn = O.sn_weight(st, "l", True)
+        ys.append(F.avg_pool2d(F.conv2d(xr[gi * n:(gi + 1) * n], wn, bias, padding=p), 2))
+    yr = torch.cat(ys)
+    yr.backward(gy)
+    close(_from_layout(y.float(), "cl"), yr, tol, "pooled conv fwd")
+    close(_from_layout(xd.grad.float(), "cl"), xr.grad * (x > 0), tol, "pooled conv masked dgrad")
+    close(wd.grad, st["l.weight_orig"].grad, tol if precision != "fp32" else 6e-5, "pooled conv sn wgrad")
+    close(bd.grad, bias.grad, 2e-5 if precision == "fp32" else tol, "pooled conv bias grad")
+    want2 = F.avg_pool2d(F.conv2d(x, 0.5 * w, None, padding=p), 2)
+    close(_from_layout(y2.float(), "cl"), want2, tol, "pooled conv after refresh_packs")
