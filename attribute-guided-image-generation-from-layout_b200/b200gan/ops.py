@@ -137,7 +137,7 @@ class PackRecipe:
 class FoldRecipe:
     """w4 = fold(w): the weight of the stride-2 convolution equal to avg_pool2(conv(x; w)); runs BEFORE the PackRecipes that
     read w4 (WeightPacks.get keeps it first in the entry's list; refresh_packs launches the folds, then the packing)"""
-    __slots__ = ("src", "dst")
+    __slots__ = ("src", "dst", "__weakref__")
 
     def __init__(self, src, dst):
         self.src, self.dst = src, dst
@@ -146,16 +146,23 @@ class FoldRecipe:
         _lib.K.fold_pool_weight(self.src, self.dst)
 
 
+_FOLD_IMAGES = weakref.WeakValueDictionary()      # parameter storage -> its live FoldRecipe (shared by the layer's operands)
+
+
 def _folded_source(g: ConvGeom, srcs, recipes):
-    """the (Cy, cx_total, kh, kw) fp32 image of a pooled convolution's parameter that the packing reads"""
+    """the (Cy, cx_total, kh, kw) fp32 image of a pooled convolution's parameter that the packing reads; the forward and the
+    data-gradient operands of a layer share one image (one fold per weight update)"""
     assert len(srcs) == 1 and g.fold
     w = srcs[0]
     assert tuple(w.shape[2:]) == (g.kh - 1, g.kw - 1) and w.is_contiguous(), (tuple(w.shape), g.key())
-    w4 = torch.empty((w.shape[0], w.shape[1], g.kh, g.kw), dtype=torch.float32, device=w.device)
-    fr = FoldRecipe(w, w4)
+    key = (w.data_ptr(), tuple(w.shape), str(w.device))
+    fr = _FOLD_IMAGES.get(key)
+    if fr is None:
+        w4 = torch.empty((w.shape[0], w.shape[1], g.kh, g.kw), dtype=torch.float32, device=w.device)
+        fr = _FOLD_IMAGES[key] = FoldRecipe(w, w4)
     fr.run()
     recipes.append(fr)
-    return (w4,)
+    return (fr.dst,)
 
 
 def unfold_pool_grad(g4: torch.Tensor) -> torch.Tensor:
@@ -235,7 +242,7 @@ def refresh_packs(params=None, owner=None):
                 if ptrs is None or any(_storage_ptr(t) in ptrs for t in e[3]):
                     items.append(e)
         every = [r for e in items for r in e[2]]
-        folds = [r for r in every if isinstance(r, FoldRecipe)]
+        folds = list({id(r): r for r in every if isinstance(r, FoldRecipe)}.values())
         recipes = [r for r in every if not isinstance(r, FoldRecipe)]
         table = _lib.K.pack_table(recipes, recipes[0].src.device) if recipes else None
         ent = (_PACK_GEN, items, table, weakref.ref(owner) if owner is not None else None, folds)

@@ -838,6 +838,84 @@ __global__ void __launch_bounds__(128) im2col_pack_staged_kernel(const T* __rest
     }
 }
 
+// Patch variant (unit input x-stride, stride-1 window walk, output rows made of whole 32-pixel strips — every few-channel
+// layer of the training step): the staged kernel above is instruction bound (one global load, bounds test and index update
+// per matrix element: ncu issue-active 75-78 %, profiles/r02m_mem_kernels.md).  Here a warp first copies the strip's INPUT
+// patch — kh rows x (32 + kw - 1) columns x Cx channels, channel-interleaved bf16 — into shared memory (kh*Cx coalesced row
+// reads, zero outside the image), then every 16-byte chunk of the strip's contiguous 32 x Kp output block is gathered from
+// the patch through a per-launch column -> patch-offset table (pixel r adds r*Cx).  ~3x fewer instructions per strip.
+template <typename T>
+__global__ void __launch_bounds__(128) im2col_pack_patch_kernel(const T* __restrict__ x, int64_t M, int Hx, int Wx, int Cx,
+                                                               int64_t sn, int64_t sh, int64_t sc, int kh, int kw, int pad,
+                                                               int Hy, int Wy, int Kp, int flip, bf16* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t pack_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int RW = 32 + kw - 1;                                   // patch columns
+    const int K = kh * kw * Cx;
+    const int row_elems = RW * Cx;
+    const int patch_pitch = (kh * row_elems + 7) & ~7;
+    uint16_t* koff = reinterpret_cast<uint16_t*>(pack_smem);      // [Kp]: patch offset of column k for pixel 0 (0xFFFF = padding)
+    uint16_t* patch = koff + Kp + (size_t)warp * patch_pitch;
+    for (int k = threadIdx.x; k < Kp; k += 128) {
+        uint16_t v = 0xFFFFu;
+        if (k < K) {
+            const int tap = k / Cx, c = k - tap * Cx;
+            const int ky = tap / kw, kx = tap - ky * kw;
+            v = (uint16_t)((ky * RW + (flip ? kw - 1 - kx : kx)) * Cx + c);
+        }
+        koff[k] = v;
+    }
+    __syncthreads();
+    const int cpr = Kp >> 3;                                      // 16-byte chunks per output row
+    const int64_t strips = M >> 5;
+    for (int64_t sidx = (int64_t)blockIdx.x * 4 + warp; sidx < strips; sidx += (int64_t)gridDim.x * 4) {
+        const int mi = (int)(sidx << 5);
+        const int qx0 = mi % Wy;
+        const int t0 = mi / Wy;
+        const int qy = t0 % Hy;
+        const int n = t0 / Hy;
+        const T* xb = x + (int64_t)n * sn;
+        // patch column j holds input column ixb + j; pixel r, tap kx reads column r + kx (flip: r + kw - 1 - kx)
+        const int ixb = flip ? qx0 + pad - (kw - 1) : qx0 - pad;
+        for (int ky = 0; ky < kh; ++ky) {
+            const int iy = flip ? qy + pad - ky : qy - pad + ky;
+            const bool rowok = iy >= 0 && iy < Hx;
+            const T* src = xb + (int64_t)iy * sh;
+            uint16_t* prow = patch + ky * row_elems;
+            int c = 0, j = lane;                                   // flattened (c, j) walk, lanes along the input row
+            while (j >= RW) { j -= RW; ++c; }
+            while (c < Cx) {
+                const int ix = ixb + j;
+                const float v = (rowok && ix >= 0 && ix < Wx) ? ldf(src + (int64_t)c * sc + ix) : 0.f;
+                prow[j * Cx + c] = f32_to_bf16_rn(v);
+                j += 32;
+                while (j >= RW) { j -= RW; ++c; }
+            }
+        }
+        __syncwarp();
+        bf16* o = out + ((int64_t)sidx << 5) * Kp;
+        int r = 0, q = lane;
+        while (q >= cpr) { q -= cpr; ++r; }
+        for (int t = lane; t < 32 * cpr; t += 32) {
+            const uint4 kt = *reinterpret_cast<const uint4*>(koff + q * 8);
+            const uint16_t* pr = patch + r * Cx;
+            const uint32_t ks[4] = {kt.x, kt.y, kt.z, kt.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t k0 = ks[e] & 0xFFFFu, k1 = ks[e] >> 16;
+                const uint32_t lo = k0 == 0xFFFFu ? 0u : pr[k0];
+                const uint32_t hi = k1 == 0xFFFFu ? 0u : pr[k1];
+                w[e] = lo | (hi << 16);
+            }
+            *reinterpret_cast<uint4*>(o + (int64_t)t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            q += 32;
+            while (q >= cpr) { q -= cpr; ++r; }
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // avg_pool2(conv_{kh x kw, stride 1, pad p}(x; W)) == conv_{(kh+1) x (kw+1), stride 2, pad p}(x; W4) with
 //     W4[f][a][b] = 0.25 * sum_{i,j in {0,1}} W[f][a-i][b-j]        (terms outside the kh x kw window dropped)
@@ -1218,6 +1296,18 @@ extern "C" int b200_im2col_pack(const void* x, int x_dt, int64_t N, int Hx, int 
     if (M == 0) return 0;
     B200_REQUIRE(Kp % 64 == 0 && Kp >= Cx * kh * kw && Kp <= 512, "im2col_pack: Kp=%d must be a multiple of 64 covering K=%d", Kp, Cx * kh * kw);
     B200_REQUIRE(M < (1ll << 31), "im2col_pack: too many output pixels");
+    const int patch_smem = Kp * 2 + 4 * (((kh * (32 + kw - 1) * Cx) + 7) & ~7) * 2;
+    if (sw == 1 && stride == 1 && Wy % 32 == 0 && patch_smem <= 48 * 1024 && kh * (32 + kw - 1) * Cx < 0xFFFF) {
+        // whole 32-pixel strips per output row: input patch staged in shared memory (see im2col_pack_patch_kernel)
+        const int64_t strips = M / 32;
+        const int grid = grid_for((strips + 3) / 4, 1, 12);
+        B200_DISPATCH_DT(x_dt, T, {
+            im2col_pack_patch_kernel<T><<<grid, 128, patch_smem, as_stream(stream)>>>((const T*)x, M, Hx, Wx, Cx, sn, sh, sc, kh, kw,
+                                                                                   pad, Hy, Wy, Kp, flip, (bf16*)out_bf16);
+        });
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
     if (sw == 1) {
         // NCHW-style input (unit stride along x): staged kernel, coalesced on both sides
         const int smem = 4 * 32 * (Kp + 8) * 2;

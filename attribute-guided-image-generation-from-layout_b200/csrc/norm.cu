@@ -212,21 +212,29 @@ __global__ void __launch_bounds__(256) norm_fwd_vec_kernel(const T* __restrict__
     const int rpb = blockDim.x / tpr;
     float ga[V], be[V];
     if (MODE == B200_NORM_AFFINE) { ldp<V>(gamma + c, ga); ldp<V>(beta + c, be); }
-    int g_cur = -1, seg_cur = -1;
     float m[V], rs[V];
     // a block owns a CONTIGUOUS range of rows: the group statistics and (conditional batch norm) the object's gamma / beta
-    // table row change only every rows_per_seg rows, so they are re-loaded on change instead of once per row
+    // table row change only every rows_per_group / rows_per_seg rows: the group and segment of a row are tracked
+    // incrementally (no integer division per row — the kernel was issue bound: ncu issue active 65 %, DRAM 21 %,
+    // profiles/r02m_mem_kernels.md) and their parameters re-loaded on change
     const int rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
     const int r_begin = blockIdx.x * rows_per_block;
     const int r_end = min(rows, r_begin + rows_per_block);
+    int r = r_begin + threadIdx.x / tpr;
+    if (r >= r_end) return;
+    int g = r / rows_per_group;
+    int64_t g_next = (int64_t)(g + 1) * rows_per_group;
+    int seg = MODE == B200_NORM_CBN ? r / rows_per_seg : 0;
+    int64_t seg_next = MODE == B200_NORM_CBN ? (int64_t)(seg + 1) * rows_per_seg : (int64_t)1 << 62;
+    bool new_g = true, new_seg = true;
 #pragma unroll 2
-    for (int r = r_begin + threadIdx.x / tpr; r < r_end; r += rpb) {
+    for (; r < r_end; r += rpb) {
         const int64_t o = (int64_t)r * C + c;
         float v[V];
         VecIO<T>::load(x + o, v);
-        const int g = r / rows_per_group;
-        if (g != g_cur) {
-            g_cur = g;
+        while (r >= g_next) { ++g; g_next += rows_per_group; new_g = true; }
+        if (new_g) {
+            new_g = false;
             float vv[V];
             ldp<V>(mean + (int64_t)g * C + c, m);
             ldp<V>(var + (int64_t)g * C + c, vv);
@@ -240,9 +248,9 @@ __global__ void __launch_bounds__(256) norm_fwd_vec_kernel(const T* __restrict__
 #pragma unroll
             for (int e = 0; e < V; ++e) out[e] = out[e] * ga[e] + be[e];
         } else if (MODE == B200_NORM_CBN) {
-            const int seg = r / rows_per_seg;
-            if (seg != seg_cur) {
-                seg_cur = seg;
+            while (r >= seg_next) { ++seg; seg_next += rows_per_seg; new_seg = true; }
+            if (new_seg) {
+                new_seg = false;
                 const float* row = gamma + (int64_t)idx[seg] * 2 * C;
                 ldp<V>(row + c, ga);
                 ldp<V>(row + C + c, be);
@@ -362,15 +370,45 @@ __global__ void __launch_bounds__(256) bn_stats_partial_vec_kernel(const T* __re
     double s1[V], s2[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.0;
-#pragma unroll 2
-    for (int64_t r = a + threadIdx.x / ct; r < b; r += rstep) {
-        float v[V];
-        VecIO<T>::load(x + r * C + c, v);
+    if (sizeof(T) == 2) {
+        // bf16 storage: runs of kRun rows are summed in fp32 (x*x is exact: 16 significant bits) and each run is folded into
+        // the fp64 accumulators — a quarter of the fp64 conversions / additions of the per-element form, and the run's loads
+        // are issued back to back (the kernel was latency bound: ncu issue active 43 %, DRAM 32 %, profiles/r02m_mem_kernels.md)
+        constexpr int kRun = 4;
+        int64_t r = a + threadIdx.x / ct;
+        for (; r + (int64_t)(kRun - 1) * rstep < b; r += (int64_t)kRun * rstep) {
+            float v[kRun][V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            const double d = (double)v[i];
-            s1[i] += d;
-            s2[i] += d * d;
+            for (int k = 0; k < kRun; ++k) VecIO<T>::load(x + (r + (int64_t)k * rstep) * C + c, v[k]);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                float f1 = v[0][i], f2 = v[0][i] * v[0][i];
+#pragma unroll
+                for (int k = 1; k < kRun; ++k) { f1 += v[k][i]; f2 = __fmaf_rn(v[k][i], v[k][i], f2); }
+                s1[i] += (double)f1;
+                s2[i] += (double)f2;
+            }
+        }
+        for (; r < b; r += rstep) {
+            float v[V];
+            VecIO<T>::load(x + r * C + c, v);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                s1[i] += (double)v[i];
+                s2[i] += (double)(v[i] * v[i]);
+            }
+        }
+    } else {
+#pragma unroll 2
+        for (int64_t r = a + threadIdx.x / ct; r < b; r += rstep) {
+            float v[V];
+            VecIO<T>::load(x + r * C + c, v);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const double d = (double)v[i];
+                s1[i] += d;
+                s2[i] += d * d;
+            }
         }
     }
     const int64_t chunk = (int64_t)blockIdx.z * gridDim.x + blockIdx.x;
@@ -628,13 +666,19 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_vec_kernel(const T* __rest
 #pragma unroll
     for (int e = 0; e < V; ++e) ga[e] = 1.f;
     if (MODE == B200_NORM_AFFINE) ldp<V>(gamma + c, ga);
-    int g_cur = -1, seg_cur = -1;
     float m[V], rs[V], sa[V], sb[V], be[V];
     const int rows_per_block = (rows + gridDim.x - 1) / gridDim.x;      // contiguous rows per block (see norm_fwd_vec_kernel)
     const int r_begin = blockIdx.x * rows_per_block;
     const int r_end = min(rows, r_begin + rows_per_block);
+    int r = r_begin + threadIdx.x / tpr;
+    if (r >= r_end) return;
+    int grp = r / rows_per_group;                                       // tracked incrementally, as in norm_fwd_vec_kernel
+    int64_t g_next = (int64_t)(grp + 1) * rows_per_group;
+    int seg = MODE == B200_NORM_CBN ? r / rows_per_seg : 0;
+    int64_t seg_next = MODE == B200_NORM_CBN ? (int64_t)(seg + 1) * rows_per_seg : (int64_t)1 << 62;
+    bool new_g = true, new_seg = true;
 #pragma unroll 2
-    for (int r = r_begin + threadIdx.x / tpr; r < r_end; r += rpb) {
+    for (; r < r_end; r += rpb) {
         const int64_t o = (int64_t)r * C + c;
         float g[V], xv[V];
         VecIO<T>::load(dy + o, g);
@@ -646,9 +690,9 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_vec_kernel(const T* __rest
             for (int e = 0; e < V; ++e)
                 if (!(yv[e] > 0.f)) g[e] = 0.f;
         }
-        const int grp = r / rows_per_group;
-        if (grp != g_cur) {
-            g_cur = grp;
+        while (r >= g_next) { ++grp; g_next += rows_per_group; new_g = true; }
+        if (new_g) {
+            new_g = false;
             float vv[V], s2[2 * V];
             ldp<V>(mean + (int64_t)grp * C + c, m);
             ldp<V>(var + (int64_t)grp * C + c, vv);
@@ -661,9 +705,9 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_vec_kernel(const T* __rest
             }
         }
         if (MODE == B200_NORM_CBN) {
-            const int seg = r / rows_per_seg;
-            if (seg != seg_cur) {
-                seg_cur = seg;
+            while (r >= seg_next) { ++seg; seg_next += rows_per_seg; new_seg = true; }
+            if (new_seg) {
+                new_seg = false;
                 const float* row = gamma + (int64_t)idx[seg] * 2 * C;
                 ldp<V>(row + c, ga);
                 if (relu == 2) ldp<V>(row + C + c, be);

@@ -632,7 +632,11 @@ def kernel_roofline(ts, b, args):
             "timing": "CUDA events around a graph of %d back-to-back launches per distinct launch shape" % R,
             "kernel_time_ms_per_step": (tc_t if tc_t > 0 else simt_t) * 1e3,
             "other_gemm_ms_per_step": (simt_t if tc_t > 0 else 0.0) * 1e3,
-            "algorithmic_tflop_per_step": (tc_f if tc_t > 0 else simt_f) / 1e12}
+            "algorithmic_tflop_per_step": (tc_f if tc_t > 0 else simt_f) / 1e12,
+            "flops_counted": "2*M*N*K of every launch as executed" + (
+                "; discriminator blocks run avg_pool2(conv3x3) as one 4x4 stride-2 convolution (16/36 of the reference's "
+                "multiply-adds for those layers), so the executed total is below the reference-model figure behind step_tflops"
+                if ops.POOLED_CONV else "")}
 
 
 def main():

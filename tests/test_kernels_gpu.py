@@ -191,6 +191,17 @@ def test_im2col_pack_bit_exact(K, case):
     got = K.im2col_pack(xd.cuda(), strides, N, H, H + 3, Cx, k, k, s, p, Hy, Wy, Kp)
     want = E.im2col_pack(xd, strides, N, H, H + 3, Cx, k, k, s, p, Hy, Wy, Kp)
     assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
+    if s == 1 and layout == "nchw":
+        # output rows made of whole 32-pixel strips: the shared-memory patch kernel (the shapes of the training step)
+        for (Hh, Ww) in ((5, 32), (32, 64), (7, 96)):
+            if 2 * p - k + 1 != 0:
+                continue
+            xs = torch.randn(N, Cx, Hh, Ww, generator=g)
+            st = ops.nchw_strides(Cx, Hh, Ww)
+            for flip in (False, True):
+                got = K.im2col_pack(xs.cuda(), st, N, Hh, Ww, Cx, k, k, 1, p, Hh, Ww, Kp, flip=flip)
+                want = E.im2col_pack(xs, st, N, Hh, Ww, Cx, k, k, 1, p, Hh, Ww, Kp, flip=flip)
+                assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16)), (Hh, Ww, flip)
     if s == 1:      # transposed window walk (the im2col matrix of an output gradient), rows over the conv INPUT grid
         Hi, Wi = H + 2 * p - k + 1, H + 3 + 2 * p - k + 1
         dyv = torch.randn(N, Cx, Hi, Wi, generator=g)
