@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -28,6 +30,9 @@ def shard_images(n_images: int, rank: int, world: int):
     per = (n_images + world - 1) // world
     lo = min(n_images, rank * per)
     return lo, min(n_images, lo + per)
+
+
+_GRADUATED = os.environ.get("B200_DDP_GRADUATED", "1") != "0"
 
 
 class GradBucketer:
@@ -64,7 +69,7 @@ class GradBucketer:
             remaining -= nb
             # graduated sizes: the buckets that complete near the END of backward have little compute left to hide behind, so
             # the last ~bucket_bytes worth of gradients goes out in quarter-size buckets
-            target = bucket_bytes if remaining > bucket_bytes else max(bucket_bytes // 4, 1 << 20)
+            target = bucket_bytes if (remaining > bucket_bytes or not _GRADUATED) else max(bucket_bytes // 4, 1 << 20)
             if size >= target:
                 self.buckets.append(cur)
                 cur, size = [], 0
