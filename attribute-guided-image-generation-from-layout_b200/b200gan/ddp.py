@@ -106,6 +106,14 @@ class GradBucketer:
 
     def _launch(self, bi: int):
         bucket, views, flat = self.buckets[bi], self.views[bi], self.flat[bi]
+        if flat.is_cuda:
+            # the bucket's gradients may have been produced on forked streams (the three discriminators run side by side,
+            # TrainStep._side_by_side): the copy and the collective are ordered after everything those streams hold so far
+            from . import ops
+            cur = torch.cuda.current_stream(flat.device)
+            for st in ops.all_forked_streams(flat.device):
+                if st != cur:
+                    cur.wait_stream(st)
         src = []
         missing = []
         for p, v in zip(bucket, views):

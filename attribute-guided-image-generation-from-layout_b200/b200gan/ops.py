@@ -8,6 +8,7 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import contextlib
 import os
 import weakref
 
@@ -524,6 +525,37 @@ def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bi
     return y
 
 
+SIDE_WGRAD = os.environ.get("B200_SIDE_WGRAD", "1") != "0"
+SIDE_WGRAD_MAX_TILES = int(os.environ.get("B200_SIDE_WGRAD_MAX_TILES", "444"))
+PARALLEL_PHASES = os.environ.get("B200_PARALLEL_PHASES", "1") != "0"
+PARALLEL_PHASES_MAX_TILES = int(os.environ.get("B200_PARALLEL_PHASES_MAX_TILES", "444"))      # per phase; 3 CTAs x 148 SMs
+_PHASE_STREAMS: Dict[str, list] = {}
+
+
+def _phase_streams(device, n: int):
+    pool = _PHASE_STREAMS.setdefault(str(device), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+_SIDE_STREAMS: Dict[str, list] = {}
+
+
+def side_streams(device, n: int):
+    """streams for coarse fork / join regions (TrainStep._side_by_side); distinct from the per-node phase / wgrad streams"""
+    pool = _SIDE_STREAMS.setdefault(str(device), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+def all_forked_streams(device):
+    """every stream this module may have launched work on besides the caller's: a collective over gradients produced under
+    fork / join regions waits for these (b200gan.ddp)"""
+    return list(_PHASE_STREAMS.get(str(device), [])) + list(_SIDE_STREAMS.get(str(device), []))
+
+
 def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layout, scale=None, out_dtype=None, mask=None):
     """dX = conv^T(dY, W)  (also the forward of nn.ConvTranspose2d).  mask: the layer input X when X is a ReLU output whose
     producer expects the masked gradient — dX is zeroed where X <= 0 (in the GEMM epilogue on the tcgen05 path)"""
@@ -538,6 +570,7 @@ def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layo
     dx, xs = _empty(N, Hx, Wx, g.Cx, out_layout, dy.device, odt)
     if any(p is None for p in phase_packs):
         dx.zero_()
+    launches = []
     for (py, px, ky0, kx0, Th, Tw), pk in zip(phases, phase_packs):
         if pk is None:
             continue
@@ -550,7 +583,31 @@ def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layo
                      in_sn=ds[0], in_sh=ds[1], in_sw=ds[2], in_sc=ds[3], out_sy=g.s, out_sx=g.s, out_oy=py, out_ox=px,
                      Ho=Hx, Wo=Wx, out_sn=xs[0], out_sh=xs[1], out_sw=xs[2], out_sc=xs[3], ldw=ldw, relu=0,
                      scale_rows=_scale_rows(scale, N * Qh * Qw))
-        _lib.K.conv_gemm(d, dy, wmat, None, scale, dx, tc, mask if (tc and mask is not None and mask.dtype == dx.dtype) else None)
+        launches.append((d, wmat))
+    emask = mask if (tc and mask is not None and mask.dtype == dx.dtype) else None
+    # the stride^2 output phases are independent launches over the same gradient (disjoint output pixels): small ones — fewer
+    # tiles each than the persistent kernel has CTA slots — run side by side on forked streams and join before returning
+    side = None
+    if PARALLEL_PHASES and tc and dy.is_cuda and len(launches) > 1:
+        d0 = launches[0][0]
+        tiles = -(-(N * d0.Qh * d0.Qw) // 128) * -(-g.Cx // (128 if g.Cx >= 128 else 64))
+        if tiles <= PARALLEL_PHASES_MAX_TILES:
+            side = _phase_streams(dy.device, len(launches) - 1)
+    if side is None:
+        for d, wmat in launches:
+            _lib.K.conv_gemm(d, dy, wmat, None, scale, dx, tc, emask)
+    else:
+        cur = torch.cuda.current_stream(dy.device)
+        for i, (d, wmat) in enumerate(launches):
+            if i == 0:
+                _lib.K.conv_gemm(d, dy, wmat, None, scale, dx, tc, emask)
+                continue
+            st = side[i - 1]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                _lib.K.conv_gemm(d, dy, wmat, None, scale, dx, tc, emask)
+        for st in side:
+            cur.wait_stream(st)
     if mask is not None and not (tc and mask.dtype == dx.dtype):
         dx = _lib.K.relu_bwd(dx, mask.to(dx.dtype) if mask.dtype != dx.dtype else mask)
     return dx
@@ -807,6 +864,15 @@ class _ConvFn(torch.autograd.Function):
         # one cast for both GEMMs (the tf32 kernels take the fp32 gradient as it is)
         dyb = tc_operand(dy, TC_BF16 if packed else max(dgrad_tc, wgrad_tc)) \
             if ((need_dx and dgrad_tc) or (need_dw and (wgrad_tc or packed))) else None
+        # small layers (fewer output tiles than the GPU has CTA slots): the weight-gradient chain (GEMM, split reduction,
+        # spectral-norm finish) runs on a forked stream next to the data-gradient launches and joins before this node returns
+        side = None
+        if SIDE_WGRAD and need_dx and need_dw and dy.is_cuda and dgrad_tc and wgrad_tc:
+            rows = dy.numel() // dy.shape[-1] if ctx.out_layout == "cl" else 0
+            if 0 < -(-rows // 128) * -(-g.Cy // (128 if g.Cy >= 128 else 64)) <= SIDE_WGRAD_MAX_TILES:
+                cur = torch.cuda.current_stream(dy.device)
+                side = _phase_streams(dy.device, 4)[3]
+                side.wait_stream(cur)
         if need_dx:
             dy_op = dyb if dgrad_tc else dy
             if not ctx.transposed:
@@ -816,48 +882,51 @@ class _ConvFn(torch.autograd.Function):
             else:
                 dx = conv_forward(g, packs, w, dy_op, ctx.out_layout, ctx.x_layout, None, scale, False, ctx.x_dtype)
         if need_dw:
-            gw = torch.empty_like(w)
-            dy_op = dyb if (wgrad_tc or packed) else dy
+          with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+              gw = torch.empty_like(w)
+              dy_op = dyb if (wgrad_tc or packed) else dy
 
-            def wgrad(xx, xl, dd, dl):
-                """the plain weight gradient in the parameter's shape (a pooled convolution: through its folded image)"""
-                if not g.fold:
-                    return conv_wgrad(g, xx, xl, dd, dl, gw)
-                g4 = torch.empty((g.Cy, g.cx_total, g.kh, g.kw), dtype=torch.float32, device=w.device)
-                return unfold_pool_grad(conv_wgrad(g, xx, xl, dd, dl, g4))
+              def wgrad(xx, xl, dd, dl):
+                  """the plain weight gradient in the parameter's shape (a pooled convolution: through its folded image)"""
+                  if not g.fold:
+                      return conv_wgrad(g, xx, xl, dd, dl, gw)
+                  g4 = torch.empty((g.Cy, g.cx_total, g.kh, g.kw), dtype=torch.float32, device=w.device)
+                  return unfold_pool_grad(conv_wgrad(g, xx, xl, dd, dl, g4))
 
-            assert not (g.fold and (packed or ctx.transposed))
-            if packed:
-                N, Hy, Wy = ctx.y_dims
-                if sn is None:
-                    dw = conv_wgrad_packed(g, x, N, Hy, Wy, dy_op, ctx.out_layout, gw)
-                else:
-                    n = N // sn.groups
-                    rows = n * Hy * Wy
-                    h, wd = w.shape[0], w[0].numel()
-                    dw = torch.empty_like(w)
-                    for gi in range(sn.groups):
-                        conv_wgrad_packed(g, x[gi * rows:(gi + 1) * rows], n, Hy, Wy, dy_op[gi * n:(gi + 1) * n],
-                                          ctx.out_layout, gw)
-                        _lib.K.sn_grad(gw, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
-            elif sn is None:
-                if not ctx.transposed:
-                    dw = wgrad(x, ctx.x_layout, dy_op, ctx.out_layout)
-                else:
-                    dw = wgrad(dy_op, ctx.out_layout, x, ctx.x_layout)
-            elif wgrad_tc and _sn_group_splits(g, dy_op.shape[0] * dy_op.shape[1] * dy_op.shape[2], sn.groups) > 0:
-                assert not ctx.transposed
-                spg = _sn_group_splits(g, dy_op.shape[0] * dy_op.shape[1] * dy_op.shape[2], sn.groups)
-                dw = conv_wgrad_sn_grouped(g, x, dy_op, sn, w, spg, wgrad_tc)
-            else:
-                # batched calls have their own sigma, u, v: gradient through W / sigma_g per group of rows
-                assert not ctx.transposed
-                n = x.shape[0] // sn.groups
-                h, wd = w.shape[0], w[0].numel()
-                dw = torch.empty_like(w)
-                for gi in range(sn.groups):
-                    gg = wgrad(x[gi * n:(gi + 1) * n], ctx.x_layout, dy_op[gi * n:(gi + 1) * n], ctx.out_layout)
-                    _lib.K.sn_grad(gg, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
+              assert not (g.fold and (packed or ctx.transposed))
+              if packed:
+                  N, Hy, Wy = ctx.y_dims
+                  if sn is None:
+                      dw = conv_wgrad_packed(g, x, N, Hy, Wy, dy_op, ctx.out_layout, gw)
+                  else:
+                      n = N // sn.groups
+                      rows = n * Hy * Wy
+                      h, wd = w.shape[0], w[0].numel()
+                      dw = torch.empty_like(w)
+                      for gi in range(sn.groups):
+                          conv_wgrad_packed(g, x[gi * rows:(gi + 1) * rows], n, Hy, Wy, dy_op[gi * n:(gi + 1) * n],
+                                            ctx.out_layout, gw)
+                          _lib.K.sn_grad(gw, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
+              elif sn is None:
+                  if not ctx.transposed:
+                      dw = wgrad(x, ctx.x_layout, dy_op, ctx.out_layout)
+                  else:
+                      dw = wgrad(dy_op, ctx.out_layout, x, ctx.x_layout)
+              elif wgrad_tc and _sn_group_splits(g, dy_op.shape[0] * dy_op.shape[1] * dy_op.shape[2], sn.groups) > 0:
+                  assert not ctx.transposed
+                  spg = _sn_group_splits(g, dy_op.shape[0] * dy_op.shape[1] * dy_op.shape[2], sn.groups)
+                  dw = conv_wgrad_sn_grouped(g, x, dy_op, sn, w, spg, wgrad_tc)
+              else:
+                  # batched calls have their own sigma, u, v: gradient through W / sigma_g per group of rows
+                  assert not ctx.transposed
+                  n = x.shape[0] // sn.groups
+                  h, wd = w.shape[0], w[0].numel()
+                  dw = torch.empty_like(w)
+                  for gi in range(sn.groups):
+                      gg = wgrad(x[gi * n:(gi + 1) * n], ctx.x_layout, dy_op[gi * n:(gi + 1) * n], ctx.out_layout)
+                      _lib.K.sn_grad(gg, w, sn.u_hist[gi], sn.v_hist[gi], sn.inv[gi:gi + 1], h, wd, dW=dw, accumulate=gi > 0)
+        if side is not None:
+            cur.wait_stream(side)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = bias_grad(dy, ctx.out_layout)
         return dx, dw, db, None, None, None, None, None, None, None, None, None, None, None, None

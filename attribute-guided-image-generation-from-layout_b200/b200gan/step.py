@@ -12,12 +12,15 @@ the discriminators' weight gradients during the G-step (zeroed before use, train
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F
 
 from . import ops
+
+PARALLEL_D = os.environ.get("B200_PARALLEL_D", "1") != "0"      # the three discriminators on forked streams (TrainStep._side_by_side)
 
 LAMBDAS = dict(img_adv=1.0, obj_adv=1.0, obj_cls=1.0, z_rec=8.0, img_rec=1.0, kl=0.01, att_cls=2.0)  # train64.py:439-446
 NUM_OBJECTS, NUM_ATTRIBUTES = 179, 106                                                               # data/vocab.json
@@ -210,6 +213,27 @@ class TrainStep:
     def g_loss(self, b, fake):
         return self.g_loss_fused(b, fake) if self.fused_losses else self.g_loss_torch(b, fake)
 
+    def _side_by_side(self, thunks):
+        """run independent sub-graphs (the three discriminators) on forked streams and join: their deep layers have fewer tiles
+        than the GPU has CTA slots, so the networks fill the machine together.  Autograd runs every backward node on its
+        forward stream, so the three backward passes overlap the same way.  Every fork starts by waiting for the current
+        stream and every use of the results follows the join (memory handed between the streams' allocator pools is ordered
+        by those two edges)."""
+        if not (PARALLEL_D and self.device.type == "cuda") or len(thunks) < 2:
+            return [t() for t in thunks]
+        cur = torch.cuda.current_stream(self.device)
+        side = ops.side_streams(self.device, len(thunks) - 1)
+        out = [None] * len(thunks)
+        for s in side:
+            s.wait_stream(cur)
+        out[0] = thunks[0]()
+        for i, s in enumerate(side):
+            with torch.cuda.stream(s):
+                out[i + 1] = thunks[i + 1]()
+        for s in side:
+            cur.wait_stream(s)
+        return out
+
     def d_loss_fused(self, b, fake):
         """train64.py:195-252 on the loss kernels: 4 term launches + 1 combine launch"""
         D_i, D_o, D_a = self.d_nets
@@ -218,12 +242,14 @@ class TrainStep:
         w4 = FAKE_W + (1.0,)
         dp = b.get("dp") or dict(img=1.0, obj=1.0, att=1.0, att_g=1.0, sum=1.0)     # count weights (sync_bn data parallel)
         acc = ops.FusedLoss(["d_img_fake", "d_img_real", "d_obj_fake", "d_obj_real", "d_obj_cls", "d_att"], self.device)
-        src = D_i(torch.cat([fake["imgs_fake"].detach(), b["imgs"]]), groups=4)
-        acc.add_bce_groups("d_img_fake", src, 4, (0, 0, 0, 1), w4, lam["img_adv"] * dp["img"], split_group=3)
-        src, cls = D_o(torch.cat([fake["crops_fake"].detach(), crops_input]), objs, groups=4)
+        src_i, (src, cls), att = self._side_by_side([
+            lambda: D_i(torch.cat([fake["imgs_fake"].detach(), b["imgs"]]), groups=4),
+            lambda: D_o(torch.cat([fake["crops_fake"].detach(), crops_input]), objs, groups=4),
+            lambda: D_a(crops_input)])
+        acc.add_bce_groups("d_img_fake", src_i, 4, (0, 0, 0, 1), w4, lam["img_adv"] * dp["img"], split_group=3)
         acc.add_bce_groups("d_obj_fake", src, 4, (0, 0, 0, 1), w4, lam["obj_adv"] * dp["obj"], split_group=3)
         acc.add_ce_groups("d_obj_cls", cls, objs, 4, (0, 0, 0, 1), lam["obj_cls"] * dp["obj"])
-        acc.add_bce_pos_weight_rows("d_att", D_a(crops_input), b["attribute_GT"], b["att_sel"], b["n_att_sel"], self.pos_weight,
+        acc.add_bce_pos_weight_rows("d_att", att, b["attribute_GT"], b["att_sel"], b["n_att_sel"], self.pos_weight,
                                     1, (1.0,), lam["att_cls"] * dp["att"])
         total = acc.total()
         return total, acc.term_dict(dict(d_img_fake=lam["img_adv"], d_img_real=lam["img_adv"], d_obj_fake=lam["obj_adv"],
@@ -247,9 +273,11 @@ class TrainStep:
         # 0.5 * mean|z_rand_rec - z| + 0.5 * mean|z_rand_shift - z|: the two crop-encoder passes are rows of one (2, O*z) tensor
         acc.add_l1_rows("g_z_rec", fake["mu2"], z, 2, None, 1.0, 0.5 * lam["z_rec"] * dp["obj"], broadcast_b=True)
         acc.add_kl("g_kl", mu, logvar, lam["kl"] * dp["sum"])
-        acc.add_bce_groups("g_img_adv", D_i(fake["imgs_fake"], groups=3), 3, (1, 1, 1), FAKE_W, lam["img_adv"] * dp["img"])
-        src, cls = D_o(fake["crops_fake"], objs, groups=3)
-        att = D_a(fake["crops_fake"], groups=3)
+        src_i, (src, cls), att = self._side_by_side([
+            lambda: D_i(fake["imgs_fake"], groups=3),
+            lambda: D_o(fake["crops_fake"], objs, groups=3),
+            lambda: D_a(fake["crops_fake"], groups=3)])
+        acc.add_bce_groups("g_img_adv", src_i, 3, (1, 1, 1), FAKE_W, lam["img_adv"] * dp["img"])
         acc.add_bce_groups("g_obj_adv", src, 3, (1, 1, 1), FAKE_W, lam["obj_adv"] * dp["obj"])
         acc.add_ce_groups("g_obj_cls", cls, objs, 3, FAKE_W, lam["obj_cls"] * dp["obj"])
         acc.add_bce_pos_weight_rows("g_obj_att", att, b["attribute"], b.get("att_sel_g", b["att_sel"]),
