@@ -1497,6 +1497,7 @@ class _ConvLSTMFn(torch.autograd.Function):
         dH = _lib.K.permute_rows(dout.contiguous().view(plan.S, hw * hid_last), plan.scatter_final,
                                  hw * hid_last).view(P, H, W, hid_last)
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        forked, keep = [], []
         for li in range(len(layers) - 1, -1, -1):
             L = layers[li]
             w = params[2 * li]
@@ -1521,16 +1522,30 @@ class _ConvLSTMFn(torch.autograd.Function):
                     dh_rec = conv_dgrad(L.gh, L.packs, w, dpre[o:o + n], "cl", (H, W), "cl", None, dout.dtype)
                     _lib.K.add(dH[op:op + n], dh_rec, out=dH[op:op + n])
                 dc_next, n_next = dc_prev, n
-            gw = torch.empty_like(w)
             dpre_op = tc_operand(dpre, _tc_dgrad_ok(L.gx, "cl"))              # one cast for the three GEMMs below
-            conv_wgrad(L.gx, xin, "cl", dpre_op, "cl", gw)
-            hprev = _lib.K.permute_rows(h_all.view(P, hw * hid), plan.hprev_src, hw * hid).view(P, H, W, hid)
-            conv_wgrad(L.gh, hprev, "cl", dpre_op, "cl", gw)
-            grads[2 * li] = gw
-            grads[2 * li + 1] = _lib.K.colsum(dpre.view(P * hw, 4 * hid))
+            # the layer's parameter gradients (two weight-gradient GEMMs + the bias column sums) are leaves of this node: they
+            # run on a forked stream next to the data gradient and the NEXT layer's latency-bound time-step loop
+            side = None
+            if SIDE_WGRAD and dout.is_cuda:
+                cur = torch.cuda.current_stream(dout.device)
+                side = _phase_streams(dout.device, 4)[3]
+                side.wait_stream(cur)
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                gw = torch.empty_like(w)
+                conv_wgrad(L.gx, xin, "cl", dpre_op, "cl", gw)
+                hprev = _lib.K.permute_rows(h_all.view(P, hw * hid), plan.hprev_src, hw * hid).view(P, H, W, hid)
+                conv_wgrad(L.gh, hprev, "cl", dpre_op, "cl", gw)
+                grads[2 * li] = gw
+                grads[2 * li + 1] = _lib.K.colsum(dpre.view(P * hw, 4 * hid))
+            if side is not None:
+                forked.append(side)
+                keep.append((dpre, dpre_op, xin, hprev, h_all))      # read on the forked stream: alive until the join below
             dxin = conv_dgrad(L.gx, L.packs, w, dpre_op, "cl", (H, W), "cl", None, dout.dtype)
             dH = dxin
         dx = _lib.K.permute_rows(dH.view(P, hw * C0), plan.unpack_src, hw * C0).view(O, H, W, C0)
+        for st in forked[-1:]:              # one stream serves every layer (in order): a single join before the node returns
+            torch.cuda.current_stream(dout.device).wait_stream(st)
+        del keep
         return (dx, None, None) + tuple(grads)
 
 

@@ -20,6 +20,7 @@ import torch.nn.functional as F
 
 from . import ops
 
+DEFER_TAIL = os.environ.get("B200_DEFER_TAIL", "1") != "0"       # the generator's last crop_encoder call next to the D passes
 PARALLEL_D = os.environ.get("B200_PARALLEL_D", "1") != "0"      # the three discriminators on forked streams (TrainStep._side_by_side)
 
 LAMBDAS = dict(img_adv=1.0, obj_adv=1.0, obj_cls=1.0, z_rec=8.0, img_rec=1.0, kl=0.01, att_cls=2.0)  # train64.py:439-446
@@ -200,9 +201,18 @@ class TrainStep:
             b["dp"] = self._global_counts(batch, b)
         return b
 
-    def generator(self, b, attribute_est):
+    def generator(self, b, attribute_est, defer_tail=False):
+        """defer_tail: see Generator.forward_batched — only _step passes it (and joins at the right places)"""
         return self.netG.forward_batched(b["imgs"], b["objs"], b["boxes"], b["masks"], b["obj_to_img"], b["z"],
-                                         b["attribute"], b["masks_shift"], b["boxes_shift"], attribute_est)
+                                         b["attribute"], b["masks_shift"], b["boxes_shift"], attribute_est,
+                                         defer_tail=defer_tail)
+
+    @staticmethod
+    def _join(fake):
+        """wait for the generator's deferred last call (Generator.forward_batched(defer_tail=True))"""
+        j = fake.get("join")
+        if j is not None:
+            j()
 
     # ---- losses (train64.py:195-252, 284-364) ----------------------------------------------------------------
     # Calls of one discriminator on different inputs are batched along dim 0 as `groups` (in the reference's call order):
@@ -270,13 +280,14 @@ class TrainStep:
         rec_mask = ops._loss_const(dp["rec_mask"], self.device)
         acc = ops.FusedLoss(["g_img_rec", "g_z_rec", "g_kl", "g_img_adv", "g_obj_adv", "g_obj_cls", "g_obj_att"], self.device)
         acc.add_l1_rows("g_img_rec", img_rec, imgs, N, rec_mask, dp["rec_denom"], lam["img_rec"] * dp["sum"])
-        # 0.5 * mean|z_rand_rec - z| + 0.5 * mean|z_rand_shift - z|: the two crop-encoder passes are rows of one (2, O*z) tensor
-        acc.add_l1_rows("g_z_rec", fake["mu2"], z, 2, None, 1.0, 0.5 * lam["z_rec"] * dp["obj"], broadcast_b=True)
         acc.add_kl("g_kl", mu, logvar, lam["kl"] * dp["sum"])
         src_i, (src, cls), att = self._side_by_side([
             lambda: D_i(fake["imgs_fake"], groups=3),
             lambda: D_o(fake["crops_fake"], objs, groups=3),
             lambda: D_a(fake["crops_fake"], groups=3)])
+        self._join(fake)
+        # 0.5 * mean|z_rand_rec - z| + 0.5 * mean|z_rand_shift - z|: the two crop-encoder passes are rows of one (2, O*z) tensor
+        acc.add_l1_rows("g_z_rec", fake["mu2"], z, 2, None, 1.0, 0.5 * lam["z_rec"] * dp["obj"], broadcast_b=True)
         acc.add_bce_groups("g_img_adv", src_i, 3, (1, 1, 1), FAKE_W, lam["img_adv"] * dp["img"])
         acc.add_bce_groups("g_obj_adv", src, 3, (1, 1, 1), FAKE_W, lam["obj_adv"] * dp["obj"])
         acc.add_ce_groups("g_obj_cls", cls, objs, 3, FAKE_W, lam["obj_cls"] * dp["obj"])
@@ -314,6 +325,7 @@ class TrainStep:
     def g_loss_torch(self, b, fake):
         (crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift, mu, logvar, z_rand_rec,
          z_rand_shift) = fake["outputs"]
+        self._join(fake)
         D_i, D_o, D_a = self.d_nets
         imgs, z, objs, attribute = b["imgs"], b["z"], b["objs"], b["attribute"]
         N, O = imgs.shape[0], objs.shape[0]
@@ -370,9 +382,9 @@ class TrainStep:
             torch.manual_seed(seeds[0])
         if self.skip_dead_work:
             with torch.no_grad():
-                fake = self.generator(b, attribute_est)                                           # train64.py:191
+                fake = self.generator(b, attribute_est, DEFER_TAIL)                               # train64.py:191
         else:
-            fake = self.generator(b, attribute_est)
+            fake = self.generator(b, attribute_est, DEFER_TAIL)
         d_total, d_terms = self.d_loss(b, fake)
         for n in self.d_nets:
             n.zero_grad(set_to_none=True)
@@ -381,6 +393,7 @@ class TrainStep:
         d_total.backward()
         if self.ddp_d is not None:
             self.ddp_d.finish()
+        self._join(fake)              # the D-step generator pass's deferred call (its running-statistics updates) ends here
         if optimizer_step:
             for o in self.opt_D:
                 o.step()
@@ -392,7 +405,7 @@ class TrainStep:
                 for p in n.parameters():
                     p.requires_grad_(False)
         try:
-            out = self.generator(b, attribute_est)                                                # train64.py:280
+            out = self.generator(b, attribute_est, DEFER_TAIL)                                    # train64.py:280
             g_total, g_terms = self.g_loss(b, out)
             self.netG.zero_grad(set_to_none=True)
             if self.ddp_g is not None:

@@ -284,13 +284,19 @@ class Generator(nn.Module):
                                     attribute_est)["outputs"]
 
     def forward_batched(self, imgs, objs, boxes, masks, obj_to_img, z_rand, attribute, masks_shift, boxes_shift,
-                        attribute_est):
+                        attribute_est, defer_tail=False):
         """generator_obj_att.py:618-647 with the three passes (rec, rand, shift) of every sub-network batched along
         dim 0 as three groups: one launch serves all three, while batch statistics, running-statistics updates, noise
         draws and ConvLSTM sequences stay per pass and in the reference's call order.  Returns the reference's 11-tuple
         ("outputs") plus the batched tensors the training step feeds to the discriminators:
         "imgs_fake" (3N,3,H,W) = [img_rec; img_rand; img_shift], "crops_fake" (3O,3,S,S) = [crops_input_rec; crops_rand;
-        crops_shift]."""
+        crops_shift].
+
+        defer_tail (training step only): the LAST sub-network call — crop_encoder on the generated crops, whose result only
+        the z-reconstruction loss reads — runs on a forked stream, and the returned dict carries "join": a callable that
+        makes the current stream wait for it.  The caller must call it before reading "mu2" / outputs[9:11], before the
+        next call of this module and before the optimizers run; until then the call overlaps whatever the caller launches
+        (the discriminator passes)."""
         o2i = obj_to_img.cpu() if obj_to_img.is_cuda else obj_to_img
         N, O = imgs.shape[0], objs.shape[0]
         objs32 = objs.to(torch.int32)
@@ -318,8 +324,19 @@ class Generator(nn.Module):
         crops_fake = crop_bbox_batch(imgs_fake, boxes3, o2i3, self.obj_size)
         crops_input_rec, crops_rand, crops_shift = crops_fake[:O], crops_fake[O:2 * O], crops_fake[2 * O:]
         # crop_encoder(crops_rand) then crop_encoder(crops_shift)   (:640, 645)
-        _, mu2, _ = self.crop_encoder(crops_fake[O:], objs32x3[:2 * O], groups=2)
+        join = None
+        if defer_tail and crops_fake.is_cuda:
+            cur = torch.cuda.current_stream(crops_fake.device)
+            tail = ops.side_streams(crops_fake.device, 3)[2]
+            tail.wait_stream(cur)
+            with torch.cuda.stream(tail):
+                _, mu2, _ = self.crop_encoder(crops_fake[O:], objs32x3[:2 * O], groups=2)
+
+            def join():
+                torch.cuda.current_stream(crops_fake.device).wait_stream(tail)
+        else:
+            _, mu2, _ = self.crop_encoder(crops_fake[O:], objs32x3[:2 * O], groups=2)
         z_rand_rec, z_rand_shift = mu2[:O], mu2[O:]
         outputs = (crops_input, crops_input_rec, crops_rand, crops_shift, img_rec, img_rand, img_shift, mu, logvar,
                    z_rand_rec, z_rand_shift)
-        return dict(outputs=outputs, imgs_fake=imgs_fake, crops_fake=crops_fake, mu2=mu2)
+        return dict(outputs=outputs, imgs_fake=imgs_fake, crops_fake=crops_fake, mu2=mu2, join=join)
