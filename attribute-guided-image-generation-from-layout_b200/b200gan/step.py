@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from . import ops
 
 DEFER_TAIL = os.environ.get("B200_DEFER_TAIL", "1") != "0"       # the generator's last crop_encoder call next to the D passes
+OVERLAP_G2 = os.environ.get("B200_OVERLAP_G2", "1") != "0"       # the G-step's generator pass next to the D-step
 PARALLEL_D = os.environ.get("B200_PARALLEL_D", "1") != "0"      # the three discriminators on forked streams (TrainStep._side_by_side)
 
 LAMBDAS = dict(img_adv=1.0, obj_adv=1.0, obj_cls=1.0, z_rec=8.0, img_rec=1.0, kl=0.01, att_cls=2.0)  # train64.py:439-446
@@ -385,6 +386,20 @@ class TrainStep:
                 fake = self.generator(b, attribute_est, DEFER_TAIL)                               # train64.py:191
         else:
             fake = self.generator(b, attribute_est, DEFER_TAIL)
+        # The G-step's generator pass (train64.py:280) reads nothing the D-step writes (discriminator weights, their
+        # spectral-norm vectors): it is issued HERE on a forked stream, after the D-step pass it must follow (batch-norm
+        # running statistics, noise draws), and runs next to the discriminators' forward / backward / Adam; joined before the
+        # G-step losses.  Its latency-bound parts (ConvLSTM time steps, 8x8 / 16x16 layers) fill the gaps of the D-step.
+        out = s2 = None
+        if OVERLAP_G2 and self.device.type == "cuda":
+            cur = torch.cuda.current_stream(self.device)
+            s2 = ops.side_streams(self.device, 4)[3]
+            s2.wait_stream(cur)
+            if seeds is not None:
+                torch.manual_seed(seeds[1])
+            with torch.cuda.stream(s2):
+                self._join(fake)                        # (the D-step pass's deferred crop_encoder call comes first)
+                out = self.generator(b, attribute_est, DEFER_TAIL)
         d_total, d_terms = self.d_loss(b, fake)
         for n in self.d_nets:
             n.zero_grad(set_to_none=True)
@@ -398,14 +413,17 @@ class TrainStep:
             for o in self.opt_D:
                 o.step()
         # ---------------- G-step ----------------
-        if seeds is not None:
+        if s2 is not None:
+            torch.cuda.current_stream(self.device).wait_stream(s2)
+        elif seeds is not None:
             torch.manual_seed(seeds[1])
         if self.skip_dead_work:
             for n in self.d_nets:
                 for p in n.parameters():
                     p.requires_grad_(False)
         try:
-            out = self.generator(b, attribute_est, DEFER_TAIL)                                    # train64.py:280
+            if out is None:
+                out = self.generator(b, attribute_est, DEFER_TAIL)                                # train64.py:280
             g_total, g_terms = self.g_loss(b, out)
             self.netG.zero_grad(set_to_none=True)
             if self.ddp_g is not None:
