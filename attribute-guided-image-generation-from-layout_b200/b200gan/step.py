@@ -148,14 +148,39 @@ class TrainStep:
         from .ddp import GradBucketer, broadcast_module
         for n in (self.netG,) + tuple(self.d_nets):
             broadcast_module(n, group=group)
-        self.ddp_d = GradBucketer([p for n in self.d_nets for p in n.parameters()], bucket_bytes, group)
-        self.ddp_g = GradBucketer(list(self.netG.parameters()), bucket_bytes, group)
+        self.ddp_d = GradBucketer(self._d_bucket_order(), bucket_bytes, group)
+        self.ddp_g = GradBucketer(self._g_bucket_order(), bucket_bytes, group)
         self.dp_group, self.sync_bn = group, bool(sync_bn)
         self.dp_world, self.dp_rank = dist.get_world_size(group), dist.get_rank(group)
         if sync_bn:
             if not self.fused_losses:
                 raise ValueError("sync_bn needs the fused loss path (count-weighted terms)")
             ops.set_sync_bn(group if group is not None else True)
+
+    def _g_bucket_order(self):
+        """generator parameters in forward order of use (GradBucketer fills its buckets from the END of the list, i.e. in the
+        order backward completes them): crop_encoder and attribute_encoder run first, then layout_encoder, global_encoder,
+        decoder — the module registration order (generator_obj_att.py:609-616 puts the decoder in the middle and the
+        attribute encoder last) would make the first bucket wait for the attribute encoder's gradients, the last to complete."""
+        rank = {"crop_encoder": 0, "attribute_encoder": 1, "layout_encoder": 2, "global_encoder": 3, "decoder": 4}
+        named = list(self.netG.named_parameters())
+        named.sort(key=lambda kv: rank.get(kv[0].split(".")[0], 5))            # stable: registration order inside a module
+        return [p for _, p in named]
+
+    def _d_bucket_order(self):
+        """discriminator parameters in the order their gradients complete, reversed (GradBucketer fills its buckets from the
+        END of the list).  The three networks run their backward passes side by side (_side_by_side), so gradients of equal
+        relative depth complete together: the parameters are merged by their fractional position inside their own network —
+        with the plain concatenation every bucket would wait for the end of the slowest network's pass."""
+        if not PARALLEL_D:
+            return [p for n in self.d_nets for p in n.parameters()]
+        keyed = []
+        for ni, n in enumerate(self.d_nets):
+            ps = list(n.parameters())
+            for i, p in enumerate(ps):
+                keyed.append(((i + 0.5) / len(ps), ni, i, p))
+        keyed.sort(key=lambda t: t[:3])
+        return [t[3] for t in keyed]
 
     def _global_counts(self, batch, b):
         """per-term weights world * n_local / n_global and the global image offset of this shard (sync_bn mode)"""
@@ -378,14 +403,18 @@ class TrainStep:
         rows = b.get("swap_rows")
         if rows is not None and rows.numel() > 0:                                               # train64.py:187-188
             attribute_est.index_copy_(0, rows, b["attribute"].index_select(0, rows))
+        if DEFER_TAIL and self.device.type == "cuda":
+            gen = lambda: self.generator(b, attribute_est, True)          # noqa: E731
+        else:
+            gen = lambda: self.generator(b, attribute_est)                # noqa: E731
         # ---------------- D-step ----------------
         if seeds is not None:
             torch.manual_seed(seeds[0])
         if self.skip_dead_work:
             with torch.no_grad():
-                fake = self.generator(b, attribute_est, DEFER_TAIL)                               # train64.py:191
+                fake = gen()                                                                   # train64.py:191
         else:
-            fake = self.generator(b, attribute_est, DEFER_TAIL)
+            fake = gen()
         # The G-step's generator pass (train64.py:280) reads nothing the D-step writes (discriminator weights, their
         # spectral-norm vectors): it is issued HERE on a forked stream, after the D-step pass it must follow (batch-norm
         # running statistics, noise draws), and runs next to the discriminators' forward / backward / Adam; joined before the
@@ -399,7 +428,7 @@ class TrainStep:
                 torch.manual_seed(seeds[1])
             with torch.cuda.stream(s2):
                 self._join(fake)                        # (the D-step pass's deferred crop_encoder call comes first)
-                out = self.generator(b, attribute_est, DEFER_TAIL)
+                out = gen()
         d_total, d_terms = self.d_loss(b, fake)
         for n in self.d_nets:
             n.zero_grad(set_to_none=True)
@@ -423,7 +452,7 @@ class TrainStep:
                     p.requires_grad_(False)
         try:
             if out is None:
-                out = self.generator(b, attribute_est, DEFER_TAIL)                                # train64.py:280
+                out = gen()                                                                       # train64.py:280
             g_total, g_terms = self.g_loss(b, out)
             self.netG.zero_grad(set_to_none=True)
             if self.ddp_g is not None:
