@@ -529,11 +529,15 @@ SIDE_WGRAD = os.environ.get("B200_SIDE_WGRAD", "1") != "0"
 SIDE_WGRAD_MAX_TILES = int(os.environ.get("B200_SIDE_WGRAD_MAX_TILES", "444"))
 PARALLEL_PHASES = os.environ.get("B200_PARALLEL_PHASES", "1") != "0"
 PARALLEL_PHASES_MAX_TILES = int(os.environ.get("B200_PARALLEL_PHASES_MAX_TILES", "444"))      # per phase; 3 CTAs x 148 SMs
-_PHASE_STREAMS: Dict[str, list] = {}
+PER_STREAM_FORKS = os.environ.get("B200_PER_STREAM_FORKS", "1") != "0"
+_PHASE_STREAMS: Dict[tuple, list] = {}
 
 
 def _phase_streams(device, n: int):
-    pool = _PHASE_STREAMS.setdefault(str(device), [])
+    """side streams of the CURRENT stream (the three discriminators run on their own streams, TrainStep._side_by_side: each
+    gets its own set, so their forked weight-gradient chains do not serialise on one shared stream)"""
+    cur = torch.cuda.current_stream(device).cuda_stream if PER_STREAM_FORKS else 0
+    pool = _PHASE_STREAMS.setdefault((str(device), cur), [])
     while len(pool) < n:
         pool.append(torch.cuda.Stream(device=device))
     return pool[:n]
@@ -553,7 +557,8 @@ def side_streams(device, n: int):
 def all_forked_streams(device):
     """every stream this module may have launched work on besides the caller's: a collective over gradients produced under
     fork / join regions waits for these (b200gan.ddp)"""
-    return list(_PHASE_STREAMS.get(str(device), [])) + list(_SIDE_STREAMS.get(str(device), []))
+    dev = str(device)
+    return [st for (d, _), pool in _PHASE_STREAMS.items() if d == dev for st in pool] + list(_SIDE_STREAMS.get(dev, []))
 
 
 def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layout, scale=None, out_dtype=None, mask=None):
