@@ -543,6 +543,40 @@ def _phase_streams(device, n: int):
     return pool[:n]
 
 
+# measured: forking the discriminator blocks' shortcut branch costs 0.5 ms per step (30.3 -> 30.85: the pooling pass and the
+# small 1x1 GEMM then compete with the residual branch's full-width GEMMs instead of filling a gap) — off
+FORK_BRANCHES = os.environ.get("B200_FORK_BRANCHES", "0") != "0"
+
+
+class forked:
+    """`with forked(x) as fk: ...` runs the body on a side stream of the current stream (a no-op off the GPU); `fk.join()`
+    makes the forking stream wait for it.  For independent branches of a module (a discriminator block's shortcut): autograd
+    keeps every node on its forward stream, so the branch's backward overlaps as well.  `x` (any tensor the branch reads) names
+    the device."""
+
+    def __init__(self, ref: torch.Tensor, index: int = 4):
+        self.on = FORK_BRANCHES and ref.is_cuda
+        if self.on:
+            self.cur = torch.cuda.current_stream(ref.device)
+            self.side = _phase_streams(ref.device, index + 1)[index]
+
+    def __enter__(self):
+        if self.on:
+            self.side.wait_stream(self.cur)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.on:
+            self.cur.wait_stream(self.side)
+
+
 _SIDE_STREAMS: Dict[str, list] = {}
 
 

@@ -64,13 +64,18 @@ class ResidualBlock(nn.Module):
     def forward(self, x, groups=1, in_relu=False, out_relu=False):
         """in_relu: x already is relu(previous block output); out_relu: return relu(block output) (see OptimizedBlock)"""
         r = x if in_relu else ops.relu(x)
-        h = self.resi[1](r, relu=True, groups=groups, grad_premasked=True)
         if self.downsample and ops.POOLED_CONV:
+            # the shortcut (pool, 1x1 convolution) is independent of the residual branch: it runs on a forked stream — forward
+            # here, and (autograd keeps every node on its forward stream) its backward next to the residual branch's
+            with ops.forked(r) as fk:
+                s = ops.avg_pool2(r)
+                if self.learnable_sc:
+                    s = self.sc(s, groups=groups)
+            h = self.resi[1](r, relu=True, groups=groups, grad_premasked=True)
             h = self.resi[3](h, groups=groups, mask_input_grad=True, pool=True)
-            s = ops.avg_pool2(r)
-            if self.learnable_sc:
-                s = self.sc(s, groups=groups)
+            fk.join()
             return ops.add_relu(h, s) if out_relu else ops.add(h, s)
+        h = self.resi[1](r, relu=True, groups=groups, grad_premasked=True)
         h = self.resi[3](h, groups=groups, mask_input_grad=True)      # the only consumer of the ReLU output above
         s = self.sc(r, groups=groups) if self.learnable_sc else r
         if self.downsample:
