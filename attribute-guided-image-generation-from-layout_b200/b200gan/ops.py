@@ -589,10 +589,10 @@ def side_streams(device, n: int):
 
 
 def all_forked_streams(device):
-    """every stream this module may have launched work on besides the caller's: a collective over gradients produced under
-    fork / join regions waits for these (b200gan.ddp)"""
-    dev = str(device)
-    return [st for (d, _), pool in _PHASE_STREAMS.items() if d == dev for st in pool] + list(_SIDE_STREAMS.get(dev, []))
+    """the streams autograd nodes may live on besides the caller's (the coarse fork / join regions of TrainStep): a collective
+    over gradients produced there waits for these (b200gan.ddp).  The per-node phase / weight-gradient streams are not listed:
+    they join their forking stream before the node returns."""
+    return list(_SIDE_STREAMS.get(str(device), []))
 
 
 def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layout, scale=None, out_dtype=None, mask=None):
