@@ -752,19 +752,20 @@ def conv_wgrad_sn_grouped(g: ConvGeom, x, dy, sn: "SNCall", w, spg: int, kind: i
                                   pooled_taps=(g.kh - 1, g.kw - 1) if g.fold else None)
 
 
-_BIAS_GRAD_MEMO = [None, None]      # (weak reference to the gradient tensor, its column sums)
+_BIAS_GRAD_MEMO: List[tuple] = []      # the last few (weak reference to a gradient tensor, its column sums)
 
 
 def bias_grad(dy: torch.Tensor, layout: str) -> torch.Tensor:
     """column sums of an output gradient.  Two convolutions that receive the SAME gradient tensor (a discriminator block's
     second convolution and its shortcut: pool(a + b) hands one tensor to both branches) share one reduction — the memo holds a
-    weak reference to the last tensor, so a hit is only possible while that very tensor object is alive."""
+    weak references to the last three tensors, so a hit is only possible while that very tensor object is alive."""
     if layout == "cl":
-        ref, val = _BIAS_GRAD_MEMO
-        if ref is not None and ref() is dy and val.shape[0] == dy.shape[-1]:
-            return val.clone()
+        for ref, val in _BIAS_GRAD_MEMO:
+            if ref() is dy and val.shape[0] == dy.shape[-1]:
+                return val.clone()
         val = _lib.K.colsum(dy.reshape(-1, dy.shape[-1]))
-        _BIAS_GRAD_MEMO[0], _BIAS_GRAD_MEMO[1] = weakref.ref(dy), val
+        _BIAS_GRAD_MEMO.insert(0, (weakref.ref(dy), val))
+        del _BIAS_GRAD_MEMO[3:]
         return val
     N, C, H, W = dy.shape
     per = _lib.K.rowsum(dy.contiguous().view(N * C, H * W))          # per-(n, c) sums, then over n
