@@ -103,6 +103,8 @@ class GradBucketer:
         self.enabled = True
         self._pending = [len(b) for b in self.buckets]
         self._work = [None] * len(self.buckets)
+        # the stream backward() is called from: gradients of sub-graphs that ran on it (not on a forked stream) complete there
+        self._ambient = torch.cuda.current_stream(self.flat[0].device) if (self.flat and self.flat[0].is_cuda) else None
 
     def _launch(self, bi: int):
         bucket, views, flat = self.buckets[bi], self.views[bi], self.flat[bi]
@@ -111,7 +113,7 @@ class GradBucketer:
             # TrainStep._side_by_side): the copy and the collective are ordered after everything those streams hold so far
             from . import ops
             cur = torch.cuda.current_stream(flat.device)
-            for st in ops.all_forked_streams(flat.device):
+            for st in ops.all_forked_streams(flat.device) + ([self._ambient] if getattr(self, "_ambient", None) is not None else []):
                 if st != cur:
                     cur.wait_stream(st)
         src = []

@@ -354,3 +354,45 @@ def test_attribute_classifier_training_iterations():
         ua = torch.cat([(p.detach().cpu() - before[k]).reshape(-1) for k, p in st.net.named_parameters()]).double()
         ur = torch.cat([(sd[k].detach() - before[k]).reshape(-1) for k, _ in st.net.named_parameters()]).double()
         assert float(torch.nn.functional.cosine_similarity(ua, ur, dim=0)) > 0.999
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forked_streams_bit_identical_to_single_stream(precision):
+    """The fork / join concurrency of the iteration (three discriminators side by side, the G-step generator pass next to the
+    D-step, deferred crop-encoder call, forked weight-gradient chains and data-gradient phases) only changes WHEN
+    kernels run: two training iterations with every lever off and with every lever on must agree bit for bit — losses, all 11
+    generator outputs, every parameter after the Adam updates, batch-norm running statistics and spectral-norm vectors.  Every
+    kernel has fixed-order reductions, so any difference would be a missing dependency between streams."""
+    import b200gan.step as step_mod
+    batch = O.synth_batch(4, 64, None, 21)                      # ragged: 3..9 objects per image
+    states = O.make_states(64, 3)
+    flags = [(step_mod, "PARALLEL_D"), (step_mod, "OVERLAP_G2"), (step_mod, "DEFER_TAIL"), (ops, "SIDE_WGRAD"),
+             (ops, "PARALLEL_PHASES"), (ops, "PER_STREAM_FORKS")]
+    saved = [getattr(m, n) for m, n in flags]
+    runs = []
+    ops.set_precision(precision)
+    try:
+        for on in (False, True, True):                          # the forked run twice: it must also agree with itself
+            for m, n in flags:
+                setattr(m, n, on)
+            torch.manual_seed(0)
+            ts = TrainStep(64, device="cuda")
+            load_states(ts, states)
+            b = ts.to_device(batch)
+            res = None
+            for it in range(2):
+                res = ts.step(b, optimizer_step=True, seeds=(31 + it, 41 + it))
+            torch.cuda.synchronize()
+            snap = [res["d_loss"].clone(), res["g_loss"].clone()] + [t.clone() for t in res["out_g"]]
+            for net in (ts.netG, ts.netD_image, ts.netD_object, ts.netD_att):
+                snap += [v.detach().clone() for _, v in sorted(net.state_dict().items())]
+            runs.append(snap)
+    finally:
+        for (m, n), v in zip(flags, saved):
+            setattr(m, n, v)
+        ops.set_precision("fp32")
+    for other in runs[1:]:
+        assert len(other) == len(runs[0])
+        for i, (a, r) in enumerate(zip(runs[0], other)):
+            assert torch.equal(a, r), "tensor %d differs between the single-stream and the forked iteration" % i
