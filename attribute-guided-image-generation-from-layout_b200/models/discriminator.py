@@ -65,8 +65,8 @@ class ResidualBlock(nn.Module):
         """in_relu: x already is relu(previous block output); out_relu: return relu(block output) (see OptimizedBlock)"""
         r = x if in_relu else ops.relu(x)
         if self.downsample and ops.POOLED_CONV:
-            # the shortcut (pool, 1x1 convolution) is independent of the residual branch: it runs on a forked stream — forward
-            # here, and (autograd keeps every node on its forward stream) its backward next to the residual branch's
+            # the shortcut (pool, 1x1 convolution) is independent of the residual branch; ops.FORK_BRANCHES puts it on a
+            # forked stream (off by default: measured 0.5 ms slower per step, DESIGN.md §7) — otherwise `forked` is a no-op
             with ops.forked(r) as fk:
                 s = ops.avg_pool2(r)
                 if self.learnable_sc:
