@@ -525,6 +525,18 @@ def conv_forward(g: ConvGeom, packs: WeightPacks, w, x, x_layout, out_layout, bi
     return y
 
 
+# When the fork / join levers below (and those of b200gan.step) apply: "capture" = only while the current stream is being
+# captured into a CUDA graph (the replayed iteration is GPU bound and gains 5 ms from them; an EAGER iteration is bound by the
+# host's ~1900 launches and the extra stream switches only cost it time: 46 -> 57-65 ms), "always", or "off".
+FORKS = os.environ.get("B200_FORKS", "capture")
+
+
+def forks_enabled(device=None) -> bool:
+    if FORKS == "always":
+        return True
+    return FORKS == "capture" and torch.cuda.is_current_stream_capturing()
+
+
 SIDE_WGRAD = os.environ.get("B200_SIDE_WGRAD", "1") != "0"
 SIDE_WGRAD_MAX_TILES = int(os.environ.get("B200_SIDE_WGRAD_MAX_TILES", "444"))
 PARALLEL_PHASES = os.environ.get("B200_PARALLEL_PHASES", "1") != "0"
@@ -555,7 +567,7 @@ class forked:
     the device."""
 
     def __init__(self, ref: torch.Tensor, index: int = 4):
-        self.on = FORK_BRANCHES and ref.is_cuda
+        self.on = FORK_BRANCHES and ref.is_cuda and forks_enabled()
         if self.on:
             self.cur = torch.cuda.current_stream(ref.device)
             self.side = _phase_streams(ref.device, index + 1)[index]
@@ -627,7 +639,7 @@ def conv_dgrad(g: ConvGeom, packs: WeightPacks, w, dy, dy_layout, x_hw, out_layo
     # the stride^2 output phases are independent launches over the same gradient (disjoint output pixels): small ones — fewer
     # tiles each than the persistent kernel has CTA slots — run side by side on forked streams and join before returning
     side = None
-    if PARALLEL_PHASES and tc and dy.is_cuda and len(launches) > 1:
+    if PARALLEL_PHASES and tc and dy.is_cuda and len(launches) > 1 and forks_enabled():
         d0 = launches[0][0]
         tiles = -(-(N * d0.Qh * d0.Qw) // 128) * -(-g.Cx // (128 if g.Cx >= 128 else 64))
         if tiles <= PARALLEL_PHASES_MAX_TILES:
@@ -907,7 +919,7 @@ class _ConvFn(torch.autograd.Function):
         # small layers (fewer output tiles than the GPU has CTA slots): the weight-gradient chain (GEMM, split reduction,
         # spectral-norm finish) runs on a forked stream next to the data-gradient launches and joins before this node returns
         side = None
-        if SIDE_WGRAD and need_dx and need_dw and dy.is_cuda and dgrad_tc and wgrad_tc:
+        if SIDE_WGRAD and need_dx and need_dw and dy.is_cuda and dgrad_tc and wgrad_tc and forks_enabled():
             rows = dy.numel() // dy.shape[-1] if ctx.out_layout == "cl" else 0
             if 0 < -(-rows // 128) * -(-g.Cy // (128 if g.Cy >= 128 else 64)) <= SIDE_WGRAD_MAX_TILES:
                 cur = torch.cuda.current_stream(dy.device)
@@ -1566,7 +1578,7 @@ class _ConvLSTMFn(torch.autograd.Function):
             # the layer's parameter gradients (two weight-gradient GEMMs + the bias column sums) are leaves of this node: they
             # run on a forked stream next to the data gradient and the NEXT layer's latency-bound time-step loop
             side = None
-            if SIDE_WGRAD and dout.is_cuda:
+            if SIDE_WGRAD and dout.is_cuda and forks_enabled():
                 cur = torch.cuda.current_stream(dout.device)
                 side = _phase_streams(dout.device, 4)[3]
                 side.wait_stream(cur)

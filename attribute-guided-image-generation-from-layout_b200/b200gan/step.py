@@ -255,7 +255,7 @@ class TrainStep:
         forward stream, so the three backward passes overlap the same way.  Every fork starts by waiting for the current
         stream and every use of the results follows the join (memory handed between the streams' allocator pools is ordered
         by those two edges)."""
-        if not (PARALLEL_D and self.device.type == "cuda") or len(thunks) < 2:
+        if not (PARALLEL_D and self.device.type == "cuda" and ops.forks_enabled()) or len(thunks) < 2:
             return [t() for t in thunks]
         cur = torch.cuda.current_stream(self.device)
         side = ops.side_streams(self.device, len(thunks) - 1)
@@ -403,7 +403,7 @@ class TrainStep:
         rows = b.get("swap_rows")
         if rows is not None and rows.numel() > 0:                                               # train64.py:187-188
             attribute_est.index_copy_(0, rows, b["attribute"].index_select(0, rows))
-        if DEFER_TAIL and self.device.type == "cuda":
+        if DEFER_TAIL and self.device.type == "cuda" and ops.forks_enabled():
             gen = lambda: self.generator(b, attribute_est, True)          # noqa: E731
         else:
             gen = lambda: self.generator(b, attribute_est)                # noqa: E731
@@ -420,7 +420,7 @@ class TrainStep:
         # running statistics, noise draws), and runs next to the discriminators' forward / backward / Adam; joined before the
         # G-step losses.  Its latency-bound parts (ConvLSTM time steps, 8x8 / 16x16 layers) fill the gaps of the D-step.
         out = s2 = None
-        if OVERLAP_G2 and self.device.type == "cuda":
+        if OVERLAP_G2 and self.device.type == "cuda" and ops.forks_enabled():
             cur = torch.cuda.current_stream(self.device)
             s2 = ops.side_streams(self.device, 4)[3]
             s2.wait_stream(cur)

@@ -370,10 +370,12 @@ def test_forked_streams_bit_identical_to_single_stream(precision):
     flags = [(step_mod, "PARALLEL_D"), (step_mod, "OVERLAP_G2"), (step_mod, "DEFER_TAIL"), (ops, "SIDE_WGRAD"),
              (ops, "PARALLEL_PHASES"), (ops, "PER_STREAM_FORKS")]
     saved = [getattr(m, n) for m, n in flags]
+    saved_mode = ops.FORKS
     runs = []
     ops.set_precision(precision)
     try:
         for on in (False, True, True):                          # the forked run twice: it must also agree with itself
+            ops.FORKS = "always" if on else "off"               # (the default applies the levers only under graph capture)
             for m, n in flags:
                 setattr(m, n, on)
             torch.manual_seed(0)
@@ -389,6 +391,7 @@ def test_forked_streams_bit_identical_to_single_stream(precision):
                 snap += [v.detach().clone() for _, v in sorted(net.state_dict().items())]
             runs.append(snap)
     finally:
+        ops.FORKS = saved_mode
         for (m, n), v in zip(flags, saved):
             setattr(m, n, v)
         ops.set_precision("fp32")
