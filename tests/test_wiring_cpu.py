@@ -217,3 +217,91 @@ def test_fused_losses_equal_the_torch_formulation(emul):
         a = torch.cat([p.grad.reshape(-1) for p in na.parameters()])
         b_ = torch.cat([p.grad.reshape(-1) for p in nb.parameters()])
         assert rel(a, b_) < 1e-4
+
+
+def test_pooled_convolution_identity_and_literal_order(emul):
+    """The discriminator blocks evaluate avg_pool2(conv3x3(h)) + avg_pool2(sc(r)) as conv4x4/2(h; fold(W)) + sc(avg_pool2(r))
+    (ops.ConvGeom.pooled, DESIGN.md §3).  (1) the defining identity and its gradient transpose in torch fp64;
+    (2) Conv2d(pool=True) through the ABI emulation against avg_pool2d(conv2d) incl. gradients; (3) a whole discriminator
+    with ops.POOLED_CONV on and off: same logits and same parameter gradients (fp32 round-off apart)."""
+    import torch.nn.functional as F
+    from abi_emul import EmulKernels
+    from b200gan import nn as bnn, ops
+    g = torch.Generator().manual_seed(5)
+    # (1)
+    for k, p in ((3, 1), (1, 0), (5, 2)):
+        w = torch.randn(6, 4, k, k, generator=g, dtype=torch.float64)
+        w4 = EmulKernels().fold_pool_weight(w, torch.empty(6, 4, k + 1, k + 1, dtype=torch.float64))
+        x = torch.randn(2, 4, 10, 14, generator=g, dtype=torch.float64)
+        assert rel(F.conv2d(x, w4, stride=2, padding=p), F.avg_pool2d(F.conv2d(x, w, padding=p), 2)) < 1e-12
+        g4 = torch.randn(6, 4, k + 1, k + 1, generator=g, dtype=torch.float64)
+        wl = w.clone().requires_grad_(True)
+        acc = torch.zeros(6, 4, k + 1, k + 1, dtype=torch.float64)
+        for i in (0, 1):
+            for j in (0, 1):
+                acc[..., i:i + k, j:j + k] += wl
+        (0.25 * acc * g4).sum().backward()
+        assert rel(ops.unfold_pool_grad(g4), wl.grad) < 1e-12
+    # (2)
+    conv = bnn.Conv2d(8, 16, kernel_size=3, stride=1, padding=1, bias=True)
+    x = torch.randn(3, 12, 12, 8, generator=g).requires_grad_(True)          # channel-last
+    y = conv(x, pool=True)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    xr = x.detach().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wr, br = conv.weight.detach().clone().requires_grad_(True), conv.bias.detach().clone().requires_grad_(True)
+    yr = F.avg_pool2d(F.conv2d(xr, wr, br, padding=1), 2)
+    yr.backward(gy.permute(0, 3, 1, 2))
+    assert rel(y.permute(0, 3, 1, 2), yr) < 1e-5
+    assert rel(x.grad.permute(0, 3, 1, 2), xr.grad) < 1e-5
+    assert rel(conv.weight.grad, wr.grad) < 1e-5 and rel(conv.bias.grad, br.grad) < 1e-5
+    # (3)
+    from models.discriminator import ObjectDiscriminator
+    torch.manual_seed(1)
+    net = bnn.add_sn(ObjectDiscriminator(n_class=179))
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+    crops = torch.randn(6, 3, 32, 32, generator=g)
+    objs = torch.randint(1, 179, (6,), generator=g)
+    outs = []
+    prev = ops.POOLED_CONV
+    try:
+        for pooled in (True, False):
+            ops.POOLED_CONV = pooled
+            net.load_state_dict(state)
+            net.zero_grad(set_to_none=True)
+            src, cls = net(crops, objs, groups=2)
+            (src.sum() + (cls * cls).mean()).backward()
+            outs.append((src.detach().clone(), cls.detach().clone(),
+                         {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+    finally:
+        ops.POOLED_CONV = prev
+    assert rel(outs[0][0], outs[1][0]) < 1e-4 and rel(outs[0][1], outs[1][1]) < 1e-4
+    assert outs[0][2].keys() == outs[1][2].keys()
+    for k in outs[0][2]:
+        assert rel(outs[0][2][k], outs[1][2][k]) < 2e-3 or float((outs[0][2][k] - outs[1][2][k]).abs().max()) < 1e-6, k
+
+
+def test_gradient_bucket_orders_follow_backward_completion(emul):
+    """TrainStep._g_bucket_order / _d_bucket_order (the lists GradBucketer fills its buckets from, END first): generator
+    parameters in forward order of use — decoder last, so its gradients (the first to complete) fill the first bucket —, and
+    the three discriminators merged by relative depth, each network's own order preserved."""
+    from b200gan.step import TrainStep
+    ts = TrainStep(64, device="cpu")
+    order = ts._g_bucket_order()
+    names = {id(p): k for k, p in ts.netG.named_parameters()}
+    tops = [names[id(p)].split(".")[0] for p in order]
+    assert len(order) == len(list(ts.netG.parameters())) and len({id(p) for p in order}) == len(order)
+    first_of = {t: tops.index(t) for t in set(tops)}
+    assert first_of["crop_encoder"] < first_of["attribute_encoder"] < first_of["layout_encoder"] < first_of["global_encoder"] \
+        < first_of["decoder"]
+    assert tops[-1] == "decoder"
+    d_order = ts._d_bucket_order()
+    assert len(d_order) == sum(len(list(n.parameters())) for n in ts.d_nets)
+    pos = {id(p): i for i, p in enumerate(d_order)}
+    for n in ts.d_nets:
+        idx = [pos[id(p)] for p in n.parameters()]
+        assert idx == sorted(idx)                                  # each network keeps its own order
+    # merged by depth: the first and the last parameters of every network sit in the first / last tenth of the list
+    for n in ts.d_nets:
+        ps = list(n.parameters())
+        assert pos[id(ps[0])] < len(d_order) // 10 and pos[id(ps[-1])] >= len(d_order) - len(d_order) // 10 - 3
