@@ -19,6 +19,8 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
+from . import ops
+
 
 def layout_key(batch: Dict[str, torch.Tensor]) -> Tuple:
     o2i = batch["obj_to_img"]
@@ -38,6 +40,7 @@ class CapturedIteration:
         self.n_images, self.n_objs = int(host["imgs"].shape[0]), int(host["objs"].shape[0])
         self.b = ts.to_device(self.pinned)
         self.graph, self.out, self.error, self.eager_result = None, None, None, None
+        self.fork_error = None
         for _ in range(warm):
             self.eager_result = ts.step(self.b, optimizer_step=True)
         torch.cuda.synchronize()
@@ -52,17 +55,32 @@ class CapturedIteration:
                     ts.step(self.b, optimizer_step=True)
                 torch.cuda.current_stream().wait_stream(side)
                 torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            # thread_local: the NCCL watchdog thread may query events while a step with all-reduces is being captured
-            with torch.cuda.graph(g, capture_error_mode="thread_local" if thread_local else "global"):
-                r = ts.step(self.b, optimizer_step=True)
-                self.out = dict(d_loss=r["d_loss"], g_loss=r["g_loss"], d_terms=r["d_terms"], g_terms=r["g_terms"],
-                                out_g=r["out_g"])
-            self.graph = g
+            self._capture(thread_local)
         except Exception as e:       # capture is an optimisation, never a correctness requirement
             self.error = "%s: %s" % (type(e).__name__, e)
             self.graph = None
             torch.cuda.synchronize()
+            if ops.FORKS != "off":
+                # second attempt as a single-stream graph (without the fork / join branches of DESIGN.md §3)
+                prev, ops.FORKS = ops.FORKS, "off"
+                try:
+                    self._capture(thread_local)
+                    self.fork_error, self.error = self.error, None       # captured, but as a single-stream graph
+                except Exception as e2:
+                    self.error += " | single-stream retry: %s: %s" % (type(e2).__name__, e2)
+                    self.graph = None
+                    torch.cuda.synchronize()
+                finally:
+                    ops.FORKS = prev
+
+    def _capture(self, thread_local: bool):
+        g = torch.cuda.CUDAGraph()
+        # thread_local: the NCCL watchdog thread may query events while a step with all-reduces is being captured
+        with torch.cuda.graph(g, capture_error_mode="thread_local" if thread_local else "global"):
+            r = self.ts.step(self.b, optimizer_step=True)
+            self.out = dict(d_loss=r["d_loss"], g_loss=r["g_loss"], d_terms=r["d_terms"], g_terms=r["g_terms"],
+                            out_g=r["out_g"])
+        self.graph = g
 
     def upload(self, host: Optional[Dict[str, torch.Tensor]] = None):
         """pinned host batch -> static device batch (asynchronous); `host`: new values for the same layout"""
